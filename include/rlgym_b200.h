@@ -1,0 +1,225 @@
+/*
+ * rlgym_b200.h — C ABI of the B200-native collection engine.
+ *
+ * This is the drop-in boundary for the reference's ThreadAgentManager/ThreadAgent
+ * collection path.  Plain C: pointers, sizes and int status codes,
+ * no C++ or torch types.  Every entry point cites the reference interface it
+ * replaces (paths relative to /root/reference/RLGymPPO_CPP unless stated):
+ *
+ *   G/ = RLGymSim_CPP/src/RLGymSim_CPP/         (gym + plugin layer)
+ *   R/ = RLGymSim_CPP/RocketSim/src/            (RocketSim game logic)
+ *   P/ = src/                                   (PPO learner library)
+ *
+ * All arrays are DEVICE pointers unless the parameter name ends in _host.
+ * All calls return RLG_OK (0) or a negative error; rlg_last_error() gives the
+ * message (the reference throws std::runtime_error via RG_ERR_CLOSE,
+ * G/Framework.h:17-22 — the C++ shim re-throws on non-zero status).
+ * There is NO CPU fallback: if no CUDA device is usable every call that needs
+ * one fails with RLG_ERR_CUDA.
+ */
+#ifndef RLGYM_B200_H
+#define RLGYM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLG_OK 0
+#define RLG_ERR_INVALID (-1)
+#define RLG_ERR_CUDA (-2)
+#define RLG_ERR_STATE (-3)
+
+#define RLG_MAX_CARS 6   /* 3v3 */
+#define RLG_NUM_PADS 34  /* R/RLConst.h:192-253 */
+#define RLG_NUM_ACTIONS 90 /* G/Utils/ActionParsers/DiscreteAction.cpp:3-67 */
+
+/* ---- host-side AoS state structs (parity injection / extraction) ----------
+ * Mirrors of RocketSim's CarState (R/Sim/Car/Car.h:17-115), BallState
+ * (R/Sim/Ball/Ball.h), BoostPadState (R/Sim/BoostPad/BoostPad.h) and CarControls
+ * (R/Sim/CarControls.h), plus the per-wheel values btVehicleRL carries between
+ * ticks (R/Sim/btVehicleRL/btVehicleRL.h:9-27; SURVEY.md §7 hard part 3).
+ * Every field is 4 bytes wide (bools are int32) except the two tick stamps. */
+typedef struct rlg_controls {
+    float throttle, steer, pitch, yaw, roll;
+    int32_t jump, boost, handbrake;
+} rlg_controls;
+
+typedef struct rlg_car_state {
+    float pos[3];
+    float rot_forward[3], rot_right[3], rot_up[3]; /* RotMat columns */
+    float vel[3];
+    float ang_vel[3];
+    int32_t is_on_ground;
+    int32_t wheels_with_contact[4];
+    int32_t has_jumped, has_double_jumped, has_flipped;
+    float flip_rel_torque[3];
+    float jump_time, flip_time;
+    int32_t is_flipping, is_jumping;
+    float air_time, air_time_since_jump;
+    float boost, time_spent_boosting;
+    int32_t is_supersonic;
+    float supersonic_time, handbrake_val;
+    int32_t is_auto_flipping;
+    float auto_flip_timer, auto_flip_torque_scale;
+    int32_t world_contact_has;
+    float world_contact_normal[3];
+    int32_t car_contact_other_id; /* car id (1-based), 0 = none */
+    float car_contact_cooldown;
+    int32_t is_demoed;
+    float demo_respawn_timer;
+    /* BallHitInfo, R/Sim/BallHitInfo/BallHitInfo.h */
+    int32_t hit_valid;
+    float hit_rel_pos_on_ball[3], hit_ball_pos[3], hit_extra_vel[3];
+    int64_t hit_tick;         /* tickCountWhenHit; -1 == ~0ULL */
+    int64_t hit_extra_tick;   /* tickCountWhenExtraImpulseApplied */
+    rlg_controls last_controls;
+    /* values btVehicleRL keeps from the previous tick */
+    float wheel_steer_angle; /* wheels 0,1; rear wheels never steer */
+    float wheel_engine_force, wheel_brake;
+    float wheel_lat_friction[4], wheel_long_friction[4], wheel_extra_pushback[4];
+    /* identity */
+    int32_t car_id; /* 1-based, as Arena::_lastCarID assigns them */
+    int32_t team;   /* 0 blue, 1 orange */
+} rlg_car_state;
+
+typedef struct rlg_ball_state {
+    float pos[3];
+    float vel[3];
+    float ang_vel[3];
+} rlg_ball_state;
+
+typedef struct rlg_pad_state {
+    int32_t is_active;
+    float cooldown;
+    int32_t prev_locked_car_id;
+} rlg_pad_state;
+
+/* ---- engine configuration ------------------------------------------------- */
+enum rlg_obs_kind { RLG_OBS_DEFAULT = 0, RLG_OBS_PADDED = 1 };
+enum rlg_state_setter { RLG_SETTER_KICKOFF = 0, RLG_SETTER_RANDOM = 1, RLG_SETTER_HOST = 2 };
+
+/* Built-in reward terms (G/Utils/RewardFunctions/CommonRewards.h). */
+enum rlg_reward_kind {
+    RLG_REW_EVENT = 0,              /* EventReward, params = 11 weights */
+    RLG_REW_VEL_PLAYER_TO_BALL = 1, /* VelocityPlayerToBallReward */
+    RLG_REW_VEL_BALL_TO_GOAL = 2,   /* VelocityBallToGoalReward, param[0] = ownGoal */
+    RLG_REW_FACE_BALL = 3,          /* FaceBallReward */
+    RLG_REW_VELOCITY = 4            /* VelocityReward, param[0] = isNegative */
+};
+#define RLG_MAX_REWARD_TERMS 8
+
+typedef struct rlg_reward_term {
+    int32_t kind;
+    float weight;      /* CombinedReward weight, CombinedReward.h:36-46 */
+    float params[11];
+} rlg_reward_term;
+
+typedef struct rlg_engine_cfg {
+    int32_t num_arenas;
+    int32_t team_size;        /* Match::teamSize, G/Envs/Match.h:27-46 */
+    int32_t spawn_opponents;  /* Match::spawnOpponents */
+    int32_t tick_skip;        /* Gym::tickSkip, G/Gym.cpp:40-41 */
+    int32_t device;           /* CUDA ordinal */
+    uint64_t seed;
+    int32_t arena_id_base;    /* global id of local arena 0 (multi-GPU sharding; RNG streams keyed by global id) */
+    /* obs */
+    int32_t obs_kind;         /* DefaultOBS / DefaultOBSPadded */
+    int32_t obs_max_players;  /* DefaultOBSPadded::maxPlayers */
+    /* reward graph: CombinedReward(terms) optionally wrapped in ZeroSumReward */
+    int32_t num_reward_terms;
+    rlg_reward_term reward_terms[RLG_MAX_REWARD_TERMS];
+    int32_t zero_sum;         /* 1 = wrap in ZeroSumReward (ZeroSumReward.cpp:3-29) */
+    float team_spirit, opponent_scale;
+    /* terminal conditions */
+    int32_t no_touch_max_steps; /* NoTouchCondition(maxSteps); <=0 disables */
+    int32_t goal_score_terminal; /* GoalScoreCondition */
+    /* state setter */
+    int32_t state_setter;     /* KickoffState / RandomState / host-provided */
+    int32_t rand_ball_speed, rand_car_speed, cars_on_ground; /* RandomState flags */
+} rlg_engine_cfg;
+
+typedef struct rlg_engine rlg_engine;
+
+const char* rlg_last_error(void);
+int rlg_abi_version(void);
+size_t rlg_sizeof_car_state(void);
+size_t rlg_sizeof_engine_cfg(void);
+
+/* Fills cfg with the examplemain.cpp:58-151 configuration (1v1, DefaultOBS,
+ * rewards {FaceBall .1, VelPlayerToBall .5, VelBallToGoal 1, Event{teamGoal 1, concede -1}*50},
+ * NoTouch 150 + GoalScore, RandomState(true,true,true), tickSkip 8). */
+void rlg_engine_cfg_default(rlg_engine_cfg* cfg);
+
+/* Replaces `new Gym(match, tickSkip)` x num_arenas in ThreadAgent::ThreadAgent
+ * (P/private/RLGymPPO_CPP/Threading/ThreadAgent.cpp:197-206, G/Gym.cpp:40-56). */
+int rlg_engine_create(const rlg_engine_cfg* cfg, rlg_engine** out);
+int rlg_engine_destroy(rlg_engine* e);
+
+/* Replaces RocketSim::Init / InitFromMem (R/RocketSim.cpp:70-212): same .cmf
+ * bytes the reference reads (format: R/CollisionMeshFile/CollisionMeshFile.cpp:11-35).
+ * Must be called before the first reset/step. Mesh order = body order. */
+int rlg_engine_load_meshes(rlg_engine* e, const void* const* cmf_blobs_host,
+                           const size_t* sizes_host, int n);
+
+/* Gym::Reset (G/Gym.cpp:58-66) on every arena whose mask byte is non-zero
+ * (NULL = all): runs the state setter + Match::EpisodeReset and writes obs. */
+int rlg_engine_reset(rlg_engine* e, const uint8_t* mask_host, void* stream);
+
+/* Car::SetState / Ball::SetState / BoostPad::SetState (R/Sim/Car/Car.cpp:23-36,
+ * R/Sim/Ball/Ball.cpp:35-49) for n arenas; cars is [n * num_cars], pads [n * 34].
+ * Any pointer may be NULL to leave that part untouched. Host pointers. */
+int rlg_engine_set_state(rlg_engine* e, const int32_t* arena_ids_host, int n,
+                         const rlg_car_state* cars_host, const rlg_ball_state* balls_host,
+                         const rlg_pad_state* pads_host, const int64_t* tick_counts_host);
+/* Car::GetState / Ball::GetState (R/Sim/Car/Car.cpp:10-21, Ball.cpp:27-33). */
+int rlg_engine_get_state(rlg_engine* e, const int32_t* arena_ids_host, int n,
+                         rlg_car_state* cars_host, rlg_ball_state* balls_host,
+                         rlg_pad_state* pads_host, int64_t* tick_counts_host);
+
+/* Arena::Step(nticks) with explicit controls (R/Sim/Arena/Arena.cpp:716-812).
+ * controls is a DEVICE array [num_arenas * num_cars] in car-id order. */
+int rlg_engine_tick(rlg_engine* e, const rlg_controls* controls, int nticks, void* stream);
+
+/* Gym::Step (G/Gym.cpp:68-102) + GameInst::Step auto-reset
+ * (P/public/RLGymPPO_CPP/Threading/GameInst.cpp:7-38) for every arena:
+ * parse -> 1 tick -> event tracker + snapshot -> (tick_skip-1) ticks ->
+ * obs/reward/done -> reset finished arenas.  action_idx: DEVICE int32 [num_arenas * num_cars]
+ * in player order (see rlg_engine_player_order). */
+int rlg_engine_step(rlg_engine* e, const int32_t* action_idx, void* stream);
+
+/* Device pointers to the step outputs; valid until the next step/reset.
+ * obs [A*P, obs_size] f32 (post-reset obs for finished arenas, as GameInst::Step
+ * stores), reward [A*P] f32, done [A] u8, next_obs_terminal is not kept: the
+ * reference never uses it (P/private/RLGymPPO_CPP/Util/TorchFuncs.cpp:24,36). */
+int rlg_engine_outputs(rlg_engine* e, float** obs, float** reward, uint8_t** done);
+int rlg_engine_obs_size(const rlg_engine* e);
+int rlg_engine_num_players(const rlg_engine* e); /* per arena */
+/* players[i] -> car id; the reference's order is unordered_set<Car*> iteration
+ * order (R/Sim/Arena/Arena.h:35), i.e. descending car id for the small sets used. */
+int rlg_engine_player_order(const rlg_engine* e, int32_t* car_ids_host);
+
+/* DiscreteAction table, 90x8 f32 (G/Utils/ActionParsers/DiscreteAction.cpp:3-67). */
+int rlg_action_table(float* table_host);
+
+/* Stand-alone fused obs/reward/done evaluation on injected states: computes what
+ * Match::BuildObservations/IsDone/GetRewards (G/Envs/Match.cpp:12-38) would for
+ * the current arena states WITHOUT stepping physics. prev_actions: DEVICE [A*P,8]. */
+int rlg_engine_eval_gym(rlg_engine* e, const float* prev_actions, void* stream);
+
+/* Host-buffer convenience used by the C++ shim / bench e2e: copies action_idx
+ * from host, steps, and copies obs/reward/done back into host buffers. */
+int rlg_engine_step_host(rlg_engine* e, const int32_t* action_idx_host,
+                         float* obs_host, float* reward_host, uint8_t* done_host);
+
+/* Number of kernel launches issued by this engine so far (bench "gpu_launches"). */
+uint64_t rlg_engine_launch_count(const rlg_engine* e);
+/* Wait for all work queued on the engine's stream. */
+int rlg_engine_sync(rlg_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLGYM_B200_H */

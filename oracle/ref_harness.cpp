@@ -1,0 +1,388 @@
+// ref_harness.cpp — TEST INFRASTRUCTURE ONLY (oracle). Not part of the product path.
+//
+// A thin C-ABI harness around the UNMODIFIED reference (RocketSim + RLGymSim_CPP
+// compiled from /root/reference by oracle/Makefile into oracle/_ref/librlref.so).
+// It exposes exactly what the parity tests and bench.py's cpu_baseline /
+// `--impl reference` leg need:
+//   * raw Arena access: inject CarState/BallState/pad state, Arena::Step(n), read back
+//   * Gym access: Gym::Reset / Gym::Step with the built-in plugins configured from
+//     the same rlg_engine_cfg the CUDA engine takes
+//   * a multithreaded Gym::Step loop that mirrors GameInst::Step (the CPU baseline)
+// State structs are the ones in include/rlgym_b200.h so both sides speak one format.
+//
+// Reference entry points used (all public API of the reference):
+//   RocketSim::InitFromMem            RocketSim/src/RocketSim.cpp:105
+//   Arena::Create/AddCar/Step         RocketSim/src/Sim/Arena/Arena.cpp:579,47,716
+//   Car::SetState/GetState            RocketSim/src/Sim/Car/Car.cpp:23,10
+//   Gym::Reset/Step                   src/RLGymSim_CPP/Gym.cpp:58,68
+#include <RLGymSim_CPP/Gym.h>
+#include <RLGymSim_CPP/Utils/OBSBuilders/DefaultOBS.h>
+#include <RLGymSim_CPP/Utils/OBSBuilders/DefaultOBSPadded.h>
+#include <RLGymSim_CPP/Utils/RewardFunctions/CombinedReward.h>
+#include <RLGymSim_CPP/Utils/RewardFunctions/CommonRewards.h>
+#include <RLGymSim_CPP/Utils/RewardFunctions/ZeroSumReward.h>
+#include <RLGymSim_CPP/Utils/ActionParsers/DiscreteAction.h>
+#include <RLGymSim_CPP/Utils/StateSetters/KickoffState.h>
+#include <RLGymSim_CPP/Utils/StateSetters/RandomState.h>
+#include <RLGymSim_CPP/Utils/TerminalConditions/NoTouchCondition.h>
+#include <RLGymSim_CPP/Utils/TerminalConditions/GoalScoreCondition.h>
+
+#include "../include/rlgym_b200.h"
+
+#include <atomic>
+#include <chrono>
+#include <thread>
+
+using namespace RLGSC;
+
+namespace {
+
+static void copy3(float* dst, const Vec& v) { dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; }
+static Vec vec3(const float* s) { return Vec(s[0], s[1], s[2]); }
+
+static Car* car_by_id(Arena* a, uint32_t id) {
+    auto it = a->_carIDMap.find(id);
+    return it == a->_carIDMap.end() ? nullptr : it->second;
+}
+
+static void controls_to_pod(const CarControls& c, rlg_controls* o) {
+    o->throttle = c.throttle; o->steer = c.steer; o->pitch = c.pitch; o->yaw = c.yaw; o->roll = c.roll;
+    o->jump = c.jump; o->boost = c.boost; o->handbrake = c.handbrake;
+}
+static CarControls controls_from_pod(const rlg_controls& c) {
+    CarControls o;
+    o.throttle = c.throttle; o.steer = c.steer; o.pitch = c.pitch; o.yaw = c.yaw; o.roll = c.roll;
+    o.jump = c.jump != 0; o.boost = c.boost != 0; o.handbrake = c.handbrake != 0;
+    return o;
+}
+
+static void car_to_pod(Car* car, rlg_car_state* o) {
+    CarState s = car->GetState();
+    memset(o, 0, sizeof(*o));
+    copy3(o->pos, s.pos);
+    copy3(o->rot_forward, s.rotMat.forward); copy3(o->rot_right, s.rotMat.right); copy3(o->rot_up, s.rotMat.up);
+    copy3(o->vel, s.vel); copy3(o->ang_vel, s.angVel);
+    o->is_on_ground = s.isOnGround;
+    for (int i = 0; i < 4; i++) o->wheels_with_contact[i] = s.wheelsWithContact[i];
+    o->has_jumped = s.hasJumped; o->has_double_jumped = s.hasDoubleJumped; o->has_flipped = s.hasFlipped;
+    copy3(o->flip_rel_torque, s.flipRelTorque);
+    o->jump_time = s.jumpTime; o->flip_time = s.flipTime;
+    o->is_flipping = s.isFlipping; o->is_jumping = s.isJumping;
+    o->air_time = s.airTime; o->air_time_since_jump = s.airTimeSinceJump;
+    o->boost = s.boost; o->time_spent_boosting = s.timeSpentBoosting;
+    o->is_supersonic = s.isSupersonic; o->supersonic_time = s.supersonicTime; o->handbrake_val = s.handbrakeVal;
+    o->is_auto_flipping = s.isAutoFlipping; o->auto_flip_timer = s.autoFlipTimer; o->auto_flip_torque_scale = s.autoFlipTorqueScale;
+    o->world_contact_has = s.worldContact.hasContact; copy3(o->world_contact_normal, s.worldContact.contactNormal);
+    o->car_contact_other_id = (int32_t)s.carContact.otherCarID; o->car_contact_cooldown = s.carContact.cooldownTimer;
+    o->is_demoed = s.isDemoed; o->demo_respawn_timer = s.demoRespawnTimer;
+    o->hit_valid = s.ballHitInfo.isValid;
+    copy3(o->hit_rel_pos_on_ball, s.ballHitInfo.relativePosOnBall);
+    copy3(o->hit_ball_pos, s.ballHitInfo.ballPos);
+    copy3(o->hit_extra_vel, s.ballHitInfo.extraHitVel);
+    o->hit_tick = (int64_t)s.ballHitInfo.tickCountWhenHit;
+    o->hit_extra_tick = (int64_t)s.ballHitInfo.tickCountWhenExtraImpulseApplied;
+    controls_to_pod(s.lastControls, &o->last_controls);
+    auto& wi = car->_bulletVehicle.m_wheelInfo;
+    o->wheel_steer_angle = wi[0].m_steerAngle;
+    o->wheel_engine_force = wi[0].m_engineForce;
+    o->wheel_brake = wi[0].m_brake;
+    for (int i = 0; i < 4; i++) {
+        o->wheel_lat_friction[i] = wi[i].m_latFriction;
+        o->wheel_long_friction[i] = wi[i].m_longFriction;
+        o->wheel_extra_pushback[i] = wi[i].m_extraPushback;
+    }
+    o->car_id = (int32_t)car->id;
+    o->team = (int32_t)car->team;
+}
+
+static void car_from_pod(Car* car, const rlg_car_state& i) {
+    CarState s;
+    s.pos = vec3(i.pos);
+    s.rotMat = RotMat(vec3(i.rot_forward), vec3(i.rot_right), vec3(i.rot_up));
+    s.vel = vec3(i.vel); s.angVel = vec3(i.ang_vel);
+    s.isOnGround = i.is_on_ground;
+    for (int k = 0; k < 4; k++) s.wheelsWithContact[k] = i.wheels_with_contact[k];
+    s.hasJumped = i.has_jumped; s.hasDoubleJumped = i.has_double_jumped; s.hasFlipped = i.has_flipped;
+    s.flipRelTorque = vec3(i.flip_rel_torque);
+    s.jumpTime = i.jump_time; s.flipTime = i.flip_time;
+    s.isFlipping = i.is_flipping; s.isJumping = i.is_jumping;
+    s.airTime = i.air_time; s.airTimeSinceJump = i.air_time_since_jump;
+    s.boost = i.boost; s.timeSpentBoosting = i.time_spent_boosting;
+    s.isSupersonic = i.is_supersonic; s.supersonicTime = i.supersonic_time; s.handbrakeVal = i.handbrake_val;
+    s.isAutoFlipping = i.is_auto_flipping; s.autoFlipTimer = i.auto_flip_timer; s.autoFlipTorqueScale = i.auto_flip_torque_scale;
+    s.worldContact.hasContact = i.world_contact_has; s.worldContact.contactNormal = vec3(i.world_contact_normal);
+    s.carContact.otherCarID = (uint32_t)i.car_contact_other_id; s.carContact.cooldownTimer = i.car_contact_cooldown;
+    s.isDemoed = i.is_demoed; s.demoRespawnTimer = i.demo_respawn_timer;
+    s.ballHitInfo.isValid = i.hit_valid;
+    s.ballHitInfo.relativePosOnBall = vec3(i.hit_rel_pos_on_ball);
+    s.ballHitInfo.ballPos = vec3(i.hit_ball_pos);
+    s.ballHitInfo.extraHitVel = vec3(i.hit_extra_vel);
+    s.ballHitInfo.tickCountWhenHit = (uint64_t)i.hit_tick;
+    s.ballHitInfo.tickCountWhenExtraImpulseApplied = (uint64_t)i.hit_extra_tick;
+    s.lastControls = controls_from_pod(i.last_controls);
+    car->SetState(s);
+    auto& wi = car->_bulletVehicle.m_wheelInfo;
+    wi[0].m_steerAngle = wi[1].m_steerAngle = i.wheel_steer_angle;
+    for (int k = 0; k < 4; k++) {
+        wi[k].m_engineForce = i.wheel_engine_force;
+        wi[k].m_brake = i.wheel_brake;
+        wi[k].m_latFriction = i.wheel_lat_friction[k];
+        wi[k].m_longFriction = i.wheel_long_friction[k];
+        wi[k].m_extraPushback = i.wheel_extra_pushback[k];
+    }
+}
+
+struct RefGym {
+    Gym* gym = nullptr;
+    Match* match = nullptr;
+    RewardFunction* reward = nullptr;
+    std::vector<TerminalCondition*> terms;
+    OBSBuilder* obs = nullptr;
+    ActionParser* parser = nullptr;
+    StateSetter* setter = nullptr;
+    ~RefGym() {
+        delete gym; delete match; delete reward;
+        for (auto t : terms) delete t;
+        delete obs; delete parser; delete setter;
+    }
+};
+
+static RewardFunction* make_term(const rlg_reward_term& t) {
+    switch (t.kind) {
+    case RLG_REW_EVENT: {
+        EventReward::WeightScales w;
+        for (int i = 0; i < 11; i++) w[i] = t.params[i];
+        return new EventReward(w);
+    }
+    case RLG_REW_VEL_PLAYER_TO_BALL: return new VelocityPlayerToBallReward();
+    case RLG_REW_VEL_BALL_TO_GOAL: return new VelocityBallToGoalReward(t.params[0] != 0);
+    case RLG_REW_FACE_BALL: return new FaceBallReward();
+    case RLG_REW_VELOCITY: return new VelocityReward(t.params[0] != 0);
+    }
+    return nullptr;
+}
+
+static RefGym* make_gym(const rlg_engine_cfg* cfg) {
+    RefGym* g = new RefGym();
+    std::vector<RewardFunction*> fns; std::vector<float> ws;
+    for (int i = 0; i < cfg->num_reward_terms; i++) {
+        fns.push_back(make_term(cfg->reward_terms[i]));
+        ws.push_back(cfg->reward_terms[i].weight);
+    }
+    RewardFunction* combined = new CombinedReward(fns, ws, true);
+    g->reward = cfg->zero_sum ? (RewardFunction*)new ZeroSumReward(combined, cfg->team_spirit, cfg->opponent_scale, true) : combined;
+    if (cfg->no_touch_max_steps > 0) g->terms.push_back(new NoTouchCondition(cfg->no_touch_max_steps));
+    if (cfg->goal_score_terminal) g->terms.push_back(new GoalScoreCondition());
+    g->obs = cfg->obs_kind == RLG_OBS_PADDED ? (OBSBuilder*)new DefaultOBSPadded(cfg->obs_max_players) : (OBSBuilder*)new DefaultOBS();
+    g->parser = new DiscreteAction();
+    g->setter = cfg->state_setter == RLG_SETTER_KICKOFF
+        ? (StateSetter*)new KickoffState()
+        : (StateSetter*)new RandomState(cfg->rand_ball_speed, cfg->rand_car_speed, cfg->cars_on_ground);
+    g->match = new Match(g->reward, g->terms, g->obs, g->parser, g->setter, cfg->team_size, cfg->spawn_opponents != 0);
+    g->gym = new Gym(g->match, cfg->tick_skip);
+    return g;
+}
+
+static int flatten_obs(const FList2& obs, float* out) {
+    int k = 0;
+    for (auto& row : obs) for (float v : row) out[k++] = v;
+    return obs.empty() ? 0 : (int)obs[0].size();
+}
+
+} // namespace
+
+extern "C" {
+
+int ref_init(const void* const* blobs, const size_t* sizes, int n) {
+    try {
+        std::map<GameMode, std::vector<RocketSim::FileData>> m;
+        auto& v = m[GameMode::SOCCAR];
+        for (int i = 0; i < n; i++) {
+            const byte* b = (const byte*)blobs[i];
+            v.emplace_back(b, b + sizes[i]);
+        }
+        RocketSim::InitFromMem(m, true);
+        return 0;
+    } catch (std::exception&) { return -1; }
+}
+
+void ref_seed(uint32_t seed) { RocketSim::Math::GetRandEngine().seed(seed); }
+
+// ---- raw arena -------------------------------------------------------------
+void* ref_arena_create(int team_size, int spawn_opponents) {
+    Arena* a = Arena::Create(GameMode::SOCCAR);
+    for (int i = 0; i < team_size; i++) {  // same order as Gym::Gym, Gym.cpp:46-50
+        a->AddCar(Team::BLUE);
+        if (spawn_opponents) a->AddCar(Team::ORANGE);
+    }
+    return a;
+}
+void ref_arena_destroy(void* h) { delete (Arena*)h; }
+int ref_arena_num_cars(void* h) { return (int)((Arena*)h)->_cars.size(); }
+
+// cars indexed by car id - 1
+void ref_arena_set_state(void* h, const rlg_car_state* cars, const rlg_ball_state* ball,
+                         const rlg_pad_state* pads, int64_t tick_count) {
+    Arena* a = (Arena*)h;
+    if (cars) {
+        int n = (int)a->_cars.size();
+        for (int i = 0; i < n; i++) car_from_pod(car_by_id(a, i + 1), cars[i]);
+    }
+    if (ball) {
+        BallState b;
+        b.pos = vec3(ball->pos); b.vel = vec3(ball->vel); b.angVel = vec3(ball->ang_vel);
+        a->ball->SetState(b);
+    }
+    if (pads) {
+        for (size_t i = 0; i < a->_boostPads.size(); i++) {
+            BoostPadState s;
+            s.isActive = pads[i].is_active; s.cooldown = pads[i].cooldown;
+            s.prevLockedCarID = pads[i].prev_locked_car_id;
+            a->_boostPads[i]->SetState(s);
+        }
+    }
+    if (tick_count >= 0) a->tickCount = (uint64_t)tick_count;
+}
+
+void ref_arena_get_state(void* h, rlg_car_state* cars, rlg_ball_state* ball, rlg_pad_state* pads,
+                         int64_t* tick_count) {
+    Arena* a = (Arena*)h;
+    if (cars) {
+        int n = (int)a->_cars.size();
+        for (int i = 0; i < n; i++) car_to_pod(car_by_id(a, i + 1), &cars[i]);
+    }
+    if (ball) {
+        BallState b = a->ball->GetState();
+        copy3(ball->pos, b.pos); copy3(ball->vel, b.vel); copy3(ball->ang_vel, b.angVel);
+    }
+    if (pads) {
+        for (size_t i = 0; i < a->_boostPads.size(); i++) {
+            BoostPadState s = a->_boostPads[i]->GetState();
+            pads[i].is_active = s.isActive; pads[i].cooldown = s.cooldown;
+            pads[i].prev_locked_car_id = (int32_t)s.prevLockedCarID;
+        }
+    }
+    if (tick_count) *tick_count = (int64_t)a->tickCount;
+}
+
+void ref_arena_step(void* h, const rlg_controls* controls, int nticks) {
+    Arena* a = (Arena*)h;
+    if (controls) {
+        int n = (int)a->_cars.size();
+        for (int i = 0; i < n; i++) car_by_id(a, i + 1)->controls = controls_from_pod(controls[i]);
+    }
+    a->Step(nticks);
+}
+
+// iteration order of Arena::_cars (the player order of every gym-level vector)
+void ref_arena_player_order(void* h, int32_t* ids) {
+    int k = 0;
+    for (Car* c : ((Arena*)h)->_cars) ids[k++] = (int32_t)c->id;
+}
+
+// ---- gym -------------------------------------------------------------------
+void* ref_gym_create(const rlg_engine_cfg* cfg) {
+    try { return make_gym(cfg); } catch (std::exception&) { return nullptr; }
+}
+void ref_gym_destroy(void* h) { delete (RefGym*)h; }
+void* ref_gym_arena(void* h) { return ((RefGym*)h)->gym->arena; }
+int ref_gym_num_players(void* h) { return ((RefGym*)h)->match->playerAmount; }
+
+int ref_gym_reset(void* h, float* obs_out) {
+    RefGym* g = (RefGym*)h;
+    return flatten_obs(g->gym->Reset(), obs_out);
+}
+
+// Gym::Reset without the state setter: adopt whatever the arena currently holds
+// (used after ref_arena_set_state to start an episode from an injected state).
+int ref_gym_reset_from_current(void* h, float* obs_out) {
+    RefGym* g = (RefGym*)h;
+    GameState s(g->gym->arena);
+    g->match->EpisodeReset(s);
+    g->gym->prevState = s;
+    g->gym->eventTracker.ResetPersistentInfo();
+    return flatten_obs(g->match->BuildObservations(s), obs_out);
+}
+
+int ref_gym_step(void* h, const int32_t* actions, float* obs_out, float* rew_out, uint8_t* done_out) {
+    RefGym* g = (RefGym*)h;
+    IList acts(actions, actions + g->match->playerAmount);
+    auto r = g->gym->Step(acts);
+    int w = flatten_obs(r.obs, obs_out);
+    for (size_t i = 0; i < r.reward.size(); i++) rew_out[i] = r.reward[i];
+    *done_out = r.done;
+    return w;
+}
+
+// gym-level extras of the last GameState (what the fused gym kernel must reproduce)
+void ref_gym_last_state(void* h, int32_t* score_line2, int32_t* last_touch, int32_t* match_counters /*[P*8]*/,
+                        uint8_t* touched_step /*[P]*/) {
+    RefGym* g = (RefGym*)h;
+    const GameState& s = g->gym->prevState;
+    score_line2[0] = s.scoreLine[0]; score_line2[1] = s.scoreLine[1];
+    *last_touch = s.lastTouchCarID;
+    for (size_t i = 0; i < s.players.size(); i++) {
+        const PlayerData& p = s.players[i];
+        int32_t* c = match_counters + i * 8;
+        c[0] = p.matchGoals; c[1] = p.matchSaves; c[2] = p.matchAssists; c[3] = p.matchShots;
+        c[4] = p.matchShotPasses; c[5] = p.matchBumps; c[6] = p.matchDemos; c[7] = p.boostPickups;
+        touched_step[i] = p.ballTouchedStep;
+    }
+}
+
+int ref_action_table(float* out) {
+    DiscreteAction d;
+    int k = 0;
+    for (auto& a : d.actions) for (int i = 0; i < 8; i++) out[k++] = a[i];
+    return (int)d.actions.size();
+}
+
+// ---- CPU baseline: the reference's multithreaded collection loop, sim only --
+// T threads x G gyms, each thread looping Gym::Step + auto-reset exactly like
+// GameInst::Step (src/public/RLGymPPO_CPP/Threading/GameInst.cpp:7-38), actions =
+// uniform random index in [0,90). Returns player-steps per second.
+double ref_bench_collect(const rlg_engine_cfg* cfg, int num_threads, int gyms_per_thread,
+                         int warmup_steps, int timed_steps, uint32_t seed) {
+    std::vector<std::vector<RefGym*>> gyms(num_threads);
+    for (int t = 0; t < num_threads; t++)
+        for (int i = 0; i < gyms_per_thread; i++) gyms[t].push_back(make_gym(cfg));
+    std::atomic<int> ready{0}; std::atomic<bool> go{false};
+    std::vector<double> secs(num_threads, 0.0);
+    std::vector<std::thread> ths;
+    int P = gyms[0][0]->match->playerAmount;
+    for (int t = 0; t < num_threads; t++) {
+        ths.emplace_back([&, t] {
+            RocketSim::Math::GetRandEngine().seed(seed + 977 * t);
+            uint32_t rng = seed * 2654435761u + t * 40503u + 1;
+            auto next = [&rng] { rng ^= rng << 13; rng ^= rng >> 17; rng ^= rng << 5; return rng; };
+            for (auto g : gyms[t]) g->gym->Reset();
+            IList acts(P);
+            auto run = [&](int steps) {
+                for (int s = 0; s < steps; s++)
+                    for (auto g : gyms[t]) {
+                        for (int p = 0; p < P; p++) acts[p] = next() % 90;
+                        auto r = g->gym->Step(acts);
+                        if (r.done) g->gym->Reset();
+                    }
+            };
+            run(warmup_steps);
+            ready++;
+            while (!go.load()) std::this_thread::yield();
+            auto t0 = std::chrono::steady_clock::now();
+            run(timed_steps);
+            secs[t] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        });
+    }
+    while (ready.load() < num_threads) std::this_thread::yield();
+    go = true;
+    for (auto& th : ths) th.join();
+    double mx = 0;
+    for (double s : secs) mx = std::max(mx, s);
+    for (auto& v : gyms) for (auto g : v) delete g;
+    double total = (double)num_threads * gyms_per_thread * timed_steps * P;
+    return total / mx;
+}
+
+size_t ref_sizeof_car_state() { return sizeof(rlg_car_state); }
+
+} // extern "C"
