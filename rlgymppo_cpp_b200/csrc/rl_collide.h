@@ -1,0 +1,422 @@
+// rl_collide.h — narrowphase for the shape pairs RocketSim's soccar actually reaches
+// (SURVEY.md §8a "Narrowphase pairs actually reached") plus the contact-added callback
+// (R/Sim/Arena/Arena.cpp:218-427).  Contacts are stateless per tick: the reference's
+// btRSBroadphase drops and rebuilds every pair (and therefore every manifold) each tick.
+//
+// Body indices: 0 = ball, 1+c = car c, -1 = static world.  A manifold's body A is the
+// dynamic one for world pairs, the car for car-ball, the lower car for car-car; normals
+// are "normalWorldOnB": they point from B towards A.
+#pragma once
+#include "rl_car.h"
+#include "rl_gjk.h"
+
+namespace rl {
+
+struct Contact {
+    int32_t a, b;
+    V3 posA, posB, normal;
+    float dist, friction, restitution;
+    int32_t special;
+};
+
+constexpr int kMaxContacts = 40;
+
+struct Manifold {
+    int32_t a, b, n;
+    float breaking;
+    Contact pt[4];
+};
+
+struct ContactSet {
+    int32_t n;
+    int32_t overflow;
+    Contact c[kMaxContacts];
+};
+
+// relative contact breaking thresholds (btCollisionDispatcher::getNewManifold,
+// btCollisionShape::getContactBreakingThreshold): 0.02 * angularMotionDisc of the shape
+struct Thresholds { float ball, car; };
+RL_HDI Thresholds contact_thresholds(const CarConsts& k) {
+    Thresholds t;
+    // btCollisionShape::getBoundingSphere, sphere case (ROCKETSIM CHANGE: radius + 0.08), centre 0
+    t.ball = (float)((double)(C::BALL_RADIUS * UU2BT) + 0.08) * C::CONTACT_BREAKING;
+    // compound: local AABB = hitbox offset +- half extents
+    V3 mn = k.hitboxOffset - k.halfExt, mx = k.hitboxOffset + k.halfExt;
+    float radius = len(mx - mn) * 0.5f;
+    V3 center = (mn + mx) * 0.5f;
+    t.car = (radius + len(center)) * C::CONTACT_BREAKING;
+    return t;
+}
+
+// btPersistentManifold::sortCachedPoints with gContactCalcArea3Points (btPersistentManifold.cpp:110-190)
+RL_HD inline int manifold_sort_cached(const Manifold& m, const Contact& pt) {
+    int maxPenIdx = -1;
+    float maxPen = pt.dist;
+    for (int i = 0; i < 4; i++)
+        if (m.pt[i].dist < maxPen) { maxPenIdx = i; maxPen = m.pt[i].dist; }
+    float res[4] = {0, 0, 0, 0};
+    const V3 &p0 = m.pt[0].posA, &p1 = m.pt[1].posA, &p2 = m.pt[2].posA, &p3 = m.pt[3].posA;
+    if (maxPenIdx != 0) res[0] = len2(cross(pt.posA - p1, p3 - p2));
+    if (maxPenIdx != 1) res[1] = len2(cross(pt.posA - p0, p3 - p2));
+    if (maxPenIdx != 2) res[2] = len2(cross(pt.posA - p0, p3 - p1));
+    if (maxPenIdx != 3) res[3] = len2(cross(pt.posA - p0, p2 - p1));
+    // btVector4::closestAxis4 == index of max |.|
+    int best = 0; float bv = fabsf(res[0]);
+    for (int i = 1; i < 4; i++) if (fabsf(res[i]) > bv) { bv = fabsf(res[i]); best = i; }
+    return best;
+}
+
+struct CollideCtx {
+    ArenaS* a;
+    const SimCfg* cfg;
+    TickW* tw;
+    const CarConsts* k;
+    int64_t tick;
+    int32_t firstTickOfStep;  // bump counters only stick when the callback fires during Gym::Step's first tick (see rl_tick.h)
+};
+
+// ---- Arena::_BulletContactAddedCallback ------------------------------------------------------
+RL_HD inline void on_car_ball(CollideCtx& x, int ci, Contact& cp) {
+    ArenaS& a = *x.a;
+    CarS& car = a.cars[ci];
+    cp.friction = C::CARBALL_FRICTION; cp.restitution = C::CARBALL_RESTITUTION;
+    V3 ballPosUU = to_uu(a.ball.pos), ballVelUU = to_uu(a.ball.vel);
+    V3 carPosUU = to_uu(car.pos), carVelUU = to_uu(car.vel);
+    car.hitValid = 1;
+    car.hitRelPos = (cp.posB - a.ball.pos) * BT2UU;  // m_localPointB of the ball (identity basis)
+    set_i64(car.hitTickLo, car.hitTickHi, x.tick);
+    car.hitBallPos = ballPosUU;
+    car.hitExtraVel = V3();
+    int64_t extraTick = get_i64(car.hitExtraTickLo, car.hitExtraTickHi);
+    // uint64 compare: ~0ULL (== -1 here) means "never"
+    bool never = extraTick < 0;
+    if (never || (x.tick > extraTick + 1) || (extraTick > x.tick)) set_i64(car.hitExtraTickLo, car.hitExtraTickHi, x.tick);
+    else return;
+    V3 carForward = car.rot.col(0);
+    V3 relPos = ballPosUU - carPosUU;
+    V3 relVel = ballVelUU - carVelUU;
+    float relSpeed = fminf_(len(relVel), C::BALL_CAR_EXTRA_IMPULSE_MAXDELTAVEL_UU);
+    if (relSpeed > 0) {
+        V3 hitDir = safe_normalized(relPos * V3(1, 1, C::BALL_CAR_EXTRA_IMPULSE_Z_SCALE));
+        V3 fwdAdj = carForward * dot(hitDir, carForward) * (1 - C::BALL_CAR_EXTRA_IMPULSE_FORWARD_SCALE);
+        hitDir = safe_normalized(hitDir - fwdAdj);
+        const float fx[4] = {0, 500.f, 2300.f, 4600.f}, fy[4] = {0.65f, 0.65f, 0.55f, 0.30f};
+        V3 addedVel = (hitDir * relSpeed) * curve(fx, fy, relSpeed) * 1.f;
+        car.hitExtraVel = addedVel;
+        x.tw->ballVelCache += addedVel * UU2BT;
+    }
+}
+
+RL_HD inline void on_car_car(CollideCtx& x, int c1, int c2, Contact& cp) {
+    ArenaS& a = *x.a;
+    cp.friction = C::CARCAR_FRICTION; cp.restitution = C::CARCAR_RESTITUTION;
+    for (int i = 0; i < 2; i++) {
+        bool swapped = i == 1;
+        if (swapped) { int t = c1; c1 = c2; c2 = t; }
+        CarS& s = a.cars[c1];
+        CarS& o = a.cars[c2];
+        if (s.isDemoed || o.isDemoed) return;
+        if (s.carContactOtherId == c2 + 1 && s.carContactCooldown > 0) continue;
+        V3 sPos = to_uu(s.pos), sVel = to_uu(s.vel), oPos = to_uu(o.pos), oVel = to_uu(o.vel);
+        V3 deltaPos = oPos - sPos;
+        if (ref_dot(sVel, deltaPos) > 0) {
+            V3 velDir = ref_normalized(sVel);
+            V3 dirToOther = ref_normalized(deltaPos);
+            float speedTowards = ref_dot(sVel, dirToOther);
+            float otherAway = ref_dot(oVel, velDir);
+            if (speedTowards > otherAway) {
+                // m_localPointA / m_localPointB in the respective car's frame; manifold A is the lower-id car
+                V3 wp = swapped ? cp.posB : cp.posA;
+                const CarS& own = a.cars[c1];
+                V3 local = tmul(wp - own.pos, own.rot);
+                bool bumper = (local.x * BT2UU) > C::BUMP_MIN_FORWARD_DIST;
+                if (bumper) {
+                    bool isDemo = s.isSupersonic != 0;
+                    if (isDemo) isDemo = car_team(c1, x.cfg->spawnOpponents) != car_team(c2, x.cfg->spawnOpponents);
+                    if (isDemo) {
+                        o.isDemoed = 1; o.demoRespawnTimer = C::DEMO_RESPAWN_TIME;
+                    } else {
+                        bool groundHit = o.isOnGround != 0;
+                        const float gx[3] = {0.f, 1400.f, 2200.f}, gy[3] = {5.f / 6.f, 1100.f, 1530.f};
+                        const float ax[3] = {0.f, 1400.f, 2200.f}, ay[3] = {5.f / 6.f, 1390.f, 1945.f};
+                        const float ux[3] = {0.f, 1400.f, 2200.f}, uy[3] = {2.f / 6.f, 278.f, 417.f};
+                        float baseScale = groundHit ? curve(gx, gy, speedTowards) : curve(ax, ay, speedTowards);
+                        V3 hitUp = o.isOnGround ? o.rot.col(2) : V3(0, 0, 1);
+                        V3 bump = velDir * baseScale + hitUp * curve(ux, uy, speedTowards) * 1.f;
+                        x.tw->cars[c2].velCache += bump * UU2BT;
+                    }
+                    s.carContactOtherId = c2 + 1;
+                    s.carContactCooldown = C::BUMP_COOLDOWN_TIME;
+                    // Gym's _BumpCallback (G/Gym.cpp:27-36): opponents only
+                    if (x.firstTickOfStep && car_team(c1, x.cfg->spawnOpponents) != car_team(c2, x.cfg->spawnOpponents)) {
+                        s.matchBumps++;
+                        if (isDemo) s.matchDemos++;
+                    }
+                }
+            }
+        }
+    }
+}
+
+RL_HDI void on_car_world(CollideCtx& x, int ci, Contact& cp) {
+    CarS& car = x.a->cars[ci];
+    car.worldContactHas = 1;
+    car.worldContactNormal = cp.normal;
+    cp.friction = C::CARWORLD_FRICTION; cp.restitution = C::CARWORLD_RESTITUTION;
+}
+
+// btManifoldResult::addContactPoint (btManifoldResult.cpp:110-215) incl. the callback dispatch
+RL_HD inline void manifold_add(CollideCtx& x, Manifold& m, V3 normalOnB, V3 pointOnB, float depth, const MeshSet* ms, int tri) {
+    if (depth > m.breaking) return;
+    Contact cp;
+    cp.a = m.a; cp.b = m.b;
+    cp.posA = pointOnB + normalOnB * depth;
+    cp.posB = pointOnB;
+    cp.normal = normalOnB;
+    cp.dist = depth;
+    cp.special = 0;
+    // combined material (btManifoldResult.cpp:63-82): min friction / max restitution against statics, product otherwise
+    if (m.a == 0 && m.b == -1) { cp.friction = fminf_(C::BALL_FRICTION, C::WORLD_FRICTION); cp.restitution = fmaxf_(C::BALL_RESTITUTION, C::WORLD_RESTITUTION); }
+    else { cp.friction = 0.3f; cp.restitution = 0.1f; }
+    int idx = m.n;
+    if (idx == 4) idx = manifold_sort_cached(m, cp);
+    else m.n++;
+    if (idx < 0) idx = 0;
+    m.pt[idx] = cp;
+    Contact& p = m.pt[idx];
+    // gContactAddedCallback; demoed cars have no contact response -> returns before anything
+    bool aCar = m.a >= 1, bCar = m.b >= 1;
+    if (aCar && x.a->cars[m.a - 1].isDemoed) return;
+    if (bCar && x.a->cars[m.b - 1].isDemoed) return;
+    if (aCar && m.b == 0) on_car_ball(x, m.a - 1, p);
+    else if (aCar && bCar) on_car_car(x, m.a - 1, m.b - 1, p);
+    else if (aCar && m.b == -1) on_car_world(x, m.a - 1, p);
+    else if (m.a == 0 && m.b == -1) p.special = 1;
+    if (ms && tri >= 0) adjust_internal_edge(p, *ms, tri);
+}
+
+RL_HDI void manifold_flush(ContactSet& cs, const Manifold& m) {
+    for (int i = 0; i < m.n; i++) {
+        if (cs.n < kMaxContacts) cs.c[cs.n++] = m.pt[i];
+        else cs.overflow++;
+    }
+}
+
+// ---- shape pairs -----------------------------------------------------------------------------
+// btConvexPlaneCollisionAlgorithm::processCollision (btConvexPlaneCollisionAlgorithm.cpp:92-125)
+RL_HD inline void sphere_plane(CollideCtx& x, ContactSet& cs, V3 center, float radius, int planeIdx, float breaking) {
+    PlaneDef p = world_plane(planeIdx);
+    V3 cIn = center - p.origin;
+    // localGetSupportingVertex(-n) = -n * radius (btSphereShape)
+    V3 vtx = cIn + (-p.n) * radius;
+    float distance = dot(p.n, vtx) - 0.f;
+    if (distance < breaking) {
+        Manifold m; m.a = 0; m.b = -1; m.n = 0; m.breaking = breaking;
+        V3 proj = vtx - p.n * distance;
+        manifold_add(x, m, p.n, proj + p.origin, distance, nullptr, -1);
+        manifold_flush(cs, m);
+    }
+}
+
+RL_HD inline void box_plane(CollideCtx& x, ContactSet& cs, int ci, int planeIdx, float breaking) {
+    const CarS& c = x.a->cars[ci];
+    const CarConsts& k = *x.k;
+    PlaneDef p = world_plane(planeIdx);
+    V3 boxCenter = c.pos + c.rot * k.hitboxOffset;
+    V3 dirLocal = tmul(-p.n, c.rot);  // planeInConvex basis * -n
+    V3 vl(dirLocal.x >= 0 ? k.halfExt.x : -k.halfExt.x, dirLocal.y >= 0 ? k.halfExt.y : -k.halfExt.y, dirLocal.z >= 0 ? k.halfExt.z : -k.halfExt.z);
+    V3 vtx = (boxCenter + c.rot * vl) - p.origin;
+    float distance = dot(p.n, vtx);
+    if (distance < breaking) {
+        Manifold m; m.a = 1 + ci; m.b = -1; m.n = 0; m.breaking = breaking;
+        V3 proj = vtx - p.n * distance;
+        manifold_add(x, m, p.n, proj + p.origin, distance, nullptr, -1);
+        manifold_flush(cs, m);
+    }
+}
+
+// TestTriangleAgainstAabb2 (LinearMath/btAabbUtil2.h)
+RL_HDI bool tri_vs_aabb(const Tri& t, V3 mn, V3 mx) {
+    if (fminf_(fminf_(t.v0.x, t.v1.x), t.v2.x) > mx.x) return false;
+    if (fmaxf_(fmaxf_(t.v0.x, t.v1.x), t.v2.x) < mn.x) return false;
+    if (fminf_(fminf_(t.v0.z, t.v1.z), t.v2.z) > mx.z) return false;
+    if (fmaxf_(fmaxf_(t.v0.z, t.v1.z), t.v2.z) < mn.z) return false;
+    if (fminf_(fminf_(t.v0.y, t.v1.y), t.v2.y) > mx.y) return false;
+    if (fmaxf_(fmaxf_(t.v0.y, t.v1.y), t.v2.y) < mn.y) return false;
+    return true;
+}
+
+// SphereTriangleDetector::collide (SphereTriangleDetector.cpp:139-243, RocketSim-modified)
+RL_HD inline bool sphere_triangle(V3 center, float radius, const Tri& t, float breaking, V3& point, V3& resultNormal, float& depth) {
+    float radiusWithThreshold = radius + breaking;
+    V3 normal = cross(t.v1 - t.v0, t.v2 - t.v0);
+    float l2 = len2(normal);
+    bool hasContact = false;
+    V3 contactPoint;
+    if (l2 >= kEps * kEps) {
+        normal = normal / sqrtf(l2);
+        V3 p1ToCentre = center - t.v0;
+        float distanceFromPlane = dot(p1ToCentre, normal);
+        if (distanceFromPlane < 0.f) { distanceFromPlane *= -1.f; normal = normal * -1.f; }
+        if (distanceFromPlane < radiusWithThreshold) {
+            // pointInTriangle (barycentric)
+            V3 u = t.v1 - t.v0, v = t.v2 - t.v0;
+            V3 n = cross(u, v);
+            float nLenSq = dot(n, n);
+            V3 w = center - t.v0;
+            float gamma = dot(cross(u, w), n) / nLenSq;
+            float beta = dot(cross(w, v), n) / nLenSq;
+            float alpha = 1 - gamma - beta;
+            bool inside = (0 <= alpha) && (alpha <= 1) && (0 <= beta) && (beta <= 1) && (0 <= gamma) && (gamma <= 1);
+            if (inside) {
+                hasContact = true;
+                contactPoint = center - normal * distanceFromPlane;
+            } else {
+                float minDistSqr = radiusWithThreshold * radiusWithThreshold;
+                V3 nearest = closest_pt_triangle(center, t.v0, t.v1, t.v2);
+                float d2 = len2(nearest - center);
+                if (d2 < minDistSqr) { hasContact = true; contactPoint = nearest; }
+            }
+        }
+    }
+    if (hasContact) {
+        V3 contactToCentre = center - contactPoint;
+        float distanceSqr = len2(contactToCentre);
+        if (distanceSqr < radiusWithThreshold * radiusWithThreshold) {
+            if (distanceSqr > kEps) {
+                float distance = sqrtf(distanceSqr);
+                resultNormal = normalized(contactToCentre);
+                point = contactPoint;
+                depth = -(radius - distance);
+            } else {
+                resultNormal = normal; point = contactPoint; depth = -radius;
+            }
+            return true;
+        }
+    }
+    return false;
+}
+
+// support-plane early out of btConvexTriangleCallback::processTriangle (btConvexConcaveCollisionAlgorithm.cpp:100-138)
+template <class Support>
+RL_HDI bool tri_early_out(const Tri& t, float threshold, Support sup) {
+    V3 n = normalized(cross(t.v1 - t.v0, t.v2 - t.v0));
+    float dist = dot(n, t.v0) - dot(n, sup(n));
+    if (dist > threshold) return true;
+    n = n * -1.f;
+    dist = dot(n, t.v0) - dot(n, sup(n));
+    return dist > threshold;
+}
+
+// ball vs every mesh: btConvexConcaveCollisionAlgorithm + btSphereTriangleCollisionAlgorithm
+RL_HD inline void sphere_meshes(CollideCtx& x, ContactSet& cs, const MeshSet& ms, V3 center, float radius, float breaking) {
+    float am = radius + 0.08f;  // btSphereShape::getAabb
+    V3 mn = center - V3(am, am, am), mx = center + V3(am, am, am);
+    for (int mi = 0; mi < ms.numMeshes; mi++) {
+        const BvhNode& root = ms.nodes[ms.nodeStart[mi]];
+        if (!aabb_overlap(root.mn, root.mx, mn, mx)) continue;
+        Manifold m; m.a = 0; m.b = -1; m.n = 0; m.breaking = breaking;
+        for (int h = ms.hdrStart[mi]; h < ms.hdrStart[mi + 1]; h++) {
+            int i = ms.hdrRoot[h], end = ms.hdrRoot[h] + ms.hdrSize[h];
+            while (i < end) {
+                const BvhNode& nd = ms.nodes[i];
+                bool ov = aabb_overlap(nd.mn, nd.mx, mn, mx);
+                if (nd.tri >= 0) {
+                    if (ov) {
+                        const Tri& t = ms.tris[nd.tri];
+                        if (tri_vs_aabb(t, mn, mx)) {
+                            auto sup = [&](V3 d) {  // btSphereShape::localGetSupportingVertex
+                                float l2 = len2(d);
+                                V3 dn = l2 < kEps * kEps ? V3(-1, -1, -1) : d;
+                                return center + normalized(dn) * radius;
+                            };
+                            if (!tri_early_out(t, breaking, sup)) {
+                                V3 point, normal; float depth;
+                                if (sphere_triangle(center, radius, t, breaking, point, normal, depth)) manifold_add(x, m, normal, point, depth, &ms, nd.tri);
+                            }
+                        }
+                    }
+                    i++;
+                } else {
+                    i += ov ? 1 : nd.escape;
+                }
+            }
+        }
+        manifold_flush(cs, m);
+    }
+}
+
+// car hitbox vs every mesh: btCompoundCollisionAlgorithm -> btConvexConcaveCollisionAlgorithm -> GJK per triangle
+RL_HD inline void box_meshes(CollideCtx& x, ContactSet& cs, const MeshSet& ms, int ci, float breaking) {
+    const CarS& c = x.a->cars[ci];
+    const CarConsts& k = *x.k;
+    V3 boxCenter = c.pos + c.rot * k.hitboxOffset;
+    // btBoxShape::getAabb -> btTransformAabb(halfExtentsWithoutMargin, margin, t)
+    V3 ext(dot(vabs(c.rot.r[0]), k.halfExt), dot(vabs(c.rot.r[1]), k.halfExt), dot(vabs(c.rot.r[2]), k.halfExt));
+    V3 mn = boxCenter - ext, mx = boxCenter + ext;
+    for (int mi = 0; mi < ms.numMeshes; mi++) {
+        const BvhNode& root = ms.nodes[ms.nodeStart[mi]];
+        if (!aabb_overlap(root.mn, root.mx, mn, mx)) continue;
+        Manifold m; m.a = 1 + ci; m.b = -1; m.n = 0; m.breaking = breaking;
+        for (int h = ms.hdrStart[mi]; h < ms.hdrStart[mi + 1]; h++) {
+            int i = ms.hdrRoot[h], end = ms.hdrRoot[h] + ms.hdrSize[h];
+            while (i < end) {
+                const BvhNode& nd = ms.nodes[i];
+                bool ov = aabb_overlap(nd.mn, nd.mx, mn, mx);
+                if (nd.tri >= 0) {
+                    if (ov) {
+                        const Tri& t = ms.tris[nd.tri];
+                        if (tri_vs_aabb(t, mn, mx)) {
+                            auto sup = [&](V3 d) {  // btBoxShape::localGetSupportingVertex (with margin)
+                                V3 dl = tmul(d, c.rot);
+                                V3 v(dl.x >= 0 ? k.halfExt.x : -k.halfExt.x, dl.y >= 0 ? k.halfExt.y : -k.halfExt.y, dl.z >= 0 ? k.halfExt.z : -k.halfExt.z);
+                                return boxCenter + c.rot * v;
+                            };
+                            if (!tri_early_out(t, breaking, sup)) {
+                                V3 normal, pointOnB; float dist;
+                                if (box_triangle_contact(boxCenter, c.rot, k.halfExt, t, breaking, normal, pointOnB, dist))
+                                    manifold_add(x, m, normal, pointOnB, dist, &ms, nd.tri);
+                            }
+                        }
+                    }
+                    i++;
+                } else {
+                    i += ov ? 1 : nd.escape;
+                }
+            }
+        }
+        manifold_flush(cs, m);
+    }
+}
+
+// ball vs car hitbox: GJK of (box core + 0.04) against (point + radius) == closest point on the core
+RL_HD inline void car_ball(CollideCtx& x, ContactSet& cs, int ci, float breaking) {
+    const CarS& c = x.a->cars[ci];
+    const CarConsts& k = *x.k;
+    float radius = C::BALL_RADIUS * UU2BT;
+    V3 boxCenter = c.pos + c.rot * k.hitboxOffset;
+    V3 normal, pointOnB; float dist;
+    if (box_sphere_contact(boxCenter, c.rot, k.halfExt, x.a->ball.pos, radius, breaking, normal, pointOnB, dist)) {
+        Manifold m; m.a = 1 + ci; m.b = 0; m.n = 0; m.breaking = breaking;
+        manifold_add(x, m, normal, pointOnB, dist, nullptr, -1);
+        manifold_flush(cs, m);
+    }
+}
+
+RL_HD inline void car_car(CollideCtx& x, ContactSet& cs, int c1, int c2, float breaking) {
+    const CarS& A = x.a->cars[c1];
+    const CarS& B = x.a->cars[c2];
+    const CarConsts& k = *x.k;
+    V3 ca = A.pos + A.rot * k.hitboxOffset, cb = B.pos + B.rot * k.hitboxOffset;
+    BoxBoxResult r;
+    box_box(ca, A.rot, k.halfExt, cb, B.rot, k.halfExt, r);
+    if (r.n > 0) {
+        Manifold m; m.a = 1 + c1; m.b = 1 + c2; m.n = 0; m.breaking = breaking;
+        for (int i = 0; i < r.n; i++) manifold_add(x, m, r.normal, r.point[i], r.depth[i], nullptr, -1);
+        manifold_flush(cs, m);
+    }
+}
+
+}  // namespace rl
+
+#include "rl_boxbox.h"

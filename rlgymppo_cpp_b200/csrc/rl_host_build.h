@@ -1,0 +1,231 @@
+// rl_host_build.h — HOST-only builders: .cmf parsing + BVH construction, lookup tables, SimCfg.
+//
+// BVH build follows btQuantizedBvh::buildTree / calcSplittingAxis / sortAndCalcSplittingIndex
+// (B/BulletCollision/BroadphaseCollision/btQuantizedBvh.cpp:117-300) and btOptimizedBvh::build's
+// leaf boxes (min extent padding 0.002), so leaves end up in the reference's order; the
+// "subtree header" list reproduces the order walkStacklessQuantizedTreeCacheFriendly visits them
+// (subtrees <= 2048 bytes of 16-byte quantised nodes = 128 nodes).
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "rl_gym.h"
+#include "rl_mesh.h"
+
+namespace rl {
+
+struct HostMeshSet {
+    std::vector<Tri> tris;
+    std::vector<BvhNode> nodes;
+    std::vector<int32_t> hdrRoot, hdrSize, triFlags;
+    std::vector<float> triEdgeAngles;
+    MeshSet meta;  // pointers unset
+};
+
+namespace detail {
+struct Leaf { V3 mn, mx; int tri; };
+
+struct BvhBuilder {
+    std::vector<Leaf> leaves;
+    std::vector<BvhNode>& nodes;
+    std::vector<int32_t>& hdrRoot;
+    std::vector<int32_t>& hdrSize;
+    int nodeBase;
+    explicit BvhBuilder(std::vector<BvhNode>& n, std::vector<int32_t>& hr, std::vector<int32_t>& hs) : nodes(n), hdrRoot(hr), hdrSize(hs), nodeBase(0) {}
+
+    static V3 center(const Leaf& l) { return (l.mx + l.mn) * 0.5f; }
+
+    int calcSplittingAxis(int s, int e) {
+        V3 means(0, 0, 0), variance(0, 0, 0);
+        int n = e - s;
+        for (int i = s; i < e; i++) means += center(leaves[i]);
+        means *= (1.f / (float)n);
+        for (int i = s; i < e; i++) { V3 d = center(leaves[i]) - means; variance += d * d; }
+        variance *= (1.f / ((float)n - 1));
+        return variance.x < variance.y ? (variance.y < variance.z ? 2 : 1) : (variance.x < variance.z ? 2 : 0);
+    }
+    int sortAndCalcSplittingIndex(int s, int e, int axis) {
+        int splitIndex = s, n = e - s;
+        V3 means(0, 0, 0);
+        for (int i = s; i < e; i++) means += center(leaves[i]);
+        means *= (1.f / (float)n);
+        float splitValue = means[axis];
+        for (int i = s; i < e; i++) {
+            if (center(leaves[i])[axis] > splitValue) { std::swap(leaves[i], leaves[splitIndex]); splitIndex++; }
+        }
+        int range = n / 3;
+        bool unbalanced = (splitIndex <= (s + range)) || (splitIndex >= (e - 1 - range));
+        if (unbalanced) splitIndex = s + (n >> 1);
+        return splitIndex;
+    }
+    static int subtreeSize(const BvhNode& n) { return n.tri >= 0 ? 1 : n.escape; }
+    void build(int s, int e) {
+        int cur = (int)nodes.size();
+        if (e - s == 1) {
+            BvhNode nd;
+            for (int a = 0; a < 3; a++) { nd.mn[a] = leaves[s].mn[a]; nd.mx[a] = leaves[s].mx[a]; }
+            nd.tri = leaves[s].tri; nd.escape = 1;
+            nodes.push_back(nd);
+            return;
+        }
+        int axis = calcSplittingAxis(s, e);
+        int split = sortAndCalcSplittingIndex(s, e, axis);
+        BvhNode nd;
+        V3 mn(1e30f, 1e30f, 1e30f), mx(-1e30f, -1e30f, -1e30f);
+        for (int i = s; i < e; i++) { mn = vmin(mn, leaves[i].mn); mx = vmax(mx, leaves[i].mx); }
+        for (int a = 0; a < 3; a++) { nd.mn[a] = mn[a]; nd.mx[a] = mx[a]; }
+        nd.tri = -1; nd.escape = 0;
+        nodes.push_back(nd);
+        int left = (int)nodes.size();
+        build(s, split);
+        int right = (int)nodes.size();
+        build(split, e);
+        int escape = (int)nodes.size() - cur;
+        nodes[cur].escape = escape;
+        const int MAX_NODES = 2048 / 16;
+        if (escape > MAX_NODES) {  // updateSubtreeHeaders
+            int ls = subtreeSize(nodes[left]), rs = subtreeSize(nodes[right]);
+            if (ls <= MAX_NODES) { hdrRoot.push_back(left); hdrSize.push_back(ls); }
+            if (rs <= MAX_NODES) { hdrRoot.push_back(right); hdrSize.push_back(rs); }
+        }
+    }
+};
+}  // namespace detail
+
+inline void host_build_meshes(const void* const* blobs, const size_t* sizes, int n, HostMeshSet& out) {
+    if (n > kMaxMeshes) throw std::runtime_error("too many collision meshes");
+    out = HostMeshSet();
+    MeshSet& ms = out.meta;
+    std::memset(&ms, 0, sizeof(ms));
+    ms.numMeshes = n;
+    for (int m = 0; m < n; m++) {
+        const uint8_t* b = (const uint8_t*)blobs[m];
+        if (sizes[m] < 8) throw std::runtime_error("collision mesh blob too small");
+        int32_t nt, nv;
+        std::memcpy(&nt, b, 4); std::memcpy(&nv, b + 4, 4);
+        if (nt <= 0 || nv <= 0 || nt > 1000000 || nv > 1000000) throw std::runtime_error("bad triangle/vertex count in collision mesh");
+        size_t need = 8 + (size_t)nt * 12 + (size_t)nv * 12;
+        if (sizes[m] < need) throw std::runtime_error("collision mesh blob truncated");
+        const int32_t* idx = (const int32_t*)(b + 8);
+        const float* vtx = (const float*)(b + 8 + (size_t)nt * 12);
+        int triBase = (int)out.tris.size();
+        detail::BvhBuilder bb(out.nodes, out.hdrRoot, out.hdrSize);
+        for (int t = 0; t < nt; t++) {
+            Tri tr;
+            V3* vs[3] = {&tr.v0, &tr.v1, &tr.v2};
+            for (int k = 0; k < 3; k++) {
+                int vi = idx[t * 3 + k];
+                if (vi < 0 || vi >= nv) throw std::runtime_error("bad triangle vertex index in collision mesh");
+                *vs[k] = V3(vtx[vi * 3 + 0], vtx[vi * 3 + 1], vtx[vi * 3 + 2]);
+            }
+            out.tris.push_back(tr);
+            detail::Leaf l;
+            l.mn = vmin(vmin(tr.v0, tr.v1), tr.v2); l.mx = vmax(vmax(tr.v0, tr.v1), tr.v2);
+            const float MIN_DIM = 0.002f, MIN_HALF = 0.001f;  // btOptimizedBvh.cpp NodeTriangleCallback
+            for (int a = 0; a < 3; a++) if (l.mx[a] - l.mn[a] < MIN_DIM) { l.mx[a] = l.mx[a] + MIN_HALF; l.mn[a] = l.mn[a] - MIN_HALF; }
+            l.tri = triBase + t;
+            bb.leaves.push_back(l);
+        }
+        ms.nodeStart[m] = (int)out.nodes.size();
+        ms.hdrStart[m] = (int)out.hdrRoot.size();
+        bb.build(0, nt);
+        ms.nodeCount[m] = (int)out.nodes.size() - ms.nodeStart[m];
+        if ((int)out.hdrRoot.size() == ms.hdrStart[m]) {  // whole tree fits one header
+            out.hdrRoot.push_back(ms.nodeStart[m]);
+            out.hdrSize.push_back(ms.nodeCount[m]);
+        }
+    }
+    ms.hdrStart[n] = (int)out.hdrRoot.size();
+    ms.numTris = (int)out.tris.size(); ms.numNodes = (int)out.nodes.size(); ms.numHdrs = (int)out.hdrRoot.size();
+    out.triFlags.assign(out.tris.size(), 0);
+    out.triEdgeAngles.assign(out.tris.size() * 3, 6.283185307179586f);
+}
+
+// DiscreteAction table (G/Utils/ActionParsers/DiscreteAction.cpp:3-67)
+inline int host_build_action_table(float* t) {
+    const float RB[2] = {0, 1}, RF[3] = {-1, 0, 1};
+    int n = 0;
+    auto push = [&](float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7) {
+        float v[8] = {a0, a1, a2, a3, a4, a5, a6, a7};
+        for (int k = 0; k < 8; k++) t[n * 8 + k] = v[k];
+        n++;
+    };
+    for (float throttle : RF) for (float steer : RF) for (float boost : RB) for (float handbrake : RB) {
+        if (boost == 1 && throttle != 1) continue;
+        push(throttle, steer, 0, steer, 0, 0, boost, handbrake);
+    }
+    for (float pitch : RF) for (float yaw : RF) for (float roll : RF) for (float jump : RB) for (float boost : RB) {
+        if (jump == 1 && yaw != 0) continue;
+        if (pitch == roll && roll == jump && jump == 0) continue;
+        float handbrake = (jump == 1) && (pitch != 0 || yaw != 0 || roll != 0);
+        push(boost, yaw, pitch, yaw, roll, jump, boost, handbrake);
+    }
+    return n;
+}
+
+inline void host_build_tables(Tables& tb) {
+    int n = host_build_action_table(tb.actions);
+    if (n != 90) throw std::runtime_error("action table size != 90");
+    // RocketSim pad order: 6 big then 28 small (R/RLConst.h:215-253, Arena.cpp:540-558)
+    static const float BIG[6][3] = {{-3584, 0, 73}, {3584, 0, 73}, {-3072, 4096, 73}, {3072, 4096, 73}, {-3072, -4096, 73}, {3072, -4096, 73}};
+    static const float SMALL[28][3] = {
+        {0, -4240, 70}, {-1792, -4184, 70}, {1792, -4184, 70}, {-940, -3308, 70}, {940, -3308, 70}, {0, -2816, 70}, {-3584, -2484, 70},
+        {3584, -2484, 70}, {-1788, -2300, 70}, {1788, -2300, 70}, {-2048, -1036, 70}, {0, -1024, 70}, {2048, -1036, 70}, {-1024, 0, 70},
+        {1024, 0, 70}, {-2048, 1036, 70}, {0, 1024, 70}, {2048, 1036, 70}, {-1788, 2300, 70}, {1788, 2300, 70}, {-3584, 2484, 70},
+        {3584, 2484, 70}, {0, 2816, 70}, {-940, 3308, 70}, {940, 3308, 70}, {-1792, 4184, 70}, {1792, 4184, 70}, {0, 4240, 70}};
+    for (int i = 0; i < 6; i++) for (int k = 0; k < 3; k++) tb.padPos[i * 3 + k] = BIG[i][k];
+    for (int i = 0; i < 28; i++) for (int k = 0; k < 3; k++) tb.padPos[(6 + i) * 3 + k] = SMALL[i][k];
+    // CommonValues::BOOST_LOCATIONS (G/Utils/CommonValues.h:40-75)
+    static const float LOC[34][2] = {
+        {0, -4240}, {-1792, -4184}, {1792, -4184}, {-3072, -4096}, {3072, -4096}, {-940, -3308}, {940, -3308}, {0, -2816}, {-3584, -2484},
+        {3584, -2484}, {-1788, -2300}, {1788, -2300}, {-2048, -1036}, {0, -1024}, {2048, -1036}, {-3584, 0}, {-1024, 0}, {1024, 0},
+        {3584, 0}, {-2048, 1036}, {0, 1024}, {2048, 1036}, {-1788, 2300}, {1788, 2300}, {-3584, 2484}, {3584, 2484}, {0, 2816},
+        {-940, 3310}, {940, 3308}, {-3072, 4096}, {3072, 4096}, {-1792, 4184}, {1792, 4184}, {0, 4240}};
+    for (int i = 0; i < 34; i++) {
+        int found = -1;
+        for (int j = 0; j < 34; j++) {
+            float dx = tb.padPos[j * 3] - LOC[i][0], dy = tb.padPos[j * 3 + 1] - LOC[i][1];
+            if (dx * dx + dy * dy < 10) { found = j; break; }
+        }
+        if (found < 0) throw std::runtime_error("boost pad index map: no matching pad");
+        tb.padMap[i] = found;
+    }
+}
+
+inline void host_build_simcfg(const rlg_engine_cfg& c, SimCfg& s) {
+    std::memset(&s, 0, sizeof(s));
+    if (c.num_arenas <= 0) throw std::runtime_error("num_arenas must be > 0");
+    if (c.team_size < 1 || c.team_size > 3) throw std::runtime_error("team_size must be 1..3");
+    if (c.tick_skip < 1) throw std::runtime_error("tick_skip must be >= 1");
+    s.numArenas = c.num_arenas;
+    s.spawnOpponents = c.spawn_opponents != 0;
+    s.numCars = c.team_size * (s.spawnOpponents ? 2 : 1);
+    s.tickSkip = c.tick_skip;
+    s.obsKind = c.obs_kind; s.obsMaxPlayers = c.obs_max_players;
+    if (s.obsKind == RLG_OBS_PADDED) {
+        // DefaultOBSPadded.cpp:41-45
+        if (c.team_size - 1 > c.obs_max_players - 1) throw std::runtime_error("DefaultOBSPadded: Too many teammates for OBS");
+        if ((s.spawnOpponents ? c.team_size : 0) > c.obs_max_players) throw std::runtime_error("DefaultOBSPadded: Too many opponents for OBS");
+        s.obsSize = 51 + 19 * 2 * c.obs_max_players;
+    } else {
+        s.obsSize = 51 + 19 * s.numCars;
+    }
+    if (c.num_reward_terms < 0 || c.num_reward_terms > RLG_MAX_REWARD_TERMS) throw std::runtime_error("bad num_reward_terms");
+    s.numRewardTerms = c.num_reward_terms;
+    for (int i = 0; i < c.num_reward_terms; i++) {
+        s.rewards[i].kind = c.reward_terms[i].kind; s.rewards[i].weight = c.reward_terms[i].weight;
+        for (int k = 0; k < 11; k++) s.rewards[i].params[k] = c.reward_terms[i].params[k];
+    }
+    s.zeroSum = c.zero_sum; s.teamSpirit = c.team_spirit; s.opponentScale = c.opponent_scale;
+    s.noTouchMaxSteps = c.no_touch_max_steps; s.goalScoreTerminal = c.goal_score_terminal;
+    s.stateSetter = c.state_setter; s.randBallSpeed = c.rand_ball_speed; s.randCarSpeed = c.rand_car_speed; s.carsOnGround = c.cars_on_ground;
+    // reference player order = unordered_set<Car*> iteration order; for the small sets used this is descending id
+    for (int i = 0; i < s.numCars; i++) s.playerOrder[i] = s.numCars - 1 - i;
+    s.ballDampFactor = powf(1.f - C::BALL_DRAG, kTickTime);                 // btRigidBody::applyDamping
+    s.flipZDampFactor = powf(1 - C::FLIP_Z_DAMP_120, kTickTime / (1 / 120.f));  // Car.cpp:753
+}
+
+}  // namespace rl

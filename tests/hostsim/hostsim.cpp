@@ -1,0 +1,131 @@
+// hostsim.cpp — TEST TOOL ONLY. Not shipped, not linked into librlgym_b200.so, never a fallback.
+//
+// Compiles the SAME device headers (rlgymppo_cpp_b200/csrc/rl_*.h, RL_HD functions) with g++ so
+// that the CPU-only test suite (`pytest -m "not gpu"`, no GPU in the dev container) can check the
+// kernel logic against the reference oracle / golden vectors before the code ever reaches a B200.
+// The product path is rlgymppo_cpp_b200/csrc/engine.cu; it fails loudly without a CUDA device.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../rlgymppo_cpp_b200/csrc/rl_convert.h"
+#include "../../rlgymppo_cpp_b200/csrc/rl_host_build.h"
+#include "../../rlgymppo_cpp_b200/csrc/rl_tick.h"
+
+using namespace rl;
+
+struct HostSim {
+    SimCfg cfg;
+    Tables tb;
+    HostMeshSet hm;
+    MeshSet ms;
+    std::vector<ArenaS> arenas;
+    std::vector<float> obs, reward;
+    std::vector<uint8_t> done;
+};
+
+static void bind_mesh(HostSim* h) {
+    h->ms = h->hm.meta;
+    h->ms.nodes = h->hm.nodes.data(); h->ms.tris = h->hm.tris.data();
+    h->ms.hdrRoot = h->hm.hdrRoot.data(); h->ms.hdrSize = h->hm.hdrSize.data();
+    h->ms.triFlags = h->hm.triFlags.data(); h->ms.triEdgeAngles = h->hm.triEdgeAngles.data();
+}
+
+extern "C" {
+
+void* hs_create(const rlg_engine_cfg* cfg, const void* const* blobs, const size_t* sizes, int n) {
+    try {
+        HostSim* h = new HostSim();
+        host_build_simcfg(*cfg, h->cfg);
+        host_build_tables(h->tb);
+        host_build_meshes(blobs, sizes, n, h->hm);
+        bind_mesh(h);
+        h->arenas.resize(cfg->num_arenas);
+        for (int a = 0; a < cfg->num_arenas; a++) arena_init(h->arenas[a], h->cfg.numCars, cfg->seed, (uint64_t)cfg->arena_id_base + a);
+        h->obs.resize((size_t)cfg->num_arenas * h->cfg.numCars * h->cfg.obsSize);
+        h->reward.resize((size_t)cfg->num_arenas * h->cfg.numCars);
+        h->done.resize(cfg->num_arenas);
+        return h;
+    } catch (std::exception& e) {
+        fprintf(stderr, "hs_create: %s\n", e.what());
+        return nullptr;
+    }
+}
+void hs_destroy(void* p) { delete (HostSim*)p; }
+int hs_obs_size(void* p) { return ((HostSim*)p)->cfg.obsSize; }
+int hs_num_cars(void* p) { return ((HostSim*)p)->cfg.numCars; }
+void hs_set_player_order(void* p, const int32_t* carIds) {
+    HostSim* h = (HostSim*)p;
+    for (int i = 0; i < h->cfg.numCars; i++) h->cfg.playerOrder[i] = carIds[i] - 1;
+}
+
+void hs_set_state(void* p, int arena, const rlg_car_state* cars, const rlg_ball_state* ball, const rlg_pad_state* pads, int64_t tick) {
+    HostSim* h = (HostSim*)p;
+    ArenaS& a = h->arenas[arena];
+    if (cars) for (int c = 0; c < h->cfg.numCars; c++) car_from_pod(a.cars[c], cars[c]);
+    if (ball) ball_from_pod(a.ball, *ball);
+    if (pads) for (int i = 0; i < kNumPads; i++) { a.pads[i].isActive = pads[i].is_active != 0; a.pads[i].cooldown = pads[i].cooldown; a.pads[i].prevLockedCarId = pads[i].prev_locked_car_id; }
+    if (tick >= 0) set_i64(a.tickLo, a.tickHi, tick);
+}
+void hs_get_state(void* p, int arena, rlg_car_state* cars, rlg_ball_state* ball, rlg_pad_state* pads, int64_t* tick) {
+    HostSim* h = (HostSim*)p;
+    ArenaS& a = h->arenas[arena];
+    if (cars) for (int c = 0; c < h->cfg.numCars; c++) { memset(&cars[c], 0, sizeof(rlg_car_state)); car_to_pod(cars[c], a.cars[c], c, h->cfg.spawnOpponents); }
+    if (ball) ball_to_pod(*ball, a.ball);
+    if (pads) for (int i = 0; i < kNumPads; i++) { pads[i].is_active = a.pads[i].isActive; pads[i].cooldown = a.pads[i].cooldown; pads[i].prev_locked_car_id = a.pads[i].prevLockedCarId; }
+    if (tick) *tick = get_i64(a.tickLo, a.tickHi);
+}
+void hs_tick(void* p, int arena, const rlg_controls* controls, int nticks) {
+    HostSim* h = (HostSim*)p;
+    ArenaS& a = h->arenas[arena];
+    if (controls) for (int c = 0; c < h->cfg.numCars; c++) a.cars[c].controls = controls_from(controls[c]);
+    for (int t = 0; t < nticks; t++) arena_tick(a, h->cfg, h->ms, h->tb, 0);
+}
+// Gym::Reset on one arena using whatever state the arena currently holds (no state setter)
+void hs_reset_from_current(void* p, int arena, float* obs) {
+    HostSim* h = (HostSim*)p;
+    ArenaS& a = h->arenas[arena];
+    episode_reset(a, h->cfg);
+    build_obs(a, h->cfg, h->tb, obs);
+}
+void hs_reset(void* p, int arena, float* obs) {
+    HostSim* h = (HostSim*)p;
+    ArenaS& a = h->arenas[arena];
+    gym_reset(a, h->cfg);
+    build_obs(a, h->cfg, h->tb, obs);
+}
+// Gym::Step WITHOUT the auto-reset so that obs of terminal steps can be compared too
+void hs_step(void* p, int arena, const int32_t* actions, float* obs, float* reward, uint8_t* done) {
+    HostSim* h = (HostSim*)p;
+    ArenaS& a = h->arenas[arena];
+    parse_actions(a, h->cfg, h->tb, actions);
+    arena_tick(a, h->cfg, h->ms, h->tb, 1);
+    event_tracker_update(a, h->cfg);
+    snapshot_update(a, h->cfg);
+    build_obs(a, h->cfg, h->tb, obs);
+    bool d = compute_done(a, h->cfg);
+    compute_rewards(a, h->cfg, reward);
+    *done = d;
+    for (int t = 1; t < h->cfg.tickSkip; t++) arena_tick(a, h->cfg, h->ms, h->tb, 0);
+}
+void hs_gym_state(void* p, int arena, int32_t* score2, int32_t* lastTouch, int32_t* counters /*[P*8] player order*/, uint8_t* touched) {
+    HostSim* h = (HostSim*)p;
+    ArenaS& a = h->arenas[arena];
+    score2[0] = a.scoreLine[0]; score2[1] = a.scoreLine[1]; *lastTouch = a.lastTouchCarId;
+    for (int i = 0; i < h->cfg.numCars; i++) {
+        const CarS& c = a.cars[h->cfg.playerOrder[i]];
+        int32_t* o = counters + i * 8;
+        o[0] = c.matchGoals; o[1] = c.matchSaves; o[2] = c.matchAssists; o[3] = c.matchShots;
+        o[4] = c.matchShotPasses; o[5] = c.matchBumps; o[6] = c.matchDemos; o[7] = c.boostPickups;
+        touched[i] = c.touchedStep;
+    }
+}
+int hs_action_table(float* t) { return host_build_action_table(t); }
+int hs_mesh_info(void* p, int32_t* out /*numTris,numNodes,numHdrs*/) {
+    HostSim* h = (HostSim*)p;
+    out[0] = h->ms.numTris; out[1] = h->ms.numNodes; out[2] = h->ms.numHdrs;
+    return h->ms.numMeshes;
+}
+size_t hs_sizeof_arena() { return sizeof(ArenaS); }
+
+}  // extern "C"
