@@ -204,10 +204,29 @@ int rlg_engine_player_order(const rlg_engine* e, int32_t* car_ids_host);
 /* DiscreteAction table, 90x8 f32 (G/Utils/ActionParsers/DiscreteAction.cpp:3-67). */
 int rlg_action_table(float* table_host);
 
-/* Stand-alone fused obs/reward/done evaluation on injected states: computes what
- * Match::BuildObservations/IsDone/GetRewards (G/Envs/Match.cpp:12-38) would for
- * the current arena states WITHOUT stepping physics. prev_actions: DEVICE [A*P,8]. */
-int rlg_engine_eval_gym(rlg_engine* e, const float* prev_actions, void* stream);
+/* Gym::Reset WITHOUT the state setter: Match::EpisodeReset + obs for whatever state the masked
+ * arenas currently hold (after rlg_engine_set_state). This is how a host/custom StateSetter
+ * plugs in (StateSetter::ResetState(Arena*), G/Utils/StateSetters/StateSetter.h:9) and how the
+ * parity tests obtain obs for injected states (G/Envs/Match.cpp:4-23). */
+int rlg_engine_reset_current(rlg_engine* e, const uint8_t* mask_host, void* stream);
+
+/* Match::BuildObservations / IsDone / GetRewards (G/Envs/Match.cpp:12-38) on the CURRENT arena states, i.e.
+ * Gym::Step (G/Gym.cpp:84-93) minus the physics ticks and the event tracker: prevActions := table[action_idx]
+ * (zeroed for demoed players), GameState::UpdateFromArena, obs, done, rewards -> outputs. action_idx: DEVICE [A*P]. */
+int rlg_engine_eval_gym(rlg_engine* e, const int32_t* action_idx, void* stream);
+
+/* Gym::Step without GameInst's auto-reset: finished arenas keep their terminal state and obs. */
+int rlg_engine_step_noreset(rlg_engine* e, const int32_t* action_idx, void* stream);
+
+/* Sets players[i] -> car id (a permutation of 1..P). Default: descending id, which is what the
+ * reference's unordered_set<Car*> yields for 1v1; tests read the order back from the oracle. */
+int rlg_engine_set_player_order(rlg_engine* e, const int32_t* car_ids_host);
+
+int rlg_engine_num_arenas(const rlg_engine* e);
+size_t rlg_engine_state_bytes_per_arena(const rlg_engine* e); /* S(P) of SURVEY.md §8d as laid out here */
+/* D2H copy of the current outputs (any pointer may be NULL); synchronises the engine stream. */
+int rlg_engine_read_outputs(rlg_engine* e, float* obs_host, float* reward_host, uint8_t* done_host);
+void* rlg_engine_stream(rlg_engine* e); /* the engine's own cudaStream_t */
 
 /* Host-buffer convenience used by the C++ shim / bench e2e: copies action_idx
  * from host, steps, and copies obs/reward/done back into host buffers. */

@@ -274,6 +274,32 @@ void ref_arena_step(void* h, const rlg_controls* controls, int nticks) {
     a->Step(nticks);
 }
 
+// debug: contact points of the last tick (manifolds live until the next tick's broadphase pass).
+// out rows: [bodyA, bodyB, posA(3), posB(3), normal(3), dist, appliedImpulse, friction, restitution, lateralImpulse]
+// body codes: -1 static, 0 ball, car id otherwise.
+int ref_arena_dump_contacts(void* h, float* out, int maxRows) {
+    Arena* a = (Arena*)h;
+    auto code = [&](const btCollisionObject* o) -> float {
+        if (o->getUserIndex() == BT_USERINFO_TYPE_BALL) return 0.f;
+        if (o->getUserIndex() == BT_USERINFO_TYPE_CAR) return (float)((Car*)o->getUserPointer())->id;
+        return -1.f;
+    };
+    int n = 0;
+    auto* disp = a->_bulletWorld.getDispatcher();
+    for (int i = 0; i < disp->getNumManifolds(); i++) {
+        btPersistentManifold* m = disp->getManifoldByIndexInternal(i);
+        for (int j = 0; j < m->getNumContacts() && n < maxRows; j++) {
+            const btManifoldPoint& p = m->getContactPoint(j);
+            float* r = out + n * 16;
+            r[0] = code(m->getBody0()); r[1] = code(m->getBody1());
+            for (int k = 0; k < 3; k++) { r[2 + k] = p.m_positionWorldOnA[k]; r[5 + k] = p.m_positionWorldOnB[k]; r[8 + k] = p.m_normalWorldOnB[k]; }
+            r[11] = p.m_distance1; r[12] = p.m_appliedImpulse; r[13] = p.m_combinedFriction; r[14] = p.m_combinedRestitution; r[15] = p.m_appliedImpulseLateral1;
+            n++;
+        }
+    }
+    return n;
+}
+
 // iteration order of Arena::_cars (the player order of every gym-level vector)
 void ref_arena_player_order(void* h, int32_t* ids) {
     int k = 0;
@@ -311,6 +337,24 @@ int ref_gym_step(void* h, const int32_t* actions, float* obs_out, float* rew_out
     int w = flatten_obs(r.obs, obs_out);
     for (size_t i = 0; i < r.reward.size(); i++) rew_out[i] = r.reward[i];
     *done_out = r.done;
+    return w;
+}
+
+// Gym::Step (Gym.cpp:68-102) minus arena->Step and eventTracker.Update: evaluates the plugins on the arena's CURRENT state.
+int ref_gym_eval_current(void* h, const int32_t* actions, float* obs_out, float* rew_out, uint8_t* done_out) {
+    RefGym* g = (RefGym*)h;
+    IList acts(actions, actions + g->match->playerAmount);
+    ActionSet parsed = g->match->ParseActions(acts, g->gym->prevState);
+    g->match->prevActions = parsed;
+    GameState state = g->gym->prevState;
+    state.UpdateFromArena(g->gym->arena);
+    FList2 obs = g->match->BuildObservations(state);
+    bool done = g->match->IsDone(state);
+    FList rewards = g->match->GetRewards(state, done);
+    g->gym->prevState = state;
+    int w = flatten_obs(obs, obs_out);
+    for (size_t i = 0; i < rewards.size(); i++) rew_out[i] = rewards[i];
+    *done_out = done;
     return w;
 }
 

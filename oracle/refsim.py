@@ -95,6 +95,11 @@ class RefArena:
             cp = controls.ctypes.data_as(C.c_void_p)
         self.L.ref_arena_step(self.h, cp, nticks)
 
+    def dump_contacts(self, max_rows=64):
+        out = np.zeros((max_rows, 16), dtype=np.float32)
+        n = self.L.ref_arena_dump_contacts(self.h, out.ctypes.data_as(C.c_void_p), max_rows)
+        return out[:n]
+
     def player_order(self):
         ids = np.zeros(self.num_cars, dtype=np.int32)
         self.L.ref_arena_player_order(self.h, ids.ctypes.data_as(C.c_void_p))
@@ -144,6 +149,15 @@ class RefGym:
         done = C.c_uint8(0)
         self.L.ref_gym_step(self.h, actions.ctypes.data_as(C.c_void_p), obs.ctypes.data_as(C.c_void_p),
                             rew.ctypes.data_as(C.c_void_p), C.byref(done))
+        return obs, rew, bool(done.value)
+
+    def eval_current(self, actions):
+        actions = np.ascontiguousarray(actions, dtype=np.int32)
+        obs = np.zeros((self.P, self.obs_size), dtype=np.float32)
+        rew = np.zeros(self.P, dtype=np.float32)
+        done = C.c_uint8(0)
+        self.L.ref_gym_eval_current(self.h, actions.ctypes.data_as(C.c_void_p), obs.ctypes.data_as(C.c_void_p),
+                                    rew.ctypes.data_as(C.c_void_p), C.byref(done))
         return obs, rew, bool(done.value)
 
     def last_state(self):

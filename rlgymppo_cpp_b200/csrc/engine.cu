@@ -1,0 +1,503 @@
+// engine.cu — the CUDA collection engine behind the C ABI of include/rlgym_b200.h.
+//
+// One thread steps one arena.  Arena state lives in HBM word-transposed
+// (word w of arena a at state[w * A + a]) so a warp's 32 arenas move as coalesced
+// 128-byte lines; a kernel loads the arena into thread-local storage, runs all ticks of
+// the step (tick_skip physics ticks + gym layer) and writes it back once: the
+// algorithmic HBM traffic per arena-step is read S + write S + actions + obs + rewards + done
+// (SURVEY.md §8d).  The collision meshes/BVH and the lookup tables are shared, read-only
+// and L2-resident.  There is no CPU fallback: every entry point that needs the device
+// returns RLG_ERR_CUDA when it is not usable.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "rl_convert.h"
+#include "rl_host_build.h"
+#include "rl_tick.h"
+
+using namespace rl;
+
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+#define CK(expr)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) return fail(RLG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+struct rlg_engine {
+    rlg_engine_cfg cfgIn;
+    SimCfg cfg;
+    int device;
+    int nwords;
+    cudaStream_t stream;
+    uint32_t* state = nullptr;
+    Tables* tables = nullptr;
+    MeshSet ms;  // device pointers
+    void* meshMem[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool meshesLoaded = false;
+    float* obs = nullptr;
+    float* reward = nullptr;
+    uint8_t* done = nullptr;
+    int32_t* actions = nullptr;  // device staging for step_host
+    // pinned host staging
+    int32_t* hActions = nullptr;
+    float* hObs = nullptr;
+    float* hReward = nullptr;
+    uint8_t* hDone = nullptr;
+    uint64_t launches = 0;
+};
+
+// ---- state movement -----------------------------------------------------------------------------
+__device__ __forceinline__ void load_arena(ArenaS& s, const uint32_t* __restrict__ buf, int A, int a, int nwords) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(&s);
+#pragma unroll 4
+    for (int i = 0; i < nwords; i++) w[i] = buf[(size_t)i * A + a];
+}
+__device__ __forceinline__ void store_arena(const ArenaS& s, uint32_t* __restrict__ buf, int A, int a, int nwords) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&s);
+#pragma unroll 4
+    for (int i = 0; i < nwords; i++) buf[(size_t)i * A + a] = w[i];
+}
+
+// ---- kernels --------------------------------------------------------------------------------------
+__global__ void k_init(uint32_t* state, SimCfg cfg, int nwords, uint64_t seed, uint64_t base) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= cfg.numArenas) return;
+    ArenaS s;
+    arena_init(s, cfg.numCars, seed, base + (uint64_t)a);
+    store_arena(s, state, cfg.numArenas, a, nwords);
+}
+
+// Gym::Reset on masked arenas (mask == nullptr: all). useSetter = 0 adopts the current arena state.
+__global__ void k_reset(uint32_t* state, SimCfg cfg, int nwords, const Tables* __restrict__ tb, const uint8_t* __restrict__ mask,
+                        int useSetter, float* __restrict__ obs) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= cfg.numArenas) return;
+    if (mask && !mask[a]) return;
+    ArenaS s;
+    load_arena(s, state, cfg.numArenas, a, nwords);
+    if (useSetter) gym_reset(s, cfg); else episode_reset(s, cfg);
+    build_obs(s, cfg, *tb, obs + (size_t)a * cfg.numCars * cfg.obsSize);
+    store_arena(s, state, cfg.numArenas, a, nwords);
+}
+
+__global__ void k_set_state(uint32_t* state, SimCfg cfg, int nwords, const int32_t* __restrict__ ids, int n,
+                            const rlg_car_state* __restrict__ cars, const rlg_ball_state* __restrict__ balls,
+                            const rlg_pad_state* __restrict__ pads, const int64_t* __restrict__ ticks) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int a = ids[i];
+    ArenaS s;
+    load_arena(s, state, cfg.numArenas, a, nwords);
+    if (cars) for (int c = 0; c < cfg.numCars; c++) car_from_pod(s.cars[c], cars[(size_t)i * cfg.numCars + c]);
+    if (balls) ball_from_pod(s.ball, balls[i]);
+    if (pads) for (int p = 0; p < kNumPads; p++) {
+        const rlg_pad_state& ps = pads[(size_t)i * kNumPads + p];
+        s.pads[p].isActive = ps.is_active != 0; s.pads[p].cooldown = ps.cooldown; s.pads[p].prevLockedCarId = ps.prev_locked_car_id;
+    }
+    if (ticks && ticks[i] >= 0) set_i64(s.tickLo, s.tickHi, ticks[i]);
+    store_arena(s, state, cfg.numArenas, a, nwords);
+}
+
+__global__ void k_get_state(const uint32_t* state, SimCfg cfg, int nwords, const int32_t* __restrict__ ids, int n,
+                            rlg_car_state* __restrict__ cars, rlg_ball_state* __restrict__ balls, rlg_pad_state* __restrict__ pads,
+                            int64_t* __restrict__ ticks) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int a = ids[i];
+    ArenaS s;
+    load_arena(s, state, cfg.numArenas, a, nwords);
+    if (cars) for (int c = 0; c < cfg.numCars; c++) {
+        rlg_car_state o;
+        memset(&o, 0, sizeof(o));
+        car_to_pod(o, s.cars[c], c, cfg.spawnOpponents);
+        cars[(size_t)i * cfg.numCars + c] = o;
+    }
+    if (balls) { rlg_ball_state o; ball_to_pod(o, s.ball); balls[i] = o; }
+    if (pads) for (int p = 0; p < kNumPads; p++) {
+        rlg_pad_state o; o.is_active = s.pads[p].isActive; o.cooldown = s.pads[p].cooldown; o.prev_locked_car_id = s.pads[p].prevLockedCarId;
+        pads[(size_t)i * kNumPads + p] = o;
+    }
+    if (ticks) ticks[i] = get_i64(s.tickLo, s.tickHi);
+}
+
+// Arena::Step(nticks) with explicit controls
+__global__ void __launch_bounds__(64) k_tick(uint32_t* state, SimCfg cfg, int nwords, MeshSet ms, const Tables* __restrict__ tb,
+                                             const rlg_controls* __restrict__ controls, int nticks) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= cfg.numArenas) return;
+    ArenaS s;
+    load_arena(s, state, cfg.numArenas, a, nwords);
+    if (controls) for (int c = 0; c < cfg.numCars; c++) s.cars[c].controls = controls_from(controls[(size_t)a * cfg.numCars + c]);
+    for (int t = 0; t < nticks; t++) arena_tick(s, cfg, ms, *tb, 0);
+    store_arena(s, state, cfg.numArenas, a, nwords);
+}
+
+// Gym::Step + GameInst::Step auto-reset, fused: all tick_skip ticks + obs/reward/done in one launch
+__global__ void __launch_bounds__(64) k_step(uint32_t* state, SimCfg cfg, int nwords, MeshSet ms, const Tables* __restrict__ tb,
+                                             const int32_t* __restrict__ actions, float* __restrict__ obs, float* __restrict__ reward,
+                                             uint8_t* __restrict__ done, int autoReset) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= cfg.numArenas) return;
+    ArenaS s;
+    load_arena(s, state, cfg.numArenas, a, nwords);
+    int32_t act[kMaxCars];
+    for (int p = 0; p < cfg.numCars; p++) {
+        int v = actions[(size_t)a * cfg.numCars + p];
+        act[p] = v < 0 ? 0 : (v >= RLG_NUM_ACTIONS ? RLG_NUM_ACTIONS - 1 : v);
+    }
+    float* o = obs + (size_t)a * cfg.numCars * cfg.obsSize;
+    parse_actions(s, cfg, *tb, act);
+    arena_tick(s, cfg, ms, *tb, 1);
+    event_tracker_update(s, cfg);
+    snapshot_update(s, cfg);
+    build_obs(s, cfg, *tb, o);
+    bool d = compute_done(s, cfg);
+    compute_rewards(s, cfg, reward + (size_t)a * cfg.numCars);
+    done[a] = d ? 1 : 0;
+    for (int t = 1; t < cfg.tickSkip; t++) arena_tick(s, cfg, ms, *tb, 0);
+    if (d && autoReset) {
+        gym_reset(s, cfg);
+        build_obs(s, cfg, *tb, o);
+    }
+    store_arena(s, state, cfg.numArenas, a, nwords);
+}
+
+// Match::BuildObservations / IsDone / GetRewards on the CURRENT arena state (Gym::Step minus the physics and the
+// event tracker): used to prove the gym layer bit-exact on states injected from the reference.
+__global__ void k_eval(uint32_t* state, SimCfg cfg, int nwords, const Tables* __restrict__ tb, const int32_t* __restrict__ actions,
+                       float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= cfg.numArenas) return;
+    ArenaS s;
+    load_arena(s, state, cfg.numArenas, a, nwords);
+    int32_t act[kMaxCars];
+    for (int p = 0; p < cfg.numCars; p++) {
+        int v = actions[(size_t)a * cfg.numCars + p];
+        act[p] = v < 0 ? 0 : (v >= RLG_NUM_ACTIONS ? RLG_NUM_ACTIONS - 1 : v);
+    }
+    parse_actions(s, cfg, *tb, act);
+    snapshot_update(s, cfg);
+    build_obs(s, cfg, *tb, obs + (size_t)a * cfg.numCars * cfg.obsSize);
+    bool d = compute_done(s, cfg);
+    compute_rewards(s, cfg, reward + (size_t)a * cfg.numCars);
+    done[a] = d ? 1 : 0;
+    store_arena(s, state, cfg.numArenas, a, nwords);
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+static inline int grid_for(int n, int block) { return (n + block - 1) / block; }
+
+extern "C" {
+
+const char* rlg_last_error(void) { return g_last_error.c_str(); }
+int rlg_abi_version(void) { return 1; }
+size_t rlg_sizeof_car_state(void) { return sizeof(rlg_car_state); }
+size_t rlg_sizeof_engine_cfg(void) { return sizeof(rlg_engine_cfg); }
+
+void rlg_engine_cfg_default(rlg_engine_cfg* c) {
+    memset(c, 0, sizeof(*c));
+    c->num_arenas = 256; c->team_size = 1; c->spawn_opponents = 1; c->tick_skip = 8; c->device = 0; c->seed = 123;
+    c->obs_kind = RLG_OBS_DEFAULT; c->obs_max_players = 3;
+    c->num_reward_terms = 4;
+    c->reward_terms[0].kind = RLG_REW_FACE_BALL; c->reward_terms[0].weight = 0.1f;
+    c->reward_terms[1].kind = RLG_REW_VEL_PLAYER_TO_BALL; c->reward_terms[1].weight = 0.5f;
+    c->reward_terms[2].kind = RLG_REW_VEL_BALL_TO_GOAL; c->reward_terms[2].weight = 1.0f;
+    c->reward_terms[3].kind = RLG_REW_EVENT; c->reward_terms[3].weight = 50.f;
+    c->reward_terms[3].params[1] = 1.f; c->reward_terms[3].params[2] = -1.f;
+    c->opponent_scale = 1.f;
+    c->no_touch_max_steps = 150; c->goal_score_terminal = 1;
+    c->state_setter = RLG_SETTER_RANDOM; c->rand_ball_speed = c->rand_car_speed = c->cars_on_ground = 1;
+}
+
+int rlg_action_table(float* table_host) {
+    if (!table_host) return fail(RLG_ERR_INVALID, "null table");
+    host_build_action_table(table_host);
+    return RLG_OK;
+}
+
+int rlg_engine_destroy(rlg_engine* e) {
+    if (!e) return RLG_OK;
+    cudaSetDevice(e->device);
+    cudaFree(e->state); cudaFree(e->tables); cudaFree(e->obs); cudaFree(e->reward); cudaFree(e->done); cudaFree(e->actions);
+    for (void* p : e->meshMem) cudaFree(p);
+    cudaFreeHost(e->hActions); cudaFreeHost(e->hObs); cudaFreeHost(e->hReward); cudaFreeHost(e->hDone);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return RLG_OK;
+}
+
+int rlg_engine_create(const rlg_engine_cfg* cfg, rlg_engine** out) {
+    if (!cfg || !out) return fail(RLG_ERR_INVALID, "null argument");
+    *out = nullptr;
+    rlg_engine* e = new (std::nothrow) rlg_engine();
+    if (!e) return fail(RLG_ERR_INVALID, "out of host memory");
+    try {
+        host_build_simcfg(*cfg, e->cfg);
+    } catch (std::exception& ex) {
+        delete e;
+        return fail(RLG_ERR_INVALID, ex.what());
+    }
+    e->cfgIn = *cfg;
+    e->device = cfg->device;
+    int ndev = 0;
+    cudaError_t err = cudaGetDeviceCount(&ndev);
+    if (err != cudaSuccess || ndev <= 0) { delete e; return fail(RLG_ERR_CUDA, "no CUDA device available: the engine has no CPU fallback"); }
+    if (cfg->device < 0 || cfg->device >= ndev) { delete e; return fail(RLG_ERR_INVALID, "bad device ordinal"); }
+#define CKD(expr)                                                                                       \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) { std::string m = std::string(#expr) + ": " + cudaGetErrorString(_e); rlg_engine_destroy(e); return fail(RLG_ERR_CUDA, m); } \
+    } while (0)
+    CKD(cudaSetDevice(e->device));
+    CKD(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    const int A = e->cfg.numArenas, P = e->cfg.numCars;
+    e->nwords = arena_words(P);
+    CKD(cudaMalloc(&e->state, (size_t)e->nwords * A * 4));
+    CKD(cudaMalloc(&e->tables, sizeof(Tables)));
+    CKD(cudaMalloc(&e->obs, (size_t)A * P * e->cfg.obsSize * 4));
+    CKD(cudaMalloc(&e->reward, (size_t)A * P * 4));
+    CKD(cudaMalloc(&e->done, (size_t)A));
+    CKD(cudaMalloc(&e->actions, (size_t)A * P * 4));
+    CKD(cudaMallocHost(&e->hActions, (size_t)A * P * 4));
+    CKD(cudaMallocHost(&e->hObs, (size_t)A * P * e->cfg.obsSize * 4));
+    CKD(cudaMallocHost(&e->hReward, (size_t)A * P * 4));
+    CKD(cudaMallocHost(&e->hDone, (size_t)A));
+    Tables tb;
+    try { host_build_tables(tb); } catch (std::exception& ex) { rlg_engine_destroy(e); return fail(RLG_ERR_INVALID, ex.what()); }
+    CKD(cudaMemcpyAsync(e->tables, &tb, sizeof(tb), cudaMemcpyHostToDevice, e->stream));
+    CKD(cudaMemsetAsync(e->obs, 0, (size_t)A * P * e->cfg.obsSize * 4, e->stream));
+    CKD(cudaMemsetAsync(e->reward, 0, (size_t)A * P * 4, e->stream));
+    CKD(cudaMemsetAsync(e->done, 0, (size_t)A, e->stream));
+    k_init<<<grid_for(A, 128), 128, 0, e->stream>>>(e->state, e->cfg, e->nwords, cfg->seed, (uint64_t)cfg->arena_id_base);
+    e->launches++;
+    CKD(cudaGetLastError());
+    CKD(cudaStreamSynchronize(e->stream));
+    memset(&e->ms, 0, sizeof(e->ms));
+    *out = e;
+    return RLG_OK;
+}
+
+int rlg_engine_load_meshes(rlg_engine* e, const void* const* blobs, const size_t* sizes, int n) {
+    if (!e || (n > 0 && (!blobs || !sizes))) return fail(RLG_ERR_INVALID, "null argument");
+    HostMeshSet hm;
+    try { host_build_meshes(blobs, sizes, n, hm); } catch (std::exception& ex) { return fail(RLG_ERR_INVALID, ex.what()); }
+    CK(cudaSetDevice(e->device));
+    for (void*& p : e->meshMem) { cudaFree(p); p = nullptr; }
+    MeshSet ms = hm.meta;
+    auto up = [&](int slot, const void* src, size_t bytes, const void** dst) -> cudaError_t {
+        if (bytes == 0) { *dst = nullptr; return cudaSuccess; }
+        cudaError_t r = cudaMalloc(&e->meshMem[slot], bytes);
+        if (r != cudaSuccess) return r;
+        *dst = e->meshMem[slot];
+        return cudaMemcpyAsync(e->meshMem[slot], src, bytes, cudaMemcpyHostToDevice, e->stream);
+    };
+    CK(up(0, hm.nodes.data(), hm.nodes.size() * sizeof(BvhNode), (const void**)&ms.nodes));
+    CK(up(1, hm.tris.data(), hm.tris.size() * sizeof(Tri), (const void**)&ms.tris));
+    CK(up(2, hm.hdrRoot.data(), hm.hdrRoot.size() * 4, (const void**)&ms.hdrRoot));
+    CK(up(3, hm.hdrSize.data(), hm.hdrSize.size() * 4, (const void**)&ms.hdrSize));
+    CK(up(4, hm.triFlags.data(), hm.triFlags.size() * 4, (const void**)&ms.triFlags));
+    CK(up(5, hm.triEdgeAngles.data(), hm.triEdgeAngles.size() * 4, (const void**)&ms.triEdgeAngles));
+    CK(cudaStreamSynchronize(e->stream));
+    e->ms = ms;
+    e->meshesLoaded = true;
+    return RLG_OK;
+}
+
+static cudaStream_t pick(rlg_engine* e, void* stream) { return stream ? (cudaStream_t)stream : e->stream; }
+
+static int do_reset(rlg_engine* e, const uint8_t* mask_host, void* stream, int useSetter) {
+    if (!e) return fail(RLG_ERR_INVALID, "null engine");
+    if (!e->meshesLoaded) return fail(RLG_ERR_STATE, "rlg_engine_load_meshes must be called first (RocketSim::Init)");
+    if (useSetter && e->cfg.stateSetter == RLG_SETTER_HOST) return fail(RLG_ERR_STATE, "host state setter: use rlg_engine_set_state + rlg_engine_reset_current");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t s = pick(e, stream);
+    uint8_t* dmask = nullptr;
+    if (mask_host) {
+        CK(cudaMallocAsync(&dmask, e->cfg.numArenas, s));
+        CK(cudaMemcpyAsync(dmask, mask_host, e->cfg.numArenas, cudaMemcpyHostToDevice, s));
+    }
+    k_reset<<<grid_for(e->cfg.numArenas, 64), 64, 0, s>>>(e->state, e->cfg, e->nwords, e->tables, dmask, useSetter, e->obs);
+    e->launches++;
+    CK(cudaGetLastError());
+    if (dmask) CK(cudaFreeAsync(dmask, s));
+    return RLG_OK;
+}
+int rlg_engine_reset(rlg_engine* e, const uint8_t* mask_host, void* stream) { return do_reset(e, mask_host, stream, 1); }
+int rlg_engine_reset_current(rlg_engine* e, const uint8_t* mask_host, void* stream) { return do_reset(e, mask_host, stream, 0); }
+
+int rlg_engine_set_player_order(rlg_engine* e, const int32_t* car_ids_host) {
+    if (!e || !car_ids_host) return fail(RLG_ERR_INVALID, "null argument");
+    int seen = 0;
+    for (int i = 0; i < e->cfg.numCars; i++) {
+        int id = car_ids_host[i];
+        if (id < 1 || id > e->cfg.numCars || (seen & (1 << id))) return fail(RLG_ERR_INVALID, "player order must be a permutation of car ids 1..P");
+        seen |= 1 << id;
+    }
+    for (int i = 0; i < e->cfg.numCars; i++) e->cfg.playerOrder[i] = car_ids_host[i] - 1;
+    return RLG_OK;
+}
+int rlg_engine_player_order(const rlg_engine* e, int32_t* car_ids_host) {
+    if (!e || !car_ids_host) return fail(RLG_ERR_INVALID, "null argument");
+    for (int i = 0; i < e->cfg.numCars; i++) car_ids_host[i] = e->cfg.playerOrder[i] + 1;
+    return RLG_OK;
+}
+
+int rlg_engine_set_state(rlg_engine* e, const int32_t* ids, int n, const rlg_car_state* cars, const rlg_ball_state* balls,
+                         const rlg_pad_state* pads, const int64_t* ticks) {
+    if (!e || !ids || n < 0) return fail(RLG_ERR_INVALID, "bad argument");
+    if (n == 0) return RLG_OK;
+    for (int i = 0; i < n; i++) if (ids[i] < 0 || ids[i] >= e->cfg.numArenas) return fail(RLG_ERR_INVALID, "arena id out of range");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t s = e->stream;
+    const int P = e->cfg.numCars;
+    int32_t* dIds = nullptr; rlg_car_state* dCars = nullptr; rlg_ball_state* dBalls = nullptr; rlg_pad_state* dPads = nullptr; int64_t* dTicks = nullptr;
+    CK(cudaMallocAsync(&dIds, (size_t)n * 4, s));
+    CK(cudaMemcpyAsync(dIds, ids, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    if (cars) { CK(cudaMallocAsync(&dCars, (size_t)n * P * sizeof(rlg_car_state), s)); CK(cudaMemcpyAsync(dCars, cars, (size_t)n * P * sizeof(rlg_car_state), cudaMemcpyHostToDevice, s)); }
+    if (balls) { CK(cudaMallocAsync(&dBalls, (size_t)n * sizeof(rlg_ball_state), s)); CK(cudaMemcpyAsync(dBalls, balls, (size_t)n * sizeof(rlg_ball_state), cudaMemcpyHostToDevice, s)); }
+    if (pads) { CK(cudaMallocAsync(&dPads, (size_t)n * kNumPads * sizeof(rlg_pad_state), s)); CK(cudaMemcpyAsync(dPads, pads, (size_t)n * kNumPads * sizeof(rlg_pad_state), cudaMemcpyHostToDevice, s)); }
+    if (ticks) { CK(cudaMallocAsync(&dTicks, (size_t)n * 8, s)); CK(cudaMemcpyAsync(dTicks, ticks, (size_t)n * 8, cudaMemcpyHostToDevice, s)); }
+    k_set_state<<<grid_for(n, 64), 64, 0, s>>>(e->state, e->cfg, e->nwords, dIds, n, dCars, dBalls, dPads, dTicks);
+    e->launches++;
+    CK(cudaGetLastError());
+    CK(cudaFreeAsync(dIds, s));
+    if (dCars) CK(cudaFreeAsync(dCars, s));
+    if (dBalls) CK(cudaFreeAsync(dBalls, s));
+    if (dPads) CK(cudaFreeAsync(dPads, s));
+    if (dTicks) CK(cudaFreeAsync(dTicks, s));
+    CK(cudaStreamSynchronize(s));
+    return RLG_OK;
+}
+
+int rlg_engine_get_state(rlg_engine* e, const int32_t* ids, int n, rlg_car_state* cars, rlg_ball_state* balls, rlg_pad_state* pads,
+                         int64_t* ticks) {
+    if (!e || !ids || n < 0) return fail(RLG_ERR_INVALID, "bad argument");
+    if (n == 0) return RLG_OK;
+    for (int i = 0; i < n; i++) if (ids[i] < 0 || ids[i] >= e->cfg.numArenas) return fail(RLG_ERR_INVALID, "arena id out of range");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t s = e->stream;
+    const int P = e->cfg.numCars;
+    int32_t* dIds = nullptr; rlg_car_state* dCars = nullptr; rlg_ball_state* dBalls = nullptr; rlg_pad_state* dPads = nullptr; int64_t* dTicks = nullptr;
+    CK(cudaMallocAsync(&dIds, (size_t)n * 4, s));
+    CK(cudaMemcpyAsync(dIds, ids, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    if (cars) CK(cudaMallocAsync(&dCars, (size_t)n * P * sizeof(rlg_car_state), s));
+    if (balls) CK(cudaMallocAsync(&dBalls, (size_t)n * sizeof(rlg_ball_state), s));
+    if (pads) CK(cudaMallocAsync(&dPads, (size_t)n * kNumPads * sizeof(rlg_pad_state), s));
+    if (ticks) CK(cudaMallocAsync(&dTicks, (size_t)n * 8, s));
+    k_get_state<<<grid_for(n, 64), 64, 0, s>>>(e->state, e->cfg, e->nwords, dIds, n, dCars, dBalls, dPads, dTicks);
+    e->launches++;
+    CK(cudaGetLastError());
+    if (cars) CK(cudaMemcpyAsync(cars, dCars, (size_t)n * P * sizeof(rlg_car_state), cudaMemcpyDeviceToHost, s));
+    if (balls) CK(cudaMemcpyAsync(balls, dBalls, (size_t)n * sizeof(rlg_ball_state), cudaMemcpyDeviceToHost, s));
+    if (pads) CK(cudaMemcpyAsync(pads, dPads, (size_t)n * kNumPads * sizeof(rlg_pad_state), cudaMemcpyDeviceToHost, s));
+    if (ticks) CK(cudaMemcpyAsync(ticks, dTicks, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaFreeAsync(dIds, s));
+    if (dCars) CK(cudaFreeAsync(dCars, s));
+    if (dBalls) CK(cudaFreeAsync(dBalls, s));
+    if (dPads) CK(cudaFreeAsync(dPads, s));
+    if (dTicks) CK(cudaFreeAsync(dTicks, s));
+    CK(cudaStreamSynchronize(s));
+    return RLG_OK;
+}
+
+int rlg_engine_tick(rlg_engine* e, const rlg_controls* controls, int nticks, void* stream) {
+    if (!e || nticks < 0) return fail(RLG_ERR_INVALID, "bad argument");
+    if (!e->meshesLoaded) return fail(RLG_ERR_STATE, "rlg_engine_load_meshes must be called first (RocketSim::Init)");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t s = pick(e, stream);
+    k_tick<<<grid_for(e->cfg.numArenas, 64), 64, 0, s>>>(e->state, e->cfg, e->nwords, e->ms, e->tables, controls, nticks);
+    e->launches++;
+    CK(cudaGetLastError());
+    return RLG_OK;
+}
+
+static int do_step(rlg_engine* e, const int32_t* action_idx, cudaStream_t s, int autoReset) {
+    k_step<<<grid_for(e->cfg.numArenas, 64), 64, 0, s>>>(e->state, e->cfg, e->nwords, e->ms, e->tables, action_idx, e->obs, e->reward, e->done, autoReset);
+    e->launches++;
+    CK(cudaGetLastError());
+    return RLG_OK;
+}
+
+int rlg_engine_step(rlg_engine* e, const int32_t* action_idx, void* stream) {
+    if (!e || !action_idx) return fail(RLG_ERR_INVALID, "null argument");
+    if (!e->meshesLoaded) return fail(RLG_ERR_STATE, "rlg_engine_load_meshes must be called first (RocketSim::Init)");
+    CK(cudaSetDevice(e->device));
+    return do_step(e, action_idx, pick(e, stream), 1);
+}
+int rlg_engine_step_noreset(rlg_engine* e, const int32_t* action_idx, void* stream) {
+    if (!e || !action_idx) return fail(RLG_ERR_INVALID, "null argument");
+    if (!e->meshesLoaded) return fail(RLG_ERR_STATE, "rlg_engine_load_meshes must be called first (RocketSim::Init)");
+    CK(cudaSetDevice(e->device));
+    return do_step(e, action_idx, pick(e, stream), 0);
+}
+
+int rlg_engine_eval_gym(rlg_engine* e, const int32_t* action_idx, void* stream) {
+    if (!e || !action_idx) return fail(RLG_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t s = pick(e, stream);
+    k_eval<<<grid_for(e->cfg.numArenas, 64), 64, 0, s>>>(e->state, e->cfg, e->nwords, e->tables, action_idx, e->obs, e->reward, e->done);
+    e->launches++;
+    CK(cudaGetLastError());
+    return RLG_OK;
+}
+
+int rlg_engine_outputs(rlg_engine* e, float** obs, float** reward, uint8_t** done) {
+    if (!e) return fail(RLG_ERR_INVALID, "null engine");
+    if (obs) *obs = e->obs;
+    if (reward) *reward = e->reward;
+    if (done) *done = e->done;
+    return RLG_OK;
+}
+int rlg_engine_obs_size(const rlg_engine* e) { return e ? e->cfg.obsSize : 0; }
+int rlg_engine_num_players(const rlg_engine* e) { return e ? e->cfg.numCars : 0; }
+int rlg_engine_num_arenas(const rlg_engine* e) { return e ? e->cfg.numArenas : 0; }
+size_t rlg_engine_state_bytes_per_arena(const rlg_engine* e) { return e ? (size_t)e->nwords * 4 : 0; }
+
+int rlg_engine_read_outputs(rlg_engine* e, float* obs_host, float* reward_host, uint8_t* done_host) {
+    if (!e) return fail(RLG_ERR_INVALID, "null engine");
+    CK(cudaSetDevice(e->device));
+    const int A = e->cfg.numArenas, P = e->cfg.numCars;
+    if (obs_host) CK(cudaMemcpyAsync(obs_host, e->obs, (size_t)A * P * e->cfg.obsSize * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (reward_host) CK(cudaMemcpyAsync(reward_host, e->reward, (size_t)A * P * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (done_host) CK(cudaMemcpyAsync(done_host, e->done, (size_t)A, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return RLG_OK;
+}
+
+int rlg_engine_step_host(rlg_engine* e, const int32_t* action_idx_host, float* obs_host, float* reward_host, uint8_t* done_host) {
+    if (!e || !action_idx_host) return fail(RLG_ERR_INVALID, "null argument");
+    if (!e->meshesLoaded) return fail(RLG_ERR_STATE, "rlg_engine_load_meshes must be called first (RocketSim::Init)");
+    CK(cudaSetDevice(e->device));
+    const int A = e->cfg.numArenas, P = e->cfg.numCars;
+    cudaStream_t s = e->stream;
+    memcpy(e->hActions, action_idx_host, (size_t)A * P * 4);
+    CK(cudaMemcpyAsync(e->actions, e->hActions, (size_t)A * P * 4, cudaMemcpyHostToDevice, s));
+    int rc = do_step(e, e->actions, s, 1);
+    if (rc != RLG_OK) return rc;
+    if (obs_host) CK(cudaMemcpyAsync(e->hObs, e->obs, (size_t)A * P * e->cfg.obsSize * 4, cudaMemcpyDeviceToHost, s));
+    if (reward_host) CK(cudaMemcpyAsync(e->hReward, e->reward, (size_t)A * P * 4, cudaMemcpyDeviceToHost, s));
+    if (done_host) CK(cudaMemcpyAsync(e->hDone, e->done, (size_t)A, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (obs_host) memcpy(obs_host, e->hObs, (size_t)A * P * e->cfg.obsSize * 4);
+    if (reward_host) memcpy(reward_host, e->hReward, (size_t)A * P * 4);
+    if (done_host) memcpy(done_host, e->hDone, (size_t)A);
+    return RLG_OK;
+}
+
+uint64_t rlg_engine_launch_count(const rlg_engine* e) { return e ? e->launches : 0; }
+void* rlg_engine_stream(rlg_engine* e) { return e ? (void*)e->stream : nullptr; }
+int rlg_engine_sync(rlg_engine* e) {
+    if (!e) return fail(RLG_ERR_INVALID, "null engine");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    return RLG_OK;
+}
+
+}  // extern "C"

@@ -28,7 +28,9 @@ struct TickW {
 
 // constants derived the way Car::_BulletSetup derives them (Car.cpp:195-283)
 struct CarConsts {
-    V3 halfExt;      // full half extents (Bullet units)
+    V3 halfExt;      // half extents WITH margin (btBoxShape::getHalfExtentsWithMargin), Bullet units
+    V3 coreHalf;     // m_implicitShapeDimensions = requested half extents - 0.04
+    float boxMargin; // collision margin after setSafeMargin: 0.1 * smallest half extent (< 0.04 for every preset)
     V3 hitboxOffset; // child transform origin
     V3 invInertiaLocal;
     float invMass;
@@ -39,7 +41,15 @@ struct CarConsts {
 
 RL_HDI CarConsts car_consts() {
     CarConsts k;
-    k.halfExt = V3((C::HITBOX_X * UU2BT) / 2, (C::HITBOX_Y * UU2BT) / 2, (C::HITBOX_Z * UU2BT) / 2);
+    // btBoxShape ctor (B/BulletCollision/CollisionShapes/btBoxShape.cpp:18-28): implicit dims = half - 0.04, then
+    // setSafeMargin lowers ONLY the margin to 0.1 * min half extent (setMargin is not virtual in this fork), so
+    // the effective box is 0.04 - margin smaller than the configured hitbox on every side.
+    V3 req((C::HITBOX_X * UU2BT) / 2, (C::HITBOX_Y * UU2BT) / 2, (C::HITBOX_Z * UU2BT) / 2);
+    k.coreHalf = req - V3(C::BOX_MARGIN, C::BOX_MARGIN, C::BOX_MARGIN);
+    float minDim = fminf_(fminf_(req.x, req.y), req.z);
+    float safe = 0.1f * minDim;
+    k.boxMargin = safe < C::BOX_MARGIN ? safe : C::BOX_MARGIN;
+    k.halfExt = k.coreHalf + V3(k.boxMargin, k.boxMargin, k.boxMargin);
     k.hitboxOffset = V3(C::HITBOX_OFF_X * UU2BT, C::HITBOX_OFF_Y * UU2BT, C::HITBOX_OFF_Z * UU2BT);
     // btBoxShape::calculateLocalInertia
     float lx = 2.f * k.halfExt.x, ly = 2.f * k.halfExt.y, lz = 2.f * k.halfExt.z;

@@ -72,6 +72,7 @@ struct CollideCtx {
     TickW* tw;
     const CarConsts* k;
     int64_t tick;
+    int32_t noResponse[kMaxCars];  // DISABLE_SIMULATION | CF_NO_CONTACT_RESPONSE for this tick: demoed when the tick started (Car.cpp:69-87)
     int32_t firstTickOfStep;  // bump counters only stick when the callback fires during Gym::Step's first tick (see rl_tick.h)
 };
 
@@ -186,8 +187,8 @@ RL_HD inline void manifold_add(CollideCtx& x, Manifold& m, V3 normalOnB, V3 poin
     Contact& p = m.pt[idx];
     // gContactAddedCallback; demoed cars have no contact response -> returns before anything
     bool aCar = m.a >= 1, bCar = m.b >= 1;
-    if (aCar && x.a->cars[m.a - 1].isDemoed) return;
-    if (bCar && x.a->cars[m.b - 1].isDemoed) return;
+    if (aCar && x.noResponse[m.a - 1]) return;
+    if (bCar && x.noResponse[m.b - 1]) return;
     if (aCar && m.b == 0) on_car_ball(x, m.a - 1, p);
     else if (aCar && bCar) on_car_car(x, m.a - 1, m.b - 1, p);
     else if (aCar && m.b == -1) on_car_world(x, m.a - 1, p);
@@ -374,7 +375,7 @@ RL_HD inline void box_meshes(CollideCtx& x, ContactSet& cs, const MeshSet& ms, i
                             };
                             if (!tri_early_out(t, breaking, sup)) {
                                 V3 normal, pointOnB; float dist;
-                                if (box_triangle_contact(boxCenter, c.rot, k.halfExt, t, breaking, normal, pointOnB, dist))
+                                if (box_triangle_contact(boxCenter, c.rot, k.halfExt, k.coreHalf, k.boxMargin, t, breaking, normal, pointOnB, dist))
                                     manifold_add(x, m, normal, pointOnB, dist, &ms, nd.tri);
                             }
                         }
@@ -396,7 +397,7 @@ RL_HD inline void car_ball(CollideCtx& x, ContactSet& cs, int ci, float breaking
     float radius = C::BALL_RADIUS * UU2BT;
     V3 boxCenter = c.pos + c.rot * k.hitboxOffset;
     V3 normal, pointOnB; float dist;
-    if (box_sphere_contact(boxCenter, c.rot, k.halfExt, x.a->ball.pos, radius, breaking, normal, pointOnB, dist)) {
+    if (box_sphere_contact(boxCenter, c.rot, k.halfExt, k.coreHalf, k.boxMargin, x.a->ball.pos, radius, breaking, normal, pointOnB, dist)) {
         Manifold m; m.a = 1 + ci; m.b = 0; m.n = 0; m.breaking = breaking;
         manifold_add(x, m, normal, pointOnB, dist, nullptr, -1);
         manifold_flush(cs, m);

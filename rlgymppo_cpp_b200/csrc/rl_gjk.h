@@ -243,10 +243,8 @@ RL_HD inline bool gjk_box_core(V3 boxCenter, const M3& rot, V3 coreHalf, V3 orig
 // ---- box vs sphere (car hitbox vs ball) ---------------------------------------------------------
 // A = box (margin 0.04), B = sphere (point core, margin = radius).  GJK between a box core and a point
 // converges to the closest point on the core; written in closed form.
-RL_HD inline bool box_sphere_contact(V3 boxCenter, const M3& rot, V3 halfExt, V3 sphereCenter, float radius, float breaking,
+RL_HD inline bool box_sphere_contact(V3 boxCenter, const M3& rot, V3 halfExt, V3 core, float marginA, V3 sphereCenter, float radius, float breaking,
                                      V3& normalOnB, V3& pointOnB, float& dist) {
-    const float marginA = C::BOX_MARGIN;
-    V3 core = halfExt - V3(marginA, marginA, marginA);
     V3 l = tmul(sphereCenter - boxCenter, rot);
     V3 q(clampf(l.x, -core.x, core.x), clampf(l.y, -core.y, core.y), clampf(l.z, -core.z, core.z));
     V3 d = q - l;  // from sphere centre (B) to box core (A)
@@ -333,10 +331,8 @@ RL_HD inline bool box_triangle_sat(V3 boxCenter, const M3& rot, V3 halfExt, cons
     return true;
 }
 
-RL_HD inline bool box_triangle_contact(V3 boxCenter, const M3& rot, V3 halfExt, const Tri& t, float breaking,
+RL_HD inline bool box_triangle_contact(V3 boxCenter, const M3& rot, V3 halfExt, V3 core, float marginA, const Tri& t, float breaking,
                                        V3& normalOnB, V3& pointOnB, float& dist) {
-    const float marginA = C::BOX_MARGIN;
-    V3 core = halfExt - V3(marginA, marginA, marginA);
     float maxDist = marginA + 0.f + breaking;
     auto supB = [&](V3 axis) {  // btTriangleShape::localGetSupportingVertexWithoutMargin(axis * basisB), basisB = I
         float d0 = dot(axis, t.v0), d1 = dot(axis, t.v1), d2 = dot(axis, t.v2);

@@ -95,6 +95,90 @@ struct BvhBuilder {
 };
 }  // namespace detail
 
+// btGenerateInternalEdgeInfo / btConnectivityProcessor (B/BulletCollision/CollisionDispatch/btInternalEdgeUtility.cpp:52-352):
+// for every triangle A, every triangle B of the same mesh overlapping A's AABB and sharing exactly two vertices
+// contributes the signed dihedral angle of the shared edge + convex / swap flags.
+inline void host_build_edge_info(HostMeshSet& out) {
+    const MeshSet& ms = out.meta;
+    const float equalVertexThreshold = 0.0001f * 0.0001f, planarEpsilon = 0.0001f;
+    const float PI = 3.1415926535897932384626433832795029f;
+    auto quatRot = [](V3 axis, float angle, V3 v) {
+        float d = len(axis); float s = sinf(angle * 0.5f) / d;
+        Quat q(axis.x * s, axis.y * s, axis.z * s, cosf(angle * 0.5f));
+        Quat t(q.w * v.x + q.y * v.z - q.z * v.y, q.w * v.y + q.z * v.x - q.x * v.z, q.w * v.z + q.x * v.y - q.y * v.x, -q.x * v.x - q.y * v.y - q.z * v.z);
+        Quat r = t * Quat(-q.x, -q.y, -q.z, q.w);
+        return V3(r.x, r.y, r.z);
+    };
+    for (int m = 0; m < ms.numMeshes; m++) {
+        int nodeEnd = ms.nodeStart[m] + ms.nodeCount[m];
+        // triangles of this mesh = leaves of its BVH
+        std::vector<int> tris;
+        for (int i = ms.nodeStart[m]; i < nodeEnd; i++) if (out.nodes[i].tri >= 0) tris.push_back(out.nodes[i].tri);
+        for (int ta : tris) {
+            const Tri& A = out.tris[ta];
+            V3 va[3] = {A.v0, A.v1, A.v2};
+            V3 amn = vmin(vmin(A.v0, A.v1), A.v2), amx = vmax(vmax(A.v0, A.v1), A.v2);
+            int i = ms.nodeStart[m];
+            while (i < nodeEnd) {
+                const BvhNode& nd = out.nodes[i];
+                float mn[3] = {nd.mn[0] - 0.01f, nd.mn[1] - 0.01f, nd.mn[2] - 0.01f}, mx[3] = {nd.mx[0] + 0.01f, nd.mx[1] + 0.01f, nd.mx[2] + 0.01f};
+                bool ov = aabb_overlap(mn, mx, amn, amx);
+                if (nd.tri < 0) { i += ov ? 1 : nd.escape; continue; }
+                i++;
+                if (!ov || nd.tri == ta) continue;
+                const Tri& B = out.tris[nd.tri];
+                V3 vb[3] = {B.v0, B.v1, B.v2};
+                if (len2(cross(vb[1] - vb[0], vb[2] - vb[0])) < equalVertexThreshold) continue;
+                if (len2(cross(va[1] - va[0], va[2] - va[0])) < equalVertexThreshold) continue;
+                int numshared = 0, sa[3] = {-1, -1, -1}, sbv[3] = {-1, -1, -1};
+                bool degenerate = false;
+                for (int p = 0; p < 3 && !degenerate; p++) {
+                    for (int q = 0; q < 3; q++) {
+                        if (len2(va[p] - vb[q]) < equalVertexThreshold) {
+                            sa[numshared] = p; sbv[numshared] = q; numshared++;
+                            if (numshared >= 3) { degenerate = true; break; }
+                        }
+                    }
+                }
+                if (degenerate || numshared != 2) continue;
+                if (sa[0] == 0 && sa[1] == 2) { sa[0] = 2; sa[1] = 0; int t = sbv[1]; sbv[1] = sbv[0]; sbv[0] = t; }
+                int sumvertsA = sa[0] + sa[1];
+                int otherIndexA = 3 - sumvertsA;
+                V3 edge = normalized(va[sa[1]] - va[sa[0]]);
+                int otherIndexB = 3 - (sbv[0] + sbv[1]);
+                V3 tb0 = vb[sbv[1]], tb1 = vb[sbv[0]], tb2 = vb[otherIndexB];
+                V3 normalA = normalized(cross(va[1] - va[0], va[2] - va[0]));
+                V3 normalB = normalized(cross(tb1 - tb0, tb2 - tb0));
+                V3 edgeCrossA = normalized(cross(edge, normalA));
+                if (dot(edgeCrossA, va[otherIndexA] - va[sa[0]]) < 0) edgeCrossA = edgeCrossA * -1.f;
+                V3 edgeCrossB = normalized(cross(edge, normalB));
+                if (dot(edgeCrossB, vb[otherIndexB] - vb[sbv[0]]) < 0) edgeCrossB = edgeCrossB * -1.f;
+                float angle2 = 0, ang4 = 0, correctedAngle = 0;
+                bool isConvex = false;
+                V3 calculatedEdge = cross(edgeCrossA, edgeCrossB);
+                if (len2(calculatedEdge) < planarEpsilon) {
+                    angle2 = 0; ang4 = 0;
+                } else {
+                    calculatedEdge = normalized(calculatedEdge);
+                    V3 calculatedNormalA = normalized(cross(calculatedEdge, edgeCrossA));
+                    angle2 = atan2f(dot(edgeCrossB, calculatedNormalA), dot(edgeCrossB, edgeCrossA));
+                    ang4 = PI - angle2;
+                    isConvex = dot(normalA, edgeCrossB) < 0.f;
+                    correctedAngle = isConvex ? ang4 : -ang4;
+                }
+                int e; V3 eAxis;
+                if (sumvertsA == 1) { e = 0; eAxis = va[0] - va[1]; }
+                else if (sumvertsA == 2) { e = 2; eAxis = va[2] - va[0]; }
+                else { e = 1; eAxis = va[1] - va[2]; }
+                V3 computedNormalB = quatRot(eAxis, -correctedAngle, normalA);
+                if (dot(computedNormalB, normalB) < 0) out.triFlags[ta] |= (8 << e);
+                out.triEdgeAngles[ta * 3 + e] = -correctedAngle;
+                if (isConvex) out.triFlags[ta] |= (1 << e);
+            }
+        }
+    }
+}
+
 inline void host_build_meshes(const void* const* blobs, const size_t* sizes, int n, HostMeshSet& out) {
     if (n > kMaxMeshes) throw std::runtime_error("too many collision meshes");
     out = HostMeshSet();
@@ -113,6 +197,8 @@ inline void host_build_meshes(const void* const* blobs, const size_t* sizes, int
         const float* vtx = (const float*)(b + 8 + (size_t)nt * 12);
         int triBase = (int)out.tris.size();
         detail::BvhBuilder bb(out.nodes, out.hdrRoot, out.hdrSize);
+        std::vector<Tri> local;
+        V3 meshMn(1e30f, 1e30f, 1e30f), meshMx(-1e30f, -1e30f, -1e30f);
         for (int t = 0; t < nt; t++) {
             Tri tr;
             V3* vs[3] = {&tr.v0, &tr.v1, &tr.v2};
@@ -120,12 +206,38 @@ inline void host_build_meshes(const void* const* blobs, const size_t* sizes, int
                 int vi = idx[t * 3 + k];
                 if (vi < 0 || vi >= nv) throw std::runtime_error("bad triangle vertex index in collision mesh");
                 *vs[k] = V3(vtx[vi * 3 + 0], vtx[vi * 3 + 1], vtx[vi * 3 + 2]);
+                meshMn = vmin(meshMn, *vs[k]); meshMx = vmax(meshMx, *vs[k]);
             }
+            local.push_back(tr);
+        }
+        // btQuantizedBvh::setQuantizationValues(meshAabb, margin 1.0) + quantize/unQuantize of the leaf boxes: the
+        // reference sorts leaves by the centres of the QUANTISED boxes, which decides ties on regular meshes.
+        V3 qMin, qMax, qScale;
+        auto quant = [&](V3 p, int isMax, unsigned short* o) {
+            V3 v = (p - qMin) * qScale;
+            for (int a = 0; a < 3; a++) o[a] = isMax ? (unsigned short)(((unsigned short)(v[a] + 1.f)) | 1) : (unsigned short)(((unsigned short)(v[a])) & 0xfffe);
+        };
+        auto unquant = [&](const unsigned short* q) { return V3((float)q[0] / qScale.x, (float)q[1] / qScale.y, (float)q[2] / qScale.z) + qMin; };
+        {
+            V3 clampV(1.f, 1.f, 1.f);
+            qMin = meshMn - clampV; qMax = meshMx + clampV;
+            V3 sz = qMax - qMin; qScale = V3(65533.f / sz.x, 65533.f / sz.y, 65533.f / sz.z);
+            unsigned short q[3];
+            quant(qMin, 0, q); qMin = vmin(qMin, unquant(q) - clampV);
+            sz = qMax - qMin; qScale = V3(65533.f / sz.x, 65533.f / sz.y, 65533.f / sz.z);
+            quant(qMax, 1, q); qMax = vmax(qMax, unquant(q) + clampV);
+            sz = qMax - qMin; qScale = V3(65533.f / sz.x, 65533.f / sz.y, 65533.f / sz.z);
+        }
+        for (int t = 0; t < nt; t++) {
+            const Tri& tr = local[t];
             out.tris.push_back(tr);
             detail::Leaf l;
             l.mn = vmin(vmin(tr.v0, tr.v1), tr.v2); l.mx = vmax(vmax(tr.v0, tr.v1), tr.v2);
             const float MIN_DIM = 0.002f, MIN_HALF = 0.001f;  // btOptimizedBvh.cpp NodeTriangleCallback
             for (int a = 0; a < 3; a++) if (l.mx[a] - l.mn[a] < MIN_DIM) { l.mx[a] = l.mx[a] + MIN_HALF; l.mn[a] = l.mn[a] - MIN_HALF; }
+            unsigned short q0[3], q1[3];
+            quant(l.mn, 0, q0); quant(l.mx, 1, q1);
+            l.mn = unquant(q0); l.mx = unquant(q1);
             l.tri = triBase + t;
             bb.leaves.push_back(l);
         }
@@ -141,7 +253,8 @@ inline void host_build_meshes(const void* const* blobs, const size_t* sizes, int
     ms.hdrStart[n] = (int)out.hdrRoot.size();
     ms.numTris = (int)out.tris.size(); ms.numNodes = (int)out.nodes.size(); ms.numHdrs = (int)out.hdrRoot.size();
     out.triFlags.assign(out.tris.size(), 0);
-    out.triEdgeAngles.assign(out.tris.size() * 3, 6.283185307179586f);
+    out.triEdgeAngles.assign(out.tris.size() * 3, 6.283185307179586232f);
+    host_build_edge_info(out);
 }
 
 // DiscreteAction table (G/Utils/ActionParsers/DiscreteAction.cpp:3-67)

@@ -188,9 +188,10 @@ RL_HD inline void solve_arena(SolverBody* sb, int numBodies, ContactSet& cs) {
 
     for (int ci = 0; ci < cs.n; ci++) {
         const Contact& cp = cs.c[ci];
-        int ia = (cp.a >= 0 && sb[cp.a].active) ? cp.a : -1;
-        int ib = (cp.b >= 0 && sb[cp.b].active) ? cp.b : -1;
-        if (ia < 0 && ib < 0) continue;  // both "static": no response (sleeping ball / demoed car)
+        // a body without contact response (demoed car) or in a sleeping island (frozen ball) takes its manifolds out of
+        // the solver entirely (btCollisionDispatcher::needsResponse / island filtering); it is NOT a static obstacle
+        if ((cp.a >= 0 && !sb[cp.a].active) || (cp.b >= 0 && !sb[cp.b].active)) continue;
+        int ia = cp.a, ib = cp.b;
         if (nRows >= kMaxRows - (1 + kMaxCars)) break;
         V3 rel1 = cp.posA - (cp.a >= 0 ? sb[cp.a].pos : V3());
         V3 rel2 = cp.posB - (cp.b >= 0 ? sb[cp.b].pos : V3());

@@ -74,6 +74,10 @@ RL_HD inline void pads_post_tick(ArenaS& a, const int32_t* locked) {
     }
 }
 
+#ifdef RL_DEBUG_CONTACTS
+static ContactSet g_dbg_contacts;
+#endif
+
 // ---- one physics tick -----------------------------------------------------------------------------
 RL_HD RL_NOINLINE void arena_tick(ArenaS& a, const SimCfg& cfg, const MeshSet& ms, const Tables& tb, int firstTickOfStep) {
     const float dt = kTickTime;
@@ -87,6 +91,10 @@ RL_HD RL_NOINLINE void arena_tick(ArenaS& a, const SimCfg& cfg, const MeshSet& m
     // ball zero-velocity sleeping (Arena.cpp:721-727)
     bool ballActive = !(len2(a.ball.vel) == 0.f && len2(a.ball.angvel) == 0.f);
 
+    // activation state / contact response are decided at the top of Car::_PreTickUpdate, before a possible respawn,
+    // and a car demolished DURING this tick still responds and integrates until the next tick (Car.cpp:38-41,69-87)
+    int32_t noResponse[kMaxCars];
+    for (int c = 0; c < P; c++) noResponse[c] = a.cars[c].isDemoed;
     for (int p = 0; p < P; p++) { int ci = cfg.playerOrder[p]; car_pre_tick(a, cfg, ms, k, ci, tw.cars[ci]); }
     if (P > 0) pads_pre_tick(a);
 
@@ -94,17 +102,22 @@ RL_HD RL_NOINLINE void arena_tick(ArenaS& a, const SimCfg& cfg, const MeshSet& m
     // applyGravity on active bodies
     const V3 g(0.f * UU2BT, 0.f * UU2BT, C::GRAVITY_Z * UU2BT);
     if (ballActive) tw.ballForce += g * C::BALL_MASS;
-    for (int c = 0; c < P; c++) if (!a.cars[c].isDemoed) tw.cars[c].force += g * C::CAR_MASS;
+    for (int c = 0; c < P; c++) if (!noResponse[c]) tw.cars[c].force += g * C::CAR_MASS;
     // predictUnconstraintMotion: damping (ball only: linear 0.03)
     a.ball.vel = a.ball.vel * cfg.ballDampFactor;
 
     // collision detection, in the reference's pair order (btRSBroadphase::calculateOverlappingPairs)
     ContactSet cs; cs.n = 0; cs.overflow = 0;
     CollideCtx cx; cx.a = &a; cx.cfg = &cfg; cx.tw = &tw; cx.k = &k; cx.tick = tick; cx.firstTickOfStep = firstTickOfStep;
+    for (int c = 0; c < kMaxCars; c++) cx.noResponse[c] = c < P ? noResponse[c] : 1;
     float ballR = C::BALL_RADIUS * UU2BT;
     float ballAabb = ballR + 0.08f;
-    sphere_meshes(cx, cs, ms, a.ball.pos, ballR, thr.ball);
-    for (int p = 0; p < 4; p++) sphere_plane(cx, cs, a.ball.pos, ballR, p, thr.ball);
+    // a sleeping ball vs the (always "sleeping") static bodies is skipped by btCollisionDispatcher::needsCollision
+    // (both inactive): on the tick it is woken by a car it has no world contacts yet.
+    if (ballActive) {
+        sphere_meshes(cx, cs, ms, a.ball.pos, ballR, thr.ball);
+        for (int p = 0; p < 4; p++) sphere_plane(cx, cs, a.ball.pos, ballR, p, thr.ball);
+    }
     bool ballWoken = false;
     V3 bmn = a.ball.pos - V3(ballAabb, ballAabb, ballAabb), bmx = a.ball.pos + V3(ballAabb, ballAabb, ballAabb);
     V3 cmn[kMaxCars], cmx[kMaxCars];
@@ -120,8 +133,8 @@ RL_HD RL_NOINLINE void arena_tick(ArenaS& a, const SimCfg& cfg, const MeshSet& m
     float thrCarBall = fminf_(thr.ball, thr.car);
     for (int c = 0; c < P; c++) {
         if (!overlap(bmn, bmx, cmn[c], cmx[c])) continue;
-        if (!a.cars[c].isDemoed) ballWoken = true;  // islands merge on broadphase overlap
-        if (!ballActive && a.cars[c].isDemoed) continue;
+        if (!noResponse[c]) ballWoken = true;  // islands merge on broadphase overlap
+        if (!ballActive && noResponse[c]) continue;
         car_ball(cx, cs, c, thrCarBall);
     }
     for (int c = 0; c < P; c++) {
@@ -133,6 +146,9 @@ RL_HD RL_NOINLINE void arena_tick(ArenaS& a, const SimCfg& cfg, const MeshSet& m
         }
     }
 
+#ifdef RL_DEBUG_CONTACTS
+    g_dbg_contacts = cs;
+#endif
     // ---- solve ----
     SolverBody sb[1 + kMaxCars];
     {
@@ -157,7 +173,7 @@ RL_HD RL_NOINLINE void arena_tick(ArenaS& a, const SimCfg& cfg, const MeshSet& m
         b.extForceImp = tw.cars[c].force * b.invMass * dt;
         b.extTorqueImp = tmul(tw.cars[c].torque, b.invInertiaWorld) * dt;
         b.dLin = b.dAng = b.push = b.turn = V3();
-        b.active = !car.isDemoed;
+        b.active = !noResponse[c];
     }
     solve_arena(sb, 1 + P, cs);
 

@@ -1,0 +1,268 @@
+"""Generates the golden fixtures under tests/golden/ from the UNMODIFIED reference (oracle/_ref).
+
+Run in the dev container (needs /root/reference to have been compiled by `make -C oracle ref`):
+
+    python tests/golden/make_golden.py
+
+Outputs (committed):
+  tick_<name>.npz   reference Arena::Step trajectories: full car/ball/pad state after every tick +
+                    the controls applied, per scenario class (free flight, ground drive, jump/flip,
+                    ball bounces, ball-mesh, car-ball, kickoff, pads, car-world, random play, car-car).
+  gym_<name>.npz    Gym-layer sequences: injected arena states + action indices -> obs / reward / done
+                    as Match::BuildObservations / GetRewards / IsDone compute them, per config.
+  action_table.npy  the 90x8 DiscreteAction table.
+The reference has no golden vectors of its own; these ARE the reference's outputs.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from oracle import refsim  # noqa: E402
+from rlgymppo_cpp_b200 import abi  # noqa: E402
+from parity_tools import make_controls, yaw_rot  # noqa: E402
+
+
+def record(arena, cars, ball, pads, controls_fn, nticks):
+    arena.set_state(cars, ball, pads, 0)
+    P = arena.num_cars
+    C = np.zeros((nticks + 1, P), dtype=abi.CAR_DTYPE)
+    B = np.zeros(nticks + 1, dtype=abi.BALL_DTYPE)
+    Pd = np.zeros((nticks + 1, abi.RLG_NUM_PADS), dtype=abi.PAD_DTYPE)
+    T = np.zeros(nticks + 1, dtype=np.int64)
+    U = np.zeros((nticks, P), dtype=abi.CONTROLS_DTYPE)
+    c, b, p, t = arena.get_state()
+    C[0], B[0], Pd[0], T[0] = c, b[0], p, t
+    for i in range(nticks):
+        u = controls_fn(i)
+        U[i] = u
+        arena.step(u, 1)
+        c, b, p, t = arena.get_state()
+        C[i + 1], B[i + 1], Pd[i + 1], T[i + 1] = c, b[0], p, t
+    return dict(cars=C, ball=B, pads=Pd, tick=T, controls=U)
+
+
+def base(P=2):
+    cars = abi.new_cars(P)
+    ball = abi.new_balls(1)
+    pads = abi.new_pads(abi.RLG_NUM_PADS)
+    spots = [(3000, -2000), (-3000, 2000), (3000, 2000), (-3000, -2000), (0, -3000), (0, 3000)]
+    for i in range(P):
+        cars["pos"][i] = (spots[i][0], spots[i][1], 17)
+    return cars, ball, pads
+
+
+def scenarios_1v1(arena):
+    out = {}
+    z = make_controls(2)
+    # free flight with air control
+    cars, ball, pads = base()
+    cars["pos"][0] = (0, -1000, 800); cars["pos"][1] = (500, 1000, 1200)
+    cars["vel"][0] = (300, 500, 200); cars["ang_vel"][0] = (1, 2, -1.5)
+    cars["vel"][1] = (-300, 100, -200); cars["ang_vel"][1] = (0.5, -2, 3)
+    cars["is_on_ground"] = 0
+    yaw_rot(cars, 0, 0.3, 0.2, 0.1); yaw_rot(cars, 1, -2.0, -0.5, 1.0)
+    ball["pos"][0] = (100, 200, 900); ball["vel"][0] = (800, -300, 400); ball["ang_vel"][0] = (1, 2, 3)
+    u = make_controls(2, throttle=1, pitch=0.5, yaw=-1, roll=1, boost=1)
+    out["free_flight"] = record(arena, cars, ball, pads, lambda t: u, 60)
+    # ground drive
+    cars, ball, pads = base()
+    cars["pos"][0] = (0, -2000, 17); cars["pos"][1] = (1000, 2000, 17); yaw_rot(cars, 0, 1.0); yaw_rot(cars, 1, -2.0)
+    u1 = make_controls(2, throttle=1, steer=0.5)
+    out["ground_drive"] = record(arena, cars, ball, pads, lambda t: u1, 120)
+    u2 = make_controls(2, throttle=1, steer=-1, boost=1, handbrake=1)
+    out["ground_powerslide"] = record(arena, cars, ball, pads, lambda t: u2, 120)
+
+    def jumpctl(t):
+        c = make_controls(2, throttle=1)
+        c["jump"] = 1 if (t < 10 or (30 <= t < 32)) else 0
+        c["pitch"] = -1 if t >= 30 else 0
+        return c
+    out["jump_flip"] = record(arena, cars, ball, pads, jumpctl, 150)
+
+    def djctl(t):
+        c = make_controls(2)
+        c["jump"] = 1 if (t < 4 or (20 <= t < 22)) else 0
+        c["yaw"] = 1 if t > 40 else 0
+        c["roll"] = -1 if t > 60 else 0
+        return c
+    out["double_jump_air_roll"] = record(arena, cars, ball, pads, djctl, 120)
+    # ball alone
+    cars, ball, pads = base()
+    ball["pos"][0] = (0, 0, 500); ball["vel"][0] = (500, 300, -200); ball["ang_vel"][0] = (2, 1, 0)
+    out["ball_bounce_floor"] = record(arena, cars, ball, pads, lambda t: z, 400)
+    cars, ball, pads = base()
+    ball["pos"][0] = (3500, 0, 800); ball["vel"][0] = (2000, 300, 100)
+    out["ball_side_wall"] = record(arena, cars, ball, pads, lambda t: z, 200)
+    cars, ball, pads = base()
+    ball["pos"][0] = (2000, 4500, 800); ball["vel"][0] = (100, 2500, 100); ball["ang_vel"][0] = (1, 0, 0)
+    out["ball_back_wall_mesh"] = record(arena, cars, ball, pads, lambda t: z, 200)
+    cars, ball, pads = base()
+    ball["pos"][0] = (3000, 4000, 500); ball["vel"][0] = (1500, 1500, 0); ball["ang_vel"][0] = (0, 0, 2)
+    out["ball_corner_mesh"] = record(arena, cars, ball, pads, lambda t: z, 200)
+    cars, ball, pads = base()
+    ball["pos"][0] = (200, 4500, 300); ball["vel"][0] = (50, 3000, 100)
+    out["ball_into_goal"] = record(arena, cars, ball, pads, lambda t: z, 200)
+    cars, ball, pads = base()
+    ball["pos"][0] = (3300, 3000, 93.15); ball["vel"][0] = (800, 900, 0)
+    out["ball_roll_ramp"] = record(arena, cars, ball, pads, lambda t: z, 300)
+    # car-ball
+    cars, ball, pads = base()
+    cars["pos"][0] = (0, -1000, 17); yaw_rot(cars, 0, np.pi / 2); cars["vel"][0] = (0, 1000, 0)
+    ball["pos"][0] = (30, 0, 93.15)
+    ub = make_controls(2, throttle=1, boost=1)
+    out["car_hits_ball"] = record(arena, cars, ball, pads, lambda t: ub, 200)
+    cars, ball, pads = base()
+    cars["pos"][0] = (-2048, -2560, 17); yaw_rot(cars, 0, np.pi / 4)
+    cars["pos"][1] = (2048, 2560, 17); yaw_rot(cars, 1, np.pi / 4 + np.pi)
+    out["kickoff"] = record(arena, cars, ball, pads, lambda t: ub, 300)
+    cars, ball, pads = base()
+    cars["pos"][0] = (0, 0, 600); yaw_rot(cars, 0, 0.5, 0.8, 1.5); cars["vel"][0] = (300, 0, -800); cars["is_on_ground"] = 0
+    out["car_lands_tumbling_hits_ball"] = record(arena, cars, ball, pads, lambda t: z, 200)
+    # pads
+    cars, ball, pads = base()
+    cars["pos"][0] = (-3584, -1000, 17); yaw_rot(cars, 0, np.pi / 2); cars["boost"][0] = 10
+    cars["pos"][1] = (0, 1500, 17); yaw_rot(cars, 1, -np.pi / 2); cars["boost"][1] = 0
+    ut = make_controls(2, throttle=1)
+    out["boost_pads"] = record(arena, cars, ball, pads, lambda t: ut, 400)
+    # car-world
+    cars, ball, pads = base()
+    cars["pos"][0] = (3000, 0, 17); yaw_rot(cars, 0, 0.0); cars["vel"][0] = (1500, 0, 0)
+    out["car_up_side_ramp"] = record(arena, cars, ball, pads, lambda t: ut, 200)
+    cars, ball, pads = base()
+    cars["pos"][0] = (0, 4000, 17); yaw_rot(cars, 0, np.pi / 2); cars["vel"][0] = (0, 1200, 0)
+    out["car_into_goal"] = record(arena, cars, ball, pads, lambda t: ut, 250)
+    # car-car
+    cars, ball, pads = base()
+    cars["pos"][0] = (0, -800, 17); yaw_rot(cars, 0, np.pi / 2); cars["vel"][0] = (0, 1000, 0)
+    cars["pos"][1] = (10, 800, 17); yaw_rot(cars, 1, -np.pi / 2); cars["vel"][1] = (0, -1000, 0)
+    ball["pos"][0] = (2000, 0, 93.15)
+    out["car_car_head_on"] = record(arena, cars, ball, pads, lambda t: ut, 150)
+    cars, ball, pads = base()
+    cars["pos"][0] = (0, -2500, 17); yaw_rot(cars, 0, np.pi / 2); cars["vel"][0] = (0, 2250, 0); cars["boost"][0] = 100
+    cars["pos"][1] = (0, 500, 17); yaw_rot(cars, 1, 0.0)
+    ball["pos"][0] = (2000, 0, 93.15)
+
+    def demo_ctl(t):
+        c = make_controls(2)
+        c["throttle"][0] = 1; c["boost"][0] = 1
+        return c
+    out["car_car_demo"] = record(arena, cars, ball, pads, demo_ctl, 500)
+    return out
+
+
+def random_play(team, nsteps, seed):
+    """Random DiscreteAction play from RandomState resets: the workload distribution of the benchmark."""
+    cfg = abi.default_cfg(num_arenas=1, team_size=team)
+    g = refsim.RefGym(cfg)
+    refsim.seed(seed)
+    rng = np.random.default_rng(seed)
+    table = refsim.action_table()
+    P = 2 * team
+    arena = refsim.RefArena(team, True)
+    chunks = []
+    for ep in range(nsteps):
+        g.reset()
+        cars, ball, pads, _ = g.arena.get_state()
+        ctl_seq = []
+        for s in range(12):
+            acts = rng.integers(0, 90, size=P)
+            u = np.zeros(P, dtype=abi.CONTROLS_DTYPE)
+            for i in range(P):
+                a = table[acts[i]]
+                u[i] = (a[0], a[1], a[2], a[3], a[4], int(a[5] == 1), int(a[6] == 1), int(a[7] == 1))
+            ctl_seq += [u] * 8
+        chunks.append(record(arena, cars, ball[0:1], pads, lambda t: ctl_seq[t], len(ctl_seq)))
+    return chunks
+
+
+def gym_sequence(cfg, nepisodes, nsteps, seed):
+    """Injected states + actions -> obs/reward/done via the reference plugins (ref_gym_eval_current)."""
+    g = refsim.RefGym(cfg)
+    team = cfg.team_size
+    P = g.P
+    phys = refsim.RefArena(team, bool(cfg.spawn_opponents))  # physics runs here so that Gym callbacks do not fire
+    refsim.seed(seed)
+    rng = np.random.default_rng(seed)
+    table = refsim.action_table()
+    order = g.arena.player_order()
+    recs = dict(cars=[], ball=[], pads=[], tick=[], actions=[], obs=[], reward=[], done=[], first=[])
+    for ep in range(nepisodes):
+        g.reset()
+        st = g.arena.get_state()
+        phys.set_state(*st)
+        st = phys.get_state()
+        g.arena.set_state(*st)
+        obs0 = g.reset_from_current()
+        recs["cars"].append(st[0]); recs["ball"].append(st[1][0]); recs["pads"].append(st[2]); recs["tick"].append(st[3])
+        recs["actions"].append(np.zeros(P, dtype=np.int32)); recs["obs"].append(obs0)
+        recs["reward"].append(np.zeros(P, dtype=np.float32)); recs["done"].append(0); recs["first"].append(1)
+        for s in range(nsteps):
+            acts = rng.integers(0, 90, size=P).astype(np.int32)
+            u = np.zeros(P, dtype=abi.CONTROLS_DTYPE)
+            for i in range(P):
+                a = table[acts[i]]
+                u[order[i] - 1] = (a[0], a[1], a[2], a[3], a[4], int(a[5] == 1), int(a[6] == 1), int(a[7] == 1))
+            phys.step(u, cfg.tick_skip)
+            st = phys.get_state()
+            g.arena.set_state(*st)
+            o, r, d = g.eval_current(acts)
+            recs["cars"].append(st[0]); recs["ball"].append(st[1][0]); recs["pads"].append(st[2]); recs["tick"].append(st[3])
+            recs["actions"].append(acts); recs["obs"].append(o); recs["reward"].append(r); recs["done"].append(int(d)); recs["first"].append(0)
+            if d:
+                break
+    out = {k: np.stack(v) if k not in ("tick", "done", "first") else np.asarray(v) for k, v in recs.items()}
+    out["player_order"] = np.asarray(order, dtype=np.int32)
+    return out
+
+
+def save(name, d):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **d)
+    print(name, {k: v.shape for k, v in d.items()}, os.path.getsize(path) // 1024, "KiB")
+
+
+def main():
+    arena = refsim.RefArena(1, True)
+    sc = scenarios_1v1(arena)
+    flat = {}
+    for name, d in sc.items():
+        for k, v in d.items():
+            flat[f"{name}/{k}"] = v
+    save("tick_scenarios_1v1", flat)
+    for team, n, seed in ((1, 6, 11), (2, 4, 12), (3, 3, 13)):
+        chunks = random_play(team, n, seed)
+        flat = {}
+        for i, d in enumerate(chunks):
+            for k, v in d.items():
+                flat[f"ep{i}/{k}"] = v
+        save(f"tick_random_{team}v{team}", flat)
+    np.save(os.path.join(HERE, "action_table.npy"), refsim.action_table())
+    # gym layer
+    cfg = abi.default_cfg(num_arenas=1, team_size=1)
+    for k in range(11):
+        cfg.reward_terms[3].params[k] = 0.1 * (k + 1)
+    save("gym_1v1_default", gym_sequence(cfg, 12, 40, 21))
+    cfg = abi.default_cfg(num_arenas=1, team_size=2)
+    cfg.zero_sum = 1; cfg.team_spirit = 0.3
+    cfg.num_reward_terms = 5
+    cfg.reward_terms[4].kind = abi.RLG_REW_VELOCITY; cfg.reward_terms[4].weight = 0.25
+    save("gym_2v2_zerosum", gym_sequence(cfg, 8, 40, 22))
+    cfg = abi.default_cfg(num_arenas=1, team_size=3)
+    cfg.obs_kind = abi.RLG_OBS_PADDED; cfg.obs_max_players = 3
+    save("gym_3v3_padded", gym_sequence(cfg, 5, 40, 23))
+    cfg = abi.default_cfg(num_arenas=1, team_size=2)
+    cfg.obs_kind = abi.RLG_OBS_PADDED; cfg.obs_max_players = 3
+    cfg.zero_sum = 1; cfg.team_spirit = 0.3
+    cfg.state_setter = abi.RLG_SETTER_KICKOFF
+    save("gym_2v2_padded_zerosum_kickoff", gym_sequence(cfg, 5, 40, 24))
+
+
+if __name__ == "__main__":
+    main()

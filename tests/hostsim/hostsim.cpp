@@ -4,6 +4,7 @@
 // that the CPU-only test suite (`pytest -m "not gpu"`, no GPU in the dev container) can check the
 // kernel logic against the reference oracle / golden vectors before the code ever reaches a B200.
 // The product path is rlgymppo_cpp_b200/csrc/engine.cu; it fails loudly without a CUDA device.
+#define RL_DEBUG_CONTACTS 1
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -108,6 +109,16 @@ void hs_step(void* p, int arena, const int32_t* actions, float* obs, float* rewa
     *done = d;
     for (int t = 1; t < h->cfg.tickSkip; t++) arena_tick(a, h->cfg, h->ms, h->tb, 0);
 }
+void hs_eval_gym(void* p, int arena, const int32_t* actions, float* obs, float* reward, uint8_t* done) {
+    HostSim* h = (HostSim*)p;
+    ArenaS& a = h->arenas[arena];
+    parse_actions(a, h->cfg, h->tb, actions);
+    snapshot_update(a, h->cfg);
+    build_obs(a, h->cfg, h->tb, obs);
+    bool d = compute_done(a, h->cfg);
+    compute_rewards(a, h->cfg, reward);
+    *done = d;
+}
 void hs_gym_state(void* p, int arena, int32_t* score2, int32_t* lastTouch, int32_t* counters /*[P*8] player order*/, uint8_t* touched) {
     HostSim* h = (HostSim*)p;
     ArenaS& a = h->arenas[arena];
@@ -125,6 +136,19 @@ int hs_mesh_info(void* p, int32_t* out /*numTris,numNodes,numHdrs*/) {
     HostSim* h = (HostSim*)p;
     out[0] = h->ms.numTris; out[1] = h->ms.numNodes; out[2] = h->ms.numHdrs;
     return h->ms.numMeshes;
+}
+// debug: contacts of the last tick; rows like ref_arena_dump_contacts (impulses not available -> 0)
+int hs_dump_contacts(float* out, int maxRows) {
+    int n = 0;
+    for (int i = 0; i < g_dbg_contacts.n && n < maxRows; i++) {
+        const Contact& c = g_dbg_contacts.c[i];
+        float* r = out + n * 16;
+        r[0] = c.a <= 0 ? (float)c.a : (float)c.a; r[1] = (float)c.b;
+        for (int k = 0; k < 3; k++) { r[2 + k] = c.posA[k]; r[5 + k] = c.posB[k]; r[8 + k] = c.normal[k]; }
+        r[11] = c.dist; r[12] = 0; r[13] = c.friction; r[14] = c.restitution; r[15] = (float)c.special;
+        n++;
+    }
+    return n;
 }
 size_t hs_sizeof_arena() { return sizeof(ArenaS); }
 

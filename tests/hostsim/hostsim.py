@@ -105,6 +105,15 @@ class HostSim:
                        rew.ctypes.data_as(C.c_void_p), C.byref(done))
         return obs, rew, bool(done.value)
 
+    def eval_gym(self, actions, arena=0):
+        actions = np.ascontiguousarray(actions, dtype=np.int32)
+        obs = np.zeros((self.P, self.obs_size), dtype=np.float32)
+        rew = np.zeros(self.P, dtype=np.float32)
+        done = C.c_uint8(0)
+        self.L.hs_eval_gym(self.h, arena, actions.ctypes.data_as(C.c_void_p), obs.ctypes.data_as(C.c_void_p),
+                           rew.ctypes.data_as(C.c_void_p), C.byref(done))
+        return obs, rew, bool(done.value)
+
     def gym_state(self, arena=0):
         score = np.zeros(2, dtype=np.int32)
         last_touch = C.c_int32(0)
@@ -113,6 +122,12 @@ class HostSim:
         self.L.hs_gym_state(self.h, arena, score.ctypes.data_as(C.c_void_p), C.byref(last_touch),
                             counters.ctypes.data_as(C.c_void_p), touched.ctypes.data_as(C.c_void_p))
         return score, last_touch.value, counters, touched
+
+
+def dump_contacts(max_rows=64):
+    out = np.zeros((max_rows, 16), dtype=np.float32)
+    n = lib().hs_dump_contacts(out.ctypes.data_as(C.c_void_p), max_rows)
+    return out[:n]
 
 
 def action_table():

@@ -1,0 +1,79 @@
+"""CPU suite: the device headers (compiled for the host by tests/hostsim — a TEST TOOL, not a product path) against
+the golden fixtures of the reference.  Same checks the -m gpu suite runs through the C ABI on the B200."""
+import numpy as np
+import pytest
+
+import common
+from hostsim import hostsim
+from rlgymppo_cpp_b200 import abi
+
+
+def _runner(team):
+    cfg = abi.default_cfg(num_arenas=1, team_size=team)
+    hs = hostsim.HostSim(cfg)
+    return (lambda c, b, p, t: hs.set_state(0, c, b, p, t)), (lambda u: hs.tick(0, u, 1)), (lambda: hs.get_state(0))
+
+
+def test_action_table(golden_dir):
+    import os
+
+    assert np.array_equal(hostsim.action_table(), np.load(os.path.join(golden_dir, "action_table.npy")))
+
+
+def test_single_tick_scenarios_1v1():
+    s, t, g = _runner(1)
+    res = common.check_single_tick_run(common.load_tick_file("tick_scenarios_1v1"), s, t, g)
+    print(res)
+
+
+@pytest.mark.parametrize("team", [1, 2, 3])
+def test_single_tick_random_play(team):
+    s, t, g = _runner(team)
+    res = common.check_single_tick_run(common.load_tick_file(f"tick_random_{team}v{team}"), s, t, g, allow_contact_frac=0.08)
+    print(res)
+
+
+@pytest.mark.parametrize("name,cfg", list(common.gym_cfgs()))
+def test_gym_layer_bit_exact(name, cfg, golden_dir):
+    import os
+
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    hs = hostsim.HostSim(cfg)
+    hs.set_player_order(g["player_order"])
+    for i in range(len(g["tick"])):
+        hs.set_state(0, g["cars"][i], g["ball"][i:i + 1], g["pads"][i], int(g["tick"][i]))
+        if g["first"][i]:
+            obs = hs.reset_from_current(0)
+            assert common.obs_equal(cfg, g["obs"][i], obs), (name, i)
+        else:
+            obs, r, d = hs.eval_gym(g["actions"][i], 0)
+            assert common.obs_equal(cfg, g["obs"][i], obs), (name, i)
+            assert np.array_equal(r.view(np.uint32), g["reward"][i].view(np.uint32)), (name, i, r, g["reward"][i])
+            assert d == bool(g["done"][i]), (name, i)
+
+
+def test_state_setters_statistics():
+    """RandomState / KickoffState use the engine's own RNG: check structure and ranges (RandomState.cpp:8-62, Arena.cpp:112-216)."""
+    cfg = abi.default_cfg(num_arenas=64, team_size=2)
+    hs = hostsim.HostSim(cfg)
+    for a in range(64):
+        hs.reset(a)
+        cars, ball, pads, tick = hs.get_state(a)
+        assert np.all(np.abs(ball["pos"][0][:2]) <= [3500, 4000]) and 92.7 <= ball["pos"][0][2] <= 1820
+        assert np.linalg.norm(ball["vel"][0]) <= 4000.01
+        assert np.allclose(cars["pos"][:, 2], 17) and np.all(cars["is_on_ground"] == 1)
+        assert np.all((cars["boost"] >= 0) & (cars["boost"] <= 100))
+        assert np.all(pads["is_active"] == 1)
+    cfg.state_setter = abi.RLG_SETTER_KICKOFF
+    hs = hostsim.HostSim(cfg)
+    spots = {(-2048, -2560), (2048, -2560), (-256, -3840), (256, -3840), (0, -4608)}
+    for a in range(16):
+        hs.reset(a)
+        cars, ball, pads, tick = hs.get_state(a)
+        assert np.allclose(ball["pos"][0], [0, 0, 93.15], atol=1e-4) and np.all(ball["vel"] == 0)
+        for c in cars:
+            x, y = float(c["pos"][0]), float(c["pos"][1])
+            if c["team"] == 1:
+                x, y = -x, -y
+            assert (round(x), round(y)) in spots
+            assert abs(c["boost"] - 100 / 3) < 1e-4
