@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py — collection steps/sec of the B200 engine (and of the reference's CPU path with --impl reference).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): 1v1 soccar, 16384 arenas per GPU, DefaultObs, examplemain rewards/terminals,
+RandomState resets, tickSkip 8, placeholder mesh set v1.  A "step" is one fused Gym::Step launch over every arena of the
+rank = 16384 * 2 player-steps (the reference counts player-timesteps: ThreadAgent.cpp:158).  Arenas shard across ranks
+with no collective on the data path (weak scaling: per-GPU work fixed).
+
+One JSON line on rank 0; see README/DESIGN.md for the meaning of `roofline`, `cpu_baseline`, `e2e`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ARENAS_PER_GPU = 16384
+TEAM = 1
+METRIC = "collection steps/sec (1v1, tickSkip=8)"
+UNIT = "player-steps/s"
+
+
+def workload_cfg(n_arenas, device, rank, seed=123):
+    from rlgymppo_cpp_b200 import abi
+
+    cfg = abi.default_cfg(num_arenas=n_arenas, team_size=TEAM, tick_skip=8, seed=seed)
+    cfg.device = device
+    cfg.arena_id_base = rank * n_arenas  # RNG streams keyed by GLOBAL arena id: results independent of the GPU count
+    return cfg
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_baseline_sample(budget_s=15.0):
+    """The reference's multithreaded collection loop (oracle/_ref) on the box's host cores, bounded sample."""
+    from oracle import refsim
+    from rlgymppo_cpp_b200 import abi
+
+    if not refsim.available():
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref/librlref.so missing"}
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    T = max(1, min(cores, 256))
+    G = 8
+    cfg = abi.default_cfg(num_arenas=T * G, team_size=TEAM)
+    b = refsim.RefBench(cfg, T, G, 7)
+    b.run(10)  # warm-up
+    t = b.run(20)
+    steps = int(max(20, min(2000, 20 * (budget_s * 0.6) / max(t, 1e-3))))
+    t = b.run(steps)
+    v = b.player_steps(steps) / t
+    b.close()
+    return {"value": v, "unit": UNIT, "cores": T, "kind": "reference",
+            "sample": f"{T} threads x {G} gyms (1v1, same plugins), {steps} env-steps each, uniform random actions, Gym::Step + auto-reset; {t:.1f}s"}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref), all host threads."""
+    if rank != 0:
+        return
+    from oracle import refsim
+    from rlgymppo_cpp_b200 import abi
+
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    T = max(1, min(cores, 256))
+    G = 8
+    cfg = abi.default_cfg(num_arenas=T * G, team_size=TEAM)
+    b = refsim.RefBench(cfg, T, G, 7)
+    t_probe = b.run(10)
+    inner = int(max(10, min(1000, 10 * 2.0 / max(t_probe, 1e-3))))  # ~2 s per bench step
+    for _ in range(args.warmup):
+        b.run(inner)
+    ts = [b.run(inner) for _ in range(args.steps)]
+    b.close()
+    total = sum(ts)
+    v = T * G * inner * b.P * args.steps / total
+    sample = f"{T} threads x {G} gyms, {inner} env-steps per gym per bench step (bounded sample of the 16384-arena workload)"
+    out = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "cfg2: 1v1 soccar, 16384 arenas/GPU, DefaultObs + examplemain rewards/terminals, RandomState, tickSkip 8, "
+                               "uniform random actions, placeholder mesh set v1", "reference_sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": T, "kind": "reference", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    from rlgymppo_cpp_b200 import abi, build, engine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    build.build()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    A = args.arenas
+    cfg = workload_cfg(A, local_rank, rank)
+    e = engine.Engine(cfg)
+    P, OBS = e.P, e.obs_size
+    ext = torch.cuda.ExternalStream(e.stream, device=torch.device("cuda", local_rank))
+    K, W = args.steps, args.warmup
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(1000 + rank)
+    # inputs resident in HBM before the timed region: one action-index array per step
+    actions = torch.randint(0, 90, (K + W, A * P), dtype=torch.int32, device="cuda", generator=gen)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    e.reset()
+    e.sync()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # settle the arenas into their steady-state mix (resets, contacts) before timing
+    with torch.cuda.stream(ext):
+        for i in range(W):
+            e.step_device(actions[i].data_ptr())
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = e.launch_count
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(K):
+        flush.fill_(i & 255)  # L2 flush between timed iterations (torch stream)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(ext):
+            starts[i].record(ext)
+            e.step_device(actions[W + i].data_ptr())
+            ends[i].record(ext)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    launches = e.launch_count - launches0
+    ms = [s.elapsed_time(t) for s, t in zip(starts, ends)]
+    total_ms = torch.tensor([sum(ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    ms_per_step = total_ms / K
+    value = world * A * P * K / (total_ms * 1e-3)
+
+    # e2e: the reference-facing host-buffer call (H2D actions from pinned memory, fused step, D2H obs/reward/done)
+    host_actions = actions[W:W + min(K, 8)].cpu().numpy()
+    e.step_host(host_actions[0])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(len(host_actions)):
+        e.step_host(host_actions[i])
+    barrier()
+    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * A * P * len(host_actions) / float(e2e_t.item())
+    h2d = A * P * 4
+    d2h = A * P * OBS * 4 + A * P * 4 + A
+
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        S = e.state_bytes
+        alg_bytes = A * (2 * S + 4 * P + 4 * P * OBS + 4 * P + 1)
+        achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic_k_step.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg2: 1v1 soccar, 16384 arenas/GPU, DefaultObs + examplemain rewards/terminals, RandomState, tickSkip 8, "
+                                   "uniform random actions (sim-only collection, BASELINE.md §3.2), placeholder mesh set v1",
+                       "arenas_per_gpu": A, "players_per_arena": P, "obs_size": OBS, "tick_skip": 8, "l2_flush_between_steps": True,
+                       "state_bytes_per_arena": S, "parallelism": f"arena-sharded x{world}, no data-path collective"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "kernel": "k_step", "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
+            "wall_s_timed_region": t_wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                out["cpu_baseline"] = cpu_baseline_sample()
+            except Exception as ex:  # the baseline is reported, never required for the GPU number
+                out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--arenas", type=int, default=ARENAS_PER_GPU, help="arenas per GPU (default: BASELINE configs[1])")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -427,6 +427,66 @@ double ref_bench_collect(const rlg_engine_cfg* cfg, int num_threads, int gyms_pe
     return total / mx;
 }
 
+// persistent variant for bench.py --impl reference: gyms are built once, every call runs `steps` env-steps per gym
+struct RefBench {
+    std::vector<std::vector<RefGym*>> gyms;
+    int P = 0;
+    uint32_t seed = 1;
+    uint64_t calls = 0;
+};
+void* ref_bench_create(const rlg_engine_cfg* cfg, int num_threads, int gyms_per_thread, uint32_t seed) {
+    RefBench* b = new RefBench();
+    b->gyms.resize(num_threads);
+    b->seed = seed;
+    std::vector<std::thread> ths;
+    for (int t = 0; t < num_threads; t++)
+        ths.emplace_back([&, t] {
+            RocketSim::Math::GetRandEngine().seed(seed + 977 * t);
+            for (int i = 0; i < gyms_per_thread; i++) { RefGym* g = make_gym(cfg); g->gym->Reset(); b->gyms[t].push_back(g); }
+        });
+    for (auto& th : ths) th.join();
+    b->P = b->gyms[0][0]->match->playerAmount;
+    return b;
+}
+// returns seconds (max over threads) for `steps` Gym::Step per gym, GameInst::Step-style auto reset
+double ref_bench_run(void* h, int steps) {
+    RefBench* b = (RefBench*)h;
+    int T = (int)b->gyms.size();
+    std::atomic<int> ready{0}; std::atomic<bool> go{false};
+    std::vector<double> secs(T, 0.0);
+    std::vector<std::thread> ths;
+    uint64_t call = b->calls++;
+    for (int t = 0; t < T; t++) {
+        ths.emplace_back([&, t] {
+            RocketSim::Math::GetRandEngine().seed(b->seed + 977 * t + 31 * (uint32_t)call);
+            uint32_t rng = (b->seed + (uint32_t)call * 7919u) * 2654435761u + t * 40503u + 1;
+            auto next = [&rng] { rng ^= rng << 13; rng ^= rng >> 17; rng ^= rng << 5; return rng; };
+            IList acts(b->P);
+            ready++;
+            while (!go.load()) std::this_thread::yield();
+            auto t0 = std::chrono::steady_clock::now();
+            for (int s = 0; s < steps; s++)
+                for (auto g : b->gyms[t]) {
+                    for (int p = 0; p < b->P; p++) acts[p] = next() % 90;
+                    auto r = g->gym->Step(acts);
+                    if (r.done) g->gym->Reset();
+                }
+            secs[t] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        });
+    }
+    while (ready.load() < T) std::this_thread::yield();
+    go = true;
+    for (auto& th : ths) th.join();
+    double mx = 0;
+    for (double s : secs) mx = std::max(mx, s);
+    return mx;
+}
+void ref_bench_destroy(void* h) {
+    RefBench* b = (RefBench*)h;
+    for (auto& v : b->gyms) for (auto g : v) delete g;
+    delete b;
+}
+
 size_t ref_sizeof_car_state() { return sizeof(rlg_car_state); }
 
 } // extern "C"

@@ -34,6 +34,8 @@ def lib():
         L.ref_gym_create.restype = C.c_void_p
         L.ref_gym_arena.restype = C.c_void_p
         L.ref_bench_collect.restype = C.c_double
+        L.ref_bench_create.restype = C.c_void_p
+        L.ref_bench_run.restype = C.c_double
         L.ref_sizeof_car_state.restype = C.c_size_t
         assert L.ref_sizeof_car_state() == C.sizeof(abi.CarState)
         blobs = meshes.generate_placeholder_soccar()
@@ -181,3 +183,25 @@ def bench_collect(cfg: abi.EngineCfg, num_threads: int, gyms_per_thread: int, wa
     """player-steps/s of the reference's threaded Gym::Step loop (sim only, random actions)."""
     return float(lib().ref_bench_collect(C.byref(cfg), num_threads, gyms_per_thread, warmup_steps, timed_steps,
                                          C.c_uint32(seed_)))
+
+
+class RefBench:
+    """Persistent multithreaded reference collection loop (Gym::Step + auto-reset, random actions)."""
+
+    def __init__(self, cfg: abi.EngineCfg, num_threads: int, gyms_per_thread: int, seed_: int = 1):
+        self.L = lib()
+        self.T, self.G = num_threads, gyms_per_thread
+        self.h = C.c_void_p(self.L.ref_bench_create(C.byref(cfg), num_threads, gyms_per_thread, C.c_uint32(seed_)))
+        self.P = abi.num_players(cfg)
+
+    def run(self, steps: int) -> float:
+        """-> seconds for `steps` env-steps on every gym"""
+        return float(self.L.ref_bench_run(self.h, steps))
+
+    def player_steps(self, steps: int) -> int:
+        return self.T * self.G * steps * self.P
+
+    def close(self):
+        if self.h:
+            self.L.ref_bench_destroy(self.h)
+            self.h = None
