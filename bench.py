@@ -41,6 +41,24 @@ def workload_cfg(n_arenas, device, rank, seed=123):
     return cfg
 
 
+class stdout_to_stderr:
+    """The reference logs through std::cout (RG_LOG); keep fd 1 clean so that rank 0 prints exactly ONE JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -111,13 +129,14 @@ def cpu_baseline_sample(budget_s=15.0):
     T = max(1, min(cores, 256))
     G = 8
     cfg = abi.default_cfg(num_arenas=T * G, team_size=TEAM)
-    b = refsim.RefBench(cfg, T, G, 7)
-    b.run(10)  # warm-up
-    t = b.run(20)
-    steps = int(max(20, min(2000, 20 * (budget_s * 0.6) / max(t, 1e-3))))
-    t = b.run(steps)
-    v = b.player_steps(steps) / t
-    b.close()
+    with stdout_to_stderr():
+        b = refsim.RefBench(cfg, T, G, 7)
+        b.run(10)  # warm-up
+        t = b.run(20)
+        steps = int(max(20, min(2000, 20 * (budget_s * 0.6) / max(t, 1e-3))))
+        t = b.run(steps)
+        v = b.player_steps(steps) / t
+        b.close()
     return {"value": v, "unit": UNIT, "cores": T, "kind": "reference",
             "sample": f"{T} threads x {G} gyms (1v1, same plugins), {steps} env-steps each, uniform random actions, Gym::Step + auto-reset; {t:.1f}s"}
 
@@ -133,13 +152,14 @@ def run_reference(args, rank, world):
     T = max(1, min(cores, 256))
     G = 8
     cfg = abi.default_cfg(num_arenas=T * G, team_size=TEAM)
-    b = refsim.RefBench(cfg, T, G, 7)
-    t_probe = b.run(10)
-    inner = int(max(10, min(1000, 10 * 2.0 / max(t_probe, 1e-3))))  # ~2 s per bench step
-    for _ in range(args.warmup):
-        b.run(inner)
-    ts = [b.run(inner) for _ in range(args.steps)]
-    b.close()
+    with stdout_to_stderr():
+        b = refsim.RefBench(cfg, T, G, 7)
+        t_probe = b.run(10)
+        inner = int(max(10, min(1000, 10 * 2.0 / max(t_probe, 1e-3))))  # ~2 s per bench step
+        for _ in range(args.warmup):
+            b.run(inner)
+        ts = [b.run(inner) for _ in range(args.steps)]
+        b.close()
     total = sum(ts)
     v = T * G * inner * b.P * args.steps / total
     sample = f"{T} threads x {G} gyms, {inner} env-steps per gym per bench step (bounded sample of the 16384-arena workload)"
