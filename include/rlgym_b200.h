@@ -223,6 +223,8 @@ int rlg_engine_step_noreset(rlg_engine* e, const int32_t* action_idx, void* stre
 int rlg_engine_set_player_order(rlg_engine* e, const int32_t* car_ids_host);
 
 int rlg_engine_num_arenas(const rlg_engine* e);
+int rlg_engine_device(const rlg_engine* e); /* CUDA ordinal the engine lives on */
+int rlg_engine_arena_id_base(const rlg_engine* e); /* rlg_engine_cfg.arena_id_base */
 size_t rlg_engine_state_bytes_per_arena(const rlg_engine* e); /* S(P) of SURVEY.md §8d as laid out here */
 /* D2H copy of the current outputs (any pointer may be NULL); synchronises the engine stream. */
 int rlg_engine_read_outputs(rlg_engine* e, float* obs_host, float* reward_host, uint8_t* done_host);
@@ -233,10 +235,79 @@ void* rlg_engine_stream(rlg_engine* e); /* the engine's own cudaStream_t */
 int rlg_engine_step_host(rlg_engine* e, const int32_t* action_idx_host,
                          float* obs_host, float* reward_host, uint8_t* done_host);
 
+/* Synchronous copies ordered after everything queued on the engine's stream (test / host-plugin plumbing). */
+int rlg_engine_copy_to_host(rlg_engine* e, void* dst_host, const void* src_dev, size_t bytes);
+int rlg_engine_copy_to_device(rlg_engine* e, void* dst_dev, const void* src_host, size_t bytes);
+
 /* Number of kernel launches issued by this engine so far (bench "gpu_launches"). */
 uint64_t rlg_engine_launch_count(const rlg_engine* e);
 /* Wait for all work queued on the engine's stream. */
 int rlg_engine_sync(rlg_engine* e);
+
+
+/* Gym::Step with caller-provided DEVICE output buffers (obs [A*P,obs], reward [A*P], done [A]); the engine's own
+ * output buffers (rlg_engine_outputs) are left untouched. This is how the collector appends straight into its
+ * trajectory ring (replaces GameTrajectory::AppendSingleStep, P/private/RLGymPPO_CPP/Threading/GameTrajectory.cpp:54-79). */
+int rlg_engine_step_to(rlg_engine* e, const int32_t* action_idx, float* obs_out, float* reward_out, uint8_t* done_out,
+                       void* stream);
+
+/* ---- collector: device-resident ThreadAgent loop --------------------------------------------------------------------
+ * Replaces ThreadAgent::_RunFunc (P/private/RLGymPPO_CPP/Threading/ThreadAgent.cpp:24-195: infer -> step -> append),
+ * DiscretePolicy::GetAction (P/private/RLGymPPO_CPP/PPO/DiscretePolicy.cpp:44-62), ValueEstimator::Forward
+ * (PPO/ValueEstimator.cpp:6-27), ThreadAgentManager::CollectTimesteps' truncation marking + concatenation
+ * (Threading/ThreadAgentManager.cpp:16-80), TorchFuncs::ComputeGAE (Util/TorchFuncs.cpp:5-52) and the layout of
+ * ExperienceBuffer::SubmitExperience rows (PPO/ExperienceBuffer.cpp:12-70).
+ *
+ * Both networks are Linear+ReLU stacks with a final Linear (DiscretePolicy.cpp:7-30, ValueEstimator.cpp:6-27); the
+ * forward runs on the 5th-gen tensor cores (tcgen05, TF32 inputs, FP32 accumulate in TMEM) fused with bias+ReLU,
+ * softmax(logits / temperature), clamp(ACTION_MIN_PROB=1e-11, 1), multinomial sampling and log-prob. */
+#define RLG_MAX_HIDDEN_LAYERS 4
+typedef struct rlg_collector_cfg {
+    int32_t num_hidden;                          /* layerSizes.size() (LearnerConfig.h policyLayerSizes / criticLayerSizes) */
+    int32_t policy_hidden[RLG_MAX_HIDDEN_LAYERS]; /* multiples of 32, <= 256 */
+    int32_t critic_hidden[RLG_MAX_HIDDEN_LAYERS];
+    int32_t max_steps;                           /* trajectory ring capacity T (env-steps per collect call) */
+    uint64_t seed;                               /* sampling RNG (counter based: seed, global row id, step counter) */
+    float temperature;                           /* DiscretePolicy::temperature */
+    int32_t deterministic;                       /* ThreadAgentManager::deterministic -> argmax, logprob 0 */
+} rlg_collector_cfg;
+
+typedef struct rlg_collector rlg_collector;
+
+/* T-major device views of the last collect: row index n = arena * P + player (player order).
+ * obs [T+1][N][obs] (slot t = what the policy saw at step t; slot T = nextStates of the last step),
+ * action [T][N] i32, logprob [T][N], reward [T][N], done [T][A] u8, value [T+1][N] (slot T = bootstrap),
+ * advantage/value_target/ret [T][N] (after rlg_collector_gae). */
+typedef struct rlg_traj_view {
+    int32_t T, N, A, P, obs_size;
+    const float* obs; const int32_t* action; const float* logprob; const float* reward; const uint8_t* done;
+    const float* value; const float* advantage; const float* value_target; const float* ret;
+} rlg_traj_view;
+
+int rlg_collector_create(rlg_engine* e, const rlg_collector_cfg* cfg, rlg_collector** out);
+int rlg_collector_destroy(rlg_collector* c);
+/* net: 0 = policy, 1 = critic. layer in [0, num_hidden]. W_host is torch's nn.Linear weight [out, in] row-major,
+ * b_host [out]. (Same tensors PPOLearner keeps in policy->parameters(), P/private/RLGymPPO_CPP/PPO/PPOLearner.cpp.) */
+int rlg_collector_set_layer(rlg_collector* c, int net, int layer, const float* W_host, const float* b_host, int out_dim, int in_dim);
+/* DiscretePolicy::GetAction + ValueEstimator::Forward on obs_dev [n_rows, obs_size]; any output may be NULL.
+ * counter selects the RNG stream position (the collector uses its env-step counter). */
+int rlg_collector_infer(rlg_collector* c, const float* obs_dev, int n_rows, uint64_t counter, int32_t* action_dev,
+                        float* logprob_dev, float* value_dev, void* stream);
+/* n_steps (<= max_steps) iterations of: infer(obs_t) -> rlg_engine_step_to(ring slot t+1) ; then the bootstrap value
+ * pass on slot T. The first call uses the engine's current obs (rlg_engine_reset must have run). */
+int rlg_collector_collect(rlg_collector* c, int n_steps, void* stream);
+/* TorchFuncs::ComputeGAE over the reference's concatenation order (player-major: each row n contributes its T steps
+ * back to back; the last step of every row is marked truncated unless done; the value after a row's last step is the
+ * NEXT row's first value — the reference's seam quirk — and the bootstrap value for the last row). */
+int rlg_collector_gae(rlg_collector* c, float gamma, float lambda, float return_std, float clip_range, void* stream);
+int rlg_collector_view(rlg_collector* c, rlg_traj_view* out);
+/* ExperienceBuffer::SubmitExperience row layout: writes the last collect in the reference's concatenated order
+ * (row i = n * T + t) into caller DEVICE buffers (any may be NULL): states [N*T, obs], actions i64 [N*T],
+ * log_probs, rewards, next_states [N*T, obs], dones f32, truncateds f32, value_targets, advantages. */
+int rlg_collector_export(rlg_collector* c, float* states, int64_t* actions, float* log_probs, float* rewards,
+                         float* next_states, float* dones, float* truncateds, float* value_targets, float* advantages,
+                         void* stream);
+uint64_t rlg_collector_launch_count(const rlg_collector* c);
 
 #ifdef __cplusplus
 }

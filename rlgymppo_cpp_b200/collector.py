@@ -1,0 +1,140 @@
+"""ctypes binding of the device-resident collector (csrc/collector.cu, include/rlgym_b200.h `rlg_collector_*`).
+
+Mirrors what ThreadAgentManager hands to Learner (reference ThreadAgentManager.cpp:16-80 / GameTrajectory.h:5-18):
+after ``collect(n)`` + ``gae(...)`` the seven trajectory tensors plus value targets and advantages exist on the device,
+either as T-major views (``view()``) or exported in the reference's concatenated row order (``export_rows``).
+There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence, Tuple
+
+import numpy as np
+
+from . import abi
+from .engine import Engine, _check, load_library
+
+
+class CollectorCfg(C.Structure):
+    _fields_ = [
+        ("num_hidden", C.c_int32), ("policy_hidden", C.c_int32 * 4), ("critic_hidden", C.c_int32 * 4), ("max_steps", C.c_int32),
+        ("seed", C.c_uint64), ("temperature", C.c_float), ("deterministic", C.c_int32),
+    ]
+
+
+class TrajView(C.Structure):
+    _fields_ = [
+        ("T", C.c_int32), ("N", C.c_int32), ("A", C.c_int32), ("P", C.c_int32), ("obs_size", C.c_int32),
+        ("obs", C.c_void_p), ("action", C.c_void_p), ("logprob", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p),
+        ("value", C.c_void_p), ("advantage", C.c_void_p), ("value_target", C.c_void_p), ("ret", C.c_void_p),
+    ]
+
+
+def default_linear_init(layer_dims: Sequence[Tuple[int, int]], seed: int):
+    """torch.nn.Linear's default init (kaiming_uniform(a=sqrt 5) == U(+-1/sqrt(in)) for W and b), the init the reference's
+    DiscretePolicy / ValueEstimator get from libtorch (DiscretePolicy.cpp:13-27). numpy Generator, not torch's stream."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for o, i in layer_dims:
+        bound = 1.0 / np.sqrt(i)
+        out.append((rng.uniform(-bound, bound, size=(o, i)).astype(np.float32), rng.uniform(-bound, bound, size=o).astype(np.float32)))
+    return out
+
+
+class Collector:
+    def __init__(self, engine: Engine, policy_hidden=(256, 256, 256), critic_hidden=(256, 256, 256), max_steps=8, seed=123,
+                 temperature=1.0, deterministic=False):
+        self.L = load_library()
+        self.L.rlg_collector_launch_count.restype = C.c_uint64
+        self.engine = engine
+        assert len(policy_hidden) == len(critic_hidden)
+        cfg = CollectorCfg()
+        cfg.num_hidden = len(policy_hidden)
+        for i, (a, b) in enumerate(zip(policy_hidden, critic_hidden)):
+            cfg.policy_hidden[i] = a
+            cfg.critic_hidden[i] = b
+        cfg.max_steps = max_steps
+        cfg.seed = seed
+        cfg.temperature = temperature
+        cfg.deterministic = int(deterministic)
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        _check(self.L.rlg_collector_create(engine.h, C.byref(cfg), C.byref(self.h)))
+        self.policy_dims = self._dims(policy_hidden, abi.RLG_NUM_ACTIONS)
+        self.critic_dims = self._dims(critic_hidden, 1)
+        self.weights = [None, None]
+
+    def _dims(self, hidden, out):
+        dims, i = [], self.engine.obs_size
+        for h in hidden:
+            dims.append((h, i))
+            i = h
+        dims.append((out, i))
+        return dims
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rlg_collector_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- weights ------------------------------------------------------------------------------------
+    def set_weights(self, net: int, layers):
+        """layers: [(W [out,in] f32, b [out] f32), ...] in torch nn.Linear convention; net 0 = policy, 1 = critic."""
+        dims = self.policy_dims if net == 0 else self.critic_dims
+        assert len(layers) == len(dims)
+        keep = []
+        for l, ((W, b), (o, i)) in enumerate(zip(layers, dims)):
+            W = np.ascontiguousarray(W, dtype=np.float32)
+            b = np.ascontiguousarray(b, dtype=np.float32)
+            assert W.shape == (o, i) and b.shape == (o,), (W.shape, b.shape, o, i)
+            _check(self.L.rlg_collector_set_layer(self.h, net, l, W.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), o, i))
+            keep.append((W, b))
+        self.weights[net] = keep
+
+    def init_default(self, seed=0):
+        self.set_weights(0, default_linear_init(self.policy_dims, seed))
+        self.set_weights(1, default_linear_init(self.critic_dims, seed + 1))
+
+    # -- calls ----------------------------------------------------------------------------------------
+    def infer(self, obs_ptr: int, n_rows: int, counter: int, action_ptr=0, logprob_ptr=0, value_ptr=0):
+        v = lambda p: C.c_void_p(p) if p else None
+        _check(self.L.rlg_collector_infer(self.h, C.c_void_p(obs_ptr), n_rows, C.c_uint64(counter), v(action_ptr), v(logprob_ptr), v(value_ptr), None))
+
+    def collect(self, n_steps: int):
+        _check(self.L.rlg_collector_collect(self.h, n_steps, None))
+
+    def gae(self, gamma=0.99, lam=0.95, return_std=1.0, clip_range=10.0):
+        _check(self.L.rlg_collector_gae(self.h, C.c_float(gamma), C.c_float(lam), C.c_float(return_std), C.c_float(clip_range), None))
+
+    def view(self) -> TrajView:
+        v = TrajView()
+        _check(self.L.rlg_collector_view(self.h, C.byref(v)))
+        return v
+
+    def export_rows(self, states=0, actions=0, log_probs=0, rewards=0, next_states=0, dones=0, truncateds=0, value_targets=0, advantages=0):
+        v = lambda p: C.c_void_p(p) if p else None
+        _check(self.L.rlg_collector_export(self.h, v(states), v(actions), v(log_probs), v(rewards), v(next_states), v(dones), v(truncateds),
+                                           v(value_targets), v(advantages), None))
+
+    def read(self, name: str) -> np.ndarray:
+        """D2H copy of one T-major view (test plumbing)."""
+        v = self.view()
+        T, N, A, O = v.T, v.N, v.A, v.obs_size
+        shapes = {"obs": ((T + 1, N, O), np.float32), "action": ((T, N), np.int32), "logprob": ((T, N), np.float32),
+                  "reward": ((T, N), np.float32), "done": ((T, A), np.uint8), "value": ((T + 1, N), np.float32),
+                  "advantage": ((T, N), np.float32), "value_target": ((T, N), np.float32), "ret": ((T, N), np.float32)}
+        shape, dt = shapes[name]
+        out = np.empty(shape, dtype=dt)
+        _check(self.L.rlg_engine_copy_to_host(self.engine.h, out.ctypes.data_as(C.c_void_p), C.c_void_p(getattr(v, name)), C.c_size_t(out.nbytes)))
+        return out
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.L.rlg_collector_launch_count(self.h))

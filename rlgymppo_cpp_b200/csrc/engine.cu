@@ -197,6 +197,7 @@ static inline int grid_for(int n, int block) { return (n + block - 1) / block; }
 extern "C" {
 
 const char* rlg_last_error(void) { return g_last_error.c_str(); }
+void rlg_internal_set_error(const char* msg) { g_last_error = msg ? msg : ""; }  // used by collector.cu
 int rlg_abi_version(void) { return 1; }
 size_t rlg_sizeof_car_state(void) { return sizeof(rlg_car_state); }
 size_t rlg_sizeof_engine_cfg(void) { return sizeof(rlg_engine_cfg); }
@@ -418,8 +419,10 @@ int rlg_engine_tick(rlg_engine* e, const rlg_controls* controls, int nticks, voi
     return RLG_OK;
 }
 
-static int do_step(rlg_engine* e, const int32_t* action_idx, cudaStream_t s, int autoReset) {
-    k_step<<<grid_for(e->cfg.numArenas, 64), 64, 0, s>>>(e->state, e->cfg, e->nwords, e->ms, e->tables, action_idx, e->obs, e->reward, e->done, autoReset);
+static int do_step(rlg_engine* e, const int32_t* action_idx, cudaStream_t s, int autoReset, float* obs = nullptr, float* reward = nullptr,
+                   uint8_t* done = nullptr) {
+    k_step<<<grid_for(e->cfg.numArenas, 64), 64, 0, s>>>(e->state, e->cfg, e->nwords, e->ms, e->tables, action_idx, obs ? obs : e->obs,
+                                                         reward ? reward : e->reward, done ? done : e->done, autoReset);
     e->launches++;
     CK(cudaGetLastError());
     return RLG_OK;
@@ -431,6 +434,14 @@ int rlg_engine_step(rlg_engine* e, const int32_t* action_idx, void* stream) {
     CK(cudaSetDevice(e->device));
     return do_step(e, action_idx, pick(e, stream), 1);
 }
+int rlg_engine_step_to(rlg_engine* e, const int32_t* action_idx, float* obs_out, float* reward_out, uint8_t* done_out, void* stream) {
+    if (!e || !action_idx || !obs_out || !reward_out || !done_out) return fail(RLG_ERR_INVALID, "null argument");
+    if (!e->meshesLoaded) return fail(RLG_ERR_STATE, "rlg_engine_load_meshes must be called first (RocketSim::Init)");
+    CK(cudaSetDevice(e->device));
+    return do_step(e, action_idx, pick(e, stream), 1, obs_out, reward_out, done_out);
+}
+int rlg_engine_device(const rlg_engine* e) { return e ? e->device : -1; }
+int rlg_engine_arena_id_base(const rlg_engine* e) { return e ? e->cfgIn.arena_id_base : 0; }
 int rlg_engine_step_noreset(rlg_engine* e, const int32_t* action_idx, void* stream) {
     if (!e || !action_idx) return fail(RLG_ERR_INVALID, "null argument");
     if (!e->meshesLoaded) return fail(RLG_ERR_STATE, "rlg_engine_load_meshes must be called first (RocketSim::Init)");
@@ -488,6 +499,21 @@ int rlg_engine_step_host(rlg_engine* e, const int32_t* action_idx_host, float* o
     if (obs_host) memcpy(obs_host, e->hObs, (size_t)A * P * e->cfg.obsSize * 4);
     if (reward_host) memcpy(reward_host, e->hReward, (size_t)A * P * 4);
     if (done_host) memcpy(done_host, e->hDone, (size_t)A);
+    return RLG_OK;
+}
+
+int rlg_engine_copy_to_host(rlg_engine* e, void* dst_host, const void* src_dev, size_t bytes) {
+    if (!e || (bytes && (!dst_host || !src_dev))) return fail(RLG_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(e->device));
+    CK(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return RLG_OK;
+}
+int rlg_engine_copy_to_device(rlg_engine* e, void* dst_dev, const void* src_host, size_t bytes) {
+    if (!e || (bytes && (!dst_dev || !src_host))) return fail(RLG_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(e->device));
+    CK(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
     return RLG_OK;
 }
 
