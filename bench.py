@@ -5,9 +5,11 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 Workload (BASELINE.json configs[1]): 1v1 soccar, 16384 arenas per GPU, DefaultObs, examplemain rewards/terminals,
-RandomState resets, tickSkip 8, placeholder mesh set v1.  A "step" is one fused Gym::Step launch over every arena of the
-rank = 16384 * 2 player-steps (the reference counts player-timesteps: ThreadAgent.cpp:158).  Arenas shard across ranks
-with no collective on the data path (weak scaling: per-GPU work fixed).
+RandomState resets, tickSkip 8, placeholder mesh set v1, on-device policy (256x256x256) + critic inference.  A bench
+"step" is one collect call = what one PPO iteration collects: 4 x (tcgen05 MLP inference + sampling -> fused Gym::Step ->
+trajectory-ring append) over every arena of the rank + the bootstrap value pass + GAE = 4 * 16384 * 2 player-steps
+(the reference counts player-timesteps: ThreadAgent.cpp:158).  Arenas shard across ranks with no collective on the data
+path (weak scaling: per-GPU work fixed).
 
 One JSON line on rank 0; see README/DESIGN.md for the meaning of `roofline`, `cpu_baseline`, `e2e`.
 """
@@ -180,7 +182,7 @@ def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
 
-    from rlgymppo_cpp_b200 import abi, build, engine
+    from rlgymppo_cpp_b200 import abi, build, collector, engine
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
@@ -188,16 +190,15 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    A = args.arenas
+    A, T = args.arenas, args.env_steps
     cfg = workload_cfg(A, local_rank, rank)
     e = engine.Engine(cfg)
     P, OBS = e.P, e.obs_size
+    col = collector.Collector(e, policy_hidden=(256, 256, 256), critic_hidden=(256, 256, 256), max_steps=T, seed=123)
+    col.init_default(seed=123)  # random-init weights of the examplemain architecture (256x256x256), same on every rank
+    col.enable_timing(True)
     ext = torch.cuda.ExternalStream(e.stream, device=torch.device("cuda", local_rank))
     K, W = args.steps, args.warmup
-    gen = torch.Generator(device="cuda")
-    gen.manual_seed(1000 + rank)
-    # inputs resident in HBM before the timed region: one action-index array per step
-    actions = torch.randint(0, 90, (K + W, A * P), dtype=torch.int32, device="cuda", generator=gen)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     e.reset()
     e.sync()
@@ -208,16 +209,24 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def one_iteration():
+        # what one PPO iteration's collection does: T x (policy+critic inference -> fused Gym::Step -> ring append),
+        # bootstrap value pass, GAE
+        col.collect(T)
+        col.gae(0.99, 0.95, 1.0, 10.0)
+
     # settle the arenas into their steady-state mix (resets, contacts) before timing
     with torch.cuda.stream(ext):
         for i in range(W):
-            e.step_device(actions[i].data_ptr())
+            one_iteration()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = e.launch_count
+    launches0 = e.launch_count + col.launch_count
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    step_ms = infer_ms = 0.0
+    step_n = infer_n = 0
     barrier()
     t_wall0 = time.perf_counter()
     for i in range(K):
@@ -225,32 +234,36 @@ def run_ours(args, rank, local_rank, world):
         torch.cuda.synchronize()
         with torch.cuda.stream(ext):
             starts[i].record(ext)
-            e.step_device(actions[W + i].data_ptr())
+            one_iteration()
             ends[i].record(ext)
+        sm, sn, im, inn = col.kernel_times()  # waits for this iteration's events
+        step_ms += sm; step_n += sn; infer_ms += im; infer_n += inn
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
-    launches = e.launch_count - launches0
+    launches = e.launch_count + col.launch_count - launches0
     ms = [s.elapsed_time(t) for s, t in zip(starts, ends)]
     total_ms = torch.tensor([sum(ms)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
     ms_per_step = total_ms / K
-    value = world * A * P * K / (total_ms * 1e-3)
+    value = world * A * P * T * K / (total_ms * 1e-3)
 
-    # e2e: the reference-facing host-buffer call (H2D actions from pinned memory, fused step, D2H obs/reward/done)
-    host_actions = actions[W:W + min(K, 8)].cpu().numpy()
+    # e2e: the reference-facing Gym::Step call with HOST buffers (H2D action indices from pinned memory, fused step,
+    # D2H obs/reward/done), i.e. what a host-side policy (the reference's ThreadAgent) would drive
+    n_e2e = min(max(K, 4), 8)
+    host_actions = np.random.default_rng(1000 + rank).integers(0, 90, size=(n_e2e + 1, A * P)).astype(np.int32)
     e.step_host(host_actions[0])
     barrier()
     t0 = time.perf_counter()
-    for i in range(len(host_actions)):
-        e.step_host(host_actions[i])
+    for i in range(n_e2e):
+        e.step_host(host_actions[i + 1])
     barrier()
     e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = world * A * P * len(host_actions) / float(e2e_t.item())
+    e2e_value = world * A * P * n_e2e / float(e2e_t.item())
     h2d = A * P * 4
     d2h = A * P * OBS * 4 + A * P * 4 + A
 
@@ -258,7 +271,8 @@ def run_ours(args, rank, local_rank, world):
         peak, peak_src = measured_peak_hbm()
         S = e.state_bytes
         alg_bytes = A * (2 * S + 4 * P + 4 * P * OBS + 4 * P + 1)
-        achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+        k_step_ms = step_ms / max(step_n, 1)
+        achieved = alg_bytes / (k_step_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic_k_step.json")
         if os.path.exists(tp):
@@ -266,18 +280,36 @@ def run_ours(args, rank, local_rank, world):
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
+        # dense part: policy fwd + critic fwd per sample, every env-step, + one critic pass for the bootstrap
+        fl_pol = 2 * (OBS * 256 + 2 * 256 * 256 + 256 * 90)
+        fl_cri = 2 * (OBS * 256 + 2 * 256 * 256 + 256 * 1)
+        mlp_flops = A * P * (T * (fl_pol + fl_cri) + fl_cri) * K
+        mlp_tflops = mlp_flops / (infer_ms * 1e-3) / 1e12 if infer_ms > 0 else None
+        try:
+            tf_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]) / 2  # TF32 = half the bf16 rate
+        except Exception:
+            tf_peak = 1125.0
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "cfg2: 1v1 soccar, 16384 arenas/GPU, DefaultObs + examplemain rewards/terminals, RandomState, tickSkip 8, "
-                                   "uniform random actions (sim-only collection, BASELINE.md §3.2), placeholder mesh set v1",
-                       "arenas_per_gpu": A, "players_per_arena": P, "obs_size": OBS, "tick_skip": 8, "l2_flush_between_steps": True,
-                       "state_bytes_per_arena": S, "parallelism": f"arena-sharded x{world}, no data-path collective"},
+                                   "on-device policy (256x256x256) + critic inference, sampling, trajectory ring, GAE; placeholder mesh set v1; "
+                                   f"one bench step = one collect of {T} env-steps over every arena + GAE",
+                       "arenas_per_gpu": A, "players_per_arena": P, "obs_size": OBS, "tick_skip": 8, "env_steps_per_bench_step": T,
+                       "player_steps_per_bench_step": world * A * P * T, "l2_flush_between_steps": True,
+                       "state_bytes_per_arena": S, "mlp_dtype": "tf32 inputs, fp32 accumulate (tcgen05)",
+                       "parallelism": f"arena-sharded x{world}, no data-path collective"},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "call": "rlg_engine_step_host (Gym::Step with host buffers, uniform random host actions)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "k_step", "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
+                         "kernel": "k_step", "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": k_step_ms, "launches_timed": step_n,
+                         "share_of_step": step_ms / total_ms, "peak_source": peak_src},
+            "roofline_mlp": {"bound": "tensor", "achieved": mlp_tflops, "peak": tf_peak, "unit": "TFLOP/s",
+                             "frac": (mlp_tflops / tf_peak) if mlp_tflops else None, "kernel": "k_mlp_infer",
+                             "launch_ms": infer_ms / max(infer_n, 1), "launches_timed": infer_n, "share_of_step": infer_ms / total_ms,
+                             "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 rate)"},
             "wall_s_timed_region": t_wall,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -297,6 +329,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--arenas", type=int, default=ARENAS_PER_GPU, help="arenas per GPU (default: BASELINE configs[1])")
+    ap.add_argument("--env-steps", type=int, default=4, help="env-steps per bench step (one collect call; cfg1's 100k timesteps/iteration ~ 4 x 32768)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

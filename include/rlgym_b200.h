@@ -308,6 +308,11 @@ int rlg_collector_export(rlg_collector* c, float* states, int64_t* actions, floa
                          float* next_states, float* dones, float* truncateds, float* value_targets, float* advantages,
                          void* stream);
 uint64_t rlg_collector_launch_count(const rlg_collector* c);
+/* Per-kernel CUDA-event timing of the LAST collect on its launching stream (bench roofline): summed durations and launch
+ * counts of the fused Gym::Step kernel and of the MLP inference kernel. Replaces ThreadAgent::Times
+ * (P/private/RLGymPPO_CPP/Threading/ThreadAgent.h "envStepTime"/"policyInferTime", ThreadAgentManager.cpp:82-117). */
+int rlg_collector_enable_timing(rlg_collector* c, int on);
+int rlg_collector_kernel_times(rlg_collector* c, double* step_ms, int32_t* step_launches, double* infer_ms, int32_t* infer_launches);
 
 #ifdef __cplusplus
 }

@@ -135,6 +135,16 @@ class Collector:
         _check(self.L.rlg_engine_copy_to_host(self.engine.h, out.ctypes.data_as(C.c_void_p), C.c_void_p(getattr(v, name)), C.c_size_t(out.nbytes)))
         return out
 
+    def enable_timing(self, on=True):
+        _check(self.L.rlg_collector_enable_timing(self.h, int(on)))
+
+    def kernel_times(self):
+        """(step_ms_total, step_launches, infer_ms_total, infer_launches) of the last collect (syncs on its events)."""
+        sm, im = C.c_double(), C.c_double()
+        sn, inn = C.c_int32(), C.c_int32()
+        _check(self.L.rlg_collector_kernel_times(self.h, C.byref(sm), C.byref(sn), C.byref(im), C.byref(inn)))
+        return sm.value, sn.value, im.value, inn.value
+
     @property
     def launch_count(self) -> int:
         return int(self.L.rlg_collector_launch_count(self.h))

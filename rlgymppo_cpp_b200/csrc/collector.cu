@@ -423,6 +423,10 @@ struct rlg_collector {
     float* dValue = nullptr; float* dAdv = nullptr; float* dTarget = nullptr; float* dRet = nullptr;
     bool haveObs0 = false;
     uint64_t stepCounter = 0, launches = 0;
+    // optional per-kernel timing of the last collect (CUDA events on the launching stream)
+    bool timing = false;
+    std::vector<cudaEvent_t> evStep, evInfer;  // pairs (start, end)
+    int nStepEv = 0, nInferEv = 0;
 };
 
 namespace {
@@ -479,6 +483,8 @@ int rlg_collector_destroy(rlg_collector* c) {
     for (int n = 0; n < 2; n++) for (int l = 0; l < kMaxLayers; l++) { cudaFree(c->L[n][l].dW); cudaFree(c->L[n][l].dB); }
     cudaFree(c->dObs); cudaFree(c->dAction); cudaFree(c->dLogprob); cudaFree(c->dReward); cudaFree(c->dDone);
     cudaFree(c->dValue); cudaFree(c->dAdv); cudaFree(c->dTarget); cudaFree(c->dRet);
+    for (auto ev : c->evStep) cudaEventDestroy(ev);
+    for (auto ev : c->evInfer) cudaEventDestroy(ev);
     delete c;
     return RLG_OK;
 }
@@ -588,18 +594,56 @@ int rlg_collector_collect(rlg_collector* c, int n_steps, void* stream) {
         CKC(cudaMemcpyAsync(c->dObs, c->dObs + (size_t)c->T * N * c->obs, N * rowBytes, cudaMemcpyDeviceToDevice, s));
     }
     c->T = n_steps;
+    c->nStepEv = c->nInferEv = 0;
+    auto mark = [&](std::vector<cudaEvent_t>& v, int& n) {
+        if (!c->timing) return;
+        if ((int)v.size() <= n) { cudaEvent_t ev; cudaEventCreate(&ev); v.push_back(ev); }
+        cudaEventRecord(v[n++], s);
+    };
     for (int t = 0; t < n_steps; t++) {
+        mark(c->evInfer, c->nInferEv);
         int rc = launch_infer(c, c->dObs + (size_t)t * N * c->obs, (int)N, c->stepCounter, c->dAction + (size_t)t * N, c->dLogprob + (size_t)t * N,
                               c->dValue + (size_t)t * N, s);
+        mark(c->evInfer, c->nInferEv);
         if (rc != RLG_OK) return rc;
+        mark(c->evStep, c->nStepEv);
         if (rlg_engine_step_to(c->e, c->dAction + (size_t)t * N, c->dObs + (size_t)(t + 1) * N * c->obs, c->dReward + (size_t)t * N,
                                c->dDone + (size_t)t * c->A, s) != RLG_OK)
             return failc(RLG_ERR_STATE, rlg_last_error());
+        mark(c->evStep, c->nStepEv);
         c->launches++;
         c->stepCounter++;
     }
     // value of the state after the last step (Learner.cpp:618-640 appends nextStates[count-1])
-    return launch_infer(c, c->dObs + (size_t)n_steps * N * c->obs, (int)N, c->stepCounter, nullptr, nullptr, c->dValue + (size_t)n_steps * N, s);
+    mark(c->evInfer, c->nInferEv);
+    int rc = launch_infer(c, c->dObs + (size_t)n_steps * N * c->obs, (int)N, c->stepCounter, nullptr, nullptr, c->dValue + (size_t)n_steps * N, s);
+    mark(c->evInfer, c->nInferEv);
+    return rc;
+}
+
+int rlg_collector_enable_timing(rlg_collector* c, int on) {
+    if (!c) return failc(RLG_ERR_INVALID, "null collector");
+    c->timing = on != 0;
+    return RLG_OK;
+}
+
+int rlg_collector_kernel_times(rlg_collector* c, double* step_ms, int32_t* step_launches, double* infer_ms, int32_t* infer_launches) {
+    if (!c) return failc(RLG_ERR_INVALID, "null collector");
+    CKC(cudaSetDevice(c->device));
+    double st = 0, in = 0;
+    for (int i = 0; i + 1 < c->nStepEv; i += 2) {
+        CKC(cudaEventSynchronize(c->evStep[i + 1]));
+        float ms = 0; CKC(cudaEventElapsedTime(&ms, c->evStep[i], c->evStep[i + 1])); st += ms;
+    }
+    for (int i = 0; i + 1 < c->nInferEv; i += 2) {
+        CKC(cudaEventSynchronize(c->evInfer[i + 1]));
+        float ms = 0; CKC(cudaEventElapsedTime(&ms, c->evInfer[i], c->evInfer[i + 1])); in += ms;
+    }
+    if (step_ms) *step_ms = st;
+    if (step_launches) *step_launches = c->nStepEv / 2;
+    if (infer_ms) *infer_ms = in;
+    if (infer_launches) *infer_launches = c->nInferEv / 2;
+    return RLG_OK;
 }
 
 int rlg_collector_gae(rlg_collector* c, float gamma, float lambda, float return_std, float clip_range, void* stream) {
