@@ -210,6 +210,9 @@ int rlg_action_table(float* table_host);
  * parity tests obtain obs for injected states (G/Envs/Match.cpp:4-23). */
 int rlg_engine_reset_current(rlg_engine* e, const uint8_t* mask_host, void* stream);
 
+/* Same, writing the masked arenas' obs rows into a caller DEVICE buffer [A*P, obs] (e.g. a trajectory-ring slot). */
+int rlg_engine_reset_current_to(rlg_engine* e, const uint8_t* mask_host, float* obs_out, void* stream);
+
 /* Match::BuildObservations / IsDone / GetRewards (G/Envs/Match.cpp:12-38) on the CURRENT arena states, i.e.
  * Gym::Step (G/Gym.cpp:84-93) minus the physics ticks and the event tracker: prevActions := table[action_idx]
  * (zeroed for demoed players), GameState::UpdateFromArena, obs, done, rewards -> outputs. action_idx: DEVICE [A*P]. */
@@ -307,6 +310,13 @@ int rlg_collector_view(rlg_collector* c, rlg_traj_view* out);
 int rlg_collector_export(rlg_collector* c, float* states, int64_t* actions, float* log_probs, float* rewards,
                          float* next_states, float* dones, float* truncateds, float* value_targets, float* advantages,
                          void* stream);
+/* Host StateSetter support (rlg_engine_cfg.state_setter == RLG_SETTER_HOST): after every env-step of a collect the
+ * collector synchronises, reads the done flags and calls hook(user, finished_arena_ids, n, obs_out) where obs_out is
+ * the DEVICE obs slot the post-reset observations must be written to (rlg_engine_set_state +
+ * rlg_engine_reset_current_to). Replaces the StateSetter::ResetState(Arena*) call in Match::ResetState
+ * (G/Envs/Match.cpp:54-70) reached from GameInst::Step's auto-reset (GameInst.cpp:20-24). */
+typedef void (*rlg_reset_hook)(void* user, const int32_t* arena_ids_host, int n, float* obs_out);
+int rlg_collector_set_reset_hook(rlg_collector* c, rlg_reset_hook hook, void* user);
 uint64_t rlg_collector_launch_count(const rlg_collector* c);
 /* Per-kernel CUDA-event timing of the LAST collect on its launching stream (bench roofline): summed durations and launch
  * counts of the fused Gym::Step kernel and of the MLP inference kernel. Replaces ThreadAgent::Times

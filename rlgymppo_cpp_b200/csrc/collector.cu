@@ -423,6 +423,10 @@ struct rlg_collector {
     float* dValue = nullptr; float* dAdv = nullptr; float* dTarget = nullptr; float* dRet = nullptr;
     bool haveObs0 = false;
     uint64_t stepCounter = 0, launches = 0;
+    rlg_reset_hook resetHook = nullptr;
+    void* resetUser = nullptr;
+    std::vector<uint8_t> hDone;
+    std::vector<int32_t> hIds;
     // optional per-kernel timing of the last collect (CUDA events on the launching stream)
     bool timing = false;
     std::vector<cudaEvent_t> evStep, evInfer;  // pairs (start, end)
@@ -613,12 +617,26 @@ int rlg_collector_collect(rlg_collector* c, int n_steps, void* stream) {
         mark(c->evStep, c->nStepEv);
         c->launches++;
         c->stepCounter++;
+        if (c->resetHook) {  // host StateSetter: re-set finished arenas before the next inference reads their obs
+            c->hDone.resize(c->A);
+            CKC(cudaMemcpyAsync(c->hDone.data(), c->dDone + (size_t)t * c->A, c->A, cudaMemcpyDeviceToHost, s));
+            CKC(cudaStreamSynchronize(s));
+            c->hIds.clear();
+            for (int a = 0; a < c->A; a++) if (c->hDone[a]) c->hIds.push_back(a);
+            if (!c->hIds.empty()) c->resetHook(c->resetUser, c->hIds.data(), (int)c->hIds.size(), c->dObs + (size_t)(t + 1) * N * c->obs);
+        }
     }
     // value of the state after the last step (Learner.cpp:618-640 appends nextStates[count-1])
     mark(c->evInfer, c->nInferEv);
     int rc = launch_infer(c, c->dObs + (size_t)n_steps * N * c->obs, (int)N, c->stepCounter, nullptr, nullptr, c->dValue + (size_t)n_steps * N, s);
     mark(c->evInfer, c->nInferEv);
     return rc;
+}
+
+int rlg_collector_set_reset_hook(rlg_collector* c, rlg_reset_hook hook, void* user) {
+    if (!c) return failc(RLG_ERR_INVALID, "null collector");
+    c->resetHook = hook; c->resetUser = user;
+    return RLG_OK;
 }
 
 int rlg_collector_enable_timing(rlg_collector* c, int on) {

@@ -313,7 +313,7 @@ int rlg_engine_load_meshes(rlg_engine* e, const void* const* blobs, const size_t
 
 static cudaStream_t pick(rlg_engine* e, void* stream) { return stream ? (cudaStream_t)stream : e->stream; }
 
-static int do_reset(rlg_engine* e, const uint8_t* mask_host, void* stream, int useSetter) {
+static int do_reset(rlg_engine* e, const uint8_t* mask_host, void* stream, int useSetter, float* obs_out = nullptr) {
     if (!e) return fail(RLG_ERR_INVALID, "null engine");
     if (!e->meshesLoaded) return fail(RLG_ERR_STATE, "rlg_engine_load_meshes must be called first (RocketSim::Init)");
     if (useSetter && e->cfg.stateSetter == RLG_SETTER_HOST) return fail(RLG_ERR_STATE, "host state setter: use rlg_engine_set_state + rlg_engine_reset_current");
@@ -324,7 +324,7 @@ static int do_reset(rlg_engine* e, const uint8_t* mask_host, void* stream, int u
         CK(cudaMallocAsync(&dmask, e->cfg.numArenas, s));
         CK(cudaMemcpyAsync(dmask, mask_host, e->cfg.numArenas, cudaMemcpyHostToDevice, s));
     }
-    k_reset<<<grid_for(e->cfg.numArenas, 64), 64, 0, s>>>(e->state, e->cfg, e->nwords, e->tables, dmask, useSetter, e->obs);
+    k_reset<<<grid_for(e->cfg.numArenas, 64), 64, 0, s>>>(e->state, e->cfg, e->nwords, e->tables, dmask, useSetter, obs_out ? obs_out : e->obs);
     e->launches++;
     CK(cudaGetLastError());
     if (dmask) CK(cudaFreeAsync(dmask, s));
@@ -332,6 +332,7 @@ static int do_reset(rlg_engine* e, const uint8_t* mask_host, void* stream, int u
 }
 int rlg_engine_reset(rlg_engine* e, const uint8_t* mask_host, void* stream) { return do_reset(e, mask_host, stream, 1); }
 int rlg_engine_reset_current(rlg_engine* e, const uint8_t* mask_host, void* stream) { return do_reset(e, mask_host, stream, 0); }
+int rlg_engine_reset_current_to(rlg_engine* e, const uint8_t* mask_host, float* obs_out, void* stream) { return do_reset(e, mask_host, stream, 0, obs_out); }
 
 int rlg_engine_set_player_order(rlg_engine* e, const int32_t* car_ids_host) {
     if (!e || !car_ids_host) return fail(RLG_ERR_INVALID, "null argument");

@@ -152,3 +152,12 @@ def write_placeholder_set(folder: str) -> List[str]:
             f.write(blob)
         paths.append(p)
     return paths
+
+
+if __name__ == "__main__":
+    import argparse
+
+    ap = argparse.ArgumentParser(description="write the placeholder soccar set as <out>/soccar/*.cmf (what RocketSim::Init reads)")
+    ap.add_argument("--out", default="collision_meshes")
+    for path in write_placeholder_set(ap.parse_args().out):
+        print(path)
