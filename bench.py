@@ -175,7 +175,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(json.dumps(out))
 
 
 def run_ours(args, rank, local_rank, world):
@@ -317,12 +317,26 @@ def run_ours(args, rank, local_rank, world):
                 out["cpu_baseline"] = cpu_baseline_sample()
             except Exception as ex:  # the baseline is reported, never required for the GPU number
                 out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
-        print(json.dumps(out), flush=True)
+        emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: str):
+    """The ONE JSON line goes to the process's real stdout; everything else (NCCL banners, the reference's RG_LOG
+    std::cout chatter) was redirected to stderr at start-up."""
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (line + "\n").encode())
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

@@ -50,6 +50,9 @@ struct rlg_engine {
     float* hObs = nullptr;
     float* hReward = nullptr;
     uint8_t* hDone = nullptr;
+    Contact* scratch = nullptr;  // per-arena contact segments (rl_collide.h ContactSink)
+    int xwords = 0, stride = 0, scratchSlots = 0;
+    size_t rolesSmem = 0;
     uint64_t launches = 0;
 };
 
@@ -97,10 +100,7 @@ __global__ void k_set_state(uint32_t* state, SimCfg cfg, int nwords, const int32
     load_arena(s, state, cfg.numArenas, a, nwords);
     if (cars) for (int c = 0; c < cfg.numCars; c++) car_from_pod(s.cars[c], cars[(size_t)i * cfg.numCars + c]);
     if (balls) ball_from_pod(s.ball, balls[i]);
-    if (pads) for (int p = 0; p < kNumPads; p++) {
-        const rlg_pad_state& ps = pads[(size_t)i * kNumPads + p];
-        s.pads[p].isActive = ps.is_active != 0; s.pads[p].cooldown = ps.cooldown; s.pads[p].prevLockedCarId = ps.prev_locked_car_id;
-    }
+    if (pads) for (int p = 0; p < kNumPads; p++) pad_from_pod(s.pads, p, pads[(size_t)i * kNumPads + p]);
     if (ticks && ticks[i] >= 0) set_i64(s.tickLo, s.tickHi, ticks[i]);
     store_arena(s, state, cfg.numArenas, a, nwords);
 }
@@ -120,53 +120,93 @@ __global__ void k_get_state(const uint32_t* state, SimCfg cfg, int nwords, const
         cars[(size_t)i * cfg.numCars + c] = o;
     }
     if (balls) { rlg_ball_state o; ball_to_pod(o, s.ball); balls[i] = o; }
-    if (pads) for (int p = 0; p < kNumPads; p++) {
-        rlg_pad_state o; o.is_active = s.pads[p].isActive; o.cooldown = s.pads[p].cooldown; o.prev_locked_car_id = s.pads[p].prevLockedCarId;
-        pads[(size_t)i * kNumPads + p] = o;
-    }
+    if (pads) for (int p = 0; p < kNumPads; p++) { rlg_pad_state o; pad_to_pod(o, s.pads, p); pads[(size_t)i * kNumPads + p] = o; }
     if (ticks) ticks[i] = get_i64(s.tickLo, s.tickHi);
 }
 
-// Arena::Step(nticks) with explicit controls
-__global__ void __launch_bounds__(64) k_tick(uint32_t* state, SimCfg cfg, int nwords, MeshSet ms, const Tables* __restrict__ tb,
-                                             const rlg_controls* __restrict__ controls, int nticks) {
-    int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= cfg.numArenas) return;
-    ArenaS s;
-    load_arena(s, state, cfg.numArenas, a, nwords);
-    if (controls) for (int c = 0; c < cfg.numCars; c++) s.cars[c].controls = controls_from(controls[(size_t)a * cfg.numCars + c]);
-    for (int t = 0; t < nticks; t++) arena_tick(s, cfg, ms, *tb, 0);
-    store_arena(s, state, cfg.numArenas, a, nwords);
-}
+// ---- the role kernel: Arena::Step x n (mode 0) or the fused Gym::Step + GameInst auto-reset (mode 1) -----------------------
+// One block = 32 consecutive arenas x (1 + numCars) warps; warp r is ROLE r (0 = ball / arena bookkeeping, 1 + c = car c)
+// of those 32 arenas, lane = arena.  The block's arenas live in shared memory for the whole launch (arena words +
+// per-tick exchange, per-lane stride odd -> conflict-free), are loaded and stored cooperatively as coalesced 128-byte
+// lines of the word-transposed HBM layout, and the phases of rl_tick.h are separated by __syncthreads().
+struct RolesArgs {
+    uint32_t* state;
+    SimCfg cfg;
+    int nwords, xwords, stride;  // arena words, exchange words, per-lane shared stride (words, odd)
+    MeshSet ms;
+    const Tables* tb;
+    Contact* scratch;
+    int scratchSlots;
+    int mode;  // 0: tick, 1: step
+    const rlg_controls* controls; int nticks;
+    const int32_t* actions; float* obs; float* reward; uint8_t* done; int autoReset;
+};
 
-// Gym::Step + GameInst::Step auto-reset, fused: all tick_skip ticks + obs/reward/done in one launch
-__global__ void __launch_bounds__(64) k_step(uint32_t* state, SimCfg cfg, int nwords, MeshSet ms, const Tables* __restrict__ tb,
-                                             const int32_t* __restrict__ actions, float* __restrict__ obs, float* __restrict__ reward,
-                                             uint8_t* __restrict__ done, int autoReset) {
-    int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= cfg.numArenas) return;
-    ArenaS s;
-    load_arena(s, state, cfg.numArenas, a, nwords);
-    int32_t act[kMaxCars];
-    for (int p = 0; p < cfg.numCars; p++) {
-        int v = actions[(size_t)a * cfg.numCars + p];
-        act[p] = v < 0 ? 0 : (v >= RLG_NUM_ACTIONS ? RLG_NUM_ACTIONS - 1 : v);
+__global__ void __maxnreg__(168) k_roles(const RolesArgs g) {
+    extern __shared__ uint32_t smem[];
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    const int P = g.cfg.numCars, roles = P + 1, A = g.cfg.numArenas;
+    const int a = blockIdx.x * 32 + lane;
+    const bool valid = a < A;
+    uint32_t* mine = smem + (size_t)lane * g.stride;
+    ArenaS& s = *reinterpret_cast<ArenaS*>(mine);
+    TickX x = make_tickx(mine + (g.stride - g.xwords));
+    Contact* scratch = g.scratch + (size_t)(valid ? a : 0) * g.scratchSlots;
+    if (valid)
+        for (int w = role; w < g.nwords; w += roles) mine[w] = g.state[(size_t)w * A + a];
+    __syncthreads();
+
+    const CarConsts k = car_consts();
+    const Thresholds thr = contact_thresholds(k);
+    CarW w;  // this car role's per-tick work state (wheel contacts, forces)
+    bool doneFlag = false;
+
+    if (valid) {
+        if (g.mode == 0) {
+            if (role > 0 && g.controls) s.cars[role - 1].controls = controls_from(g.controls[(size_t)a * P + (role - 1)]);
+        } else if (role == 0) {
+            int32_t act[kMaxCars];
+            for (int p = 0; p < P; p++) {
+                int v = g.actions[(size_t)a * P + p];
+                act[p] = v < 0 ? 0 : (v >= RLG_NUM_ACTIONS ? RLG_NUM_ACTIONS - 1 : v);
+            }
+            parse_actions(s, g.cfg, *g.tb, act);
+        }
     }
-    float* o = obs + (size_t)a * cfg.numCars * cfg.obsSize;
-    parse_actions(s, cfg, *tb, act);
-    arena_tick(s, cfg, ms, *tb, 1);
-    event_tracker_update(s, cfg);
-    snapshot_update(s, cfg);
-    build_obs(s, cfg, *tb, o);
-    bool d = compute_done(s, cfg);
-    compute_rewards(s, cfg, reward + (size_t)a * cfg.numCars);
-    done[a] = d ? 1 : 0;
-    for (int t = 1; t < cfg.tickSkip; t++) arena_tick(s, cfg, ms, *tb, 0);
-    if (d && autoReset) {
-        gym_reset(s, cfg);
-        build_obs(s, cfg, *tb, o);
+    const int nticks = g.mode == 0 ? g.nticks : g.cfg.tickSkip;
+    for (int t = 0; t < nticks; t++) {
+        const int first = (g.mode == 1 && t == 0) ? 1 : 0;
+        if (valid) { if (role == 0) tick_s0_ball(s, x); else tick_s0_car(s, x, role - 1); }
+        __syncthreads();  // B1
+        if (valid) {
+            if (role == 0) tick_p1_ball(s, x, g.cfg, g.ms, k, thr, scratch);
+            else tick_p1_car(s, x, g.cfg, g.ms, k, thr, role - 1, w, scratch, first);
+        }
+        __syncthreads();  // B2
+        if (valid && role == 0) tick_p2_solve(s, x, g.cfg, k, thr, scratch, first);
+        __syncthreads();  // B3
+        if (valid && role > 0) tick_p3_car(s, x, *g.tb, k, role - 1, w);
+        __syncthreads();  // B4
+        if (valid && role == 0) {
+            tick_p4_pads(s, x, g.cfg);
+            if (first) {  // Gym::Step after its first tick (G/Gym.cpp:84-93)
+                float* o = g.obs + (size_t)a * P * g.cfg.obsSize;
+                event_tracker_update(s, g.cfg);
+                snapshot_update(s, g.cfg);
+                build_obs(s, g.cfg, *g.tb, o);
+                doneFlag = compute_done(s, g.cfg);
+                compute_rewards(s, g.cfg, g.reward + (size_t)a * P);
+                g.done[a] = doneFlag ? 1 : 0;
+            }
+        }
     }
-    store_arena(s, state, cfg.numArenas, a, nwords);
+    if (valid && role == 0 && g.mode == 1 && doneFlag && g.autoReset) {  // GameInst::Step auto-reset (GameInst.cpp:20-24)
+        gym_reset(s, g.cfg);
+        build_obs(s, g.cfg, *g.tb, g.obs + (size_t)a * P * g.cfg.obsSize);
+    }
+    __syncthreads();
+    if (valid)
+        for (int w2 = role; w2 < g.nwords; w2 += roles) g.state[(size_t)w2 * A + a] = mine[w2];
 }
 
 // Match::BuildObservations / IsDone / GetRewards on the CURRENT arena state (Gym::Step minus the physics and the
@@ -226,6 +266,7 @@ int rlg_action_table(float* table_host) {
 int rlg_engine_destroy(rlg_engine* e) {
     if (!e) return RLG_OK;
     cudaSetDevice(e->device);
+    cudaFree(e->scratch);
     cudaFree(e->state); cudaFree(e->tables); cudaFree(e->obs); cudaFree(e->reward); cudaFree(e->done); cudaFree(e->actions);
     for (void* p : e->meshMem) cudaFree(p);
     cudaFreeHost(e->hActions); cudaFreeHost(e->hObs); cudaFreeHost(e->hReward); cudaFreeHost(e->hDone);
@@ -260,7 +301,14 @@ int rlg_engine_create(const rlg_engine_cfg* cfg, rlg_engine** out) {
     CKD(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     const int A = e->cfg.numArenas, P = e->cfg.numCars;
     e->nwords = arena_words(P);
+    e->xwords = tickx_words(P);
+    e->stride = e->nwords + e->xwords;
+    if ((e->stride & 1) == 0) e->stride++;  // odd per-lane stride: the 32 lanes of a warp hit 32 different banks
+    e->scratchSlots = contact_scratch_slots(P);
+    e->rolesSmem = (size_t)32 * e->stride * 4;
+    CKD(cudaFuncSetAttribute(k_roles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->rolesSmem));
     CKD(cudaMalloc(&e->state, (size_t)e->nwords * A * 4));
+    CKD(cudaMalloc(&e->scratch, (size_t)A * e->scratchSlots * sizeof(Contact)));
     CKD(cudaMalloc(&e->tables, sizeof(Tables)));
     CKD(cudaMalloc(&e->obs, (size_t)A * P * e->cfg.obsSize * 4));
     CKD(cudaMalloc(&e->reward, (size_t)A * P * 4));
@@ -309,6 +357,14 @@ int rlg_engine_load_meshes(rlg_engine* e, const void* const* blobs, const size_t
     e->ms = ms;
     e->meshesLoaded = true;
     return RLG_OK;
+}
+
+static RolesArgs roles_args(rlg_engine* e) {
+    RolesArgs g;
+    memset(&g, 0, sizeof(g));
+    g.state = e->state; g.cfg = e->cfg; g.nwords = e->nwords; g.xwords = e->xwords; g.stride = e->stride;
+    g.ms = e->ms; g.tb = e->tables; g.scratch = e->scratch; g.scratchSlots = e->scratchSlots;
+    return g;
 }
 
 static cudaStream_t pick(rlg_engine* e, void* stream) { return stream ? (cudaStream_t)stream : e->stream; }
@@ -414,7 +470,9 @@ int rlg_engine_tick(rlg_engine* e, const rlg_controls* controls, int nticks, voi
     if (!e->meshesLoaded) return fail(RLG_ERR_STATE, "rlg_engine_load_meshes must be called first (RocketSim::Init)");
     CK(cudaSetDevice(e->device));
     cudaStream_t s = pick(e, stream);
-    k_tick<<<grid_for(e->cfg.numArenas, 64), 64, 0, s>>>(e->state, e->cfg, e->nwords, e->ms, e->tables, controls, nticks);
+    RolesArgs g = roles_args(e);
+    g.mode = 0; g.controls = controls; g.nticks = nticks;
+    k_roles<<<grid_for(e->cfg.numArenas, 32), 32 * (1 + e->cfg.numCars), e->rolesSmem, s>>>(g);
     e->launches++;
     CK(cudaGetLastError());
     return RLG_OK;
@@ -422,8 +480,10 @@ int rlg_engine_tick(rlg_engine* e, const rlg_controls* controls, int nticks, voi
 
 static int do_step(rlg_engine* e, const int32_t* action_idx, cudaStream_t s, int autoReset, float* obs = nullptr, float* reward = nullptr,
                    uint8_t* done = nullptr) {
-    k_step<<<grid_for(e->cfg.numArenas, 64), 64, 0, s>>>(e->state, e->cfg, e->nwords, e->ms, e->tables, action_idx, obs ? obs : e->obs,
-                                                         reward ? reward : e->reward, done ? done : e->done, autoReset);
+    RolesArgs g = roles_args(e);
+    g.mode = 1; g.actions = action_idx; g.obs = obs ? obs : e->obs; g.reward = reward ? reward : e->reward; g.done = done ? done : e->done;
+    g.autoReset = autoReset;
+    k_roles<<<grid_for(e->cfg.numArenas, 32), 32 * (1 + e->cfg.numCars), e->rolesSmem, s>>>(g);
     e->launches++;
     CK(cudaGetLastError());
     return RLG_OK;

@@ -22,7 +22,7 @@ RL_HDI V3 quat_rotate(Quat q, V3 v) {
     Quat r = t * inv;
     return V3(r.x, r.y, r.z);
 }
-RL_HDI float bt_angle(V3 edgeA, V3 normalA, V3 normalB) { return atan2f(dot(normalB, edgeA), dot(normalB, normalA)); }
+RL_HDI float bt_angle(V3 edgeA, V3 normalA, V3 normalB) { return rl_atan2(dot(normalB, edgeA), dot(normalB, normalA)); }
 
 RL_HD inline bool clamp_normal(V3 edge, V3 triNormal, V3 localN, float correctedEdgeAngle, V3& out) {
     V3 edgeCross = normalized(cross(edge, triNormal));
@@ -42,7 +42,7 @@ RL_HD inline bool clamp_normal(V3 edge, V3 triNormal, V3 localN, float corrected
     return false;
 }
 
-RL_HD inline void adjust_internal_edge(Contact& cp, const MeshSet& ms, int tri) {
+RL_HD RL_NOINLINE inline void adjust_internal_edge(Contact& cp, const MeshSet& ms, int tri) {
     const float kTwoPi = 6.283185307179586232f;
     const float edgeDistanceThreshold = 0.1f;
     const Tri& t = ms.tris[tri];
@@ -159,7 +159,7 @@ RL_HD inline void bb_cull_points(int n, const float* p, int m, int i0, int* iret
     }
     float A[8];
     int avail[8];
-    for (int i = 0; i < n; i++) { A[i] = atan2f(p[i * 2 + 1] - cy, p[i * 2] - cx); avail[i] = 1; }
+    for (int i = 0; i < n; i++) { A[i] = rl_atan2(p[i * 2 + 1] - cy, p[i * 2] - cx); avail[i] = 1; }
     avail[i0] = 0;
     iret[0] = i0;
     iret++;
@@ -180,7 +180,7 @@ RL_HD inline void bb_cull_points(int n, const float* p, int m, int i0, int* iret
     }
 }
 
-RL_HD inline void box_box(V3 p1, const M3& R1, V3 A, V3 p2, const M3& R2, V3 B, BoxBoxResult& out) {
+RL_HD RL_NOINLINE inline void box_box(V3 p1, const M3& R1, V3 A, V3 p2, const M3& R2, V3 B, BoxBoxResult& out) {
     out.n = 0;
     const float fudge_factor = 1.05f;
     V3 p = p2 - p1;

@@ -18,13 +18,43 @@ struct CarW {
     V3 force, torque, velCache;
     M3 invInertiaWorld;
     WheelW w[4];
+    MeshCands cands;  // this tick's mesh triangles near the car (wheel rays + hitbox), see rl_mesh.h
 };
 
-struct TickW {
-    CarW cars[kMaxCars];
-    V3 ballVelCache;
-    V3 ballForce;
+// ---- per-arena exchange between the roles of a tick (ball role + one role per car) --------------------------------
+// On the device this lives in shared memory next to the arena state (engine.cu k_roles); the host test build uses a
+// plain buffer.  The snapshot members are written at the start of a tick and are what OTHER roles read while the
+// owner updates its body (wheel rays against other cars / the ball, car-ball tests), so the result does not depend on
+// the order in which the roles run.
+struct CarX {
+    V3 pos, vel, angvel;  // start-of-tick snapshot
+    M3 rot;
+    int32_t demoed;
+    V3 force, torque;     // accumulated by Car::_PreTickUpdate (+ gravity), consumed by the solver
+    V3 cmn, cmx;          // hitbox AABB after the pre-tick
+    V3 ballVelCache;      // this car's contribution to Ball::_velocityImpulseCache
+    V3 velCache;          // Car::_velocityImpulseCache (bumps), written by the pair phase
+    int32_t noResponse;   // demoed when the tick started
+    int32_t nCarBall, nCarWorld;  // contacts written to this car's scratch segments
+    uint32_t padHitLo, padHitHi;
 };
+struct TickXHdr {
+    V3 ballPos, ballVel, ballAngvel;  // start-of-tick snapshot (vel undamped)
+    int32_t nBall, nPair, ballActive;
+};
+constexpr int kTickXHdrWords = sizeof(TickXHdr) / 4;
+constexpr int kCarXWords = sizeof(CarX) / 4;
+RL_HDI int tickx_words(int ncars) { return kTickXHdrWords + ncars * kCarXWords; }
+struct TickX {
+    TickXHdr* h;
+    CarX* car;
+};
+RL_HDI TickX make_tickx(uint32_t* words) {
+    TickX x;
+    x.h = reinterpret_cast<TickXHdr*>(words);
+    x.car = reinterpret_cast<CarX*>(words + kTickXHdrWords);
+    return x;
+}
 
 // constants derived the way Car::_BulletSetup derives them (Car.cpp:195-283)
 struct CarConsts {
@@ -97,43 +127,44 @@ struct DynView {
     int32_t responds;  // hasContactResponse (false for demoed cars)
 };
 
-RL_HD inline DynView dyn_view(const ArenaS& a, int body, const CarConsts& k) {
+RL_HD inline DynView dyn_view(const TickX& x, int body, const CarConsts& k) {
     DynView d;
     if (body == 0) {
-        d.pos = a.ball.pos; d.vel = a.ball.vel; d.angvel = a.ball.angvel; d.rot = M3::identity();
+        d.pos = x.h->ballPos; d.vel = x.h->ballVel; d.angvel = x.h->ballAngvel; d.rot = M3::identity();
         float r = C::BALL_RADIUS * UU2BT;
         float inertia = 0.4f * C::BALL_MASS * r * r;
         d.invInertiaLocal = V3(1.f / inertia, 1.f / inertia, 1.f / inertia);
         d.invMass = 1.f / C::BALL_MASS; d.responds = 1;
     } else {
-        const CarS& c = a.cars[body - 1];
+        const CarX& c = x.car[body - 1];
         d.pos = c.pos; d.vel = c.vel; d.angvel = c.angvel; d.rot = c.rot;
-        d.invInertiaLocal = k.invInertiaLocal; d.invMass = k.invMass; d.responds = !c.isDemoed;
+        d.invInertiaLocal = k.invInertiaLocal; d.invMass = k.invMass; d.responds = !c.demoed;
     }
     d.invInertiaWorld = world_inertia(d.rot, d.invInertiaLocal);
     return d;
 }
 
 // btCollisionWorld::rayTest through btRSBroadphase::rayTest for one wheel ray
-RL_HD inline RayHit wheel_ray(const ArenaS& a, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, int self, V3 from, V3 to) {
+RL_HD inline RayHit wheel_ray(const TickX& x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, const MeshCands& cands, int self, V3 from, V3 to) {
     RayHit hit; hit.frac = 1.0f; hit.body = -2; hit.normal = V3(0, 0, 1);
-    ray_meshes(from, to, ms, hit);
+    if (cands.n >= 0) ray_candidates(from, to, ms, cands, hit);
+    else ray_meshes(from, to, ms, hit);
     for (int p = 0; p < 4; p++) ray_plane(from, to, world_plane(p), hit);
-    ray_sphere(from, to, a.ball.pos, C::BALL_RADIUS * UU2BT, 0, hit);
+    ray_sphere(from, to, x.h->ballPos, C::BALL_RADIUS * UU2BT, 0, hit);
     for (int c = 0; c < cfg.numCars; c++) {
         if (c == self) continue;
-        const CarS& o = a.cars[c];
+        const CarX& o = x.car[c];
         V3 center = o.pos + o.rot * k.hitboxOffset;
         ray_obb(from, to, center, o.rot, k.halfExt, 1 + c, hit);
     }
-    if (hit.body >= 1 && a.cars[hit.body - 1].isDemoed) hit.body = -2;  // btDefaultVehicleRaycaster.cpp:40-51
+    if (hit.body >= 1 && x.car[hit.body - 1].demoed) hit.body = -2;  // btDefaultVehicleRaycaster.cpp:40-51
     return hit;
 }
 
 // ---- btVehicleRL::updateVehicleFirst ---------------------------------------------------------
-RL_HD inline void vehicle_first(ArenaS& a, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, int ci, CarW& w) {
-    CarS& c = a.cars[ci];
+RL_HD inline void vehicle_first(CarS& c, const TickX& x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, int ci, CarW& w) {
     V3 carFwd = c.rot.col(0), carRight = c.rot.col(1), carUp = c.rot.col(2);
+#pragma unroll 1
     for (int i = 0; i < 4; i++) {
         WheelW& wh = w.w[i];
         // updateWheelTransformsWS + updateWheelTransform: only the steered axle (basis column 1) is consumed later
@@ -152,7 +183,7 @@ RL_HD inline void vehicle_first(ArenaS& a, const SimCfg& cfg, const MeshSet& ms,
         V3 target = source + wheelDir * rayLen;
         wh.contactPoint = target;
         wh.ground = -2; wh.inContact = 0; wh.inContactWorld = 0;
-        RayHit hit = wheel_ray(a, cfg, ms, k, ci, source, target);
+        RayHit hit = wheel_ray(x, cfg, ms, k, w.cands, ci, source, target);
         if (hit.body != -2) {
             wh.contactPoint = source + (target - source) * hit.frac;
             wh.contactNormal = hit.normal;
@@ -200,6 +231,7 @@ RL_HD inline void vehicle_first(ArenaS& a, const SimCfg& cfg, const MeshSet& ms,
 
     // calcFrictionImpulses (btVehicleRL.cpp:313-388) — consumes LAST tick's engine/brake/friction values
     float frictionScale = C::CAR_MASS / 3;
+#pragma unroll 1
     for (int i = 0; i < 4; i++) {
         WheelW& wh = w.w[i];
         if (wh.ground == -2) { wh.impulse = V3(); continue; }
@@ -213,7 +245,7 @@ RL_HD inline void vehicle_first(ArenaS& a, const SimCfg& cfg, const MeshSet& ms,
         // resolveSingleBilateral (btContactConstraint.cpp:108-157)
         DynView g;
         bool dynGround = wh.ground >= 0;
-        if (dynGround) g = dyn_view(a, wh.ground, k);
+        if (dynGround) g = dyn_view(x, wh.ground, k);
         V3 rel1 = wh.contactPoint - c.pos;
         V3 rel2 = dynGround ? (wh.contactPoint - g.pos) : V3();
         V3 vel1 = vel_at(c.vel, c.angvel, rel1);
@@ -301,6 +333,7 @@ RL_HD inline void update_wheels(CarS& c, CarW& w, int numWheelsInContact, float 
         steerAngle *= c.controls.steer;
         c.wheelSteer = steerAngle;
     }
+#pragma unroll 1
     for (int i = 0; i < 4; i++) {
         WheelW& wh = w.w[i];
         if (wh.ground == -2) continue;
@@ -422,8 +455,8 @@ RL_HD inline void update_jump(CarS& c, CarW& w, const CarConsts& k, bool jumpPre
 // btMatrix3x3::getEulerYPR -> Angle::FromRotMat (MathTypes.cpp:62-71); only roll is consumed
 RL_HDI float rotmat_roll(const M3& rot) {
     // bulletMat[i][j] = rotMat[j][i] where rotMat rows are forward/right/up vectors == our basis
-    float pitch = asinf(clampf(-rot.r[2].x, -1.f, 1.f));
-    float roll = atan2f(rot.r[2].y, rot.r[2].z);
+    float pitch = rl_asin(clampf(-rot.r[2].x, -1.f, 1.f));
+    float roll = rl_atan2(rot.r[2].y, rot.r[2].z);
     if (fabsf(pitch) == kHalfPi) { if (roll > 0) roll -= kPi; else roll += kPi; }
     return roll * -1.f;
 }
@@ -484,8 +517,9 @@ RL_HD inline void update_double_jump_or_flip(CarS& c, const CarConsts& k, const 
                         v.y *= ((C::FLIP_SIDE_IMPULSE_MAX_SPEED_SCALE - 1) * forwardSpeedRatio) + 1.f;
                         if (backwards) v.x *= C::FLIP_BACKWARD_IMPULSE_SCALE_X;
                         V3 fwd = c.rot.col(0);
-                        float ang = atan2f(fwd.y, fwd.x);
-                        V3 xDir(cosf(ang), -sinf(ang), 0.f), yDir(sinf(ang), cosf(ang), 0.f);
+                        float ang = rl_atan2(fwd.y, fwd.x);
+                        float ca = rl_cos(ang), sa = rl_sin(ang);
+                        V3 xDir(ca, -sa, 0.f), yDir(sa, ca, 0.f);
                         V3 dv(dot(v, xDir), dot(v, yDir), 0.f);
                         c.vel += (dv * UU2BT * C::CAR_MASS) * k.invMass;
                     }
@@ -537,6 +571,7 @@ RL_HD inline void vehicle_second(CarS& c, CarW& w, const CarConsts& k) {
             wh.suspForce = 0;
         }
     }
+#pragma unroll 1
     for (int i = 0; i < 4; i++) {
         WheelW& wh = w.w[i];
         if (wh.suspForce != 0) {
@@ -546,6 +581,7 @@ RL_HD inline void vehicle_second(CarS& c, CarW& w, const CarConsts& k) {
         }
     }
     V3 upDir = c.rot.col(2);
+#pragma unroll 1
     for (int i = 0; i < 4; i++) {
         WheelW& wh = w.w[i];
         if (!is_zero(wh.impulse)) {
@@ -593,11 +629,12 @@ RL_HDI void car_set_default(CarS& c) {
     c.lastControls = Controls{0, 0, 0, 0, 0, 0, 0, 0};
 }
 // Car::Respawn (Car.cpp:43-56)
-RL_HD inline void car_respawn(ArenaS& a, CarS& c, int team);
+RL_HD inline void car_respawn(CarS& c, int team, uint32_t rnd);
 
 // ---- Car::_PreTickUpdate (Car.cpp:58-131) -----------------------------------------------------
-RL_HD inline void car_pre_tick(ArenaS& a, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, int ci, CarW& w) {
-    CarS& c = a.cars[ci];
+// respawnRnd: a random word for Car::Respawn's spawn-slot pick; derived by the caller from the arena RNG state, the
+// tick and the car index WITHOUT advancing the arena RNG (the roles of a tick run concurrently)
+RL_HD inline void car_pre_tick(CarS& c, const TickX& x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, int ci, CarW& w, uint32_t respawnRnd) {
     w.force = V3(); w.torque = V3(); w.velCache = V3();
     c.controls.throttle = clampf(c.controls.throttle, -1.f, 1.f);
     c.controls.steer = clampf(c.controls.steer, -1.f, 1.f);
@@ -606,12 +643,27 @@ RL_HD inline void car_pre_tick(ArenaS& a, const SimCfg& cfg, const MeshSet& ms, 
     c.controls.roll = clampf(c.controls.roll, -1.f, 1.f);
     if (c.isDemoed) {
         c.demoRespawnTimer = fmaxf_(c.demoRespawnTimer - kTickTime, 0.f);
-        if (c.demoRespawnTimer == 0) car_respawn(a, c, car_team(ci, cfg.spawnOpponents));
+        if (c.demoRespawnTimer == 0) car_respawn(c, car_team(ci, cfg.spawnOpponents), respawnRnd);
     }
     w.invInertiaWorld = world_inertia(c.rot, k.invInertiaLocal);
+    {   // one BVH query for the hitbox and the four wheel rays (pose is final for this tick: only a respawn moves it)
+        V3 center = c.pos + c.rot * k.hitboxOffset;
+        V3 ext(dot(vabs(c.rot.r[0]), k.halfExt), dot(vabs(c.rot.r[1]), k.halfExt), dot(vabs(c.rot.r[2]), k.halfExt));
+        V3 mn = center - ext, mx = center + ext;
+        V3 wheelDir = c.rot * V3(0, 0, -1);
+#pragma unroll 1
+        for (int i = 0; i < 4; i++) {
+            V3 hp = c.pos + c.rot * k.wheelConn[i];
+            float rayLen = k.wheelRest[i] + k.suspTravel + k.wheelRadius[i] - C::SUSPENSION_SUBTRACTION;
+            V3 tg = hp + wheelDir * rayLen;
+            mn = vmin(mn, vmin(hp, tg)); mx = vmax(mx, vmax(hp, tg));
+        }
+        const V3 pad(0.02f, 0.02f, 0.02f);  // > the 0.01 box padding of the direct ray walk
+        collect_candidates(ms, mn - pad, mx + pad, w.cands);
+    }
     if (c.isDemoed) return;
 
-    vehicle_first(a, cfg, ms, k, ci, w);
+    vehicle_first(c, x, cfg, ms, k, ci, w);
     bool jumpPressed = c.controls.jump && !c.lastControls.jump;
     int n = 0;
     for (int i = 0; i < 4; i++) { c.wheelContact[i] = w.w[i].inContact; n += w.w[i].inContact; }
@@ -629,10 +681,10 @@ RL_HD inline void car_pre_tick(ArenaS& a, const SimCfg& cfg, const MeshSet& ms, 
     update_boost(c, w);
 }
 
-RL_HD inline void car_respawn(ArenaS& a, CarS& c, int team) {
+RL_HD inline void car_respawn(CarS& c, int team, uint32_t rnd) {
     const float RX[4] = {-2304, -2688, 2304, 2688};
     const float RY = -4608;
-    int idx = (int)(rng_next(a) % 4u);
+    int idx = (int)(rnd % 4u);
     car_set_default(c);
     V3 pos(RX[idx], RY * (team == 0 ? 1.f : -1.f), C::CAR_RESPAWN_Z);
     float yaw = (float)(3.14159265358979323846 / 2 + (team == 0 ? 0.0 : 3.14159265358979323846));

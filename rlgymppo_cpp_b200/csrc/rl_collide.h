@@ -33,6 +33,16 @@ struct ContactSet {
     Contact c[kMaxContacts];
 };
 
+// Where a role appends the contacts it finds: a segment of the arena's contact scratch (global memory on the device).
+// Segment layout per arena: [ball: kSegBall][per car: 1 car-ball slot + kSegCarWorld world slots][car-car: kSegPair]
+constexpr int kSegBall = 12, kSegCarWorld = 13, kSegCar = 1 + kSegCarWorld, kSegPair = 16;
+RL_HDI int contact_scratch_slots(int ncars) { return kSegBall + ncars * kSegCar + kSegPair; }
+struct ContactSink {
+    Contact* base;
+    int32_t n, cap, overflow;
+};
+RL_HDI ContactSink make_sink(Contact* base, int cap) { ContactSink s; s.base = base; s.n = 0; s.cap = cap; s.overflow = 0; return s; }
+
 // relative contact breaking thresholds (btCollisionDispatcher::getNewManifold,
 // btCollisionShape::getContactBreakingThreshold): 0.02 * angularMotionDisc of the shape
 struct Thresholds { float ball, car; };
@@ -69,10 +79,10 @@ RL_HD inline int manifold_sort_cached(const Manifold& m, const Contact& pt) {
 struct CollideCtx {
     ArenaS* a;
     const SimCfg* cfg;
-    TickW* tw;
+    TickX tx;   // tx.car[c].noResponse: DISABLE_SIMULATION | CF_NO_CONTACT_RESPONSE for this tick (demoed when it started, Car.cpp:69-87)
     const CarConsts* k;
     int64_t tick;
-    int32_t noResponse[kMaxCars];  // DISABLE_SIMULATION | CF_NO_CONTACT_RESPONSE for this tick: demoed when the tick started (Car.cpp:69-87)
+    V3 ballPos, ballVel;      // the ball as the narrowphase sees it: start-of-tick position, DAMPED velocity
     int32_t firstTickOfStep;  // bump counters only stick when the callback fires during Gym::Step's first tick (see rl_tick.h)
 };
 
@@ -81,10 +91,10 @@ RL_HD inline void on_car_ball(CollideCtx& x, int ci, Contact& cp) {
     ArenaS& a = *x.a;
     CarS& car = a.cars[ci];
     cp.friction = C::CARBALL_FRICTION; cp.restitution = C::CARBALL_RESTITUTION;
-    V3 ballPosUU = to_uu(a.ball.pos), ballVelUU = to_uu(a.ball.vel);
+    V3 ballPosUU = to_uu(x.ballPos), ballVelUU = to_uu(x.ballVel);
     V3 carPosUU = to_uu(car.pos), carVelUU = to_uu(car.vel);
     car.hitValid = 1;
-    car.hitRelPos = (cp.posB - a.ball.pos) * BT2UU;  // m_localPointB of the ball (identity basis)
+    car.hitRelPos = (cp.posB - x.ballPos) * BT2UU;  // m_localPointB of the ball (identity basis)
     set_i64(car.hitTickLo, car.hitTickHi, x.tick);
     car.hitBallPos = ballPosUU;
     car.hitExtraVel = V3();
@@ -104,7 +114,7 @@ RL_HD inline void on_car_ball(CollideCtx& x, int ci, Contact& cp) {
         const float fx[4] = {0, 500.f, 2300.f, 4600.f}, fy[4] = {0.65f, 0.65f, 0.55f, 0.30f};
         V3 addedVel = (hitDir * relSpeed) * curve(fx, fy, relSpeed) * 1.f;
         car.hitExtraVel = addedVel;
-        x.tw->ballVelCache += addedVel * UU2BT;
+        x.tx.car[ci].ballVelCache += addedVel * UU2BT;
     }
 }
 
@@ -144,7 +154,7 @@ RL_HD inline void on_car_car(CollideCtx& x, int c1, int c2, Contact& cp) {
                         float baseScale = groundHit ? curve(gx, gy, speedTowards) : curve(ax, ay, speedTowards);
                         V3 hitUp = o.isOnGround ? o.rot.col(2) : V3(0, 0, 1);
                         V3 bump = velDir * baseScale + hitUp * curve(ux, uy, speedTowards) * 1.f;
-                        x.tw->cars[c2].velCache += bump * UU2BT;
+                        x.tx.car[c2].velCache += bump * UU2BT;
                     }
                     s.carContactOtherId = c2 + 1;
                     s.carContactCooldown = C::BUMP_COOLDOWN_TIME;
@@ -187,8 +197,8 @@ RL_HD inline void manifold_add(CollideCtx& x, Manifold& m, V3 normalOnB, V3 poin
     Contact& p = m.pt[idx];
     // gContactAddedCallback; demoed cars have no contact response -> returns before anything
     bool aCar = m.a >= 1, bCar = m.b >= 1;
-    if (aCar && x.noResponse[m.a - 1]) return;
-    if (bCar && x.noResponse[m.b - 1]) return;
+    if (aCar && x.tx.car[m.a - 1].noResponse) return;
+    if (bCar && x.tx.car[m.b - 1].noResponse) return;
     if (aCar && m.b == 0) on_car_ball(x, m.a - 1, p);
     else if (aCar && bCar) on_car_car(x, m.a - 1, m.b - 1, p);
     else if (aCar && m.b == -1) on_car_world(x, m.a - 1, p);
@@ -196,16 +206,16 @@ RL_HD inline void manifold_add(CollideCtx& x, Manifold& m, V3 normalOnB, V3 poin
     if (ms && tri >= 0) adjust_internal_edge(p, *ms, tri);
 }
 
-RL_HDI void manifold_flush(ContactSet& cs, const Manifold& m) {
+RL_HDI void manifold_flush(ContactSink& cs, const Manifold& m) {
     for (int i = 0; i < m.n; i++) {
-        if (cs.n < kMaxContacts) cs.c[cs.n++] = m.pt[i];
+        if (cs.n < cs.cap) cs.base[cs.n++] = m.pt[i];
         else cs.overflow++;
     }
 }
 
 // ---- shape pairs -----------------------------------------------------------------------------
 // btConvexPlaneCollisionAlgorithm::processCollision (btConvexPlaneCollisionAlgorithm.cpp:92-125)
-RL_HD inline void sphere_plane(CollideCtx& x, ContactSet& cs, V3 center, float radius, int planeIdx, float breaking) {
+RL_HD inline void sphere_plane(CollideCtx& x, ContactSink& cs, V3 center, float radius, int planeIdx, float breaking) {
     PlaneDef p = world_plane(planeIdx);
     V3 cIn = center - p.origin;
     // localGetSupportingVertex(-n) = -n * radius (btSphereShape)
@@ -219,7 +229,7 @@ RL_HD inline void sphere_plane(CollideCtx& x, ContactSet& cs, V3 center, float r
     }
 }
 
-RL_HD inline void box_plane(CollideCtx& x, ContactSet& cs, int ci, int planeIdx, float breaking) {
+RL_HD inline void box_plane(CollideCtx& x, ContactSink& cs, int ci, int planeIdx, float breaking) {
     const CarS& c = x.a->cars[ci];
     const CarConsts& k = *x.k;
     PlaneDef p = world_plane(planeIdx);
@@ -310,9 +320,10 @@ RL_HDI bool tri_early_out(const Tri& t, float threshold, Support sup) {
 }
 
 // ball vs every mesh: btConvexConcaveCollisionAlgorithm + btSphereTriangleCollisionAlgorithm
-RL_HD inline void sphere_meshes(CollideCtx& x, ContactSet& cs, const MeshSet& ms, V3 center, float radius, float breaking) {
+RL_HD inline void sphere_meshes(CollideCtx& x, ContactSink& cs, const MeshSet& ms, V3 center, float radius, float breaking) {
     float am = radius + 0.08f;  // btSphereShape::getAabb
     V3 mn = center - V3(am, am, am), mx = center + V3(am, am, am);
+    if (inside_free_box(ms, mn, mx)) return;
     for (int mi = 0; mi < ms.numMeshes; mi++) {
         const BvhNode& root = ms.nodes[ms.nodeStart[mi]];
         if (!aabb_overlap(root.mn, root.mx, mn, mx)) continue;
@@ -348,13 +359,49 @@ RL_HD inline void sphere_meshes(CollideCtx& x, ContactSet& cs, const MeshSet& ms
 }
 
 // car hitbox vs every mesh: btCompoundCollisionAlgorithm -> btConvexConcaveCollisionAlgorithm -> GJK per triangle
-RL_HD inline void box_meshes(CollideCtx& x, ContactSet& cs, const MeshSet& ms, int ci, float breaking) {
+// one candidate triangle of the hitbox-vs-mesh narrowphase (shared by the direct walk and the candidate-list path)
+RL_HDI void box_mesh_triangle(CollideCtx& x, Manifold& m, const MeshSet& ms, const CarS& c, const CarConsts& k, V3 boxCenter, V3 mn, V3 mx,
+                              int triIdx, float breaking) {
+    const Tri& t = ms.tris[triIdx];
+    if (!tri_vs_aabb(t, mn, mx)) return;
+    auto sup = [&](V3 d) {  // btBoxShape::localGetSupportingVertex (with margin)
+        V3 dl = tmul(d, c.rot);
+        V3 v(dl.x >= 0 ? k.halfExt.x : -k.halfExt.x, dl.y >= 0 ? k.halfExt.y : -k.halfExt.y, dl.z >= 0 ? k.halfExt.z : -k.halfExt.z);
+        return boxCenter + c.rot * v;
+    };
+    if (tri_early_out(t, breaking, sup)) return;
+    V3 normal, pointOnB; float dist;
+    if (box_triangle_contact(boxCenter, c.rot, k.halfExt, k.coreHalf, k.boxMargin, t, breaking, normal, pointOnB, dist))
+        manifold_add(x, m, normal, pointOnB, dist, &ms, triIdx);
+}
+
+// hitbox vs the candidate list collected in Car::_PreTickUpdate (same leaves, same order as the direct walk below)
+RL_HD inline void box_meshes_candidates(CollideCtx& x, ContactSink& cs, const MeshSet& ms, const MeshCands& cands, int ci, float breaking) {
+    const CarS& c = x.a->cars[ci];
+    const CarConsts& k = *x.k;
+    V3 boxCenter = c.pos + c.rot * k.hitboxOffset;
+    V3 ext(dot(vabs(c.rot.r[0]), k.halfExt), dot(vabs(c.rot.r[1]), k.halfExt), dot(vabs(c.rot.r[2]), k.halfExt));
+    V3 mn = boxCenter - ext, mx = boxCenter + ext;
+    int j = 0;
+    while (j < cands.n) {
+        const int mi = cands.node[j] >> 24;
+        Manifold m; m.a = 1 + ci; m.b = -1; m.n = 0; m.breaking = breaking;
+        for (; j < cands.n && (cands.node[j] >> 24) == mi; j++) {
+            const BvhNode& nd = ms.nodes[cands.node[j] & 0xffffff];
+            if (aabb_overlap(nd.mn, nd.mx, mn, mx)) box_mesh_triangle(x, m, ms, c, k, boxCenter, mn, mx, nd.tri, breaking);
+        }
+        manifold_flush(cs, m);
+    }
+}
+
+RL_HD inline void box_meshes(CollideCtx& x, ContactSink& cs, const MeshSet& ms, int ci, float breaking) {
     const CarS& c = x.a->cars[ci];
     const CarConsts& k = *x.k;
     V3 boxCenter = c.pos + c.rot * k.hitboxOffset;
     // btBoxShape::getAabb -> btTransformAabb(halfExtentsWithoutMargin, margin, t)
     V3 ext(dot(vabs(c.rot.r[0]), k.halfExt), dot(vabs(c.rot.r[1]), k.halfExt), dot(vabs(c.rot.r[2]), k.halfExt));
     V3 mn = boxCenter - ext, mx = boxCenter + ext;
+    if (inside_free_box(ms, mn, mx)) return;
     for (int mi = 0; mi < ms.numMeshes; mi++) {
         const BvhNode& root = ms.nodes[ms.nodeStart[mi]];
         if (!aabb_overlap(root.mn, root.mx, mn, mx)) continue;
@@ -365,21 +412,7 @@ RL_HD inline void box_meshes(CollideCtx& x, ContactSet& cs, const MeshSet& ms, i
                 const BvhNode& nd = ms.nodes[i];
                 bool ov = aabb_overlap(nd.mn, nd.mx, mn, mx);
                 if (nd.tri >= 0) {
-                    if (ov) {
-                        const Tri& t = ms.tris[nd.tri];
-                        if (tri_vs_aabb(t, mn, mx)) {
-                            auto sup = [&](V3 d) {  // btBoxShape::localGetSupportingVertex (with margin)
-                                V3 dl = tmul(d, c.rot);
-                                V3 v(dl.x >= 0 ? k.halfExt.x : -k.halfExt.x, dl.y >= 0 ? k.halfExt.y : -k.halfExt.y, dl.z >= 0 ? k.halfExt.z : -k.halfExt.z);
-                                return boxCenter + c.rot * v;
-                            };
-                            if (!tri_early_out(t, breaking, sup)) {
-                                V3 normal, pointOnB; float dist;
-                                if (box_triangle_contact(boxCenter, c.rot, k.halfExt, k.coreHalf, k.boxMargin, t, breaking, normal, pointOnB, dist))
-                                    manifold_add(x, m, normal, pointOnB, dist, &ms, nd.tri);
-                            }
-                        }
-                    }
+                    if (ov) box_mesh_triangle(x, m, ms, c, k, boxCenter, mn, mx, nd.tri, breaking);
                     i++;
                 } else {
                     i += ov ? 1 : nd.escape;
@@ -391,20 +424,20 @@ RL_HD inline void box_meshes(CollideCtx& x, ContactSet& cs, const MeshSet& ms, i
 }
 
 // ball vs car hitbox: GJK of (box core + 0.04) against (point + radius) == closest point on the core
-RL_HD inline void car_ball(CollideCtx& x, ContactSet& cs, int ci, float breaking) {
+RL_HD inline void car_ball(CollideCtx& x, ContactSink& cs, int ci, float breaking) {
     const CarS& c = x.a->cars[ci];
     const CarConsts& k = *x.k;
     float radius = C::BALL_RADIUS * UU2BT;
     V3 boxCenter = c.pos + c.rot * k.hitboxOffset;
     V3 normal, pointOnB; float dist;
-    if (box_sphere_contact(boxCenter, c.rot, k.halfExt, k.coreHalf, k.boxMargin, x.a->ball.pos, radius, breaking, normal, pointOnB, dist)) {
+    if (box_sphere_contact(boxCenter, c.rot, k.halfExt, k.coreHalf, k.boxMargin, x.ballPos, radius, breaking, normal, pointOnB, dist)) {
         Manifold m; m.a = 1 + ci; m.b = 0; m.n = 0; m.breaking = breaking;
         manifold_add(x, m, normal, pointOnB, dist, nullptr, -1);
         manifold_flush(cs, m);
     }
 }
 
-RL_HD inline void car_car(CollideCtx& x, ContactSet& cs, int c1, int c2, float breaking) {
+RL_HD RL_NOINLINE inline void car_car(CollideCtx& x, ContactSink& cs, int c1, int c2, float breaking) {
     const CarS& A = x.a->cars[c1];
     const CarS& B = x.a->cars[c2];
     const CarConsts& k = *x.k;

@@ -83,6 +83,11 @@ RL_HDI void ball_to_pod(rlg_ball_state& o, const BallS& b) {
     v3_to(o.ang_vel, b.angvel);
 }
 
+RL_HDI void pad_from_pod(PadsS& p, int i, const rlg_pad_state& s) { pad_set(p, i, s.is_active != 0, s.cooldown, s.prev_locked_car_id); }
+RL_HDI void pad_to_pod(rlg_pad_state& o, const PadsS& p, int i) {
+    o.is_active = (int32_t)((pads_active(p) >> i) & 1ULL); o.cooldown = p.cooldown[i]; o.prev_locked_car_id = pad_locked(p, i);
+}
+
 // fresh arena: what Arena::Create + AddCar leaves behind (cars respawned, wheel carry-over zero)
 RL_HD inline void arena_init(ArenaS& a, int numCars, uint64_t seed, uint64_t globalArenaId) {
     uint32_t* w = (uint32_t*)&a;
@@ -91,7 +96,7 @@ RL_HD inline void arena_init(ArenaS& a, int numCars, uint64_t seed, uint64_t glo
     a.rngLo = (uint32_t)s; a.rngHi = (uint32_t)(s >> 32);
     (void)rng_next(a); (void)rng_next(a);
     a.ball.pos = V3(0, 0, C::BALL_REST_Z * UU2BT);
-    for (int i = 0; i < kNumPads; i++) { a.pads[i].isActive = 1; }
+    pads_reset(a.pads);
     a.lastTouchCarId = -1;
     for (int c = 0; c < numCars; c++) {
         CarS& car = a.cars[c];

@@ -243,7 +243,7 @@ RL_HD inline bool gjk_box_core(V3 boxCenter, const M3& rot, V3 coreHalf, V3 orig
 // ---- box vs sphere (car hitbox vs ball) ---------------------------------------------------------
 // A = box (margin 0.04), B = sphere (point core, margin = radius).  GJK between a box core and a point
 // converges to the closest point on the core; written in closed form.
-RL_HD inline bool box_sphere_contact(V3 boxCenter, const M3& rot, V3 halfExt, V3 core, float marginA, V3 sphereCenter, float radius, float breaking,
+RL_HD RL_NOINLINE inline bool box_sphere_contact(V3 boxCenter, const M3& rot, V3 halfExt, V3 core, float marginA, V3 sphereCenter, float radius, float breaking,
                                      V3& normalOnB, V3& pointOnB, float& dist) {
     V3 l = tmul(sphereCenter - boxCenter, rot);
     V3 q(clampf(l.x, -core.x, core.x), clampf(l.y, -core.y, core.y), clampf(l.z, -core.z, core.z));
@@ -331,7 +331,7 @@ RL_HD inline bool box_triangle_sat(V3 boxCenter, const M3& rot, V3 halfExt, cons
     return true;
 }
 
-RL_HD inline bool box_triangle_contact(V3 boxCenter, const M3& rot, V3 halfExt, V3 core, float marginA, const Tri& t, float breaking,
+RL_HD RL_NOINLINE inline bool box_triangle_contact(V3 boxCenter, const M3& rot, V3 halfExt, V3 core, float marginA, const Tri& t, float breaking,
                                        V3& normalOnB, V3& pointOnB, float& dist) {
     float maxDist = marginA + 0.f + breaking;
     auto supB = [&](V3 axis) {  // btTriangleShape::localGetSupportingVertexWithoutMargin(axis * basisB), basisB = I

@@ -15,6 +15,10 @@ struct Tables {
     float actions[90 * 8];    // DiscreteAction table (G/Utils/ActionParsers/DiscreteAction.cpp:3-67)
     int32_t padMap[kNumPads]; // GameState pad i -> RocketSim pad index (G/Utils/Gamestates/GameState.cpp:10-50)
     float padPos[kNumPads * 3]; // RocketSim pad order (6 big, 28 small), uu
+    float padPosBT[kNumPads * 3]; // same, Bullet units (uu * (1/50), as BoostPad::_BulletSetup stores it)
+    // BoostPadGrid (BoostPadGrid.cpp:5-25): for car cell (ix, iy), ix in [-1, 8], iy in [-1, 10], the pads whose own cell
+    // lies in the clamped 3x3 neighbourhood; entry (ix+1) + 10*(iy+1), lo/hi words of a 34-bit mask
+    uint32_t padCellMask[10 * 12 * 2];
 };
 
 RL_HDI V3 car_pos_uu(const CarS& c) { return V3(c.pos.x * BT2UU, c.pos.y * BT2UU, c.pos.z * BT2UU); }
@@ -43,7 +47,7 @@ RL_HDI void parse_actions(ArenaS& a, const SimCfg& cfg, const Tables& tb, const 
 
 // ---- GameEventTracker (R/Sim/GameEventTracker/GameEventTracker.cpp) -----------------------
 // Arena::IsBallProbablyGoingIn, soccar branch (R/Sim/Arena/Arena.cpp:827-863)
-RL_HDI bool ball_probably_going_in(const BallS& b, float maxTime, float extraMargin, int* goalTeamOut) {
+RL_HD RL_NOINLINE inline bool ball_probably_going_in(const BallS& b, float maxTime, float extraMargin, int* goalTeamOut) {
     V3 pos = ball_pos_uu(b), vel = ball_vel_uu(b);
     if (fabsf(vel.y) < kEps) return false;
     float scoreDirSgn = (float)sgn(vel.y);
@@ -63,7 +67,7 @@ RL_HDI bool ball_probably_going_in(const BallS& b, float maxTime, float extraMar
 }
 
 // GetShooterPasser (GameEventTracker.cpp:5-46); returns car indices or -1. Iterates in _cars order.
-RL_HDI bool get_shooter_passer(const ArenaS& a, const SimCfg& cfg, int team, int& shooter, bool findPasser, int& passer,
+RL_HD RL_NOINLINE inline bool get_shooter_passer(const ArenaS& a, const SimCfg& cfg, int team, int& shooter, bool findPasser, int& passer,
                                int64_t maxShooterTicks, int64_t maxPasserTicks) {
     shooter = passer = -1;
     int64_t tick = get_i64(a.tickLo, a.tickHi);
@@ -202,7 +206,7 @@ RL_HDI void shuffle_slots(ArenaS& a, int* slots, int n) {
 }
 
 // obs row stride is `stride` floats (so a transposed/strided output buffer can be used)
-RL_HDI void build_obs(ArenaS& a, const SimCfg& cfg, const Tables& tb, float* out /*[P][obsSize]*/) {
+RL_HD RL_NOINLINE inline void build_obs(ArenaS& a, const SimCfg& cfg, const Tables& tb, float* out /*[P][obsSize]*/) {
     const float px = 1 / C::ARENA_EXTENT_X, py = 1 / C::ARENA_EXTENT_Y, pz = 1 / 2044.f;
     const float velCoef = 1 / C::CAR_MAX_SPEED, angCoef = 1 / C::CAR_MAX_ANG_SPEED;
     for (int p = 0; p < cfg.numCars; p++) {
@@ -223,7 +227,7 @@ RL_HDI void build_obs(ArenaS& a, const SimCfg& cfg, const Tables& tb, float* out
         for (int i = 0; i < 8; i++) o[k++] = me.prevAction[i];
         for (int i = 0; i < kNumPads; i++) {
             int gi = inv ? (kNumPads - i - 1) : i;  // GameState.cpp:84-91
-            o[k++] = (float)(a.pads[tb.padMap[gi]].isActive != 0);
+            o[k++] = (float)((pads_active(a.pads) >> tb.padMap[gi]) & 1ULL);
         }
         k += add_player_obs(o + k, me, inv);
         if (cfg.obsKind == 0) {
@@ -309,7 +313,7 @@ RL_HDI float reward_term(ArenaS& a, const SimCfg& cfg, const RewardTerm& t, int 
 }
 
 // CombinedReward::GetAllRewards (+ ZeroSumReward::GetAllRewards), output in player order
-RL_HDI void compute_rewards(ArenaS& a, const SimCfg& cfg, float* out /*[P]*/) {
+RL_HD RL_NOINLINE inline void compute_rewards(ArenaS& a, const SimCfg& cfg, float* out /*[P]*/) {
     float r[kMaxCars];
     for (int p = 0; p < cfg.numCars; p++) r[p] = 0.f;
     for (int i = 0; i < cfg.numRewardTerms; i++)
@@ -388,7 +392,7 @@ RL_HDI void reset_to_kickoff(ArenaS& a, const SimCfg& cfg) {
     a.ball.pos = V3(0.f * UU2BT, 0.f * UU2BT, C::BALL_REST_Z * UU2BT);
     a.ball.vel = V3(); a.ball.angvel = V3();
     a.ball.updateCounterLo = 0;
-    for (int i = 0; i < kNumPads; i++) { a.pads[i].isActive = 1; a.pads[i].cooldown = 0; a.pads[i].prevLockedCarId = 0; }
+    pads_reset(a.pads);
 }
 
 RL_HDI V3 rand_vec(ArenaS& a, V3 lo, V3 hi) {
@@ -438,7 +442,7 @@ RL_HDI void reset_to_random(ArenaS& a, const SimCfg& cfg) {
     }
 }
 
-RL_HDI void gym_reset(ArenaS& a, const SimCfg& cfg) {
+RL_HD RL_NOINLINE inline void gym_reset(ArenaS& a, const SimCfg& cfg) {
     if (cfg.stateSetter == 0) reset_to_kickoff(a, cfg);
     else if (cfg.stateSetter == 1) reset_to_random(a, cfg);
     episode_reset(a, cfg);

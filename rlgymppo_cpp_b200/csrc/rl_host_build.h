@@ -6,6 +6,7 @@
 // "subtree header" list reproduces the order walkStacklessQuantizedTreeCacheFriendly visits them
 // (subtrees <= 2048 bytes of 16-byte quantised nodes = 128 nodes).
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <stdexcept>
@@ -252,6 +253,26 @@ inline void host_build_meshes(const void* const* blobs, const size_t* sizes, int
     }
     ms.hdrStart[n] = (int)out.hdrRoot.size();
     ms.numTris = (int)out.tris.size(); ms.numNodes = (int)out.nodes.size(); ms.numHdrs = (int)out.hdrRoot.size();
+    {   // free box (rl_mesh.h MeshSet::freeMn/freeMx): largest s with [-sX, sX] x [-sY, sY] x (-inf, inf) clear of every leaf box
+        const float PAD = 0.05f;  // > the 0.01 ray-walk padding
+        float X = 0.f, Y = 0.f;
+        for (const BvhNode& nd : out.nodes) if (nd.tri >= 0) {
+            X = std::max(X, std::max(std::fabs(nd.mn[0]), std::fabs(nd.mx[0])));
+            Y = std::max(Y, std::max(std::fabs(nd.mn[1]), std::fabs(nd.mx[1])));
+        }
+        auto touches = [&](float s) {
+            for (const BvhNode& nd : out.nodes) if (nd.tri >= 0) {
+                if (nd.mx[0] + PAD >= -s * X && nd.mn[0] - PAD <= s * X && nd.mx[1] + PAD >= -s * Y && nd.mn[1] - PAD <= s * Y) return true;
+            }
+            return false;
+        };
+        ms.freeMn = V3(1, 1, 1); ms.freeMx = V3(-1, -1, -1);
+        if (!out.nodes.empty() && X > 0.f && Y > 0.f && !touches(0.f)) {
+            float lo = 0.f, hi = 1.f;
+            for (int it = 0; it < 24; it++) { float mid = 0.5f * (lo + hi); if (touches(mid)) hi = mid; else lo = mid; }
+            ms.freeMn = V3(-lo * X, -lo * Y, -1e30f); ms.freeMx = V3(lo * X, lo * Y, 1e30f);
+        }
+    }
     out.triFlags.assign(out.tris.size(), 0);
     out.triEdgeAngles.assign(out.tris.size() * 3, 6.283185307179586232f);
     host_build_edge_info(out);
@@ -291,6 +312,24 @@ inline void host_build_tables(Tables& tb) {
         {3584, 2484, 70}, {0, 2816, 70}, {-940, 3308, 70}, {940, 3308, 70}, {-1792, 4184, 70}, {1792, 4184, 70}, {0, 4240, 70}};
     for (int i = 0; i < 6; i++) for (int k = 0; k < 3; k++) tb.padPos[i * 3 + k] = BIG[i][k];
     for (int i = 0; i < 28; i++) for (int k = 0; k < 3; k++) tb.padPos[(6 + i) * 3 + k] = SMALL[i][k];
+    for (int i = 0; i < 34 * 3; i++) tb.padPosBT[i] = tb.padPos[i] * UU2BT;
+    {   // BoostPadGrid: pad cell + the clamped 3x3 neighbourhood rule of BoostPadGrid::CheckCollision (BoostPadGrid.cpp:5-25)
+        const int CELLS_X = 8, CELLS_Y = 10;
+        const int CELL_SIZE_X = (int)(4096.f / (CELLS_X / 2)), CELL_SIZE_Y = (int)(5120.f / (CELLS_Y / 2));
+        for (int iy = -1; iy <= CELLS_Y; iy++)
+            for (int ix = -1; ix <= CELLS_X; ix++) {
+                uint64_t mask = 0;
+                int lox = ix - 1 > 0 ? ix - 1 : 0, hix = ix + 1 < CELLS_X - 1 ? ix + 1 : CELLS_X - 1;
+                int loy = iy - 1 > 0 ? iy - 1 : 0, hiy = iy + 1 < CELLS_Y - 1 ? iy + 1 : CELLS_Y - 1;
+                for (int i = 0; i < 34; i++) {
+                    int px = (int)(tb.padPos[i * 3] / CELL_SIZE_X + (CELLS_X / 2));
+                    int py = (int)(tb.padPos[i * 3 + 1] / CELL_SIZE_Y + (CELLS_Y / 2));
+                    if (px >= lox && px <= hix && py >= loy && py <= hiy) mask |= 1ULL << i;
+                }
+                int cell = (ix + 1) + (CELLS_X + 2) * (iy + 1);
+                tb.padCellMask[cell * 2] = (uint32_t)mask; tb.padCellMask[cell * 2 + 1] = (uint32_t)(mask >> 32);
+            }
+    }
     // CommonValues::BOOST_LOCATIONS (G/Utils/CommonValues.h:40-75)
     static const float LOC[34][2] = {
         {0, -4240}, {-1792, -4184}, {1792, -4184}, {-3072, -4096}, {3072, -4096}, {-940, -3308}, {940, -3308}, {0, -2816}, {-3584, -2484},

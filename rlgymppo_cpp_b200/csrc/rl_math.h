@@ -25,6 +25,13 @@ constexpr float kPi = 3.14159265358979323846f;
 constexpr float kHalfPi = 1.57079632679489661923f;
 constexpr float kEps = 1.1920928955078125e-7f;  // FLT_EPSILON == SIMD_EPSILON
 
+// libm calls go through out-of-line wrappers: the device versions carry long argument-reduction slow paths and the role
+// kernel is instruction-cache bound, so each must exist ONCE in the image (same results as the inlined calls).
+RL_HD RL_NOINLINE float rl_sin(float x);
+RL_HD RL_NOINLINE float rl_cos(float x);
+RL_HD RL_NOINLINE float rl_atan2(float y, float x);
+RL_HD RL_NOINLINE float rl_asin(float x);
+
 struct V3 {
     float x, y, z;
     RL_HDI V3() : x(0), y(0), z(0) {}
@@ -137,15 +144,15 @@ RL_HDI M3 quat_to_mat(Quat q) {
 // btQuaternion(axis, angle) -> matrix; used for the wheel steering transform
 RL_HDI Quat quat_axis_angle(V3 axis, float angle) {
     float d = len(axis);
-    float s = sinf(angle * 0.5f) / d;
-    return Quat(axis.x * s, axis.y * s, axis.z * s, cosf(angle * 0.5f));
+    float s = rl_sin(angle * 0.5f) / d;
+    return Quat(axis.x * s, axis.y * s, axis.z * s, rl_cos(angle * 0.5f));
 }
 
 // btMatrix3x3::setEulerYPR(yaw, pitch, roll) == setEulerZYX(roll, pitch, yaw)
-RL_HDI M3 euler_ypr_to_mat(float yaw, float pitch, float roll) {
+RL_HD RL_NOINLINE inline M3 euler_ypr_to_mat(float yaw, float pitch, float roll) {
     float eulerX = roll, eulerY = pitch, eulerZ = yaw;
-    float ci = cosf(eulerX), cj = cosf(eulerY), ch = cosf(eulerZ);
-    float si = sinf(eulerX), sj = sinf(eulerY), sh = sinf(eulerZ);
+    float ci = rl_cos(eulerX), cj = rl_cos(eulerY), ch = rl_cos(eulerZ);
+    float si = rl_sin(eulerX), sj = rl_sin(eulerY), sh = rl_sin(eulerZ);
     float cc = ci * ch, cs = ci * sh, sc = si * ch, ss = si * sh;
     return M3(V3(cj * ch, sj * sc - cs, sj * cc + ss), V3(cj * sh, sj * ss + cc, sj * cs - sc),
               V3(-sj, cj * si, cj * ci));
@@ -165,6 +172,11 @@ RL_HDI V3 ref_normalized(V3 v) {
 }
 RL_HDI float ref_dot(V3 a, V3 b) { return ((a.x * b.x + a.y * b.y) + a.z * b.z) + 0.f * 0.f; }
 RL_HDI V3 to_uu(V3 v) { return V3(v.x * 50.f, v.y * 50.f, v.z * 50.f); }
+
+RL_HD RL_NOINLINE inline float rl_sin(float x) { return sinf(x); }
+RL_HD RL_NOINLINE inline float rl_cos(float x) { return cosf(x); }
+RL_HD RL_NOINLINE inline float rl_atan2(float y, float x) { return atan2f(y, x); }
+RL_HD RL_NOINLINE inline float rl_asin(float x) { return asinf(x); }
 
 // piecewise-linear curves (reference Math.cpp:7-38 LinearPieceCurve::GetOutput)
 template <int N>

@@ -58,7 +58,7 @@ RL_HDI void plane_space(V3 n, V3& p, V3& q) {
     }
 }
 
-RL_HD inline void setup_contact_row(Row& r, const SolverBody* sb, int ia, int ib, V3 n, V3 rel1, V3 rel2, float dist, float restitutionCoef, float frictionCoef, int special) {
+RL_HD RL_NOINLINE inline void setup_contact_row(Row& r, const SolverBody* sb, int ia, int ib, V3 n, V3 rel1, V3 rel2, float dist, float restitutionCoef, float frictionCoef, int special) {
     const float invDt = 1.f / kTickTime;
     bool hasA = ia >= 0, hasB = ib >= 0;
     r.a = ia; r.b = ib;
@@ -98,7 +98,7 @@ RL_HD inline void setup_contact_row(Row& r, const SolverBody* sb, int ia, int ib
     r.frictionIndex = -1;
 }
 
-RL_HD inline void setup_friction_row(Row& r, const SolverBody* sb, int ia, int ib, V3 axis, V3 rel1, V3 rel2, float friction, int contactIndex) {
+RL_HD RL_NOINLINE inline void setup_friction_row(Row& r, const SolverBody* sb, int ia, int ib, V3 axis, V3 rel1, V3 rel2, float friction, int contactIndex) {
     bool hasA = ia >= 0, hasB = ib >= 0;
     r.a = ia; r.b = ib;
     r.friction = friction; r.applied = 0.f; r.appliedPush = 0.f;
@@ -166,8 +166,8 @@ RL_HD inline void integrate_transform(V3& pos, M3& rot, V3 linvel, V3 angvel, fl
     if (fAngle * dt > ANGULAR_MOTION_THRESHOLD) fAngle = ANGULAR_MOTION_THRESHOLD / dt;
     V3 axis;
     if (fAngle < 0.001f) axis = angvel * (0.5f * dt - (dt * dt * dt) * 0.020833333333f * fAngle * fAngle);
-    else axis = angvel * (sinf(0.5f * fAngle * dt) / fAngle);
-    Quat dorn(axis.x, axis.y, axis.z, cosf(fAngle * dt * 0.5f));
+    else axis = angvel * (rl_sin(0.5f * fAngle * dt) / fAngle);
+    Quat dorn(axis.x, axis.y, axis.z, rl_cos(fAngle * dt * 0.5f));
     Quat orn0 = mat_to_quat(rot);
     Quat pred = dorn * orn0;
     float l2 = pred.x * pred.x + pred.y * pred.y + pred.z * pred.z + pred.w * pred.w;
@@ -178,7 +178,7 @@ RL_HD inline void integrate_transform(V3& pos, M3& rot, V3 linvel, V3 angvel, fl
 }
 
 // solveGroup for every awake body of the arena.  bodies: 0 ball, 1+c cars.
-RL_HD inline void solve_arena(SolverBody* sb, int numBodies, ContactSet& cs) {
+RL_HD RL_NOINLINE inline void solve_arena(SolverBody* sb, int numBodies, ContactSet& cs) {
     Row rows[kMaxRows];
     Row fric[kMaxRows];
     int nRows = 0, nFric = 0;

@@ -131,15 +131,50 @@ struct BallS {
     int32_t updateCounterLo;  // BallState::updateCounter (only compared, 32 bits suffice per episode)
 };
 
-struct PadS {
-    int32_t isActive;
-    float cooldown;
-    int32_t prevLockedCarId;
+// All 34 boost pads of an arena (R/Sim/BoostPad/BoostPad.h BoostPadState x 34) as bit masks + sparse cooldowns: a tick
+// only touches the pads that are cooling down or that a car is near.
+//   active  bit i : BoostPadState::isActive
+//   cooling bit i : cooldown[i] > 0
+//   locked byte i : prevLockedCarID (car index + 1, 0 = none)
+struct PadsS {
+    uint32_t activeLo, activeHi;
+    uint32_t coolingLo, coolingHi;
+    float cooldown[kNumPads];
+    uint32_t locked[(kNumPads + 3) / 4];
 };
+constexpr uint64_t kAllPadsMask = (1ULL << kNumPads) - 1;
+RL_HDI uint64_t pads_active(const PadsS& p) { return ((uint64_t)p.activeHi << 32) | p.activeLo; }
+RL_HDI uint64_t pads_cooling(const PadsS& p) { return ((uint64_t)p.coolingHi << 32) | p.coolingLo; }
+RL_HDI void pads_set_active(PadsS& p, uint64_t m) { p.activeLo = (uint32_t)m; p.activeHi = (uint32_t)(m >> 32); }
+RL_HDI void pads_set_cooling(PadsS& p, uint64_t m) { p.coolingLo = (uint32_t)m; p.coolingHi = (uint32_t)(m >> 32); }
+RL_HDI int pad_locked(const PadsS& p, int i) { return (int)((p.locked[i >> 2] >> ((i & 3) * 8)) & 0xffu); }
+RL_HDI void pad_set_locked(PadsS& p, int i, int v) {
+    uint32_t sh = (uint32_t)(i & 3) * 8;
+    p.locked[i >> 2] = (p.locked[i >> 2] & ~(0xffu << sh)) | ((uint32_t)(v & 0xff) << sh);
+}
+RL_HDI void pads_reset(PadsS& p) {  // all active, no cooldown, nobody locked (Match.cpp:66-67 / fresh arena)
+    pads_set_active(p, kAllPadsMask); pads_set_cooling(p, 0);
+    for (int i = 0; i < kNumPads; i++) p.cooldown[i] = 0.f;
+    for (int i = 0; i < (kNumPads + 3) / 4; i++) p.locked[i] = 0u;
+}
+RL_HDI void pad_set(PadsS& p, int i, bool isActive, float cooldown, int prevLockedCarId) {
+    uint64_t bit = 1ULL << i;
+    pads_set_active(p, isActive ? (pads_active(p) | bit) : (pads_active(p) & ~bit));
+    pads_set_cooling(p, cooldown > 0 ? (pads_cooling(p) | bit) : (pads_cooling(p) & ~bit));
+    p.cooldown[i] = cooldown;
+    pad_set_locked(p, i, prevLockedCarId);
+}
+RL_HDI int lowest_bit(uint64_t m) {
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)m) - 1;
+#else
+    return __builtin_ctzll(m);
+#endif
+}
 
 struct ArenaS {
     BallS ball;
-    PadS pads[kNumPads];
+    PadsS pads;
     int32_t tickLo, tickHi;  // Arena::tickCount
     // GameEventTracker persistent info
     float shotCooldown;

@@ -10,36 +10,43 @@ namespace rl {
 // ---- boost pads --------------------------------------------------------------------------------
 RL_HDI bool pad_is_big(int i) { return i < kNumPadsBig; }
 
+// BoostPad::_PreTickUpdate for all pads (BoostPad.cpp:51-58): only pads with cooldown > 0 are touched, then
+// isActive = (cooldown == 0) for every pad
 RL_HD inline void pads_pre_tick(ArenaS& a) {
-    for (int i = 0; i < kNumPads; i++) {
-        PadS& p = a.pads[i];
-        if (p.cooldown > 0) p.cooldown = fmaxf_(p.cooldown - kTickTime, 0.f);
-        p.isActive = (p.cooldown == 0);
+    uint64_t cooling = pads_cooling(a.pads);
+    for (uint64_t m = cooling; m; m &= m - 1) {
+        int i = lowest_bit(m);
+        float cd = fmaxf_(a.pads.cooldown[i] - kTickTime, 0.f);
+        a.pads.cooldown[i] = cd;
+        if (cd == 0.f) cooling &= ~(1ULL << i);
     }
+    pads_set_cooling(a.pads, cooling);
+    pads_set_active(a.pads, ~cooling & kAllPadsMask);
 }
 
-// BoostPadGrid::CheckCollision + BoostPad::_CheckCollide; locked[] = curLockedCar (car index + 1, 0 none)
-RL_HD inline void pads_check_car(const ArenaS& a, const Tables& tb, const CarConsts& k, int ci, int32_t* locked) {
+// BoostPadGrid::CheckCollision + BoostPad::_CheckCollide (BoostPadGrid.cpp:5-25, BoostPad.cpp:60-92) for one car:
+// returns the mask of pads the car is colliding with this tick. The 3x3 cell neighbourhood is a table lookup
+// (Tables::padCellMask, built with the reference's index rule).
+RL_HD inline uint64_t pads_check_car(const ArenaS& a, const Tables& tb, const CarConsts& k, int ci) {
     const CarS& c = a.cars[ci];
-    if (c.isDemoed || c.boost >= 100) return;
+    if (c.isDemoed || c.boost >= 100) return 0;
     V3 carPos = c.pos * BT2UU;
     const float EXTENT_Z = C::PAD_CYL_HEIGHT + 250.f;
-    if (carPos.z > EXTENT_Z) return;
+    if (carPos.z > EXTENT_Z) return 0;
     const int CELLS_X = 8, CELLS_Y = 10;
     const int CELL_SIZE_X = (int)(4096.f / (CELLS_X / 2)), CELL_SIZE_Y = (int)(5120.f / (CELLS_Y / 2));
     int indexX = (int)(carPos.x / CELL_SIZE_X + (CELLS_X / 2));
     int indexY = (int)(carPos.y / CELL_SIZE_Y + (CELLS_Y / 2));
-    for (int i = 0; i < kNumPads; i++) {
-        V3 pp(tb.padPos[i * 3 + 0], tb.padPos[i * 3 + 1], tb.padPos[i * 3 + 2]);
-        int px = (int)(pp.x / CELL_SIZE_X + (CELLS_X / 2));
-        int py = (int)(pp.y / CELL_SIZE_Y + (CELLS_Y / 2));
-        int lox = indexX - 1 > 0 ? indexX - 1 : 0, hix = indexX + 1 < CELLS_X - 1 ? indexX + 1 : CELLS_X - 1;
-        int loy = indexY - 1 > 0 ? indexY - 1 : 0, hiy = indexY + 1 < CELLS_Y - 1 ? indexY + 1 : CELLS_Y - 1;
-        if (px < lox || px > hix || py < loy || py > hiy) continue;
-        V3 posBT = pp * UU2BT;
+    if (indexX < -1 || indexX > CELLS_X || indexY < -1 || indexY > CELLS_Y) return 0;
+    int cell = (indexX + 1) + (CELLS_X + 2) * (indexY + 1);
+    uint64_t cand = ((uint64_t)tb.padCellMask[cell * 2 + 1] << 32) | tb.padCellMask[cell * 2];
+    uint64_t hit = 0;
+    for (uint64_t m = cand; m; m &= m - 1) {
+        int i = lowest_bit(m);
+        V3 posBT(tb.padPosBT[i * 3 + 0], tb.padPosBT[i * 3 + 1], tb.padPosBT[i * 3 + 2]);
         bool big = pad_is_big(i);
         bool colliding = false;
-        if (a.pads[i].prevLockedCarId == ci + 1) {
+        if (pad_locked(a.pads, i) == ci + 1) {
             float boxRad = (big ? C::PAD_BOX_RAD_BIG : C::PAD_BOX_RAD_SMALL) * UU2BT;
             V3 boxMin = posBT - V3(boxRad, boxRad, 0), boxMax = posBT + V3(boxRad, boxRad, C::PAD_BOX_HEIGHT * UU2BT);
             // car AABB: compound -> child box AABB
@@ -52,155 +59,250 @@ RL_HD inline void pads_check_car(const ArenaS& a, const Tables& tb, const CarCon
             float dx = c.pos.x - posBT.x, dy = c.pos.y - posBT.y;
             if (dx * dx + dy * dy < rad * rad) colliding = fabsf(c.pos.z - posBT.z) < (C::PAD_CYL_HEIGHT * UU2BT);
         }
-        if (colliding) locked[i] = ci + 1;
+        if (colliding) hit |= 1ULL << i;
     }
+    return hit;
 }
 
-RL_HD inline void pads_post_tick(ArenaS& a, const int32_t* locked) {
-    for (int i = 0; i < kNumPads; i++) {
-        PadS& p = a.pads[i];
-        int lockedId = 0;
-        if (locked[i]) {
-            lockedId = locked[i];
-            if (p.isActive) {
-                CarS& c = a.cars[locked[i] - 1];
-                float add = pad_is_big(i) ? C::PAD_BOOST_BIG : C::PAD_BOOST_SMALL;
-                c.boost = fminf_(c.boost + add, C::BOOST_MAX);
-                p.isActive = 0;
-                p.cooldown = pad_is_big(i) ? C::PAD_COOLDOWN_BIG : C::PAD_COOLDOWN_SMALL;
-            }
+// BoostPad::_PostTickUpdate (BoostPad.cpp:94-108): hitMask[ci] from pads_check_car; the LAST car in _cars order that
+// collides with a pad locks it (BoostPad.cpp:88 overwrites _internalState.curLockedCar)
+RL_HD inline void pads_post_tick(ArenaS& a, const SimCfg& cfg, const uint64_t* hitMask) {
+    uint64_t any = 0;
+    for (int c = 0; c < cfg.numCars; c++) any |= hitMask[c];
+    for (int i = 0; i < (kNumPads + 3) / 4; i++) a.pads.locked[i] = 0u;
+    if (!any) return;
+    uint64_t active = pads_active(a.pads), cooling = pads_cooling(a.pads);
+    for (uint64_t m = any; m; m &= m - 1) {
+        int i = lowest_bit(m);
+        int lockedCar = -1;
+        for (int p = 0; p < cfg.numCars; p++) { int ci = cfg.playerOrder[p]; if ((hitMask[ci] >> i) & 1ULL) lockedCar = ci; }
+        if ((active >> i) & 1ULL) {
+            CarS& c = a.cars[lockedCar];
+            float add = pad_is_big(i) ? C::PAD_BOOST_BIG : C::PAD_BOOST_SMALL;
+            c.boost = fminf_(c.boost + add, C::BOOST_MAX);
+            active &= ~(1ULL << i);
+            a.pads.cooldown[i] = pad_is_big(i) ? C::PAD_COOLDOWN_BIG : C::PAD_COOLDOWN_SMALL;
+            cooling |= 1ULL << i;
         }
-        p.prevLockedCarId = lockedId;
+        pad_set_locked(a.pads, i, lockedCar + 1);
     }
+    pads_set_active(a.pads, active); pads_set_cooling(a.pads, cooling);
 }
 
 #ifdef RL_DEBUG_CONTACTS
 static ContactSet g_dbg_contacts;
 #endif
 
-// ---- one physics tick -----------------------------------------------------------------------------
-RL_HD RL_NOINLINE void arena_tick(ArenaS& a, const SimCfg& cfg, const MeshSet& ms, const Tables& tb, int firstTickOfStep) {
-    const float dt = kTickTime;
-    const CarConsts k = car_consts();
-    const Thresholds thr = contact_thresholds(k);
-    TickW tw;
-    tw.ballVelCache = V3(); tw.ballForce = V3();
-    int64_t tick = get_i64(a.tickLo, a.tickHi);
-    const int P = cfg.numCars;
+// ---- one physics tick, split by ROLE ------------------------------------------------------------------------------
+// Arena::Step (R/Sim/Arena/Arena.cpp:716-812) + btDiscreteDynamicsWorld::internalSingleStepSimulation
+// (B/BulletDynamics/Dynamics/btDiscreteDynamicsWorld.cpp:393-437) for one arena, executed by 1 + numCars roles:
+// role 0 = ball / arena, role 1+c = car c.  On the device each role of an arena is one lane of a different warp of the
+// same block and the phases are separated by __syncthreads() (engine.cu k_roles); the host test build runs the same
+// phases role after role (arena_tick).  Phase order and who-writes-what:
+//
+//   S0  every role snapshots its own body into the exchange (TickX)                                  | barrier B1
+//   P1  car c : Car::_PreTickUpdate (wheel rays read the snapshots), gravity, hitbox AABB,
+//               car-ball, hitbox-mesh, hitbox-plane narrowphase -> own contact segments
+//       ball  : pads pre-tick, sphere-mesh, sphere-plane narrowphase -> own contact segment          | barrier B2
+//   P2  ball  : ball damping, car-car pairs (+bump/demo callbacks), gather contacts in the reference's manifold
+//               order, sequential-impulse solve, write velocities / pushed transforms back,
+//               integrate + finish the ball, tick count                                              | barrier B3
+//   P3  car c : integrate transform, Car::_PostTickUpdate/_FinishPhysicsTick, boost-pad overlap mask | barrier B4
+//   P4  ball  : BoostPad::_PostTickUpdate (pick-ups)
+struct Thresholds;
 
+// segment pointers inside one arena's contact scratch
+RL_HDI Contact* seg_ball(Contact* scratch) { return scratch; }
+RL_HDI Contact* seg_car(Contact* scratch, int c) { return scratch + kSegBall + c * kSegCar; }
+RL_HDI Contact* seg_pair(Contact* scratch, int ncars) { return scratch + kSegBall + ncars * kSegCar; }
+
+RL_HDI uint32_t respawn_rnd(const ArenaS& a, int ci) {
+    uint64_t z = (((uint64_t)a.rngHi << 32) | a.rngLo) + 0x9E3779B97F4A7C15ULL * (uint64_t)(uint32_t)(a.tickLo + 1) + 0xD1B54A32D192ED03ULL * (uint64_t)(ci + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return (uint32_t)((z ^ (z >> 31)) >> 32);
+}
+
+RL_HDI void tick_s0_car(const ArenaS& a, TickX x, int c) {
+    const CarS& car = a.cars[c];
+    CarX& o = x.car[c];
+    o.pos = car.pos; o.vel = car.vel; o.angvel = car.angvel; o.rot = car.rot; o.demoed = car.isDemoed;
+}
+RL_HDI void tick_s0_ball(const ArenaS& a, TickX x) {
+    x.h->ballPos = a.ball.pos; x.h->ballVel = a.ball.vel; x.h->ballAngvel = a.ball.angvel;
     // ball zero-velocity sleeping (Arena.cpp:721-727)
-    bool ballActive = !(len2(a.ball.vel) == 0.f && len2(a.ball.angvel) == 0.f);
+    x.h->ballActive = !(len2(a.ball.vel) == 0.f && len2(a.ball.angvel) == 0.f);
+}
 
+RL_HD inline void tick_p1_car(ArenaS& a, TickX x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, const Thresholds& thr, int c, CarW& w,
+                              Contact* scratch, int firstTickOfStep) {
+    CarS& car = a.cars[c];
+    CarX& o = x.car[c];
     // activation state / contact response are decided at the top of Car::_PreTickUpdate, before a possible respawn,
     // and a car demolished DURING this tick still responds and integrates until the next tick (Car.cpp:38-41,69-87)
-    int32_t noResponse[kMaxCars];
-    for (int c = 0; c < P; c++) noResponse[c] = a.cars[c].isDemoed;
-    for (int p = 0; p < P; p++) { int ci = cfg.playerOrder[p]; car_pre_tick(a, cfg, ms, k, ci, tw.cars[ci]); }
-    if (P > 0) pads_pre_tick(a);
+    o.noResponse = car.isDemoed;
+    o.ballVelCache = V3(); o.velCache = V3();
+    car_pre_tick(car, x, cfg, ms, k, c, w, respawn_rnd(a, c));
+    if (!o.noResponse) w.force += V3(0.f * UU2BT, 0.f * UU2BT, C::GRAVITY_Z * UU2BT) * C::CAR_MASS;  // applyGravity on active bodies
+    o.force = w.force; o.torque = w.torque;
+    V3 center = car.pos + car.rot * k.hitboxOffset;
+    V3 ext(dot(vabs(car.rot.r[0]), k.halfExt), dot(vabs(car.rot.r[1]), k.halfExt), dot(vabs(car.rot.r[2]), k.halfExt));
+    o.cmn = center - ext; o.cmx = center + ext;
 
-    // ---- btDiscreteDynamicsWorld::stepSimulation ----
-    // applyGravity on active bodies
-    const V3 g(0.f * UU2BT, 0.f * UU2BT, C::GRAVITY_Z * UU2BT);
-    if (ballActive) tw.ballForce += g * C::BALL_MASS;
-    for (int c = 0; c < P; c++) if (!noResponse[c]) tw.cars[c].force += g * C::CAR_MASS;
+    CollideCtx cx; cx.a = &a; cx.cfg = &cfg; cx.tx = x; cx.k = &k; cx.tick = get_i64(a.tickLo, a.tickHi); cx.firstTickOfStep = firstTickOfStep;
+    cx.ballPos = x.h->ballPos; cx.ballVel = x.h->ballVel * cfg.ballDampFactor;  // predictUnconstraintMotion damping precedes the narrowphase
+    // car-ball (manifold order: all car-ball pairs precede the car-world pairs)
+    ContactSink cb = make_sink(seg_car(scratch, c), 1);
+    float ballAabb = C::BALL_RADIUS * UU2BT + 0.08f;
+    V3 bmn = cx.ballPos - V3(ballAabb, ballAabb, ballAabb), bmx = cx.ballPos + V3(ballAabb, ballAabb, ballAabb);
+    bool overlapBall = !(bmn.x > o.cmx.x || bmx.x < o.cmn.x || bmn.y > o.cmx.y || bmx.y < o.cmn.y || bmn.z > o.cmx.z || bmx.z < o.cmn.z);
+    if (overlapBall && !(!x.h->ballActive && o.noResponse)) car_ball(cx, cb, c, fminf_(thr.ball, thr.car));
+    o.nCarBall = cb.n;
+    ContactSink cw = make_sink(seg_car(scratch, c) + 1, kSegCarWorld);
+    if (w.cands.n >= 0) box_meshes_candidates(cx, cw, ms, w.cands, c, thr.car);
+    else box_meshes(cx, cw, ms, c, thr.car);
+#pragma unroll 1
+    for (int p = 0; p < 4; p++) box_plane(cx, cw, c, p, thr.car);
+    o.nCarWorld = cw.n;
+}
+
+RL_HD inline void tick_p1_ball(ArenaS& a, TickX x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, const Thresholds& thr, Contact* scratch) {
+    if (cfg.numCars > 0) pads_pre_tick(a);
+    CollideCtx cx; cx.a = &a; cx.cfg = &cfg; cx.tx = x; cx.k = &k; cx.tick = get_i64(a.tickLo, a.tickHi); cx.firstTickOfStep = 0;
+    cx.ballPos = x.h->ballPos; cx.ballVel = x.h->ballVel * cfg.ballDampFactor;
+    ContactSink cs = make_sink(seg_ball(scratch), kSegBall);
+    // a sleeping ball vs the (always "sleeping") static bodies is skipped by btCollisionDispatcher::needsCollision
+    // (both inactive): on the tick it is woken by a car it has no world contacts yet.
+    if (x.h->ballActive) {
+        float ballR = C::BALL_RADIUS * UU2BT;
+        sphere_meshes(cx, cs, ms, cx.ballPos, ballR, thr.ball);
+#pragma unroll 1
+        for (int p = 0; p < 4; p++) sphere_plane(cx, cs, cx.ballPos, ballR, p, thr.ball);
+    }
+    x.h->nBall = cs.n;
+}
+
+RL_HD inline void tick_p2_solve(ArenaS& a, TickX x, const SimCfg& cfg, const CarConsts& k, const Thresholds& thr, Contact* scratch, int firstTickOfStep) {
+    const float dt = kTickTime;
+    const int P = cfg.numCars;
+    const int64_t tick = get_i64(a.tickLo, a.tickHi);
+    const bool ballActive = x.h->ballActive != 0;
+    const float ballR = C::BALL_RADIUS * UU2BT;
     // predictUnconstraintMotion: damping (ball only: linear 0.03)
     a.ball.vel = a.ball.vel * cfg.ballDampFactor;
 
-    // collision detection, in the reference's pair order (btRSBroadphase::calculateOverlappingPairs)
-    ContactSet cs; cs.n = 0; cs.overflow = 0;
-    CollideCtx cx; cx.a = &a; cx.cfg = &cfg; cx.tw = &tw; cx.k = &k; cx.tick = tick; cx.firstTickOfStep = firstTickOfStep;
-    for (int c = 0; c < kMaxCars; c++) cx.noResponse[c] = c < P ? noResponse[c] : 1;
-    float ballR = C::BALL_RADIUS * UU2BT;
-    float ballAabb = ballR + 0.08f;
-    // a sleeping ball vs the (always "sleeping") static bodies is skipped by btCollisionDispatcher::needsCollision
-    // (both inactive): on the tick it is woken by a car it has no world contacts yet.
-    if (ballActive) {
-        sphere_meshes(cx, cs, ms, a.ball.pos, ballR, thr.ball);
-        for (int p = 0; p < 4; p++) sphere_plane(cx, cs, a.ball.pos, ballR, p, thr.ball);
-    }
+    // islands merge on broadphase overlap: a sleeping ball is woken by any responding car whose AABB overlaps
     bool ballWoken = false;
-    V3 bmn = a.ball.pos - V3(ballAabb, ballAabb, ballAabb), bmx = a.ball.pos + V3(ballAabb, ballAabb, ballAabb);
-    V3 cmn[kMaxCars], cmx[kMaxCars];
-    for (int c = 0; c < P; c++) {
-        const CarS& car = a.cars[c];
-        V3 center = car.pos + car.rot * k.hitboxOffset;
-        V3 ext(dot(vabs(car.rot.r[0]), k.halfExt), dot(vabs(car.rot.r[1]), k.halfExt), dot(vabs(car.rot.r[2]), k.halfExt));
-        cmn[c] = center - ext; cmx[c] = center + ext;
-    }
-    auto overlap = [](V3 amn, V3 amx, V3 bmn_, V3 bmx_) {
-        return !(amn.x > bmx_.x || amx.x < bmn_.x || amn.y > bmx_.y || amx.y < bmn_.y || amn.z > bmx_.z || amx.z < bmn_.z);
-    };
-    float thrCarBall = fminf_(thr.ball, thr.car);
-    for (int c = 0; c < P; c++) {
-        if (!overlap(bmn, bmx, cmn[c], cmx[c])) continue;
-        if (!noResponse[c]) ballWoken = true;  // islands merge on broadphase overlap
-        if (!ballActive && noResponse[c]) continue;
-        car_ball(cx, cs, c, thrCarBall);
-    }
-    for (int c = 0; c < P; c++) {
-        box_meshes(cx, cs, ms, c, thr.car);
-        for (int p = 0; p < 4; p++) box_plane(cx, cs, c, p, thr.car);
-        for (int d = c + 1; d < P; d++) {
-            if (!overlap(cmn[c], cmx[c], cmn[d], cmx[d])) continue;
-            car_car(cx, cs, c, d, thr.car);
+    {
+        float ballAabb = ballR + 0.08f;
+        V3 bmn = a.ball.pos - V3(ballAabb, ballAabb, ballAabb), bmx = a.ball.pos + V3(ballAabb, ballAabb, ballAabb);
+        for (int c = 0; c < P; c++) {
+            const CarX& o = x.car[c];
+            bool ov = !(bmn.x > o.cmx.x || bmx.x < o.cmn.x || bmn.y > o.cmx.y || bmx.y < o.cmn.y || bmn.z > o.cmx.z || bmx.z < o.cmn.z);
+            if (ov && !o.noResponse) ballWoken = true;
         }
     }
+    // car-car pairs in the reference's pair order; contacts of pair (c, d) carry a == 1 + c
+    CollideCtx cx; cx.a = &a; cx.cfg = &cfg; cx.tx = x; cx.k = &k; cx.tick = tick; cx.firstTickOfStep = firstTickOfStep;
+    cx.ballPos = x.h->ballPos; cx.ballVel = a.ball.vel;
+    ContactSink cp = make_sink(seg_pair(scratch, P), kSegPair);
+    for (int c = 0; c < P; c++)
+        for (int d = c + 1; d < P; d++) {
+            const CarX &oc = x.car[c], &od = x.car[d];
+            bool ov = !(oc.cmn.x > od.cmx.x || oc.cmx.x < od.cmn.x || oc.cmn.y > od.cmx.y || oc.cmx.y < od.cmn.y || oc.cmn.z > od.cmx.z || oc.cmx.z < od.cmn.z);
+            if (ov) car_car(cx, cp, c, d, thr.car);
+        }
+    x.h->nPair = cp.n;
 
-#ifdef RL_DEBUG_CONTACTS
-    g_dbg_contacts = cs;
+    int totalContacts = x.h->nBall + cp.n;
+    for (int c = 0; c < P; c++) totalContacts += x.car[c].nCarBall + x.car[c].nCarWorld;
+    const V3 gImp = V3(0.f * UU2BT, 0.f * UU2BT, C::GRAVITY_Z * UU2BT) * C::BALL_MASS;
+#ifndef RL_P2_FAST  // measured on B200 (profiles/r01c_ab.md): the extra branch costs more (code size) than it saves; off by default
+    totalContacts = 1;
 #endif
-    // ---- solve ----
-    SolverBody sb[1 + kMaxCars];
-    {
-        SolverBody& b = sb[0];
-        b.pos = a.ball.pos; b.rot = M3::identity();
-        b.linVel = a.ball.vel; b.angVel = a.ball.angvel;
-        b.invMass = 1.f / C::BALL_MASS;
-        float inertia = 0.4f * C::BALL_MASS * ballR * ballR;
-        float ii = 1.f / inertia;
-        b.invInertiaWorld = M3(V3(ii, 0, 0), V3(0, ii, 0), V3(0, 0, ii));
-        b.extForceImp = tw.ballForce * b.invMass * dt;
-        b.extTorqueImp = V3();
-        b.dLin = b.dAng = b.push = b.turn = V3();
-        b.active = ballActive || ballWoken;
+    if (totalContacts == 0) {
+        // no manifolds anywhere in the arena (the common tick): the solver degenerates to writeBackBodies
+        // (btSequentialImpulseConstraintSolver.cpp:1878-1904): v += 0 (deltas) then v += externalForceImpulse
+#ifdef RL_DEBUG_CONTACTS
+        g_dbg_contacts.n = 0; g_dbg_contacts.overflow = 0;
+#endif
+        for (int c = 0; c < P; c++) {
+            if (x.car[c].noResponse) continue;
+            CarS& car = a.cars[c];
+            M3 iiw = world_inertia(car.rot, k.invInertiaLocal);
+            car.vel = (car.vel + V3()) + x.car[c].force * k.invMass * dt;
+            car.angvel = (car.angvel + V3()) + tmul(x.car[c].torque, iiw) * dt;
+        }
+        if (ballActive || ballWoken) {
+            V3 ballForce;
+            if (ballActive) ballForce += gImp;
+            a.ball.vel = (a.ball.vel + V3()) + ballForce * (1.f / C::BALL_MASS) * dt;
+            a.ball.angvel = (a.ball.angvel + V3()) + V3();
+            a.ball.pos = a.ball.pos + a.ball.vel * dt;  // integrateTransformNoRot
+        }
+    } else {
+        // gather in manifold order: ball-world, car-ball (c ascending), then per car: car-world, car-car (c, d > c)
+        ContactSet cs; cs.n = 0; cs.overflow = 0;
+        auto take = [&](const Contact* src, int n) {
+            for (int i = 0; i < n; i++) {
+                if (cs.n < kMaxContacts) cs.c[cs.n++] = src[i];
+                else cs.overflow++;
+            }
+        };
+        take(seg_ball(scratch), x.h->nBall);
+        for (int c = 0; c < P; c++) take(seg_car(scratch, c), x.car[c].nCarBall);
+        for (int c = 0; c < P; c++) {
+            take(seg_car(scratch, c) + 1, x.car[c].nCarWorld);
+            const Contact* pr = seg_pair(scratch, P);
+            for (int i = 0; i < cp.n; i++) if (pr[i].a == 1 + c) take(pr + i, 1);
+        }
+#ifdef RL_DEBUG_CONTACTS
+        g_dbg_contacts = cs;
+#endif
+        SolverBody sb[1 + kMaxCars];
+        {
+            SolverBody& b = sb[0];
+            b.pos = a.ball.pos; b.rot = M3::identity();
+            b.linVel = a.ball.vel; b.angVel = a.ball.angvel;
+            b.invMass = 1.f / C::BALL_MASS;
+            float inertia = 0.4f * C::BALL_MASS * ballR * ballR;
+            float ii = 1.f / inertia;
+            b.invInertiaWorld = M3(V3(ii, 0, 0), V3(0, ii, 0), V3(0, 0, ii));
+            V3 ballForce;
+            if (ballActive) ballForce += gImp;
+            b.extForceImp = ballForce * b.invMass * dt;
+            b.extTorqueImp = V3();
+            b.dLin = b.dAng = b.push = b.turn = V3();
+            b.active = ballActive || ballWoken;
+        }
+        for (int c = 0; c < P; c++) {
+            SolverBody& b = sb[1 + c];
+            const CarS& car = a.cars[c];
+            b.pos = car.pos; b.rot = car.rot; b.linVel = car.vel; b.angVel = car.angvel;
+            b.invMass = k.invMass;
+            b.invInertiaWorld = world_inertia(car.rot, k.invInertiaLocal);
+            b.extForceImp = x.car[c].force * b.invMass * dt;
+            b.extTorqueImp = tmul(x.car[c].torque, b.invInertiaWorld) * dt;
+            b.dLin = b.dAng = b.push = b.turn = V3();
+            b.active = !x.car[c].noResponse;
+        }
+        solve_arena(sb, 1 + P, cs);
+        // write back; the cars integrate themselves in P3
+        for (int c = 0; c < P; c++) {
+            if (!sb[1 + c].active) continue;
+            CarS& car = a.cars[c];
+            car.vel = sb[1 + c].linVel; car.angvel = sb[1 + c].angVel;
+            car.pos = sb[1 + c].pos; car.rot = sb[1 + c].rot;
+        }
+        if (sb[0].active) {
+            a.ball.vel = sb[0].linVel; a.ball.angvel = sb[0].angVel;
+            a.ball.pos = sb[0].pos + a.ball.vel * dt;  // integrateTransformNoRot
+        }
     }
-    for (int c = 0; c < P; c++) {
-        SolverBody& b = sb[1 + c];
-        const CarS& car = a.cars[c];
-        b.pos = car.pos; b.rot = car.rot; b.linVel = car.vel; b.angVel = car.angvel;
-        b.invMass = k.invMass;
-        b.invInertiaWorld = tw.cars[c].invInertiaWorld;
-        b.extForceImp = tw.cars[c].force * b.invMass * dt;
-        b.extTorqueImp = tmul(tw.cars[c].torque, b.invInertiaWorld) * dt;
-        b.dLin = b.dAng = b.push = b.turn = V3();
-        b.active = !noResponse[c];
-    }
-    solve_arena(sb, 1 + P, cs);
-
-    // ---- integrateTransforms ----
-    if (sb[0].active) {
-        a.ball.vel = sb[0].linVel; a.ball.angvel = sb[0].angVel;
-        a.ball.pos = sb[0].pos + a.ball.vel * dt;  // integrateTransformNoRot
-    }
-    for (int c = 0; c < P; c++) {
-        if (!sb[1 + c].active) continue;
-        CarS& car = a.cars[c];
-        car.vel = sb[1 + c].linVel; car.angvel = sb[1 + c].angVel;
-        car.pos = sb[1 + c].pos; car.rot = sb[1 + c].rot;
-        integrate_transform(car.pos, car.rot, car.vel, car.angvel, dt);
-    }
-
-    // ---- post tick ----
-    int32_t locked[kNumPads];
-    for (int i = 0; i < kNumPads; i++) locked[i] = 0;
-    for (int p = 0; p < P; p++) {
-        int ci = cfg.playerOrder[p];
-        car_post_tick(a.cars[ci], tw.cars[ci]);
-        pads_check_car(a, tb, k, ci, locked);
-    }
-    if (P > 0) pads_post_tick(a, locked);
     // Ball::_FinishPhysicsTick (Ball.cpp:112-138)
-    if (!is_zero(tw.ballVelCache)) a.ball.vel += tw.ballVelCache;
+    V3 ballVelCache;
+    for (int c = 0; c < P; c++) ballVelCache += x.car[c].ballVelCache;
+    if (!is_zero(ballVelCache)) a.ball.vel += ballVelCache;
     {
         const float maxSpeed = C::BALL_MAX_SPEED * UU2BT;
         if (len2(a.ball.vel) > maxSpeed * maxSpeed) a.ball.vel = normalized(a.ball.vel) * maxSpeed;
@@ -210,18 +312,55 @@ RL_HD RL_NOINLINE void arena_tick(ArenaS& a, const SimCfg& cfg, const MeshSet& m
     set_i64(a.tickLo, a.tickHi, tick + 1);
 }
 
+RL_HD inline void tick_p3_car(ArenaS& a, TickX x, const Tables& tb, const CarConsts& k, int c, CarW& w) {
+    CarS& car = a.cars[c];
+    CarX& o = x.car[c];
+    if (!o.noResponse) integrate_transform(car.pos, car.rot, car.vel, car.angvel, kTickTime);
+    w.velCache = o.velCache;
+    car_post_tick(car, w);
+    uint64_t hit = pads_check_car(a, tb, k, c);
+    o.padHitLo = (uint32_t)hit; o.padHitHi = (uint32_t)(hit >> 32);
+}
+
+RL_HD inline void tick_p4_pads(ArenaS& a, TickX x, const SimCfg& cfg) {
+    if (cfg.numCars <= 0) return;
+    uint64_t hits[kMaxCars];
+    for (int c = 0; c < cfg.numCars; c++) hits[c] = ((uint64_t)x.car[c].padHitHi << 32) | x.car[c].padHitLo;
+    pads_post_tick(a, cfg, hits);
+}
+
+// scratch sizes for one arena (words / contacts)
+RL_HDI int tick_scratch_words(int ncars) { return tickx_words(ncars); }
+
+// Serial driver: the same phases, role after role.  Used by the host test build and by single-lane device paths.
+// xwords: tickx_words(numCars) uint32 words, scratch: contact_scratch_slots(numCars) contacts.
+RL_HD inline void arena_tick(ArenaS& a, const SimCfg& cfg, const MeshSet& ms, const Tables& tb, int firstTickOfStep, uint32_t* xwords, Contact* scratch) {
+    const CarConsts k = car_consts();
+    const Thresholds thr = contact_thresholds(k);
+    TickX x = make_tickx(xwords);
+    const int P = cfg.numCars;
+    CarW w[kMaxCars];
+    tick_s0_ball(a, x);
+    for (int c = 0; c < P; c++) tick_s0_car(a, x, c);
+    for (int c = 0; c < P; c++) tick_p1_car(a, x, cfg, ms, k, thr, c, w[c], scratch, firstTickOfStep);
+    tick_p1_ball(a, x, cfg, ms, k, thr, scratch);
+    tick_p2_solve(a, x, cfg, k, thr, scratch, firstTickOfStep);
+    for (int c = 0; c < P; c++) tick_p3_car(a, x, tb, k, c, w[c]);
+    tick_p4_pads(a, x, cfg);
+}
+
 // ---- Gym::Step (G/Gym.cpp:68-102) + GameInst::Step auto-reset --------------------------------------
 RL_HD inline void gym_step(ArenaS& a, const SimCfg& cfg, const MeshSet& ms, const Tables& tb, const int32_t* actionIdx,
-                           float* obsOut, float* rewardOut, uint8_t* doneOut) {
+                           float* obsOut, float* rewardOut, uint8_t* doneOut, uint32_t* xwords, Contact* scratch) {
     parse_actions(a, cfg, tb, actionIdx);
-    arena_tick(a, cfg, ms, tb, 1);
+    arena_tick(a, cfg, ms, tb, 1, xwords, scratch);
     event_tracker_update(a, cfg);
     snapshot_update(a, cfg);
     build_obs(a, cfg, tb, obsOut);
     bool done = compute_done(a, cfg);
     compute_rewards(a, cfg, rewardOut);
     *doneOut = done ? 1 : 0;
-    for (int t = 1; t < cfg.tickSkip; t++) arena_tick(a, cfg, ms, tb, 0);
+    for (int t = 1; t < cfg.tickSkip; t++) arena_tick(a, cfg, ms, tb, 0, xwords, scratch);
     if (done) {
         gym_reset(a, cfg);
         build_obs(a, cfg, tb, obsOut);

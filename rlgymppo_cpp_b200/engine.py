@@ -16,7 +16,7 @@ import numpy as np
 from . import abi, meshes
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "librlgym_b200.so")
+LIB_PATH = os.environ.get("RLG_B200_LIB") or os.path.join(_HERE, "csrc", "librlgym_b200.so")  # override: A/B builds while profiling
 
 EXPORTS = [
     "rlg_last_error", "rlg_abi_version", "rlg_sizeof_car_state", "rlg_sizeof_engine_cfg", "rlg_engine_cfg_default",

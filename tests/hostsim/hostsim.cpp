@@ -23,6 +23,8 @@ struct HostSim {
     std::vector<ArenaS> arenas;
     std::vector<float> obs, reward;
     std::vector<uint8_t> done;
+    std::vector<uint32_t> xw;       // one arena's role exchange (TickX)
+    std::vector<Contact> scratch;   // one arena's contact segments
 };
 
 static void bind_mesh(HostSim* h) {
@@ -42,6 +44,8 @@ void* hs_create(const rlg_engine_cfg* cfg, const void* const* blobs, const size_
         host_build_meshes(blobs, sizes, n, h->hm);
         bind_mesh(h);
         h->arenas.resize(cfg->num_arenas);
+        h->xw.assign(tickx_words(h->cfg.numCars), 0u);
+        h->scratch.resize(contact_scratch_slots(h->cfg.numCars));
         for (int a = 0; a < cfg->num_arenas; a++) arena_init(h->arenas[a], h->cfg.numCars, cfg->seed, (uint64_t)cfg->arena_id_base + a);
         h->obs.resize((size_t)cfg->num_arenas * h->cfg.numCars * h->cfg.obsSize);
         h->reward.resize((size_t)cfg->num_arenas * h->cfg.numCars);
@@ -65,7 +69,7 @@ void hs_set_state(void* p, int arena, const rlg_car_state* cars, const rlg_ball_
     ArenaS& a = h->arenas[arena];
     if (cars) for (int c = 0; c < h->cfg.numCars; c++) car_from_pod(a.cars[c], cars[c]);
     if (ball) ball_from_pod(a.ball, *ball);
-    if (pads) for (int i = 0; i < kNumPads; i++) { a.pads[i].isActive = pads[i].is_active != 0; a.pads[i].cooldown = pads[i].cooldown; a.pads[i].prevLockedCarId = pads[i].prev_locked_car_id; }
+    if (pads) for (int i = 0; i < kNumPads; i++) pad_from_pod(a.pads, i, pads[i]);
     if (tick >= 0) set_i64(a.tickLo, a.tickHi, tick);
 }
 void hs_get_state(void* p, int arena, rlg_car_state* cars, rlg_ball_state* ball, rlg_pad_state* pads, int64_t* tick) {
@@ -73,14 +77,14 @@ void hs_get_state(void* p, int arena, rlg_car_state* cars, rlg_ball_state* ball,
     ArenaS& a = h->arenas[arena];
     if (cars) for (int c = 0; c < h->cfg.numCars; c++) { memset(&cars[c], 0, sizeof(rlg_car_state)); car_to_pod(cars[c], a.cars[c], c, h->cfg.spawnOpponents); }
     if (ball) ball_to_pod(*ball, a.ball);
-    if (pads) for (int i = 0; i < kNumPads; i++) { pads[i].is_active = a.pads[i].isActive; pads[i].cooldown = a.pads[i].cooldown; pads[i].prev_locked_car_id = a.pads[i].prevLockedCarId; }
+    if (pads) for (int i = 0; i < kNumPads; i++) pad_to_pod(pads[i], a.pads, i);
     if (tick) *tick = get_i64(a.tickLo, a.tickHi);
 }
 void hs_tick(void* p, int arena, const rlg_controls* controls, int nticks) {
     HostSim* h = (HostSim*)p;
     ArenaS& a = h->arenas[arena];
     if (controls) for (int c = 0; c < h->cfg.numCars; c++) a.cars[c].controls = controls_from(controls[c]);
-    for (int t = 0; t < nticks; t++) arena_tick(a, h->cfg, h->ms, h->tb, 0);
+    for (int t = 0; t < nticks; t++) arena_tick(a, h->cfg, h->ms, h->tb, 0, h->xw.data(), h->scratch.data());
 }
 // Gym::Reset on one arena using whatever state the arena currently holds (no state setter)
 void hs_reset_from_current(void* p, int arena, float* obs) {
@@ -100,14 +104,14 @@ void hs_step(void* p, int arena, const int32_t* actions, float* obs, float* rewa
     HostSim* h = (HostSim*)p;
     ArenaS& a = h->arenas[arena];
     parse_actions(a, h->cfg, h->tb, actions);
-    arena_tick(a, h->cfg, h->ms, h->tb, 1);
+    arena_tick(a, h->cfg, h->ms, h->tb, 1, h->xw.data(), h->scratch.data());
     event_tracker_update(a, h->cfg);
     snapshot_update(a, h->cfg);
     build_obs(a, h->cfg, h->tb, obs);
     bool d = compute_done(a, h->cfg);
     compute_rewards(a, h->cfg, reward);
     *done = d;
-    for (int t = 1; t < h->cfg.tickSkip; t++) arena_tick(a, h->cfg, h->ms, h->tb, 0);
+    for (int t = 1; t < h->cfg.tickSkip; t++) arena_tick(a, h->cfg, h->ms, h->tb, 0, h->xw.data(), h->scratch.data());
 }
 void hs_eval_gym(void* p, int arena, const int32_t* actions, float* obs, float* reward, uint8_t* done) {
     HostSim* h = (HostSim*)p;
