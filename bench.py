@@ -304,7 +304,7 @@ def run_ours(args, rank, local_rank, world):
                     "call": "rlg_engine_step_host (Gym::Step with host buffers, uniform random host actions)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "k_step", "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": k_step_ms, "launches_timed": step_n,
+                         "kernel": "k_roles (fused Gym::Step)", "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": k_step_ms, "launches_timed": step_n,
                          "share_of_step": step_ms / total_ms, "peak_source": peak_src},
             "roofline_mlp": {"bound": "tensor", "achieved": mlp_tflops, "peak": tf_peak, "unit": "TFLOP/s",
                              "frac": (mlp_tflops / tf_peak) if mlp_tflops else None, "kernel": "k_mlp_infer",

@@ -183,9 +183,13 @@ __global__ void __maxnreg__(168) k_roles(const RolesArgs g) {
             else tick_p1_car(s, x, g.cfg, g.ms, k, thr, role - 1, w, scratch, first);
         }
         __syncthreads();  // B2
-        if (valid && role == 0) tick_p2_solve(s, x, g.cfg, k, thr, scratch, first);
+        bool self = false;
+        if (valid) {
+            if (role == 0) tick_p2_solve(s, x, g.cfg, k, thr, scratch, first);
+            else if ((self = tick_p2_car_self(s, x, g.cfg, k, role - 1, scratch))) tick_p3_car(s, x, *g.tb, k, role - 1, w);
+        }
         __syncthreads();  // B3
-        if (valid && role > 0) tick_p3_car(s, x, *g.tb, k, role - 1, w);
+        if (valid && role > 0 && !self) tick_p3_car(s, x, *g.tb, k, role - 1, w);
         __syncthreads();  // B4
         if (valid && role == 0) {
             tick_p4_pads(s, x, g.cfg);

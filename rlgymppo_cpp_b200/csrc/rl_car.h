@@ -164,7 +164,7 @@ RL_HD inline RayHit wheel_ray(const TickX& x, const SimCfg& cfg, const MeshSet& 
 // ---- btVehicleRL::updateVehicleFirst ---------------------------------------------------------
 RL_HD inline void vehicle_first(CarS& c, const TickX& x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, int ci, CarW& w) {
     V3 carFwd = c.rot.col(0), carRight = c.rot.col(1), carUp = c.rot.col(2);
-#pragma unroll 1
+    RL_WHEEL_LOOP
     for (int i = 0; i < 4; i++) {
         WheelW& wh = w.w[i];
         // updateWheelTransformsWS + updateWheelTransform: only the steered axle (basis column 1) is consumed later
@@ -231,7 +231,7 @@ RL_HD inline void vehicle_first(CarS& c, const TickX& x, const SimCfg& cfg, cons
 
     // calcFrictionImpulses (btVehicleRL.cpp:313-388) — consumes LAST tick's engine/brake/friction values
     float frictionScale = C::CAR_MASS / 3;
-#pragma unroll 1
+    RL_WHEEL_LOOP
     for (int i = 0; i < 4; i++) {
         WheelW& wh = w.w[i];
         if (wh.ground == -2) { wh.impulse = V3(); continue; }
@@ -333,7 +333,7 @@ RL_HD inline void update_wheels(CarS& c, CarW& w, int numWheelsInContact, float 
         steerAngle *= c.controls.steer;
         c.wheelSteer = steerAngle;
     }
-#pragma unroll 1
+    RL_WHEEL_LOOP
     for (int i = 0; i < 4; i++) {
         WheelW& wh = w.w[i];
         if (wh.ground == -2) continue;
@@ -571,7 +571,7 @@ RL_HD inline void vehicle_second(CarS& c, CarW& w, const CarConsts& k) {
             wh.suspForce = 0;
         }
     }
-#pragma unroll 1
+    RL_WHEEL_LOOP
     for (int i = 0; i < 4; i++) {
         WheelW& wh = w.w[i];
         if (wh.suspForce != 0) {
@@ -581,7 +581,7 @@ RL_HD inline void vehicle_second(CarS& c, CarW& w, const CarConsts& k) {
         }
     }
     V3 upDir = c.rot.col(2);
-#pragma unroll 1
+    RL_WHEEL_LOOP
     for (int i = 0; i < 4; i++) {
         WheelW& wh = w.w[i];
         if (!is_zero(wh.impulse)) {

@@ -206,7 +206,7 @@ RL_HD inline void manifold_add(CollideCtx& x, Manifold& m, V3 normalOnB, V3 poin
     if (ms && tri >= 0) adjust_internal_edge(p, *ms, tri);
 }
 
-RL_HDI void manifold_flush(ContactSink& cs, const Manifold& m) {
+RL_HD RL_NOINLINE inline void manifold_flush(ContactSink& cs, const Manifold& m) {
     for (int i = 0; i < m.n; i++) {
         if (cs.n < cs.cap) cs.base[cs.n++] = m.pt[i];
         else cs.overflow++;

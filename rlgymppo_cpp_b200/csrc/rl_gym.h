@@ -3,8 +3,10 @@
 // CombinedReward / EventReward / ZeroSumReward, terminal conditions, state setters.
 //
 // Everything here must be BIT-EXACT against the reference given identical arena
-// states, so each expression keeps the reference's operation order and the library is
-// built with -fmad=false (the oracle is built for baseline x86-64: no FMA).
+// states, so each expression keeps the reference's operation order and every floating-point
+// operation whose result feeds another one goes through the strict s_* helpers of rl_math.h
+// (the oracle is built for baseline x86-64: no FMA, IEEE division and square root), while the
+// physics around it is free to use FMA contraction.
 // Reference paths: G/ = RLGymPPO_CPP/RLGymSim_CPP/src/RLGymSim_CPP, R/ = .../RocketSim/src.
 #pragma once
 #include "rl_car.h"
@@ -21,10 +23,10 @@ struct Tables {
     uint32_t padCellMask[10 * 12 * 2];
 };
 
-RL_HDI V3 car_pos_uu(const CarS& c) { return V3(c.pos.x * BT2UU, c.pos.y * BT2UU, c.pos.z * BT2UU); }
-RL_HDI V3 car_vel_uu(const CarS& c) { return V3(c.vel.x * BT2UU, c.vel.y * BT2UU, c.vel.z * BT2UU); }
-RL_HDI V3 ball_pos_uu(const BallS& b) { return V3(b.pos.x * BT2UU, b.pos.y * BT2UU, b.pos.z * BT2UU); }
-RL_HDI V3 ball_vel_uu(const BallS& b) { return V3(b.vel.x * BT2UU, b.vel.y * BT2UU, b.vel.z * BT2UU); }
+RL_HDI V3 car_pos_uu(const CarS& c) { return to_uu(c.pos); }
+RL_HDI V3 car_vel_uu(const CarS& c) { return to_uu(c.vel); }
+RL_HDI V3 ball_pos_uu(const BallS& b) { return to_uu(b.pos); }
+RL_HDI V3 ball_vel_uu(const BallS& b) { return to_uu(b.vel); }
 
 // G/Math.cpp:3-5
 RL_HDI bool is_ball_scored_y(float yUU) { return fabsf(yUU) > C::GOAL_THRESHOLD_Y + C::BALL_RADIUS; }
@@ -52,14 +54,14 @@ RL_HD RL_NOINLINE inline bool ball_probably_going_in(const BallS& b, float maxTi
     if (fabsf(vel.y) < kEps) return false;
     float scoreDirSgn = (float)sgn(vel.y);
     float goalY = C::GOAL_THRESHOLD_Y * scoreDirSgn;
-    float distToGoal = fabsf(pos.y - goalY);
-    float timeToGoal = distToGoal / fabsf(vel.y);
+    float distToGoal = fabsf(s_sub(pos.y, goalY));
+    float timeToGoal = s_div(distToGoal, fabsf(vel.y));
     if (timeToGoal > maxTime) return false;
     // ballPos + ballVel*t + gravity*t*t/2 ; gravity = (0,0,-650)
-    float ex = (pos.x + vel.x * timeToGoal) + ((0.f * timeToGoal) * timeToGoal) / 2;
-    float ez = (pos.z + vel.z * timeToGoal) + ((C::GRAVITY_Z * timeToGoal) * timeToGoal) / 2;
+    float ex = s_add(s_add(pos.x, s_mul(vel.x, timeToGoal)), s_div(s_mul(s_mul(0.f, timeToGoal), timeToGoal), 2.f));
+    float ez = s_add(s_add(pos.z, s_mul(vel.z, timeToGoal)), s_div(s_mul(s_mul(C::GRAVITY_Z, timeToGoal), timeToGoal), 2.f));
     const float APPROX_GOAL_HALF_WIDTH = 892.755f, APPROX_GOAL_HEIGHT = (float)642.775;
-    float scoreMargin = C::BALL_RADIUS * 0.1f + extraMargin;
+    float scoreMargin = s_add(s_mul(C::BALL_RADIUS, 0.1f), extraMargin);
     if (ez > APPROX_GOAL_HEIGHT + scoreMargin) return false;
     if (fabsf(ex) > APPROX_GOAL_HALF_WIDTH + scoreMargin) return false;
     if (goalTeamOut) *goalTeamOut = scoreDirSgn < 0 ? 0 : 1;  // RS_TEAM_FROM_Y(scoreDirSgn)
@@ -100,11 +102,11 @@ RL_HDI void event_tracker_update(ArenaS& a, const SimCfg& cfg) {
     // default GameEventTrackerConfig (GameEventTracker.h:11-40); tick rate 120
     const float shotMinSpeed = 1750, predScoreExtraMargin = 0, shotEventCooldown = 1.0f, shotMinScoreTime = 2.0f;
     const int64_t goalMaxTouchTicks = 480, passMaxTouchTicks = 240, shotMinTouchDelayTicks = 36;
-    bool scored = is_ball_scored_y(a.ball.pos.y * BT2UU);
+    bool scored = is_ball_scored_y(s_mul(a.ball.pos.y, BT2UU));
     int32_t cnt = a.ball.updateCounterLo;
     if (cnt > a.lastBallUpdateCount) {
         int64_t deltaTicks = (int64_t)cnt - a.lastBallUpdateCount;
-        float deltaTime = (float)deltaTicks * kTickTime;
+        float deltaTime = s_mul((float)deltaTicks, kTickTime);
         if (scored && !a.ballScoredLast) {
             int shooter, passer;
             int team = (-a.ball.pos.y) < 0 ? 0 : 1;  // RS_TEAM_FROM_Y(-ball y)
@@ -114,10 +116,10 @@ RL_HDI void event_tracker_update(ArenaS& a, const SimCfg& cfg) {
             }
         } else if (!a.ballShot) {
             if (a.shotCooldown > 0) {
-                a.shotCooldown = fmaxf_(a.shotCooldown - deltaTime, 0.f);
+                a.shotCooldown = fmaxf_(s_sub(a.shotCooldown, deltaTime), 0.f);
             } else {
                 V3 v = ball_vel_uu(a.ball);
-                float speedSq = len2(v);
+                float speedSq = s_add(s_add(s_mul(v.x, v.x), s_mul(v.y, v.y)), s_mul(v.z, v.z));  // Vec::LengthSq via btVector3::length2
                 if (speedSq >= shotMinSpeed * shotMinSpeed) {
                     int goalTeam = 0;
                     if (ball_probably_going_in(a.ball, shotMinScoreTime, predScoreExtraMargin, &goalTeam)) {
@@ -167,7 +169,7 @@ RL_HDI void snapshot_update(ArenaS& a, const SimCfg& cfg) {
         if (c.touchedStep) a.lastTouchCarId = ci + 1;
         c.snapIsDemoed = c.isDemoed;
     }
-    float by = a.ball.pos.y * BT2UU;
+    float by = s_mul(a.ball.pos.y, BT2UU);
     if (is_ball_scored_y(by)) a.scoreLine[1 - (by < 0 ? 0 : 1)]++;
     set_i64(a.lastTickLo, a.lastTickHi, tick);
 }
@@ -188,7 +190,7 @@ RL_HDI int add_player_obs(float* o, const CarS& c, bool inv) {
     o[6] = up.x; o[7] = up.y; o[8] = up.z;
     o[9] = vel.x * velCoef; o[10] = vel.y * velCoef; o[11] = vel.z * velCoef;
     o[12] = ang.x * angCoef; o[13] = ang.y * angCoef; o[14] = ang.z * angCoef;
-    o[15] = c.boost / 100;                 // PlayerData.cpp:32
+    o[15] = s_div(c.boost, 100.f);         // PlayerData.cpp:32
     o[16] = (float)(c.isOnGround != 0);
     bool hasFlip = !c.hasDoubleJumped && !c.hasFlipped && c.airTimeSinceJump < C::DOUBLEJUMP_MAX_DELAY;  // PlayerData.cpp:28-30
     o[17] = (float)hasFlip;
@@ -271,7 +273,7 @@ RL_HDI void event_values(const ArenaS& a, const SimCfg& cfg, int ci, float* v) {
     v[0] = (float)c.matchGoals; v[1] = (float)a.scoreLine[team]; v[2] = (float)a.scoreLine[1 - team];
     v[3] = (float)c.matchAssists; v[4] = (float)(c.touchedStep != 0); v[5] = (float)c.matchShots;
     v[6] = (float)c.matchShotPasses; v[7] = (float)c.matchSaves; v[8] = (float)c.matchDemos;
-    v[9] = (float)(c.isDemoed != 0); v[10] = c.boost / 100;
+    v[9] = (float)(c.isDemoed != 0); v[10] = s_div(c.boost, 100.f);
 }
 
 RL_HDI float reward_term(ArenaS& a, const SimCfg& cfg, const RewardTerm& t, int ci) {
@@ -281,13 +283,13 @@ RL_HDI float reward_term(ArenaS& a, const SimCfg& cfg, const RewardTerm& t, int 
     case 0: {  // EventReward::GetReward (CommonRewards.cpp:32-43)
         float nv[11]; event_values(a, cfg, ci, nv);
         float r = 0;
-        for (int i = 0; i < 11; i++) { r += fmaxf_(nv[i] - c.eventMemo[i], 0.f) * t.params[i]; c.eventMemo[i] = nv[i]; }
+        for (int i = 0; i < 11; i++) { r = s_add(r, s_mul(fmaxf_(s_sub(nv[i], c.eventMemo[i]), 0.f), t.params[i])); c.eventMemo[i] = nv[i]; }
         return r;
     }
     case 1: {  // VelocityPlayerToBallReward (CommonRewards.h:91-98)
-        V3 d = ref_normalized(ballPos - car_pos_uu(c));
+        V3 d = ref_normalized(s_sub3(ballPos, car_pos_uu(c)));
         V3 v = car_vel_uu(c);
-        V3 nvv = V3(v.x / C::CAR_MAX_SPEED, v.y / C::CAR_MAX_SPEED, v.z / C::CAR_MAX_SPEED);
+        V3 nvv = V3(s_div(v.x, C::CAR_MAX_SPEED), s_div(v.y, C::CAR_MAX_SPEED), s_div(v.z, C::CAR_MAX_SPEED));
         return ref_dot(d, nvv);
     }
     case 2: {  // VelocityBallToGoalReward (CommonRewards.h:73-88)
@@ -295,18 +297,18 @@ RL_HDI float reward_term(ArenaS& a, const SimCfg& cfg, const RewardTerm& t, int 
         if (t.params[0] != 0.f) targetOrange = !targetOrange;
         const float goalZ = ((float)642.775) / 2;
         V3 target = targetOrange ? V3(0, 6000, goalZ) : V3(0, -6000, goalZ);
-        V3 d = ref_normalized(target - ballPos);
+        V3 d = ref_normalized(s_sub3(target, ballPos));
         V3 v = ball_vel_uu(a.ball);
-        V3 nvv = V3(v.x / C::BALL_MAX_SPEED, v.y / C::BALL_MAX_SPEED, v.z / C::BALL_MAX_SPEED);
+        V3 nvv = V3(s_div(v.x, C::BALL_MAX_SPEED), s_div(v.y, C::BALL_MAX_SPEED), s_div(v.z, C::BALL_MAX_SPEED));
         return ref_dot(d, nvv);
     }
     case 3: {  // FaceBallReward (CommonRewards.h:101-108)
-        V3 d = ref_normalized(ballPos - car_pos_uu(c));
+        V3 d = ref_normalized(s_sub3(ballPos, car_pos_uu(c)));
         return ref_dot(c.rot.col(0), d);
     }
     case 4: {  // VelocityReward (CommonRewards.h:52-58)
         float neg = t.params[0] != 0.f ? 1.f : 0.f;
-        return ref_len(car_vel_uu(c)) / C::CAR_MAX_SPEED * (float)(1 - 2 * (int)neg);
+        return s_mul(s_div(ref_len(car_vel_uu(c)), C::CAR_MAX_SPEED), (float)(1 - 2 * (int)neg));
     }
     }
     return 0.f;
@@ -317,15 +319,15 @@ RL_HD RL_NOINLINE inline void compute_rewards(ArenaS& a, const SimCfg& cfg, floa
     float r[kMaxCars];
     for (int p = 0; p < cfg.numCars; p++) r[p] = 0.f;
     for (int i = 0; i < cfg.numRewardTerms; i++)
-        for (int p = 0; p < cfg.numCars; p++) r[p] += reward_term(a, cfg, cfg.rewards[i], cfg.playerOrder[p]) * cfg.rewards[i].weight;
+        for (int p = 0; p < cfg.numCars; p++) r[p] = s_add(r[p], s_mul(reward_term(a, cfg, cfg.rewards[i], cfg.playerOrder[p]), cfg.rewards[i].weight));
     if (cfg.zeroSum) {  // ZeroSumReward.cpp:3-29
         int cnt[2] = {0, 0};
         float avg[2] = {0.f, 0.f};
-        for (int p = 0; p < cfg.numCars; p++) { int t = car_team(cfg.playerOrder[p], cfg.spawnOpponents); cnt[t]++; avg[t] += r[p]; }
-        for (int t = 0; t < 2; t++) avg[t] /= (float)(cnt[t] > 1 ? cnt[t] : 1);
+        for (int p = 0; p < cfg.numCars; p++) { int t = car_team(cfg.playerOrder[p], cfg.spawnOpponents); cnt[t]++; avg[t] = s_add(avg[t], r[p]); }
+        for (int t = 0; t < 2; t++) avg[t] = s_div(avg[t], (float)(cnt[t] > 1 ? cnt[t] : 1));
         for (int p = 0; p < cfg.numCars; p++) {
             int t = car_team(cfg.playerOrder[p], cfg.spawnOpponents);
-            r[p] = r[p] * (1 - cfg.teamSpirit) + (avg[t] * cfg.teamSpirit) - (avg[1 - t] * cfg.opponentScale);
+            r[p] = s_sub(s_add(s_mul(r[p], s_sub(1.f, cfg.teamSpirit)), s_mul(avg[t], cfg.teamSpirit)), s_mul(avg[1 - t], cfg.opponentScale));
         }
     }
     for (int p = 0; p < cfg.numCars; p++) out[p] = r[p];
@@ -340,7 +342,7 @@ RL_HDI bool compute_done(ArenaS& a, const SimCfg& cfg) {
         if (touched) a.stepsSinceTouch = 0;
         else { a.stepsSinceTouch++; done = a.stepsSinceTouch >= cfg.noTouchMaxSteps; }
     }
-    if (!done && cfg.goalScoreTerminal) done = is_ball_scored_y(a.ball.pos.y * BT2UU);
+    if (!done && cfg.goalScoreTerminal) done = is_ball_scored_y(s_mul(a.ball.pos.y, BT2UU));
     return done;
 }
 

@@ -4,7 +4,10 @@
 //  * M3 is row-major like btMatrix3x3; a body's basis has forward/right/up as COLUMNS
 //    (reference RocketSim/src/Math/MathTypes/MathTypes.h:171-178).
 //  * dot() associates as (x*x' + y*y') + z*z' (reference bullet LinearMath/btVector3.h:230-247).
-//  * No FMA contraction is relied upon: the library is compiled with -fmad=false.
+//  * The physics may be compiled with FMA contraction and approximate division / square root (parity there is
+//    tolerance based); everything that must be BIT-EXACT against the FMA-free x86 reference build (the gym layer:
+//    obs, rewards, event tracker) goes through the s_* helpers below, which are IEEE round-to-nearest single
+//    operations that the compiler never fuses or approximates, whatever the flags.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -19,6 +22,14 @@
 #define RL_NOINLINE __attribute__((noinline))
 #endif
 
+// the four per-wheel loops: rolled by default (the role kernel is instruction-cache bound); -DRL_UNROLL_WHEELS trades code
+// size for instruction-level parallelism across the wheels (A/B: profiles/)
+#ifdef RL_UNROLL_WHEELS
+#define RL_WHEEL_LOOP _Pragma("unroll")
+#else
+#define RL_WHEEL_LOOP _Pragma("unroll 1")
+#endif
+
 namespace rl {
 
 constexpr float kPi = 3.14159265358979323846f;
@@ -31,6 +42,21 @@ RL_HD RL_NOINLINE float rl_sin(float x);
 RL_HD RL_NOINLINE float rl_cos(float x);
 RL_HD RL_NOINLINE float rl_atan2(float y, float x);
 RL_HD RL_NOINLINE float rl_asin(float x);
+
+// strict single operations (never contracted into FMA, never approximated)
+#if defined(__CUDA_ARCH__)
+RL_HDI float s_mul(float a, float b) { return __fmul_rn(a, b); }
+RL_HDI float s_add(float a, float b) { return __fadd_rn(a, b); }
+RL_HDI float s_sub(float a, float b) { return __fsub_rn(a, b); }
+RL_HDI float s_div(float a, float b) { return __fdiv_rn(a, b); }
+RL_HDI float s_sqrt(float a) { return __fsqrt_rn(a); }
+#else
+RL_HDI float s_mul(float a, float b) { return a * b; }
+RL_HDI float s_add(float a, float b) { return a + b; }
+RL_HDI float s_sub(float a, float b) { return a - b; }
+RL_HDI float s_div(float a, float b) { return a / b; }
+RL_HDI float s_sqrt(float a) { return sqrtf(a); }
+#endif
 
 struct V3 {
     float x, y, z;
@@ -161,17 +187,19 @@ RL_HD RL_NOINLINE inline M3 euler_ypr_to_mat(float yaw, float pitch, float roll)
 RL_HDI M3 angle_to_rotmat(float yaw, float pitch, float roll) { return euler_ypr_to_mat(yaw, -pitch, -roll); }
 
 // ---- reference Vec helpers (R/Math/MathTypes/MathTypes.h) — they include the zero 4th lane ----
-RL_HDI float ref_len(V3 v) {
-    float l2 = ((v.x * v.x + v.y * v.y) + v.z * v.z) + 0.f * 0.f;
-    return l2 > 0 ? sqrtf(l2) : 0.f;
+// (strict: these feed the bit-exact rewards; out of line so the IEEE division / square-root sequences exist once)
+RL_HDI float ref_dot(V3 a, V3 b) { return s_add(s_add(s_add(s_mul(a.x, b.x), s_mul(a.y, b.y)), s_mul(a.z, b.z)), 0.f); }
+RL_HDI V3 s_sub3(V3 a, V3 b) { return V3(s_sub(a.x, b.x), s_sub(a.y, b.y), s_sub(a.z, b.z)); }
+RL_HD RL_NOINLINE inline float ref_len(V3 v) {
+    float l2 = ref_dot(v, v);
+    return l2 > 0 ? s_sqrt(l2) : 0.f;
 }
-RL_HDI V3 ref_normalized(V3 v) {
+RL_HD RL_NOINLINE inline V3 ref_normalized(V3 v) {
     float l = ref_len(v);
-    if (l > kEps * kEps) return V3(v.x / l, v.y / l, v.z / l);
+    if (l > kEps * kEps) return V3(s_div(v.x, l), s_div(v.y, l), s_div(v.z, l));
     return V3(0, 0, 0);
 }
-RL_HDI float ref_dot(V3 a, V3 b) { return ((a.x * b.x + a.y * b.y) + a.z * b.z) + 0.f * 0.f; }
-RL_HDI V3 to_uu(V3 v) { return V3(v.x * 50.f, v.y * 50.f, v.z * 50.f); }
+RL_HDI V3 to_uu(V3 v) { return V3(s_mul(v.x, 50.f), s_mul(v.y, 50.f), s_mul(v.z, 50.f)); }
 
 RL_HD RL_NOINLINE inline float rl_sin(float x) { return sinf(x); }
 RL_HD RL_NOINLINE inline float rl_cos(float x) { return cosf(x); }

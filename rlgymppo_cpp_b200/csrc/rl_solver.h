@@ -177,8 +177,13 @@ RL_HD inline void integrate_transform(V3& pos, M3& rot, V3 linvel, V3 angvel, fl
     if (pl2 > kEps) rot = quat_to_mat(pred);
 }
 
-// solveGroup for every awake body of the arena.  bodies: 0 ball, 1+c cars.
-RL_HD RL_NOINLINE inline void solve_arena(SolverBody* sb, int numBodies, ContactSet& cs) {
+// solveGroup for one simulation island.  `sb` holds the island's bodies; a contact's body index i (0 ball, 1+c car c,
+// -1 static) maps to sb[i - base].  Islands that share no body do not interact in a Gauss-Seidel sweep, so solving them
+// one by one (each with its rows in the reference's manifold order) gives exactly what the reference's single
+// solveGroup over all manifolds gives; this is what lets every role of a tick solve its own island concurrently
+// (rl_tick.h).  The split-impulse early exit on a zero residual is per island for the same reason: an island whose
+// rows all returned a zero delta is at a fixed point of the sweep.
+RL_HD RL_NOINLINE inline void solve_island(SolverBody* sb, int numBodies, int base, const Contact* contacts, int numContacts) {
     Row rows[kMaxRows];
     Row fric[kMaxRows];
     int nRows = 0, nFric = 0;
@@ -186,22 +191,22 @@ RL_HD RL_NOINLINE inline void solve_arena(SolverBody* sb, int numBodies, Contact
     int spN[1 + kMaxCars]; float spFriction[1 + kMaxCars], spRestitution[1 + kMaxCars], spDist[1 + kMaxCars]; V3 spNormal[1 + kMaxCars];
     for (int i = 0; i < numBodies; i++) { spN[i] = 0; spDist[i] = 0; spNormal[i] = V3(); spFriction[i] = spRestitution[i] = 0; }
 
-    for (int ci = 0; ci < cs.n; ci++) {
-        const Contact& cp = cs.c[ci];
+    for (int ci = 0; ci < numContacts; ci++) {
+        const Contact& cp = contacts[ci];
+        const int ia = cp.a < 0 ? -1 : cp.a - base, ib = cp.b < 0 ? -1 : cp.b - base;
         // a body without contact response (demoed car) or in a sleeping island (frozen ball) takes its manifolds out of
         // the solver entirely (btCollisionDispatcher::needsResponse / island filtering); it is NOT a static obstacle
-        if ((cp.a >= 0 && !sb[cp.a].active) || (cp.b >= 0 && !sb[cp.b].active)) continue;
-        int ia = cp.a, ib = cp.b;
+        if ((ia >= 0 && !sb[ia].active) || (ib >= 0 && !sb[ib].active)) continue;
         if (nRows >= kMaxRows - (1 + kMaxCars)) break;
-        V3 rel1 = cp.posA - (cp.a >= 0 ? sb[cp.a].pos : V3());
-        V3 rel2 = cp.posB - (cp.b >= 0 ? sb[cp.b].pos : V3());
+        V3 rel1 = cp.posA - (ia >= 0 ? sb[ia].pos : V3());
+        V3 rel2 = cp.posB - (ib >= 0 ? sb[ib].pos : V3());
         int idx = nRows;
         setup_contact_row(rows[nRows], sb, ia, ib, cp.normal, rel1, rel2, cp.dist, cp.restitution, cp.friction, cp.special);
         rows[nRows].frictionIndex = nFric;
         nRows++;
         if (cp.special) {
             for (int s = 0; s < 2; s++) {
-                int bi = s ? cp.b : cp.a;
+                int bi = s ? ib : ia;
                 if (bi >= 0) {
                     spN[bi]++; spFriction[bi] = cp.friction; spRestitution[bi] = cp.restitution;
                     spNormal[bi] += cp.normal; spDist[bi] += len(s ? rel2 : rel1);

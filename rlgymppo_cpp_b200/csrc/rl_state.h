@@ -202,7 +202,7 @@ RL_HDI void set_i64(int32_t& lo, int32_t& hi, int64_t v) { lo = (int32_t)(uint32
 RL_HDI int car_team(int c, int spawnOpponents) { return spawnOpponents ? (c & 1) : 0; }
 
 // pcg32
-RL_HDI uint32_t rng_next(ArenaS& a) {
+RL_HD RL_NOINLINE inline uint32_t rng_next(ArenaS& a) {
     uint64_t s = ((uint64_t)a.rngHi << 32) | a.rngLo;
     uint64_t old = s;
     s = old * 6364136223846793005ULL + 1442695040888963407ULL;
@@ -213,8 +213,8 @@ RL_HDI uint32_t rng_next(ArenaS& a) {
 }
 // Math::RandFloat(min,max) = min + (r / float(max_r)) * (max - min)  (reference Math.cpp:54-57)
 RL_HDI float rng_float(ArenaS& a, float lo, float hi) {
-    float u = (float)(rng_next(a) >> 8) * (1.0f / 16777215.0f);
-    return lo + u * (hi - lo);
+    float u = s_mul((float)(rng_next(a) >> 8), 1.0f / 16777215.0f);
+    return s_add(lo, s_mul(u, s_sub(hi, lo)));
 }
 
 // static configuration shared by all arenas of an engine (kernel parameter, by value)

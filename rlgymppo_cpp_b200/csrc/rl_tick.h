@@ -104,10 +104,12 @@ static ContactSet g_dbg_contacts;
 //   P1  car c : Car::_PreTickUpdate (wheel rays read the snapshots), gravity, hitbox AABB,
 //               car-ball, hitbox-mesh, hitbox-plane narrowphase -> own contact segments
 //       ball  : pads pre-tick, sphere-mesh, sphere-plane narrowphase -> own contact segment          | barrier B2
-//   P2  ball  : ball damping, car-car pairs (+bump/demo callbacks), gather contacts in the reference's manifold
-//               order, sequential-impulse solve, write velocities / pushed transforms back,
-//               integrate + finish the ball, tick count                                              | barrier B3
-//   P3  car c : integrate transform, Car::_PostTickUpdate/_FinishPhysicsTick, boost-pad overlap mask | barrier B4
+//   P2  ball  : ball damping, car-car pairs (+bump/demo callbacks), sequential-impulse solve of the island(s) of the
+//               ball and the COUPLED cars (contacts gathered in the reference's manifold order), write back,
+//               integrate + finish the ball, tick count
+//       car c : if uncoupled (no car-ball / car-car manifold possible): solve its own island, then P3   | barrier B3
+//   P3  car c : (coupled cars; the others did it before B3) integrate transform,
+//               Car::_PostTickUpdate/_FinishPhysicsTick, boost-pad overlap mask                          | barrier B4
 //   P4  ball  : BoostPad::_PostTickUpdate (pick-ups)
 struct Thresholds;
 
@@ -182,6 +184,58 @@ RL_HD inline void tick_p1_ball(ArenaS& a, TickX x, const SimCfg& cfg, const Mesh
     x.h->nBall = cs.n;
 }
 
+// ---- P2: constraint solve, one simulation island per role ---------------------------------------------------------
+// A car is COUPLED this tick when it may share a manifold with another dynamic body: it produced a car-ball contact, or
+// its hitbox AABB overlaps another car's (the broadphase condition for a car-car manifold).  Everything else it touches
+// is static, so an uncoupled car is a simulation island of its own and its role solves it (tick_p2_car_self) while the
+// ball role solves the island(s) made of the ball and the coupled cars (tick_p2_solve); see solve_island (rl_solver.h)
+// for why this equals the reference's single solveGroup.
+RL_HDI bool car_is_coupled(const TickX& x, int P, int c) {
+    const CarX& o = x.car[c];
+    if (o.noResponse) return false;  // not simulated this tick: nobody solves it
+    if (o.nCarBall > 0) return true;
+    for (int d = 0; d < P; d++) {
+        if (d == c) continue;
+        const CarX& od = x.car[d];
+        bool ov = !(o.cmn.x > od.cmx.x || o.cmx.x < od.cmn.x || o.cmn.y > od.cmx.y || o.cmx.y < od.cmn.y || o.cmn.z > od.cmx.z || o.cmx.z < od.cmn.z);
+        if (ov) return true;
+    }
+    return false;
+}
+
+RL_HDI void solver_body_from_car(SolverBody& b, const CarS& car, const CarX& o, const CarConsts& k) {
+    const float dt = kTickTime;
+    b.pos = car.pos; b.rot = car.rot; b.linVel = car.vel; b.angVel = car.angvel;
+    b.invMass = k.invMass;
+    b.invInertiaWorld = world_inertia(car.rot, k.invInertiaLocal);
+    b.extForceImp = o.force * b.invMass * dt;
+    b.extTorqueImp = tmul(o.torque, b.invInertiaWorld) * dt;
+    b.dLin = b.dAng = b.push = b.turn = V3();
+    b.active = !o.noResponse;
+}
+
+// an uncoupled car's own island: its car-world contacts only.  Returns false when the car is coupled (the ball role
+// solves it and the car finishes its tick after the next barrier).
+RL_HD inline bool tick_p2_car_self(ArenaS& a, TickX x, const SimCfg& cfg, const CarConsts& k, int c, Contact* scratch) {
+    const CarX& o = x.car[c];
+    if (car_is_coupled(x, cfg.numCars, c)) return false;
+    if (o.noResponse) return true;
+    CarS& car = a.cars[c];
+    if (o.nCarWorld == 0) {
+        // no manifold: the solver degenerates to writeBackBodies (btSequentialImpulseConstraintSolver.cpp:1878-1904):
+        // v += 0 (deltas), then v += externalForceImpulse
+        M3 iiw = world_inertia(car.rot, k.invInertiaLocal);
+        car.vel = (car.vel + V3()) + o.force * k.invMass * kTickTime;
+        car.angvel = (car.angvel + V3()) + tmul(o.torque, iiw) * kTickTime;
+        return true;
+    }
+    SolverBody b;
+    solver_body_from_car(b, car, o, k);
+    solve_island(&b, 1, 1 + c, seg_car(scratch, c) + 1, o.nCarWorld);
+    car.vel = b.linVel; car.angvel = b.angVel; car.pos = b.pos; car.rot = b.rot;
+    return true;
+}
+
 RL_HD inline void tick_p2_solve(ArenaS& a, TickX x, const SimCfg& cfg, const CarConsts& k, const Thresholds& thr, Contact* scratch, int firstTickOfStep) {
     const float dt = kTickTime;
     const int P = cfg.numCars;
@@ -193,6 +247,7 @@ RL_HD inline void tick_p2_solve(ArenaS& a, TickX x, const SimCfg& cfg, const Car
 
     // islands merge on broadphase overlap: a sleeping ball is woken by any responding car whose AABB overlaps
     bool ballWoken = false;
+    uint32_t coupled = 0;
     {
         float ballAabb = ballR + 0.08f;
         V3 bmn = a.ball.pos - V3(ballAabb, ballAabb, ballAabb), bmx = a.ball.pos + V3(ballAabb, ballAabb, ballAabb);
@@ -200,6 +255,7 @@ RL_HD inline void tick_p2_solve(ArenaS& a, TickX x, const SimCfg& cfg, const Car
             const CarX& o = x.car[c];
             bool ov = !(bmn.x > o.cmx.x || bmx.x < o.cmn.x || bmn.y > o.cmx.y || bmx.y < o.cmn.y || bmn.z > o.cmx.z || bmx.z < o.cmn.z);
             if (ov && !o.noResponse) ballWoken = true;
+            if (car_is_coupled(x, P, c)) coupled |= 1u << c;
         }
     }
     // car-car pairs in the reference's pair order; contacts of pair (c, d) carry a == 1 + c
@@ -214,34 +270,52 @@ RL_HD inline void tick_p2_solve(ArenaS& a, TickX x, const SimCfg& cfg, const Car
         }
     x.h->nPair = cp.n;
 
-    int totalContacts = x.h->nBall + cp.n;
-    for (int c = 0; c < P; c++) totalContacts += x.car[c].nCarBall + x.car[c].nCarWorld;
     const V3 gImp = V3(0.f * UU2BT, 0.f * UU2BT, C::GRAVITY_Z * UU2BT) * C::BALL_MASS;
-#ifndef RL_P2_FAST  // measured on B200 (profiles/r01c_ab.md): the extra branch costs more (code size) than it saves; off by default
-    totalContacts = 1;
-#endif
-    if (totalContacts == 0) {
-        // no manifolds anywhere in the arena (the common tick): the solver degenerates to writeBackBodies
-        // (btSequentialImpulseConstraintSolver.cpp:1878-1904): v += 0 (deltas) then v += externalForceImpulse
 #ifdef RL_DEBUG_CONTACTS
-        g_dbg_contacts.n = 0; g_dbg_contacts.overflow = 0;
-#endif
+    {   // every contact of the tick in the reference's manifold order (host debugging only)
+        ContactSet& cs = g_dbg_contacts; cs.n = 0; cs.overflow = 0;
+        auto take = [&](const Contact* src, int n) { for (int i = 0; i < n; i++) { if (cs.n < kMaxContacts) cs.c[cs.n++] = src[i]; else cs.overflow++; } };
+        take(seg_ball(scratch), x.h->nBall);
+        for (int c = 0; c < P; c++) take(seg_car(scratch, c), x.car[c].nCarBall);
         for (int c = 0; c < P; c++) {
-            if (x.car[c].noResponse) continue;
-            CarS& car = a.cars[c];
-            M3 iiw = world_inertia(car.rot, k.invInertiaLocal);
-            car.vel = (car.vel + V3()) + x.car[c].force * k.invMass * dt;
-            car.angvel = (car.angvel + V3()) + tmul(x.car[c].torque, iiw) * dt;
+            take(seg_car(scratch, c) + 1, x.car[c].nCarWorld);
+            const Contact* pr = seg_pair(scratch, P);
+            for (int i = 0; i < cp.n; i++) if (pr[i].a == 1 + c) take(pr + i, 1);
         }
-        if (ballActive || ballWoken) {
-            V3 ballForce;
-            if (ballActive) ballForce += gImp;
-            a.ball.vel = (a.ball.vel + V3()) + ballForce * (1.f / C::BALL_MASS) * dt;
-            a.ball.angvel = (a.ball.angvel + V3()) + V3();
-            a.ball.pos = a.ball.pos + a.ball.vel * dt;  // integrateTransformNoRot
+    }
+#endif
+    SolverBody sb[1 + kMaxCars];
+    {
+        SolverBody& b = sb[0];
+        b.pos = a.ball.pos; b.rot = M3::identity();
+        b.linVel = a.ball.vel; b.angVel = a.ball.angvel;
+        b.invMass = 1.f / C::BALL_MASS;
+        float inertia = 0.4f * C::BALL_MASS * ballR * ballR;
+        float ii = 1.f / inertia;
+        b.invInertiaWorld = M3(V3(ii, 0, 0), V3(0, ii, 0), V3(0, 0, ii));
+        V3 ballForce;
+        if (ballActive) ballForce += gImp;
+        b.extForceImp = ballForce * b.invMass * dt;
+        b.extTorqueImp = V3();
+        b.dLin = b.dAng = b.push = b.turn = V3();
+        b.active = ballActive || ballWoken;
+    }
+    if (coupled == 0) {
+        // the ball is an island of its own: ball-world contacts only, straight from its segment
+        if (sb[0].active) {
+            if (x.h->nBall > 0) {
+                solve_island(sb, 1, 0, seg_ball(scratch), x.h->nBall);
+                a.ball.vel = sb[0].linVel; a.ball.angvel = sb[0].angVel;
+                a.ball.pos = sb[0].pos + a.ball.vel * dt;  // integrateTransformNoRot
+            } else {
+                a.ball.vel = (a.ball.vel + V3()) + sb[0].extForceImp;
+                a.ball.angvel = (a.ball.angvel + V3()) + V3();
+                a.ball.pos = a.ball.pos + a.ball.vel * dt;
+            }
         }
     } else {
-        // gather in manifold order: ball-world, car-ball (c ascending), then per car: car-world, car-car (c, d > c)
+        // the ball and the coupled cars: gather in manifold order — ball-world, car-ball (c ascending), then per car:
+        // car-world, car-car (c, d > c)
         ContactSet cs; cs.n = 0; cs.overflow = 0;
         auto take = [&](const Contact* src, int n) {
             for (int i = 0; i < n; i++) {
@@ -250,46 +324,21 @@ RL_HD inline void tick_p2_solve(ArenaS& a, TickX x, const SimCfg& cfg, const Car
             }
         };
         take(seg_ball(scratch), x.h->nBall);
-        for (int c = 0; c < P; c++) take(seg_car(scratch, c), x.car[c].nCarBall);
+        for (int c = 0; c < P; c++) if ((coupled >> c) & 1u) take(seg_car(scratch, c), x.car[c].nCarBall);
         for (int c = 0; c < P; c++) {
+            if (!((coupled >> c) & 1u)) continue;
             take(seg_car(scratch, c) + 1, x.car[c].nCarWorld);
             const Contact* pr = seg_pair(scratch, P);
             for (int i = 0; i < cp.n; i++) if (pr[i].a == 1 + c) take(pr + i, 1);
         }
-#ifdef RL_DEBUG_CONTACTS
-        g_dbg_contacts = cs;
-#endif
-        SolverBody sb[1 + kMaxCars];
-        {
-            SolverBody& b = sb[0];
-            b.pos = a.ball.pos; b.rot = M3::identity();
-            b.linVel = a.ball.vel; b.angVel = a.ball.angvel;
-            b.invMass = 1.f / C::BALL_MASS;
-            float inertia = 0.4f * C::BALL_MASS * ballR * ballR;
-            float ii = 1.f / inertia;
-            b.invInertiaWorld = M3(V3(ii, 0, 0), V3(0, ii, 0), V3(0, 0, ii));
-            V3 ballForce;
-            if (ballActive) ballForce += gImp;
-            b.extForceImp = ballForce * b.invMass * dt;
-            b.extTorqueImp = V3();
-            b.dLin = b.dAng = b.push = b.turn = V3();
-            b.active = ballActive || ballWoken;
-        }
         for (int c = 0; c < P; c++) {
-            SolverBody& b = sb[1 + c];
-            const CarS& car = a.cars[c];
-            b.pos = car.pos; b.rot = car.rot; b.linVel = car.vel; b.angVel = car.angvel;
-            b.invMass = k.invMass;
-            b.invInertiaWorld = world_inertia(car.rot, k.invInertiaLocal);
-            b.extForceImp = x.car[c].force * b.invMass * dt;
-            b.extTorqueImp = tmul(x.car[c].torque, b.invInertiaWorld) * dt;
-            b.dLin = b.dAng = b.push = b.turn = V3();
-            b.active = !x.car[c].noResponse;
+            if ((coupled >> c) & 1u) solver_body_from_car(sb[1 + c], a.cars[c], x.car[c], k);
+            else sb[1 + c].active = 0;  // its own island (or not simulated): contacts that name it are skipped
         }
-        solve_arena(sb, 1 + P, cs);
+        solve_island(sb, 1 + P, 0, cs.c, cs.n);
         // write back; the cars integrate themselves in P3
         for (int c = 0; c < P; c++) {
-            if (!sb[1 + c].active) continue;
+            if (!((coupled >> c) & 1u) || !sb[1 + c].active) continue;
             CarS& car = a.cars[c];
             car.vel = sb[1 + c].linVel; car.angvel = sb[1 + c].angVel;
             car.pos = sb[1 + c].pos; car.rot = sb[1 + c].rot;
@@ -344,8 +393,10 @@ RL_HD inline void arena_tick(ArenaS& a, const SimCfg& cfg, const MeshSet& ms, co
     for (int c = 0; c < P; c++) tick_s0_car(a, x, c);
     for (int c = 0; c < P; c++) tick_p1_car(a, x, cfg, ms, k, thr, c, w[c], scratch, firstTickOfStep);
     tick_p1_ball(a, x, cfg, ms, k, thr, scratch);
+    bool self[kMaxCars];
+    for (int c = 0; c < P; c++) { self[c] = tick_p2_car_self(a, x, cfg, k, c, scratch); if (self[c]) tick_p3_car(a, x, tb, k, c, w[c]); }
     tick_p2_solve(a, x, cfg, k, thr, scratch, firstTickOfStep);
-    for (int c = 0; c < P; c++) tick_p3_car(a, x, tb, k, c, w[c]);
+    for (int c = 0; c < P; c++) if (!self[c]) tick_p3_car(a, x, tb, k, c, w[c]);
     tick_p4_pads(a, x, cfg);
 }
 
