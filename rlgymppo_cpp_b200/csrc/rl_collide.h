@@ -17,6 +17,8 @@ struct Contact {
     V3 posA, posB, normal;
     float dist, friction, restitution;
     int32_t special;
+    // uninitialised on purpose (see NoInit): manifold_add writes every member before a contact is stored
+    RL_HDI Contact() : posA(NoInit()), posB(NoInit()), normal(NoInit()) {}
 };
 
 constexpr int kMaxContacts = 40;

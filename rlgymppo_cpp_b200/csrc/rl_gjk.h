@@ -42,6 +42,9 @@ struct Simplex {
     V3 cachedV, cachedP1, cachedP2;
     float bc[4];
     bool valid;
+    // vertices are uninitialised (see NoInit; slots < n are always written first); the cached results start at zero
+    RL_HDI Simplex() : W{V3(NoInit()), V3(NoInit()), V3(NoInit()), V3(NoInit())}, P{V3(NoInit()), V3(NoInit()), V3(NoInit()), V3(NoInit())},
+                       Q{V3(NoInit()), V3(NoInit()), V3(NoInit()), V3(NoInit())}, n(0), bc{0, 0, 0, 0}, valid(false) {}
 };
 
 struct SubResult { float bc[4]; bool used[4]; V3 closest; bool degenerate; };

@@ -58,9 +58,15 @@ RL_HDI float s_div(float a, float b) { return a / b; }
 RL_HDI float s_sqrt(float a) { return sqrtf(a); }
 #endif
 
+// Tag for constructors that leave the storage uninitialised: per-thread arrays of solver rows / contacts / simplex
+// vertices live in local memory, and zero-filling them on every call was 25 % of the role kernel's local-memory traffic
+// (profiles/r01e_*).  Every member is written before it is read.
+struct NoInit {};
+
 struct V3 {
     float x, y, z;
     RL_HDI V3() : x(0), y(0), z(0) {}
+    RL_HDI explicit V3(NoInit) {}
     RL_HDI V3(float x_, float y_, float z_) : x(x_), y(y_), z(z_) {}
     RL_HDI float& operator[](int i) { return (&x)[i]; }
     RL_HDI float operator[](int i) const { return (&x)[i]; }
@@ -99,6 +105,7 @@ RL_HDI int sgn(float v) { return (v > 0.f) - (v < 0.f); }
 struct M3 {
     V3 r[3];  // rows
     RL_HDI M3() {}
+    RL_HDI explicit M3(NoInit) : r{V3(NoInit()), V3(NoInit()), V3(NoInit())} {}
     RL_HDI M3(V3 r0, V3 r1, V3 r2) { r[0] = r0; r[1] = r1; r[2] = r2; }
     RL_HDI V3 col(int i) const { return V3(r[0][i], r[1][i], r[2][i]); }
     RL_HDI static M3 identity() { return M3(V3(1, 0, 0), V3(0, 1, 0), V3(0, 0, 1)); }

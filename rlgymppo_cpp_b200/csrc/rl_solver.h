@@ -21,6 +21,10 @@ struct SolverBody {
     M3 invInertiaWorld;
     float invMass;
     int32_t active;  // has an m_originalBody in an awake island
+    // uninitialised on purpose (see NoInit): solver_body_from_car / tick_p2_solve write every member of an active body,
+    // and an inactive body is never read past `active`
+    RL_HDI SolverBody() : pos(NoInit()), rot(NoInit()), linVel(NoInit()), angVel(NoInit()), extForceImp(NoInit()), extTorqueImp(NoInit()),
+                          dLin(NoInit()), dAng(NoInit()), push(NoInit()), turn(NoInit()), invInertiaWorld(NoInit()) {}
 };
 
 struct Row {
@@ -28,6 +32,8 @@ struct Row {
     float jacDiagInv, rhs, rhsPen, lower, upper, applied, appliedPush, friction;
     int32_t a, b;        // solver body indices; -1 = fixed body
     int32_t frictionIndex, special;
+    // uninitialised on purpose (see NoInit): setup_contact_row / setup_friction_row write every member
+    RL_HDI Row() : n1(NoInit()), rxn1(NoInit()), n2(NoInit()), rxn2(NoInit()), angA(NoInit()), angB(NoInit()) {}
 };
 
 constexpr int kMaxRows = kMaxContacts + kMaxCars + 1;
