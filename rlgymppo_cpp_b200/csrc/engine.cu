@@ -52,6 +52,7 @@ struct rlg_engine {
     uint8_t* hDone = nullptr;
     Contact* scratch = nullptr;  // per-arena contact segments (rl_collide.h ContactSink)
     int xwords = 0, stride = 0, scratchSlots = 0;
+    int arenasPerBlock = 32, groupsPerBlock = 1;
     size_t rolesSmem = 0;
     uint64_t launches = 0;
 };
@@ -125,14 +126,15 @@ __global__ void k_get_state(const uint32_t* state, SimCfg cfg, int nwords, const
 }
 
 // ---- the role kernel: Arena::Step x n (mode 0) or the fused Gym::Step + GameInst auto-reset (mode 1) -----------------------
-// One block = 32 consecutive arenas x (1 + numCars) warps; warp r is ROLE r (0 = ball / arena bookkeeping, 1 + c = car c)
-// of those 32 arenas, lane = arena.  The block's arenas live in shared memory for the whole launch (arena words +
+// One block = G groups of 32 consecutive arenas x (1 + numCars) warps; a warp is ROLE r (0 = ball / arena bookkeeping,
+// 1 + c = car c) of one group's 32 arenas, lane = arena.  The block's arenas live in shared memory for the whole launch (arena words +
 // per-tick exchange, per-lane stride odd -> conflict-free), are loaded and stored cooperatively as coalesced 128-byte
 // lines of the word-transposed HBM layout, and the phases of rl_tick.h are separated by __syncthreads().
 struct RolesArgs {
     uint32_t* state;
     SimCfg cfg;
     int nwords, xwords, stride;  // arena words, exchange words, per-lane shared stride (words, odd)
+    int arenasPerBlock;          // arenas of one block = its arena groups x 32 lanes (the last group may be partial)
     MeshSet ms;
     const Tables* tb;
     Contact* scratch;
@@ -144,11 +146,15 @@ struct RolesArgs {
 
 __global__ void __maxnreg__(168) k_roles(const RolesArgs g) {
     extern __shared__ uint32_t smem[];
-    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    // warp = (arena group, role): the groups of a block run the same phase at the same time, so a role's instruction
+    // stream is fetched once per block and shared by its groups (the kernel is bound by instruction-cache misses).
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int P = g.cfg.numCars, roles = P + 1, A = g.cfg.numArenas;
-    const int a = blockIdx.x * 32 + lane;
-    const bool valid = a < A;
-    uint32_t* mine = smem + (size_t)lane * g.stride;
+    const int group = warp / roles, role = warp - group * roles;
+    const int slot = group * 32 + lane;
+    const int a = blockIdx.x * g.arenasPerBlock + slot;
+    const bool valid = slot < g.arenasPerBlock && a < A;
+    uint32_t* mine = smem + (size_t)slot * g.stride;
     ArenaS& s = *reinterpret_cast<ArenaS*>(mine);
     TickX x = make_tickx(mine + (g.stride - g.xwords));
     Contact* scratch = g.scratch + (size_t)(valid ? a : 0) * g.scratchSlots;
@@ -309,8 +315,31 @@ int rlg_engine_create(const rlg_engine_cfg* cfg, rlg_engine** out) {
     e->stride = e->nwords + e->xwords;
     if ((e->stride & 1) == 0) e->stride++;  // odd per-lane stride: the 32 lanes of a warp hit 32 different banks
     e->scratchSlots = contact_scratch_slots(P);
-    e->rolesSmem = (size_t)32 * e->stride * 4;
+    {   // block shape of the role kernel: one block per SM holding ceil(A / SMs) arenas (all SMs busy, one wave), capped
+        // by the shared memory one block may use
+        cudaDeviceProp prop;
+        CKD(cudaGetDeviceProperties(&prop, e->device));
+        int perSm = (A + prop.multiProcessorCount - 1) / prop.multiProcessorCount;
+        int maxBySmem = (int)((prop.sharedMemPerBlockOptin - 1024) / ((size_t)e->stride * 4));
+        cudaFuncAttributes fa;
+        CKD(cudaFuncGetAttributes(&fa, k_roles));
+        int maxThreads = prop.regsPerBlock / (fa.numRegs > 0 ? fa.numRegs : 1);
+        if (maxThreads > 1024) maxThreads = 1024;
+        int maxByThreads = (maxThreads / (32 * (1 + P))) * 32;
+        int cap = maxBySmem < maxByThreads ? maxBySmem : maxByThreads;
+        if (cap < 1) cap = 1;
+        int waves = (perSm + cap - 1) / cap;              // blocks each SM runs one after the other
+        int apb = (perSm + waves - 1) / waves;            // ... of equal size
+        if (apb < 32) apb = 32 < cap ? 32 : cap;          // small engines: whole warps
+        if (const char* ev = getenv("RLG_ARENAS_PER_BLOCK")) apb = atoi(ev);  // profiling A/B only
+        if (apb > cap) apb = cap;
+        if (apb < 1) apb = 1;
+        e->arenasPerBlock = apb;
+        e->groupsPerBlock = (apb + 31) / 32;
+    }
+    e->rolesSmem = (size_t)e->arenasPerBlock * e->stride * 4;
     CKD(cudaFuncSetAttribute(k_roles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->rolesSmem));
+    if (const char* cv = getenv("RLG_SMEM_CARVEOUT")) CKD(cudaFuncSetAttribute(k_roles, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
     CKD(cudaMalloc(&e->state, (size_t)e->nwords * A * 4));
     CKD(cudaMalloc(&e->scratch, (size_t)A * e->scratchSlots * sizeof(Contact)));
     CKD(cudaMalloc(&e->tables, sizeof(Tables)));
@@ -368,6 +397,7 @@ static RolesArgs roles_args(rlg_engine* e) {
     memset(&g, 0, sizeof(g));
     g.state = e->state; g.cfg = e->cfg; g.nwords = e->nwords; g.xwords = e->xwords; g.stride = e->stride;
     g.ms = e->ms; g.tb = e->tables; g.scratch = e->scratch; g.scratchSlots = e->scratchSlots;
+    g.arenasPerBlock = e->arenasPerBlock;
     return g;
 }
 
@@ -476,7 +506,7 @@ int rlg_engine_tick(rlg_engine* e, const rlg_controls* controls, int nticks, voi
     cudaStream_t s = pick(e, stream);
     RolesArgs g = roles_args(e);
     g.mode = 0; g.controls = controls; g.nticks = nticks;
-    k_roles<<<grid_for(e->cfg.numArenas, 32), 32 * (1 + e->cfg.numCars), e->rolesSmem, s>>>(g);
+    k_roles<<<grid_for(e->cfg.numArenas, e->arenasPerBlock), 32 * e->groupsPerBlock * (1 + e->cfg.numCars), e->rolesSmem, s>>>(g);
     e->launches++;
     CK(cudaGetLastError());
     return RLG_OK;
@@ -487,7 +517,7 @@ static int do_step(rlg_engine* e, const int32_t* action_idx, cudaStream_t s, int
     RolesArgs g = roles_args(e);
     g.mode = 1; g.actions = action_idx; g.obs = obs ? obs : e->obs; g.reward = reward ? reward : e->reward; g.done = done ? done : e->done;
     g.autoReset = autoReset;
-    k_roles<<<grid_for(e->cfg.numArenas, 32), 32 * (1 + e->cfg.numCars), e->rolesSmem, s>>>(g);
+    k_roles<<<grid_for(e->cfg.numArenas, e->arenasPerBlock), 32 * e->groupsPerBlock * (1 + e->cfg.numCars), e->rolesSmem, s>>>(g);
     e->launches++;
     CK(cudaGetLastError());
     return RLG_OK;
