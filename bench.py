@@ -252,13 +252,18 @@ def run_ours(args, rank, local_rank, world):
 
     # e2e: the reference-facing Gym::Step call with HOST buffers (H2D action indices from pinned memory, fused step,
     # D2H obs/reward/done), i.e. what a host-side policy (the reference's ThreadAgent) would drive
-    n_e2e = min(max(K, 4), 8)
+    n_e2e = min(max(4 * K, 16), 200)
     host_actions = np.random.default_rng(1000 + rank).integers(0, 90, size=(n_e2e + 1, A * P)).astype(np.int32)
-    e.step_host(host_actions[0])
+    pinned_actions, pinned_obs, pinned_rew, pinned_done = e.host_buffers()  # the engine's page-locked host buffers
+    pinned_actions[:] = host_actions[0]
+    e.step_pinned()
     barrier()
     t0 = time.perf_counter()
+    e2e_checksum = 0.0
     for i in range(n_e2e):
-        e.step_host(host_actions[i + 1])
+        pinned_actions[:] = host_actions[i + 1]          # this step's inputs, written by the host
+        e.step_pinned()                                  # H2D actions -> fused Gym::Step -> D2H obs/reward/done, synchronous
+        e2e_checksum += float(pinned_rew[::997].sum())   # the host reads the step's result
     barrier()
     e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -301,7 +306,8 @@ def run_ours(args, rank, local_rank, world):
                        "parallelism": f"arena-sharded x{world}, no data-path collective"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "call": "rlg_engine_step_host (Gym::Step with host buffers, uniform random host actions)"},
+                    "call": "rlg_engine_step_pinned (Gym::Step for every arena through the engine's page-locked host buffers: H2D action indices, "
+                            "fused step, D2H obs/reward/done; uniform random host actions)", "reward_checksum": e2e_checksum},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "k_roles (fused Gym::Step)", "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": k_step_ms, "launches_timed": step_n,

@@ -238,6 +238,13 @@ void* rlg_engine_stream(rlg_engine* e); /* the engine's own cudaStream_t */
 int rlg_engine_step_host(rlg_engine* e, const int32_t* action_idx_host,
                          float* obs_host, float* reward_host, uint8_t* done_host);
 
+/* Zero-copy variant of rlg_engine_step_host: the engine owns page-locked host buffers (action_idx [A*P] i32 in;
+ * obs [A*P, obs] f32, reward [A*P] f32, done [A] u8 out — the StepResult of G/Gym.h:24-29 for every arena); the
+ * caller writes action indices into *action_idx, calls rlg_engine_step_pinned and reads the results in place.
+ * The pointers stay valid for the engine's lifetime; the outputs are overwritten by the next host-buffer step. */
+int rlg_engine_host_buffers(rlg_engine* e, int32_t** action_idx, float** obs, float** reward, uint8_t** done);
+int rlg_engine_step_pinned(rlg_engine* e, int want_obs);
+
 /* Synchronous copies ordered after everything queued on the engine's stream (test / host-plugin plumbing). */
 int rlg_engine_copy_to_host(rlg_engine* e, void* dst_host, const void* src_dev, size_t bytes);
 int rlg_engine_copy_to_device(rlg_engine* e, void* dst_dev, const void* src_host, size_t bytes);

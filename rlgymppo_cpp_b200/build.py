@@ -42,26 +42,37 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, variant: str = "", extra_flags=()) -> str:
+    """variant != "": an A/B or diagnostic build (extra_flags, e.g. -DRLG_PHASE_TIMING) into build_ab/lib_<variant>.so,
+    selected at run time with RLG_B200_LIB; the product library is the variant-less build."""
+    if not variant and not force and not needs_build():
         return LIB
     env = dict(os.environ)
     env.pop("CXX", None)  # an inherited /opt/gcc wrapper links libstdc++ statically; let nvcc pick the distro g++
-    objdir = os.path.join(CSRC, "build")
+    objdir = os.path.join(CSRC, "build" + ("_" + variant if variant else ""))
+    lib = LIB
+    if variant:
+        os.makedirs(os.path.join(os.path.dirname(_HERE), "build_ab"), exist_ok=True)
+        lib = os.path.join(os.path.dirname(_HERE), "build_ab", f"lib_{variant}.so")
     os.makedirs(objdir, exist_ok=True)
     procs, objs = [], []
     for src in sources():
         name = os.path.basename(src)
         obj = os.path.join(objdir, name[:-3] + ".o")
         objs.append(obj)
-        cmd = [_nvcc()] + NVCC_FLAGS + FP_FLAGS.get(name, FP_DEFAULT) + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        cmd = [_nvcc()] + NVCC_FLAGS + FP_FLAGS.get(name, FP_DEFAULT) + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd, env=env)))
     for cmd, p in procs:
         if p.wait() != 0:
             raise subprocess.CalledProcessError(p.returncode, cmd)
-    subprocess.check_call([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", LIB], env=env)
-    return LIB
+    subprocess.check_call([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", lib], env=env)
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force=True, verbose=True))
+    import sys
+
+    if len(sys.argv) > 1:  # python -m rlgymppo_cpp_b200.build VARIANT [extra nvcc flags...]
+        print(build(force=True, variant=sys.argv[1], extra_flags=sys.argv[2:]))
+    else:
+        print(build(force=True, verbose=True))

@@ -1,11 +1,10 @@
 // engine.cu — the CUDA collection engine behind the C ABI of include/rlgym_b200.h.
 //
-// One thread steps one arena.  Arena state lives in HBM word-transposed
-// (word w of arena a at state[w * A + a]) so a warp's 32 arenas move as coalesced
-// 128-byte lines; a kernel loads the arena into thread-local storage, runs all ticks of
-// the step (tick_skip physics ticks + gym layer) and writes it back once: the
-// algorithmic HBM traffic per arena-step is read S + write S + actions + obs + rewards + done
-// (SURVEY.md §8d).  The collision meshes/BVH and the lookup tables are shared, read-only
+// Arena state lives in HBM word-transposed (word w of arena a at state[w * A + a]) so a warp's
+// 32 arenas move as coalesced 128-byte lines.  The role kernel (k_roles) keeps a block's arenas
+// in shared memory for all ticks of the step (tick_skip physics ticks + gym layer), one warp per
+// (group of 32 arenas, body role), and writes them back once: the algorithmic HBM traffic per
+// arena-step is read S + write S + actions + obs + rewards + done.  The collision meshes/BVH and the lookup tables are shared, read-only
 // and L2-resident.  There is no CPU fallback: every entry point that needs the device
 // returns RLG_ERR_CUDA when it is not usable.
 #include <cuda_runtime.h>
@@ -39,7 +38,7 @@ struct rlg_engine {
     uint32_t* state = nullptr;
     Tables* tables = nullptr;
     MeshSet ms;  // device pointers
-    void* meshMem[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void* meshMem[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool meshesLoaded = false;
     float* obs = nullptr;
     float* reward = nullptr;
@@ -54,6 +53,8 @@ struct rlg_engine {
     int xwords = 0, stride = 0, scratchSlots = 0;
     int arenasPerBlock = 32, groupsPerBlock = 1;
     size_t rolesSmem = 0;
+    int barMode = 0, asyncLoad = 1;
+    uint32_t *prof = nullptr, *prof2 = nullptr;  // RLG_PHASE_TIMING builds only
     uint64_t launches = 0;
 };
 
@@ -140,11 +141,31 @@ struct RolesArgs {
     Contact* scratch;
     int scratchSlots;
     int mode;  // 0: tick, 1: step
+    int barMode;    // 0: block-wide barriers, 1: per-group named barriers, 2: per-group inside a tick + one block barrier per tick
+    int asyncLoad;  // 1: state words move HBM -> shared memory with cp.async
+    uint32_t* prof; // RLG_PHASE_TIMING builds: [block][warp][kProfSlots] cycle counters
+    CarConsts k;    // car preset constants and contact thresholds: read from the kernel-parameter constant bank
+    Thresholds thr; // instead of a per-thread local-memory copy (the wheel arrays are indexed dynamically)
     const rlg_controls* controls; int nticks;
     const int32_t* actions; float* obs; float* reward; uint8_t* done; int autoReset;
 };
 
-__global__ void __maxnreg__(168) k_roles(const RolesArgs g) {
+constexpr int kProfSlots = 10;  // load, s0, p1, p2, p3, p4+gym, reset+store, barrier wait, total, unused
+#ifdef RLG_PHASE_TIMING
+#define PT_DECL() uint32_t pt[kProfSlots]; for (int i = 0; i < kProfSlots; i++) pt[i] = 0; long long ptStart = clock64(), ptT = ptStart
+#define PT_WORK(i) do { long long n_ = clock64(); pt[i] += (uint32_t)(n_ - ptT); ptT = n_; } while (0)
+#else
+#define PT_DECL() do {} while (0)
+#define PT_WORK(i) do {} while (0)
+#endif
+
+__device__ __forceinline__ void bar_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void cp_async4(uint32_t* smemDst, const uint32_t* gmemSrc) {
+    uint32_t d = (uint32_t)__cvta_generic_to_shared(smemDst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmemSrc) : "memory");
+}
+
+__global__ void __maxnreg__(168) k_roles(const __grid_constant__ RolesArgs g) {
     extern __shared__ uint32_t smem[];
     // warp = (arena group, role): the groups of a block run the same phase at the same time, so a role's instruction
     // stream is fetched once per block and shared by its groups (the kernel is bound by instruction-cache misses).
@@ -158,12 +179,24 @@ __global__ void __maxnreg__(168) k_roles(const RolesArgs g) {
     ArenaS& s = *reinterpret_cast<ArenaS*>(mine);
     TickX x = make_tickx(mine + (g.stride - g.xwords));
     Contact* scratch = g.scratch + (size_t)(valid ? a : 0) * g.scratchSlots;
-    if (valid)
-        for (int w = role; w < g.nwords; w += roles) mine[w] = g.state[(size_t)w * A + a];
-    __syncthreads();
+    // the groups of a block never touch each other's arenas: every barrier may be group-local (named barrier 1 + group)
+    const int barId = 1 + group, barThreads = 32 * roles;
+#define SYNC_GROUP() do { PT_WORK(9); if (g.barMode == 0) __syncthreads(); else bar_named(barId, barThreads); PT_WORK(7); } while (0)
+#define SYNC_TICK() do { PT_WORK(9); if (g.barMode == 1) bar_named(barId, barThreads); else __syncthreads(); PT_WORK(7); } while (0)
+    PT_DECL();
+    if (valid) {
+        if (g.asyncLoad) {
+            for (int w = role; w < g.nwords; w += roles) cp_async4(mine + w, g.state + (size_t)w * A + a);
+            asm volatile("cp.async.wait_all;" ::: "memory");
+        } else {
+            for (int w = role; w < g.nwords; w += roles) mine[w] = g.state[(size_t)w * A + a];
+        }
+    }
+    PT_WORK(0);
+    SYNC_TICK();
 
-    const CarConsts k = car_consts();
-    const Thresholds thr = contact_thresholds(k);
+    const CarConsts& k = g.k;
+    const Thresholds& thr = g.thr;
     CarW w;  // this car role's per-tick work state (wheel contacts, forces)
     bool doneFlag = false;
 
@@ -183,20 +216,24 @@ __global__ void __maxnreg__(168) k_roles(const RolesArgs g) {
     for (int t = 0; t < nticks; t++) {
         const int first = (g.mode == 1 && t == 0) ? 1 : 0;
         if (valid) { if (role == 0) tick_s0_ball(s, x); else tick_s0_car(s, x, role - 1); }
-        __syncthreads();  // B1
+        PT_WORK(1);
+        if (g.barMode == 2 && t > 0) SYNC_TICK(); else SYNC_GROUP();  // B1
         if (valid) {
             if (role == 0) tick_p1_ball(s, x, g.cfg, g.ms, k, thr, scratch);
             else tick_p1_car(s, x, g.cfg, g.ms, k, thr, role - 1, w, scratch, first);
         }
-        __syncthreads();  // B2
+        PT_WORK(2);
+        SYNC_GROUP();  // B2
         bool self = false;
         if (valid) {
             if (role == 0) tick_p2_solve(s, x, g.cfg, k, thr, scratch, first);
             else if ((self = tick_p2_car_self(s, x, g.cfg, k, role - 1, scratch))) tick_p3_car(s, x, *g.tb, k, role - 1, w);
         }
-        __syncthreads();  // B3
+        PT_WORK(3);
+        SYNC_GROUP();  // B3
         if (valid && role > 0 && !self) tick_p3_car(s, x, *g.tb, k, role - 1, w);
-        __syncthreads();  // B4
+        PT_WORK(4);
+        SYNC_GROUP();  // B4
         if (valid && role == 0) {
             tick_p4_pads(s, x, g.cfg);
             if (first) {  // Gym::Step after its first tick (G/Gym.cpp:84-93)
@@ -209,14 +246,26 @@ __global__ void __maxnreg__(168) k_roles(const RolesArgs g) {
                 g.done[a] = doneFlag ? 1 : 0;
             }
         }
+        PT_WORK(5);
     }
     if (valid && role == 0 && g.mode == 1 && doneFlag && g.autoReset) {  // GameInst::Step auto-reset (GameInst.cpp:20-24)
         gym_reset(s, g.cfg);
         build_obs(s, g.cfg, *g.tb, g.obs + (size_t)a * P * g.cfg.obsSize);
     }
-    __syncthreads();
+    PT_WORK(6);
+    SYNC_GROUP();
     if (valid)
         for (int w2 = role; w2 < g.nwords; w2 += roles) g.state[(size_t)w2 * A + a] = mine[w2];
+    PT_WORK(6);
+#ifdef RLG_PHASE_TIMING
+    if (g.prof && lane == 0) {
+        pt[8] = (uint32_t)(clock64() - ptStart);
+        uint32_t* dst = g.prof + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * kProfSlots;
+        for (int i = 0; i < kProfSlots; i++) dst[i] += pt[i];
+    }
+#endif
+#undef SYNC_GROUP
+#undef SYNC_TICK
 }
 
 // Match::BuildObservations / IsDone / GetRewards on the CURRENT arena state (Gym::Step minus the physics and the
@@ -276,6 +325,23 @@ int rlg_action_table(float* table_host) {
 int rlg_engine_destroy(rlg_engine* e) {
     if (!e) return RLG_OK;
     cudaSetDevice(e->device);
+#ifdef RLG_PHASE_TIMING
+    if (e->prof) {  // diagnostic build: dump the per-warp phase cycle counters
+        const int blocks = (e->cfg.numArenas + e->arenasPerBlock - 1) / e->arenasPerBlock, warps = e->groupsPerBlock * (1 + e->cfg.numCars);
+        std::vector<uint32_t> h((size_t)blocks * warps * kProfSlots);
+        cudaMemcpy(h.data(), e->prof, h.size() * 4, cudaMemcpyDeviceToHost);
+        const char* path = getenv("RLG_PHASE_DUMP");
+        if (FILE* f = fopen(path ? path : "phase_prof.bin", "wb")) {
+            int32_t hdr[4] = {blocks, warps, kProfSlots, 1 + e->cfg.numCars};
+            fwrite(hdr, 4, 4, f); fwrite(h.data(), 4, h.size(), f);
+            std::vector<uint32_t> h2((size_t)blocks * warps * 32);
+            cudaMemcpy(h2.data(), e->prof2, h2.size() * 4, cudaMemcpyDeviceToHost);
+            fwrite(h2.data(), 4, h2.size(), f);
+            fclose(f);
+        }
+        cudaFree(e->prof); cudaFree(e->prof2);
+    }
+#endif
     cudaFree(e->scratch);
     cudaFree(e->state); cudaFree(e->tables); cudaFree(e->obs); cudaFree(e->reward); cudaFree(e->done); cudaFree(e->actions);
     for (void* p : e->meshMem) cudaFree(p);
@@ -337,6 +403,19 @@ int rlg_engine_create(const rlg_engine_cfg* cfg, rlg_engine** out) {
         e->arenasPerBlock = apb;
         e->groupsPerBlock = (apb + 31) / 32;
     }
+    if (const char* ev = getenv("RLG_BARRIER_MODE")) e->barMode = atoi(ev);
+    if (const char* ev = getenv("RLG_ASYNC_LOAD")) e->asyncLoad = atoi(ev);
+    if (e->groupsPerBlock > 15) e->barMode = 0;  // 16 hardware barriers per block
+#ifdef RLG_PHASE_TIMING
+    {
+        const int blocks = (A + e->arenasPerBlock - 1) / e->arenasPerBlock, warps = e->groupsPerBlock * (1 + P);
+        CKD(cudaMalloc(&e->prof, (size_t)blocks * warps * kProfSlots * 4));
+        CKD(cudaMemset(e->prof, 0, (size_t)blocks * warps * kProfSlots * 4));
+        CKD(cudaMalloc(&e->prof2, (size_t)blocks * warps * 32 * 4));
+        CKD(cudaMemset(e->prof2, 0, (size_t)blocks * warps * 32 * 4));
+        CKD(cudaMemcpyToSymbol(g_rl_pt, &e->prof2, sizeof(e->prof2)));
+    }
+#endif
     e->rolesSmem = (size_t)e->arenasPerBlock * e->stride * 4;
     CKD(cudaFuncSetAttribute(k_roles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->rolesSmem));
     if (const char* cv = getenv("RLG_SMEM_CARVEOUT")) CKD(cudaFuncSetAttribute(k_roles, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
@@ -386,6 +465,8 @@ int rlg_engine_load_meshes(rlg_engine* e, const void* const* blobs, const size_t
     CK(up(3, hm.hdrSize.data(), hm.hdrSize.size() * 4, (const void**)&ms.hdrSize));
     CK(up(4, hm.triFlags.data(), hm.triFlags.size() * 4, (const void**)&ms.triFlags));
     CK(up(5, hm.triEdgeAngles.data(), hm.triEdgeAngles.size() * 4, (const void**)&ms.triEdgeAngles));
+    CK(up(6, hm.gridRange.data(), hm.gridRange.size() * 4, (const void**)&ms.gridRange));
+    CK(up(7, hm.gridList.data(), hm.gridList.size() * 4, (const void**)&ms.gridList));
     CK(cudaStreamSynchronize(e->stream));
     e->ms = ms;
     e->meshesLoaded = true;
@@ -398,6 +479,8 @@ static RolesArgs roles_args(rlg_engine* e) {
     g.state = e->state; g.cfg = e->cfg; g.nwords = e->nwords; g.xwords = e->xwords; g.stride = e->stride;
     g.ms = e->ms; g.tb = e->tables; g.scratch = e->scratch; g.scratchSlots = e->scratchSlots;
     g.arenasPerBlock = e->arenasPerBlock;
+    g.barMode = e->barMode; g.asyncLoad = e->asyncLoad; g.prof = e->prof;
+    g.k = car_consts(); g.thr = contact_thresholds(g.k);
     return g;
 }
 
@@ -594,6 +677,31 @@ int rlg_engine_step_host(rlg_engine* e, const int32_t* action_idx_host, float* o
     if (obs_host) memcpy(obs_host, e->hObs, (size_t)A * P * e->cfg.obsSize * 4);
     if (reward_host) memcpy(reward_host, e->hReward, (size_t)A * P * 4);
     if (done_host) memcpy(done_host, e->hDone, (size_t)A);
+    return RLG_OK;
+}
+
+int rlg_engine_host_buffers(rlg_engine* e, int32_t** action_idx, float** obs, float** reward, uint8_t** done) {
+    if (!e) return fail(RLG_ERR_INVALID, "null engine");
+    if (action_idx) *action_idx = e->hActions;
+    if (obs) *obs = e->hObs;
+    if (reward) *reward = e->hReward;
+    if (done) *done = e->hDone;
+    return RLG_OK;
+}
+
+int rlg_engine_step_pinned(rlg_engine* e, int want_obs) {
+    if (!e) return fail(RLG_ERR_INVALID, "null engine");
+    if (!e->meshesLoaded) return fail(RLG_ERR_STATE, "rlg_engine_load_meshes must be called first (RocketSim::Init)");
+    CK(cudaSetDevice(e->device));
+    const int A = e->cfg.numArenas, P = e->cfg.numCars;
+    cudaStream_t s = e->stream;
+    CK(cudaMemcpyAsync(e->actions, e->hActions, (size_t)A * P * 4, cudaMemcpyHostToDevice, s));
+    int rc = do_step(e, e->actions, s, 1);
+    if (rc != RLG_OK) return rc;
+    if (want_obs) CK(cudaMemcpyAsync(e->hObs, e->obs, (size_t)A * P * e->cfg.obsSize * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(e->hReward, e->reward, (size_t)A * P * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(e->hDone, e->done, (size_t)A, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
     return RLG_OK;
 }
 

@@ -661,9 +661,11 @@ RL_HD inline void car_pre_tick(CarS& c, const TickX& x, const SimCfg& cfg, const
         const V3 pad(0.02f, 0.02f, 0.02f);  // > the 0.01 box padding of the direct ray walk
         collect_candidates(ms, mn - pad, mx + pad, w.cands);
     }
+    RL_PT(0);
     if (c.isDemoed) return;
 
     vehicle_first(c, x, cfg, ms, k, ci, w);
+    RL_PT(1);
     bool jumpPressed = c.controls.jump && !c.lastControls.jump;
     int n = 0;
     for (int i = 0; i < 4; i++) { c.wheelContact[i] = w.w[i].inContact; n += w.w[i].inContact; }
@@ -677,8 +679,10 @@ RL_HD inline void car_pre_tick(CarS& c, const TickX& x, const SimCfg& cfg, const
     update_double_jump_or_flip(c, k, cfg, jumpPressed, forwardSpeedUU);
     if (c.controls.throttle != 0 && ((n > 0 && n < 4) || c.worldContactHas)) update_auto_roll(c, w, k, n);
     c.worldContactHas = 0;
+    RL_PT(2);
     vehicle_second(c, w, k);
     update_boost(c, w);
+    RL_PT(3);
 }
 
 RL_HD inline void car_respawn(CarS& c, int team, uint32_t rnd) {

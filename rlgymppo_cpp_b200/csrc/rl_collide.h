@@ -326,6 +326,32 @@ RL_HD inline void sphere_meshes(CollideCtx& x, ContactSink& cs, const MeshSet& m
     float am = radius + 0.08f;  // btSphereShape::getAabb
     V3 mn = center - V3(am, am, am), mx = center + V3(am, am, am);
     if (inside_free_box(ms, mn, mx)) return;
+    auto leaf = [&](Manifold& m, const BvhNode& nd) {  // one leaf whose box overlaps the sphere's
+        const Tri& t = ms.tris[nd.tri];
+        if (!tri_vs_aabb(t, mn, mx)) return;
+        auto sup = [&](V3 d) {  // btSphereShape::localGetSupportingVertex
+            float l2 = len2(d);
+            V3 dn = l2 < kEps * kEps ? V3(-1, -1, -1) : d;
+            return center + normalized(dn) * radius;
+        };
+        if (tri_early_out(t, breaking, sup)) return;
+        V3 point, normal; float depth;
+        if (sphere_triangle(center, radius, t, breaking, point, normal, depth)) manifold_add(x, m, normal, point, depth, &ms, nd.tri);
+    };
+    int first, count;
+    if (grid_lookup(ms, mn, mx, first, count)) {  // flat scan of the cell's leaf list: same leaves, same order as the walk below
+        int j = 0;
+        while (j < count) {
+            const int mi = ms.gridList[first + j] >> 24;
+            Manifold m; m.a = 0; m.b = -1; m.n = 0; m.breaking = breaking;
+            for (; j < count && (ms.gridList[first + j] >> 24) == mi; j++) {
+                const BvhNode& nd = ms.nodes[ms.gridList[first + j] & 0xffffff];
+                if (aabb_overlap(nd.mn, nd.mx, mn, mx)) leaf(m, nd);
+            }
+            manifold_flush(cs, m);
+        }
+        return;
+    }
     for (int mi = 0; mi < ms.numMeshes; mi++) {
         const BvhNode& root = ms.nodes[ms.nodeStart[mi]];
         if (!aabb_overlap(root.mn, root.mx, mn, mx)) continue;
@@ -336,20 +362,7 @@ RL_HD inline void sphere_meshes(CollideCtx& x, ContactSink& cs, const MeshSet& m
                 const BvhNode& nd = ms.nodes[i];
                 bool ov = aabb_overlap(nd.mn, nd.mx, mn, mx);
                 if (nd.tri >= 0) {
-                    if (ov) {
-                        const Tri& t = ms.tris[nd.tri];
-                        if (tri_vs_aabb(t, mn, mx)) {
-                            auto sup = [&](V3 d) {  // btSphereShape::localGetSupportingVertex
-                                float l2 = len2(d);
-                                V3 dn = l2 < kEps * kEps ? V3(-1, -1, -1) : d;
-                                return center + normalized(dn) * radius;
-                            };
-                            if (!tri_early_out(t, breaking, sup)) {
-                                V3 point, normal; float depth;
-                                if (sphere_triangle(center, radius, t, breaking, point, normal, depth)) manifold_add(x, m, normal, point, depth, &ms, nd.tri);
-                            }
-                        }
-                    }
+                    if (ov) leaf(m, nd);
                     i++;
                 } else {
                     i += ov ? 1 : nd.escape;

@@ -23,6 +23,8 @@ struct HostMeshSet {
     std::vector<BvhNode> nodes;
     std::vector<int32_t> hdrRoot, hdrSize, triFlags;
     std::vector<float> triEdgeAngles;
+    std::vector<uint32_t> gridRange;
+    std::vector<int32_t> gridList;
     MeshSet meta;  // pointers unset
 };
 
@@ -180,6 +182,57 @@ inline void host_build_edge_info(HostMeshSet& out) {
     }
 }
 
+// Leaf grid (rl_mesh.h MeshSet::gridRange/gridList): per cell, the leaves (mesh-major, depth-first order = the order of
+// the stackless walks) whose box overlaps the cell grown by margin + slack.  The slack absorbs the rounding of the
+// query's centre / half extents so that "half extents <= margin" really implies "inside the grown cell".
+inline void host_build_leaf_grid(HostMeshSet& out) {
+    MeshSet& ms = out.meta;
+    ms.gridRange = nullptr; ms.gridList = nullptr;
+    out.gridRange.clear(); out.gridList.clear();
+    if (out.nodes.empty()) return;
+    const float CELL = 5.f, MARGIN = 2.6f, SLACK = 0.05f;  // Bullet units (250 uu cells; ball box 1.905, car + wheel rays < 2.6)
+    V3 lo(1e30f, 1e30f, 1e30f), hi(-1e30f, -1e30f, -1e30f);
+    for (const BvhNode& nd : out.nodes) if (nd.tri >= 0) {
+        lo = vmin(lo, V3(nd.mn[0], nd.mn[1], nd.mn[2])); hi = vmax(hi, V3(nd.mx[0], nd.mx[1], nd.mx[2]));
+    }
+    // bodies can only be where the meshes / the four planes let them; cover the leaf bounds plus one cell
+    lo = lo - V3(CELL, CELL, CELL); hi = hi + V3(CELL, CELL, CELL);
+    int nx = (int)std::ceil((hi.x - lo.x) / CELL), ny = (int)std::ceil((hi.y - lo.y) / CELL), nz = (int)std::ceil((hi.z - lo.z) / CELL);
+    if (nx < 1 || ny < 1 || nz < 1 || (int64_t)nx * ny * nz > (int64_t)4 << 20) return;  // degenerate / absurd extents: BVH walks only
+    ms.gridOrigin = lo; ms.gridCell = CELL; ms.gridInvCell = 1.f / CELL; ms.gridMargin = MARGIN;
+    ms.gridNx = nx; ms.gridNy = ny; ms.gridNz = nz;
+    std::vector<std::vector<int32_t>> cells((size_t)nx * ny * nz);
+    const float G = MARGIN + SLACK;
+    for (int m = 0; m < ms.numMeshes; m++) {
+        for (int i = ms.nodeStart[m]; i < ms.nodeStart[m] + ms.nodeCount[m]; i++) {
+            const BvhNode& nd = out.nodes[i];
+            if (nd.tri < 0) continue;
+            int c0[3], c1[3];
+            const int dims[3] = {nx, ny, nz};
+            for (int a = 0; a < 3; a++) {
+                // cell k grown: [lo + k*CELL - G, lo + (k+1)*CELL + G] overlaps [mn, mx]
+                c0[a] = (int)std::floor((nd.mn[a] - G - lo[a]) / CELL) - 1;
+                c1[a] = (int)std::floor((nd.mx[a] + G - lo[a]) / CELL) + 1;
+                c0[a] = std::max(c0[a], 0); c1[a] = std::min(c1[a], dims[a] - 1);
+            }
+            for (int iz = c0[2]; iz <= c1[2]; iz++) for (int iy = c0[1]; iy <= c1[1]; iy++) for (int ix = c0[0]; ix <= c1[0]; ix++) {
+                float cmn[3] = {lo.x + ix * CELL - G, lo.y + iy * CELL - G, lo.z + iz * CELL - G};
+                float cmx[3] = {lo.x + (ix + 1) * CELL + G, lo.y + (iy + 1) * CELL + G, lo.z + (iz + 1) * CELL + G};
+                bool ov = !(nd.mn[0] > cmx[0] || nd.mx[0] < cmn[0] || nd.mn[1] > cmx[1] || nd.mx[1] < cmn[1] || nd.mn[2] > cmx[2] || nd.mx[2] < cmn[2]);
+                if (ov) cells[((size_t)iz * ny + iy) * nx + ix].push_back(i | (m << 24));
+            }
+        }
+    }
+    out.gridRange.resize(cells.size());
+    for (size_t c = 0; c < cells.size(); c++) {
+        size_t first = out.gridList.size();
+        if (cells[c].size() >= 255 || first >= ((size_t)1 << 24)) { out.gridRange[c] = 255u; continue; }  // too long: walk the BVH there
+        out.gridRange[c] = (uint32_t)(first << 8) | (uint32_t)cells[c].size();
+        out.gridList.insert(out.gridList.end(), cells[c].begin(), cells[c].end());
+    }
+    if (out.gridList.empty()) out.gridList.push_back(0);
+}
+
 inline void host_build_meshes(const void* const* blobs, const size_t* sizes, int n, HostMeshSet& out) {
     if (n > kMaxMeshes) throw std::runtime_error("too many collision meshes");
     out = HostMeshSet();
@@ -276,6 +329,7 @@ inline void host_build_meshes(const void* const* blobs, const size_t* sizes, int
     out.triFlags.assign(out.tris.size(), 0);
     out.triEdgeAngles.assign(out.tris.size() * 3, 6.283185307179586232f);
     host_build_edge_info(out);
+    host_build_leaf_grid(out);
 }
 
 // DiscreteAction table (G/Utils/ActionParsers/DiscreteAction.cpp:3-67)

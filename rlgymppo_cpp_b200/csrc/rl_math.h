@@ -30,6 +30,24 @@
 #define RL_WHEEL_LOOP _Pragma("unroll 1")
 #endif
 
+// Diagnostic builds (-DRLG_PHASE_TIMING, tools/phase_prof.py): per-warp cycle counters of the sub-phases of a tick.
+// RL_PT(i) adds the cycles since the warp's previous mark to slot i; no-ops in the product build.
+#if defined(RLG_PHASE_TIMING) && defined(__CUDACC__)
+static __device__ uint32_t* g_rl_pt;  // [block][warp][32]; slot 31 = last time stamp
+#endif
+#if defined(RLG_PHASE_TIMING) && defined(__CUDA_ARCH__)
+__device__ __forceinline__ void rl_pt_mark(int i) {
+    if ((int)(threadIdx.x & 31) != __ffs(__activemask()) - 1 || !g_rl_pt) return;
+    uint32_t* b = g_rl_pt + ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+    uint32_t now = (uint32_t)clock64();
+    if (i >= 0) b[i] += now - b[31];
+    b[31] = now;
+}
+#define RL_PT(i) rl_pt_mark(i)
+#else
+#define RL_PT(i) do {} while (0)
+#endif
+
 namespace rl {
 
 constexpr float kPi = 3.14159265358979323846f;

@@ -47,6 +47,17 @@ struct MeshSet {
     // lies inside it cannot reach a triangle, so the BVH walks are skipped with the same result (the arena meshes hug
     // the perimeter; most bodies are in the open field).  Empty (mn > mx) when a mesh covers the centre.
     V3 freeMn, freeMx;
+    // Leaf grid: the arena is static, so the set of leaf boxes a SMALL query box can overlap is precomputed per cell of
+    // a uniform grid: cell (ix, iy, iz) lists, in (mesh, depth-first leaf) order, every leaf whose box overlaps the cell
+    // grown by gridMargin on each side.  A query box whose half extents are <= gridMargin lies inside the grown cell of
+    // its centre, so scanning that one list with the same per-leaf overlap test returns exactly the leaves — in
+    // exactly the order — of the stackless BVH walks, as a short flat scan of independent loads instead of a chain of
+    // dependent node fetches (host_build_leaf_grid).  Bigger / out-of-grid queries fall back to the walks.
+    V3 gridOrigin;
+    float gridCell, gridInvCell, gridMargin;
+    int32_t gridNx, gridNy, gridNz;
+    const uint32_t* gridRange;  // per cell: first entry of gridList (24 bits) << 8 | min(count, 255); 255 = "walk the BVH"
+    const int32_t* gridList;    // leaf node index (global) | mesh << 24
 };
 RL_HDI bool inside_free_box(const MeshSet& ms, V3 mn, V3 mx) {
 #ifdef RL_NO_FREEBOX
@@ -163,9 +174,39 @@ struct MeshCands {
     int32_t n;        // -1: overflow -> callers use the direct BVH walks
     int32_t node[kMaxCands];  // global BVH leaf-node index | mesh << 24
 };
+// Leaf-grid lookup for the query box [mn, mx]: true + the list range when the grid answers it.
+RL_HDI bool grid_lookup(const MeshSet& ms, V3 mn, V3 mx, int& first, int& count) {
+#ifdef RL_NO_LEAF_GRID
+    return false;
+#endif
+    if (!ms.gridRange) return false;
+    V3 h = (mx - mn) * 0.5f, c = (mn + mx) * 0.5f;
+    if (!(fmaxf_(fmaxf_(h.x, h.y), h.z) <= ms.gridMargin)) return false;
+    V3 r = (c - ms.gridOrigin) * ms.gridInvCell;
+    if (!(r.x >= 0.f && r.y >= 0.f && r.z >= 0.f)) return false;
+    int ix = (int)r.x, iy = (int)r.y, iz = (int)r.z;
+    if (ix >= ms.gridNx || iy >= ms.gridNy || iz >= ms.gridNz) return false;
+    uint32_t e = ms.gridRange[(iz * ms.gridNy + iy) * ms.gridNx + ix];
+    count = (int)(e & 255u);
+    first = (int)(e >> 8);
+    return count != 255;
+}
+
 RL_HD inline void collect_candidates(const MeshSet& ms, V3 mn, V3 mx, MeshCands& out) {
     out.n = 0;
     if (inside_free_box(ms, mn, mx)) return;
+    int first, count;
+    if (grid_lookup(ms, mn, mx, first, count)) {
+        for (int j = 0; j < count; j++) {
+            int e = ms.gridList[first + j];
+            const BvhNode& nd = ms.nodes[e & 0xffffff];
+            if (aabb_overlap(nd.mn, nd.mx, mn, mx)) {
+                if (out.n >= kMaxCands) { out.n = -1; return; }
+                out.node[out.n++] = e;
+            }
+        }
+        return;
+    }
     for (int m = 0; m < ms.numMeshes; m++) {
         int i = ms.nodeStart[m], end = ms.nodeStart[m] + ms.nodeCount[m];
         while (i < end) {

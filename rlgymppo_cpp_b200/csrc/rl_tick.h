@@ -144,6 +144,7 @@ RL_HD inline void tick_p1_car(ArenaS& a, TickX x, const SimCfg& cfg, const MeshS
     // and a car demolished DURING this tick still responds and integrates until the next tick (Car.cpp:38-41,69-87)
     o.noResponse = car.isDemoed;
     o.ballVelCache = V3(); o.velCache = V3();
+    RL_PT(-1);
     car_pre_tick(car, x, cfg, ms, k, c, w, respawn_rnd(a, c));
     if (!o.noResponse) w.force += V3(0.f * UU2BT, 0.f * UU2BT, C::GRAVITY_Z * UU2BT) * C::CAR_MASS;  // applyGravity on active bodies
     o.force = w.force; o.torque = w.torque;
@@ -160,16 +161,21 @@ RL_HD inline void tick_p1_car(ArenaS& a, TickX x, const SimCfg& cfg, const MeshS
     bool overlapBall = !(bmn.x > o.cmx.x || bmx.x < o.cmn.x || bmn.y > o.cmx.y || bmx.y < o.cmn.y || bmn.z > o.cmx.z || bmx.z < o.cmn.z);
     if (overlapBall && !(!x.h->ballActive && o.noResponse)) car_ball(cx, cb, c, fminf_(thr.ball, thr.car));
     o.nCarBall = cb.n;
+    RL_PT(4);
     ContactSink cw = make_sink(seg_car(scratch, c) + 1, kSegCarWorld);
     if (w.cands.n >= 0) box_meshes_candidates(cx, cw, ms, w.cands, c, thr.car);
     else box_meshes(cx, cw, ms, c, thr.car);
+    RL_PT(5);
 #pragma unroll 1
     for (int p = 0; p < 4; p++) box_plane(cx, cw, c, p, thr.car);
     o.nCarWorld = cw.n;
+    RL_PT(6);
 }
 
 RL_HD inline void tick_p1_ball(ArenaS& a, TickX x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, const Thresholds& thr, Contact* scratch) {
+    RL_PT(-1);
     if (cfg.numCars > 0) pads_pre_tick(a);
+    RL_PT(7);
     CollideCtx cx; cx.a = &a; cx.cfg = &cfg; cx.tx = x; cx.k = &k; cx.tick = get_i64(a.tickLo, a.tickHi); cx.firstTickOfStep = 0;
     cx.ballPos = x.h->ballPos; cx.ballVel = x.h->ballVel * cfg.ballDampFactor;
     ContactSink cs = make_sink(seg_ball(scratch), kSegBall);
@@ -178,10 +184,12 @@ RL_HD inline void tick_p1_ball(ArenaS& a, TickX x, const SimCfg& cfg, const Mesh
     if (x.h->ballActive) {
         float ballR = C::BALL_RADIUS * UU2BT;
         sphere_meshes(cx, cs, ms, cx.ballPos, ballR, thr.ball);
+        RL_PT(8);
 #pragma unroll 1
         for (int p = 0; p < 4; p++) sphere_plane(cx, cs, cx.ballPos, ballR, p, thr.ball);
     }
     x.h->nBall = cs.n;
+    RL_PT(9);
 }
 
 // ---- P2: constraint solve, one simulation island per role ---------------------------------------------------------
@@ -218,6 +226,7 @@ RL_HDI void solver_body_from_car(SolverBody& b, const CarS& car, const CarX& o, 
 // solves it and the car finishes its tick after the next barrier).
 RL_HD inline bool tick_p2_car_self(ArenaS& a, TickX x, const SimCfg& cfg, const CarConsts& k, int c, Contact* scratch) {
     const CarX& o = x.car[c];
+    RL_PT(-1);
     if (car_is_coupled(x, cfg.numCars, c)) return false;
     if (o.noResponse) return true;
     CarS& car = a.cars[c];
@@ -233,6 +242,7 @@ RL_HD inline bool tick_p2_car_self(ArenaS& a, TickX x, const SimCfg& cfg, const 
     solver_body_from_car(b, car, o, k);
     solve_island(&b, 1, 1 + c, seg_car(scratch, c) + 1, o.nCarWorld);
     car.vel = b.linVel; car.angvel = b.angVel; car.pos = b.pos; car.rot = b.rot;
+    RL_PT(13);
     return true;
 }
 
@@ -242,6 +252,7 @@ RL_HD inline void tick_p2_solve(ArenaS& a, TickX x, const SimCfg& cfg, const Car
     const int64_t tick = get_i64(a.tickLo, a.tickHi);
     const bool ballActive = x.h->ballActive != 0;
     const float ballR = C::BALL_RADIUS * UU2BT;
+    RL_PT(-1);
     // predictUnconstraintMotion: damping (ball only: linear 0.03)
     a.ball.vel = a.ball.vel * cfg.ballDampFactor;
 
@@ -269,6 +280,7 @@ RL_HD inline void tick_p2_solve(ArenaS& a, TickX x, const SimCfg& cfg, const Car
             if (ov) car_car(cx, cp, c, d, thr.car);
         }
     x.h->nPair = cp.n;
+    RL_PT(10);
 
     const V3 gImp = V3(0.f * UU2BT, 0.f * UU2BT, C::GRAVITY_Z * UU2BT) * C::BALL_MASS;
 #ifdef RL_DEBUG_CONTACTS
@@ -348,6 +360,7 @@ RL_HD inline void tick_p2_solve(ArenaS& a, TickX x, const SimCfg& cfg, const Car
             a.ball.pos = sb[0].pos + a.ball.vel * dt;  // integrateTransformNoRot
         }
     }
+    RL_PT(11);
     // Ball::_FinishPhysicsTick (Ball.cpp:112-138)
     V3 ballVelCache;
     for (int c = 0; c < P; c++) ballVelCache += x.car[c].ballVelCache;
@@ -359,16 +372,19 @@ RL_HD inline void tick_p2_solve(ArenaS& a, TickX x, const SimCfg& cfg, const Car
     }
     a.ball.updateCounterLo++;
     set_i64(a.tickLo, a.tickHi, tick + 1);
+    RL_PT(12);
 }
 
 RL_HD inline void tick_p3_car(ArenaS& a, TickX x, const Tables& tb, const CarConsts& k, int c, CarW& w) {
     CarS& car = a.cars[c];
     CarX& o = x.car[c];
+    RL_PT(-1);
     if (!o.noResponse) integrate_transform(car.pos, car.rot, car.vel, car.angvel, kTickTime);
     w.velCache = o.velCache;
     car_post_tick(car, w);
     uint64_t hit = pads_check_car(a, tb, k, c);
     o.padHitLo = (uint32_t)hit; o.padHitHi = (uint32_t)(hit >> 32);
+    RL_PT(14);
 }
 
 RL_HD inline void tick_p4_pads(ArenaS& a, TickX x, const SimCfg& cfg) {

@@ -24,7 +24,7 @@ EXPORTS = [
     "rlg_engine_set_state", "rlg_engine_get_state", "rlg_engine_tick", "rlg_engine_eval_gym", "rlg_engine_step", "rlg_engine_step_noreset",
     "rlg_engine_outputs", "rlg_engine_obs_size", "rlg_engine_num_players", "rlg_engine_num_arenas",
     "rlg_engine_state_bytes_per_arena", "rlg_engine_player_order", "rlg_engine_set_player_order", "rlg_action_table",
-    "rlg_engine_step_host", "rlg_engine_read_outputs", "rlg_engine_launch_count", "rlg_engine_stream", "rlg_engine_sync",
+    "rlg_engine_step_host", "rlg_engine_host_buffers", "rlg_engine_step_pinned", "rlg_engine_read_outputs", "rlg_engine_launch_count", "rlg_engine_stream", "rlg_engine_sync",
     # collector / plumbing (bound in rlgymppo_cpp_b200.collector)
     "rlg_engine_step_to", "rlg_engine_device", "rlg_engine_arena_id_base", "rlg_engine_copy_to_host", "rlg_engine_copy_to_device",
     "rlg_collector_create", "rlg_collector_destroy", "rlg_collector_set_layer", "rlg_collector_infer", "rlg_collector_collect",
@@ -177,6 +177,26 @@ class Engine:
                                            None if obs is None else obs.ctypes.data_as(C.c_void_p),
                                            rew.ctypes.data_as(C.c_void_p), done.ctypes.data_as(C.c_void_p)))
         return obs, rew, done
+
+    def host_buffers(self):
+        """numpy views of the engine's page-locked host buffers: (action_idx [A*P] i32, obs [A*P, obs] f32,
+        reward [A*P] f32, done [A] u8); valid for the engine's lifetime."""
+        if getattr(self, "_hb", None) is None:
+            a, o, r, d = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+            _check(self.L.rlg_engine_host_buffers(self.h, C.byref(a), C.byref(o), C.byref(r), C.byref(d)))
+            n = self.A * self.P
+
+            def view(ptr, ctype, count, dtype, shape):
+                return np.frombuffer((ctype * count).from_address(ptr.value), dtype=dtype).reshape(shape)
+
+            self._hb = (view(a, C.c_int32, n, np.int32, (n,)), view(o, C.c_float, n * self.obs_size, np.float32, (n, self.obs_size)),
+                        view(r, C.c_float, n, np.float32, (n,)), view(d, C.c_uint8, self.A, np.uint8, (self.A,)))
+        return self._hb
+
+    def step_pinned(self, want_obs=True):
+        """Gym::Step for every arena through the page-locked host buffers of host_buffers() (no staging copies)."""
+        _check(self.L.rlg_engine_step_pinned(self.h, 1 if want_obs else 0))
+        return self.host_buffers()[1:]
 
     def read_outputs(self):
         obs = np.empty((self.A * self.P, self.obs_size), dtype=np.float32)

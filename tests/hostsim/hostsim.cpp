@@ -32,6 +32,7 @@ static void bind_mesh(HostSim* h) {
     h->ms.nodes = h->hm.nodes.data(); h->ms.tris = h->hm.tris.data();
     h->ms.hdrRoot = h->hm.hdrRoot.data(); h->ms.hdrSize = h->hm.hdrSize.data();
     h->ms.triFlags = h->hm.triFlags.data(); h->ms.triEdgeAngles = h->hm.triEdgeAngles.data();
+    if (!h->hm.gridRange.empty()) { h->ms.gridRange = h->hm.gridRange.data(); h->ms.gridList = h->hm.gridList.data(); }
 }
 
 extern "C" {
@@ -155,5 +156,30 @@ int hs_dump_contacts(float* out, int maxRows) {
     return n;
 }
 size_t hs_sizeof_arena() { return sizeof(ArenaS); }
+
+// leaf grid vs stackless BVH walk on random query boxes (centres over the whole arena incl. the goal boxes, half extents
+// in [halfMin, halfMax] Bullet units): out = {queries the grid answered, candidate leaves found, mismatching queries}
+void hs_grid_check(void* p, int n, uint64_t seed, float halfMin, float halfMax, int64_t* out) {
+    HostSim* h = (HostSim*)p;
+    MeshSet walk = h->ms; walk.gridRange = nullptr; walk.gridList = nullptr;
+    MeshSet nofree = h->ms; nofree.freeMn = V3(1, 1, 1); nofree.freeMx = V3(-1, -1, -1);  // exercise the empty cells too
+    walk.freeMn = nofree.freeMn; walk.freeMx = nofree.freeMx;
+    uint64_t z = seed;
+    auto rnd = [&]() { z += 0x9E3779B97F4A7C15ULL; uint64_t v = z; v = (v ^ (v >> 30)) * 0xBF58476D1CE4E5B9ULL; v = (v ^ (v >> 27)) * 0x94D049BB133111EBULL; v ^= v >> 31; return (float)((v >> 40) * (1.0 / 16777216.0)); };
+    out[0] = out[1] = out[2] = 0;
+    for (int q = 0; q < n; q++) {
+        V3 c((rnd() * 2 - 1) * 4200.f * UU2BT, (rnd() * 2 - 1) * 6100.f * UU2BT, (rnd() * 2150.f - 50.f) * UU2BT);
+        V3 hext(halfMin + rnd() * (halfMax - halfMin), halfMin + rnd() * (halfMax - halfMin), halfMin + rnd() * (halfMax - halfMin));
+        MeshCands a, b;
+        collect_candidates(nofree, c - hext, c + hext, a);
+        collect_candidates(walk, c - hext, c + hext, b);
+        int first, count;
+        if (grid_lookup(nofree, c - hext, c + hext, first, count)) out[0]++;
+        if (a.n > 0) out[1] += a.n;
+        bool same = a.n == b.n;
+        for (int i = 0; same && i < a.n; i++) same = a.node[i] == b.node[i];
+        if (!same) out[2]++;
+    }
+}
 
 }  // extern "C"

@@ -148,9 +148,10 @@ def test_full_size_properties(torch_cuda):
 def test_step_host_matches_device_path(torch_cuda):
     torch = torch_cuda
     cfg = abi.default_cfg(num_arenas=256, team_size=1)
-    e1, e2 = engine.Engine(cfg), engine.Engine(cfg)
-    e1.reset(); e2.reset()
+    e1, e2, e3 = engine.Engine(cfg), engine.Engine(cfg), engine.Engine(cfg)
+    e1.reset(); e2.reset(); e3.reset()
     rng = np.random.default_rng(1)
+    pinned_actions = e3.host_buffers()[0]
     for s in range(8):
         a = rng.integers(0, 90, size=e1.A * e1.P).astype(np.int32)
         o1, r1, d1 = e1.step_host(a)
@@ -158,6 +159,9 @@ def test_step_host_matches_device_path(torch_cuda):
         e2.step_device(t.data_ptr())
         o2, r2, d2 = e2.read_outputs()
         assert np.array_equal(o1, o2) and np.array_equal(r1, r2) and np.array_equal(d1, d2)
+        pinned_actions[:] = a  # the zero-copy variant: engine-owned page-locked buffers
+        o3, r3, d3 = e3.step_pinned()
+        assert np.array_equal(o1, o3) and np.array_equal(r1, r3) and np.array_equal(d1, d3)
 
 
 def test_against_compiled_reference_if_present(torch_cuda):

@@ -77,3 +77,18 @@ def test_state_setters_statistics():
                 x, y = -x, -y
             assert (round(x), round(y)) in spots
             assert abs(c["boost"] - 100 / 3) < 1e-4
+
+
+def test_leaf_grid_returns_the_bvh_walks_leaves_in_order():
+    """The per-cell leaf lists (rl_mesh.h grid_lookup) must give exactly the stackless walks' candidate leaves, in the
+    walks' order, for every query box the grid accepts; bigger boxes must fall back to the walk."""
+    import ctypes as C
+
+    h = hostsim.HostSim(abi.default_cfg(num_arenas=1, team_size=1))
+    out = (C.c_int64 * 3)()
+    h.L.hs_grid_check(h.h, 200000, C.c_uint64(7), C.c_float(0.3), C.c_float(2.6), out)
+    answered, found, mismatches = out[0], out[1], out[2]
+    assert mismatches == 0
+    assert answered == 200000 and found > 10000  # every small box is answered by the grid, and plenty reach leaves
+    h.L.hs_grid_check(h.h, 20000, C.c_uint64(8), C.c_float(2.0), C.c_float(6.0), out)
+    assert out[2] == 0 and 0 < out[0] < 20000  # mixed: some too big for the grid -> walk, same answer
