@@ -165,6 +165,101 @@ __device__ __forceinline__ void cp_async4(uint32_t* smemDst, const uint32_t* gme
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmemSrc) : "memory");
 }
 
+// ---- warp-cooperative hitbox-vs-mesh narrowphase ---------------------------------------------------------------------
+// In a car-role warp only a few lanes (cars near the mesh) have candidate triangles, and the per-triangle test
+// (support-plane early out + GJK / SAT) is the longest serial stretch of the tick.  Instead of every such lane looping
+// over its own triangles while the rest of the warp idles, the warp gathers all (car, triangle) pairs into a small
+// shared-memory queue (a lane's pairs stay contiguous and in candidate order), evaluates them 32 at a time — one pair
+// per lane, every lane in the same code — and each car's own lane then feeds its results, in order, to the manifold
+// exactly like box_meshes_candidates does.  Cars whose pairs do not fit the queue, or whose candidate list overflowed,
+// take the serial path.  All 32 lanes of the warp must call this (active = the lane has a car to process).
+constexpr int kWqItems = 96;                       // pairs queued per warp and tick
+constexpr int kWqResWords = 8;                     // hit, normal, pointOnB, dist
+constexpr int kWqWords = kWqItems + 32 * kWqResWords;
+__device__ __forceinline__ void box_meshes_warp(CollideCtx& cx, ContactSink& cw, const MeshSet& ms, const MeshCands& cands, int ci, float breaking,
+                                                bool active, const CarConsts& k, const uint32_t* mine, uint32_t* wq, int stride) {
+    // cx / cw / cands are only meaningful on active lanes; k, mine (this lane's arena slot), wq and stride on all of them
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    bool serial = active && cands.n < 0;
+    const int n = (active && cands.n > 0) ? cands.n : 0;
+    uint32_t mask = 0, groupStart = 0;  // candidates that pass the node-box test; first candidate of each mesh group
+    if (n > 0) {
+        const CarS& c = cx.a->cars[ci];
+        V3 boxCenter = c.pos + c.rot * k.hitboxOffset;
+        V3 ext(dot(vabs(c.rot.r[0]), k.halfExt), dot(vabs(c.rot.r[1]), k.halfExt), dot(vabs(c.rot.r[2]), k.halfExt));
+        V3 mn = boxCenter - ext, mx = boxCenter + ext;
+        for (int j = 0; j < n; j++) {
+            const BvhNode& nd = ms.nodes[cands.node[j] & 0xffffff];
+            if (aabb_overlap(nd.mn, nd.mx, mn, mx)) mask |= 1u << j;
+            if (j == 0 || (cands.node[j] >> 24) != (cands.node[j - 1] >> 24)) groupStart |= 1u << j;
+        }
+    }
+    const int cnt = __popc(mask);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(full, incl, d); if (lane >= d) incl += v; }
+    const int base = incl - cnt;
+    const bool fits = cnt > 0 && incl <= kWqItems;
+    if (cnt > 0 && !fits) serial = true;
+    const unsigned fitLanes = __ballot_sync(full, fits);
+    if (fitLanes) {
+        const int totalFit = __shfl_sync(full, incl, 31 - __clz(fitLanes));  // the fitting lanes' pairs are a prefix of the queue
+        if (fits) {
+            int i = base;
+            for (uint32_t m = mask; m; m &= m - 1) wq[i++] = (uint32_t)(cands.node[__ffs(m) - 1] & 0xffffff) | ((uint32_t)lane << 24);
+        }
+        __syncwarp();
+        Manifold m; m.a = 1 + ci; m.b = -1; m.n = 0; m.breaking = breaking;
+        uint32_t rem = fits ? mask : 0u;  // own pairs not yet consumed
+        int next = base;                  // queue index of the next own pair
+        int lastJ = 0;                    // candidate that last fed the open manifold
+        uint32_t* res = wq + kWqItems;
+        for (int r0 = 0; r0 < totalFit; r0 += 32) {
+            const int g = r0 + lane;
+            if (g < totalFit) {
+                const uint32_t it = wq[g];
+                const int owner = (int)(it >> 24);
+                const ArenaS& so = *reinterpret_cast<const ArenaS*>(mine + (owner - lane) * stride);
+                const CarS& c = so.cars[ci];
+                V3 boxCenter = c.pos + c.rot * k.hitboxOffset;
+                V3 ext(dot(vabs(c.rot.r[0]), k.halfExt), dot(vabs(c.rot.r[1]), k.halfExt), dot(vabs(c.rot.r[2]), k.halfExt));
+                V3 normal, point; float dist = 0.f;
+                const bool hit = box_mesh_item(c, k, boxCenter, boxCenter - ext, boxCenter + ext, ms.tris[ms.nodes[it & 0xffffff].tri], breaking, normal, point, dist);
+                uint32_t* r = res + lane * kWqResWords;
+                r[0] = hit ? 1u : 0u;
+                if (hit) {
+                    r[1] = __float_as_uint(normal.x); r[2] = __float_as_uint(normal.y); r[3] = __float_as_uint(normal.z);
+                    r[4] = __float_as_uint(point.x); r[5] = __float_as_uint(point.y); r[6] = __float_as_uint(point.z);
+                    r[7] = __float_as_uint(dist);
+                }
+            }
+            __syncwarp();
+            while (rem && next < r0 + 32) {
+                const int j = __ffs(rem) - 1;
+                rem &= rem - 1;
+                const uint32_t* r = res + (next - r0) * kWqResWords;
+                next++;
+                if (r[0]) {
+                    // a mesh-group boundary in (lastJ, j]: the open manifold belongs to an earlier mesh -> close it
+                    // (one manifold per mesh: btCompoundCollisionAlgorithm -> btConvexConcaveCollisionAlgorithm)
+                    if (m.n > 0 && (groupStart & ((2u << j) - 1u) & ~((2u << lastJ) - 1u))) { manifold_flush(cw, m); m.n = 0; }
+                    lastJ = j;
+                    manifold_add(cx, m, V3(__uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3])),
+                                 V3(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6])), __uint_as_float(r[7]), &ms,
+                                 ms.nodes[cands.node[j] & 0xffffff].tri);
+                }
+            }
+            __syncwarp();
+        }
+        if (m.n > 0) manifold_flush(cw, m);
+    }
+    if (serial) {
+        if (cands.n >= 0) box_meshes_candidates(cx, cw, ms, cands, ci, breaking);
+        else box_meshes(cx, cw, ms, ci, breaking);
+    }
+}
+
 __global__ void __maxnreg__(168) k_roles(const __grid_constant__ RolesArgs g) {
     extern __shared__ uint32_t smem[];
     // warp = (arena group, role): the groups of a block run the same phase at the same time, so a role's instruction
@@ -179,6 +274,8 @@ __global__ void __maxnreg__(168) k_roles(const __grid_constant__ RolesArgs g) {
     ArenaS& s = *reinterpret_cast<ArenaS*>(mine);
     TickX x = make_tickx(mine + (g.stride - g.xwords));
     Contact* scratch = g.scratch + (size_t)(valid ? a : 0) * g.scratchSlots;
+    // per car-role warp: the pair queue of the cooperative hitbox-mesh narrowphase, behind the arena slots
+    uint32_t* wq = smem + (size_t)g.arenasPerBlock * g.stride + (size_t)(group * P + (role > 0 ? role - 1 : 0)) * kWqWords;
     // the groups of a block never touch each other's arenas: every barrier may be group-local (named barrier 1 + group)
     const int barId = 1 + group, barThreads = 32 * roles;
 #define SYNC_GROUP() do { PT_WORK(9); if (g.barMode == 0) __syncthreads(); else bar_named(barId, barThreads); PT_WORK(7); } while (0)
@@ -218,9 +315,13 @@ __global__ void __maxnreg__(168) k_roles(const __grid_constant__ RolesArgs g) {
         if (valid) { if (role == 0) tick_s0_ball(s, x); else tick_s0_car(s, x, role - 1); }
         PT_WORK(1);
         if (g.barMode == 2 && t > 0) SYNC_TICK(); else SYNC_GROUP();  // B1
-        if (valid) {
-            if (role == 0) tick_p1_ball(s, x, g.cfg, g.ms, k, thr, scratch);
-            else tick_p1_car(s, x, g.cfg, g.ms, k, thr, role - 1, w, scratch, first);
+        if (role == 0) {
+            if (valid) tick_p1_ball(s, x, g.cfg, g.ms, k, thr, scratch);
+        } else {
+            CollideCtx cx; ContactSink cw;
+            if (valid) tick_p1_car_begin(s, x, g.cfg, g.ms, k, thr, role - 1, w, scratch, first, cx, cw);
+            box_meshes_warp(cx, cw, g.ms, w.cands, role - 1, thr.car, valid, k, mine, wq, g.stride);  // whole warp
+            if (valid) tick_p1_car_end(cx, cw, x, thr, role - 1);
         }
         PT_WORK(2);
         SYNC_GROUP();  // B2
@@ -386,7 +487,9 @@ int rlg_engine_create(const rlg_engine_cfg* cfg, rlg_engine** out) {
         cudaDeviceProp prop;
         CKD(cudaGetDeviceProperties(&prop, e->device));
         int perSm = (A + prop.multiProcessorCount - 1) / prop.multiProcessorCount;
-        int maxBySmem = (int)((prop.sharedMemPerBlockOptin - 1024) / ((size_t)e->stride * 4));
+        // per arena slot: its words + its share of the car warps' pair queues; slots are allocated in whole groups of 32
+        // (the last group may be partial: keep one group's queues in reserve)
+        int maxBySmem = (int)((prop.sharedMemPerBlockOptin - 1024 - (size_t)P * kWqWords * 4) / (((size_t)e->stride + (size_t)P * kWqWords / 32) * 4));
         cudaFuncAttributes fa;
         CKD(cudaFuncGetAttributes(&fa, k_roles));
         int maxThreads = prop.regsPerBlock / (fa.numRegs > 0 ? fa.numRegs : 1);
@@ -416,7 +519,7 @@ int rlg_engine_create(const rlg_engine_cfg* cfg, rlg_engine** out) {
         CKD(cudaMemcpyToSymbol(g_rl_pt, &e->prof2, sizeof(e->prof2)));
     }
 #endif
-    e->rolesSmem = (size_t)e->arenasPerBlock * e->stride * 4;
+    e->rolesSmem = ((size_t)e->arenasPerBlock * e->stride + (size_t)e->groupsPerBlock * P * kWqWords) * 4;
     CKD(cudaFuncSetAttribute(k_roles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->rolesSmem));
     if (const char* cv = getenv("RLG_SMEM_CARVEOUT")) CKD(cudaFuncSetAttribute(k_roles, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
     CKD(cudaMalloc(&e->state, (size_t)e->nwords * A * 4));

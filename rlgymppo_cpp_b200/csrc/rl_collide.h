@@ -375,18 +375,23 @@ RL_HD inline void sphere_meshes(CollideCtx& x, ContactSink& cs, const MeshSet& m
 
 // car hitbox vs every mesh: btCompoundCollisionAlgorithm -> btConvexConcaveCollisionAlgorithm -> GJK per triangle
 // one candidate triangle of the hitbox-vs-mesh narrowphase (shared by the direct walk and the candidate-list path)
-RL_HDI void box_mesh_triangle(CollideCtx& x, Manifold& m, const MeshSet& ms, const CarS& c, const CarConsts& k, V3 boxCenter, V3 mn, V3 mx,
-                              int triIdx, float breaking) {
-    const Tri& t = ms.tris[triIdx];
-    if (!tri_vs_aabb(t, mn, mx)) return;
+// The geometric part is a pure function of (car pose, triangle) — the role kernel evaluates it for many (car, triangle)
+// pairs at once, one pair per lane (engine.cu box_meshes_warp); the manifold bookkeeping stays with the car's own lane.
+RL_HDI bool box_mesh_item(const CarS& c, const CarConsts& k, V3 boxCenter, V3 mn, V3 mx, const Tri& t, float breaking, V3& normal, V3& pointOnB,
+                          float& dist) {
+    if (!tri_vs_aabb(t, mn, mx)) return false;
     auto sup = [&](V3 d) {  // btBoxShape::localGetSupportingVertex (with margin)
         V3 dl = tmul(d, c.rot);
         V3 v(dl.x >= 0 ? k.halfExt.x : -k.halfExt.x, dl.y >= 0 ? k.halfExt.y : -k.halfExt.y, dl.z >= 0 ? k.halfExt.z : -k.halfExt.z);
         return boxCenter + c.rot * v;
     };
-    if (tri_early_out(t, breaking, sup)) return;
+    if (tri_early_out(t, breaking, sup)) return false;
+    return box_triangle_contact(boxCenter, c.rot, k.halfExt, k.coreHalf, k.boxMargin, t, breaking, normal, pointOnB, dist);
+}
+RL_HDI void box_mesh_triangle(CollideCtx& x, Manifold& m, const MeshSet& ms, const CarS& c, const CarConsts& k, V3 boxCenter, V3 mn, V3 mx,
+                              int triIdx, float breaking) {
     V3 normal, pointOnB; float dist;
-    if (box_triangle_contact(boxCenter, c.rot, k.halfExt, k.coreHalf, k.boxMargin, t, breaking, normal, pointOnB, dist))
+    if (box_mesh_item(c, k, boxCenter, mn, mx, ms.tris[triIdx], breaking, normal, pointOnB, dist))
         manifold_add(x, m, normal, pointOnB, dist, &ms, triIdx);
 }
 

@@ -136,8 +136,11 @@ RL_HDI void tick_s0_ball(const ArenaS& a, TickX x) {
     x.h->ballActive = !(len2(a.ball.vel) == 0.f && len2(a.ball.angvel) == 0.f);
 }
 
-RL_HD inline void tick_p1_car(ArenaS& a, TickX x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, const Thresholds& thr, int c, CarW& w,
-                              Contact* scratch, int firstTickOfStep) {
+// tick_p1_car = begin (pre-tick, car-ball) + hitbox-mesh narrowphase + end (hitbox-plane, counts).  The role kernel
+// replaces the middle part by the warp-cooperative box_meshes_warp (engine.cu): same triangles, same order, same
+// arithmetic per triangle (box_mesh_item), so the contacts are identical.
+RL_HD inline void tick_p1_car_begin(ArenaS& a, TickX x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, const Thresholds& thr, int c, CarW& w,
+                                    Contact* scratch, int firstTickOfStep, CollideCtx& cx, ContactSink& cw) {
     CarS& car = a.cars[c];
     CarX& o = x.car[c];
     // activation state / contact response are decided at the top of Car::_PreTickUpdate, before a possible respawn,
@@ -152,7 +155,7 @@ RL_HD inline void tick_p1_car(ArenaS& a, TickX x, const SimCfg& cfg, const MeshS
     V3 ext(dot(vabs(car.rot.r[0]), k.halfExt), dot(vabs(car.rot.r[1]), k.halfExt), dot(vabs(car.rot.r[2]), k.halfExt));
     o.cmn = center - ext; o.cmx = center + ext;
 
-    CollideCtx cx; cx.a = &a; cx.cfg = &cfg; cx.tx = x; cx.k = &k; cx.tick = get_i64(a.tickLo, a.tickHi); cx.firstTickOfStep = firstTickOfStep;
+    cx.a = &a; cx.cfg = &cfg; cx.tx = x; cx.k = &k; cx.tick = get_i64(a.tickLo, a.tickHi); cx.firstTickOfStep = firstTickOfStep;
     cx.ballPos = x.h->ballPos; cx.ballVel = x.h->ballVel * cfg.ballDampFactor;  // predictUnconstraintMotion damping precedes the narrowphase
     // car-ball (manifold order: all car-ball pairs precede the car-world pairs)
     ContactSink cb = make_sink(seg_car(scratch, c), 1);
@@ -162,14 +165,24 @@ RL_HD inline void tick_p1_car(ArenaS& a, TickX x, const SimCfg& cfg, const MeshS
     if (overlapBall && !(!x.h->ballActive && o.noResponse)) car_ball(cx, cb, c, fminf_(thr.ball, thr.car));
     o.nCarBall = cb.n;
     RL_PT(4);
-    ContactSink cw = make_sink(seg_car(scratch, c) + 1, kSegCarWorld);
-    if (w.cands.n >= 0) box_meshes_candidates(cx, cw, ms, w.cands, c, thr.car);
-    else box_meshes(cx, cw, ms, c, thr.car);
+    cw = make_sink(seg_car(scratch, c) + 1, kSegCarWorld);
+}
+
+RL_HD inline void tick_p1_car_end(CollideCtx& cx, ContactSink& cw, TickX x, const Thresholds& thr, int c) {
     RL_PT(5);
 #pragma unroll 1
     for (int p = 0; p < 4; p++) box_plane(cx, cw, c, p, thr.car);
-    o.nCarWorld = cw.n;
+    x.car[c].nCarWorld = cw.n;
     RL_PT(6);
+}
+
+RL_HD inline void tick_p1_car(ArenaS& a, TickX x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, const Thresholds& thr, int c, CarW& w,
+                              Contact* scratch, int firstTickOfStep) {
+    CollideCtx cx; ContactSink cw;
+    tick_p1_car_begin(a, x, cfg, ms, k, thr, c, w, scratch, firstTickOfStep, cx, cw);
+    if (w.cands.n >= 0) box_meshes_candidates(cx, cw, ms, w.cands, c, thr.car);
+    else box_meshes(cx, cw, ms, c, thr.car);
+    tick_p1_car_end(cx, cw, x, thr, c);
 }
 
 RL_HD inline void tick_p1_ball(ArenaS& a, TickX x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, const Thresholds& thr, Contact* scratch) {
