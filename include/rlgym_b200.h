@@ -249,6 +249,23 @@ int rlg_engine_step_pinned(rlg_engine* e, int want_obs);
 int rlg_engine_copy_to_host(rlg_engine* e, void* dst_host, const void* src_dev, size_t bytes);
 int rlg_engine_copy_to_device(rlg_engine* e, void* dst_dev, const void* src_host, size_t bytes);
 
+/* GameInst's reward metrics (P/public/RLGymPPO_CPP/Threading/GameInst.cpp:13-31: avgStepRew.Add(sum of the players'
+ * rewards, playerAmount); curEpRew += that sum / playerAmount; on done avgEpRew += curEpRew) accumulated on the device
+ * per arena by every fused Gym::Step, and summed over the arenas in arena order like
+ * ThreadAgentManager::GetMetrics (P/private/RLGymPPO_CPP/Threading/ThreadAgentManager.cpp:82-92).  The averages are
+ * NaN while their count is 0 (AvgTracker::Get, P/public/RLGymPPO_CPP/Util/AvgTracker.h:14-20). */
+typedef struct rlg_metrics_host {
+    float avg_step_reward;      /* report["Average Step Reward"] */
+    float avg_episode_reward;   /* report["Average Episode Reward"] */
+    float step_reward_total;
+    float episode_reward_total;
+    uint64_t step_reward_count; /* player-steps */
+    uint64_t episode_count;     /* finished episodes */
+    uint64_t total_steps;       /* GameInst::totalSteps summed over the arenas (never reset) */
+} rlg_metrics_host;
+int rlg_engine_metrics(rlg_engine* e, rlg_metrics_host* out);   /* synchronises the engine stream */
+int rlg_engine_reset_metrics(rlg_engine* e);                    /* GameInst::ResetMetrics for every arena */
+
 /* Number of kernel launches issued by this engine so far (bench "gpu_launches"). */
 uint64_t rlg_engine_launch_count(const rlg_engine* e);
 /* Wait for all work queued on the engine's stream. */

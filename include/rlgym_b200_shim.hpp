@@ -589,9 +589,13 @@ public:
     void GetMetrics(Report& report) {
         double sm = 0, im = 0; int32_t sn = 0, in = 0;
         RLGB200::Check(rlg_collector_kernel_times(collector, &sm, &sn, &im, &in));
+        rlg_metrics_host m;
+        RLGB200::Check(rlg_engine_metrics(engine->h, &m));
+        report["Average Step Reward"] = m.avg_step_reward;
+        report["Average Episode Reward"] = m.avg_episode_reward;
         report["Env Step Time"] = sm * 1e-3;
         report["Policy Infer Time"] = im * 1e-3;
     }
-    void ResetMetrics() {}
+    void ResetMetrics() { RLGB200::Check(rlg_engine_reset_metrics(engine->h)); }
 };
 }  // namespace RLGPC

@@ -54,6 +54,13 @@ class CarState(C.Structure):
     ]
 
 
+class MetricsHost(C.Structure):
+    """rlg_metrics_host: GameInst's avgStepRew / avgEpRew summed over the arenas (GameInst.cpp:13-31, ThreadAgentManager.cpp:82-92)."""
+    _fields_ = [("avg_step_reward", C.c_float), ("avg_episode_reward", C.c_float), ("step_reward_total", C.c_float),
+                ("episode_reward_total", C.c_float), ("step_reward_count", C.c_uint64), ("episode_count", C.c_uint64),
+                ("total_steps", C.c_uint64)]
+
+
 class BallState(C.Structure):
     _fields_ = [("pos", F3), ("vel", F3), ("ang_vel", F3)]
 

@@ -9,6 +9,7 @@
 // returns RLG_ERR_CUDA when it is not usable.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -50,6 +51,7 @@ struct rlg_engine {
     float* hReward = nullptr;
     uint8_t* hDone = nullptr;
     Contact* scratch = nullptr;  // per-arena contact segments (rl_collide.h ContactSink)
+    float* metrics = nullptr;    // [kMetricWords][A]: stepTotal, stepCount (u32), epTotal, epCount (u32), curEpRew, totalSteps (u32)
     int xwords = 0, stride = 0, scratchSlots = 0;
     int arenasPerBlock = 32, groupsPerBlock = 1;
     size_t rolesSmem = 0;
@@ -148,7 +150,9 @@ struct RolesArgs {
     Thresholds thr; // instead of a per-thread local-memory copy (the wheel arrays are indexed dynamically)
     const rlg_controls* controls; int nticks;
     const int32_t* actions; float* obs; float* reward; uint8_t* done; int autoReset;
+    float* metrics;  // GameInst reward metrics, word-transposed [kMetricWords][A] (nullptr: not tracked)
 };
+constexpr int kMetricWords = 6;
 
 constexpr int kProfSlots = 10;  // load, s0, p1, p2, p3, p4+gym, reset+store, barrier wait, total, unused
 #ifdef RLG_PHASE_TIMING
@@ -165,46 +169,114 @@ __device__ __forceinline__ void cp_async4(uint32_t* smemDst, const uint32_t* gme
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmemSrc) : "memory");
 }
 
-// ---- warp-cooperative hitbox-vs-mesh narrowphase ---------------------------------------------------------------------
-// In a car-role warp only a few lanes (cars near the mesh) have candidate triangles, and the per-triangle test
-// (support-plane early out + GJK / SAT) is the longest serial stretch of the tick.  Instead of every such lane looping
-// over its own triangles while the rest of the warp idles, the warp gathers all (car, triangle) pairs into a small
-// shared-memory queue (a lane's pairs stay contiguous and in candidate order), evaluates them 32 at a time — one pair
-// per lane, every lane in the same code — and each car's own lane then feeds its results, in order, to the manifold
-// exactly like box_meshes_candidates does.  Cars whose pairs do not fit the queue, or whose candidate list overflowed,
-// take the serial path.  All 32 lanes of the warp must call this (active = the lane has a car to process).
-constexpr int kWqItems = 96;                       // pairs queued per warp and tick
-constexpr int kWqResWords = 8;                     // hit, normal, pointOnB, dist
+// ---- warp-cooperative mesh passes of a car-role warp --------------------------------------------------------------------
+// In a car-role warp only a few lanes (cars near the mesh) have candidate triangles, and scanning a candidate list is a
+// chain of dependent loads (list entry -> BVH leaf -> triangle) followed by the longest serial stretches of the tick
+// (ray-triangle tests for four wheels, support-plane early out + GJK / SAT for the hitbox).  Instead of every such lane
+// walking its own list while the rest of the warp idles, the warp queues its (car, candidate) pairs in shared memory —
+// a lane's pairs stay contiguous and in candidate order — and evaluates them 32 at a time, one pair per lane, every lane
+// in the same code; each car's own lane then folds its results in candidate order, exactly like the serial scans
+// (wheel_mesh_rays, box_meshes_candidates).  Cars whose pairs do not fit the queue, or whose candidate list overflowed,
+// take the serial path.  All 32 lanes of the warp must call these (active = the lane has a car to process); cx / cw /
+// w are only meaningful on active lanes, k, mine (this lane's arena slot), wq and stride on all of them.
+constexpr int kWqItems = 128;                      // pairs queued per warp and pass
+constexpr int kWqResWords = 8;
 constexpr int kWqWords = kWqItems + 32 * kWqResWords;
-__device__ __forceinline__ void box_meshes_warp(CollideCtx& cx, ContactSink& cw, const MeshSet& ms, const MeshCands& cands, int ci, float breaking,
-                                                bool active, const CarConsts& k, const uint32_t* mine, uint32_t* wq, int stride) {
-    // cx / cw / cands are only meaningful on active lanes; k, mine (this lane's arena slot), wq and stride on all of them
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += u; }
+    return v;
+}
+
+// Pass 1 (right after the candidates are collected): the mesh part of the four wheel rays -> w.meshHit, and the hitbox
+// pre-filter (leaf box vs hitbox AABB) -> w.candMask / w.candGroupStart.
+__device__ __forceinline__ void cands_pass_warp(CarW& w, int ci, bool active, const CarConsts& k, const MeshSet& ms, const uint32_t* mine, uint32_t* wq,
+                                                int stride) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    bool serial = active && cands.n < 0;
-    const int n = (active && cands.n > 0) ? cands.n : 0;
-    uint32_t mask = 0, groupStart = 0;  // candidates that pass the node-box test; first candidate of each mesh group
-    if (n > 0) {
-        const CarS& c = cx.a->cars[ci];
-        V3 boxCenter = c.pos + c.rot * k.hitboxOffset;
-        V3 ext(dot(vabs(c.rot.r[0]), k.halfExt), dot(vabs(c.rot.r[1]), k.halfExt), dot(vabs(c.rot.r[2]), k.halfExt));
-        V3 mn = boxCenter - ext, mx = boxCenter + ext;
-        for (int j = 0; j < n; j++) {
-            const BvhNode& nd = ms.nodes[cands.node[j] & 0xffffff];
-            if (aabb_overlap(nd.mn, nd.mx, mn, mx)) mask |= 1u << j;
-            if (j == 0 || (cands.node[j] >> 24) != (cands.node[j - 1] >> 24)) groupStart |= 1u << j;
+    if (active) wheel_mesh_rays_init(w);
+    const int n = (active && w.cands.n > 0) ? w.cands.n : 0;
+    const int incl = warp_incl_scan(n, lane);
+    const int base = incl - n;
+    const bool fits = active && w.cands.n >= 0 && incl <= kWqItems;
+    const unsigned fitLanes = __ballot_sync(full, fits && n > 0);
+    if (fitLanes) {
+        const int totalFit = __shfl_sync(full, incl, 31 - __clz(fitLanes));  // the fitting lanes' pairs are a prefix of the queue
+        if (fits) {
+            uint32_t gs = 0;
+            for (int j = 0; j < n; j++) {
+                const int e = w.cands.node[j];
+                wq[base + j] = (uint32_t)(e & 0xffffff) | ((uint32_t)lane << 24);
+                if (j == 0 || (e >> 24) != (w.cands.node[j - 1] >> 24)) gs |= 1u << j;
+            }
+            w.candGroupStart = gs;
         }
+        __syncwarp();
+        uint32_t* res = wq + kWqItems;
+        int next = 0;  // own candidates folded so far
+        uint32_t mask = 0;
+        for (int r0 = 0; r0 < totalFit; r0 += 32) {
+            const int g = r0 + lane;
+            if (g < totalFit) {
+                const uint32_t it = wq[g];
+                const int owner = (int)(it >> 24);
+                const ArenaS& so = *reinterpret_cast<const ArenaS*>(mine + (owner - lane) * stride);
+                const CarS& c = so.cars[ci];
+                const BvhNode& nd = ms.nodes[it & 0xffffff];
+                V3 boxCenter = c.pos + c.rot * k.hitboxOffset;
+                V3 ext(dot(vabs(c.rot.r[0]), k.halfExt), dot(vabs(c.rot.r[1]), k.halfExt), dot(vabs(c.rot.r[2]), k.halfExt));
+                uint32_t flags = aabb_overlap(nd.mn, nd.mx, boxCenter - ext, boxCenter + ext) ? 16u : 0u;
+                uint32_t* r = res + lane * kWqResWords;
+                if (!c.isDemoed) {  // Car::_PreTickUpdate returns before the vehicle update
+                    const Tri& t = ms.tris[nd.tri];
+                    V3 from[4], to[4];
+                    wheel_ray_segments(c, k, from, to);
+                    TriRays tr;
+                    ray_tri4(from, to, t.v0, t.v1, t.v2, tr);
+                    r[0] = __float_as_uint(tr.d[0]); r[1] = __float_as_uint(tr.d[1]); r[2] = __float_as_uint(tr.d[2]); r[3] = __float_as_uint(tr.d[3]);
+                    r[4] = __float_as_uint(tr.nn.x); r[5] = __float_as_uint(tr.nn.y); r[6] = __float_as_uint(tr.nn.z);
+                    flags |= tr.neg;
+                } else {
+                    r[0] = r[1] = r[2] = r[3] = __float_as_uint(2.f);
+                }
+                r[7] = flags;
+            }
+            __syncwarp();
+            if (fits) {
+                while (next < n && base + next < r0 + 32) {
+                    const uint32_t* r = res + (base + next - r0) * kWqResWords;
+                    const float d[4] = {__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3])};
+                    ray_tri4_apply(d, V3(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6])), r[7] & 15u, w.meshHit);
+                    mask |= ((r[7] >> 4) & 1u) << next;
+                    next++;
+                }
+            }
+            __syncwarp();
+        }
+        if (fits) w.candMask = mask;
     }
+    if (fits) w.haveMask = 1;
+    else if (active) wheel_mesh_rays(reinterpret_cast<const ArenaS*>(mine)->cars[ci], k, ms, w);  // serial; haveMask stays 0
+}
+
+// Pass 2 (after car-ball): hitbox vs the pre-filtered candidate triangles -> the car's car-world contact segment.
+__device__ __forceinline__ void box_meshes_warp(CollideCtx& cx, ContactSink& cw, const MeshSet& ms, const CarW& w, int ci, float breaking,
+                                                bool active, const CarConsts& k, const uint32_t* mine, uint32_t* wq, int stride) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const MeshCands& cands = w.cands;
+    bool serial = active && !w.haveMask;
+    const uint32_t mask = (active && w.haveMask) ? w.candMask : 0u;
+    const uint32_t groupStart = mask ? w.candGroupStart : 0u;
     const int cnt = __popc(mask);
-    int incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(full, incl, d); if (lane >= d) incl += v; }
+    const int incl = warp_incl_scan(cnt, lane);
     const int base = incl - cnt;
     const bool fits = cnt > 0 && incl <= kWqItems;
     if (cnt > 0 && !fits) serial = true;
     const unsigned fitLanes = __ballot_sync(full, fits);
     if (fitLanes) {
-        const int totalFit = __shfl_sync(full, incl, 31 - __clz(fitLanes));  // the fitting lanes' pairs are a prefix of the queue
+        const int totalFit = __shfl_sync(full, incl, 31 - __clz(fitLanes));
         if (fits) {
             int i = base;
             for (uint32_t m = mask; m; m &= m - 1) wq[i++] = (uint32_t)(cands.node[__ffs(m) - 1] & 0xffffff) | ((uint32_t)lane << 24);
@@ -319,8 +391,10 @@ __global__ void __maxnreg__(168) k_roles(const __grid_constant__ RolesArgs g) {
             if (valid) tick_p1_ball(s, x, g.cfg, g.ms, k, thr, scratch);
         } else {
             CollideCtx cx; ContactSink cw;
+            if (valid) tick_p1_car_pose(s, x, g.cfg, g.ms, k, role - 1, w);
+            cands_pass_warp(w, role - 1, valid, k, g.ms, mine, wq, g.stride);  // whole warp
             if (valid) tick_p1_car_begin(s, x, g.cfg, g.ms, k, thr, role - 1, w, scratch, first, cx, cw);
-            box_meshes_warp(cx, cw, g.ms, w.cands, role - 1, thr.car, valid, k, mine, wq, g.stride);  // whole warp
+            box_meshes_warp(cx, cw, g.ms, w, role - 1, thr.car, valid, k, mine, wq, g.stride);  // whole warp
             if (valid) tick_p1_car_end(cx, cw, x, thr, role - 1);
         }
         PT_WORK(2);
@@ -345,6 +419,20 @@ __global__ void __maxnreg__(168) k_roles(const __grid_constant__ RolesArgs g) {
                 doneFlag = compute_done(s, g.cfg);
                 compute_rewards(s, g.cfg, g.reward + (size_t)a * P);
                 g.done[a] = doneFlag ? 1 : 0;
+                if (g.metrics) {  // GameInst::Step (GameInst.cpp:13-31)
+                    float totalRew = 0;
+                    for (int p = 0; p < P; p++) totalRew += g.reward[(size_t)a * P + p];
+                    float* m = g.metrics + a;
+                    uint32_t* mu = reinterpret_cast<uint32_t*>(m);
+                    if (!isnan(totalRew)) { m[0] += totalRew; mu[(size_t)1 * A] += (uint32_t)P; }
+                    float cur = m[(size_t)4 * A] + totalRew / P;
+                    if (doneFlag) {
+                        if (!isnan(cur)) { m[(size_t)2 * A] += cur; mu[(size_t)3 * A] += 1u; }
+                        cur = 0;
+                    }
+                    m[(size_t)4 * A] = cur;
+                    mu[(size_t)5 * A] += 1u;
+                }
             }
         }
         PT_WORK(5);
@@ -443,7 +531,7 @@ int rlg_engine_destroy(rlg_engine* e) {
         cudaFree(e->prof); cudaFree(e->prof2);
     }
 #endif
-    cudaFree(e->scratch);
+    cudaFree(e->scratch); cudaFree(e->metrics);
     cudaFree(e->state); cudaFree(e->tables); cudaFree(e->obs); cudaFree(e->reward); cudaFree(e->done); cudaFree(e->actions);
     for (void* p : e->meshMem) cudaFree(p);
     cudaFreeHost(e->hActions); cudaFreeHost(e->hObs); cudaFreeHost(e->hReward); cudaFreeHost(e->hDone);
@@ -524,6 +612,8 @@ int rlg_engine_create(const rlg_engine_cfg* cfg, rlg_engine** out) {
     if (const char* cv = getenv("RLG_SMEM_CARVEOUT")) CKD(cudaFuncSetAttribute(k_roles, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
     CKD(cudaMalloc(&e->state, (size_t)e->nwords * A * 4));
     CKD(cudaMalloc(&e->scratch, (size_t)A * e->scratchSlots * sizeof(Contact)));
+    CKD(cudaMalloc(&e->metrics, (size_t)kMetricWords * A * 4));
+    CKD(cudaMemsetAsync(e->metrics, 0, (size_t)kMetricWords * A * 4, e->stream));
     CKD(cudaMalloc(&e->tables, sizeof(Tables)));
     CKD(cudaMalloc(&e->obs, (size_t)A * P * e->cfg.obsSize * 4));
     CKD(cudaMalloc(&e->reward, (size_t)A * P * 4));
@@ -703,6 +793,7 @@ static int do_step(rlg_engine* e, const int32_t* action_idx, cudaStream_t s, int
     RolesArgs g = roles_args(e);
     g.mode = 1; g.actions = action_idx; g.obs = obs ? obs : e->obs; g.reward = reward ? reward : e->reward; g.done = done ? done : e->done;
     g.autoReset = autoReset;
+    g.metrics = autoReset ? e->metrics : nullptr;  // GameInst::Step is the auto-resetting step
     k_roles<<<grid_for(e->cfg.numArenas, e->arenasPerBlock), 32 * e->groupsPerBlock * (1 + e->cfg.numCars), e->rolesSmem, s>>>(g);
     e->launches++;
     CK(cudaGetLastError());
@@ -720,6 +811,36 @@ int rlg_engine_step_to(rlg_engine* e, const int32_t* action_idx, float* obs_out,
     if (!e->meshesLoaded) return fail(RLG_ERR_STATE, "rlg_engine_load_meshes must be called first (RocketSim::Init)");
     CK(cudaSetDevice(e->device));
     return do_step(e, action_idx, pick(e, stream), 1, obs_out, reward_out, done_out);
+}
+int rlg_engine_metrics(rlg_engine* e, rlg_metrics_host* out) {
+    if (!e || !out) return fail(RLG_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(e->device));
+    const size_t A = (size_t)e->cfg.numArenas;
+    std::vector<uint32_t> h((size_t)kMetricWords * A);
+    CK(cudaMemcpyAsync(h.data(), e->metrics, h.size() * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    auto f = [&](int w, size_t a) { float v; memcpy(&v, &h[(size_t)w * A + a], 4); return v; };
+    // ThreadAgentManager::GetMetrics: AvgTracker += AvgTracker over the games, float totals (AvgTracker.h:34-44)
+    float stepTotal = 0, epTotal = 0;
+    uint64_t stepCount = 0, epCount = 0, steps = 0;
+    for (size_t a = 0; a < A; a++) {
+        float st = f(0, a), et = f(2, a);
+        if (!std::isnan(st)) { stepTotal += st; stepCount += h[1 * A + a]; }
+        if (!std::isnan(et)) { epTotal += et; epCount += h[3 * A + a]; }
+        steps += h[5 * A + a];
+    }
+    out->step_reward_total = stepTotal; out->episode_reward_total = epTotal;
+    out->step_reward_count = stepCount; out->episode_count = epCount; out->total_steps = steps;
+    out->avg_step_reward = stepCount ? stepTotal / stepCount : NAN;
+    out->avg_episode_reward = epCount ? epTotal / epCount : NAN;
+    return RLG_OK;
+}
+int rlg_engine_reset_metrics(rlg_engine* e) {
+    if (!e) return fail(RLG_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(e->device));
+    // GameInst::ResetMetrics clears the two trackers; curEpRew and totalSteps keep running (GameInst.h)
+    CK(cudaMemsetAsync(e->metrics, 0, (size_t)4 * e->cfg.numArenas * 4, e->stream));
+    return RLG_OK;
 }
 int rlg_engine_device(const rlg_engine* e) { return e ? e->device : -1; }
 int rlg_engine_arena_id_base(const rlg_engine* e) { return e ? e->cfgIn.arena_id_base : 0; }

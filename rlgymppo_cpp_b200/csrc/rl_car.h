@@ -19,6 +19,11 @@ struct CarW {
     M3 invInertiaWorld;
     WheelW w[4];
     MeshCands cands;  // this tick's mesh triangles near the car (wheel rays + hitbox), see rl_mesh.h
+    RayHit meshHit[4];  // the four wheel rays against the mesh candidates (wheel_mesh_rays), the start of wheel_ray
+    // hitbox narrowphase pre-filter from the same pass: candidates whose leaf box overlaps the hitbox AABB, and the first
+    // candidate of every mesh (haveMask = 0: not computed, the narrowphase takes its serial path)
+    uint32_t candMask, candGroupStart;
+    int32_t haveMask;
 };
 
 // ---- per-arena exchange between the roles of a tick (ball role + one role per car) --------------------------------
@@ -145,10 +150,43 @@ RL_HD inline DynView dyn_view(const TickX& x, int body, const CarConsts& k) {
 }
 
 // btCollisionWorld::rayTest through btRSBroadphase::rayTest for one wheel ray
-RL_HD inline RayHit wheel_ray(const TickX& x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, const MeshCands& cands, int self, V3 from, V3 to) {
-    RayHit hit; hit.frac = 1.0f; hit.body = -2; hit.normal = V3(0, 0, 1);
-    if (cands.n >= 0) ray_candidates(from, to, ms, cands, hit);
-    else ray_meshes(from, to, ms, hit);
+// the wheel rays of a car (btVehicleRL.cpp:118-216 rayCast): wheel i from its hard point down the suspension
+RL_HDI void wheel_ray_segments(const CarS& c, const CarConsts& k, V3* from, V3* to) {
+    V3 wheelDir = c.rot * V3(0, 0, -1);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float rayLen = k.wheelRest[i] + k.suspTravel + k.wheelRadius[i] - C::SUSPENSION_SUBTRACTION;
+        from[i] = c.pos + c.rot * k.wheelConn[i];
+        to[i] = from[i] + wheelDir * rayLen;
+    }
+}
+RL_HDI void wheel_mesh_rays_init(CarW& w) {
+    for (int i = 0; i < 4; i++) { w.meshHit[i].frac = 1.0f; w.meshHit[i].body = -2; w.meshHit[i].normal = V3(0, 0, 1); }
+    w.candMask = 0; w.candGroupStart = 0; w.haveMask = 0;
+}
+// Serial form of the candidate pass: the mesh part of the four wheel rays (triangle-major over the candidate list, or the
+// direct BVH walks when the list overflowed).  The role kernel does the same per (car, candidate) pair across the warp
+// (engine.cu cands_pass_warp).
+RL_HD inline void wheel_mesh_rays(const CarS& c, const CarConsts& k, const MeshSet& ms, CarW& w) {
+    wheel_mesh_rays_init(w);
+    if (c.isDemoed) return;  // Car::_PreTickUpdate returns before the vehicle update
+    V3 from[4], to[4];
+    wheel_ray_segments(c, k, from, to);
+    if (w.cands.n >= 0) {
+        for (int j = 0; j < w.cands.n; j++) {
+            const BvhNode& nd = ms.nodes[w.cands.node[j] & 0xffffff];
+            const Tri& t = ms.tris[nd.tri];
+            TriRays r;
+            ray_tri4(from, to, t.v0, t.v1, t.v2, r);
+            ray_tri4_apply(r.d, r.nn, r.neg, w.meshHit);
+        }
+    } else {
+        for (int i = 0; i < 4; i++) ray_meshes(from[i], to[i], ms, w.meshHit[i]);
+    }
+}
+
+RL_HD inline RayHit wheel_ray(const TickX& x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, const RayHit& meshHit, int self, V3 from, V3 to) {
+    RayHit hit = meshHit;  // static meshes first (wheel_mesh_rays), then planes, ball, other cars
     for (int p = 0; p < 4; p++) ray_plane(from, to, world_plane(p), hit);
     ray_sphere(from, to, x.h->ballPos, C::BALL_RADIUS * UU2BT, 0, hit);
     for (int c = 0; c < cfg.numCars; c++) {
@@ -183,7 +221,7 @@ RL_HD inline void vehicle_first(CarS& c, const TickX& x, const SimCfg& cfg, cons
         V3 target = source + wheelDir * rayLen;
         wh.contactPoint = target;
         wh.ground = -2; wh.inContact = 0; wh.inContactWorld = 0;
-        RayHit hit = wheel_ray(x, cfg, ms, k, w.cands, ci, source, target);
+        RayHit hit = wheel_ray(x, cfg, ms, k, w.meshHit[i], ci, source, target);
         if (hit.body != -2) {
             wh.contactPoint = source + (target - source) * hit.frac;
             wh.contactNormal = hit.normal;
@@ -634,7 +672,8 @@ RL_HD inline void car_respawn(CarS& c, int team, uint32_t rnd);
 // ---- Car::_PreTickUpdate (Car.cpp:58-131) -----------------------------------------------------
 // respawnRnd: a random word for Car::Respawn's spawn-slot pick; derived by the caller from the arena RNG state, the
 // tick and the car index WITHOUT advancing the arena RNG (the roles of a tick run concurrently)
-RL_HD inline void car_pre_tick(CarS& c, const TickX& x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, int ci, CarW& w, uint32_t respawnRnd) {
+// part A: up to the pose being final for this tick and the mesh candidates collected
+RL_HD inline void car_pre_tick_a(CarS& c, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, int ci, CarW& w, uint32_t respawnRnd) {
     w.force = V3(); w.torque = V3(); w.velCache = V3();
     c.controls.throttle = clampf(c.controls.throttle, -1.f, 1.f);
     c.controls.steer = clampf(c.controls.steer, -1.f, 1.f);
@@ -662,6 +701,9 @@ RL_HD inline void car_pre_tick(CarS& c, const TickX& x, const SimCfg& cfg, const
         collect_candidates(ms, mn - pad, mx + pad, w.cands);
     }
     RL_PT(0);
+}
+// part B: the vehicle update and the control -> force model (needs w.meshHit: wheel_mesh_rays / cands_pass_warp)
+RL_HD inline void car_pre_tick_b(CarS& c, const TickX& x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, int ci, CarW& w) {
     if (c.isDemoed) return;
 
     vehicle_first(c, x, cfg, ms, k, ci, w);
@@ -683,6 +725,11 @@ RL_HD inline void car_pre_tick(CarS& c, const TickX& x, const SimCfg& cfg, const
     vehicle_second(c, w, k);
     update_boost(c, w);
     RL_PT(3);
+}
+RL_HD inline void car_pre_tick(CarS& c, const TickX& x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, int ci, CarW& w, uint32_t respawnRnd) {
+    car_pre_tick_a(c, cfg, ms, k, ci, w, respawnRnd);
+    wheel_mesh_rays(c, k, ms, w);
+    car_pre_tick_b(c, x, cfg, ms, k, ci, w);
 }
 
 RL_HD inline void car_respawn(CarS& c, int team, uint32_t rnd) {

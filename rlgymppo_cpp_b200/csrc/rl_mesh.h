@@ -224,12 +224,47 @@ RL_HD inline void collect_candidates(const MeshSet& ms, V3 mn, V3 mx, MeshCands&
         }
     }
 }
-RL_HD inline void ray_candidates(V3 from, V3 to, const MeshSet& ms, const MeshCands& cands, RayHit& hit) {
-    for (int j = 0; j < cands.n; j++) {
-        const BvhNode& nd = ms.nodes[cands.node[j] & 0xffffff];
-        const Tri& t = ms.tris[nd.tri];
-        ray_triangle(from, to, t.v0, t.v1, t.v2, hit);
+// One triangle against the four wheel rays of a car, independent of any earlier hit: d[i] = hit fraction along ray i
+// (2 = no hit), nn = unit triangle normal, bit i of neg = ray i starts behind the triangle (hit normal = -nn).  The same
+// arithmetic as ray_triangle; the caller applies ray_triangle's `distance < hit.frac` gate in candidate order
+// (ray_tri4_apply), so scanning the candidates triangle-major gives the same hits as four ray-major scans.
+struct TriRays { float d[4]; V3 nn; uint32_t neg; };
+RL_HDI void ray_tri4(const V3* from, const V3* to, V3 vert0, V3 vert1, V3 vert2, TriRays& out) {
+    V3 v10 = vert1 - vert0, v20 = vert2 - vert0;
+    V3 n = cross(v10, v20);
+    float dist = dot(vert0, n);
+    float edge_tol = len2(n) * -0.0001f;
+    out.neg = 0; out.nn = V3();
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        out.d[i] = 2.f;
+        float dist_a = dot(n, from[i]) - dist;
+        float dist_b = dot(n, to[i]) - dist;
+        if (dist_a * dist_b >= 0.f) continue;
+        float proj_length = dist_a - dist_b;
+        float distance = dist_a / proj_length;
+        V3 point = from[i] + (to[i] - from[i]) * distance;  // setInterpolate3
+        V3 v0p = vert0 - point, v1p = vert1 - point;
+        if (dot(cross(v0p, v1p), n) >= edge_tol) {
+            V3 v2p = vert2 - point;
+            if (dot(cross(v1p, v2p), n) >= edge_tol && dot(cross(v2p, v0p), n) >= edge_tol) {
+                out.d[i] = distance;
+                if (dist_a <= 0.f) out.neg |= 1u << i;
+                any = true;
+            }
+        }
     }
+    if (any) out.nn = normalized(n);
+}
+RL_HDI void ray_tri4_apply(const float* d, V3 nn, uint32_t neg, RayHit* hit) {
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        if (d[i] < hit[i].frac) {
+            hit[i].frac = d[i];
+            hit[i].normal = ((neg >> i) & 1u) ? -nn : nn;
+            hit[i].body = -1;
+        }
 }
 
 // ray vs sphere (what the sub-simplex convex cast of a point against btSphereShape converges to)

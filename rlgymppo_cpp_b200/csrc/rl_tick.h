@@ -136,11 +136,11 @@ RL_HDI void tick_s0_ball(const ArenaS& a, TickX x) {
     x.h->ballActive = !(len2(a.ball.vel) == 0.f && len2(a.ball.angvel) == 0.f);
 }
 
-// tick_p1_car = begin (pre-tick, car-ball) + hitbox-mesh narrowphase + end (hitbox-plane, counts).  The role kernel
-// replaces the middle part by the warp-cooperative box_meshes_warp (engine.cu): same triangles, same order, same
-// arithmetic per triangle (box_mesh_item), so the contacts are identical.
-RL_HD inline void tick_p1_car_begin(ArenaS& a, TickX x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, const Thresholds& thr, int c, CarW& w,
-                                    Contact* scratch, int firstTickOfStep, CollideCtx& cx, ContactSink& cw) {
+// tick_p1_car = pose (respawn, mesh candidates) + mesh part of the wheel rays + begin (vehicle update, control model,
+// car-ball) + hitbox-mesh narrowphase + end (hitbox-plane, counts).  The role kernel replaces the two mesh parts by
+// warp-cooperative passes (engine.cu cands_pass_warp / box_meshes_warp): same triangles, same order, same arithmetic
+// per triangle (ray_tri4, box_mesh_item), so hits and contacts are identical.
+RL_HD inline void tick_p1_car_pose(ArenaS& a, TickX x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, int c, CarW& w) {
     CarS& car = a.cars[c];
     CarX& o = x.car[c];
     // activation state / contact response are decided at the top of Car::_PreTickUpdate, before a possible respawn,
@@ -148,7 +148,14 @@ RL_HD inline void tick_p1_car_begin(ArenaS& a, TickX x, const SimCfg& cfg, const
     o.noResponse = car.isDemoed;
     o.ballVelCache = V3(); o.velCache = V3();
     RL_PT(-1);
-    car_pre_tick(car, x, cfg, ms, k, c, w, respawn_rnd(a, c));
+    car_pre_tick_a(car, cfg, ms, k, c, w, respawn_rnd(a, c));
+}
+// between the two: w.meshHit (+ the hitbox pre-filter) from wheel_mesh_rays or the role kernel's cooperative pass
+RL_HD inline void tick_p1_car_begin(ArenaS& a, TickX x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, const Thresholds& thr, int c, CarW& w,
+                                    Contact* scratch, int firstTickOfStep, CollideCtx& cx, ContactSink& cw) {
+    CarS& car = a.cars[c];
+    CarX& o = x.car[c];
+    car_pre_tick_b(car, x, cfg, ms, k, c, w);
     if (!o.noResponse) w.force += V3(0.f * UU2BT, 0.f * UU2BT, C::GRAVITY_Z * UU2BT) * C::CAR_MASS;  // applyGravity on active bodies
     o.force = w.force; o.torque = w.torque;
     V3 center = car.pos + car.rot * k.hitboxOffset;
@@ -179,6 +186,8 @@ RL_HD inline void tick_p1_car_end(CollideCtx& cx, ContactSink& cw, TickX x, cons
 RL_HD inline void tick_p1_car(ArenaS& a, TickX x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, const Thresholds& thr, int c, CarW& w,
                               Contact* scratch, int firstTickOfStep) {
     CollideCtx cx; ContactSink cw;
+    tick_p1_car_pose(a, x, cfg, ms, k, c, w);
+    wheel_mesh_rays(a.cars[c], k, ms, w);
     tick_p1_car_begin(a, x, cfg, ms, k, thr, c, w, scratch, firstTickOfStep, cx, cw);
     if (w.cands.n >= 0) box_meshes_candidates(cx, cw, ms, w.cands, c, thr.car);
     else box_meshes(cx, cw, ms, c, thr.car);

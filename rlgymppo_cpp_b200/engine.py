@@ -25,6 +25,7 @@ EXPORTS = [
     "rlg_engine_outputs", "rlg_engine_obs_size", "rlg_engine_num_players", "rlg_engine_num_arenas",
     "rlg_engine_state_bytes_per_arena", "rlg_engine_player_order", "rlg_engine_set_player_order", "rlg_action_table",
     "rlg_engine_step_host", "rlg_engine_host_buffers", "rlg_engine_step_pinned", "rlg_engine_read_outputs", "rlg_engine_launch_count", "rlg_engine_stream", "rlg_engine_sync",
+    "rlg_engine_metrics", "rlg_engine_reset_metrics",
     # collector / plumbing (bound in rlgymppo_cpp_b200.collector)
     "rlg_engine_step_to", "rlg_engine_device", "rlg_engine_arena_id_base", "rlg_engine_copy_to_host", "rlg_engine_copy_to_device",
     "rlg_collector_create", "rlg_collector_destroy", "rlg_collector_set_layer", "rlg_collector_infer", "rlg_collector_collect",
@@ -210,6 +211,15 @@ class Engine:
         o, r, d = C.c_void_p(), C.c_void_p(), C.c_void_p()
         _check(self.L.rlg_engine_outputs(self.h, C.byref(o), C.byref(r), C.byref(d)))
         return o.value, r.value, d.value
+
+    def metrics(self) -> dict:
+        """ThreadAgentManager::GetMetrics' reward entries ("Average Step Reward", "Average Episode Reward") + raw totals."""
+        m = abi.MetricsHost()
+        _check(self.L.rlg_engine_metrics(self.h, C.byref(m)))
+        return {k: getattr(m, k) for k, _ in abi.MetricsHost._fields_}
+
+    def reset_metrics(self):
+        _check(self.L.rlg_engine_reset_metrics(self.h))
 
     def sync(self):
         _check(self.L.rlg_engine_sync(self.h))

@@ -164,6 +164,61 @@ def test_step_host_matches_device_path(torch_cuda):
         assert np.array_equal(o1, o3) and np.array_equal(r1, r3) and np.array_equal(d1, d3)
 
 
+def test_reward_metrics_follow_gameinst(torch_cuda):
+    """rlg_engine_metrics == GameInst::Step's AvgTracker arithmetic (GameInst.cpp:13-31) replayed on the host in float32
+    from the rewards/dones the steps returned, summed over the games like ThreadAgentManager::GetMetrics (:82-92)."""
+    cfg = abi.default_cfg(num_arenas=96, team_size=2)
+    cfg.no_touch_max_steps = 6  # episodes end often
+    e = engine.Engine(cfg)
+    e.reset()
+    m0 = e.metrics()
+    assert np.isnan(m0["avg_step_reward"]) and np.isnan(m0["avg_episode_reward"]) and m0["total_steps"] == 0
+    A, P = e.A, e.P
+    f32 = np.float32
+    step_tot = np.zeros(A, f32); ep_tot = np.zeros(A, f32); cur = np.zeros(A, f32)
+    step_cnt = np.zeros(A, np.uint64); ep_cnt = np.zeros(A, np.uint64)
+    rng = np.random.default_rng(5)
+
+    def replay(rew, done):
+        for a in range(A):
+            tot = f32(0)
+            for p in range(P):
+                tot = f32(tot + rew[a * P + p])
+            step_tot[a] = f32(step_tot[a] + tot); step_cnt[a] += P
+            cur[a] = f32(cur[a] + f32(tot / f32(P)))
+            if done[a]:
+                ep_tot[a] = f32(ep_tot[a] + cur[a]); ep_cnt[a] += 1
+                cur[a] = 0
+
+    def expect():
+        st = f32(0); et = f32(0)
+        for a in range(A):
+            st = f32(st + step_tot[a]); et = f32(et + ep_tot[a])
+        return st, et
+
+    for s in range(20):
+        _, rew, done = e.step_host(rng.integers(0, 90, size=A * P).astype(np.int32), want_obs=False)
+        replay(rew, done)
+    m = e.metrics()
+    st, et = expect()
+    assert m["total_steps"] == 20 * A and m["step_reward_count"] == int(step_cnt.sum()) and m["episode_count"] == int(ep_cnt.sum())
+    assert m["episode_count"] > 0
+    assert f32(m["step_reward_total"]).view(np.uint32) == st.view(np.uint32)
+    assert f32(m["episode_reward_total"]).view(np.uint32) == et.view(np.uint32)
+    assert f32(m["avg_step_reward"]).view(np.uint32) == f32(st / f32(step_cnt.sum())).view(np.uint32)
+    # ResetMetrics clears the trackers, not the running episode sums
+    e.reset_metrics()
+    step_tot[:] = 0; ep_tot[:] = 0; step_cnt[:] = 0; ep_cnt[:] = 0
+    for s in range(8):
+        _, rew, done = e.step_host(rng.integers(0, 90, size=A * P).astype(np.int32), want_obs=False)
+        replay(rew, done)
+    m = e.metrics()
+    st, et = expect()
+    assert m["total_steps"] == 28 * A
+    assert f32(m["step_reward_total"]).view(np.uint32) == st.view(np.uint32)
+    assert f32(m["episode_reward_total"]).view(np.uint32) == et.view(np.uint32)
+
+
 def test_against_compiled_reference_if_present(torch_cuda):
     """Live comparison with oracle/_ref (travels to the GPU box as a prebuilt .so): fresh random states every run."""
     from oracle import refsim
