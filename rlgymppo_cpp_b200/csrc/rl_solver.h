@@ -189,9 +189,9 @@ RL_HD inline void integrate_transform(V3& pos, M3& rot, V3 linvel, V3 angvel, fl
 // solveGroup over all manifolds gives; this is what lets every role of a tick solve its own island concurrently
 // (rl_tick.h).  The split-impulse early exit on a zero residual is per island for the same reason: an island whose
 // rows all returned a zero delta is at a fixed point of the sweep.
-RL_HD RL_NOINLINE inline void solve_island(SolverBody* sb, int numBodies, int base, const Contact* contacts, int numContacts) {
-    Row rows[kMaxRows];
-    Row fric[kMaxRows];
+// rows of one island in the reference's order: a contact row + its friction row per contact, then the averaged special rows
+RL_HD RL_NOINLINE inline void island_setup(const SolverBody* sb, int numBodies, int base, const Contact* contacts, int numContacts, Row* rows, Row* fric,
+                                          int& nRowsOut, int& nFricOut) {
     int nRows = 0, nFric = 0;
     // special-contact accumulators per body (btCollisionObject::m_specialResolveInfo)
     int spN[1 + kMaxCars]; float spFriction[1 + kMaxCars], spRestitution[1 + kMaxCars], spDist[1 + kMaxCars]; V3 spNormal[1 + kMaxCars];
@@ -250,6 +250,26 @@ RL_HD RL_NOINLINE inline void solve_island(SolverBody* sb, int numBodies, int ba
         setup_friction_row(fric[nFric], sb, bi, -1, dir, rel1, V3(), spFriction[bi], idx);
         nFric++;
     }
+    nRowsOut = nRows; nFricOut = nFric;
+}
+
+// writeBackBodies (+ the split-impulse transform correction)
+RL_HD RL_NOINLINE inline void island_finish(SolverBody* sb, int numBodies) {
+    for (int i = 0; i < numBodies; i++) {
+        if (!sb[i].active) continue;
+        sb[i].linVel += sb[i].dLin;
+        sb[i].angVel += sb[i].dAng;
+        if (!is_zero(sb[i].push) || !is_zero(sb[i].turn)) integrate_transform(sb[i].pos, sb[i].rot, sb[i].push, sb[i].turn * 0.1f, kTickTime);
+        sb[i].linVel = sb[i].linVel + sb[i].extForceImp;
+        sb[i].angVel = sb[i].angVel + sb[i].extTorqueImp;
+    }
+}
+
+RL_HD RL_NOINLINE inline void solve_island(SolverBody* sb, int numBodies, int base, const Contact* contacts, int numContacts) {
+    Row rows[kMaxRows];
+    Row fric[kMaxRows];
+    int nRows, nFric;
+    island_setup(sb, numBodies, base, contacts, numContacts, rows, fric, nRows, nFric);
 
     const int numIterations = 10;
     // split impulse (position) iterations — includes the special rows
@@ -275,15 +295,70 @@ RL_HD RL_NOINLINE inline void solve_island(SolverBody* sb, int numBodies, int ba
             }
         }
     }
-    // writeBackBodies
-    for (int i = 0; i < numBodies; i++) {
-        if (!sb[i].active) continue;
-        sb[i].linVel += sb[i].dLin;
-        sb[i].angVel += sb[i].dAng;
-        if (!is_zero(sb[i].push) || !is_zero(sb[i].turn)) integrate_transform(sb[i].pos, sb[i].rot, sb[i].push, sb[i].turn * 0.1f, kTickTime);
-        sb[i].linVel = sb[i].linVel + sb[i].extForceImp;
-        sb[i].angVel = sb[i].angVel + sb[i].extTorqueImp;
+    island_finish(sb, numBodies);
+}
+
+// The common island: ONE dynamic body against the static world (the ball on the floor / a wall, a car's hitbox on the
+// ground) — every contact has a == body, b == -1.  Same rows and the same sweep as solve_island, but the body's
+// velocity / push deltas live in registers for the 10 + 10 iterations instead of round-tripping through the
+// SolverBody array between rows (the B side of every row is the fixed body: its terms are exact zeros).
+RL_HD RL_NOINLINE inline void solve_island_one(SolverBody& b, int body, const Contact* contacts, int numContacts) {
+    Row rows[kMaxRows];
+    Row fric[kMaxRows];
+    int nRows, nFric;
+    island_setup(&b, 1, body, contacts, numContacts, rows, fric, nRows, nFric);
+    if (b.active) {
+        const float invMass = b.invMass;
+        V3 dLin = b.dLin, dAng = b.dAng, push = b.push, turn = b.turn;
+        const int numIterations = 10;
+        for (int it = 0; it < numIterations; it++) {
+            float residual = 0.f;
+            for (int j = 0; j < nRows; j++) {
+                Row& c = rows[j];
+                float deltaImpulse = 0.f;
+                if (c.rhsPen != 0.f) {  // resolve_split
+                    deltaImpulse = c.rhsPen - c.appliedPush * 0.f;
+                    float dv1 = dot(c.n1, push) + dot(c.rxn1, turn);
+                    deltaImpulse -= dv1 * c.jacDiagInv;
+                    float sum = c.appliedPush + deltaImpulse;
+                    if (sum < c.lower) { deltaImpulse = c.lower - c.appliedPush; c.appliedPush = c.lower; }
+                    else c.appliedPush = sum;
+                    push += (c.n1 * invMass) * deltaImpulse;
+                    turn += c.angA * deltaImpulse;
+                }
+                float d = deltaImpulse * (1.f / c.jacDiagInv);
+                residual = fmaxf_(residual, d * d);
+            }
+            if (residual <= 0.f || it >= numIterations - 1) break;
+        }
+        auto resolve = [&](Row& c, bool lowerOnly) {  // resolve_row
+            float deltaImpulse = c.rhs - c.applied * 0.f;
+            float dv1 = dot(c.n1, dLin) + dot(c.rxn1, dAng);
+            deltaImpulse -= dv1 * c.jacDiagInv;
+            float sum = c.applied + deltaImpulse;
+            if (sum < c.lower) { deltaImpulse = c.lower - c.applied; c.applied = c.lower; }
+            else if (!lowerOnly && sum > c.upper) { deltaImpulse = c.upper - c.applied; c.applied = c.upper; }
+            else c.applied = sum;
+            dLin += (c.n1 * invMass) * deltaImpulse;
+            dAng += c.angA * deltaImpulse;
+        };
+        for (int it = 0; it < numIterations; it++) {
+            for (int j = 0; j < nRows; j++) {
+                if (rows[j].special) continue;
+                resolve(rows[j], true);
+            }
+            for (int j = 0; j < nFric; j++) {
+                float total = rows[fric[j].frictionIndex].applied;
+                if (total > 0.f) {
+                    fric[j].lower = -(fric[j].friction * total);
+                    fric[j].upper = fric[j].friction * total;
+                    resolve(fric[j], false);
+                }
+            }
+        }
+        b.dLin = dLin; b.dAng = dAng; b.push = push; b.turn = turn;
     }
+    island_finish(&b, 1);
 }
 
 }  // namespace rl

@@ -262,7 +262,7 @@ RL_HD inline bool tick_p2_car_self(ArenaS& a, TickX x, const SimCfg& cfg, const 
     }
     SolverBody b;
     solver_body_from_car(b, car, o, k);
-    solve_island(&b, 1, 1 + c, seg_car(scratch, c) + 1, o.nCarWorld);
+    solve_island_one(b, 1 + c, seg_car(scratch, c) + 1, o.nCarWorld);
     car.vel = b.linVel; car.angvel = b.angVel; car.pos = b.pos; car.rot = b.rot;
     RL_PT(13);
     return true;
@@ -338,7 +338,7 @@ RL_HD inline void tick_p2_solve(ArenaS& a, TickX x, const SimCfg& cfg, const Car
         // the ball is an island of its own: ball-world contacts only, straight from its segment
         if (sb[0].active) {
             if (x.h->nBall > 0) {
-                solve_island(sb, 1, 0, seg_ball(scratch), x.h->nBall);
+                solve_island_one(sb[0], 0, seg_ball(scratch), x.h->nBall);
                 a.ball.vel = sb[0].linVel; a.ball.angvel = sb[0].angVel;
                 a.ball.pos = sb[0].pos + a.ball.vel * dt;  // integrateTransformNoRot
             } else {
