@@ -51,6 +51,9 @@ struct rlg_engine {
     float* hReward = nullptr;
     uint8_t* hDone = nullptr;
     Contact* scratch = nullptr;  // per-arena contact segments (rl_collide.h ContactSink)
+    cudaStream_t copyStream = nullptr; cudaEvent_t evFirst = nullptr;  // host-buffer step: D2H of the results overlaps ticks 1..
+    int32_t* resetCount = nullptr; int32_t* hResetCount = nullptr; int32_t* hResetIds = nullptr; float* hResetObs = nullptr;
+    int32_t* dResetIds = nullptr; float* dResetObs = nullptr;  // device views of the two mapped host buffers
     float* metrics = nullptr;    // [kMetricWords][A]: stepTotal, stepCount (u32), epTotal, epCount (u32), curEpRew, totalSteps (u32)
     int xwords = 0, stride = 0, scratchSlots = 0;
     int arenasPerBlock = 32, groupsPerBlock = 1;
@@ -149,6 +152,12 @@ struct RolesArgs {
     CarConsts k;    // car preset constants and contact thresholds: read from the kernel-parameter constant bank
     Thresholds thr; // instead of a per-thread local-memory copy (the wheel arrays are indexed dynamically)
     const rlg_controls* controls; int nticks;
+    // mode 1 may run a sub-range [tickBegin, tickEnd) of the step's ticks: the host-buffer step launches tick 0 (+ the gym
+    // layer) and the rest separately so the obs / reward / done copy to the host overlaps the remaining ticks
+    int tickBegin, tickEnd;
+    // auto-reset bookkeeping of that split step: arenas re-set at the end of the step (their obs row changes after the
+    // first launch's copy) are listed here — count in device memory, ids / obs rows in mapped page-locked host memory
+    int32_t* resetCount; int32_t* resetIds; float* resetObs;
     const int32_t* actions; float* obs; float* reward; uint8_t* done; int autoReset;
     float* metrics;  // GameInst reward metrics, word-transposed [kMetricWords][A] (nullptr: not tracked)
 };
@@ -372,7 +381,7 @@ __global__ void __maxnreg__(168) k_roles(const __grid_constant__ RolesArgs g) {
     if (valid) {
         if (g.mode == 0) {
             if (role > 0 && g.controls) s.cars[role - 1].controls = controls_from(g.controls[(size_t)a * P + (role - 1)]);
-        } else if (role == 0) {
+        } else if (role == 0 && g.tickBegin == 0) {
             int32_t act[kMaxCars];
             for (int p = 0; p < P; p++) {
                 int v = g.actions[(size_t)a * P + p];
@@ -381,12 +390,12 @@ __global__ void __maxnreg__(168) k_roles(const __grid_constant__ RolesArgs g) {
             parse_actions(s, g.cfg, *g.tb, act);
         }
     }
-    const int nticks = g.mode == 0 ? g.nticks : g.cfg.tickSkip;
-    for (int t = 0; t < nticks; t++) {
+    const int tBegin = g.mode == 0 ? 0 : g.tickBegin, tEnd = g.mode == 0 ? g.nticks : g.tickEnd;
+    for (int t = tBegin; t < tEnd; t++) {
         const int first = (g.mode == 1 && t == 0) ? 1 : 0;
         if (valid) { if (role == 0) tick_s0_ball(s, x); else tick_s0_car(s, x, role - 1); }
         PT_WORK(1);
-        if (g.barMode == 2 && t > 0) SYNC_TICK(); else SYNC_GROUP();  // B1
+        if (g.barMode == 2 && t > tBegin) SYNC_TICK(); else SYNC_GROUP();  // B1
         if (role == 0) {
             if (valid) tick_p1_ball(s, x, g.cfg, g.ms, k, thr, scratch);
         } else {
@@ -437,9 +446,20 @@ __global__ void __maxnreg__(168) k_roles(const __grid_constant__ RolesArgs g) {
         }
         PT_WORK(5);
     }
-    if (valid && role == 0 && g.mode == 1 && doneFlag && g.autoReset) {  // GameInst::Step auto-reset (GameInst.cpp:20-24)
-        gym_reset(s, g.cfg);
-        build_obs(s, g.cfg, *g.tb, g.obs + (size_t)a * P * g.cfg.obsSize);
+    if (valid && role == 0 && g.mode == 1 && g.autoReset && tEnd == g.cfg.tickSkip) {  // GameInst::Step auto-reset (GameInst.cpp:20-24)
+        if (tBegin > 0) doneFlag = g.done[a] != 0;  // decided by the launch that ran tick 0
+        if (doneFlag) {
+            float* o = g.obs + (size_t)a * P * g.cfg.obsSize;
+            gym_reset(s, g.cfg);
+            build_obs(s, g.cfg, *g.tb, o);
+            if (g.resetCount) {
+                const int row = P * g.cfg.obsSize;
+                const int i = atomicAdd(g.resetCount, 1);
+                g.resetIds[i] = a;
+                float* dst = g.resetObs + (size_t)i * row;
+                for (int q = 0; q < row; q++) dst[q] = o[q];
+            }
+        }
     }
     PT_WORK(6);
     SYNC_GROUP();
@@ -535,6 +555,9 @@ int rlg_engine_destroy(rlg_engine* e) {
     cudaFree(e->state); cudaFree(e->tables); cudaFree(e->obs); cudaFree(e->reward); cudaFree(e->done); cudaFree(e->actions);
     for (void* p : e->meshMem) cudaFree(p);
     cudaFreeHost(e->hActions); cudaFreeHost(e->hObs); cudaFreeHost(e->hReward); cudaFreeHost(e->hDone);
+    cudaFreeHost(e->hResetCount); cudaFreeHost(e->hResetIds); cudaFreeHost(e->hResetObs); cudaFree(e->resetCount);
+    if (e->copyStream) cudaStreamDestroy(e->copyStream);
+    if (e->evFirst) cudaEventDestroy(e->evFirst);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return RLG_OK;
@@ -623,6 +646,14 @@ int rlg_engine_create(const rlg_engine_cfg* cfg, rlg_engine** out) {
     CKD(cudaMallocHost(&e->hObs, (size_t)A * P * e->cfg.obsSize * 4));
     CKD(cudaMallocHost(&e->hReward, (size_t)A * P * 4));
     CKD(cudaMallocHost(&e->hDone, (size_t)A));
+    CKD(cudaStreamCreateWithFlags(&e->copyStream, cudaStreamNonBlocking));
+    CKD(cudaEventCreateWithFlags(&e->evFirst, cudaEventDisableTiming));
+    CKD(cudaMalloc(&e->resetCount, 4));
+    CKD(cudaMallocHost(&e->hResetCount, 4));
+    CKD(cudaHostAlloc(&e->hResetIds, (size_t)A * 4, cudaHostAllocMapped));
+    CKD(cudaHostAlloc(&e->hResetObs, (size_t)A * P * e->cfg.obsSize * 4, cudaHostAllocMapped));
+    CKD(cudaHostGetDevicePointer((void**)&e->dResetIds, e->hResetIds, 0));
+    CKD(cudaHostGetDevicePointer((void**)&e->dResetObs, e->hResetObs, 0));
     Tables tb;
     try { host_build_tables(tb); } catch (std::exception& ex) { rlg_engine_destroy(e); return fail(RLG_ERR_INVALID, ex.what()); }
     CKD(cudaMemcpyAsync(e->tables, &tb, sizeof(tb), cudaMemcpyHostToDevice, e->stream));
@@ -789,8 +820,10 @@ int rlg_engine_tick(rlg_engine* e, const rlg_controls* controls, int nticks, voi
 }
 
 static int do_step(rlg_engine* e, const int32_t* action_idx, cudaStream_t s, int autoReset, float* obs = nullptr, float* reward = nullptr,
-                   uint8_t* done = nullptr) {
+                   uint8_t* done = nullptr, int tickBegin = 0, int tickEnd = -1, bool listResets = false) {
     RolesArgs g = roles_args(e);
+    g.tickBegin = tickBegin; g.tickEnd = tickEnd < 0 ? e->cfg.tickSkip : tickEnd;
+    if (listResets) { g.resetCount = e->resetCount; g.resetIds = e->dResetIds; g.resetObs = e->dResetObs; }
     g.mode = 1; g.actions = action_idx; g.obs = obs ? obs : e->obs; g.reward = reward ? reward : e->reward; g.done = done ? done : e->done;
     g.autoReset = autoReset;
     g.metrics = autoReset ? e->metrics : nullptr;  // GameInst::Step is the auto-resetting step
@@ -884,20 +917,53 @@ int rlg_engine_read_outputs(rlg_engine* e, float* obs_host, float* reward_host, 
     return RLG_OK;
 }
 
+// The host-buffer Gym::Step: H2D action indices -> tick 0 + gym layer -> [D2H obs / reward / done on a second stream]
+// overlapped with ticks 1.. + auto-reset -> the obs rows of re-set arenas (written by the kernel straight into mapped
+// page-locked memory) are patched into the host obs buffer.  Obs, rewards and done flags are final after the first tick
+// of a step (G/Gym.cpp:84-93) except for the arenas GameInst::Step re-sets (GameInst.cpp:20-24), so the 11.8 MB result
+// copy (cfg2) hides behind 7/8 of the physics instead of following it.
+static int step_pinned_impl(rlg_engine* e, int want_obs) {
+    const int A = e->cfg.numArenas, P = e->cfg.numCars;
+    const size_t row = (size_t)P * e->cfg.obsSize;
+    cudaStream_t s = e->stream, c = e->copyStream;
+    CK(cudaMemcpyAsync(e->actions, e->hActions, (size_t)A * P * 4, cudaMemcpyHostToDevice, s));
+    if (e->cfg.tickSkip < 2) {  // nothing to overlap with
+        int rc = do_step(e, e->actions, s, 1);
+        if (rc != RLG_OK) return rc;
+        if (want_obs) CK(cudaMemcpyAsync(e->hObs, e->obs, (size_t)A * row * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(e->hReward, e->reward, (size_t)A * P * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(e->hDone, e->done, (size_t)A, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        return RLG_OK;
+    }
+    CK(cudaMemsetAsync(e->resetCount, 0, 4, s));
+    int rc = do_step(e, e->actions, s, 1, nullptr, nullptr, nullptr, 0, 1);
+    if (rc != RLG_OK) return rc;
+    CK(cudaEventRecord(e->evFirst, s));
+    CK(cudaStreamWaitEvent(c, e->evFirst, 0));
+    if (want_obs) CK(cudaMemcpyAsync(e->hObs, e->obs, (size_t)A * row * 4, cudaMemcpyDeviceToHost, c));
+    CK(cudaMemcpyAsync(e->hReward, e->reward, (size_t)A * P * 4, cudaMemcpyDeviceToHost, c));
+    CK(cudaMemcpyAsync(e->hDone, e->done, (size_t)A, cudaMemcpyDeviceToHost, c));
+    rc = do_step(e, e->actions, s, 1, nullptr, nullptr, nullptr, 1, e->cfg.tickSkip, want_obs != 0);
+    if (rc != RLG_OK) return rc;
+    CK(cudaMemcpyAsync(e->hResetCount, e->resetCount, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(c));
+    CK(cudaStreamSynchronize(s));
+    if (want_obs) {
+        const int n = *e->hResetCount;
+        for (int i = 0; i < n; i++) memcpy(e->hObs + (size_t)e->hResetIds[i] * row, e->hResetObs + (size_t)i * row, row * 4);
+    }
+    return RLG_OK;
+}
+
 int rlg_engine_step_host(rlg_engine* e, const int32_t* action_idx_host, float* obs_host, float* reward_host, uint8_t* done_host) {
     if (!e || !action_idx_host) return fail(RLG_ERR_INVALID, "null argument");
     if (!e->meshesLoaded) return fail(RLG_ERR_STATE, "rlg_engine_load_meshes must be called first (RocketSim::Init)");
     CK(cudaSetDevice(e->device));
     const int A = e->cfg.numArenas, P = e->cfg.numCars;
-    cudaStream_t s = e->stream;
     memcpy(e->hActions, action_idx_host, (size_t)A * P * 4);
-    CK(cudaMemcpyAsync(e->actions, e->hActions, (size_t)A * P * 4, cudaMemcpyHostToDevice, s));
-    int rc = do_step(e, e->actions, s, 1);
+    int rc = step_pinned_impl(e, obs_host != nullptr);
     if (rc != RLG_OK) return rc;
-    if (obs_host) CK(cudaMemcpyAsync(e->hObs, e->obs, (size_t)A * P * e->cfg.obsSize * 4, cudaMemcpyDeviceToHost, s));
-    if (reward_host) CK(cudaMemcpyAsync(e->hReward, e->reward, (size_t)A * P * 4, cudaMemcpyDeviceToHost, s));
-    if (done_host) CK(cudaMemcpyAsync(e->hDone, e->done, (size_t)A, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
     if (obs_host) memcpy(obs_host, e->hObs, (size_t)A * P * e->cfg.obsSize * 4);
     if (reward_host) memcpy(reward_host, e->hReward, (size_t)A * P * 4);
     if (done_host) memcpy(done_host, e->hDone, (size_t)A);
@@ -917,16 +983,7 @@ int rlg_engine_step_pinned(rlg_engine* e, int want_obs) {
     if (!e) return fail(RLG_ERR_INVALID, "null engine");
     if (!e->meshesLoaded) return fail(RLG_ERR_STATE, "rlg_engine_load_meshes must be called first (RocketSim::Init)");
     CK(cudaSetDevice(e->device));
-    const int A = e->cfg.numArenas, P = e->cfg.numCars;
-    cudaStream_t s = e->stream;
-    CK(cudaMemcpyAsync(e->actions, e->hActions, (size_t)A * P * 4, cudaMemcpyHostToDevice, s));
-    int rc = do_step(e, e->actions, s, 1);
-    if (rc != RLG_OK) return rc;
-    if (want_obs) CK(cudaMemcpyAsync(e->hObs, e->obs, (size_t)A * P * e->cfg.obsSize * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(e->hReward, e->reward, (size_t)A * P * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(e->hDone, e->done, (size_t)A, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    return RLG_OK;
+    return step_pinned_impl(e, want_obs);
 }
 
 int rlg_engine_copy_to_host(rlg_engine* e, void* dst_host, const void* src_dev, size_t bytes) {
