@@ -40,7 +40,9 @@ constexpr int kNumWSlots = 3;
 constexpr int kSmemA = (kMaxWidth / kBlockK) * kABlockBytes;  // 128 KB
 constexpr int kSmemW = kNumWSlots * kWSlotBytes;            // 64 KB
 constexpr int kSmemBar = kSmemA + kSmemW;
-constexpr int kSmemTotal = kSmemBar + 128;
+constexpr int kSmemBias = kSmemBar + 128;                  // this layer's bias (kMaxWidth floats)
+constexpr int kSmemTotal = kSmemBias + kMaxWidth * 4;
+constexpr int kThreads = 256;                               // two warpgroups: both read the 128 TMEM lanes, each half of the columns
 constexpr int kMaxLayers = RLG_MAX_HIDDEN_LAYERS + 1;
 constexpr float kActionMinProb = 1e-11f;                    // DiscretePolicy::ACTION_MIN_PROB
 
@@ -133,11 +135,9 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ float to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
+// round-to-nearest (ties away) to TF32 like cvt.rna.tf32.f32, as two integer ops: the cvt runs on a narrow pipe and was
+// 25 % of the kernel's stall samples (profiles/r01h_k_mlp_infer.md); inputs are finite (obs, ReLU outputs)
+__device__ __forceinline__ float to_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 
 // UMMA shared-memory matrix descriptor, K-major, SWIZZLE_NONE (layout_type 0), version 1 (Blackwell)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
@@ -171,13 +171,15 @@ struct ChunkIter {  // walks (net, layer, kblock) over the nets that run
     }
 };
 
-__global__ void __launch_bounds__(kTileM, 1) k_mlp_infer(const InferArgs a) {
+__global__ void __launch_bounds__(kThreads, 1) k_mlp_infer(const InferArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;
     uint8_t* sW = smem + kSmemA;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBar);  // [0..S) full, [S..2S) free, [2S] mma_done
     uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(smem + kSmemBar + 64);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int r = t & (kTileM - 1), half = t >> 7;  // accumulator row (TMEM lane) and column half of this thread
+    float* sBias = reinterpret_cast<float*>(smem + kSmemBias);
     const int row0 = blockIdx.x * kTileM;
     const uint32_t barFull = smem_u32(&bars[0]), barFree = smem_u32(&bars[kNumWSlots]), barDone = smem_u32(&bars[2 * kNumWSlots]);
 
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(kTileM, 1) k_mlp_infer(const InferArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmemBase = *tmemSlot;
-    const uint32_t tmemLane = tmemBase + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tmemLane = tmemBase + ((uint32_t)((warp & 3) * 32) << 16);  // a warp reads TMEM lanes 32 * (warp % 4) ..
 
     // producer / MMA-issuer bookkeeping (thread 0 only)
     ChunkIter loadIt{0, 0, 0};
@@ -207,11 +209,25 @@ __global__ void __launch_bounds__(kTileM, 1) k_mlp_infer(const InferArgs a) {
         // ---- stage the observation tile as layer 0's A operand (zero padded to kPad) ----
         {
             const int kPad0 = N.layer[0].kPad;
-            for (int idx = t; idx < kTileM * kPad0; idx += kTileM) {
-                int r = idx / kPad0, k = idx - r * kPad0;
-                int gr = row0 + r;
-                float v = (gr < a.nRows && k < a.obsDim) ? to_tf32(__ldg(a.obs + (size_t)gr * a.obsDim + k)) : 0.f;
-                *reinterpret_cast<float*>(sA + (k >> 5) * kABlockBytes + canon_off(r, k & 31)) = v;
+            // 8 independent loads in flight per thread (the loop was latency bound: 26 % of the stall samples)
+            const int total = kTileM * kPad0;
+            for (int idx0 = t; idx0 < total; idx0 += kThreads * 8) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    int idx = idx0 + u * kThreads;
+                    int rr = idx / kPad0, k = idx - rr * kPad0;
+                    int gr = row0 + rr;
+                    v[u] = (idx < total && gr < a.nRows && k < a.obsDim) ? __ldg(a.obs + (size_t)gr * a.obsDim + k) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    int idx = idx0 + u * kThreads;
+                    if (idx < total) {
+                        int rr = idx / kPad0, k = idx - rr * kPad0;
+                        *reinterpret_cast<float*>(sA + (k >> 5) * kABlockBytes + canon_off(rr, k & 31)) = to_tf32(v[u]);
+                    }
+                }
             }
         }
         fence_proxy_async();
@@ -220,6 +236,8 @@ __global__ void __launch_bounds__(kTileM, 1) k_mlp_infer(const InferArgs a) {
         for (int l = 0; l < N.numLayers; l++) {
             const MlpLayer& L = N.layer[l];
             const int nkb = L.kPad / kBlockK;
+            for (int j = t; j < L.nPad; j += kThreads) sBias[j] = __ldg(L.b + j);
+            __syncthreads();
             if (warp == 0) {
                 if (lane == 0) {
                     const uint32_t idesc = make_idesc(kTileM, L.nPad);
@@ -255,28 +273,41 @@ __global__ void __launch_bounds__(kTileM, 1) k_mlp_infer(const InferArgs a) {
 
             const bool last = (l == N.numLayers - 1);
             if (!last) {
-                // bias + ReLU -> next layer's A operand (K block c of the next layer = columns [32c, 32c+32))
-                for (int c = 0; c < L.nPad / 32; c++) {
-                    uint32_t v[32];
-                    tc_ld32(tmemLane + c * 32, v);
+                // bias + ReLU -> next layer's A operand (K block c of the next layer = columns [32c, 32c+32)); the two
+                // warpgroups take alternate column chunks, two chunks in flight per thread
+                const int nChunks = L.nPad / 32;
+                for (int c = half; c < nChunks; c += 4) {
+                    const bool two = c + 2 < nChunks;
+                    uint32_t v0[32], v1[32];
+                    tc_ld32(tmemLane + c * 32, v0);
+                    if (two) tc_ld32(tmemLane + (c + 2) * 32, v1);
                     tc_wait_ld();
-                    uint8_t* dst = sA + c * kABlockBytes + (t >> 3) * 1024 + (t & 7) * 16;
 #pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        float4 o;
-                        o.x = to_tf32(fmaxf(__uint_as_float(v[4 * q + 0]) + __ldg(L.b + c * 32 + 4 * q + 0), 0.f));
-                        o.y = to_tf32(fmaxf(__uint_as_float(v[4 * q + 1]) + __ldg(L.b + c * 32 + 4 * q + 1), 0.f));
-                        o.z = to_tf32(fmaxf(__uint_as_float(v[4 * q + 2]) + __ldg(L.b + c * 32 + 4 * q + 2), 0.f));
-                        o.w = to_tf32(fmaxf(__uint_as_float(v[4 * q + 3]) + __ldg(L.b + c * 32 + 4 * q + 3), 0.f));
-                        *reinterpret_cast<float4*>(dst + q * 128) = o;
+                    for (int h = 0; h < 2; h++) {
+                        if (h == 1 && !two) break;
+                        const int cc = c + 2 * h;
+                        const uint32_t* v = h ? v1 : v0;
+                        uint8_t* dst = sA + cc * kABlockBytes + (r >> 3) * 1024 + (r & 7) * 16;
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            const float4 bq = *reinterpret_cast<const float4*>(sBias + cc * 32 + 4 * q);
+                            float4 o;
+                            o.x = to_tf32(fmaxf(__uint_as_float(v[4 * q + 0]) + bq.x, 0.f));
+                            o.y = to_tf32(fmaxf(__uint_as_float(v[4 * q + 1]) + bq.y, 0.f));
+                            o.z = to_tf32(fmaxf(__uint_as_float(v[4 * q + 2]) + bq.z, 0.f));
+                            o.w = to_tf32(fmaxf(__uint_as_float(v[4 * q + 3]) + bq.w, 0.f));
+                            *reinterpret_cast<float4*>(dst + q * 128) = o;
+                        }
                     }
                 }
+            } else if (half != 0) {
+                // the heads are one row per thread: the first warpgroup does them
             } else if (net == 1) {
                 uint32_t v[16];
                 tc_ld16(tmemLane, v);
                 tc_wait_ld();
-                int gr = row0 + t;
-                if (gr < a.nRows && a.value) a.value[gr] = __uint_as_float(v[0]) + __ldg(L.b);
+                int gr = row0 + r;
+                if (gr < a.nRows && a.value) a.value[gr] = __uint_as_float(v[0]) + sBias[0];
             } else {
                 // policy head: softmax(logits / temperature) -> clamp -> sample -> log-prob  (DiscretePolicy.cpp:37-62)
                 constexpr int kMaxAct = 96;
@@ -292,7 +323,7 @@ __global__ void __launch_bounds__(kTileM, 1) k_mlp_infer(const InferArgs a) {
 #pragma unroll
                     for (int i = 0; i < 32; i++) {
                         int j = c * 32 + i;
-                        p[j] = (j < nAct) ? (__uint_as_float(v[i]) + __ldg(L.b + j)) / a.temperature : -INFINITY;
+                        p[j] = (j < nAct) ? (__uint_as_float(v[i]) + sBias[j]) / a.temperature : -INFINITY;
                     }
                 }
                 float mx = -INFINITY;
@@ -306,7 +337,7 @@ __global__ void __launch_bounds__(kTileM, 1) k_mlp_infer(const InferArgs a) {
                 for (int j = 0; j < kMaxAct; j++) {
                     if (j < nAct) { p[j] = fminf(fmaxf(p[j] / sum, kActionMinProb), 1.f); total += p[j]; }
                 }
-                int gr = row0 + t;
+                int gr = row0 + r;
                 int act = 0;
                 float pa = p[0];
                 if (a.deterministic) {
@@ -472,7 +503,7 @@ int launch_infer(rlg_collector* c, const float* obs, int nRows, uint64_t counter
     a.seed = c->cfg.seed; a.counter = counter; a.rowBase = c->rowBase;
     a.deterministic = c->cfg.deterministic; a.temperature = c->cfg.temperature;
     int grid = (nRows + kTileM - 1) / kTileM;
-    k_mlp_infer<<<grid, kTileM, kSmemTotal, s>>>(a);
+    k_mlp_infer<<<grid, kThreads, kSmemTotal, s>>>(a);
     c->launches++;
     CKC(cudaGetLastError());
     return RLG_OK;
