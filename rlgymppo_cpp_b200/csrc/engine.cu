@@ -204,6 +204,7 @@ __device__ __forceinline__ void cands_pass_warp(CarW& w, int ci, bool active, co
                                                 int stride) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    RL_PT(-1);
     if (active) wheel_mesh_rays_init(w);
     const int n = (active && w.cands.n > 0) ? w.cands.n : 0;
     const int incl = warp_incl_scan(n, lane);
@@ -222,6 +223,7 @@ __device__ __forceinline__ void cands_pass_warp(CarW& w, int ci, bool active, co
             w.candGroupStart = gs;
         }
         __syncwarp();
+        RL_PT(15);
         uint32_t* res = wq + kWqItems;
         int next = 0;  // own candidates folded so far
         uint32_t mask = 0;
@@ -252,6 +254,7 @@ __device__ __forceinline__ void cands_pass_warp(CarW& w, int ci, bool active, co
                 r[7] = flags;
             }
             __syncwarp();
+            RL_PT(16);
             if (fits) {
                 while (next < n && base + next < r0 + 32) {
                     const uint32_t* r = res + (base + next - r0) * kWqResWords;
@@ -262,11 +265,13 @@ __device__ __forceinline__ void cands_pass_warp(CarW& w, int ci, bool active, co
                 }
             }
             __syncwarp();
+            RL_PT(17);
         }
         if (fits) w.candMask = mask;
     }
     if (fits) w.haveMask = 1;
     else if (active) wheel_mesh_rays(reinterpret_cast<const ArenaS*>(mine)->cars[ci], k, ms, w);  // serial; haveMask stays 0
+    RL_PT(18);
 }
 
 // Pass 2 (after car-ball): hitbox vs the pre-filtered candidate triangles -> the car's car-world contact segment.
@@ -291,6 +296,7 @@ __device__ __forceinline__ void box_meshes_warp(CollideCtx& cx, ContactSink& cw,
             for (uint32_t m = mask; m; m &= m - 1) wq[i++] = (uint32_t)(cands.node[__ffs(m) - 1] & 0xffffff) | ((uint32_t)lane << 24);
         }
         __syncwarp();
+        RL_PT(19);
         Manifold m; m.a = 1 + ci; m.b = -1; m.n = 0; m.breaking = breaking;
         uint32_t rem = fits ? mask : 0u;  // own pairs not yet consumed
         int next = base;                  // queue index of the next own pair
@@ -316,6 +322,7 @@ __device__ __forceinline__ void box_meshes_warp(CollideCtx& cx, ContactSink& cw,
                 }
             }
             __syncwarp();
+            RL_PT(20);
             while (rem && next < r0 + 32) {
                 const int j = __ffs(rem) - 1;
                 rem &= rem - 1;
@@ -332,9 +339,11 @@ __device__ __forceinline__ void box_meshes_warp(CollideCtx& cx, ContactSink& cw,
                 }
             }
             __syncwarp();
+            RL_PT(21);
         }
         if (m.n > 0) manifold_flush(cw, m);
     }
+    RL_PT(22);
     if (serial) {
         if (cands.n >= 0) box_meshes_candidates(cx, cw, ms, cands, ci, breaking);
         else box_meshes(cx, cw, ms, ci, breaking);

@@ -201,19 +201,19 @@ RL_HD inline RayHit wheel_ray(const TickX& x, const SimCfg& cfg, const MeshSet& 
 
 // ---- btVehicleRL::updateVehicleFirst ---------------------------------------------------------
 RL_HD inline void vehicle_first(CarS& c, const TickX& x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, int ci, CarW& w) {
-    V3 carFwd = c.rot.col(0), carRight = c.rot.col(1), carUp = c.rot.col(2);
+    V3 carUp = c.rot.col(2);
+    // updateWheelTransformsWS + updateWheelTransform: only the steered axle (basis column 1) is consumed later.  The two
+    // front wheels share one steering rotation; a zero angle (the rear wheels) gives the exact identity rotation
+    // (quat_axis_angle(up, 0) = (0, 0, 0, 1)), so its axle is -wheelAxle itself.
+    const V3 wheelDir = c.rot * V3(0, 0, -1);
+    const V3 wheelAxle = c.rot * V3(0, -1, 0);
+    const V3 rearAxle = -wheelAxle;
+    const V3 frontAxle = (c.wheelSteer == 0.f) ? rearAxle : quat_to_mat(quat_axis_angle(-wheelDir, c.wheelSteer)) * (-wheelAxle);
     RL_WHEEL_LOOP
     for (int i = 0; i < 4; i++) {
         WheelW& wh = w.w[i];
-        // updateWheelTransformsWS + updateWheelTransform: only the steered axle (basis column 1) is consumed later
         wh.hardPoint = c.pos + c.rot * k.wheelConn[i];
-        V3 wheelDir = c.rot * V3(0, 0, -1);
-        V3 wheelAxle = c.rot * V3(0, -1, 0);
-        V3 up = -wheelDir;
-        float steer = (i < 2) ? c.wheelSteer : 0.f;
-        M3 steerMat = quat_to_mat(quat_axis_angle(up, steer));
-        wh.axle = steerMat * (-wheelAxle);
-        (void)carFwd; (void)carRight;
+        wh.axle = (i < 2) ? frontAxle : rearAxle;
 
         // rayCast (btVehicleRL.cpp:118-216)
         float rayLen = k.wheelRest[i] + k.suspTravel + k.wheelRadius[i] - C::SUSPENSION_SUBTRACTION;
@@ -597,25 +597,29 @@ RL_HD inline void update_auto_roll(CarS& c, CarW& w, const CarConsts& k, int num
 // ---- btVehicleRL::updateVehicleSecond (btVehicleRL.cpp:237-311,390-402) -----------------------
 RL_HD inline void vehicle_second(CarS& c, CarW& w, const CarConsts& k) {
     const float dt = kTickTime;
-    for (int i = 0; i < 4; i++) {
-        WheelW& wh = w.w[i];
-        if (wh.inContact) {
-            float force = (k.wheelRest[i] - wh.suspLen) * C::SUSPENSION_STIFFNESS * wh.clippedInv;
-            float damp = (wh.suspRelVel < 0) ? C::WHEELS_DAMPING_COMPRESSION : C::WHEELS_DAMPING_RELAXATION;
-            wh.suspForce = force - (damp * wh.suspRelVel);
-            wh.suspForce *= k.wheelForceScale[i];
-            if (wh.suspForce < 0) wh.suspForce = 0;
-        } else {
-            wh.suspForce = 0;
-        }
-    }
+    // the chassis velocities and the inertia tensor stay in registers across the eight applyImpulse calls (same
+    // operations in the same order as btRigidBody::applyImpulse on the body)
+    const V3 pos = c.pos;
+    V3 vel = c.vel, angvel = c.angvel;
+    const M3 iiw = w.invInertiaWorld;
     RL_WHEEL_LOOP
     for (int i = 0; i < 4; i++) {
         WheelW& wh = w.w[i];
-        if (wh.suspForce != 0) {
-            V3 off = wh.contactPoint - c.pos;
-            float scale = (wh.suspForce * dt) + c.wheelPush[i];
-            apply_impulse(c, w, k.invMass, wh.contactNormal * scale, off);
+        float suspForce = 0;
+        if (wh.inContact) {
+            float force = (k.wheelRest[i] - wh.suspLen) * C::SUSPENSION_STIFFNESS * wh.clippedInv;
+            float damp = (wh.suspRelVel < 0) ? C::WHEELS_DAMPING_COMPRESSION : C::WHEELS_DAMPING_RELAXATION;
+            suspForce = force - (damp * wh.suspRelVel);
+            suspForce *= k.wheelForceScale[i];
+            if (suspForce < 0) suspForce = 0;
+        }
+        wh.suspForce = suspForce;
+        if (suspForce != 0) {
+            V3 off = wh.contactPoint - pos;
+            float scale = (suspForce * dt) + c.wheelPush[i];
+            V3 impulse = wh.contactNormal * scale;
+            vel += impulse * k.invMass;
+            angvel += iiw * cross(off, impulse);
         }
     }
     V3 upDir = c.rot.col(2);
@@ -623,12 +627,15 @@ RL_HD inline void vehicle_second(CarS& c, CarW& w, const CarConsts& k) {
     for (int i = 0; i < 4; i++) {
         WheelW& wh = w.w[i];
         if (!is_zero(wh.impulse)) {
-            V3 off = wh.contactPoint - c.pos;
+            V3 off = wh.contactPoint - pos;
             float upDot = dot(upDir, off);
             V3 rel = off - upDir * upDot;
-            apply_impulse(c, w, k.invMass, wh.impulse * dt, rel);
+            V3 impulse = wh.impulse * dt;
+            vel += impulse * k.invMass;
+            angvel += iiw * cross(rel, impulse);
         }
     }
+    c.vel = vel; c.angvel = angvel;
 }
 
 // ---- Car::_UpdateBoost (Car.cpp:477-505) ------------------------------------------------------

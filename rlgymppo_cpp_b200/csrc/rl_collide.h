@@ -12,11 +12,12 @@
 
 namespace rl {
 
-struct Contact {
+struct alignas(16) Contact {  // 64 bytes: moves between the scratch segments (global memory) and the roles as 4 x 16 B
     int32_t a, b;
     V3 posA, posB, normal;
     float dist, friction, restitution;
     int32_t special;
+    int32_t pad_;
     // uninitialised on purpose (see NoInit): manifold_add writes every member before a contact is stored
     RL_HDI Contact() : posA(NoInit()), posB(NoInit()), normal(NoInit()) {}
 };

@@ -198,7 +198,7 @@ RL_HD RL_NOINLINE inline void island_setup(const SolverBody* sb, int numBodies, 
     for (int i = 0; i < numBodies; i++) { spN[i] = 0; spDist[i] = 0; spNormal[i] = V3(); spFriction[i] = spRestitution[i] = 0; }
 
     for (int ci = 0; ci < numContacts; ci++) {
-        const Contact& cp = contacts[ci];
+        const Contact cp = contacts[ci];  // one 64-byte fetch instead of field-by-field round trips to the scratch segment
         const int ia = cp.a < 0 ? -1 : cp.a - base, ib = cp.b < 0 ? -1 : cp.b - base;
         // a body without contact response (demoed car) or in a sleeping island (frozen ball) takes its manifolds out of
         // the solver entirely (btCollisionDispatcher::needsResponse / island filtering); it is NOT a static obstacle
@@ -306,7 +306,9 @@ RL_HD RL_NOINLINE inline void solve_island_one(SolverBody& b, int body, const Co
     Row rows[kMaxRows];
     Row fric[kMaxRows];
     int nRows, nFric;
+    RL_PT(-1);
     island_setup(&b, 1, body, contacts, numContacts, rows, fric, nRows, nFric);
+    RL_PT(23);
     if (b.active) {
         const float invMass = b.invMass;
         V3 dLin = b.dLin, dAng = b.dAng, push = b.push, turn = b.turn;
@@ -331,6 +333,7 @@ RL_HD RL_NOINLINE inline void solve_island_one(SolverBody& b, int body, const Co
             }
             if (residual <= 0.f || it >= numIterations - 1) break;
         }
+        RL_PT(24);
         auto resolve = [&](Row& c, bool lowerOnly) {  // resolve_row
             float deltaImpulse = c.rhs - c.applied * 0.f;
             float dv1 = dot(c.n1, dLin) + dot(c.rxn1, dAng);
@@ -358,7 +361,9 @@ RL_HD RL_NOINLINE inline void solve_island_one(SolverBody& b, int body, const Co
         }
         b.dLin = dLin; b.dAng = dAng; b.push = push; b.turn = turn;
     }
+    RL_PT(25);
     island_finish(&b, 1);
+    RL_PT(26);
 }
 
 }  // namespace rl

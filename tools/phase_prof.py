@@ -32,10 +32,14 @@ def main(path):
                "car p1: wheels/air/jump/flip/auto-roll", "car p1: vehicle_second + boost", "car p1: car-ball", "car p1: hitbox-mesh",
                "car p1: hitbox-plane", "ball p1: pads pre-tick", "ball p1: sphere-mesh", "ball p1: sphere-plane",
                "ball p2: damping, car-car pairs", "ball p2: gather + solve + write back", "ball p2: finish", "car p2: own island solve",
-               "car p3: integrate, post-tick, pad overlap"]
+               "car p3: integrate, post-tick, pad overlap",
+               "car cands pass: scan + queue", "car cands pass: pair evaluation (rays x4, pre-filter)", "car cands pass: fold",
+               "car cands pass: tail / serial lanes", "car hitbox pass: scan + queue", "car hitbox pass: pair evaluation (early-out, GJK/SAT)",
+               "car hitbox pass: manifold fold", "car hitbox pass: tail", "* island_one: row setup (both roles)",
+               "* island_one: split-impulse iterations", "* island_one: velocity iterations", "* island_one: finish"]
         print("sub-phases (mean over the warps of the role, percent of the mean warp total):")
         for i, nm in enumerate(SUB):
-            sel = (role > 0) if nm.startswith("car") else (role == 0)
+            sel = (role > 0) if nm.startswith("car") else ((role == 0) if nm.startswith("ball") else (role >= 0))
             print(f"  {nm:<58}{100 * sub[:, sel, i].mean() / tot:>7.2f}%")
     bt = d[:, :, 8].max(axis=1)
     print(f"block totals: mean {bt.mean():.0f} max {bt.max():.0f} min {bt.min():.0f} cycles; slowest/mean = {bt.max() / bt.mean():.3f}")
