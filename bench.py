@@ -272,6 +272,15 @@ def run_ours(args, rank, local_rank, world):
     h2d = A * P * 4
     d2h = A * P * OBS * 4 + A * P * 4 + A
 
+    ppo_iter = None
+    if not args.no_ppo:
+        # the metric's second half: one whole PPO iteration (collect -> GAE -> ExperienceBuffer -> minibatch update -> push
+        # weights) of the examplemain-shaped learner (batch = what one iteration collects, 4 minibatches, 1 epoch)
+        try:
+            ppo_iter = ppo_iteration_time(args, rank, local_rank, world)
+        except Exception as ex:  # reported, never required for the collection number
+            ppo_iter = {"error": f"{type(ex).__name__}: {ex}"}
+
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         S = e.state_bytes
@@ -318,6 +327,8 @@ def run_ours(args, rank, local_rank, world):
                              "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 rate)"},
             "wall_s_timed_region": t_wall,
         }
+        if ppo_iter is not None:
+            out["ppo_iteration"] = ppo_iter
         if world == 1 and not args.no_cpu_baseline:
             try:
                 out["cpu_baseline"] = cpu_baseline_sample()
@@ -326,6 +337,28 @@ def run_ours(args, rank, local_rank, world):
         emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def ppo_iteration_time(args, rank, local_rank, world, iters=6):
+    """"Total Iteration Time" (Learner.cpp:558) of the device learner on the bench workload, median of the last iterations."""
+    import torch
+
+    from rlgymppo_cpp_b200 import learner
+
+    A, T = args.arenas, args.env_steps
+    rows = A * 2 * T  # per rank
+    cfg = learner.LearnerConfig(timestepsPerIteration=rows * world, expBufferSize=rows * world, randomSeed=123)
+    cfg.ppo = learner.PPOLearnerConfig(batchSize=rows, miniBatchSize=rows // 4, epochs=1, policyLR=2e-4, criticLR=2e-4, entCoef=0.01)
+    L = learner.Learner(workload_cfg(A, local_rank, rank), cfg, device_index=local_rank)
+    reports = L.learn(max_iterations=iters)
+    torch.cuda.synchronize()
+    tail = reports[2:]
+    med = lambda k: float(np.median([r[k] for r in tail]))
+    return {"total_iteration_time_s": med("Total Iteration Time"), "collection_time_s": med("Collection Time"),
+            "consumption_time_s": med("Consumption Time"), "ppo_learn_time_s": med("PPO Learn Time"),
+            "timesteps_per_iteration": int(tail[-1]["Timesteps Collected"]), "overall_steps_per_s": med("Overall Steps/Second"),
+            "config": f"batch {rows} rows/rank, 4 minibatches, 1 epoch, Adam lr 2e-4, policy/critic 256x256x256, torch autograd (TF32) update, "
+                      f"{world} data-parallel rank(s)", "iterations_timed": len(tail)}
 
 
 _REAL_STDOUT = None
@@ -351,6 +384,7 @@ def main():
     ap.add_argument("--arenas", type=int, default=ARENAS_PER_GPU, help="arenas per GPU (default: BASELINE configs[1])")
     ap.add_argument("--env-steps", type=int, default=4, help="env-steps per bench step (one collect call; cfg1's 100k timesteps/iteration ~ 4 x 32768)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ppo", action="store_true", help="skip the PPO iteration-time measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

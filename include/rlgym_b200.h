@@ -266,6 +266,11 @@ typedef struct rlg_metrics_host {
 int rlg_engine_metrics(rlg_engine* e, rlg_metrics_host* out);   /* synchronises the engine stream */
 int rlg_engine_reset_metrics(rlg_engine* e);                    /* GameInst::ResetMetrics for every arena */
 
+/* GameState::scoreLine of every arena (G/Utils/Gamestates/GameState.cpp:100-101: incremented by the step's snapshot when the
+ * ball is behind a goal line, index 0 = ball at y > 0 = blue scored; zeroed by a reset): out_host is [A][2] int32.
+ * What SkillTracker's goal test (Math::IsBallScored on stepResult.state, SkillTracker.cpp:132-134) reads. */
+int rlg_engine_score_lines(rlg_engine* e, int32_t* out_host);
+
 /* Number of kernel launches issued by this engine so far (bench "gpu_launches"). */
 uint64_t rlg_engine_launch_count(const rlg_engine* e);
 /* Wait for all work queued on the engine's stream. */

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -875,6 +876,17 @@ int rlg_engine_metrics(rlg_engine* e, rlg_metrics_host* out) {
     out->step_reward_count = stepCount; out->episode_count = epCount; out->total_steps = steps;
     out->avg_step_reward = stepCount ? stepTotal / stepCount : NAN;
     out->avg_episode_reward = epCount ? epTotal / epCount : NAN;
+    return RLG_OK;
+}
+int rlg_engine_score_lines(rlg_engine* e, int32_t* out_host) {
+    if (!e || !out_host) return fail(RLG_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(e->device));
+    const size_t A = (size_t)e->cfg.numArenas;
+    const size_t w0 = offsetof(ArenaS, scoreLine) / 4;  // word-transposed state: one contiguous row of A words per member word
+    std::vector<int32_t> h(2 * A);
+    CK(cudaMemcpyAsync(h.data(), e->state + w0 * A, 2 * A * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    for (size_t a = 0; a < A; a++) { out_host[2 * a] = h[a]; out_host[2 * a + 1] = h[A + a]; }
     return RLG_OK;
 }
 int rlg_engine_reset_metrics(rlg_engine* e) {

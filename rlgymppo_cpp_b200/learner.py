@@ -77,6 +77,7 @@ class LearnerConfig:  # LearnerConfig.h:14-81 (render / metrics-sender / checkpo
     metricsProjectName: str = "rlgymppo-cpp"
     metricsGroupName: str = "unnamed-runs"
     metricsRunName: str = "rlgymppo-cpp-run"
+    skillTrackerConfig: "object" = None  # skill_tracker.SkillTrackerConfig (LearnerConfig.h:79); None = disabled
 
     @property
     def num_arenas(self) -> int:
@@ -214,8 +215,9 @@ class PPOLearner:
     def learn(self, exp: ExperienceBuffer, report: dict):
         cfg = self.cfg
         n_iter = n_mb = 0
-        mean_entropy = mean_div = mean_val_loss = mean_ratio = 0.0
-        clip_fracs = []
+        # diagnostics accumulate on the device and are read once at the end: no host sync inside the minibatch loop
+        acc = torch.zeros(5, dtype=torch.float32, device=self.device)  # entropy, kl, ratio, value loss, clip fraction
+        n_clip = 0
         before_p = torch.cat([p.detach().reshape(-1) for p in self.policy.parameters()]).clone()
         before_c = torch.cat([p.detach().reshape(-1) for p in self.value_net.parameters()]).clone()
         train_policy, train_critic = cfg.policyLR != 0, cfg.criticLR != 0
@@ -241,15 +243,16 @@ class PPOLearner:
                         ppo_loss = (policy_loss - entropy * cfg.entCoef) * ratio_b
                         with torch.no_grad():  # SB3-style diagnostics (PPOLearner.cpp:181-196)
                             log_ratio = logp - old
-                            mean_div += float(((torch.exp(log_ratio) - 1) - log_ratio).mean())
-                            clip_fracs.append(float(((ratio - 1).abs() > cfg.clipRange).float().mean()))
-                            mean_ratio += float(ratio.mean())
-                            mean_entropy += float(entropy)
+                            acc[1] += ((torch.exp(log_ratio) - 1) - log_ratio).mean()
+                            acc[4] += ((ratio - 1).abs() > cfg.clipRange).float().mean()
+                            acc[2] += ratio.mean()
+                            acc[0] += entropy.detach()
+                            n_clip += 1
                         ppo_loss.backward()
                     if train_critic:
                         value_loss = torch.nn.functional.mse_loss(vals, tgt) * ratio_b
                         value_loss.backward()
-                        mean_val_loss += float(value_loss.detach())
+                        acc[3] += value_loss.detach()
                     n_mb += 1
                 if train_policy:
                     self._allreduce_grads(self.policy)
@@ -264,11 +267,12 @@ class PPOLearner:
         after_p = torch.cat([p.detach().reshape(-1) for p in self.policy.parameters()])
         after_c = torch.cat([p.detach().reshape(-1) for p in self.value_net.parameters()])
         self.cumulative_model_updates += n_iter
+        mean_entropy, mean_div, mean_ratio, mean_val_loss, clip_sum = (float(x) for x in acc.tolist())  # the one sync
         total = time.perf_counter() - t0
         report.update({
             "PPO Batch Consumption Time": total / n_iter, "Cumulative Model Updates": self.cumulative_model_updates,
             "Policy Entropy": mean_entropy / n_mb, "Mean KL Divergence": mean_div / n_mb, "Mean Ratio": mean_ratio / n_mb,
-            "Value Function Loss": mean_val_loss / n_mb, "SB3 Clip Fraction": float(np.mean(clip_fracs)) if clip_fracs else 0.0,
+            "Value Function Loss": mean_val_loss / n_mb, "SB3 Clip Fraction": clip_sum / n_clip if n_clip else 0.0,
             "Policy Update Magnitude": float((before_p - after_p).norm()), "Value Function Update Magnitude": float((before_c - after_c).norm()),
             "PPO Learn Time": total,
         })
@@ -303,6 +307,12 @@ class Learner:
         self.total_timesteps = 0
         self.total_epochs = 0
         self.iteration_callback = iteration_callback
+        self.skill_tracker = None
+        stc = cfg.skillTrackerConfig
+        if stc is not None and stc.enabled and self.rank == 0:  # eval arenas live on rank 0 only (Learner.cpp:137-144)
+            from . import skill_tracker
+
+            self.skill_tracker = skill_tracker.SkillTracker.on_engine(stc, engine_cfg, tuple(cfg.ppo.policyLayerSizes), device_index, cfg.randomSeed)
         self._push_weights()
         self.engine.reset()
 
@@ -358,6 +368,10 @@ class Learner:
             self.ppo.learn(self.exp, report)
             self._push_weights()
             torch.cuda.synchronize()
+            if self.skill_tracker is not None:  # Learner.cpp:526-538
+                self.skill_tracker.run_games(mlp_layers_numpy(self.ppo.policy), collected)
+                for mode, rating in self.skill_tracker.cur_rating.items():
+                    report["Skill Rating" + ("" if mode == "" else " ") + mode] = rating
             self.total_epochs += cfg.ppo.epochs
             t_total = time.perf_counter() - t0
             rew = self.collector.read("reward")

@@ -39,3 +39,57 @@ def test_learner_two_iterations_and_weight_roundtrip():
     lr.engine.sync()
     ref = po.mlp_forward(L.mlp_layers_numpy(lr.ppo.value_net), obs)[:, 0]
     assert np.all(np.abs(val.cpu().numpy() - ref) <= 2e-2 + 1e-2 * np.abs(ref))
+
+
+def test_skill_tracker_on_engine_detects_goals_and_rates():
+    """SkillTracker over a device eval pool: a ball injected behind a goal line is a goal for the policy on the scoring side
+    (Math::IsBallScored on the step's snapshot, SkillTracker.cpp:132-149) and ends the episode; RunGames moves the ELO."""
+    import torch
+
+    from rlgymppo_cpp_b200 import collector, skill_tracker as stm
+
+    assert torch.cuda.is_available()
+    stc = stm.SkillTrackerConfig(enabled=True, numEnvs=6, simTime=6 * 8 * 5 / 120, updateInterval=1, timestepsPerVersion=10 ** 9)
+    ecfg = abi.default_cfg(num_arenas=64, team_size=1)
+    st = stm.SkillTracker.on_engine(stc, ecfg, (64, 64), seed=7)
+    e = st.engine
+    assert e.A == 6 and st.mode == "1v1" and sorted(st.teams.tolist()) == [0, 1]
+    # dummy reward: every reward is exactly 0
+    done, scored = st.step_fn(np.zeros(e.A * e.P, dtype=np.int32))
+    assert not scored.any()
+    assert not e.read_outputs()[1].any()
+    # ball behind the orange goal line (y > 0) in arena 1, behind the blue one in arena 4
+    ids = np.array([1, 4], dtype=np.int32)
+    cars, balls, pads, ticks = e.get_state(ids)
+    balls["pos"][0] = (0.0, 5300.0, 100.0)
+    balls["pos"][1] = (0.0, -5300.0, 100.0)
+    balls["vel"][:] = 0
+    e.set_state(ids, balls=balls)
+    done, scored = st.step_fn(np.zeros(e.A * e.P, dtype=np.int32))
+    assert scored.tolist() == [0, 1, 0, 0, -1, 0] and done[1] and done[4]
+    # the finished arenas were re-set to kickoffs: no goal on the next step, ball back at the centre
+    done, scored = st.step_fn(np.zeros(e.A * e.P, dtype=np.int32))
+    assert not scored.any()
+    _, b2, _, _ = e.get_state(ids)
+    assert np.all(np.abs(b2["pos"][:, 1]) < 200)
+    # RunGames with two different weight sets: plays 5 steps per game, freezes version 0, ratings stay finite and zero-sum
+    w_cur = collector.default_linear_init(st.collector.policy_dims, 1)
+    played = st.run_games(w_cur, 1000)
+    assert played is not None and len(st.old_policies) == 1
+    total = st.cur_rating["1v1"] + st.old_ratings[0]["1v1"]
+    assert abs(total - 2000.0) < 1e-2
+
+
+def test_learner_reports_skill_rating():
+    import torch
+
+    from rlgymppo_cpp_b200 import learner as L, skill_tracker as stm
+
+    assert torch.cuda.is_available()
+    stc = stm.SkillTrackerConfig(enabled=True, numEnvs=4, simTime=4 * 8 * 3 / 120, updateInterval=1, timestepsPerVersion=3000, maxVersions=2)
+    cfg = L.LearnerConfig(numThreads=4, numGamesPerThread=32, timestepsPerIteration=1024, expBufferSize=2048, randomSeed=9, skillTrackerConfig=stc,
+                          ppo=L.PPOLearnerConfig(batchSize=1024, miniBatchSize=512, epochs=1, policyLR=2e-4, criticLR=2e-4))
+    lr = L.Learner(abi.default_cfg(num_arenas=cfg.num_arenas, team_size=1), cfg)
+    reps = lr.learn(max_iterations=4)
+    assert all("Skill Rating 1v1" in r and np.isfinite(r["Skill Rating 1v1"]) for r in reps)
+    assert 1 <= len(lr.skill_tracker.old_policies) <= 2

@@ -13,8 +13,8 @@ cat gpurun_out/bench.json | cut -c1-1500
 timeout 600 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
 cat gpurun_out/bench_ref.json | cut -c1-600
 # launch list (cold-cache, serialised): shares only
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-ppo > gpurun_out/ncu_bench.log 2>&1
 # one full capture of the dominant kernel
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_roles -s 8 -c 1 -o gpurun_out/prof_k_roles python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_mlp_infer -s 12 -c 1 -o gpurun_out/prof_k_mlp python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_mlp.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_roles -s 8 -c 1 -o gpurun_out/prof_k_roles python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-ppo > gpurun_out/ncu_full.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_mlp_infer -s 12 -c 1 -o gpurun_out/prof_k_mlp python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-ppo > gpurun_out/ncu_full_mlp.log 2>&1
 ls -la gpurun_out
