@@ -74,7 +74,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -215,13 +215,14 @@ def run_ours(args, rank, local_rank, world):
         col.collect(T)
         col.gae(0.99, 0.95, 1.0, 10.0)
 
+    # clocks / throttle reasons are sampled under load: from the warm-up on (nvidia-smi needs ~0.1 s to produce its first line)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     # settle the arenas into their steady-state mix (resets, contacts) before timing
     with torch.cuda.stream(ext):
         for i in range(W):
             one_iteration()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = e.launch_count + col.launch_count
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
@@ -306,7 +307,7 @@ def run_ours(args, rank, local_rank, world):
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg2: 1v1 soccar, 16384 arenas/GPU, DefaultObs + examplemain rewards/terminals, RandomState, tickSkip 8, "
+            "config": {"workload": f"{'cfg2: ' if (TEAM == 1 and A == ARENAS_PER_GPU) else 'sweep: '}{TEAM}v{TEAM} soccar, {A} arenas/GPU, DefaultObs + examplemain rewards/terminals, RandomState, tickSkip 8, "
                                    "on-device policy (256x256x256) + critic inference, sampling, trajectory ring, GAE; placeholder mesh set v1; "
                                    f"one bench step = one collect of {T} env-steps over every arena + GAE",
                        "arenas_per_gpu": A, "players_per_arena": P, "obs_size": OBS, "tick_skip": 8, "env_steps_per_bench_step": T,
@@ -346,7 +347,7 @@ def ppo_iteration_time(args, rank, local_rank, world, iters=6):
     from rlgymppo_cpp_b200 import learner
 
     A, T = args.arenas, args.env_steps
-    rows = A * 2 * T  # per rank
+    rows = A * 2 * TEAM * T  # per rank
     cfg = learner.LearnerConfig(timestepsPerIteration=rows * world, expBufferSize=rows * world, randomSeed=123)
     cfg.ppo = learner.PPOLearnerConfig(batchSize=rows, miniBatchSize=rows // 4, epochs=1, policyLR=2e-4, criticLR=2e-4, entCoef=0.01)
     L = learner.Learner(workload_cfg(A, local_rank, rank), cfg, device_index=local_rank)
@@ -385,7 +386,12 @@ def main():
     ap.add_argument("--env-steps", type=int, default=4, help="env-steps per bench step (one collect call; cfg1's 100k timesteps/iteration ~ 4 x 32768)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ppo", action="store_true", help="skip the PPO iteration-time measurement")
+    ap.add_argument("--team", type=int, default=1, help="players per team (sweep only: the headline metric is quoted on 1v1)")
     args = ap.parse_args()
+    global TEAM, METRIC
+    if args.team != 1:
+        TEAM = args.team
+        METRIC = f"collection steps/sec ({TEAM}v{TEAM}, tickSkip=8)"
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

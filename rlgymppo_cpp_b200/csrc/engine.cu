@@ -199,6 +199,67 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
     return v;
 }
 
+// Pass 0: the candidate lists themselves — the leaf-grid cell lists of the cars near the mesh are scanned one (car, leaf)
+// pair per lane; the owning lane appends the overlapping leaves in list order (== collect_candidates).
+__device__ __forceinline__ void collect_candidates_warp(CarW& w, int ci, bool active, const CarConsts& k, const MeshSet& ms, const uint32_t* mine,
+                                                        uint32_t* wq) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    V3 mn, mx;
+    int first = 0, count = 0;
+    bool useGrid = false, walk = false;
+    if (active) {
+        car_cands_box(reinterpret_cast<const ArenaS*>(mine)->cars[ci], k, mn, mx);
+        w.cands.n = 0;
+        if (!inside_free_box(ms, mn, mx)) {
+            if (grid_lookup(ms, mn, mx, first, count)) useGrid = true; else walk = true;
+        }
+    }
+    const int n = useGrid ? count : 0;
+    const int incl = warp_incl_scan(n, lane);
+    const int base = incl - n;
+    const bool fits = useGrid && incl <= kWqItems;
+    if (useGrid && !fits) walk = true;
+    const unsigned fitLanes = __ballot_sync(full, fits && n > 0);
+    if (fitLanes) {
+        const int totalFit = __shfl_sync(full, incl, 31 - __clz(fitLanes));
+        float* box = reinterpret_cast<float*>(wq + kWqItems);  // per owner lane: query box (6) + first list index (1)
+        uint32_t* ev = wq + kWqItems + 32 * 7;                 // per worker lane: the list entry it tested this round
+        if (fits && n > 0) {
+            float* b = box + lane * 7;
+            b[0] = mn.x; b[1] = mn.y; b[2] = mn.z; b[3] = mx.x; b[4] = mx.y; b[5] = mx.z; b[6] = __int_as_float(first);
+            for (int j = 0; j < n; j++) wq[base + j] = (uint32_t)lane | ((uint32_t)j << 5);
+        }
+        __syncwarp();
+        for (int r0 = 0; r0 < totalFit; r0 += 32) {
+            const int g = r0 + lane;
+            bool pass = false;
+            if (g < totalFit) {
+                const uint32_t it = wq[g];
+                const float* b = box + (it & 31u) * 7;
+                const int e = ms.gridList[__float_as_int(b[6]) + (int)(it >> 5)];
+                const BvhNode& nd = ms.nodes[e & 0xffffff];
+                pass = aabb_overlap(nd.mn, nd.mx, V3(b[0], b[1], b[2]), V3(b[3], b[4], b[5]));
+                ev[lane] = (uint32_t)e;
+            }
+            const unsigned bits = __ballot_sync(full, pass);
+            __syncwarp();
+            if (fits && n > 0 && base < r0 + 32 && base + n > r0) {
+                const int lo = (base > r0 ? base : r0) - r0, hi = (base + n < r0 + 32 ? base + n : r0 + 32) - r0;  // own lanes of this round
+                unsigned m = bits & (hi >= 32 ? full : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+                for (; m; m &= m - 1) {
+                    if (w.cands.n < 0) break;
+                    if (w.cands.n >= kMaxCands) { w.cands.n = -1; break; }
+                    w.cands.node[w.cands.n++] = (int)ev[__ffs(m) - 1];
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (walk) collect_candidates(ms, mn, mx, w.cands);
+    RL_PT(0);
+}
+
 // Pass 1 (right after the candidates are collected): the mesh part of the four wheel rays -> w.meshHit, and the hitbox
 // pre-filter (leaf box vs hitbox AABB) -> w.candMask / w.candGroupStart.
 __device__ __forceinline__ void cands_pass_warp(CarW& w, int ci, bool active, const CarConsts& k, const MeshSet& ms, const uint32_t* mine, uint32_t* wq,
@@ -410,7 +471,8 @@ __global__ void __maxnreg__(168) k_roles(const __grid_constant__ RolesArgs g) {
             if (valid) tick_p1_ball(s, x, g.cfg, g.ms, k, thr, scratch);
         } else {
             CollideCtx cx; ContactSink cw;
-            if (valid) tick_p1_car_pose(s, x, g.cfg, g.ms, k, role - 1, w);
+            if (valid) tick_p1_car_pose(s, x, g.cfg, g.ms, k, role - 1, w, false);
+            collect_candidates_warp(w, role - 1, valid, k, g.ms, mine, wq);  // whole warp
             cands_pass_warp(w, role - 1, valid, k, g.ms, mine, wq, g.stride);  // whole warp
             if (valid) tick_p1_car_begin(s, x, g.cfg, g.ms, k, thr, role - 1, w, scratch, first, cx, cw);
             box_meshes_warp(cx, cw, g.ms, w, role - 1, thr.car, valid, k, mine, wq, g.stride);  // whole warp

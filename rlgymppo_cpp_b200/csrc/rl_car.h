@@ -679,8 +679,25 @@ RL_HD inline void car_respawn(CarS& c, int team, uint32_t rnd);
 // ---- Car::_PreTickUpdate (Car.cpp:58-131) -----------------------------------------------------
 // respawnRnd: a random word for Car::Respawn's spawn-slot pick; derived by the caller from the arena RNG state, the
 // tick and the car index WITHOUT advancing the arena RNG (the roles of a tick run concurrently)
-// part A: up to the pose being final for this tick and the mesh candidates collected
-RL_HD inline void car_pre_tick_a(CarS& c, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, int ci, CarW& w, uint32_t respawnRnd) {
+// query box of a car's mesh candidates: hitbox AABB united with the four wheel-ray segments, padded
+RL_HDI void car_cands_box(const CarS& c, const CarConsts& k, V3& mnOut, V3& mxOut) {
+    V3 center = c.pos + c.rot * k.hitboxOffset;
+    V3 ext(dot(vabs(c.rot.r[0]), k.halfExt), dot(vabs(c.rot.r[1]), k.halfExt), dot(vabs(c.rot.r[2]), k.halfExt));
+    V3 mn = center - ext, mx = center + ext;
+    V3 wheelDir = c.rot * V3(0, 0, -1);
+#pragma unroll 1
+    for (int i = 0; i < 4; i++) {
+        V3 hp = c.pos + c.rot * k.wheelConn[i];
+        float rayLen = k.wheelRest[i] + k.suspTravel + k.wheelRadius[i] - C::SUSPENSION_SUBTRACTION;
+        V3 tg = hp + wheelDir * rayLen;
+        mn = vmin(mn, vmin(hp, tg)); mx = vmax(mx, vmax(hp, tg));
+    }
+    const V3 pad(0.02f, 0.02f, 0.02f);  // > the 0.01 box padding of the direct ray walk
+    mnOut = mn - pad; mxOut = mx + pad;
+}
+// part A: up to the pose being final for this tick and (collect) the mesh candidates collected
+RL_HD inline void car_pre_tick_a(CarS& c, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, int ci, CarW& w, uint32_t respawnRnd,
+                                 bool collect = true) {
     w.force = V3(); w.torque = V3(); w.velCache = V3();
     c.controls.throttle = clampf(c.controls.throttle, -1.f, 1.f);
     c.controls.steer = clampf(c.controls.steer, -1.f, 1.f);
@@ -692,20 +709,10 @@ RL_HD inline void car_pre_tick_a(CarS& c, const SimCfg& cfg, const MeshSet& ms, 
         if (c.demoRespawnTimer == 0) car_respawn(c, car_team(ci, cfg.spawnOpponents), respawnRnd);
     }
     w.invInertiaWorld = world_inertia(c.rot, k.invInertiaLocal);
-    {   // one BVH query for the hitbox and the four wheel rays (pose is final for this tick: only a respawn moves it)
-        V3 center = c.pos + c.rot * k.hitboxOffset;
-        V3 ext(dot(vabs(c.rot.r[0]), k.halfExt), dot(vabs(c.rot.r[1]), k.halfExt), dot(vabs(c.rot.r[2]), k.halfExt));
-        V3 mn = center - ext, mx = center + ext;
-        V3 wheelDir = c.rot * V3(0, 0, -1);
-#pragma unroll 1
-        for (int i = 0; i < 4; i++) {
-            V3 hp = c.pos + c.rot * k.wheelConn[i];
-            float rayLen = k.wheelRest[i] + k.suspTravel + k.wheelRadius[i] - C::SUSPENSION_SUBTRACTION;
-            V3 tg = hp + wheelDir * rayLen;
-            mn = vmin(mn, vmin(hp, tg)); mx = vmax(mx, vmax(hp, tg));
-        }
-        const V3 pad(0.02f, 0.02f, 0.02f);  // > the 0.01 box padding of the direct ray walk
-        collect_candidates(ms, mn - pad, mx + pad, w.cands);
+    if (collect) {  // one BVH query for the hitbox and the four wheel rays (pose is final for this tick: only a respawn moves it)
+        V3 mn, mx;
+        car_cands_box(c, k, mn, mx);
+        collect_candidates(ms, mn, mx, w.cands);
     }
     RL_PT(0);
 }

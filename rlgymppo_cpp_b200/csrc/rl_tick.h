@@ -140,7 +140,7 @@ RL_HDI void tick_s0_ball(const ArenaS& a, TickX x) {
 // car-ball) + hitbox-mesh narrowphase + end (hitbox-plane, counts).  The role kernel replaces the two mesh parts by
 // warp-cooperative passes (engine.cu cands_pass_warp / box_meshes_warp): same triangles, same order, same arithmetic
 // per triangle (ray_tri4, box_mesh_item), so hits and contacts are identical.
-RL_HD inline void tick_p1_car_pose(ArenaS& a, TickX x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, int c, CarW& w) {
+RL_HD inline void tick_p1_car_pose(ArenaS& a, TickX x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, int c, CarW& w, bool collect = true) {
     CarS& car = a.cars[c];
     CarX& o = x.car[c];
     // activation state / contact response are decided at the top of Car::_PreTickUpdate, before a possible respawn,
@@ -148,7 +148,7 @@ RL_HD inline void tick_p1_car_pose(ArenaS& a, TickX x, const SimCfg& cfg, const 
     o.noResponse = car.isDemoed;
     o.ballVelCache = V3(); o.velCache = V3();
     RL_PT(-1);
-    car_pre_tick_a(car, cfg, ms, k, c, w, respawn_rnd(a, c));
+    car_pre_tick_a(car, cfg, ms, k, c, w, respawn_rnd(a, c), collect);
 }
 // between the two: w.meshHit (+ the hitbox pre-filter) from wheel_mesh_rays or the role kernel's cooperative pass
 RL_HD inline void tick_p1_car_begin(ArenaS& a, TickX x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, const Thresholds& thr, int c, CarW& w,
