@@ -316,6 +316,18 @@ class Learner:
         self._push_weights()
         self.engine.reset()
 
+    def save(self, folder=None):
+        """Learner::Save (Learner.cpp:244-281), reference on-disk layout (checkpoint.py)."""
+        from . import checkpoint
+
+        return checkpoint.save_learner(self, folder)
+
+    def load(self, folder=None):
+        """Learner::Load (Learner.cpp:283-365)."""
+        from . import checkpoint
+
+        return checkpoint.load_learner(self, folder)
+
     def _push_weights(self):
         self.collector.set_weights(0, mlp_layers_numpy(self.ppo.policy))
         self.collector.set_weights(1, mlp_layers_numpy(self.ppo.value_net))
