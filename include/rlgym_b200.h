@@ -293,6 +293,19 @@ int rlg_engine_step_to(rlg_engine* e, const int32_t* action_idx, float* obs_out,
  * Both networks are Linear+ReLU stacks with a final Linear (DiscretePolicy.cpp:7-30, ValueEstimator.cpp:6-27); the
  * forward runs on the 5th-gen tensor cores (tcgen05, TF32 inputs, FP32 accumulate in TMEM) fused with bias+ReLU,
  * softmax(logits / temperature), clamp(ACTION_MIN_PROB=1e-11, 1), multinomial sampling and log-prob. */
+/* ---- PPO minibatch update: the dense contractions on the tensor cores (csrc/gemm.cu) ----------------------------------
+ * C[M, N] (+)= A[M, K] . B[N, K]^T (+ bias[N]) (ReLU): row-major fp32 device matrices, TF32 tcgen05.mma with FP32
+ * accumulation.  Replaces the three cuBLAS GEMMs per torch::nn::Linear that autograd runs for PPOLearner::Learn
+ * (P/private/RLGymPPO_CPP/PPO/PPOLearner.cpp:125-290): forward (A = X, B = W), input gradient (A = dY, B = W^T) and
+ * weight gradient (A = dY^T, B = X^T, split over K = rows with RLG_GEMM_ATOMIC).  K, lda, ldb multiples of 4 floats,
+ * A and B 16-byte aligned; bias may be NULL; split_k >= 1 (> 1 needs RLG_GEMM_ATOMIC: C must hold the sum's start). */
+#define RLG_GEMM_RELU 1         /* C = max(., 0) */
+#define RLG_GEMM_ACCUMULATE 2   /* C += (non-atomic read-modify-write) */
+#define RLG_GEMM_ATOMIC 4       /* C += with atomic adds (split-K) */
+#define RLG_GEMM_SCALAR_STORE 8 /* internal: unaligned C */
+int rlg_gemm_tf32(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, const float* bias,
+                  int flags, int split_k, void* stream);
+
 #define RLG_MAX_HIDDEN_LAYERS 4
 typedef struct rlg_collector_cfg {
     int32_t num_hidden;                          /* layerSizes.size() (LearnerConfig.h policyLayerSizes / criticLayerSizes) */
