@@ -305,6 +305,11 @@ int rlg_engine_step_to(rlg_engine* e, const int32_t* action_idx, float* obs_out,
 #define RLG_GEMM_SCALAR_STORE 8 /* internal: unaligned C */
 int rlg_gemm_tf32(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, const float* bias,
                   int flags, int split_k, void* stream);
+/* The same with two fused epilogue extras (either may be NULL): mask [M, N] (ld ldm) zeroes C where mask <= 0 — the ReLU
+ * backward of the input-gradient GEMM, mask = the layer's forward output — and Ct [N, M] (ld ldct) receives the
+ * transposed result too, which is the K-major operand the weight-gradient GEMM of the neighbouring layer needs. */
+int rlg_gemm_tf32_fused(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, const float* bias,
+                        int flags, int split_k, const float* mask, int ldm, float* Ct, int ldct, void* stream);
 
 #define RLG_MAX_HIDDEN_LAYERS 4
 typedef struct rlg_collector_cfg {

@@ -15,9 +15,11 @@
 // core matrices), rounding to TF32; two stages, recycled through mbarriers that tcgen05.commit arrives on; one thread
 // issues tcgen05.mma kind::tf32 (4 x K=8 per block).  The epilogue reads the accumulator with tcgen05.ld (both
 // warpgroups, alternate 32-column chunks), applies bias / ReLU and stores or atomically adds (split-K) into C.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 
 #include "../../include/rlgym_b200.h"
@@ -37,6 +39,8 @@ struct GemmArgs {
     int32_t M, N, K, lda, ldb, ldc;
     int32_t flags;    // RLG_GEMM_*
     int32_t kbPerSplit;  // K blocks per blockIdx.z
+    const float* mask; int32_t ldm;  // optional [M, N]: C = mask > 0 ? C : 0 (ReLU backward with the layer's output)
+    float* Ct; int32_t ldct;         // optional [N, M]: the transposed result as well (the K-major operand of a later dW GEMM)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -97,27 +101,32 @@ __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// one (rows x 32) K block of a row-major matrix -> canonical K-major shared memory (rows beyond `rowsValid` and k beyond K: 0)
-__device__ __forceinline__ void stage_block(uint8_t* dst, const float* __restrict__ src, int ld, int row0, int rowsValid, int rowsTile, int k0, int K,
-                                            int t) {
-    const int total = rowsTile * (kGK / 4);  // float4 slots
-    for (int idx0 = t; idx0 < total; idx0 += kGThreads * 4) {
-        float4 v[4];
+// One (rows x 32) K block of a row-major matrix on its way to canonical K-major shared memory, in two halves so that the
+// global loads of the NEXT block are in flight while the tensor core works on the current one: slot idx = t + u * 256
+// covers (row = idx[2:0] | idx[..:6] << 3, float4 column = idx[5:3]): the 8 lanes of a 128-bit shared-memory store phase
+// hold 8 consecutive rows of one 16-byte column = one contiguous 128-byte core matrix (conflict free; the row-major
+// mapping made every phase an 8-way bank conflict); rows beyond `rowsValid` and k beyond K read as 0.
+template <int U>
+__device__ __forceinline__ void block_load(float4 (&v)[U], const float* __restrict__ src, int ld, int row0, int rowsValid, int rowsTile, int k0, int K, int t) {
+    const int total = rowsTile * (kGK / 4);
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int idx = idx0 + u * kGThreads;
-            const int r = idx >> 3, k = k0 + (idx & 7) * 4;
-            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (idx < total && row0 + r < rowsValid && k < K) v[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)(row0 + r) * ld + k));
-        }
+    for (int u = 0; u < U; u++) {
+        const int idx = t + u * kGThreads;
+        const int r = (idx & 7) | ((idx >> 6) << 3), k = k0 + ((idx >> 3) & 7) * 4;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < total && row0 + r < rowsValid && k < K) v[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)(row0 + r) * ld + k));
+    }
+}
+template <int U>
+__device__ __forceinline__ void block_store(uint8_t* dst, const float4 (&v)[U], int rowsTile, int t) {
+    const int total = rowsTile * (kGK / 4);
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int idx = idx0 + u * kGThreads;
-            if (idx < total) {
-                const uint32_t r = (uint32_t)(idx >> 3), c4 = (uint32_t)(idx & 7);
-                float4 o = make_float4(to_tf32(v[u].x), to_tf32(v[u].y), to_tf32(v[u].z), to_tf32(v[u].w));
-                *reinterpret_cast<float4*>(dst + (r >> 3) * 1024u + c4 * 128u + (r & 7u) * 16u) = o;
-            }
+    for (int u = 0; u < U; u++) {
+        const int idx = t + u * kGThreads;
+        if (idx < total) {
+            const uint32_t r = (uint32_t)((idx & 7) | ((idx >> 6) << 3)), c4 = (uint32_t)((idx >> 3) & 7);
+            float4 o = make_float4(to_tf32(v[u].x), to_tf32(v[u].y), to_tf32(v[u].z), to_tf32(v[u].w));
+            *reinterpret_cast<float4*>(dst + (r >> 3) * 1024u + c4 * 128u + (r & 7u) * 16u) = o;
         }
     }
 }
@@ -153,16 +162,25 @@ __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tf32(const GemmArgs g) {
     const uint32_t tmemBase = *tmemSlot;
     const uint32_t idesc = make_idesc(kGM, NT);
 
+    constexpr int kUA = kGM * (kGK / 4) / kGThreads;   // 4 float4 per thread for the A block
+    constexpr int kUB = 256 * (kGK / 4) / kGThreads;   // 8 for a full-width B block
+    float4 ra[kUA], rb[kUB];
+    block_load<kUA>(ra, g.A, g.lda, m0, g.M, kGM, kbBegin * kGK, g.K, t);
+    block_load<kUB>(rb, g.B, g.ldb, n0, g.N, NT, kbBegin * kGK, g.K, t);
     for (int it = 0; it < nIt; it++) {
         const int s = it & 1;
         uint8_t* sA = smem + s * (kGABytes + kGBBytes);
         uint8_t* sB = sA + kGABytes;
         if (it >= kGStages) mbar_wait(barBase + 8 * s, ((it >> 1) - 1) & 1);  // the MMAs that read this stage two iterations ago are done
-        const int k0 = (kbBegin + it) * kGK;
-        stage_block(sA, g.A, g.lda, m0, g.M, kGM, k0, g.K, t);
-        stage_block(sB, g.B, g.ldb, n0, g.N, NT, k0, g.K, t);
+        block_store<kUA>(sA, ra, kGM, t);
+        block_store<kUB>(sB, rb, NT, t);
         fence_proxy_async();
         __syncthreads();
+        if (it + 1 < nIt) {  // next block's loads fly while this block's MMAs run
+            const int k0 = (kbBegin + it + 1) * kGK;
+            block_load<kUA>(ra, g.A, g.lda, m0, g.M, kGM, k0, g.K, t);
+            block_load<kUB>(rb, g.B, g.ldb, n0, g.N, NT, k0, g.K, t);
+        }
         if (t == 0) {
             tc_fence_after();
             const uint32_t aBase = smem_u32(sA), bBase = smem_u32(sB);
@@ -198,6 +216,11 @@ __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tf32(const GemmArgs g) {
                     o[i] = __uint_as_float(v[4 * q + i]);
                     if (addBias && n + i < nValid) o[i] += __ldg(g.bias + n0 + n + i);
                     if (g.flags & RLG_GEMM_RELU) o[i] = fmaxf(o[i], 0.f);
+                    if (g.mask && n + i < nValid && !(__ldg(g.mask + (size_t)row * g.ldm + n0 + n + i) > 0.f)) o[i] = 0.f;
+                }
+                if (g.Ct) {  // lanes = consecutive rows: one 128-byte line per column
+#pragma unroll
+                    for (int i = 0; i < 4; i++) if (n + i < nValid) g.Ct[(size_t)(n0 + n + i) * g.ldct + row] = o[i];
                 }
                 if (g.flags & RLG_GEMM_ATOMIC) {
 #pragma unroll
@@ -216,20 +239,177 @@ __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tf32(const GemmArgs g) {
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"(tmemCols) : "memory");
 }
 
+
+// ---- the same GEMM fed by the TMA ---------------------------------------------------------------------------------------
+// Operand blocks (128 x 32 of A, NT x 32 of B) arrive as cp.async.bulk.tensor boxes in the 128-byte swizzled K-major layout
+// (one 128-byte row per matrix row, 16-byte chunks XOR-ed with row % 8 — conflict free for the tensor core, nothing passes
+// through registers), S stages recycled through full / empty mbarriers: one producer thread, one MMA-issuing thread, both
+// warpgroups in the epilogue.  The tensor core reads the fp32 bits as TF32 (low mantissa bits ignored).
+struct GemmTmaArgs {
+    GemmArgs g;
+    int32_t stages, stageBytes;
+};
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(map),
+                 "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B: SBO = 1024 B (8 rows x 128 B), LBO unused, version 1
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(kGThreads, 1) k_gemm_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                                                           const GemmTmaArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const GemmArgs& g = a.g;
+    const int S = a.stages;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * a.stageBytes);  // full[S], empty[S], done
+    uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(smem + S * a.stageBytes + 8 * (2 * 4 + 1));
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int m0 = blockIdx.x * kGM;
+    const int n0 = blockIdx.y * 256;
+    const int nValid = g.N - n0 < 256 ? g.N - n0 : 256;
+    const int NT = (nValid + 15) & ~15;
+    const uint32_t tmemCols = NT <= 32 ? 32u : (NT <= 64 ? 64u : (NT <= 128 ? 128u : 256u));
+    const int nkbAll = (g.K + kGK - 1) / kGK;
+    const int kbBegin = blockIdx.z * g.kbPerSplit;
+    const int kbEnd = kbBegin + g.kbPerSplit < nkbAll ? kbBegin + g.kbPerSplit : nkbAll;
+    const int nIt = kbEnd - kbBegin;
+    if (nIt <= 0) return;
+    const uint32_t barFull = smem_u32(&bars[0]), barEmpty = smem_u32(&bars[4]), barDone = smem_u32(&bars[8]);
+
+    if (t == 0) {
+        for (int i = 0; i < S; i++) { mbar_init(barFull + 8 * i, 1); mbar_init(barEmpty + 8 * i, 1); }
+        mbar_init(barDone, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmemSlot)), "r"(tmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmemBase = *tmemSlot;
+
+    if (warp == 0 && lane == 0) {  // producer
+        const uint32_t bytes = (uint32_t)(kGABytes + NT * kGK * 4);
+        const int boxRowsB = a.stageBytes / (kGK * 4) - kGM;  // rows of the B box (the map's box is fixed: >= NT)
+        const uint32_t bytesBox = (uint32_t)(kGABytes + boxRowsB * kGK * 4);
+        (void)bytes;
+        for (int it = 0; it < nIt; it++) {
+            const int s = it % S, k = it / S;
+            if (k >= 1) mbar_wait(barEmpty + 8 * s, (k - 1) & 1);
+            mbar_expect_tx(barFull + 8 * s, bytesBox);
+            const uint32_t dst = smem_u32(smem + s * a.stageBytes);
+            const int k0 = (kbBegin + it) * kGK;
+            tma_load_2d(dst, &mapA, k0, m0, barFull + 8 * s);
+            tma_load_2d(dst + kGABytes, &mapB, k0, n0, barFull + 8 * s);
+        }
+    } else if (warp == 1 && lane == 0) {  // MMA issuer
+        const uint32_t idesc = make_idesc(kGM, NT);
+        for (int it = 0; it < nIt; it++) {
+            const int s = it % S, k = it / S;
+            mbar_wait(barFull + 8 * s, k & 1);
+            tc_fence_after();
+            const uint32_t aBase = smem_u32(smem + s * a.stageBytes), bBase = aBase + kGABytes;
+#pragma unroll
+            for (int j = 0; j < kGK / 8; j++)
+                tc_mma_tf32(tmemBase, make_desc_sw128(aBase + j * 32), make_desc_sw128(bBase + j * 32), idesc, (it > 0 || j > 0) ? 1u : 0u);
+            tc_commit(barEmpty + 8 * s);
+        }
+        tc_commit(barDone);
+    }
+    __syncwarp();
+    mbar_wait(barDone, 0);
+    tc_fence_after();
+
+    // epilogue (as k_gemm_tf32)
+    const int r = t & (kGM - 1), half = t >> 7;
+    const uint32_t tmemLane = tmemBase + ((uint32_t)((warp & 3) * 32) << 16);
+    const int row = m0 + r;
+    const bool addBias = g.bias != nullptr && blockIdx.z == 0;
+    for (int c = half; c * 32 < NT; c += 2) {
+        uint32_t v[32];
+        tc_ld32(tmemLane + c * 32, v);
+        tc_wait_ld();
+        if (row < g.M) {
+            float* dst = g.C + (size_t)row * g.ldc + n0 + c * 32;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int n = c * 32 + 4 * q;
+                if (n >= nValid) break;
+                float o[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    o[i] = __uint_as_float(v[4 * q + i]);
+                    if (addBias && n + i < nValid) o[i] += __ldg(g.bias + n0 + n + i);
+                    if (g.flags & RLG_GEMM_RELU) o[i] = fmaxf(o[i], 0.f);
+                    if (g.mask && n + i < nValid && !(__ldg(g.mask + (size_t)row * g.ldm + n0 + n + i) > 0.f)) o[i] = 0.f;
+                }
+                if (g.Ct) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) if (n + i < nValid) g.Ct[(size_t)(n0 + n + i) * g.ldct + row] = o[i];
+                }
+                if (g.flags & RLG_GEMM_ATOMIC) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) if (n + i < nValid) atomicAdd(dst + 4 * q + i, o[i]);
+                } else if (n + 3 < nValid && (g.flags & (RLG_GEMM_ACCUMULATE | RLG_GEMM_SCALAR_STORE)) == 0) {
+                    *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) if (n + i < nValid) dst[4 * q + i] = ((g.flags & RLG_GEMM_ACCUMULATE) ? dst[4 * q + i] : 0.f) + o[i];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"(tmemCols) : "memory");
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+bool g_encode_tried = false;
+
+// row-major [rows, K] fp32 matrix, boxes of 32 K-elements (128 B) x boxRows rows, 128-byte swizzle, zero fill out of bounds
+bool make_map(CUtensorMap* map, const float* base, int rows, int K, int ld, int boxRows) {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)kGK, (cuuint32_t)boxRows};
+    cuuint32_t estr[2] = {1, 1};
+    return g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+bool g_attr_tma[64] = {};
+
 int failg(int code, const std::string& m) { rlg_internal_set_error(m.c_str()); return code; }
 bool g_attr_set[64] = {};
 
 }  // namespace
 
+extern "C" int rlg_gemm_tf32_fused(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, const float* bias,
+                                   int flags, int split_k, const float* mask, int ldm, float* Ct, int ldct, void* stream);
 extern "C" int rlg_gemm_tf32(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, const float* bias, int flags,
                              int split_k, void* stream) {
+    return rlg_gemm_tf32_fused(M, N, K, A, lda, B, ldb, C, ldc, bias, flags, split_k, nullptr, 0, nullptr, 0, stream);
+}
+extern "C" int rlg_gemm_tf32_fused(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, const float* bias,
+                                   int flags, int split_k, const float* mask, int ldm, float* Ct, int ldct, void* stream) {
     if (M <= 0 || N <= 0 || K <= 0 || !A || !B || !C) return failg(RLG_ERR_INVALID, "rlg_gemm_tf32: bad argument");
     if ((K & 3) || (lda & 3) || (ldb & 3) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15))
         return failg(RLG_ERR_INVALID, "rlg_gemm_tf32: K, lda and ldb must be multiples of 4 floats and A, B 16-byte aligned");
     if (((ldc & 3) || ((uintptr_t)C & 15)) && !(flags & RLG_GEMM_ATOMIC)) flags |= RLG_GEMM_SCALAR_STORE;
     if (split_k < 1) split_k = 1;
     if (split_k > 1 && !(flags & RLG_GEMM_ATOMIC)) return failg(RLG_ERR_INVALID, "rlg_gemm_tf32: split_k > 1 needs RLG_GEMM_ATOMIC (C accumulates)");
-    if ((flags & RLG_GEMM_ATOMIC) && (flags & RLG_GEMM_RELU)) return failg(RLG_ERR_INVALID, "rlg_gemm_tf32: ReLU cannot follow a partial sum");
+    if ((flags & RLG_GEMM_ATOMIC) && ((flags & RLG_GEMM_RELU) || mask || Ct))
+        return failg(RLG_ERR_INVALID, "rlg_gemm_tf32: ReLU / mask / transposed output cannot follow a partial sum");
+    if ((mask && ldm < N) || (Ct && ldct < M)) return failg(RLG_ERR_INVALID, "rlg_gemm_tf32: bad mask / transposed-output leading dimension");
     int dev = 0;
     cudaError_t err = cudaGetDevice(&dev);
     if (err != cudaSuccess) return failg(RLG_ERR_CUDA, std::string("rlg_gemm_tf32: ") + cudaGetErrorString(err));
@@ -240,12 +420,40 @@ extern "C" int rlg_gemm_tf32(int M, int N, int K, const float* A, int lda, const
     }
     GemmArgs g;
     g.A = A; g.B = B; g.C = C; g.bias = bias; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldc = ldc; g.flags = flags;
+    g.mask = mask; g.ldm = ldm; g.Ct = Ct; g.ldct = ldct;
     const int nkb = (K + kGK - 1) / kGK;
     if (split_k > nkb) split_k = nkb;
     g.kbPerSplit = (nkb + split_k - 1) / split_k;
     split_k = (nkb + g.kbPerSplit - 1) / g.kbPerSplit;
     dim3 grid((M + kGM - 1) / kGM, (N + 255) / 256, split_k);
-    k_gemm_tf32<<<grid, kGThreads, kGSmem, (cudaStream_t)stream>>>(g);
+    if (!g_encode_tried) {
+        g_encode_tried = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            g_encode = (EncodeTiledFn)fn;
+        if (const char* ev = getenv("RLG_GEMM_NO_TMA")) { if (atoi(ev)) g_encode = nullptr; }  // A/B switch: the register-staged kernel
+    }
+    if (g_encode) {
+        const int boxRowsB = N >= 256 ? 256 : ((N + 15) & ~15);
+        GemmTmaArgs ta;
+        ta.g = g;
+        ta.stageBytes = kGABytes + boxRowsB * kGK * 4;
+        ta.stages = (100 * 1024) / ta.stageBytes;  // two CTAs per SM
+        if (ta.stages > 4) ta.stages = 4;
+        if (ta.stages < 2) ta.stages = 2;
+        const int smemBytes = ta.stages * ta.stageBytes + 128;
+        CUtensorMap mapA, mapB;
+        if (!make_map(&mapA, A, M, K, lda, kGM) || !make_map(&mapB, B, N, K, ldb, boxRowsB)) return failg(RLG_ERR_CUDA, "rlg_gemm_tf32: cuTensorMapEncodeTiled failed");
+        if (dev >= 0 && dev < 64 && !g_attr_tma[dev]) {
+            err = cudaFuncSetAttribute(k_gemm_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (kGABytes + kGBBytes) + 128);
+            if (err != cudaSuccess) return failg(RLG_ERR_CUDA, std::string("rlg_gemm_tf32: ") + cudaGetErrorString(err));
+            g_attr_tma[dev] = true;
+        }
+        k_gemm_tma<<<grid, kGThreads, smemBytes, (cudaStream_t)stream>>>(mapA, mapB, ta);
+    } else {
+        k_gemm_tf32<<<grid, kGThreads, kGSmem, (cudaStream_t)stream>>>(g);
+    }
     err = cudaGetLastError();
     if (err != cudaSuccess) return failg(RLG_ERR_CUDA, std::string("rlg_gemm_tf32 launch: ") + cudaGetErrorString(err));
     return RLG_OK;

@@ -25,7 +25,7 @@ EXPORTS = [
     "rlg_engine_outputs", "rlg_engine_obs_size", "rlg_engine_num_players", "rlg_engine_num_arenas",
     "rlg_engine_state_bytes_per_arena", "rlg_engine_player_order", "rlg_engine_set_player_order", "rlg_action_table",
     "rlg_engine_step_host", "rlg_engine_host_buffers", "rlg_engine_step_pinned", "rlg_engine_read_outputs", "rlg_engine_launch_count", "rlg_engine_stream", "rlg_engine_sync",
-    "rlg_engine_metrics", "rlg_engine_reset_metrics", "rlg_engine_score_lines", "rlg_gemm_tf32",
+    "rlg_engine_metrics", "rlg_engine_reset_metrics", "rlg_engine_score_lines", "rlg_gemm_tf32", "rlg_gemm_tf32_fused",
     # collector / plumbing (bound in rlgymppo_cpp_b200.collector)
     "rlg_engine_step_to", "rlg_engine_device", "rlg_engine_arena_id_base", "rlg_engine_copy_to_host", "rlg_engine_copy_to_device",
     "rlg_collector_create", "rlg_collector_destroy", "rlg_collector_set_layer", "rlg_collector_infer", "rlg_collector_collect",

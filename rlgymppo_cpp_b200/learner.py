@@ -8,9 +8,10 @@ Reference (paths under /root/reference/RLGymPPO_CPP/src/):
   public/RLGymPPO_CPP/Util/WelfordRunningStat.h:36-83.
 
 Collection (simulation, policy/critic inference, sampling, trajectory ring, GAE, buffer rows) runs in the hand-written
-CUDA engine (csrc/*.cu).  The minibatch UPDATE here is plain library work, exactly like the reference: torch autograd
-over cuBLAS GEMMs (TF32 tensor-core math enabled), Adam, clip-by-global-norm 0.5 — plus what the reference does not
-have: data-parallel replicas, one all-reduce of the flattened gradients per optimiser step (NCCL on GPUs, gloo in the
+CUDA engine (csrc/*.cu).  In the minibatch UPDATE the dense contractions (forward, input-gradient and weight-gradient
+GEMM of every Linear layer) run on the hand-written tcgen05 TF32 kernel of csrc/gemm.cu through gemm.MLPTF32; torch
+autograd strings them together and does the element-wise parts (softmax / losses / Adam / clip-by-global-norm 0.5) —
+plus what the reference does not have: data-parallel replicas, one all-reduce of the flattened gradients per optimiser step (NCCL on GPUs, gloo in the
 CPU tests).  PyTorch is plumbing here (memory, autograd, torch.distributed), not the product path.
 """
 from __future__ import annotations
@@ -187,7 +188,19 @@ class PPOLearner:
         self.value_net = make_mlp(obs_size, cfg.criticLayerSizes, 1).to(self.device)
         self.policy_opt = torch.optim.Adam(self.policy.parameters(), lr=cfg.policyLR)
         self.value_opt = torch.optim.Adam(self.value_net.parameters(), lr=cfg.criticLR)
+        # on the GPU the networks are evaluated (forward AND backward) through the hand-written tcgen05 GEMM (csrc/gemm.cu)
+        # via gemm.MLPTF32, which shares these modules' parameters; the CPU path (plain torch) exists for the gloo tests of
+        # the host logic only
+        if self.device.type == "cuda":
+            from . import gemm
+
+            self.policy_fwd, self.value_fwd = gemm.MLPTF32(self.policy), gemm.MLPTF32(self.value_net)
+        else:
+            self.policy_fwd, self.value_fwd = self.policy, self.value_net
         self.pg = process_group
+        self.use_cuda_graph = True
+        self._graph = None
+        self._graph_rows = 0
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.cumulative_model_updates = 0
         if self.world > 1:  # replicas start identical (rank 0's init)
@@ -196,7 +209,7 @@ class PPOLearner:
 
     def action_log_probs_entropy(self, obs, acts):
         """DiscretePolicy::GetBackpropData (DiscretePolicy.cpp:64-75)."""
-        probs = torch.softmax(self.policy(obs) / self.cfg.policyTemperature, dim=-1).clamp(ACTION_MIN_PROB, 1)
+        probs = torch.softmax(self.policy_fwd(obs) / self.cfg.policyTemperature, dim=-1).clamp(ACTION_MIN_PROB, 1)
         logp = torch.log(probs)
         return logp.gather(-1, acts.view(-1, 1).long()).view(-1), -(logp * probs).sum(-1).mean()
 
@@ -211,6 +224,65 @@ class PPOLearner:
         for g in grads:
             g.copy_(flat[off:off + g.numel()].view_as(g))
             off += g.numel()
+
+    def _minibatch(self, obs, acts, adv, old, tgt, acc):
+        """Forward + backward of one minibatch for both networks (PPOLearner.cpp:125-271); gradients accumulate in .grad,
+        diagnostics in acc (entropy, kl, ratio, value loss, clip fraction)."""
+        cfg = self.cfg
+        ratio_b = cfg.miniBatchSize / float(cfg.batchSize)
+        vals = self.value_fwd(obs).reshape(-1)
+        if cfg.policyLR != 0:
+            logp, entropy = self.action_log_probs_entropy(obs, acts)
+            ratio = torch.exp(logp - old)
+            clipped = ratio.clamp(1 - cfg.clipRange, 1 + cfg.clipRange)
+            policy_loss = -torch.min(ratio * adv, clipped * adv).mean()
+            ppo_loss = (policy_loss - entropy * cfg.entCoef) * ratio_b
+            with torch.no_grad():  # SB3-style diagnostics (PPOLearner.cpp:181-196)
+                log_ratio = logp - old
+                acc[1] += ((torch.exp(log_ratio) - 1) - log_ratio).mean()
+                acc[4] += ((ratio - 1).abs() > cfg.clipRange).float().mean()
+                acc[2] += ratio.mean()
+                acc[0] += entropy.detach()
+            ppo_loss.backward()
+        if cfg.criticLR != 0:
+            value_loss = torch.nn.functional.mse_loss(vals, tgt) * ratio_b
+            value_loss.backward()
+            acc[3] += value_loss.detach()
+
+    def _graph_minibatch(self, mb, acc):
+        """The minibatch step as ONE CUDA-graph replay (~100 small launches: the GEMMs of csrc/gemm.cu plus the element-wise
+        kernels): captured once per minibatch shape, inputs and the diagnostics vector are static buffers."""
+        n = mb["states"].shape[0]
+        if self._graph is None or self._graph_rows != n:
+            st = {k: torch.empty_like(mb[k]) for k in ExperienceBuffer.KEYS}
+            st_acc = torch.zeros(5, dtype=torch.float32, device=self.device)
+            for k in st:
+                st[k].copy_(mb[k])
+            params = list(self.policy.parameters()) + list(self.value_net.parameters())
+            saved = [None if p.grad is None else p.grad.clone() for p in params]
+            for p in params:  # capture with defined grads: backward then ACCUMULATES in place
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):  # warm-up outside the capture (lazy initialisations, cudaFuncSetAttribute)
+                    self._minibatch(st["states"], st["actions"], st["advantages"], st["log_probs"], st["values"], st_acc)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._minibatch(st["states"], st["actions"], st["advantages"], st["log_probs"], st["values"], st_acc)
+            for p, g in zip(params, saved):  # the warm-up / capture must not leave a trace in the gradients
+                if g is None:
+                    p.grad.zero_()
+                else:
+                    p.grad.copy_(g)
+            self._graph, self._graph_rows, self._graph_in, self._graph_acc = graph, n, st, st_acc
+        for k in ExperienceBuffer.KEYS:
+            self._graph_in[k].copy_(mb[k])
+        self._graph_acc.zero_()
+        self._graph.replay()
+        acc += self._graph_acc
 
     def learn(self, exp: ExperienceBuffer, report: dict):
         cfg = self.cfg
@@ -228,31 +300,12 @@ class PPOLearner:
                 self.value_opt.zero_grad(set_to_none=False)
                 for start in range(0, cfg.batchSize, cfg.miniBatchSize):
                     stop = start + cfg.miniBatchSize
-                    ratio_b = (stop - start) / float(cfg.batchSize)
-                    obs = batch["states"][start:stop]
-                    acts = batch["actions"][start:stop]
-                    adv = batch["advantages"][start:stop]
-                    old = batch["log_probs"][start:stop]
-                    tgt = batch["values"][start:stop]
-                    vals = self.value_net(obs).view(-1)
-                    if train_policy:
-                        logp, entropy = self.action_log_probs_entropy(obs, acts)
-                        ratio = torch.exp(logp - old)
-                        clipped = ratio.clamp(1 - cfg.clipRange, 1 + cfg.clipRange)
-                        policy_loss = -torch.min(ratio * adv, clipped * adv).mean()
-                        ppo_loss = (policy_loss - entropy * cfg.entCoef) * ratio_b
-                        with torch.no_grad():  # SB3-style diagnostics (PPOLearner.cpp:181-196)
-                            log_ratio = logp - old
-                            acc[1] += ((torch.exp(log_ratio) - 1) - log_ratio).mean()
-                            acc[4] += ((ratio - 1).abs() > cfg.clipRange).float().mean()
-                            acc[2] += ratio.mean()
-                            acc[0] += entropy.detach()
-                            n_clip += 1
-                        ppo_loss.backward()
-                    if train_critic:
-                        value_loss = torch.nn.functional.mse_loss(vals, tgt) * ratio_b
-                        value_loss.backward()
-                        acc[3] += value_loss.detach()
+                    mb = {k: batch[k][start:stop] for k in ExperienceBuffer.KEYS}
+                    if self.device.type == "cuda" and self.use_cuda_graph:
+                        self._graph_minibatch(mb, acc)
+                    else:
+                        self._minibatch(mb["states"], mb["actions"], mb["advantages"], mb["log_probs"], mb["values"], acc)
+                    n_clip += 1 if train_policy else 0
                     n_mb += 1
                 if train_policy:
                     self._allreduce_grads(self.policy)

@@ -39,16 +39,41 @@ def test_gemm_matches_fp32(M, N, K, kw):
     res = G.gemm(a, b, out=out, bias=bias, relu=kw.get("relu", False), accumulate=kw.get("accumulate", False), atomic=split > 1, split_k=split)
     torch.cuda.synchronize()
     torch.backends.cuda.matmul.allow_tf32 = False
-    exact = _tf32(a).double() @ _tf32(b).double().t()    # what the tensor core multiplies: TF32-rounded inputs, wide accumulation
+    # what the tensor core multiplies: fp32 bits read as TF32 (low 13 mantissa bits dropped: the TMA-fed kernel) or operands
+    # rounded to nearest TF32 on the way to shared memory (the register-staged kernel), wide accumulation
+    trunc = lambda x: (x.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+    exact_rn = _tf32(a).double() @ _tf32(b).double().t()
+    exact_tr = trunc(a).double() @ trunc(b).double().t()
     full = a.double() @ b.double().t()
-    for ref, tol in ((exact, 2e-5), (full, 3e-3)):
+
+    def err(ref):
         r = ref + (bias.double() if bias is not None else 0)
         if kw.get("relu"):
             r = r.clamp_min(0)
         if base is not None:
             r = r + base.double()
-        scale = float(ref.abs().max())
-        assert float((res.double() - r).abs().max()) <= tol * scale, (M, N, K, tol)
+        return float((res.double() - r).abs().max()) / float(ref.abs().max())
+
+    assert min(err(exact_rn), err(exact_tr)) <= 2e-5, (M, N, K, err(exact_rn), err(exact_tr))
+    assert err(full) <= 4e-3, (M, N, K, err(full))
+
+
+def test_gemm_fused_mask_and_transposed_output():
+    import torch
+
+    from rlgymppo_cpp_b200 import gemm as G
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randn(1000, 92, device="cuda", generator=g); b = torch.randn(256, 92, device="cuda", generator=g)
+    mask = torch.randn(1000, 256, device="cuda", generator=g).clamp_min(0)
+    out_t = torch.full((256, 1000), float("nan"), device="cuda")
+    res = G.gemm(a, b, mask=mask, out_t=out_t)
+    ref = G.gemm(a, b) * (mask > 0)
+    assert torch.equal(res, ref) and torch.equal(out_t, res.t())
+    # ReLU + transposed output (the forward of a hidden layer)
+    out_t = torch.empty((256, 1000), device="cuda")
+    res = G.gemm(a, b, relu=True, out_t=out_t)
+    assert torch.equal(res, G.gemm(a, b).clamp_min(0)) and torch.equal(out_t, res.t())
 
 
 def test_gemm_argument_errors():
@@ -90,8 +115,9 @@ def test_mlp_autograd_matches_torch():
         ytf, gtf = grads(seq, True)
         ymine, gmine = grads(G.MLPTF32(seq), False)
         torch.backends.cuda.matmul.allow_tf32 = False
-        assert float((ymine - y32).abs().max()) <= 3 * float((ytf - y32).abs().max()) + 1e-6
+        # (the TMA-fed kernel reads fp32 bits as TF32, i.e. truncates where cuBLAS rounds: up to ~2x its error per operand)
+        assert float((ymine - y32).abs().max()) <= 8 * float((ytf - y32).abs().max()) + 1e-6
         for p, a, b, c in zip(seq.parameters(), g32, gtf, gmine):
             assert c.shape == a.shape
             e_mine, e_torch = float((c - a).abs().max()), float((b - a).abs().max())
-            assert e_mine <= 4 * e_torch + 1e-3 * float(a.abs().max()), (tuple(p.shape), e_mine, e_torch, float(a.abs().max()))
+            assert e_mine <= 8 * e_torch + 2e-3 * float(a.abs().max()), (tuple(p.shape), e_mine, e_torch, float(a.abs().max()))
