@@ -358,7 +358,7 @@ def ppo_iteration_time(args, rank, local_rank, world, iters=6):
     return {"total_iteration_time_s": med("Total Iteration Time"), "collection_time_s": med("Collection Time"),
             "consumption_time_s": med("Consumption Time"), "ppo_learn_time_s": med("PPO Learn Time"),
             "timesteps_per_iteration": int(tail[-1]["Timesteps Collected"]), "overall_steps_per_s": med("Overall Steps/Second"),
-            "config": f"batch {rows} rows/rank, 4 minibatches, 1 epoch, Adam lr 2e-4, policy/critic 256x256x256, torch autograd (TF32) update, "
+            "config": f"batch {rows} rows/rank, 4 minibatches, 1 epoch, Adam lr 2e-4, policy/critic 256x256x256, the update's GEMMs on the hand-written tcgen05/TMA TF32 kernel (csrc/gemm.cu), minibatch step as a CUDA graph, "
                       f"{world} data-parallel rank(s)", "iterations_timed": len(tail)}
 
 

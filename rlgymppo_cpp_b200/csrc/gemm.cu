@@ -223,8 +223,12 @@ __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tf32(const GemmArgs g) {
                     for (int i = 0; i < 4; i++) if (n + i < nValid) g.Ct[(size_t)(n0 + n + i) * g.ldct + row] = o[i];
                 }
                 if (g.flags & RLG_GEMM_ATOMIC) {
+                    if (n + 3 < nValid && (g.flags & RLG_GEMM_SCALAR_STORE) == 0) {
+                        atomicAdd(reinterpret_cast<float4*>(dst + 4 * q), make_float4(o[0], o[1], o[2], o[3]));  // one 16-byte reduction
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < 4; i++) if (n + i < nValid) atomicAdd(dst + 4 * q + i, o[i]);
+                        for (int i = 0; i < 4; i++) if (n + i < nValid) atomicAdd(dst + 4 * q + i, o[i]);
+                    }
                 } else if (n + 3 < nValid && (g.flags & (RLG_GEMM_ACCUMULATE | RLG_GEMM_SCALAR_STORE)) == 0) {
                     *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
                 } else {
@@ -356,8 +360,12 @@ __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tma(const __grid_constant
                     for (int i = 0; i < 4; i++) if (n + i < nValid) g.Ct[(size_t)(n0 + n + i) * g.ldct + row] = o[i];
                 }
                 if (g.flags & RLG_GEMM_ATOMIC) {
+                    if (n + 3 < nValid && (g.flags & RLG_GEMM_SCALAR_STORE) == 0) {
+                        atomicAdd(reinterpret_cast<float4*>(dst + 4 * q), make_float4(o[0], o[1], o[2], o[3]));  // one 16-byte reduction
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < 4; i++) if (n + i < nValid) atomicAdd(dst + 4 * q + i, o[i]);
+                        for (int i = 0; i < 4; i++) if (n + i < nValid) atomicAdd(dst + 4 * q + i, o[i]);
+                    }
                 } else if (n + 3 < nValid && (g.flags & (RLG_GEMM_ACCUMULATE | RLG_GEMM_SCALAR_STORE)) == 0) {
                     *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
                 } else {
@@ -404,7 +412,7 @@ extern "C" int rlg_gemm_tf32_fused(int M, int N, int K, const float* A, int lda,
     if (M <= 0 || N <= 0 || K <= 0 || !A || !B || !C) return failg(RLG_ERR_INVALID, "rlg_gemm_tf32: bad argument");
     if ((K & 3) || (lda & 3) || (ldb & 3) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15))
         return failg(RLG_ERR_INVALID, "rlg_gemm_tf32: K, lda and ldb must be multiples of 4 floats and A, B 16-byte aligned");
-    if (((ldc & 3) || ((uintptr_t)C & 15)) && !(flags & RLG_GEMM_ATOMIC)) flags |= RLG_GEMM_SCALAR_STORE;
+    if ((ldc & 3) || ((uintptr_t)C & 15)) flags |= RLG_GEMM_SCALAR_STORE;
     if (split_k < 1) split_k = 1;
     if (split_k > 1 && !(flags & RLG_GEMM_ATOMIC)) return failg(RLG_ERR_INVALID, "rlg_gemm_tf32: split_k > 1 needs RLG_GEMM_ATOMIC (C accumulates)");
     if ((flags & RLG_GEMM_ATOMIC) && ((flags & RLG_GEMM_RELU) || mask || Ct))
@@ -439,7 +447,10 @@ extern "C" int rlg_gemm_tf32_fused(int M, int N, int K, const float* A, int lda,
         GemmTmaArgs ta;
         ta.g = g;
         ta.stageBytes = kGABytes + boxRowsB * kGK * 4;
-        ta.stages = (100 * 1024) / ta.stageBytes;  // two CTAs per SM
+        ta.stages = (100 * 1024) / ta.stageBytes;  // two CTAs per SM ...
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if ((long long)grid.x * grid.y * grid.z <= sms) ta.stages = 4;  // ... unless one wave of single CTAs (split-K): a deeper pipeline instead
         if (ta.stages > 4) ta.stages = 4;
         if (ta.stages < 2) ta.stages = 2;
         const int smemBytes = ta.stages * ta.stageBytes + 128;
