@@ -107,7 +107,9 @@ enum rlg_reward_kind {
     RLG_REW_VEL_PLAYER_TO_BALL = 1, /* VelocityPlayerToBallReward */
     RLG_REW_VEL_BALL_TO_GOAL = 2,   /* VelocityBallToGoalReward, param[0] = ownGoal */
     RLG_REW_FACE_BALL = 3,          /* FaceBallReward */
-    RLG_REW_VELOCITY = 4            /* VelocityReward, param[0] = isNegative */
+    RLG_REW_VELOCITY = 4,           /* VelocityReward, param[0] = isNegative */
+    RLG_REW_SAVE_BOOST = 5,         /* SaveBoostReward, param[0] = exponent (CommonRewards.h:61-70; powf: 1 ulp) */
+    RLG_REW_TOUCH_BALL = 6          /* TouchBallReward, param[0] = aerialWeight (CommonRewards.h:110-124; powf: 1 ulp) */
 };
 #define RLG_MAX_REWARD_TERMS 8
 

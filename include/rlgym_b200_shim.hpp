@@ -260,6 +260,16 @@ public:
     bool isNegative;
     explicit VelocityReward(bool isNegative_ = false) : isNegative(isNegative_) {}
 };
+class SaveBoostReward : public RewardFunction {  // CommonRewards.h:61-70
+public:
+    float exponent;
+    explicit SaveBoostReward(float exponent_ = 0.5f) : exponent(exponent_) {}
+};
+class TouchBallReward : public RewardFunction {  // CommonRewards.h:110-124
+public:
+    float aerialWeight;
+    explicit TouchBallReward(float aerialWeight_ = 0) : aerialWeight(aerialWeight_) {}
+};
 class VelocityPlayerToBallReward : public RewardFunction {};
 class FaceBallReward : public RewardFunction {};
 class VelocityBallToGoalReward : public RewardFunction {
@@ -385,6 +395,8 @@ inline rlg_engine_cfg CfgFromMatch(const Match& m, int tickSkip, int numArenas, 
         else if (auto* g = dynamic_cast<VelocityBallToGoalReward*>(f)) { t.kind = RLG_REW_VEL_BALL_TO_GOAL; t.params[0] = g->ownGoal ? 1.f : 0.f; }
         else if (dynamic_cast<FaceBallReward*>(f)) t.kind = RLG_REW_FACE_BALL;
         else if (auto* v = dynamic_cast<VelocityReward*>(f)) { t.kind = RLG_REW_VELOCITY; t.params[0] = v->isNegative ? 1.f : 0.f; }
+        else if (auto* sb = dynamic_cast<SaveBoostReward*>(f)) { t.kind = RLG_REW_SAVE_BOOST; t.params[0] = sb->exponent; }
+        else if (auto* tb = dynamic_cast<TouchBallReward*>(f)) { t.kind = RLG_REW_TOUCH_BALL; t.params[0] = tb->aerialWeight; }
         else throw std::runtime_error("RLGB200: user-defined RewardFunction needs the host-plugin path (not built yet)");
     }
     // terminals

@@ -87,6 +87,23 @@ def _vnorm(v):
     return np.zeros(3, dtype=np.float32)
 
 
+
+_LIBM = None
+
+
+def _powf(x, e):
+    """glibc powf — the function the reference's SaveBoostReward / TouchBallReward call (same libm as oracle/_ref here)."""
+    global _LIBM
+    if _LIBM is None:
+        import ctypes
+        import ctypes.util
+
+        _LIBM = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+        _LIBM.powf.restype = ctypes.c_float
+        _LIBM.powf.argtypes = [ctypes.c_float, ctypes.c_float]
+    return f32(_LIBM.powf(float(x), float(e)))
+
+
 def _vdot(a, b):
     return f32(f32(f32(a[0] * b[0]) + f32(a[1] * b[1])) + f32(a[2] * b[2])) + f32(0)
 
@@ -204,6 +221,12 @@ class GymOracle:
             return _vdot(c["rot_forward"].astype(np.float32), _vnorm(bpos - cpos))
         if kind == 4:  # VelocityReward (CommonRewards.h:52-58)
             return f32(f32(_vlen(cvel) / f32(2300)) * f32(1 - 2 * int(params[0] != 0)))
+        if kind == 5:  # SaveBoostReward (CommonRewards.h:61-70); boostFraction = boost / 100 (PlayerData.cpp:32)
+            return f32(min(max(_powf(f32(f32(c["boost"]) / f32(100)), f32(params[0])), f32(0)), f32(1)))
+        if kind == 6:  # TouchBallReward (CommonRewards.h:110-124)
+            if not self.touched[p]:
+                return f32(0)
+            return _powf(f32(f32(bpos[2] + f32(91.25)) / f32(f32(91.25) * f32(2))), f32(params[0]))
         raise ValueError(kind)
 
     def rewards(self, cars, ball):

@@ -158,6 +158,8 @@ static RewardFunction* make_term(const rlg_reward_term& t) {
     case RLG_REW_VEL_BALL_TO_GOAL: return new VelocityBallToGoalReward(t.params[0] != 0);
     case RLG_REW_FACE_BALL: return new FaceBallReward();
     case RLG_REW_VELOCITY: return new VelocityReward(t.params[0] != 0);
+    case RLG_REW_SAVE_BOOST: return new SaveBoostReward(t.params[0]);
+    case RLG_REW_TOUCH_BALL: return new TouchBallReward(t.params[0]);
     }
     return nullptr;
 }

@@ -17,7 +17,7 @@ RLG_MAX_REWARD_TERMS = 8
 
 RLG_OBS_DEFAULT, RLG_OBS_PADDED = 0, 1
 RLG_SETTER_KICKOFF, RLG_SETTER_RANDOM, RLG_SETTER_HOST = 0, 1, 2
-RLG_REW_EVENT, RLG_REW_VEL_PLAYER_TO_BALL, RLG_REW_VEL_BALL_TO_GOAL, RLG_REW_FACE_BALL, RLG_REW_VELOCITY = range(5)
+RLG_REW_EVENT, RLG_REW_VEL_PLAYER_TO_BALL, RLG_REW_VEL_BALL_TO_GOAL, RLG_REW_FACE_BALL, RLG_REW_VELOCITY, RLG_REW_SAVE_BOOST, RLG_REW_TOUCH_BALL = range(7)
 
 F3 = C.c_float * 3
 F4 = C.c_float * 4

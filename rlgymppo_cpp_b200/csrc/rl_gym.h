@@ -310,6 +310,17 @@ RL_HDI float reward_term(ArenaS& a, const SimCfg& cfg, const RewardTerm& t, int 
         float neg = t.params[0] != 0.f ? 1.f : 0.f;
         return s_mul(s_div(ref_len(car_vel_uu(c)), C::CAR_MAX_SPEED), (float)(1 - 2 * (int)neg));
     }
+    // the two powf rewards: glibc's powf evaluates in double and rounds once; so does this (within 1 ulp of it, tests say so)
+    case 5: {  // SaveBoostReward (CommonRewards.h:61-70): RS_CLAMP(powf(boostFraction, exponent), 0, 1), boostFraction = boost / 100
+        float frac = s_div(c.boost, 100.f);
+        float v = (float)pow((double)frac, (double)t.params[0]);
+        return fminf_(fmaxf_(v, 0.f), 1.f);
+    }
+    case 6: {  // TouchBallReward (CommonRewards.h:110-124)
+        if (!c.touchedStep) return 0.f;
+        float x = s_div(s_add(ballPos.z, C::BALL_RADIUS), s_mul(C::BALL_RADIUS, 2.f));
+        return (float)pow((double)x, (double)t.params[0]);
+    }
     }
     return 0.f;
 }

@@ -97,6 +97,33 @@ def gym_cfgs():
     c.obs_kind = abi.RLG_OBS_PADDED; c.obs_max_players = 3
     c.zero_sum = 1; c.team_spirit = 0.3; c.state_setter = abi.RLG_SETTER_KICKOFF
     yield "gym_2v2_padded_zerosum_kickoff", c
+    c = extra_rewards_cfg()
+    yield "gym_1v1_extra_rewards", c
+
+
+def extra_rewards_cfg():
+    """cfg-1 rewards + SaveBoostReward(0.5), SaveBoostReward(0.37), TouchBallReward(0.8), TouchBallReward(0) (the powf rewards:
+    compared within 1 ulp, see REWARD_ULPS)."""
+    c = abi.default_cfg(1, 1)
+    c.num_reward_terms = 8
+    for i, (kind, w, p0) in enumerate([(abi.RLG_REW_SAVE_BOOST, 0.3, 0.5), (abi.RLG_REW_SAVE_BOOST, 0.2, 0.37), (abi.RLG_REW_TOUCH_BALL, 2.0, 0.8),
+                                        (abi.RLG_REW_TOUCH_BALL, 1.0, 0.0)]):
+        c.reward_terms[4 + i].kind = kind; c.reward_terms[4 + i].weight = w; c.reward_terms[4 + i].params[0] = p0
+    c.reward_terms[3].params[4] = 0.5  # EventReward touch weight: touches show up in two places
+    return c
+
+
+# rewards are bit-exact, except configurations with a powf reward (SaveBoostReward / TouchBallReward): every such term may be 1 ulp
+# off glibc's powf, and the weighted sum carries it: |delta| <= REWARD_ULPS ulps of the largest term magnitude (~3)
+REWARD_ULPS = {"gym_1v1_extra_rewards": 8}
+
+
+def rewards_equal(name, ref, got):
+    ulps = REWARD_ULPS.get(name, 0)
+    if ulps == 0:
+        return np.array_equal(np.asarray(ref, np.float32).view(np.uint32), np.asarray(got, np.float32).view(np.uint32))
+    scale = np.maximum(np.abs(np.asarray(ref, np.float64)), 1.0)
+    return bool(np.all(np.abs(np.asarray(ref, np.float64) - np.asarray(got, np.float64)) <= ulps * scale * 2.0 ** -23))
 
 
 def obs_equal(cfg, ref, got):

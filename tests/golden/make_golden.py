@@ -262,7 +262,19 @@ def main():
     cfg.zero_sum = 1; cfg.team_spirit = 0.3
     cfg.state_setter = abi.RLG_SETTER_KICKOFF
     save("gym_2v2_padded_zerosum_kickoff", gym_sequence(cfg, 5, 40, 24))
+    extra()
+
+
+def extra():
+    """Fixtures added after the first set (kept separate so that the earlier files are not rewritten):
+    python tests/golden/make_golden.py extra"""
+    import common
+
+    save("gym_1v1_extra_rewards", gym_sequence(common.extra_rewards_cfg(), 14, 40, 25))
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "extra":
+        extra()
+    else:
+        main()

@@ -48,7 +48,7 @@ def test_gym_layer_bit_exact(name, cfg, golden_dir):
         else:
             obs, r, d = hs.eval_gym(g["actions"][i], 0)
             assert common.obs_equal(cfg, g["obs"][i], obs), (name, i)
-            assert np.array_equal(r.view(np.uint32), g["reward"][i].view(np.uint32)), (name, i, r, g["reward"][i])
+            assert common.rewards_equal(name, g["reward"][i], r), (name, i, r, g["reward"][i])
             assert d == bool(g["done"][i]), (name, i)
 
 

@@ -33,7 +33,7 @@ def test_numpy_gym_oracle_bit_exact_vs_reference_golden(name, cfg, golden_dir):
             continue
         assert common.obs_equal(cfg, g["obs"][i], obs), (name, i)
         if r is not None:
-            assert np.array_equal(r.view(np.uint32), g["reward"][i].view(np.uint32)), (name, i, r, g["reward"][i])
+            assert common.rewards_equal(name, g["reward"][i], r), (name, i, r, g["reward"][i])
             assert d == bool(g["done"][i]), (name, i)
 
 
