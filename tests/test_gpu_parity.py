@@ -262,3 +262,58 @@ def test_against_compiled_reference_if_present(torch_cuda):
                     assert common.within(e, common.TOL_CONTACT), e
                     loose += 1
     assert loose <= 0.08 * (tight + loose)
+
+
+def test_rollout_statistics_match_the_reference(torch_cuda):
+    """Free-running collection (RandomState resets, uniform random actions, auto-reset) on both sides: the per-step statistics a
+    learner sees — mean reward, episode-end rate, ball height / speed, cars on the ground, boost, demolitions — agree within
+    the reference sample's own standard error (4 sigma + a small absolute slack).  The two runs share no random numbers, so
+    this is the distribution-level check behind "learning curves statistically indistinguishable"."""
+    from oracle import refsim
+
+    if not refsim.available():
+        pytest.skip("oracle/_ref/librlref.so not present")
+    cfg = abi.default_cfg(num_arenas=4096, team_size=1)
+    steps, warm = 220, 60  # warm-up: both sides forget the all-fresh start
+
+    def stats(obs, rew, done):
+        """obs [n, P, 89]: ball pos/vel at 0:6 (scaled by 1/2300, 1/2300), self block at 51 (boost 66, onGround 67, demoed 69)."""
+        o = obs.reshape(-1, obs.shape[-1])
+        return dict(reward=rew.reshape(-1), done=done.reshape(-1).astype(np.float64), ball_z=o[:, 2], ball_speed=np.linalg.norm(o[:, 3:6], axis=1),
+                    car_z=o[:, 53], car_speed=np.linalg.norm(o[:, 60:63], axis=1), boost=o[:, 66], on_ground=o[:, 67], has_flip=o[:, 68],
+                    demoed=o[:, 69])
+
+    # reference: G gyms, one (correlated) sample per gym-step; the standard error is taken over per-gym means
+    G = 48
+    refsim.seed(4242)
+    gyms = [refsim.RefGym(abi.default_cfg(num_arenas=1, team_size=1)) for _ in range(G)]
+    rng = np.random.default_rng(77)
+    per_gym = []
+    for g in gyms:
+        g.reset()
+        acc = {}
+        for s in range(steps):
+            o, r, d = g.step(rng.integers(0, 90, size=2))
+            if s >= warm:
+                for k, v in stats(o[None], r[None], np.array([d])).items():
+                    acc.setdefault(k, []).append(np.mean(v))
+            if d:
+                g.reset()
+        per_gym.append({k: float(np.mean(v)) for k, v in acc.items()})
+    ref_mean = {k: float(np.mean([p[k] for p in per_gym])) for k in per_gym[0]}
+    ref_se = {k: float(np.std([p[k] for p in per_gym], ddof=1) / np.sqrt(G)) for k in per_gym[0]}
+
+    e = engine.Engine(cfg)
+    e.reset()
+    rng = np.random.default_rng(78)
+    acc = {}
+    for s in range(steps):
+        o, r, d = e.step_host(rng.integers(0, 90, size=e.A * e.P).astype(np.int32))
+        if s >= warm:
+            for k, v in stats(o.reshape(e.A, e.P, -1), r, d).items():
+                acc.setdefault(k, []).append(np.mean(v))
+    got = {k: float(np.mean(v)) for k, v in acc.items()}
+    slack = dict(reward=0.01, done=0.002, ball_z=0.01, ball_speed=0.01, car_z=0.005, car_speed=0.01, boost=0.01, on_ground=0.02, has_flip=0.02,
+                 demoed=0.002)
+    bad = {k: (got[k], ref_mean[k], ref_se[k]) for k in got if abs(got[k] - ref_mean[k]) > 4 * ref_se[k] + slack[k]}
+    assert not bad, bad
