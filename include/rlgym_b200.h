@@ -99,6 +99,7 @@ typedef struct rlg_pad_state {
 
 /* ---- engine configuration ------------------------------------------------- */
 enum rlg_obs_kind { RLG_OBS_DEFAULT = 0, RLG_OBS_PADDED = 1 };
+enum rlg_car_preset { RLG_CAR_OCTANE = 0, RLG_CAR_DOMINUS = 1, RLG_CAR_PLANK = 2, RLG_CAR_BREAKOUT = 3, RLG_CAR_HYBRID = 4, RLG_CAR_MERC = 5 };
 enum rlg_state_setter { RLG_SETTER_KICKOFF = 0, RLG_SETTER_RANDOM = 1, RLG_SETTER_HOST = 2 };
 
 /* Built-in reward terms (G/Utils/RewardFunctions/CommonRewards.h). */
@@ -141,6 +142,10 @@ typedef struct rlg_engine_cfg {
     /* state setter */
     int32_t state_setter;     /* KickoffState / RandomState / host-provided */
     int32_t rand_ball_speed, rand_car_speed, cars_on_ground; /* RandomState flags */
+    /* car */
+    int32_t car_preset;       /* Gym's CarConfig argument (G/Gym.h:18): 0 OCTANE (default), 1 DOMINUS, 2 PLANK, 3 BREAKOUT, 4 HYBRID,
+                                 5 MERC — hitbox, wheel and suspension geometry of R/Sim/Car/CarConfig/CarConfig.cpp:20-88 */
+    int32_t reserved_;
 } rlg_engine_cfg;
 
 typedef struct rlg_engine rlg_engine;

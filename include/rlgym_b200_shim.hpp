@@ -47,6 +47,10 @@ inline void Check(int rc) {
 
 // ---------------------------------------------------------------------------------------------------------------------
 namespace RocketSim {
+// R/Sim/Car/CarConfig/CarConfig.h: the six stock configurations; the engine holds their geometry (rlg_engine_cfg.car_preset)
+struct CarConfig { int preset; };
+static const CarConfig CAR_CONFIG_OCTANE{RLG_CAR_OCTANE}, CAR_CONFIG_DOMINUS{RLG_CAR_DOMINUS}, CAR_CONFIG_PLANK{RLG_CAR_PLANK},
+    CAR_CONFIG_BREAKOUT{RLG_CAR_BREAKOUT}, CAR_CONFIG_HYBRID{RLG_CAR_HYBRID}, CAR_CONFIG_MERC{RLG_CAR_MERC};
 struct Vec {
     float x = 0, y = 0, z = 0, _w = 0;  // R/Math/MathTypes/MathTypes.h:7-16 (16-byte Vec)
     Vec() = default;
@@ -352,7 +356,9 @@ public:
         FList reward;
         bool done;
     };
-    Gym(Match* match_, int tickSkip_) : match(match_), tickSkip(tickSkip_) {}
+    RocketSim::CarConfig carConfig;
+    Gym(Match* match_, int tickSkip_, RocketSim::CarConfig carConfig_ = RocketSim::CAR_CONFIG_OCTANE)
+        : match(match_), tickSkip(tickSkip_), carConfig(carConfig_) {}  // G/Gym.h:18 (soccar, default mutators)
 };
 }  // namespace RLGSC
 
@@ -554,6 +560,7 @@ public:
     void CreateAgents(EnvCreateFn func, int amount, int gamesPerAgent) {
         probe = func();  // one Match/Gym to read the plugin configuration from (ThreadAgent.cpp:197-206 makes one per game)
         rlg_engine_cfg ec = RLGB200::CfgFromMatch(*probe.match, probe.gym->tickSkip, amount * gamesPerAgent, device, (uint64_t)cfg.randomSeed);
+        ec.car_preset = probe.gym->carConfig.preset;
         engine.reset(new RLGB200::Engine(ec));
         engine->LoadMeshes(RocketSim::CollisionMeshBlobs());
         const int N = engine->NumArenas() * engine->NumPlayers();

@@ -147,6 +147,16 @@ struct RefGym {
     }
 };
 
+static const CarConfig& preset_config(int preset) {
+    switch (preset) {
+    case RLG_CAR_DOMINUS: return CAR_CONFIG_DOMINUS;
+    case RLG_CAR_PLANK: return CAR_CONFIG_PLANK;
+    case RLG_CAR_BREAKOUT: return CAR_CONFIG_BREAKOUT;
+    case RLG_CAR_HYBRID: return CAR_CONFIG_HYBRID;
+    case RLG_CAR_MERC: return CAR_CONFIG_MERC;
+    }
+    return CAR_CONFIG_OCTANE;
+}
 static RewardFunction* make_term(const rlg_reward_term& t) {
     switch (t.kind) {
     case RLG_REW_EVENT: {
@@ -181,7 +191,7 @@ static RefGym* make_gym(const rlg_engine_cfg* cfg) {
         ? (StateSetter*)new KickoffState()
         : (StateSetter*)new RandomState(cfg->rand_ball_speed, cfg->rand_car_speed, cfg->cars_on_ground);
     g->match = new Match(g->reward, g->terms, g->obs, g->parser, g->setter, cfg->team_size, cfg->spawn_opponents != 0);
-    g->gym = new Gym(g->match, cfg->tick_skip);
+    g->gym = new Gym(g->match, cfg->tick_skip, preset_config(cfg->car_preset));
     return g;
 }
 
@@ -211,14 +221,15 @@ int ref_init(const void* const* blobs, const size_t* sizes, int n) {
 void ref_seed(uint32_t seed) { RocketSim::Math::GetRandEngine().seed(seed); }
 
 // ---- raw arena -------------------------------------------------------------
-void* ref_arena_create(int team_size, int spawn_opponents) {
+void* ref_arena_create_preset(int team_size, int spawn_opponents, int preset) {
     Arena* a = Arena::Create(GameMode::SOCCAR);
     for (int i = 0; i < team_size; i++) {  // same order as Gym::Gym, Gym.cpp:46-50
-        a->AddCar(Team::BLUE);
-        if (spawn_opponents) a->AddCar(Team::ORANGE);
+        a->AddCar(Team::BLUE, preset_config(preset));
+        if (spawn_opponents) a->AddCar(Team::ORANGE, preset_config(preset));
     }
     return a;
 }
+void* ref_arena_create(int team_size, int spawn_opponents) { return ref_arena_create_preset(team_size, spawn_opponents, 0); }
 void ref_arena_destroy(void* h) { delete (Arena*)h; }
 int ref_arena_num_cars(void* h) { return (int)((Arena*)h)->_cars.size(); }
 

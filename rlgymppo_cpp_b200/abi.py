@@ -17,6 +17,7 @@ RLG_MAX_REWARD_TERMS = 8
 
 RLG_OBS_DEFAULT, RLG_OBS_PADDED = 0, 1
 RLG_SETTER_KICKOFF, RLG_SETTER_RANDOM, RLG_SETTER_HOST = 0, 1, 2
+RLG_CAR_OCTANE, RLG_CAR_DOMINUS, RLG_CAR_PLANK, RLG_CAR_BREAKOUT, RLG_CAR_HYBRID, RLG_CAR_MERC = range(6)
 RLG_REW_EVENT, RLG_REW_VEL_PLAYER_TO_BALL, RLG_REW_VEL_BALL_TO_GOAL, RLG_REW_FACE_BALL, RLG_REW_VELOCITY, RLG_REW_SAVE_BOOST, RLG_REW_TOUCH_BALL = range(7)
 
 F3 = C.c_float * 3
@@ -83,6 +84,7 @@ class EngineCfg(C.Structure):
         ("no_touch_max_steps", C.c_int32), ("goal_score_terminal", C.c_int32),
         ("state_setter", C.c_int32), ("rand_ball_speed", C.c_int32), ("rand_car_speed", C.c_int32),
         ("cars_on_ground", C.c_int32),
+        ("car_preset", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 

@@ -74,18 +74,19 @@ struct CarConsts {
     float suspTravel;  // m_maxSuspensionTravelCm / 100
 };
 
-RL_HDI CarConsts car_consts() {
+RL_HDI CarConsts car_consts(int preset = 0) {
     CarConsts k;
+    const C::CarPreset cp = C::car_preset(preset);
     // btBoxShape ctor (B/BulletCollision/CollisionShapes/btBoxShape.cpp:18-28): implicit dims = half - 0.04, then
     // setSafeMargin lowers ONLY the margin to 0.1 * min half extent (setMargin is not virtual in this fork), so
     // the effective box is 0.04 - margin smaller than the configured hitbox on every side.
-    V3 req((C::HITBOX_X * UU2BT) / 2, (C::HITBOX_Y * UU2BT) / 2, (C::HITBOX_Z * UU2BT) / 2);
+    V3 req((cp.hitbox[0] * UU2BT) / 2, (cp.hitbox[1] * UU2BT) / 2, (cp.hitbox[2] * UU2BT) / 2);
     k.coreHalf = req - V3(C::BOX_MARGIN, C::BOX_MARGIN, C::BOX_MARGIN);
     float minDim = fminf_(fminf_(req.x, req.y), req.z);
     float safe = 0.1f * minDim;
     k.boxMargin = safe < C::BOX_MARGIN ? safe : C::BOX_MARGIN;
     k.halfExt = k.coreHalf + V3(k.boxMargin, k.boxMargin, k.boxMargin);
-    k.hitboxOffset = V3(C::HITBOX_OFF_X * UU2BT, C::HITBOX_OFF_Y * UU2BT, C::HITBOX_OFF_Z * UU2BT);
+    k.hitboxOffset = V3(cp.hitboxOff[0] * UU2BT, cp.hitboxOff[1] * UU2BT, cp.hitboxOff[2] * UU2BT);
     // btBoxShape::calculateLocalInertia
     float lx = 2.f * k.halfExt.x, ly = 2.f * k.halfExt.y, lz = 2.f * k.halfExt.z;
     V3 inertia(C::CAR_MASS / 12.f * (ly * ly + lz * lz), C::CAR_MASS / 12.f * (lx * lx + lz * lz), C::CAR_MASS / 12.f * (lx * lx + ly * ly));
@@ -93,11 +94,11 @@ RL_HDI CarConsts car_consts() {
     k.invMass = 1.f / C::CAR_MASS;
     for (int i = 0; i < 4; i++) {
         bool front = i < 2, left = (i % 2) != 0;
-        V3 off = front ? V3(C::WHEEL_FX, C::WHEEL_FY, C::WHEEL_FZ) : V3(C::WHEEL_BX, C::WHEEL_BY, C::WHEEL_BZ);
+        V3 off = front ? V3(cp.wheelF[0], cp.wheelF[1], cp.wheelF[2]) : V3(cp.wheelB[0], cp.wheelB[1], cp.wheelB[2]);
         if (left) off.y *= -1.f;
         k.wheelConn[i] = V3(off.x * UU2BT, off.y * UU2BT, off.z * UU2BT);
-        k.wheelRadius[i] = (front ? C::WHEEL_R_FRONT : C::WHEEL_R_BACK) * UU2BT;
-        float rest = front ? C::SUS_REST_FRONT : C::SUS_REST_BACK;
+        k.wheelRadius[i] = (front ? cp.wheelRFront : cp.wheelRBack) * UU2BT;
+        float rest = front ? cp.susRestFront : cp.susRestBack;
         rest -= C::MAX_SUSPENSION_TRAVEL;
         k.wheelRest[i] = rest * UU2BT;
         k.wheelForceScale[i] = front ? C::SUSPENSION_FORCE_SCALE_FRONT : C::SUSPENSION_FORCE_SCALE_BACK;

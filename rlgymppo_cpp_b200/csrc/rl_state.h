@@ -68,13 +68,20 @@ constexpr float AIR_DAMP_P = 30, AIR_DAMP_Y = 20, AIR_DAMP_R = 50;
 constexpr float PAD_CYL_HEIGHT = 95, PAD_CYL_RAD_BIG = 208, PAD_CYL_RAD_SMALL = 144;
 constexpr float PAD_BOX_HEIGHT = 64, PAD_BOX_RAD_BIG = 160, PAD_BOX_RAD_SMALL = 120;
 constexpr float PAD_COOLDOWN_BIG = 10, PAD_COOLDOWN_SMALL = 4, PAD_BOOST_BIG = 100, PAD_BOOST_SMALL = 12;
-// Octane (CarConfig.cpp:20-72)
-constexpr float HITBOX_X = 120.507f, HITBOX_Y = 86.6994f, HITBOX_Z = 38.6591f;
-constexpr float HITBOX_OFF_X = (float)13.87566, HITBOX_OFF_Y = 0.f, HITBOX_OFF_Z = 20.755f;
-constexpr float WHEEL_R_FRONT = 12.50f, WHEEL_R_BACK = 15.00f;
-constexpr float SUS_REST_FRONT = 38.755f, SUS_REST_BACK = 37.055f;
-constexpr float WHEEL_FX = 51.25f, WHEEL_FY = 25.90f, WHEEL_FZ = 20.755f;
-constexpr float WHEEL_BX = -33.75f, WHEEL_BY = 29.50f, WHEEL_BZ = 20.755f;
+// car presets (R/Sim/Car/CarConfig/CarConfig.cpp:20-88): OCTANE, DOMINUS, PLANK, BREAKOUT, HYBRID, MERC
+constexpr int kNumCarPresets = 6;
+struct CarPreset { float hitbox[3], hitboxOff[3], wheelRFront, wheelRBack, susRestFront, susRestBack, wheelF[3], wheelB[3]; };
+RL_HDI CarPreset car_preset(int i) {
+    const CarPreset T[kNumCarPresets] = {
+        {{120.507f, 86.6994f, 38.6591f}, {(float)13.87566, 0.f, 20.755f}, 12.50f, 15.00f, 38.755f, 37.055f, {51.25f, 25.90f, 20.755f}, {-33.75f, 29.50f, 20.755f}},
+        {{130.427f, 85.7799f, 33.8f}, {9.f, 0.f, 15.75f}, 12.00f, 13.50f, 33.95f, 33.85f, {50.30f, 31.10f, 15.75f}, {-34.75f, 33.00f, 15.75f}},
+        {{131.32f, 87.1704f, 31.8944f}, {9.00857f, 0.f, 12.0942f}, 12.50f, 17.00f, 31.9242f, 27.9242f, {49.97f, 27.80f, 12.0942f}, {-35.43f, 20.28f, 12.0942f}},
+        {{133.992f, 83.021f, 32.8f}, {12.5f, 0.f, 11.75f}, 13.50f, 15.00f, 29.7f, 29.666f, {51.50f, 26.67f, 11.75f}, {-35.75f, 35.00f, 11.75f}},
+        {{129.519f, 84.6879f, 36.6591f}, {13.8757f, 0.f, 20.755f}, 12.50f, 15.00f, 38.755f, 37.055f, {51.25f, 25.90f, 20.755f}, {-34.00f, 29.50f, 20.755f}},
+        {{123.22f, 79.2103f, 44.1591f}, {11.3757f, 0.f, 21.505f}, 15.00f, 15.00f, 39.505f, 39.105f, {51.25f, 25.90f, 21.505f}, {-33.75f, 29.50f, 21.505f}},
+    };
+    return T[(i < 0 || i >= kNumCarPresets) ? 0 : i];
+}
 constexpr float DODGE_DEADZONE = 0.5f;  // CarConfig.h default
 // Bullet
 constexpr float BOX_MARGIN = 0.04f;          // btCollisionMargin.h:22 CONVEX_DISTANCE_MARGIN
@@ -221,6 +228,7 @@ RL_HDI float rng_float(ArenaS& a, float lo, float hi) {
 struct RewardTerm { int32_t kind; float weight; float params[11]; };
 struct SimCfg {
     int32_t numArenas, numCars, spawnOpponents, tickSkip;
+    int32_t carPreset;  // rlg_engine_cfg.car_preset
     int32_t obsKind, obsMaxPlayers, obsSize;
     int32_t numRewardTerms;
     RewardTerm rewards[8];

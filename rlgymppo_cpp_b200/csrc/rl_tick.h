@@ -422,7 +422,7 @@ RL_HDI int tick_scratch_words(int ncars) { return tickx_words(ncars); }
 // Serial driver: the same phases, role after role.  Used by the host test build and by single-lane device paths.
 // xwords: tickx_words(numCars) uint32 words, scratch: contact_scratch_slots(numCars) contacts.
 RL_HD inline void arena_tick(ArenaS& a, const SimCfg& cfg, const MeshSet& ms, const Tables& tb, int firstTickOfStep, uint32_t* xwords, Contact* scratch) {
-    const CarConsts k = car_consts();
+    const CarConsts k = car_consts(cfg.carPreset);
     const Thresholds thr = contact_thresholds(k);
     TickX x = make_tickx(xwords);
     const int P = cfg.numCars;

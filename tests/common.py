@@ -81,6 +81,9 @@ def check_single_tick_run(groups, set_state, tick, get_state, allow_contact_frac
     return dict(total=total, loose=loose, worst_tight=worst)
 
 
+CAR_PRESETS = ((1, "dominus"), (2, "plank"), (3, "breakout"), (4, "hybrid"), (5, "merc"))
+
+
 def gym_cfgs():
     c = abi.default_cfg(1, 1)
     for k in range(11):

@@ -157,15 +157,16 @@ def scenarios_1v1(arena):
     return out
 
 
-def random_play(team, nsteps, seed):
+def random_play(team, nsteps, seed, car_preset=0):
     """Random DiscreteAction play from RandomState resets: the workload distribution of the benchmark."""
     cfg = abi.default_cfg(num_arenas=1, team_size=team)
+    cfg.car_preset = car_preset
     g = refsim.RefGym(cfg)
     refsim.seed(seed)
     rng = np.random.default_rng(seed)
     table = refsim.action_table()
     P = 2 * team
-    arena = refsim.RefArena(team, True)
+    arena = refsim.RefArena(team, True, car_preset=car_preset)
     chunks = []
     for ep in range(nsteps):
         g.reset()
@@ -271,10 +272,24 @@ def extra():
     import common
 
     save("gym_1v1_extra_rewards", gym_sequence(common.extra_rewards_cfg(), 14, 40, 25))
+    presets()
+
+
+def presets():
+    """python tests/golden/make_golden.py presets — random play with the five non-Octane CarConfigs"""
+    for preset, name in ((1, "dominus"), (2, "plank"), (3, "breakout"), (4, "hybrid"), (5, "merc")):
+        chunks = random_play(1, 4, 30 + preset, car_preset=preset)
+        flat = {}
+        for i, d in enumerate(chunks):
+            for k, v in d.items():
+                flat[f"ep{i}/{k}"] = v
+        save(f"tick_random_1v1_{name}", flat)
 
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "extra":
         extra()
+    elif len(sys.argv) > 1 and sys.argv[1] == "presets":
+        presets()
     else:
         main()

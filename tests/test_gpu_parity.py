@@ -30,8 +30,8 @@ def _engine(team, n=1, **kw):
 class _TickRunner:
     """Injects one reference state into arena 0, ticks once with explicit controls, reads the state back."""
 
-    def __init__(self, team, torch):
-        self.e = _engine(team)
+    def __init__(self, team, torch, **kw):
+        self.e = _engine(team, **kw)
         self.torch = torch
         self.ids = np.zeros(1, dtype=np.int32)
 
@@ -62,6 +62,15 @@ def test_single_tick_scenarios_1v1(torch_cuda):
 def test_single_tick_random_play(team, torch_cuda):
     r = _TickRunner(team, torch_cuda)
     res = common.check_single_tick_run(common.load_tick_file(f"tick_random_{team}v{team}"), r.set_state, r.tick, r.get_state,
+                                       allow_contact_frac=0.08)
+    print(res)
+
+
+@pytest.mark.parametrize("preset,name", list(common.CAR_PRESETS))
+def test_single_tick_random_play_car_presets(preset, name, torch_cuda):
+    """The five non-Octane CarConfigs (CarConfig.cpp:20-88) against the reference's trajectories, same tolerances."""
+    r = _TickRunner(1, torch_cuda, car_preset=preset)
+    res = common.check_single_tick_run(common.load_tick_file(f"tick_random_1v1_{name}"), r.set_state, r.tick, r.get_state,
                                        allow_contact_frac=0.08)
     print(res)
 
@@ -315,5 +324,11 @@ def test_rollout_statistics_match_the_reference(torch_cuda):
     got = {k: float(np.mean(v)) for k, v in acc.items()}
     slack = dict(reward=0.01, done=0.002, ball_z=0.01, ball_speed=0.01, car_z=0.005, car_speed=0.01, boost=0.01, on_ground=0.02, has_flip=0.02,
                  demoed=0.002)
+    out = os.environ.get("RLG_STATS_OUT")
+    if out:  # evidence file for profiles/: engine mean, reference mean, reference standard error per statistic
+        import json
+
+        with open(out, "w") as f:
+            json.dump({k: dict(engine=got[k], reference=ref_mean[k], reference_se=ref_se[k]) for k in got}, f, indent=1)
     bad = {k: (got[k], ref_mean[k], ref_se[k]) for k in got if abs(got[k] - ref_mean[k]) > 4 * ref_se[k] + slack[k]}
     assert not bad, bad

@@ -8,8 +8,9 @@ from hostsim import hostsim
 from rlgymppo_cpp_b200 import abi
 
 
-def _runner(team):
+def _runner(team, car_preset=0):
     cfg = abi.default_cfg(num_arenas=1, team_size=team)
+    cfg.car_preset = car_preset
     hs = hostsim.HostSim(cfg)
     return (lambda c, b, p, t: hs.set_state(0, c, b, p, t)), (lambda u: hs.tick(0, u, 1)), (lambda: hs.get_state(0))
 
@@ -30,6 +31,14 @@ def test_single_tick_scenarios_1v1():
 def test_single_tick_random_play(team):
     s, t, g = _runner(team)
     res = common.check_single_tick_run(common.load_tick_file(f"tick_random_{team}v{team}"), s, t, g, allow_contact_frac=0.08)
+    print(res)
+
+
+@pytest.mark.parametrize("preset,name", list(common.CAR_PRESETS))
+def test_single_tick_random_play_car_presets(preset, name):
+    """The five non-Octane CarConfigs (CarConfig.cpp:20-88): hitbox, wheel and suspension geometry."""
+    s, t, g = _runner(1, preset)
+    res = common.check_single_tick_run(common.load_tick_file(f"tick_random_1v1_{name}"), s, t, g, allow_contact_frac=0.08)
     print(res)
 
 
