@@ -135,7 +135,7 @@ def cpu_baseline_sample(budget_s=15.0):
         b = refsim.RefBench(cfg, T, G, 7)
         b.run(10)  # warm-up
         t = b.run(20)
-        steps = int(max(20, min(2000, 20 * (budget_s * 0.6) / max(t, 1e-3))))
+        steps = int(max(20, min(12000, 20 * (budget_s * 0.6) / max(t, 1e-3))))
         t = b.run(steps)
         v = b.player_steps(steps) / t
         b.close()

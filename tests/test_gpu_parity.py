@@ -293,7 +293,7 @@ def test_rollout_statistics_match_the_reference(torch_cuda):
                     demoed=o[:, 69])
 
     # reference: G gyms, one (correlated) sample per gym-step; the standard error is taken over per-gym means
-    G = 48
+    G = 96
     refsim.seed(4242)
     gyms = [refsim.RefGym(abi.default_cfg(num_arenas=1, team_size=1)) for _ in range(G)]
     rng = np.random.default_rng(77)
@@ -319,11 +319,16 @@ def test_rollout_statistics_match_the_reference(torch_cuda):
     for s in range(steps):
         o, r, d = e.step_host(rng.integers(0, 90, size=e.A * e.P).astype(np.int32))
         if s >= warm:
-            for k, v in stats(o.reshape(e.A, e.P, -1), r, d).items():
+            # GameInst::Step hands back the RESET observation for a finished arena; the reference loop above looks at the
+            # terminal one and discards the reset's, so finished arenas are left out of the observation statistics here
+            live = d == 0
+            st = stats(o.reshape(e.A, e.P, -1)[live], r.reshape(e.A, e.P)[live], d[live])
+            st["done"], st["reward"] = d.astype(np.float64), r
+            for k, v in st.items():
                 acc.setdefault(k, []).append(np.mean(v))
     got = {k: float(np.mean(v)) for k, v in acc.items()}
-    slack = dict(reward=0.01, done=0.002, ball_z=0.01, ball_speed=0.01, car_z=0.005, car_speed=0.01, boost=0.01, on_ground=0.02, has_flip=0.02,
-                 demoed=0.002)
+    slack = dict(reward=0.01, done=0.001, ball_z=0.01, ball_speed=0.01, car_z=0.003, car_speed=0.01, boost=0.01, on_ground=0.008, has_flip=0.01,
+                 demoed=0.001)
     out = os.environ.get("RLG_STATS_OUT")
     if out:  # evidence file for profiles/: engine mean, reference mean, reference standard error per statistic
         import json
