@@ -93,3 +93,23 @@ def test_learner_reports_skill_rating():
     reps = lr.learn(max_iterations=4)
     assert all("Skill Rating 1v1" in r and np.isfinite(r["Skill Rating 1v1"]) for r in reps)
     assert 1 <= len(lr.skill_tracker.old_policies) <= 2
+
+
+def test_render_sender_document_from_engine():
+    """RenderSender over a live engine: one arena's document has the reference's schema and the engine's values."""
+    from rlgymppo_cpp_b200 import engine, sinks
+
+    e = engine.Engine(abi.default_cfg(num_arenas=8, team_size=2))
+    e.reset()
+    acts = np.random.default_rng(0).integers(0, 90, size=e.A * e.P).astype(np.int32)
+    e.step_host(acts)
+    rs = sinks.RenderSender(e)
+    doc = rs.document(arena=3, action_idx=acts[3 * e.P:4 * e.P])
+    st = doc["state"]
+    assert len(st["players"]) == 4 and len(st["boost_pads"]) == 34 and len(doc["actions"]) == 4 and len(doc["actions"][0]) == 8
+    cars, balls, _, _ = e.get_state(np.array([3], dtype=np.int32))
+    assert np.allclose(st["ball"]["pos"], balls[0]["pos"])
+    assert sorted(p["team_num"] for p in st["players"]) == [0, 0, 1, 1]
+    for p in st["players"]:
+        assert np.allclose(p["phys"]["pos"], cars[0][p["car_id"] - 1]["pos"]) and 0 <= p["boost_amount"] <= 1
+    rs.send(arena=3)  # UDP, nobody needs to listen
