@@ -12,10 +12,12 @@ Plain numpy-float32 restatement of the learner-side arithmetic of the collection
                                                             (private/RLGymPPO_CPP/Util/TorchFuncs.cpp:5-52)
 * ``ExperienceBufferOracle``           — ExperienceBuffer::SubmitExperience FIFO (PPO/ExperienceBuffer.cpp:12-70)
 
-Pinning: the reference has no tests or golden vectors for this code and its GEMM/softmax/multinomial live in libtorch
-(third party, not vendored; pip torch 2.11.0+cu128 here), so **MLP parity is unpinned** against the reference's own
-binary; ``compute_gae`` / the buffer / the concatenation are first-party scalar code and are pinned by hand-derived
-known-answer cases in tests/test_ppo_oracle.py.
+Pinning: the reference has no tests or golden vectors for this code, so it is pinned against the reference's own
+binaries instead — TorchFuncs.cpp, DiscretePolicy.cpp and ValueEstimator.cpp compiled UNMODIFIED against the pip libtorch
+(oracle/Makefile ``ref_ppo`` -> oracle/_ref/librlref_ppo.so, bound by oracle/refppo.py); their outputs on seeded inputs are
+tests/golden/ppo_reference.npz.  tests/test_ppo_oracle.py: ``compute_gae`` bit-exact, probabilities / log-probs / entropy
+/ critic values within 2e-6 .. 2e-5 (ATen sums in another order).  The buffer and the concatenation (first-party scalar
+code) additionally have hand-derived known-answer cases.  Not pinned: torch.multinomial's random stream.
 
 Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this module.
 """

@@ -275,6 +275,37 @@ def extra():
     presets()
 
 
+def ppo():
+    """python tests/golden/make_golden.py ppo — the reference's own ComputeGAE / DiscretePolicy / ValueEstimator outputs
+    (oracle/_ref/librlref_ppo.so: the unmodified reference TUs against the pip libtorch) on seeded inputs."""
+    from oracle import refppo
+
+    rng = np.random.default_rng(41)
+    out = {}
+    for i, (n, gamma, lam, std, clip) in enumerate([(257, 0.99, 0.95, 1.0, 10.0), (64, 0.995, 0.9, 2.5, 0.5), (40, 0.9, 1.0, 0.0, 10.0), (33, 0.99, 0.95, 0.37, 0.0)]):
+        r = (rng.standard_normal(n) * 3).astype(np.float32)
+        d = (rng.random(n) < 0.08).astype(np.float32)
+        t = ((rng.random(n) < 0.05) & (d == 0)).astype(np.float32)
+        v = rng.standard_normal(n + 1).astype(np.float32)
+        adv, tgt, ret = refppo.compute_gae(r, d, t, v, gamma, lam, std, clip)
+        out.update({f"gae{i}/rews": r, f"gae{i}/dones": d, f"gae{i}/truncated": t, f"gae{i}/values": v, f"gae{i}/params": np.array([gamma, lam, std, clip], np.float64),
+                    f"gae{i}/adv": adv, f"gae{i}/target": tgt, f"gae{i}/ret": ret})
+    dims = [(64, 89), (64, 64), (90, 64)]
+    layers = [((rng.standard_normal(s) * (1.5 / np.sqrt(s[1]))).astype(np.float32), (rng.standard_normal(s[0]) * 0.1).astype(np.float32)) for s in dims]
+    obs = rng.uniform(-1.5, 1.5, size=(48, 89)).astype(np.float32)
+    acts = rng.integers(0, 90, size=48)
+    for temp, tag in ((1.0, "t1"), (0.7, "t07")):
+        probs, arg, lp, ent = refppo.policy(layers, obs, acts, temp)
+        out.update({f"policy_{tag}/probs": probs, f"policy_{tag}/argmax": arg, f"policy_{tag}/logprob": lp, f"policy_{tag}/entropy": np.float32(ent)})
+    cl = layers[:-1] + [((rng.standard_normal((1, 64)) * 0.2).astype(np.float32), np.array([0.05], np.float32))]
+    out["critic/values"] = refppo.critic(cl, obs)
+    for l, (W, b) in enumerate(layers):
+        out[f"net/W{l}"] = W; out[f"net/b{l}"] = b
+    out["net/Wc"], out["net/bc"] = cl[-1]
+    out["net/obs"], out["net/acts"] = obs, acts
+    save("ppo_reference", out)
+
+
 def presets():
     """python tests/golden/make_golden.py presets — random play with the five non-Octane CarConfigs"""
     for preset, name in ((1, "dominus"), (2, "plank"), (3, "breakout"), (4, "hybrid"), (5, "merc")):
@@ -291,5 +322,7 @@ if __name__ == "__main__":
         extra()
     elif len(sys.argv) > 1 and sys.argv[1] == "presets":
         presets()
+    elif len(sys.argv) > 1 and sys.argv[1] == "ppo":
+        ppo()
     else:
         main()
