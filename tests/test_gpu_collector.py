@@ -165,3 +165,24 @@ def test_collector_argument_errors(torch_cuda):
         c.collect(3)  # > max_steps
     with pytest.raises(engine.EngineError):
         c.gae()  # nothing collected yet
+
+
+def test_inference_kernel_against_the_reference_binary_fixture(torch_cuda, golden_dir):
+    """k_mlp_infer on the network / observations of tests/golden/ppo_reference.npz — the outputs of the reference's own
+    DiscretePolicy::GetAction(deterministic) and ValueEstimator::Forward (libtorch fp32): same argmax wherever the top two
+    probabilities are further apart than the TF32 error, values within 2e-3."""
+    import os
+
+    g = np.load(os.path.join(golden_dir, "ppo_reference.npz"))
+    e = engine.Engine(abi.default_cfg(num_arenas=32, team_size=1))
+    c = collector.Collector(e, policy_hidden=(64, 64), critic_hidden=(64, 64), max_steps=1, seed=1, deterministic=True)
+    layers = [(g[f"net/W{l}"], g[f"net/b{l}"]) for l in range(3)]
+    c.set_weights(0, layers)
+    c.set_weights(1, layers[:-1] + [(g["net/Wc"], g["net/bc"])])
+    act, lp, val = _infer(torch_cuda, c, np.ascontiguousarray(g["net/obs"]))
+    ref = g["policy_t1/probs"]
+    top2 = np.sort(ref, axis=1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > 2e-3
+    assert clear.sum() > 20 and np.array_equal(act[clear], g["policy_t1/argmax"][clear])
+    assert np.abs(val - g["critic/values"]).max() < 2e-3 * max(1.0, float(np.abs(g["critic/values"]).max()))
+    assert np.all(lp == 0)  # deterministic: GetAction returns zeros for the log-probs (DiscretePolicy.cpp:49-52)
