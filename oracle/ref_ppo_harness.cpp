@@ -5,8 +5,10 @@
 //   RLGPC::TorchFuncs::ComputeGAE        RLGymPPO_CPP/src/private/RLGymPPO_CPP/Util/TorchFuncs.cpp:5-52
 //   RLGPC::DiscretePolicy                RLGymPPO_CPP/src/private/RLGymPPO_CPP/PPO/DiscretePolicy.cpp:7-75
 //   RLGPC::ValueEstimator                RLGymPPO_CPP/src/private/RLGymPPO_CPP/PPO/ValueEstimator.cpp:6-27
+//   RLGPC::ExperienceBuffer              RLGymPPO_CPP/src/private/RLGymPPO_CPP/PPO/ExperienceBuffer.cpp:12-121
 // It pins oracle/ppo_oracle.py (and, through it, the device kernels) to what the reference's own binaries compute.
 #include <private/RLGymPPO_CPP/PPO/DiscretePolicy.h>
+#include <private/RLGymPPO_CPP/PPO/ExperienceBuffer.h>
 #include <private/RLGymPPO_CPP/PPO/ValueEstimator.h>
 #include <private/RLGymPPO_CPP/Util/TorchFuncs.h>
 
@@ -92,6 +94,34 @@ int ref_ppo_critic(int rows, int in, int nHidden, const int32_t* hidden, const f
         return 0;
     } catch (std::exception& e) {
         fprintf(stderr, "ref_ppo_critic: %s\n", e.what());
+        return -1;
+    }
+}
+
+// ExperienceBuffer(maxSize): SubmitExperience with `nSubmits` batches; batch k has sizes[k] rows whose `states` rows are
+// [width] floats and whose other tensors carry one scalar per row, all filled with consecutive numbers from start[k] so the
+// FIFO order is visible.  Returns curSize and the buffer's states / actions / advantages tensors ([maxSize, ...], NaN = unset).
+int ref_ppo_buffer(int64_t maxSize, int width, int nSubmits, const int32_t* sizes, const float* start, float* outStates, float* outActions,
+                   float* outAdvantages, int64_t* outCurSize, int64_t batchSize, int32_t* outNumBatches) {
+    try {
+        ExperienceBuffer buf(maxSize, 123, torch::kCPU);
+        for (int k = 0; k < nSubmits; k++) {
+            const int n = sizes[k];
+            auto col = torch::arange(n, torch::kFloat32) + start[k];
+            ExperienceTensors t;
+            t.states = col.view({n, 1}).repeat({1, width}) + torch::arange(width, torch::kFloat32).view({1, width}) * 0.001f;
+            t.actions = col + 0.1f; t.logProbs = col + 0.2f; t.rewards = col + 0.3f;
+            t.nextStates = t.states + 0.5f; t.dones = col + 0.4f; t.truncated = col + 0.5f; t.values = col + 0.6f; t.advantages = col + 0.7f;
+            buf.SubmitExperience(t);
+        }
+        *outCurSize = buf.curSize;
+        memcpy(outStates, buf.data.states.contiguous().data_ptr<float>(), (size_t)maxSize * width * 4);
+        memcpy(outActions, buf.data.actions.contiguous().data_ptr<float>(), (size_t)maxSize * 4);
+        memcpy(outAdvantages, buf.data.advantages.contiguous().data_ptr<float>(), (size_t)maxSize * 4);
+        *outNumBatches = batchSize > 0 ? (int32_t)buf.GetAllBatchesShuffled(batchSize).size() : 0;
+        return 0;
+    } catch (std::exception& e) {
+        fprintf(stderr, "ref_ppo_buffer: %s\n", e.what());
         return -1;
     }
 }

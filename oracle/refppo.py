@@ -75,3 +75,15 @@ def critic(layers, obs):
     rc = lib().ref_ppo_critic(rows, in_dim, len(hidden), _p(hidden), keep[2], keep[3], _p(obs), _p(out))
     assert rc == 0, rc
     return out
+
+
+def buffer_fifo(max_size, width, sizes, starts, batch_size=0):
+    """ExperienceBuffer(maxSize).SubmitExperience x len(sizes) with counting data (ref_ppo_harness.cpp ref_ppo_buffer): returns
+    (curSize, states [maxSize, width], actions [maxSize], advantages [maxSize], number of shuffled full batches)."""
+    sizes = np.ascontiguousarray(sizes, np.int32); starts = np.ascontiguousarray(starts, np.float32)
+    st = np.empty((max_size, width), np.float32); ac = np.empty(max_size, np.float32); ad = np.empty(max_size, np.float32)
+    cur = C.c_int64(0); nb = C.c_int32(0)
+    rc = lib().ref_ppo_buffer(C.c_int64(max_size), width, len(sizes), _p(sizes), _p(starts), _p(st), _p(ac), _p(ad), C.byref(cur),
+                              C.c_int64(batch_size), C.byref(nb))
+    assert rc == 0, rc
+    return int(cur.value), st, ac, ad, int(nb.value)

@@ -303,6 +303,12 @@ def ppo():
         out[f"net/W{l}"] = W; out[f"net/b{l}"] = b
     out["net/Wc"], out["net/bc"] = cl[-1]
     out["net/obs"], out["net/acts"] = obs, acts
+    # ExperienceBuffer FIFO: (maxSize, submit sizes) incl. overflow, a submit larger than the buffer, exact fill
+    for i, (max_size, sizes, bs) in enumerate([(10, [4, 4, 4, 3], 4), (8, [20], 3), (12, [5, 7, 1], 5), (16, [3, 2], 4)]):
+        starts = np.cumsum([0] + sizes[:-1]).astype(np.float32) * 1.0 + 100 * np.arange(len(sizes), dtype=np.float32)
+        cur, st, ac, ad, nb = refppo.buffer_fifo(max_size, 3, sizes, starts, bs)
+        out.update({f"buf{i}/max_size": np.int64(max_size), f"buf{i}/sizes": np.array(sizes, np.int32), f"buf{i}/starts": starts, f"buf{i}/batch": np.int64(bs),
+                    f"buf{i}/cur": np.int64(cur), f"buf{i}/states": st, f"buf{i}/actions": ac, f"buf{i}/advantages": ad, f"buf{i}/num_batches": np.int64(nb)})
     save("ppo_reference", out)
 
 
