@@ -30,6 +30,8 @@ sys.path.insert(0, ROOT)
 
 ARENAS_PER_GPU = 16384
 TEAM = 1
+PADDED_OBS = False
+ZERO_SUM = False
 METRIC = "collection steps/sec (1v1, tickSkip=8)"
 UNIT = "player-steps/s"
 
@@ -40,6 +42,13 @@ def workload_cfg(n_arenas, device, rank, seed=123):
     cfg = abi.default_cfg(num_arenas=n_arenas, team_size=TEAM, tick_skip=8, seed=seed)
     cfg.device = device
     cfg.arena_id_base = rank * n_arenas  # RNG streams keyed by GLOBAL arena id: results independent of the GPU count
+    if PADDED_OBS:  # BASELINE configs[2]: DefaultOBSPadded(maxPlayers = 3) with slot shuffling
+        cfg.obs_kind = abi.RLG_OBS_PADDED
+        cfg.obs_max_players = 3
+    if ZERO_SUM:    # ... + ZeroSumReward(CombinedReward(cfg-1 set), teamSpirit 0.3, opponentScale 1) (SURVEY 8d cfg 3)
+        cfg.zero_sum = 1
+        cfg.team_spirit = 0.3
+        cfg.opponent_scale = 1.0
     return cfg
 
 
@@ -307,7 +316,7 @@ def run_ours(args, rank, local_rank, world):
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{'cfg2: ' if (TEAM == 1 and A == ARENAS_PER_GPU) else 'sweep: '}{TEAM}v{TEAM} soccar, {A} arenas/GPU, DefaultObs + examplemain rewards/terminals, RandomState, tickSkip 8, "
+            "config": {"workload": f"{'cfg2: ' if (TEAM == 1 and A == ARENAS_PER_GPU) else 'sweep: '}{TEAM}v{TEAM} soccar, {A} arenas/GPU, {'DefaultOBSPadded(3)' if PADDED_OBS else 'DefaultObs'} + examplemain rewards{' in ZeroSumReward(0.3)' if ZERO_SUM else ''}/terminals, RandomState, tickSkip 8, "
                                    "on-device policy (256x256x256) + critic inference, sampling, trajectory ring, GAE; placeholder mesh set v1; "
                                    f"one bench step = one collect of {T} env-steps over every arena + GAE",
                        "arenas_per_gpu": A, "players_per_arena": P, "obs_size": OBS, "tick_skip": 8, "env_steps_per_bench_step": T,
@@ -387,8 +396,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ppo", action="store_true", help="skip the PPO iteration-time measurement")
     ap.add_argument("--team", type=int, default=1, help="players per team (sweep only: the headline metric is quoted on 1v1)")
+    ap.add_argument("--padded-obs", action="store_true", help="DefaultOBSPadded(3) (sweep only: BASELINE configs[2])")
+    ap.add_argument("--zero-sum", action="store_true", help="ZeroSumReward(teamSpirit 0.3) around the reward set (sweep only)")
     args = ap.parse_args()
-    global TEAM, METRIC
+    global TEAM, METRIC, PADDED_OBS, ZERO_SUM
+    PADDED_OBS, ZERO_SUM = args.padded_obs, args.zero_sum
     if args.team != 1:
         TEAM = args.team
         METRIC = f"collection steps/sec ({TEAM}v{TEAM}, tickSkip=8)"

@@ -301,10 +301,8 @@ __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tma(const __grid_constant
     const uint32_t tmemBase = *tmemSlot;
 
     if (warp == 0 && lane == 0) {  // producer
-        const uint32_t bytes = (uint32_t)(kGABytes + NT * kGK * 4);
-        const int boxRowsB = a.stageBytes / (kGK * 4) - kGM;  // rows of the B box (the map's box is fixed: >= NT)
-        const uint32_t bytesBox = (uint32_t)(kGABytes + boxRowsB * kGK * 4);
-        (void)bytes;
+        // a TMA box always delivers its full size (out-of-bounds rows / columns arrive as zeros): A box + B box = one stage
+        const uint32_t bytesBox = (uint32_t)a.stageBytes;
         for (int it = 0; it < nIt; it++) {
             const int s = it % S, k = it / S;
             if (k >= 1) mbar_wait(barEmpty + 8 * s, (k - 1) & 1);
