@@ -102,6 +102,52 @@ class Collector:
         self.set_weights(0, default_linear_init(self.policy_dims, seed))
         self.set_weights(1, default_linear_init(self.critic_dims, seed + 1))
 
+    # -- host StateSetter (StateSetter::ResetState(Arena*), G/Utils/StateSetters/StateSetter.h:9) ------------------------------
+    def set_state_setter(self, fn):
+        """A user StateSetter on the host: ``fn(arena_ids, cars, balls) -> None`` fills ``cars`` ([n, P] abi.CAR_DTYPE, car-id
+        order, pre-filled with default CarStates carrying the right car_id / team) and ``balls`` ([n] abi.BALL_DTYPE) for the
+        arenas whose episode ended; boost pads come back active (Match.cpp:66-67).  The engine must have been created with
+        ``state_setter = RLG_SETTER_HOST``.  The collector calls it between steps (rlg_collector_set_reset_hook) and
+        ``reset_with_setter()`` applies it to every arena (GameInst::Start)."""
+        e = self.engine
+        if e.cfg.state_setter != abi.RLG_SETTER_HOST:
+            raise RuntimeError("set_state_setter: create the engine with state_setter = RLG_SETTER_HOST")
+        self._setter = fn
+        teams = np.array([(c & 1) if e.cfg.spawn_opponents else 0 for c in range(e.P)], dtype=np.int32)
+
+        def apply(ids: np.ndarray, obs_out_ptr):
+            n = len(ids)
+            if n == 0:
+                return
+            cars = np.stack([abi.new_cars(e.P) for _ in range(n)])
+            cars["car_id"] = np.arange(1, e.P + 1, dtype=np.int32)[None, :]
+            cars["team"] = teams[None, :]
+            balls = abi.new_balls(n)
+            fn(ids, cars, balls)
+            pads = np.zeros((n, abi.RLG_NUM_PADS), dtype=abi.PAD_DTYPE)
+            pads["is_active"] = 1
+            e.set_state(ids, cars, balls, pads, np.full(n, -1, dtype=np.int64))
+            mask = np.zeros(e.A, dtype=np.uint8)
+            mask[ids] = 1
+            if obs_out_ptr:
+                _check(self.L.rlg_engine_reset_current_to(e.h, mask.ctypes.data_as(C.c_void_p), C.c_void_p(obs_out_ptr), None))
+            else:
+                e.reset_current(mask)
+            e.sync()
+
+        self._apply_setter = apply
+        HOOK = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.c_void_p)
+
+        def hook(user, ids_ptr, n, obs_out):
+            apply(np.ctypeslib.as_array(ids_ptr, shape=(n,)).astype(np.int32).copy(), obs_out)
+
+        self._hook = HOOK(hook)  # keep alive
+        _check(self.L.rlg_collector_set_reset_hook(self.h, self._hook, None))
+
+    def reset_with_setter(self):
+        """GameInst::Start for every arena through the host StateSetter."""
+        self._apply_setter(np.arange(self.engine.A, dtype=np.int32), 0)
+
     # -- calls ----------------------------------------------------------------------------------------
     def infer(self, obs_ptr: int, n_rows: int, counter: int, action_ptr=0, logprob_ptr=0, value_ptr=0):
         v = lambda p: C.c_void_p(p) if p else None

@@ -336,7 +336,7 @@ class Learner:
     torch.distributed initialised every rank owns ``cfg.num_arenas`` arenas (global ids offset by rank) and the PPO
     update is data parallel."""
 
-    def __init__(self, engine_cfg, cfg: LearnerConfig, device_index: int = 0, iteration_callback=None):
+    def __init__(self, engine_cfg, cfg: LearnerConfig, device_index: int = 0, iteration_callback=None, state_setter=None):
         from . import abi, collector, engine  # CUDA extension: fails loudly if missing
 
         self.cfg = cfg
@@ -348,6 +348,8 @@ class Learner:
         engine_cfg.device = device_index
         engine_cfg.seed = cfg.randomSeed
         engine_cfg.arena_id_base = self.rank * engine_cfg.num_arenas
+        if state_setter is not None:  # a user StateSetter on the host (collector.set_state_setter)
+            engine_cfg.state_setter = abi.RLG_SETTER_HOST
         self.engine = engine.Engine(engine_cfg)
         A, P = self.engine.A, self.engine.P
         self.steps_per_iter = max(1, math.ceil(cfg.timestepsPerIteration / (self.world * A * P)))  # CollectTimesteps: >= amount rows
@@ -367,7 +369,11 @@ class Learner:
 
             self.skill_tracker = skill_tracker.SkillTracker.on_engine(stc, engine_cfg, tuple(cfg.ppo.policyLayerSizes), device_index, cfg.randomSeed)
         self._push_weights()
-        self.engine.reset()
+        if state_setter is not None:
+            self.collector.set_state_setter(state_setter)
+            self.collector.reset_with_setter()
+        else:
+            self.engine.reset()
 
     def save(self, folder=None):
         """Learner::Save (Learner.cpp:244-281), reference on-disk layout (checkpoint.py)."""

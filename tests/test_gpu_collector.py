@@ -186,3 +186,37 @@ def test_inference_kernel_against_the_reference_binary_fixture(torch_cuda, golde
     assert clear.sum() > 20 and np.array_equal(act[clear], g["policy_t1/argmax"][clear])
     assert np.abs(val - g["critic/values"]).max() < 2e-3 * max(1.0, float(np.abs(g["critic/values"]).max()))
     assert np.all(lp == 0)  # deterministic: GetAction returns zeros for the log-probs (DiscretePolicy.cpp:49-52)
+
+
+def test_python_host_state_setter(torch_cuda):
+    """A user StateSetter in Python (BASELINE configs[3]: "custom StateSetter"): every episode starts from the state it
+    writes — at GameInst::Start and whenever an arena's episode ends during collection."""
+    cfg = abi.default_cfg(num_arenas=64, team_size=1)
+    cfg.state_setter = abi.RLG_SETTER_HOST
+    cfg.no_touch_max_steps = 3  # episodes end every 3 steps
+    e = engine.Engine(cfg)
+    c = collector.Collector(e, policy_hidden=(64, 64), critic_hidden=(64, 64), max_steps=8, seed=3)
+    c.init_default(seed=3)
+    calls = []
+
+    def setter(ids, cars, balls):
+        calls.append(len(ids))
+        balls["pos"][:] = (0.0, 0.0, 500.0)
+        balls["vel"][:] = (0.0, 0.0, 0.0)
+        cars["pos"][:, 0] = (-1000.0, 0.0, 17.0)
+        cars["pos"][:, 1] = (1000.0, 0.0, 17.0)
+        cars["boost"][:] = 42.0
+
+    c.set_state_setter(setter)
+    c.reset_with_setter()
+    assert calls == [64]
+    cars, balls, pads, _ = e.get_state(np.arange(64, dtype=np.int32))
+    assert np.allclose(balls["pos"], (0, 0, 500)) and np.allclose(cars["boost"], 42.0) and np.all(pads["is_active"] == 1)
+    c.collect(8)
+    e.sync()
+    done = c.read("done")  # [T, A]
+    assert done[2].all() and done[5].all() and not done[0].any()  # NoTouchCondition(3): every arena ends at steps 3 and 6
+    assert calls[1:] == [64, 64]
+    # the observation that follows a finished step is the custom reset state: ball at (0, 0, 500) / (4096, 5120, 2044)
+    obs = c.read("obs")  # [T+1, N, obs]
+    assert np.allclose(obs[3][:, 2], 500.0 / 2044.0, atol=1e-6) and np.allclose(obs[6][:, 0:2], 0.0, atol=1e-7)
