@@ -4,7 +4,7 @@
 //
 //   g++ -std=c++17 -O2 -Iinclude examples/examplemain.cpp -o examplemain
 //       -Lrlgymppo_cpp_b200/csrc -lrlgym_b200 -Wl,-rpath,$PWD/rlgymppo_cpp_b200/csrc   (one line)
-//   python -m rlgymppo_cpp_b200.meshes --out collision_meshes && ./examplemain collision_meshes [iterations] [--custom-setter]
+//   python -m rlgymppo_cpp_b200.meshes --out collision_meshes && ./examplemain collision_meshes [iterations] [--custom-setter] [--low-gravity]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -16,6 +16,7 @@ using namespace RLGPC;  // RLGymPPO
 using namespace RLGSC;  // RLGymSim
 
 static bool g_customSetter = false;
+static bool g_lowGravity = false;  // a MutatorConfig through Gym's last constructor argument (G/Gym.h:18)
 
 // A user-defined StateSetter (runs on the host through Arena/Car/Ball proxies): ball dropped above midfield, cars on
 // their own half facing the ball.
@@ -61,14 +62,23 @@ EnvCreateResult EnvCreateFunc() {
     StateSetter* stateSetter = g_customSetter ? (StateSetter*)new MidfieldDropState() : (StateSetter*)new RandomState(true, true, true);
 
     Match* match = new Match(rewards, terminalConditions, obs, actionParser, stateSetter, 1, true);
-    Gym* gym = new Gym(match, TICK_SKIP);
+    MutatorConfig mutators(GameMode::SOCCAR);
+    if (g_lowGravity) {
+        mutators.gravity = Vec(0, 0, -325.f);
+        mutators.unlimitedFlips = true;
+        mutators.demoMode = DemoMode::DISABLED;
+    }
+    Gym* gym = new Gym(match, TICK_SKIP, CAR_CONFIG_OCTANE, GameMode::SOCCAR, mutators);
     return {match, gym};
 }
 
 int main(int argc, char** argv) {
     const char* meshDir = argc > 1 ? argv[1] : "./collision_meshes";
     int iterations = argc > 2 ? atoi(argv[2]) : 5;
-    for (int i = 1; i < argc; i++) if (std::string(argv[i]) == "--custom-setter") g_customSetter = true;
+    for (int i = 1; i < argc; i++) {
+        if (std::string(argv[i]) == "--custom-setter") g_customSetter = true;
+        if (std::string(argv[i]) == "--low-gravity") g_lowGravity = true;
+    }
     try {
         RocketSim::Init(meshDir);
 

@@ -120,6 +120,27 @@ typedef struct rlg_reward_term {
     float params[11];
 } rlg_reward_term;
 
+/* MutatorConfig (R/Sim/MutatorConfig/MutatorConfig.h:16-72), Gym's last constructor argument (G/Gym.h:18).  Filled with the
+ * soccar defaults by rlg_engine_cfg_default / rlg_mutators_default; honoured when rlg_engine_cfg.mutators_set != 0.
+ * car_mass, ball_mass and ball_radius must keep their defaults (rlg_engine_create rejects other values). */
+enum rlg_demo_mode { RLG_DEMO_NORMAL = 0, RLG_DEMO_ON_CONTACT = 1, RLG_DEMO_DISABLED = 2 };
+typedef struct rlg_mutators {
+    float gravity[3];
+    float car_mass, car_world_friction, car_world_restitution;
+    float ball_mass, ball_max_speed, ball_drag, ball_world_friction, ball_world_restitution;
+    float jump_accel, jump_immediate_force;
+    float boost_accel_ground, boost_accel_air, boost_used_per_second;
+    float respawn_delay, bump_cooldown_time;
+    float boost_pad_cooldown_big, boost_pad_cooldown_small;
+    float car_spawn_boost_amount;
+    float ball_hit_extra_force_scale, bump_force_scale;
+    float ball_radius;
+    int32_t unlimited_flips, unlimited_double_jumps;
+    int32_t demo_mode;         /* rlg_demo_mode */
+    int32_t enable_team_demos;
+    float goal_base_threshold_y;
+} rlg_mutators;
+
 typedef struct rlg_engine_cfg {
     int32_t num_arenas;
     int32_t team_size;        /* Match::teamSize, G/Envs/Match.h:27-46 */
@@ -145,7 +166,8 @@ typedef struct rlg_engine_cfg {
     /* car */
     int32_t car_preset;       /* Gym's CarConfig argument (G/Gym.h:18): 0 OCTANE (default), 1 DOMINUS, 2 PLANK, 3 BREAKOUT, 4 HYBRID,
                                  5 MERC — hitbox, wheel and suspension geometry of R/Sim/Car/CarConfig/CarConfig.cpp:20-88 */
-    int32_t reserved_;
+    int32_t mutators_set;     /* 0: default MutatorConfig(SOCCAR); 1: use `mutators` */
+    rlg_mutators mutators;
 } rlg_engine_cfg;
 
 typedef struct rlg_engine rlg_engine;
@@ -159,6 +181,7 @@ size_t rlg_sizeof_engine_cfg(void);
  * rewards {FaceBall .1, VelPlayerToBall .5, VelBallToGoal 1, Event{teamGoal 1, concede -1}*50},
  * NoTouch 150 + GoalScore, RandomState(true,true,true), tickSkip 8). */
 void rlg_engine_cfg_default(rlg_engine_cfg* cfg);
+void rlg_mutators_default(rlg_mutators* m); /* MutatorConfig(GameMode::SOCCAR) */
 
 /* Replaces `new Gym(match, tickSkip)` x num_arenas in ThreadAgent::ThreadAgent
  * (P/private/RLGymPPO_CPP/Threading/ThreadAgent.cpp:197-206, G/Gym.cpp:40-56). */

@@ -64,6 +64,50 @@ struct Vec {
     float Length() const { float l = LengthSq(); return l > 0 ? std::sqrt(l) : 0; }
     Vec Normalized() const { float l = Length(); return l > 1e-12f ? Vec(x / l, y / l, z / l) : Vec(); }
 };
+// R/Sim/GameMode.h, R/Sim/MutatorConfig/MutatorConfig.h:10-72: same field names and defaults; Gym's last constructor arguments.
+// Only soccar is built (north_star names soccar); carMass / ballMass / ballRadius must keep their defaults.
+enum class GameMode : uint8_t { SOCCAR = 0 };
+enum class DemoMode : uint8_t { NORMAL = RLG_DEMO_NORMAL, ON_CONTACT = RLG_DEMO_ON_CONTACT, DISABLED = RLG_DEMO_DISABLED };
+struct MutatorConfig {
+    Vec gravity;
+    float carMass, carWorldFriction, carWorldRestitution, ballMass, ballMaxSpeed, ballDrag, ballWorldFriction, ballWorldRestitution, jumpAccel,
+        jumpImmediateForce, boostAccelGround, boostAccelAir, boostUsedPerSecond, respawnDelay, bumpCooldownTime, boostPadCooldown_Big,
+        boostPadCooldown_Small, carSpawnBoostAmount;
+    float ballHitExtraForceScale = 1, bumpForceScale = 1;
+    float ballRadius;
+    bool unlimitedFlips = false, unlimitedDoubleJumps = false;
+    DemoMode demoMode = DemoMode::NORMAL;
+    bool enableTeamDemos = false;
+    float goalBaseThresholdY;
+    MutatorConfig(GameMode = GameMode::SOCCAR) {
+        rlg_mutators m;
+        rlg_mutators_default(&m);
+        gravity = Vec(m.gravity[0], m.gravity[1], m.gravity[2]);
+        carMass = m.car_mass; carWorldFriction = m.car_world_friction; carWorldRestitution = m.car_world_restitution;
+        ballMass = m.ball_mass; ballMaxSpeed = m.ball_max_speed; ballDrag = m.ball_drag;
+        ballWorldFriction = m.ball_world_friction; ballWorldRestitution = m.ball_world_restitution;
+        jumpAccel = m.jump_accel; jumpImmediateForce = m.jump_immediate_force;
+        boostAccelGround = m.boost_accel_ground; boostAccelAir = m.boost_accel_air; boostUsedPerSecond = m.boost_used_per_second;
+        respawnDelay = m.respawn_delay; bumpCooldownTime = m.bump_cooldown_time;
+        boostPadCooldown_Big = m.boost_pad_cooldown_big; boostPadCooldown_Small = m.boost_pad_cooldown_small;
+        carSpawnBoostAmount = m.car_spawn_boost_amount; ballRadius = m.ball_radius; goalBaseThresholdY = m.goal_base_threshold_y;
+    }
+    rlg_mutators ToC() const {  // field for field
+        rlg_mutators m;
+        m.gravity[0] = gravity.x; m.gravity[1] = gravity.y; m.gravity[2] = gravity.z;
+        m.car_mass = carMass; m.car_world_friction = carWorldFriction; m.car_world_restitution = carWorldRestitution;
+        m.ball_mass = ballMass; m.ball_max_speed = ballMaxSpeed; m.ball_drag = ballDrag;
+        m.ball_world_friction = ballWorldFriction; m.ball_world_restitution = ballWorldRestitution;
+        m.jump_accel = jumpAccel; m.jump_immediate_force = jumpImmediateForce;
+        m.boost_accel_ground = boostAccelGround; m.boost_accel_air = boostAccelAir; m.boost_used_per_second = boostUsedPerSecond;
+        m.respawn_delay = respawnDelay; m.bump_cooldown_time = bumpCooldownTime;
+        m.boost_pad_cooldown_big = boostPadCooldown_Big; m.boost_pad_cooldown_small = boostPadCooldown_Small;
+        m.car_spawn_boost_amount = carSpawnBoostAmount; m.ball_hit_extra_force_scale = ballHitExtraForceScale; m.bump_force_scale = bumpForceScale;
+        m.ball_radius = ballRadius; m.unlimited_flips = unlimitedFlips; m.unlimited_double_jumps = unlimitedDoubleJumps;
+        m.demo_mode = (int32_t)demoMode; m.enable_team_demos = enableTeamDemos; m.goal_base_threshold_y = goalBaseThresholdY;
+        return m;
+    }
+};
 struct RotMat {
     Vec forward{1, 0, 0}, right{0, 1, 0}, up{0, 0, 1};
 };
@@ -159,6 +203,7 @@ inline void Init(const std::string& collisionMeshesFolder) {
 }  // namespace RocketSim
 
 // ---------------------------------------------------------------------------------------------------------------------
+using namespace RocketSim;  // G/Framework.h:8 does the same: user code names Vec, CarConfig, MutatorConfig unqualified
 namespace RLGSC {
 using RocketSim::Vec; using RocketSim::RotMat; using RocketSim::Angle; using RocketSim::Team; using RocketSim::CarState;
 using RocketSim::BallState; using RocketSim::Arena; using RocketSim::Car; using RocketSim::Ball;
@@ -357,8 +402,10 @@ public:
         bool done;
     };
     RocketSim::CarConfig carConfig;
-    Gym(Match* match_, int tickSkip_, RocketSim::CarConfig carConfig_ = RocketSim::CAR_CONFIG_OCTANE)
-        : match(match_), tickSkip(tickSkip_), carConfig(carConfig_) {}  // G/Gym.h:18 (soccar, default mutators)
+    RocketSim::MutatorConfig mutatorConfig;
+    Gym(Match* match_, int tickSkip_, RocketSim::CarConfig carConfig_ = RocketSim::CAR_CONFIG_OCTANE,
+        RocketSim::GameMode gameMode = RocketSim::GameMode::SOCCAR, RocketSim::MutatorConfig mutatorConfig_ = RocketSim::MutatorConfig(RocketSim::GameMode::SOCCAR))
+        : match(match_), tickSkip(tickSkip_), carConfig(carConfig_), mutatorConfig(mutatorConfig_) {}  // G/Gym.h:18 (soccar only)
 };
 }  // namespace RLGSC
 
@@ -561,6 +608,8 @@ public:
         probe = func();  // one Match/Gym to read the plugin configuration from (ThreadAgent.cpp:197-206 makes one per game)
         rlg_engine_cfg ec = RLGB200::CfgFromMatch(*probe.match, probe.gym->tickSkip, amount * gamesPerAgent, device, (uint64_t)cfg.randomSeed);
         ec.car_preset = probe.gym->carConfig.preset;
+        ec.mutators = probe.gym->mutatorConfig.ToC();  // Gym.cpp:43 arena->SetMutatorConfig
+        ec.mutators_set = 1;
         engine.reset(new RLGB200::Engine(ec));
         engine->LoadMeshes(RocketSim::CollisionMeshBlobs());
         const int N = engine->NumArenas() * engine->NumPlayers();

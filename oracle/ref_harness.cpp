@@ -147,6 +147,23 @@ struct RefGym {
     }
 };
 
+static MutatorConfig mutators_from(const rlg_engine_cfg* cfg) {
+    MutatorConfig m(GameMode::SOCCAR);
+    if (!cfg || !cfg->mutators_set) return m;
+    const rlg_mutators& u = cfg->mutators;
+    m.gravity = Vec(u.gravity[0], u.gravity[1], u.gravity[2]);
+    m.carMass = u.car_mass; m.carWorldFriction = u.car_world_friction; m.carWorldRestitution = u.car_world_restitution;
+    m.ballMass = u.ball_mass; m.ballMaxSpeed = u.ball_max_speed; m.ballDrag = u.ball_drag;
+    m.ballWorldFriction = u.ball_world_friction; m.ballWorldRestitution = u.ball_world_restitution;
+    m.jumpAccel = u.jump_accel; m.jumpImmediateForce = u.jump_immediate_force;
+    m.boostAccelGround = u.boost_accel_ground; m.boostAccelAir = u.boost_accel_air; m.boostUsedPerSecond = u.boost_used_per_second;
+    m.respawnDelay = u.respawn_delay; m.bumpCooldownTime = u.bump_cooldown_time;
+    m.boostPadCooldown_Big = u.boost_pad_cooldown_big; m.boostPadCooldown_Small = u.boost_pad_cooldown_small;
+    m.carSpawnBoostAmount = u.car_spawn_boost_amount; m.ballHitExtraForceScale = u.ball_hit_extra_force_scale; m.bumpForceScale = u.bump_force_scale;
+    m.ballRadius = u.ball_radius; m.unlimitedFlips = u.unlimited_flips != 0; m.unlimitedDoubleJumps = u.unlimited_double_jumps != 0;
+    m.demoMode = (DemoMode)u.demo_mode; m.enableTeamDemos = u.enable_team_demos != 0; m.goalBaseThresholdY = u.goal_base_threshold_y;
+    return m;
+}
 static const CarConfig& preset_config(int preset) {
     switch (preset) {
     case RLG_CAR_DOMINUS: return CAR_CONFIG_DOMINUS;
@@ -191,7 +208,7 @@ static RefGym* make_gym(const rlg_engine_cfg* cfg) {
         ? (StateSetter*)new KickoffState()
         : (StateSetter*)new RandomState(cfg->rand_ball_speed, cfg->rand_car_speed, cfg->cars_on_ground);
     g->match = new Match(g->reward, g->terms, g->obs, g->parser, g->setter, cfg->team_size, cfg->spawn_opponents != 0);
-    g->gym = new Gym(g->match, cfg->tick_skip, preset_config(cfg->car_preset));
+    g->gym = new Gym(g->match, cfg->tick_skip, preset_config(cfg->car_preset), GameMode::SOCCAR, mutators_from(cfg));
     return g;
 }
 
@@ -221,6 +238,16 @@ int ref_init(const void* const* blobs, const size_t* sizes, int n) {
 void ref_seed(uint32_t seed) { RocketSim::Math::GetRandEngine().seed(seed); }
 
 // ---- raw arena -------------------------------------------------------------
+// arena with the cfg's car preset and mutators (cars added in Gym::Gym order, mutators set like Gym.cpp:43)
+void* ref_arena_create_cfg(const rlg_engine_cfg* cfg) {
+    Arena* a = Arena::Create(GameMode::SOCCAR);
+    a->SetMutatorConfig(mutators_from(cfg));
+    for (int i = 0; i < cfg->team_size; i++) {
+        a->AddCar(Team::BLUE, preset_config(cfg->car_preset));
+        if (cfg->spawn_opponents) a->AddCar(Team::ORANGE, preset_config(cfg->car_preset));
+    }
+    return a;
+}
 void* ref_arena_create_preset(int team_size, int spawn_opponents, int preset) {
     Arena* a = Arena::Create(GameMode::SOCCAR);
     for (int i = 0; i < team_size; i++) {  // same order as Gym::Gym, Gym.cpp:46-50

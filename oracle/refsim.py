@@ -56,10 +56,13 @@ def seed(s: int):
 class RefArena:
     """Raw RocketSim Arena (soccar), cars added in Gym::Gym order; indices are car id - 1."""
 
-    def __init__(self, team_size=1, spawn_opponents=True, handle=None, car_preset=0):
+    def __init__(self, team_size=1, spawn_opponents=True, handle=None, car_preset=0, cfg=None):
         self.L = lib()
         self._own = handle is None
         self.L.ref_arena_create_preset.restype = C.c_void_p
+        self.L.ref_arena_create_cfg.restype = C.c_void_p
+        if handle is None and cfg is not None:  # car preset + mutators of an EngineCfg
+            handle, self._own = self.L.ref_arena_create_cfg(C.byref(cfg)), True
         self.h = C.c_void_p(handle if handle is not None else self.L.ref_arena_create_preset(team_size, int(spawn_opponents), int(car_preset)))
         self.num_cars = self.L.ref_arena_num_cars(self.h)
 

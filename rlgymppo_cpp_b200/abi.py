@@ -74,6 +74,35 @@ class RewardTerm(C.Structure):
     _fields_ = [("kind", C.c_int32), ("weight", C.c_float), ("params", C.c_float * 11)]
 
 
+class Mutators(C.Structure):
+    """rlg_mutators (MutatorConfig.h:16-72)."""
+    _fields_ = [("gravity", F3), ("car_mass", C.c_float), ("car_world_friction", C.c_float), ("car_world_restitution", C.c_float),
+                ("ball_mass", C.c_float), ("ball_max_speed", C.c_float), ("ball_drag", C.c_float), ("ball_world_friction", C.c_float),
+                ("ball_world_restitution", C.c_float), ("jump_accel", C.c_float), ("jump_immediate_force", C.c_float),
+                ("boost_accel_ground", C.c_float), ("boost_accel_air", C.c_float), ("boost_used_per_second", C.c_float),
+                ("respawn_delay", C.c_float), ("bump_cooldown_time", C.c_float), ("boost_pad_cooldown_big", C.c_float),
+                ("boost_pad_cooldown_small", C.c_float), ("car_spawn_boost_amount", C.c_float), ("ball_hit_extra_force_scale", C.c_float),
+                ("bump_force_scale", C.c_float), ("ball_radius", C.c_float), ("unlimited_flips", C.c_int32), ("unlimited_double_jumps", C.c_int32),
+                ("demo_mode", C.c_int32), ("enable_team_demos", C.c_int32), ("goal_base_threshold_y", C.c_float)]
+
+
+def default_mutators() -> "Mutators":
+    """MutatorConfig(GameMode::SOCCAR) (MutatorConfig.cpp; RLConst.h)."""
+    m = Mutators()
+    m.gravity[0], m.gravity[1], m.gravity[2] = 0.0, 0.0, -650.0
+    m.car_mass, m.car_world_friction, m.car_world_restitution = 180.0, 0.3, 0.3
+    m.ball_mass, m.ball_max_speed, m.ball_drag, m.ball_world_friction, m.ball_world_restitution = 30.0, 6000.0, 0.03, 0.35, 0.6
+    m.jump_accel, m.jump_immediate_force = 4375.0 / 3.0, 875.0 / 3.0
+    m.boost_accel_ground, m.boost_accel_air, m.boost_used_per_second = 2975.0 / 3.0, 3175.0 / 3.0, 100.0 / 3.0
+    m.respawn_delay, m.bump_cooldown_time = 3.0, 0.25
+    m.boost_pad_cooldown_big, m.boost_pad_cooldown_small = 10.0, 4.0
+    m.car_spawn_boost_amount = 100.0 / 3.0
+    m.ball_hit_extra_force_scale, m.bump_force_scale = 1.0, 1.0
+    m.ball_radius = 91.25
+    m.goal_base_threshold_y = 5124.25
+    return m
+
+
 class EngineCfg(C.Structure):
     _fields_ = [
         ("num_arenas", C.c_int32), ("team_size", C.c_int32), ("spawn_opponents", C.c_int32),
@@ -84,7 +113,7 @@ class EngineCfg(C.Structure):
         ("no_touch_max_steps", C.c_int32), ("goal_score_terminal", C.c_int32),
         ("state_setter", C.c_int32), ("rand_ball_speed", C.c_int32), ("rand_car_speed", C.c_int32),
         ("cars_on_ground", C.c_int32),
-        ("car_preset", C.c_int32), ("reserved_", C.c_int32),
+        ("car_preset", C.c_int32), ("mutators_set", C.c_int32), ("mutators", Mutators),
     ]
 
 
@@ -120,6 +149,8 @@ def default_cfg(num_arenas: int = 256, team_size: int = 1, tick_skip: int = 8, s
     cfg.goal_score_terminal = 1
     cfg.state_setter = RLG_SETTER_RANDOM
     cfg.rand_ball_speed = cfg.rand_car_speed = cfg.cars_on_ground = 1
+    cfg.mutators = default_mutators()
+    cfg.mutators_set = 0
     return cfg
 
 

@@ -595,7 +595,10 @@ void rlg_engine_cfg_default(rlg_engine_cfg* c) {
     c->opponent_scale = 1.f;
     c->no_touch_max_steps = 150; c->goal_score_terminal = 1;
     c->state_setter = RLG_SETTER_RANDOM; c->rand_ball_speed = c->rand_car_speed = c->cars_on_ground = 1;
+    host_mutators_default(c->mutators); c->mutators_set = 0;
 }
+
+void rlg_mutators_default(rlg_mutators* m) { if (m) host_mutators_default(*m); }
 
 int rlg_action_table(float* table_host) {
     if (!table_host) return fail(RLG_ERR_INVALID, "null table");

@@ -466,7 +466,7 @@ RL_HD inline void update_air_torque(CarS& c, CarW& w, const CarConsts& k, bool u
 }
 
 // ---- Car::_UpdateJump (Car.cpp:507-554) -------------------------------------------------------
-RL_HD inline void update_jump(CarS& c, CarW& w, const CarConsts& k, bool jumpPressed) {
+RL_HD inline void update_jump(CarS& c, CarW& w, const CarConsts& k, const SimCfg& cfg, bool jumpPressed) {
     const float dt = kTickTime;
     if (c.isOnGround && !c.isJumping) {
         if (c.hasJumped && c.jumpTime < C::JUMP_MIN_TIME + C::JUMP_RESET_TIME_PAD) {
@@ -479,12 +479,12 @@ RL_HD inline void update_jump(CarS& c, CarW& w, const CarConsts& k, bool jumpPre
         else c.isJumping = 0;
     } else if (c.isOnGround && jumpPressed) {
         c.isJumping = 1; c.jumpTime = 0;
-        V3 imp = c.rot.col(2) * C::JUMP_IMMEDIATE_FORCE * UU2BT * C::CAR_MASS;
+        V3 imp = c.rot.col(2) * cfg.mut.jumpImmediateForce * UU2BT * C::CAR_MASS;
         c.vel += imp * k.invMass;
     }
     if (c.isJumping) {
         c.hasJumped = 1;
-        V3 f = c.rot.col(2) * C::JUMP_ACCEL;
+        V3 f = c.rot.col(2) * cfg.mut.jumpAccel;
         if (c.jumpTime < C::JUMP_MIN_TIME) f *= 0.62f;
         w.force += f * UU2BT * C::CAR_MASS;
     }
@@ -534,7 +534,7 @@ RL_HD inline void update_double_jump_or_flip(CarS& c, const CarConsts& k, const 
         if (jumpPressed && c.airTimeSinceJump < C::DOUBLEJUMP_MAX_DELAY) {
             float inputMagnitude = fabsf(c.controls.yaw) + fabsf(c.controls.pitch) + fabsf(c.controls.roll);
             bool isFlipInput = inputMagnitude >= C::DODGE_DEADZONE;
-            bool canUse = !c.hasDoubleJumped && !c.hasFlipped;
+            bool canUse = (!c.hasDoubleJumped && !c.hasFlipped) || (isFlipInput ? cfg.mut.unlimitedFlips : cfg.mut.unlimitedDoubleJumps);  // Car.cpp:665-671
             if (c.isAutoFlipping) canUse = false;
             if (canUse) {
                 if (isFlipInput) {
@@ -640,7 +640,7 @@ RL_HD inline void vehicle_second(CarS& c, CarW& w, const CarConsts& k) {
 }
 
 // ---- Car::_UpdateBoost (Car.cpp:477-505) ------------------------------------------------------
-RL_HD inline void update_boost(CarS& c, CarW& w) {
+RL_HD inline void update_boost(CarS& c, CarW& w, const SimCfg& cfg) {
     const float dt = kTickTime;
     if (c.timeSpentBoosting > 0) {
         if (!c.controls.boost && c.timeSpentBoosting >= C::BOOST_MIN_TIME) c.timeSpentBoosting = 0;
@@ -649,22 +649,22 @@ RL_HD inline void update_boost(CarS& c, CarW& w) {
         c.timeSpentBoosting = dt;
     }
     if (c.boost > 0 && c.timeSpentBoosting > 0) {
-        c.boost = fmaxf_(c.boost - C::BOOST_USED_PER_SECOND * dt, 0.f);
-        w.force += (c.isOnGround ? C::BOOST_ACCEL_GROUND : C::BOOST_ACCEL_AIR) * UU2BT * c.rot.col(0) * C::CAR_MASS;
+        c.boost = fmaxf_(c.boost - cfg.mut.boostUsedPerSecond * dt, 0.f);
+        w.force += (c.isOnGround ? cfg.mut.boostAccelGround : cfg.mut.boostAccelAir) * UU2BT * c.rot.col(0) * C::CAR_MASS;
     }
     c.boost = fminf_(c.boost, C::BOOST_MAX);
 }
 
 // Car::SetState with a default CarState (Car.cpp:23-36, Car.h:17-101): wheel carry-over values and
 // controls are NOT touched, exactly like the reference.
-RL_HDI void car_set_default(CarS& c) {
+RL_HDI void car_set_default(CarS& c, float spawnBoost) {
     c.vel = V3(); c.angvel = V3();
     c.isOnGround = 1;
     for (int i = 0; i < 4; i++) c.wheelContact[i] = 0;
     c.hasJumped = c.hasDoubleJumped = c.hasFlipped = c.isFlipping = c.isJumping = 0;
     c.flipRelTorque = V3();
     c.jumpTime = c.flipTime = c.airTime = c.airTimeSinceJump = 0;
-    c.boost = C::BOOST_SPAWN_AMOUNT; c.timeSpentBoosting = 0;
+    c.boost = spawnBoost; c.timeSpentBoosting = 0;
     c.isSupersonic = 0; c.supersonicTime = 0; c.handbrakeVal = 0;
     c.isAutoFlipping = 0; c.autoFlipTimer = 0; c.autoFlipTorqueScale = 0;
     c.worldContactHas = 0; c.worldContactNormal = V3();
@@ -675,7 +675,7 @@ RL_HDI void car_set_default(CarS& c) {
     c.lastControls = Controls{0, 0, 0, 0, 0, 0, 0, 0};
 }
 // Car::Respawn (Car.cpp:43-56)
-RL_HD inline void car_respawn(CarS& c, int team, uint32_t rnd);
+RL_HD inline void car_respawn(CarS& c, int team, uint32_t rnd, float spawnBoost);
 
 // ---- Car::_PreTickUpdate (Car.cpp:58-131) -----------------------------------------------------
 // respawnRnd: a random word for Car::Respawn's spawn-slot pick; derived by the caller from the arena RNG state, the
@@ -707,7 +707,7 @@ RL_HD inline void car_pre_tick_a(CarS& c, const SimCfg& cfg, const MeshSet& ms, 
     c.controls.roll = clampf(c.controls.roll, -1.f, 1.f);
     if (c.isDemoed) {
         c.demoRespawnTimer = fmaxf_(c.demoRespawnTimer - kTickTime, 0.f);
-        if (c.demoRespawnTimer == 0) car_respawn(c, car_team(ci, cfg.spawnOpponents), respawnRnd);
+        if (c.demoRespawnTimer == 0) car_respawn(c, car_team(ci, cfg.spawnOpponents), respawnRnd, cfg.mut.carSpawnBoost);
     }
     w.invInertiaWorld = world_inertia(c.rot, k.invInertiaLocal);
     if (collect) {  // one BVH query for the hitbox and the four wheel rays (pose is final for this tick: only a respawn moves it)
@@ -731,14 +731,14 @@ RL_HD inline void car_pre_tick_b(CarS& c, const TickX& x, const SimCfg& cfg, con
     update_wheels(c, w, n, forwardSpeedUU);
     if (n < 3) update_air_torque(c, w, k, n == 0);
     else c.isFlipping = 0;
-    update_jump(c, w, k, jumpPressed);
+    update_jump(c, w, k, cfg, jumpPressed);
     update_auto_flip(c, k, jumpPressed);
     update_double_jump_or_flip(c, k, cfg, jumpPressed, forwardSpeedUU);
     if (c.controls.throttle != 0 && ((n > 0 && n < 4) || c.worldContactHas)) update_auto_roll(c, w, k, n);
     c.worldContactHas = 0;
     RL_PT(2);
     vehicle_second(c, w, k);
-    update_boost(c, w);
+    update_boost(c, w, cfg);
     RL_PT(3);
 }
 RL_HD inline void car_pre_tick(CarS& c, const TickX& x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, int ci, CarW& w, uint32_t respawnRnd) {
@@ -747,16 +747,16 @@ RL_HD inline void car_pre_tick(CarS& c, const TickX& x, const SimCfg& cfg, const
     car_pre_tick_b(c, x, cfg, ms, k, ci, w);
 }
 
-RL_HD inline void car_respawn(CarS& c, int team, uint32_t rnd) {
+RL_HD inline void car_respawn(CarS& c, int team, uint32_t rnd, float spawnBoost) {
     const float RX[4] = {-2304, -2688, 2304, 2688};
     const float RY = -4608;
     int idx = (int)(rnd % 4u);
-    car_set_default(c);
+    car_set_default(c, spawnBoost);
     V3 pos(RX[idx], RY * (team == 0 ? 1.f : -1.f), C::CAR_RESPAWN_Z);
     float yaw = (float)(3.14159265358979323846 / 2 + (team == 0 ? 0.0 : 3.14159265358979323846));
     c.pos = V3(pos.x * UU2BT, pos.y * UU2BT, pos.z * UU2BT);
     c.rot = angle_to_rotmat(yaw, 0.f, 0.f);
-    c.boost = C::BOOST_SPAWN_AMOUNT;
+    c.boost = spawnBoost;
 }
 
 // ---- Car::_PostTickUpdate + _FinishPhysicsTick (Car.cpp:133-193) ------------------------------

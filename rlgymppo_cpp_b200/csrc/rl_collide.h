@@ -115,7 +115,7 @@ RL_HD inline void on_car_ball(CollideCtx& x, int ci, Contact& cp) {
         V3 fwdAdj = carForward * dot(hitDir, carForward) * (1 - C::BALL_CAR_EXTRA_IMPULSE_FORWARD_SCALE);
         hitDir = safe_normalized(hitDir - fwdAdj);
         const float fx[4] = {0, 500.f, 2300.f, 4600.f}, fy[4] = {0.65f, 0.65f, 0.55f, 0.30f};
-        V3 addedVel = (hitDir * relSpeed) * curve(fx, fy, relSpeed) * 1.f;
+        V3 addedVel = (hitDir * relSpeed) * curve(fx, fy, relSpeed) * x.cfg->mut.ballHitExtraForceScale;
         car.hitExtraVel = addedVel;
         x.tx.car[ci].ballVelCache += addedVel * UU2BT;
     }
@@ -145,10 +145,11 @@ RL_HD inline void on_car_car(CollideCtx& x, int c1, int c2, Contact& cp) {
                 V3 local = tmul(wp - own.pos, own.rot);
                 bool bumper = (local.x * BT2UU) > C::BUMP_MIN_FORWARD_DIST;
                 if (bumper) {
-                    bool isDemo = s.isSupersonic != 0;
-                    if (isDemo) isDemo = car_team(c1, x.cfg->spawnOpponents) != car_team(c2, x.cfg->spawnOpponents);
+                    const Mut& mu = x.cfg->mut;
+                    bool isDemo = mu.demoMode == RLG_DEMO_ON_CONTACT ? true : (mu.demoMode == RLG_DEMO_DISABLED ? false : s.isSupersonic != 0);  // Arena.cpp:375-385
+                    if (isDemo && !mu.enableTeamDemos) isDemo = car_team(c1, x.cfg->spawnOpponents) != car_team(c2, x.cfg->spawnOpponents);
                     if (isDemo) {
-                        o.isDemoed = 1; o.demoRespawnTimer = C::DEMO_RESPAWN_TIME;
+                        o.isDemoed = 1; o.demoRespawnTimer = mu.respawnDelay;
                     } else {
                         bool groundHit = o.isOnGround != 0;
                         const float gx[3] = {0.f, 1400.f, 2200.f}, gy[3] = {5.f / 6.f, 1100.f, 1530.f};
@@ -156,11 +157,11 @@ RL_HD inline void on_car_car(CollideCtx& x, int c1, int c2, Contact& cp) {
                         const float ux[3] = {0.f, 1400.f, 2200.f}, uy[3] = {2.f / 6.f, 278.f, 417.f};
                         float baseScale = groundHit ? curve(gx, gy, speedTowards) : curve(ax, ay, speedTowards);
                         V3 hitUp = o.isOnGround ? o.rot.col(2) : V3(0, 0, 1);
-                        V3 bump = velDir * baseScale + hitUp * curve(ux, uy, speedTowards) * 1.f;
+                        V3 bump = velDir * baseScale + hitUp * curve(ux, uy, speedTowards) * mu.bumpForceScale;
                         x.tx.car[c2].velCache += bump * UU2BT;
                     }
                     s.carContactOtherId = c2 + 1;
-                    s.carContactCooldown = C::BUMP_COOLDOWN_TIME;
+                    s.carContactCooldown = mu.bumpCooldownTime;
                     // Gym's _BumpCallback (G/Gym.cpp:27-36): opponents only
                     if (x.firstTickOfStep && car_team(c1, x.cfg->spawnOpponents) != car_team(c2, x.cfg->spawnOpponents)) {
                         s.matchBumps++;
@@ -176,7 +177,7 @@ RL_HDI void on_car_world(CollideCtx& x, int ci, Contact& cp) {
     CarS& car = x.a->cars[ci];
     car.worldContactHas = 1;
     car.worldContactNormal = cp.normal;
-    cp.friction = C::CARWORLD_FRICTION; cp.restitution = C::CARWORLD_RESTITUTION;
+    cp.friction = x.cfg->mut.carWorldFriction; cp.restitution = x.cfg->mut.carWorldRestitution;
 }
 
 // btManifoldResult::addContactPoint (btManifoldResult.cpp:110-215) incl. the callback dispatch
@@ -190,7 +191,7 @@ RL_HD inline void manifold_add(CollideCtx& x, Manifold& m, V3 normalOnB, V3 poin
     cp.dist = depth;
     cp.special = 0;
     // combined material (btManifoldResult.cpp:63-82): min friction / max restitution against statics, product otherwise
-    if (m.a == 0 && m.b == -1) { cp.friction = fminf_(C::BALL_FRICTION, C::WORLD_FRICTION); cp.restitution = fmaxf_(C::BALL_RESTITUTION, C::WORLD_RESTITUTION); }
+    if (m.a == 0 && m.b == -1) { cp.friction = fminf_(x.cfg->mut.ballWorldFriction, C::WORLD_FRICTION); cp.restitution = fmaxf_(x.cfg->mut.ballWorldRestitution, C::WORLD_RESTITUTION); }
     else { cp.friction = 0.3f; cp.restitution = 0.1f; }
     int idx = m.n;
     if (idx == 4) idx = manifold_sort_cached(m, cp);

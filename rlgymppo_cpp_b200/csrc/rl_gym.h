@@ -49,17 +49,17 @@ RL_HDI void parse_actions(ArenaS& a, const SimCfg& cfg, const Tables& tb, const 
 
 // ---- GameEventTracker (R/Sim/GameEventTracker/GameEventTracker.cpp) -----------------------
 // Arena::IsBallProbablyGoingIn, soccar branch (R/Sim/Arena/Arena.cpp:827-863)
-RL_HD RL_NOINLINE inline bool ball_probably_going_in(const BallS& b, float maxTime, float extraMargin, int* goalTeamOut) {
+RL_HD RL_NOINLINE inline bool ball_probably_going_in(const BallS& b, const Mut& mu, float maxTime, float extraMargin, int* goalTeamOut) {
     V3 pos = ball_pos_uu(b), vel = ball_vel_uu(b);
     if (fabsf(vel.y) < kEps) return false;
     float scoreDirSgn = (float)sgn(vel.y);
-    float goalY = C::GOAL_THRESHOLD_Y * scoreDirSgn;
+    float goalY = mu.goalBaseThresholdY * scoreDirSgn;
     float distToGoal = fabsf(s_sub(pos.y, goalY));
     float timeToGoal = s_div(distToGoal, fabsf(vel.y));
     if (timeToGoal > maxTime) return false;
     // ballPos + ballVel*t + gravity*t*t/2 ; gravity = (0,0,-650)
-    float ex = s_add(s_add(pos.x, s_mul(vel.x, timeToGoal)), s_div(s_mul(s_mul(0.f, timeToGoal), timeToGoal), 2.f));
-    float ez = s_add(s_add(pos.z, s_mul(vel.z, timeToGoal)), s_div(s_mul(s_mul(C::GRAVITY_Z, timeToGoal), timeToGoal), 2.f));
+    float ex = s_add(s_add(pos.x, s_mul(vel.x, timeToGoal)), s_div(s_mul(s_mul(mu.gravityX, timeToGoal), timeToGoal), 2.f));
+    float ez = s_add(s_add(pos.z, s_mul(vel.z, timeToGoal)), s_div(s_mul(s_mul(mu.gravityZ, timeToGoal), timeToGoal), 2.f));
     const float APPROX_GOAL_HALF_WIDTH = 892.755f, APPROX_GOAL_HEIGHT = (float)642.775;
     float scoreMargin = s_add(s_mul(C::BALL_RADIUS, 0.1f), extraMargin);
     if (ez > APPROX_GOAL_HEIGHT + scoreMargin) return false;
@@ -102,7 +102,7 @@ RL_HDI void event_tracker_update(ArenaS& a, const SimCfg& cfg) {
     // default GameEventTrackerConfig (GameEventTracker.h:11-40); tick rate 120
     const float shotMinSpeed = 1750, predScoreExtraMargin = 0, shotEventCooldown = 1.0f, shotMinScoreTime = 2.0f;
     const int64_t goalMaxTouchTicks = 480, passMaxTouchTicks = 240, shotMinTouchDelayTicks = 36;
-    bool scored = is_ball_scored_y(s_mul(a.ball.pos.y, BT2UU));
+    bool scored = fabsf(s_mul(a.ball.pos.y, BT2UU)) > cfg.mut.goalBaseThresholdY + C::BALL_RADIUS;  // Arena::IsBallScored (Arena.cpp:949-957)
     int32_t cnt = a.ball.updateCounterLo;
     if (cnt > a.lastBallUpdateCount) {
         int64_t deltaTicks = (int64_t)cnt - a.lastBallUpdateCount;
@@ -122,7 +122,7 @@ RL_HDI void event_tracker_update(ArenaS& a, const SimCfg& cfg) {
                 float speedSq = s_add(s_add(s_mul(v.x, v.x), s_mul(v.y, v.y)), s_mul(v.z, v.z));  // Vec::LengthSq via btVector3::length2
                 if (speedSq >= shotMinSpeed * shotMinSpeed) {
                     int goalTeam = 0;
-                    if (ball_probably_going_in(a.ball, shotMinScoreTime, predScoreExtraMargin, &goalTeam)) {
+                    if (ball_probably_going_in(a.ball, cfg.mut, shotMinScoreTime, predScoreExtraMargin, &goalTeam)) {
                         int shooterTeam = 1 - goalTeam;
                         int shooter, passer;
                         if (get_shooter_passer(a, cfg, shooterTeam, shooter, true, passer,
@@ -140,7 +140,7 @@ RL_HDI void event_tracker_update(ArenaS& a, const SimCfg& cfg) {
                 }
             }
         } else {
-            bool willScore = ball_probably_going_in(a.ball, shotMinScoreTime, predScoreExtraMargin, nullptr);
+            bool willScore = ball_probably_going_in(a.ball, cfg.mut, shotMinScoreTime, predScoreExtraMargin, nullptr);
             if (!willScore) {
                 int saver, unused;
                 if (get_shooter_passer(a, cfg, a.ballShotGoalTeam, saver, false, unused, deltaTicks, 0)) a.cars[saver].matchSaves++;
@@ -396,7 +396,7 @@ RL_HDI void reset_to_kickoff(ArenaS& a, const SimCfg& cfg) {
         int i = nTeam[team]++;
         int s = order[i < 5 ? i : 4];
         CarS& car = a.cars[c];
-        car_set_default(car);
+        car_set_default(car, cfg.mut.carSpawnBoost);
         V3 pos(SX[s], SY[s], C::CAR_SPAWN_REST_Z);
         float yaw = SYAW[s];
         if (team == 1) { pos = V3(pos.x * -1.f, pos.y * -1.f, pos.z * 1.f); yaw = (float)((double)yaw + 3.14159265358979323846); }
@@ -434,7 +434,7 @@ RL_HDI void reset_to_random(ArenaS& a, const SimCfg& cfg) {
     }
     for (int ci = 0; ci < cfg.numCars; ci++) {
         CarS& car = a.cars[cfg.playerOrder[ci]];
-        car_set_default(car);
+        car_set_default(car, cfg.mut.carSpawnBoost);
         V3 p = rand_vec(a, V3(-X_MAX, -Y_MAX, CAR_Z_MIN), V3(X_MAX, Y_MAX, Z_MAX));
         V3 v, w;
         if (cfg.randCarSpeed) {

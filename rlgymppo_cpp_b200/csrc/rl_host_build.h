@@ -401,6 +401,19 @@ inline void host_build_tables(Tables& tb) {
     }
 }
 
+inline void host_mutators_default(rlg_mutators& m) {  // MutatorConfig(GameMode::SOCCAR): RLConst.h values
+    memset(&m, 0, sizeof(m));
+    m.gravity[2] = C::GRAVITY_Z;
+    m.car_mass = C::CAR_MASS; m.car_world_friction = C::CARWORLD_FRICTION; m.car_world_restitution = C::CARWORLD_RESTITUTION;
+    m.ball_mass = C::BALL_MASS; m.ball_max_speed = C::BALL_MAX_SPEED; m.ball_drag = C::BALL_DRAG;
+    m.ball_world_friction = C::BALL_FRICTION; m.ball_world_restitution = C::BALL_RESTITUTION;
+    m.jump_accel = C::JUMP_ACCEL; m.jump_immediate_force = C::JUMP_IMMEDIATE_FORCE;
+    m.boost_accel_ground = C::BOOST_ACCEL_GROUND; m.boost_accel_air = C::BOOST_ACCEL_AIR; m.boost_used_per_second = C::BOOST_USED_PER_SECOND;
+    m.respawn_delay = C::DEMO_RESPAWN_TIME; m.bump_cooldown_time = C::BUMP_COOLDOWN_TIME;
+    m.boost_pad_cooldown_big = C::PAD_COOLDOWN_BIG; m.boost_pad_cooldown_small = C::PAD_COOLDOWN_SMALL;
+    m.car_spawn_boost_amount = C::BOOST_SPAWN_AMOUNT; m.ball_hit_extra_force_scale = 1.f; m.bump_force_scale = 1.f;
+    m.ball_radius = C::BALL_RADIUS; m.goal_base_threshold_y = C::GOAL_THRESHOLD_Y;
+}
 inline void host_build_simcfg(const rlg_engine_cfg& c, SimCfg& s) {
     std::memset(&s, 0, sizeof(s));
     if (c.num_arenas <= 0) throw std::runtime_error("num_arenas must be > 0");
@@ -432,7 +445,27 @@ inline void host_build_simcfg(const rlg_engine_cfg& c, SimCfg& s) {
     s.stateSetter = c.state_setter; s.randBallSpeed = c.rand_ball_speed; s.randCarSpeed = c.rand_car_speed; s.carsOnGround = c.cars_on_ground;
     // reference player order = unordered_set<Car*> iteration order; for the small sets used this is descending id
     for (int i = 0; i < s.numCars; i++) s.playerOrder[i] = s.numCars - 1 - i;
-    s.ballDampFactor = powf(1.f - C::BALL_DRAG, kTickTime);                 // btRigidBody::applyDamping
+    rlg_mutators m;
+    host_mutators_default(m);
+    if (c.mutators_set) m = c.mutators;
+    if (m.car_mass != C::CAR_MASS || m.ball_mass != C::BALL_MASS || m.ball_radius != C::BALL_RADIUS)
+        throw std::runtime_error("mutators: car_mass, ball_mass and ball_radius must keep their defaults (not supported by the engine)");
+    if (m.demo_mode < 0 || m.demo_mode > 2) throw std::runtime_error("mutators: bad demo_mode");
+    if (!(m.ball_drag >= 0.f && m.ball_drag < 1.f)) throw std::runtime_error("mutators: ball_drag must be in [0, 1)");
+    Mut& u = s.mut;
+    u.gravityBT = V3(m.gravity[0] * UU2BT, m.gravity[1] * UU2BT, m.gravity[2] * UU2BT);
+    u.gravityX = m.gravity[0]; u.gravityZ = m.gravity[2];
+    u.carWorldFriction = m.car_world_friction; u.carWorldRestitution = m.car_world_restitution;
+    u.ballWorldFriction = m.ball_world_friction; u.ballWorldRestitution = m.ball_world_restitution;
+    u.ballMaxSpeed = m.ball_max_speed; u.jumpAccel = m.jump_accel; u.jumpImmediateForce = m.jump_immediate_force;
+    u.boostAccelGround = m.boost_accel_ground; u.boostAccelAir = m.boost_accel_air; u.boostUsedPerSecond = m.boost_used_per_second;
+    u.respawnDelay = m.respawn_delay; u.bumpCooldownTime = m.bump_cooldown_time;
+    u.padCooldownBig = m.boost_pad_cooldown_big; u.padCooldownSmall = m.boost_pad_cooldown_small;
+    u.carSpawnBoost = m.car_spawn_boost_amount; u.ballHitExtraForceScale = m.ball_hit_extra_force_scale; u.bumpForceScale = m.bump_force_scale;
+    u.goalBaseThresholdY = m.goal_base_threshold_y;
+    u.unlimitedFlips = m.unlimited_flips != 0; u.unlimitedDoubleJumps = m.unlimited_double_jumps != 0;
+    u.demoMode = m.demo_mode; u.enableTeamDemos = m.enable_team_demos != 0;
+    s.ballDampFactor = powf(1.f - m.ball_drag, kTickTime);                  // btRigidBody::applyDamping
     s.flipZDampFactor = powf(1 - C::FLIP_Z_DAMP_120, kTickTime / (1 / 120.f));  // Car.cpp:753
 }
 

@@ -226,7 +226,17 @@ RL_HDI float rng_float(ArenaS& a, float lo, float hi) {
 
 // static configuration shared by all arenas of an engine (kernel parameter, by value)
 struct RewardTerm { int32_t kind; float weight; float params[11]; };
+struct Mut {  // MutatorConfig as the tick reads it (rlg_mutators; Bullet units where the use site wants them)
+    V3 gravityBT;               // world gravity, uu/s^2 * UU2BT
+    float gravityX, gravityZ;   // uu/s^2 (Arena::IsBallProbablyGoingIn)
+    float carWorldFriction, carWorldRestitution, ballWorldFriction, ballWorldRestitution;
+    float ballMaxSpeed, jumpAccel, jumpImmediateForce, boostAccelGround, boostAccelAir, boostUsedPerSecond;
+    float respawnDelay, bumpCooldownTime, padCooldownBig, padCooldownSmall, carSpawnBoost, ballHitExtraForceScale, bumpForceScale;
+    float goalBaseThresholdY;
+    int32_t unlimitedFlips, unlimitedDoubleJumps, demoMode, enableTeamDemos;
+};
 struct SimCfg {
+    Mut mut;
     int32_t numArenas, numCars, spawnOpponents, tickSkip;
     int32_t carPreset;  // rlg_engine_cfg.car_preset
     int32_t obsKind, obsMaxPlayers, obsSize;

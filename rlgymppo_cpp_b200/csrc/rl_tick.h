@@ -81,7 +81,7 @@ RL_HD inline void pads_post_tick(ArenaS& a, const SimCfg& cfg, const uint64_t* h
             float add = pad_is_big(i) ? C::PAD_BOOST_BIG : C::PAD_BOOST_SMALL;
             c.boost = fminf_(c.boost + add, C::BOOST_MAX);
             active &= ~(1ULL << i);
-            a.pads.cooldown[i] = pad_is_big(i) ? C::PAD_COOLDOWN_BIG : C::PAD_COOLDOWN_SMALL;
+            a.pads.cooldown[i] = pad_is_big(i) ? cfg.mut.padCooldownBig : cfg.mut.padCooldownSmall;
             cooling |= 1ULL << i;
         }
         pad_set_locked(a.pads, i, lockedCar + 1);
@@ -156,7 +156,7 @@ RL_HD inline void tick_p1_car_begin(ArenaS& a, TickX x, const SimCfg& cfg, const
     CarS& car = a.cars[c];
     CarX& o = x.car[c];
     car_pre_tick_b(car, x, cfg, ms, k, c, w);
-    if (!o.noResponse) w.force += V3(0.f * UU2BT, 0.f * UU2BT, C::GRAVITY_Z * UU2BT) * C::CAR_MASS;  // applyGravity on active bodies
+    if (!o.noResponse) w.force += cfg.mut.gravityBT * C::CAR_MASS;  // applyGravity on active bodies
     o.force = w.force; o.torque = w.torque;
     V3 center = car.pos + car.rot * k.hitboxOffset;
     V3 ext(dot(vabs(car.rot.r[0]), k.halfExt), dot(vabs(car.rot.r[1]), k.halfExt), dot(vabs(car.rot.r[2]), k.halfExt));
@@ -304,7 +304,7 @@ RL_HD inline void tick_p2_solve(ArenaS& a, TickX x, const SimCfg& cfg, const Car
     x.h->nPair = cp.n;
     RL_PT(10);
 
-    const V3 gImp = V3(0.f * UU2BT, 0.f * UU2BT, C::GRAVITY_Z * UU2BT) * C::BALL_MASS;
+    const V3 gImp = cfg.mut.gravityBT * C::BALL_MASS;
 #ifdef RL_DEBUG_CONTACTS
     {   // every contact of the tick in the reference's manifold order (host debugging only)
         ContactSet& cs = g_dbg_contacts; cs.n = 0; cs.overflow = 0;
@@ -388,7 +388,7 @@ RL_HD inline void tick_p2_solve(ArenaS& a, TickX x, const SimCfg& cfg, const Car
     for (int c = 0; c < P; c++) ballVelCache += x.car[c].ballVelCache;
     if (!is_zero(ballVelCache)) a.ball.vel += ballVelCache;
     {
-        const float maxSpeed = C::BALL_MAX_SPEED * UU2BT;
+        const float maxSpeed = cfg.mut.ballMaxSpeed * UU2BT;
         if (len2(a.ball.vel) > maxSpeed * maxSpeed) a.ball.vel = normalized(a.ball.vel) * maxSpeed;
         if (len2(a.ball.angvel) > C::BALL_MAX_ANG_SPEED * C::BALL_MAX_ANG_SPEED) a.ball.angvel = normalized(a.ball.angvel) * C::BALL_MAX_ANG_SPEED;
     }

@@ -84,6 +84,26 @@ def check_single_tick_run(groups, set_state, tick, get_state, allow_contact_frac
 CAR_PRESETS = ((1, "dominus"), (2, "plank"), (3, "breakout"), (4, "hybrid"), (5, "merc"))
 
 
+def apply_test_mutators(cfg):
+    """A MutatorConfig that differs from the default in every field the engine honours (MutatorConfig.h:16-72)."""
+    m = abi.default_mutators()
+    m.gravity[0], m.gravity[1], m.gravity[2] = 20.0, -15.0, -380.0
+    m.car_world_friction, m.car_world_restitution = 0.45, 0.15
+    m.ball_max_speed, m.ball_drag, m.ball_world_friction, m.ball_world_restitution = 3500.0, 0.06, 0.5, 0.75
+    m.jump_accel, m.jump_immediate_force = 1800.0, 350.0
+    m.boost_accel_ground, m.boost_accel_air, m.boost_used_per_second = 1400.0, 1500.0, 20.0
+    m.respawn_delay, m.bump_cooldown_time = 1.0, 0.1
+    m.boost_pad_cooldown_big, m.boost_pad_cooldown_small = 3.0, 1.5
+    m.car_spawn_boost_amount = 60.0
+    m.ball_hit_extra_force_scale, m.bump_force_scale = 1.6, 0.5
+    m.unlimited_flips, m.unlimited_double_jumps = 1, 1
+    m.demo_mode, m.enable_team_demos = 1, 1  # ON_CONTACT
+    m.goal_base_threshold_y = 5000.0
+    cfg.mutators = m
+    cfg.mutators_set = 1
+    return cfg
+
+
 def gym_cfgs():
     c = abi.default_cfg(1, 1)
     for k in range(11):

@@ -157,16 +157,18 @@ def scenarios_1v1(arena):
     return out
 
 
-def random_play(team, nsteps, seed, car_preset=0):
+def random_play(team, nsteps, seed, car_preset=0, mutate=None):
     """Random DiscreteAction play from RandomState resets: the workload distribution of the benchmark."""
     cfg = abi.default_cfg(num_arenas=1, team_size=team)
     cfg.car_preset = car_preset
+    if mutate is not None:
+        mutate(cfg)
     g = refsim.RefGym(cfg)
     refsim.seed(seed)
     rng = np.random.default_rng(seed)
     table = refsim.action_table()
     P = 2 * team
-    arena = refsim.RefArena(team, True, car_preset=car_preset)
+    arena = refsim.RefArena(cfg=cfg)
     chunks = []
     for ep in range(nsteps):
         g.reset()
@@ -312,6 +314,19 @@ def ppo():
     save("ppo_reference", out)
 
 
+def mutators():
+    """python tests/golden/make_golden.py mutators — random play under a non-default MutatorConfig (common.mutated_cfg)"""
+    import common
+
+    for team, n, seed in ((1, 6, 51), (2, 3, 52)):
+        chunks = random_play(team, n, seed, mutate=common.apply_test_mutators)
+        flat = {}
+        for i, d in enumerate(chunks):
+            for k, v in d.items():
+                flat[f"ep{i}/{k}"] = v
+        save(f"tick_random_{team}v{team}_mutators", flat)
+
+
 def presets():
     """python tests/golden/make_golden.py presets — random play with the five non-Octane CarConfigs"""
     for preset, name in ((1, "dominus"), (2, "plank"), (3, "breakout"), (4, "hybrid"), (5, "merc")):
@@ -328,6 +343,8 @@ if __name__ == "__main__":
         extra()
     elif len(sys.argv) > 1 and sys.argv[1] == "presets":
         presets()
+    elif len(sys.argv) > 1 and sys.argv[1] == "mutators":
+        mutators()
     elif len(sys.argv) > 1 and sys.argv[1] == "ppo":
         ppo()
     else:

@@ -47,6 +47,8 @@ def test_default_cfg_matches_examplemain(lib):
                 assert c.reward_terms[i].kind == d.reward_terms[i].kind
                 assert c.reward_terms[i].weight == d.reward_terms[i].weight
                 assert list(c.reward_terms[i].params) == list(d.reward_terms[i].params)
+        elif f == "mutators":  # MutatorConfig(SOCCAR) defaults, byte for byte
+            assert bytes(c.mutators) == bytes(d.mutators)
         else:
             assert getattr(c, f) == getattr(d, f), f
 

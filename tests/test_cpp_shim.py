@@ -55,13 +55,13 @@ def test_shim_rejects_missing_meshes(example_bin, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("custom", [False, True])
+@pytest.mark.parametrize("custom", [False, True, "mutators"])
 def test_examplemain_collects_on_gpu(example_bin, mesh_dir, custom):
-    args = [example_bin, mesh_dir, "3"] + (["--custom-setter"] if custom else [])
+    args = [example_bin, mesh_dir, "3"] + (["--custom-setter"] if custom is True else ["--low-gravity"] if custom == "mutators" else [])
     r = subprocess.run(args, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
     last = json.loads(r.stdout.strip().splitlines()[-1])
-    assert last["arenas"] == 16 * 24 and last["custom_setter"] == custom
+    assert last["arenas"] == 16 * 24 and last["custom_setter"] == (custom is True)
     assert last["steps_per_second"] > 1000
     assert -5 < last["mean_step_reward"] < 5
     assert r.stdout.count("Timesteps Collected 100608") == 3  # ceil(100000 / 768) = 131 env-steps x 768 players

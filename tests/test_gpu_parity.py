@@ -22,8 +22,11 @@ def torch_cuda():
 
 def _engine(team, n=1, **kw):
     cfg = abi.default_cfg(num_arenas=n, team_size=team)
+    mutate = kw.pop("mutate", None)
     for k, v in kw.items():
         setattr(cfg, k, v)
+    if mutate is not None:
+        mutate(cfg)
     return engine.Engine(cfg)
 
 
@@ -73,6 +76,24 @@ def test_single_tick_random_play_car_presets(preset, name, torch_cuda):
     res = common.check_single_tick_run(common.load_tick_file(f"tick_random_1v1_{name}"), r.set_state, r.tick, r.get_state,
                                        allow_contact_frac=0.08)
     print(res)
+
+
+@pytest.mark.parametrize("team", [1, 2])
+def test_single_tick_random_play_mutators(team, torch_cuda):
+    """Non-default MutatorConfig (every honoured field changed, common.apply_test_mutators) against the reference's
+    trajectories under the same mutators, same tolerances."""
+    r = _TickRunner(team, torch_cuda, mutate=common.apply_test_mutators)
+    res = common.check_single_tick_run(common.load_tick_file(f"tick_random_{team}v{team}_mutators"), r.set_state, r.tick, r.get_state,
+                                       allow_contact_frac=0.08)
+    print(res)
+
+
+def test_mutators_unsupported_rejected():
+    cfg = abi.default_cfg(num_arenas=1, team_size=1)
+    cfg.mutators_set = 1
+    cfg.mutators.ball_radius = 120.0
+    with pytest.raises(Exception):
+        engine.Engine(cfg)
 
 
 @pytest.mark.parametrize("name,cfg", list(common.gym_cfgs()))

@@ -8,9 +8,11 @@ from hostsim import hostsim
 from rlgymppo_cpp_b200 import abi
 
 
-def _runner(team, car_preset=0):
+def _runner(team, car_preset=0, mutate=None):
     cfg = abi.default_cfg(num_arenas=1, team_size=team)
     cfg.car_preset = car_preset
+    if mutate is not None:
+        mutate(cfg)
     hs = hostsim.HostSim(cfg)
     return (lambda c, b, p, t: hs.set_state(0, c, b, p, t)), (lambda u: hs.tick(0, u, 1)), (lambda: hs.get_state(0))
 
@@ -40,6 +42,37 @@ def test_single_tick_random_play_car_presets(preset, name):
     s, t, g = _runner(1, preset)
     res = common.check_single_tick_run(common.load_tick_file(f"tick_random_1v1_{name}"), s, t, g, allow_contact_frac=0.08)
     print(res)
+
+
+@pytest.mark.parametrize("team", [1, 2])
+def test_single_tick_random_play_mutators(team):
+    """A MutatorConfig that differs from the soccar default in every honoured field (MutatorConfig.h:16-72; gravity with x/y
+    components, drag, frictions / restitutions, jump and boost accelerations, pad cooldowns, demo-on-contact with team demos,
+    unlimited flips): random play recorded from the reference under common.apply_test_mutators."""
+    s, t, g = _runner(team, mutate=common.apply_test_mutators)
+    res = common.check_single_tick_run(common.load_tick_file(f"tick_random_{team}v{team}_mutators"), s, t, g, allow_contact_frac=0.08)
+    print(res)
+
+
+def test_mutators_default_is_identity():
+    """mutators_set = 1 with rlg_mutators_default values is the same engine as mutators_set = 0."""
+    import ctypes as C
+
+    from rlgymppo_cpp_b200 import engine
+
+    m = abi.Mutators()
+    engine.load_library().rlg_mutators_default(C.byref(m))
+    d = abi.default_mutators()
+    assert bytes(m) == bytes(d)
+
+
+@pytest.mark.parametrize("field,value", [("car_mass", 200.0), ("ball_mass", 20.0), ("ball_radius", 100.0), ("demo_mode", 7)])
+def test_mutators_unsupported_rejected(field, value):
+    cfg = abi.default_cfg(num_arenas=1, team_size=1)
+    cfg.mutators_set = 1
+    setattr(cfg.mutators, field, type(getattr(cfg.mutators, field))(value))
+    with pytest.raises(Exception):
+        hostsim.HostSim(cfg)
 
 
 @pytest.mark.parametrize("name,cfg", list(common.gym_cfgs()))
