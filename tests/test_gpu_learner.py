@@ -113,3 +113,57 @@ def test_render_sender_document_from_engine():
     for p in st["players"]:
         assert np.allclose(p["phys"]["pos"], cars[0][p["car_id"] - 1]["pos"]) and 0 <= p["boost_amount"] <= 1
     rs.send(arena=3)  # UDP, nobody needs to listen
+
+
+def test_infer_unit_policy_and_critic_from_a_checkpoint(tmp_path):
+    """InferUnit (InferUnit.cpp:11-138) on the engine: a PPO_POLICY.lt / PPO_CRITIC.lt pair saved in the reference's format,
+    loaded back, evaluated on the engine's current obs rows through the tcgen05 inference kernel, against torch fp32."""
+    import torch
+
+    from rlgymppo_cpp_b200 import checkpoint, engine, infer_unit
+    from rlgymppo_cpp_b200.learner import make_mlp
+
+    e = engine.Engine(abi.default_cfg(num_arenas=64, team_size=1))
+    e.reset()
+    e.step_host(np.random.default_rng(1).integers(0, 90, size=e.A * e.P).astype(np.int32))
+    torch.manual_seed(5)
+    sizes = [128, 128]
+    pol, cri = make_mlp(e.obs_size, sizes, 90), make_mlp(e.obs_size, sizes, 1)
+    checkpoint.save_seq(pol, str(tmp_path / "PPO_POLICY.lt"))
+    checkpoint.save_seq(cri, str(tmp_path / "PPO_CRITIC.lt"))
+    up = infer_unit.InferUnit(e, str(tmp_path / "PPO_POLICY.lt"), True, e.obs_size, sizes)
+    uc = infer_unit.InferUnit(e, str(tmp_path / "PPO_CRITIC.lt"), False, e.obs_size, sizes)
+    obs = up.get_obs()
+    assert obs.shape == (e.A * e.P, e.obs_size)
+    with torch.no_grad():
+        logits = pol(torch.from_numpy(obs)).numpy()
+        values = cri(torch.from_numpy(obs)).numpy().reshape(-1)
+    # deterministic = argmax (ties / TF32 near-ties: the chosen logit is within 2e-3 of the best)
+    idx = up.infer_policy_indices(True)
+    assert idx.shape == (e.A * e.P,) and idx.min() >= 0 and idx.max() < 90
+    assert np.all(logits.max(1) - logits[np.arange(len(idx)), idx] <= 2e-3 * np.maximum(1, np.abs(logits).max(1)))
+    acts = up.infer_policy_all(True)
+    assert acts.shape == (e.A * e.P, 8) and np.array_equal(acts, engine.action_table()[idx])
+    # the same rows handed in by the caller, and one row alone
+    assert np.array_equal(up.infer_policy_indices(True, obs=obs[:10]), idx[:10])
+    assert np.array_equal(up.infer_policy_single(7, True), acts[7])
+    # sampling: indices in range, not all equal to the argmax at a high temperature
+    samp = up.infer_policy_indices(False, temperature=5.0)
+    assert samp.min() >= 0 and samp.max() < 90 and (samp != idx).mean() > 0.5
+    # distribution of one row
+    p = up.infer_policy_single_distrib(3, temperature=2.0)
+    ref = torch.softmax(torch.from_numpy(logits[3]) / 2.0, -1).clamp(1e-11, 1).numpy()
+    assert p.shape == (90,) and np.allclose(p, ref, rtol=5e-3, atol=1e-6) and abs(p.sum() - 1) < 1e-4
+    # critic
+    v = uc.infer_critic_all()
+    assert np.allclose(v, values, rtol=2e-3, atol=2e-3)
+    assert abs(uc.infer_critic_single(5) - values[5]) < 2e-3 * max(1, abs(values[5]))
+    # ASSERT_RIGHT_TYPE
+    with pytest.raises(engine.EngineError, match="created to infer the critic"):
+        uc.infer_policy_all(True)
+    with pytest.raises(engine.EngineError, match="created to infer the policy"):
+        up.infer_critic_all()
+    # a model of another architecture is refused (InferUnit.cpp:31-39)
+    with pytest.raises(RuntimeError):
+        infer_unit.InferUnit(e, str(tmp_path / "PPO_POLICY.lt"), True, e.obs_size, [64, 64])
+    up.close(); uc.close()
