@@ -240,7 +240,8 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     t_wall0 = time.perf_counter()
     for i in range(K):
-        flush.fill_(i & 255)  # L2 flush between timed iterations (torch stream)
+        if not args.no_l2_flush:
+            flush.fill_(i & 255)  # L2 flush between timed iterations (torch stream)
         torch.cuda.synchronize()
         with torch.cuda.stream(ext):
             starts[i].record(ext)
@@ -320,7 +321,7 @@ def run_ours(args, rank, local_rank, world):
                                    "on-device policy (256x256x256) + critic inference, sampling, trajectory ring, GAE; placeholder mesh set v1; "
                                    f"one bench step = one collect of {T} env-steps over every arena + GAE",
                        "arenas_per_gpu": A, "players_per_arena": P, "obs_size": OBS, "tick_skip": 8, "env_steps_per_bench_step": T,
-                       "player_steps_per_bench_step": world * A * P * T, "l2_flush_between_steps": True,
+                       "player_steps_per_bench_step": world * A * P * T, "l2_flush_between_steps": not args.no_l2_flush,
                        "state_bytes_per_arena": S, "mlp_dtype": "tf32 inputs, fp32 accumulate (tcgen05)",
                        "parallelism": f"arena-sharded x{world}, no data-path collective"},
             "clocks": clocks,
@@ -395,6 +396,8 @@ def main():
     ap.add_argument("--env-steps", type=int, default=4, help="env-steps per bench step (one collect call; cfg1's 100k timesteps/iteration ~ 4 x 32768)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ppo", action="store_true", help="skip the PPO iteration-time measurement")
+    ap.add_argument("--no-l2-flush", action="store_true", help="profiling only (ncu DRAM-traffic capture of the kernel alone: the flush buffer's "
+                    "dirty lines are written back during the next kernels and would be counted as theirs); a bench line needs the flush")
     ap.add_argument("--team", type=int, default=1, help="players per team (sweep only: the headline metric is quoted on 1v1)")
     ap.add_argument("--padded-obs", action="store_true", help="DefaultOBSPadded(3) (sweep only: BASELINE configs[2])")
     ap.add_argument("--zero-sum", action="store_true", help="ZeroSumReward(teamSpirit 0.3) around the reward set (sweep only)")

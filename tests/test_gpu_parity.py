@@ -176,6 +176,46 @@ def test_full_size_properties(torch_cuda):
     assert np.allclose(np.linalg.norm(fw, axis=2), 1, atol=1e-3)
 
 
+@pytest.mark.parametrize("team", [1, 2])
+def test_sharded_engines_equal_one_engine(team, torch_cuda):
+    """arenas are independent and the per-arena RNG streams are keyed by the GLOBAL arena id
+    (rlg_engine_cfg.arena_id_base), so a pool split over ranks gives bit-identical obs / rewards / done flags to one engine
+    holding all arenas - at ragged sizes (not multiples of the warp or SM count, a 1-arena shard), with many auto-resets."""
+    torch = torch_cuda
+    sizes = [100, 1, 112]
+    A = sum(sizes)
+
+    def mk(n, base):
+        cfg = abi.default_cfg(num_arenas=n, team_size=team)
+        cfg.no_touch_max_steps = 5  # frequent RandomState resets: the reset RNG is what could depend on the sharding
+        cfg.arena_id_base = base
+        return engine.Engine(cfg)
+
+    whole = mk(A, 0)
+    shards, base = [], 0
+    for n in sizes:
+        shards.append(mk(n, base))
+        base += n
+    whole.reset()
+    for sh in shards:
+        sh.reset()
+    P = whole.P
+    rng = np.random.default_rng(team)
+    n_done = 0
+    for s in range(24):
+        acts = rng.integers(0, 90, size=A * P).astype(np.int32)
+        o, r, d = whole.step_host(acts)
+        lo = 0
+        for sh, n in zip(shards, sizes):
+            o2, r2, d2 = sh.step_host(acts[lo * P:(lo + n) * P])
+            assert np.array_equal(o[lo * P:(lo + n) * P].view(np.uint32), o2.view(np.uint32)), (s, lo)
+            assert np.array_equal(r[lo * P:(lo + n) * P].view(np.uint32), r2.view(np.uint32)), (s, lo)
+            assert np.array_equal(d[lo:lo + n], d2), (s, lo)
+            lo += n
+        n_done += int(d.sum())
+    assert n_done > A  # every arena was re-set at least once on average
+
+
 def test_step_host_matches_device_path(torch_cuda):
     torch = torch_cuda
     cfg = abi.default_cfg(num_arenas=256, team_size=1)

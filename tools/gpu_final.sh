@@ -5,6 +5,9 @@ mkdir -p gpurun_out
 timeout 900 python bench.py --steps 50 --warmup 10 > gpurun_out/bench_$tag.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 timeout 600 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/bench_reference_$tag.json 2> gpurun_out/bench_ref.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_$tag.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-ppo > gpurun_out/ncu_bench.log 2>&1
+# DRAM bytes of k_roles alone (no L2 flush: the flush buffer's write-back would be attributed to the kernel) and with the bench's flush
+timeout 300 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:k_roles -s 60 -c 8 --csv --log-file gpurun_out/traffic_noflush_$tag.csv python bench.py --steps 10 --warmup 10 --no-cpu-baseline --no-ppo --no-l2-flush > /dev/null 2>&1
+timeout 300 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:k_roles -s 60 -c 8 --csv --log-file gpurun_out/traffic_flush_$tag.csv python bench.py --steps 10 --warmup 10 --no-cpu-baseline --no-ppo > /dev/null 2>&1
 timeout 800 ncu --set full --clock-control none --import-source on -k regex:k_roles -s 70 -c 1 -o gpurun_out/prof_k_roles_$tag -f python bench.py --steps 20 --warmup 10 --no-cpu-baseline --no-ppo > gpurun_out/ncu_full.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_mlp_infer -s 40 -c 1 -o gpurun_out/prof_k_mlp_$tag -f python bench.py --steps 8 --warmup 5 --no-cpu-baseline --no-ppo > gpurun_out/ncu_full_mlp.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_gemm_tma -s 5 -c 1 -o gpurun_out/prof_k_gemm_$tag -f python tools/gemm_bench.py > gpurun_out/ncu_gemm.log 2>&1
