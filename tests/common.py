@@ -63,6 +63,15 @@ def check_single_tick_run(groups, set_state, tick, get_state, allow_contact_frac
             set_state(cars0, ball0, pads0, tick0)
             tick(g["controls"][t])
             cars1, ball1, pads1, tick1 = get_state()
+            # Car::Respawn picks one of the team's four respawn spots with the global RNG (Car.cpp:43-56, RLConst.h
+            # CAR_RESPAWN_LOCATIONS): the engine's per-arena RNG differs by construction, so on the tick a car respawns its spot
+            # is checked for membership and the reference's x is taken for the comparison (y, z, yaw are the same for all four)
+            resp = (g["cars"][t]["is_demoed"] != 0) & (g["cars"][t + 1]["is_demoed"] == 0)
+            if resp.any():
+                cars1 = cars1.copy()
+                for ci in np.nonzero(resp)[0]:
+                    assert min(abs(abs(float(cars1["pos"][ci][0])) - v) for v in (2304.0, 2688.0)) < 1e-2, (gname, t, cars1["pos"][ci])
+                    cars1["pos"][ci][0] = g["cars"][t + 1]["pos"][ci][0]
             e = phys_err(g["cars"][t + 1], g["ball"][t + 1:t + 2], cars1, ball1)
             total += 1
             flags_ok = all(np.array_equal(g["cars"][t + 1][f] != 0, cars1[f] != 0) for f in FLAGS)

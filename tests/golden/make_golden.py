@@ -327,6 +327,52 @@ def mutators():
         save(f"tick_random_{team}v{team}_mutators", flat)
 
 
+def mutator_scenarios():
+    """python tests/golden/make_golden.py mutator_scenarios — the scripted 1v1 scenarios (bumps, demos, ball hits, pads, jumps) and
+    two mutator-specific ones, recorded from the reference under common.apply_test_mutators."""
+    import common
+
+    cfg = common.apply_test_mutators(abi.default_cfg(num_arenas=1, team_size=1))
+    arena = refsim.RefArena(cfg=cfg)
+    sc = scenarios_1v1(arena)
+    # unlimitedFlips: a second dodge in the same jump (Car.cpp:665-671)
+    cars, ball, pads = base()
+    cars["pos"][0] = (0, -2000, 17); cars["pos"][1] = (1000, 2000, 17); yaw_rot(cars, 0, 1.0); yaw_rot(cars, 1, -2.0)
+
+    def flips(t):
+        c = make_controls(2, throttle=1)
+        c["jump"] = 1 if (t < 10 or (30 <= t < 32) or (75 <= t < 77) or (120 <= t < 122)) else 0
+        c["pitch"] = -1 if (30 <= t < 40 or 120 <= t < 130) else 0
+        c["yaw"] = 1 if 75 <= t < 85 else 0
+        return c
+    sc["unlimited_flips"] = record(arena, cars, ball, pads, flips, 220)
+    flat = {}
+    for name, d in sc.items():
+        for k, v in d.items():
+            flat[f"{name}/{k}"] = v
+    save("tick_scenarios_1v1_mutators", flat)
+    # enableTeamDemos + DemoMode::ON_CONTACT: a slow bump between team mates demolishes (Arena.cpp:375-391), 2v2
+    cfg2 = common.apply_test_mutators(abi.default_cfg(num_arenas=1, team_size=2))
+    arena2 = refsim.RefArena(cfg=cfg2)
+    out = {}
+    for name, victim in (("team_mate_demo", 2), ("opponent_demo", 1)):  # car ids 1, 3 are blue (Gym.cpp:46-50 add order)
+        cars, ball, pads = base(4)
+        cars["pos"][0] = (0, -800, 17); yaw_rot(cars, 0, np.pi / 2); cars["vel"][0] = (0, 900, 0)
+        cars["pos"][victim] = (10, 300, 17); yaw_rot(cars, victim, 0.0)
+        ball["pos"][0] = (2500, 0, 93.15)
+
+        def ram(t):
+            c = make_controls(4)
+            c["throttle"][0] = 1
+            return c
+        out[name] = record(arena2, cars, ball, pads, ram, 260)
+    flat = {}
+    for name, d in out.items():
+        for k, v in d.items():
+            flat[f"{name}/{k}"] = v
+    save("tick_scenarios_2v2_mutators", flat)
+
+
 def presets():
     """python tests/golden/make_golden.py presets — random play with the five non-Octane CarConfigs"""
     for preset, name in ((1, "dominus"), (2, "plank"), (3, "breakout"), (4, "hybrid"), (5, "merc")):
@@ -345,6 +391,8 @@ if __name__ == "__main__":
         presets()
     elif len(sys.argv) > 1 and sys.argv[1] == "mutators":
         mutators()
+    elif len(sys.argv) > 1 and sys.argv[1] == "mutator_scenarios":
+        mutator_scenarios()
     elif len(sys.argv) > 1 and sys.argv[1] == "ppo":
         ppo()
     else:

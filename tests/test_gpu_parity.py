@@ -88,6 +88,15 @@ def test_single_tick_random_play_mutators(team, torch_cuda):
     print(res)
 
 
+def test_single_tick_scenarios_mutators(torch_cuda):
+    """The scripted scenarios under the test mutators (demolition on contact, 1 s respawn, team-mate demolition, pad cooldowns,
+    ball-hit scale, repeated flips) against the reference's recordings."""
+    r = _TickRunner(1, torch_cuda, mutate=common.apply_test_mutators)
+    print(common.check_single_tick_run(common.load_tick_file("tick_scenarios_1v1_mutators"), r.set_state, r.tick, r.get_state))
+    r = _TickRunner(2, torch_cuda, mutate=common.apply_test_mutators)
+    print(common.check_single_tick_run(common.load_tick_file("tick_scenarios_2v2_mutators"), r.set_state, r.tick, r.get_state))
+
+
 def test_mutators_unsupported_rejected():
     cfg = abi.default_cfg(num_arenas=1, team_size=1)
     cfg.mutators_set = 1

@@ -54,6 +54,15 @@ def test_single_tick_random_play_mutators(team):
     print(res)
 
 
+def test_single_tick_scenarios_mutators():
+    """The scripted scenarios under the test mutators: demolition on contact at bump speed, 1 s respawn with 60 boost, team-mate
+    demolition (2v2), pad cooldowns of 1.5 / 3 s, ball hits with the extra-impulse scale, repeated flips in one jump."""
+    s, t, g = _runner(1, mutate=common.apply_test_mutators)
+    print(common.check_single_tick_run(common.load_tick_file("tick_scenarios_1v1_mutators"), s, t, g))
+    s, t, g = _runner(2, mutate=common.apply_test_mutators)
+    print(common.check_single_tick_run(common.load_tick_file("tick_scenarios_2v2_mutators"), s, t, g))
+
+
 def test_mutators_default_is_identity():
     """mutators_set = 1 with rlg_mutators_default values is the same engine as mutators_set = 0."""
     import ctypes as C
