@@ -81,7 +81,7 @@ __global__ void k_init(uint32_t* state, SimCfg cfg, int nwords, uint64_t seed, u
     int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= cfg.numArenas) return;
     ArenaS s;
-    arena_init(s, cfg.numCars, seed, base + (uint64_t)a);
+    arena_init(s, cfg.numCars, seed, base + (uint64_t)a, cfg.mut.carSpawnBoost);
     store_arena(s, state, cfg.numArenas, a, nwords);
 }
 

@@ -89,7 +89,7 @@ RL_HDI void pad_to_pod(rlg_pad_state& o, const PadsS& p, int i) {
 }
 
 // fresh arena: what Arena::Create + AddCar leaves behind (cars respawned, wheel carry-over zero)
-RL_HD inline void arena_init(ArenaS& a, int numCars, uint64_t seed, uint64_t globalArenaId) {
+RL_HD inline void arena_init(ArenaS& a, int numCars, uint64_t seed, uint64_t globalArenaId, float spawnBoost) {
     uint32_t* w = (uint32_t*)&a;
     for (size_t i = 0; i < sizeof(ArenaS) / 4; i++) w[i] = 0;
     uint64_t s = seed * 0x9E3779B97F4A7C15ULL + globalArenaId * 0xD1B54A32D192ED03ULL + 0x2545F4914F6CDD1DULL;
@@ -103,7 +103,7 @@ RL_HD inline void arena_init(ArenaS& a, int numCars, uint64_t seed, uint64_t glo
         car.rot = M3::identity();
         car.pos = V3(0, 0, C::CAR_SPAWN_REST_Z * UU2BT);
         car.isOnGround = 1;
-        car.boost = C::BOOST_SPAWN_AMOUNT;
+        car.boost = spawnBoost;  // Gym.cpp:42-48: SetMutatorConfig runs before AddCar -> Respawn(carSpawnBoostAmount)
         car.hitTickLo = car.hitTickHi = car.hitExtraTickLo = car.hitExtraTickHi = -1;
     }
 }

@@ -47,7 +47,7 @@ void* hs_create(const rlg_engine_cfg* cfg, const void* const* blobs, const size_
         h->arenas.resize(cfg->num_arenas);
         h->xw.assign(tickx_words(h->cfg.numCars), 0u);
         h->scratch.resize(contact_scratch_slots(h->cfg.numCars));
-        for (int a = 0; a < cfg->num_arenas; a++) arena_init(h->arenas[a], h->cfg.numCars, cfg->seed, (uint64_t)cfg->arena_id_base + a);
+        for (int a = 0; a < cfg->num_arenas; a++) arena_init(h->arenas[a], h->cfg.numCars, cfg->seed, (uint64_t)cfg->arena_id_base + a, h->cfg.mut.carSpawnBoost);
         h->obs.resize((size_t)cfg->num_arenas * h->cfg.numCars * h->cfg.obsSize);
         h->reward.resize((size_t)cfg->num_arenas * h->cfg.numCars);
         h->done.resize(cfg->num_arenas);
