@@ -159,6 +159,14 @@ def run_reference(args, rank, world):
     from oracle import refsim
     from rlgymppo_cpp_b200 import abi
 
+    if not refsim.available() and os.path.isdir("/root/reference"):  # build the checker where the reference's sources are
+        import subprocess
+
+        subprocess.call(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "ref"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    if not refsim.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/librlref.so (the reference compiled by oracle/Makefile) is not in this tree"}))
+        sys.stdout.flush()
+        return
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     T = max(1, min(cores, 256))
     G = 8
