@@ -207,6 +207,16 @@ class PPOLearner:
             for p in list(self.policy.parameters()) + list(self.value_net.parameters()):
                 dist.broadcast(p.data, src=0, group=self.pg)
 
+    def update_learning_rates(self, policy_lr: float, critic_lr: float):
+        """PPOLearner::UpdateLearningRates (PPOLearner.cpp:504-517).  The optimiser steps run outside the captured minibatch
+        graph, so the new rates take effect at the next step without a re-capture."""
+        self.cfg.policyLR, self.cfg.criticLR = float(policy_lr), float(critic_lr)
+        for g in self.policy_opt.param_groups:
+            g["lr"] = float(policy_lr)
+        for g in self.value_opt.param_groups:
+            g["lr"] = float(critic_lr)
+        print(f"PPOLearner: Updated learning rate to [{policy_lr:e}, {critic_lr:e}]")
+
     def action_log_probs_entropy(self, obs, acts):
         """DiscretePolicy::GetBackpropData (DiscretePolicy.cpp:64-75)."""
         probs = torch.softmax(self.policy_fwd(obs) / self.cfg.policyTemperature, dim=-1).clamp(ACTION_MIN_PROB, 1)
@@ -374,6 +384,10 @@ class Learner:
             self.collector.reset_with_setter()
         else:
             self.engine.reset()
+
+    def update_learning_rates(self, policy_lr: float, critic_lr: float):
+        """Learner::UpdateLearningRates (Learner.cpp:705-707), e.g. from the iteration callback."""
+        self.ppo.update_learning_rates(policy_lr, critic_lr)
 
     def save(self, folder=None):
         """Learner::Save (Learner.cpp:244-281), reference on-disk layout (checkpoint.py)."""

@@ -88,6 +88,24 @@ def test_ppo_learn_step_matches_restatement():
         assert torch.allclose(p, q, atol=1e-6)
 
 
+def test_update_learning_rates():
+    """PPOLearner::UpdateLearningRates (PPOLearner.cpp:504-517): config and both Adam groups; a zero rate freezes that network
+    (Learn skips its optimiser step, PPOLearner.cpp:262-281)."""
+    torch.manual_seed(1)
+    cfg = L.PPOLearnerConfig(policyLayerSizes=[16], criticLayerSizes=[16], batchSize=32, miniBatchSize=32, epochs=1)
+    ppo = L.PPOLearner(5, 90, cfg, "cpu")
+    ppo.update_learning_rates(0.0, 3e-3)
+    assert cfg.policyLR == 0.0 and cfg.criticLR == 3e-3
+    assert all(g["lr"] == 0.0 for g in ppo.policy_opt.param_groups) and all(g["lr"] == 3e-3 for g in ppo.value_opt.param_groups)
+    pol0 = [p.detach().clone() for p in ppo.policy.parameters()]
+    val0 = [p.detach().clone() for p in ppo.value_net.parameters()]
+    exp = L.ExperienceBuffer(32, 0, "cpu")
+    exp.submit(_fake_rows(32, 5, 4))
+    ppo.learn(exp, {})
+    assert all(torch.equal(a, b) for a, b in zip(pol0, ppo.policy.parameters()))
+    assert any(not torch.equal(a, b) for a, b in zip(val0, ppo.value_net.parameters()))
+
+
 def _dp_worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
