@@ -27,6 +27,14 @@
 #include <RLGymSim_CPP/Utils/TerminalConditions/NoTouchCondition.h>
 #include <RLGymSim_CPP/Utils/TerminalConditions/GoalScoreCondition.h>
 
+#include <RocketSim/libsrc/bullet3-3.24/BulletCollision/CollisionShapes/btBoxShape.h>
+#include <RocketSim/libsrc/bullet3-3.24/BulletCollision/CollisionShapes/btSphereShape.h>
+#include <RocketSim/libsrc/bullet3-3.24/BulletCollision/CollisionShapes/btTriangleShape.h>
+#include <RocketSim/libsrc/bullet3-3.24/BulletCollision/CollisionDispatch/btBoxBoxDetector.h>
+#include <RocketSim/libsrc/bullet3-3.24/BulletCollision/NarrowPhaseCollision/btGjkEpaPenetrationDepthSolver.h>
+#include <RocketSim/libsrc/bullet3-3.24/BulletCollision/NarrowPhaseCollision/btGjkPairDetector.h>
+#include <RocketSim/libsrc/bullet3-3.24/BulletCollision/NarrowPhaseCollision/btVoronoiSimplexSolver.h>
+
 #include "../include/rlgym_b200.h"
 
 #include <atomic>
@@ -338,6 +346,132 @@ int ref_arena_dump_contacts(void* h, float* out, int maxRows) {
         }
     }
     return n;
+}
+
+
+
+// wheel rays of the last tick: rows {contact point xyz, normal xyz, suspension length, in contact, ground is static} per wheel
+void ref_arena_dump_wheels(void* h, int carIdx, float* out) {
+    Car* car = car_by_id((Arena*)h, carIdx + 1);
+    for (int i = 0; i < 4; i++) {
+        const btWheelInfoRL& w = car->_bulletVehicle.m_wheelInfo[i];
+        float* r = out + 9 * i;
+        for (int k = 0; k < 3; k++) { r[k] = w.m_raycastInfo.m_contactPointWS[k]; r[3 + k] = w.m_raycastInfo.m_contactNormalWS[k]; }
+        r[6] = w.m_raycastInfo.m_suspensionLength; r[7] = w.m_raycastInfo.m_isInContact ? 1.f : 0.f; r[8] = w.m_isInContactWithWorld ? -1.f : 0.f;
+    }
+}
+
+// ---- contact-added trace: every point btManifoldResult::addContactPoint hands to the reference's callback, in call order ----
+static ContactAddedCallback g_prev_added = nullptr;
+static float g_trace[256][12];
+static int g_trace_n = 0;
+static bool trace_added(btManifoldPoint& cp, const btCollisionObjectWrapper* o0, int part0, int idx0, const btCollisionObjectWrapper* o1, int part1, int idx1) {
+    if (g_trace_n < 256) {
+        float* r = g_trace[g_trace_n++];
+        auto code = [&](const btCollisionObject* o) -> float {
+            if (o->getUserIndex() == BT_USERINFO_TYPE_BALL) return 0.f;
+            if (o->getUserIndex() == BT_USERINFO_TYPE_CAR) return (float)((Car*)o->getUserPointer())->id;
+            return -1.f;
+        };
+        r[0] = code(o0->m_collisionObject); r[1] = code(o1->m_collisionObject);
+        for (int k = 0; k < 3; k++) { r[2 + k] = cp.m_normalWorldOnB[k]; r[5 + k] = cp.m_positionWorldOnB[k]; }
+        r[8] = cp.m_distance1; r[9] = (float)idx0; r[10] = (float)idx1; r[11] = (float)part1;
+    }
+    return g_prev_added ? g_prev_added(cp, o0, part0, idx0, o1, part1, idx1) : true;
+}
+void ref_trace_contacts(int enable) {
+    if (enable && gContactAddedCallback != trace_added) { g_prev_added = gContactAddedCallback; gContactAddedCallback = trace_added; }
+    if (!enable && gContactAddedCallback == trace_added) gContactAddedCallback = g_prev_added;
+    g_trace_n = 0;
+}
+int ref_trace_read(float* out, int maxRows) {
+    int n = g_trace_n < maxRows ? g_trace_n : maxRows;
+    memcpy(out, g_trace, sizeof(float) * 12 * n);
+    g_trace_n = 0;
+    return n;
+}
+
+// ---- narrowphase probes (unit parity of rl_gjk.h / rl_epa.h / rl_boxbox.h against the reference's own detectors) ----
+// broadphase unique ids of the ball and the cars (pair body order: btHashedOverlappingPairCache::internalAddPair)
+void ref_arena_unique_ids(void* h, int32_t* out) {
+    Arena* a = (Arena*)h;
+    out[0] = a->ball->_rigidBody.getBroadphaseHandle()->m_uniqueId;
+    int n = (int)a->_cars.size();
+    for (int i = 0; i < n; i++) out[1 + i] = car_by_id(a, i + 1)->_rigidBody.getBroadphaseHandle()->m_uniqueId;
+}
+
+struct ProbeResult : public btDiscreteCollisionDetectorInterface::Result {
+    int n = 0; btVector3 normal, point; btScalar depth = 0;
+    void setShapeIdentifiersA(int, int) override {}
+    void setShapeIdentifiersB(int, int) override {}
+    void addContactPoint(const btVector3& normalOnBInWorld, const btVector3& pointInWorld, btScalar d) override {
+        n++; normal = normalOnBInWorld; point = pointInWorld; depth = d;
+    }
+};
+
+// btConvexConvexAlgorithm::processCollision's detector call for (box with margin 0.04, triangle with margin 0):
+// boxT = {origin xyz, basis rows 9}, tri = 3 x xyz (world, BT units), breaking = manifold contact-breaking threshold.
+// out = {normal xyz, point xyz, depth}; returns the number of contact points reported (0 / 1) and the detector's last method.
+int ref_probe_box_triangle(const float* halfExt, const float* boxT, const float* tri, float breaking, float* out, int* method) {
+    btBoxShape box(btVector3(halfExt[0], halfExt[1], halfExt[2]));
+    btTriangleShape tm(btVector3(tri[0], tri[1], tri[2]), btVector3(tri[3], tri[4], tri[5]), btVector3(tri[6], tri[7], tri[8]));
+    tm.setMargin(0.f);
+    btVoronoiSimplexSolver simplex;
+    btGjkEpaPenetrationDepthSolver pd;
+    btGjkPairDetector det(&box, &tm, &simplex, &pd);
+    btGjkPairDetector::ClosestPointInput in;
+    in.m_maximumDistanceSquared = box.getMargin() + tm.getMargin() + breaking;
+    in.m_maximumDistanceSquared *= in.m_maximumDistanceSquared;
+    in.m_transformA.setOrigin(btVector3(boxT[0], boxT[1], boxT[2]));
+    in.m_transformA.setBasis(btMatrix3x3(boxT[3], boxT[4], boxT[5], boxT[6], boxT[7], boxT[8], boxT[9], boxT[10], boxT[11]));
+    in.m_transformB.setIdentity();
+    ProbeResult r;
+    det.getClosestPoints(in, r, false);
+    if (method) *method = det.m_lastUsedMethod;
+    if (r.n) { for (int k = 0; k < 3; k++) { out[k] = r.normal[k]; out[3 + k] = r.point[k]; } out[6] = r.depth; }
+    return r.n;
+}
+int ref_probe_box_sphere(const float* halfExt, const float* boxT, const float* center, float radius, float breaking, float* out, int* method) {
+    btBoxShape box(btVector3(halfExt[0], halfExt[1], halfExt[2]));
+    btSphereShape sp(radius);
+    btVoronoiSimplexSolver simplex;
+    btGjkEpaPenetrationDepthSolver pd;
+    btGjkPairDetector det(&box, &sp, &simplex, &pd);
+    btGjkPairDetector::ClosestPointInput in;
+    in.m_maximumDistanceSquared = box.getMargin() + sp.getMargin() + breaking;
+    in.m_maximumDistanceSquared *= in.m_maximumDistanceSquared;
+    in.m_transformA.setOrigin(btVector3(boxT[0], boxT[1], boxT[2]));
+    in.m_transformA.setBasis(btMatrix3x3(boxT[3], boxT[4], boxT[5], boxT[6], boxT[7], boxT[8], boxT[9], boxT[10], boxT[11]));
+    in.m_transformB.setIdentity();
+    in.m_transformB.setOrigin(btVector3(center[0], center[1], center[2]));
+    ProbeResult r;
+    det.getClosestPoints(in, r, false);
+    if (method) *method = det.m_lastUsedMethod;
+    if (r.n) { for (int k = 0; k < 3; k++) { out[k] = r.normal[k]; out[3 + k] = r.point[k]; } out[6] = r.depth; }
+    return r.n;
+}
+// btBoxBoxDetector for two boxes: out rows of {normal xyz, point xyz, depth}; returns the number of points
+struct ProbeMulti : public btDiscreteCollisionDetectorInterface::Result {
+    int n = 0; float* out; int cap;
+    void setShapeIdentifiersA(int, int) override {}
+    void setShapeIdentifiersB(int, int) override {}
+    void addContactPoint(const btVector3& nrm, const btVector3& p, btScalar d) override {
+        if (n < cap) { float* r = out + 7 * n; for (int k = 0; k < 3; k++) { r[k] = nrm[k]; r[3 + k] = p[k]; } r[6] = d; }
+        n++;
+    }
+};
+int ref_probe_box_box(const float* halfA, const float* tA, const float* halfB, const float* tB, float* out, int cap) {
+    btBoxShape a(btVector3(halfA[0], halfA[1], halfA[2])), b(btVector3(halfB[0], halfB[1], halfB[2]));
+    btBoxBoxDetector det(&a, &b);
+    btDiscreteCollisionDetectorInterface::ClosestPointInput in;
+    in.m_maximumDistanceSquared = BT_LARGE_FLOAT;
+    in.m_transformA.setOrigin(btVector3(tA[0], tA[1], tA[2]));
+    in.m_transformA.setBasis(btMatrix3x3(tA[3], tA[4], tA[5], tA[6], tA[7], tA[8], tA[9], tA[10], tA[11]));
+    in.m_transformB.setOrigin(btVector3(tB[0], tB[1], tB[2]));
+    in.m_transformB.setBasis(btMatrix3x3(tB[3], tB[4], tB[5], tB[6], tB[7], tB[8], tB[9], tB[10], tB[11]));
+    ProbeMulti r; r.out = out; r.cap = cap;
+    det.getClosestPoints(in, r, false);
+    return r.n;
 }
 
 // iteration order of Arena::_cars (the player order of every gym-level vector)

@@ -55,6 +55,7 @@ struct rlg_engine {
     cudaStream_t copyStream = nullptr; cudaEvent_t evFirst = nullptr;  // host-buffer step: D2H of the results overlaps ticks 1..
     int32_t* resetCount = nullptr; int32_t* hResetCount = nullptr; int32_t* hResetIds = nullptr; float* hResetObs = nullptr;
     int32_t* dResetIds = nullptr; float* dResetObs = nullptr;  // device views of the two mapped host buffers
+    EpaWs* epa = nullptr;        // [block][warp] penetration-depth workspaces of the role kernel
     float* metrics = nullptr;    // [kMetricWords][A]: stepTotal, stepCount (u32), epTotal, epCount (u32), curEpRew, totalSteps (u32)
     int xwords = 0, stride = 0, scratchSlots = 0;
     int arenasPerBlock = 32, groupsPerBlock = 1;
@@ -161,6 +162,7 @@ struct RolesArgs {
     int32_t* resetCount; int32_t* resetIds; float* resetObs;
     const int32_t* actions; float* obs; float* reward; uint8_t* done; int autoReset;
     float* metrics;  // GameInst reward metrics, word-transposed [kMetricWords][A] (nullptr: not tracked)
+    EpaWs* epa;      // [block][warp] penetration-depth workspaces (rl_epa.h): deep hitbox contacts are rare, a warp's lanes take turns
 };
 constexpr int kMetricWords = 6;
 
@@ -338,7 +340,7 @@ __device__ __forceinline__ void cands_pass_warp(CarW& w, int ci, bool active, co
 
 // Pass 2 (after car-ball): hitbox vs the pre-filtered candidate triangles -> the car's car-world contact segment.
 __device__ __forceinline__ void box_meshes_warp(CollideCtx& cx, ContactSink& cw, const MeshSet& ms, const CarW& w, int ci, float breaking,
-                                                bool active, const CarConsts& k, const uint32_t* mine, uint32_t* wq, int stride) {
+                                                bool active, const CarConsts& k, const uint32_t* mine, uint32_t* wq, int stride, EpaWs* ws) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const MeshCands& cands = w.cands;
@@ -374,7 +376,7 @@ __device__ __forceinline__ void box_meshes_warp(CollideCtx& cx, ContactSink& cw,
                 V3 boxCenter = c.pos + c.rot * k.hitboxOffset;
                 V3 ext(dot(vabs(c.rot.r[0]), k.halfExt), dot(vabs(c.rot.r[1]), k.halfExt), dot(vabs(c.rot.r[2]), k.halfExt));
                 V3 normal, point; float dist = 0.f;
-                const bool hit = box_mesh_item(c, k, boxCenter, boxCenter - ext, boxCenter + ext, ms.tris[ms.nodes[it & 0xffffff].tri], breaking, normal, point, dist);
+                const bool hit = box_mesh_item(c, k, boxCenter, boxCenter - ext, boxCenter + ext, ms.tris[ms.nodes[it & 0xffffff].tri], breaking, ws, normal, point, dist);
                 uint32_t* r = res + lane * kWqResWords;
                 r[0] = hit ? 1u : 0u;
                 if (hit) {
@@ -474,8 +476,8 @@ __global__ void __maxnreg__(168) k_roles(const __grid_constant__ RolesArgs g) {
             if (valid) tick_p1_car_pose(s, x, g.cfg, g.ms, k, role - 1, w, false);
             collect_candidates_warp(w, role - 1, valid, k, g.ms, mine, wq);  // whole warp
             cands_pass_warp(w, role - 1, valid, k, g.ms, mine, wq, g.stride);  // whole warp
-            if (valid) tick_p1_car_begin(s, x, g.cfg, g.ms, k, thr, role - 1, w, scratch, first, cx, cw);
-            box_meshes_warp(cx, cw, g.ms, w, role - 1, thr.car, valid, k, mine, wq, g.stride);  // whole warp
+            if (valid) tick_p1_car_begin(s, x, g.cfg, g.ms, k, thr, role - 1, w, scratch, first, cx, cw, g.epa + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp));
+            box_meshes_warp(cx, cw, g.ms, w, role - 1, thr.car, valid, k, mine, wq, g.stride, g.epa + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp));  // whole warp
             if (valid) tick_p1_car_end(cx, cw, x, thr, role - 1);
         }
         PT_WORK(2);
@@ -626,7 +628,7 @@ int rlg_engine_destroy(rlg_engine* e) {
         cudaFree(e->prof); cudaFree(e->prof2);
     }
 #endif
-    cudaFree(e->scratch); cudaFree(e->metrics);
+    cudaFree(e->scratch); cudaFree(e->metrics); cudaFree(e->epa);
     cudaFree(e->state); cudaFree(e->tables); cudaFree(e->obs); cudaFree(e->reward); cudaFree(e->done); cudaFree(e->actions);
     for (void* p : e->meshMem) cudaFree(p);
     cudaFreeHost(e->hActions); cudaFreeHost(e->hObs); cudaFreeHost(e->hReward); cudaFreeHost(e->hDone);
@@ -710,6 +712,11 @@ int rlg_engine_create(const rlg_engine_cfg* cfg, rlg_engine** out) {
     if (const char* cv = getenv("RLG_SMEM_CARVEOUT")) CKD(cudaFuncSetAttribute(k_roles, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
     CKD(cudaMalloc(&e->state, (size_t)e->nwords * A * 4));
     CKD(cudaMalloc(&e->scratch, (size_t)A * e->scratchSlots * sizeof(Contact)));
+    {   // one penetration-depth workspace per warp of the role kernel's grid (their locks start free)
+        const size_t blocks = (A + e->arenasPerBlock - 1) / e->arenasPerBlock, warps = (size_t)e->groupsPerBlock * (1 + P);
+        CKD(cudaMalloc(&e->epa, blocks * warps * sizeof(EpaWs)));
+        CKD(cudaMemsetAsync(e->epa, 0, blocks * warps * sizeof(EpaWs), e->stream));
+    }
     CKD(cudaMalloc(&e->metrics, (size_t)kMetricWords * A * 4));
     CKD(cudaMemsetAsync(e->metrics, 0, (size_t)kMetricWords * A * 4, e->stream));
     CKD(cudaMalloc(&e->tables, sizeof(Tables)));
@@ -780,6 +787,7 @@ static RolesArgs roles_args(rlg_engine* e) {
     g.arenasPerBlock = e->arenasPerBlock;
     g.barMode = e->barMode; g.asyncLoad = e->asyncLoad; g.prof = e->prof;
     g.k = car_consts(e->cfg.carPreset); g.thr = contact_thresholds(g.k);
+    g.epa = e->epa;
     return g;
 }
 

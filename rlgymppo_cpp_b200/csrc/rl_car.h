@@ -46,6 +46,7 @@ struct CarX {
 struct TickXHdr {
     V3 ballPos, ballVel, ballAngvel;  // start-of-tick snapshot (vel undamped)
     int32_t nBall, nPair, ballActive;
+    float solverDt;                   // btContactSolverInfo::m_timeStep as the vehicle update sees it (ArenaS::worldStepped)
 };
 constexpr int kTickXHdrWords = sizeof(TickXHdr) / 4;
 constexpr int kCarXWords = sizeof(CarX) / 4;
@@ -250,7 +251,7 @@ RL_HD inline void vehicle_first(CarS& c, const TickX& x, const SimCfg& cfg, cons
                     // (B/BulletDynamics/ConstraintSolver/btContactConstraint.cpp:60-106; m_erp = 0.2)
                     float delta = traceLen - thresh;
                     float rel_vel = dot(hit.normal, velAt);
-                    float positionalError = 0.2f * -delta / kTickTime;
+                    float positionalError = 0.2f * -delta / x.h->solverDt;
                     float velocityError = -(1.0f + 0.f) * rel_vel;
                     float denom0 = impulse_denom(c.pos, w.invInertiaWorld, k.invMass, wh.contactPoint, hit.normal);
                     float jacDiagABInv = 1.f / (denom0 + 0.f);

@@ -4,7 +4,7 @@
 // btRSBroadphase drops and rebuilds every pair (and therefore every manifold) each tick.
 //
 // Body indices: 0 = ball, 1+c = car c, -1 = static world.  A manifold's body A is the
-// dynamic one for world pairs, the car for car-ball, the lower car for car-car; normals
+// dynamic one for world pairs, the car for car-ball, the HIGHER car for car-car (see car_car); normals
 // are "normalWorldOnB": they point from B towards A.
 #pragma once
 #include "rl_car.h"
@@ -87,6 +87,7 @@ struct CollideCtx {
     int64_t tick;
     V3 ballPos, ballVel;      // the ball as the narrowphase sees it: start-of-tick position, DAMPED velocity
     int32_t firstTickOfStep;  // bump counters only stick when the callback fires during Gym::Step's first tick (see rl_tick.h)
+    EpaWs* epa;               // penetration-depth workspace (device: the warp's; host: nullptr = local, rl_epa.h)
 };
 
 // ---- Arena::_BulletContactAddedCallback ------------------------------------------------------
@@ -139,7 +140,7 @@ RL_HD inline void on_car_car(CollideCtx& x, int c1, int c2, Contact& cp) {
             float speedTowards = ref_dot(sVel, dirToOther);
             float otherAway = ref_dot(oVel, velDir);
             if (speedTowards > otherAway) {
-                // m_localPointA / m_localPointB in the respective car's frame; manifold A is the lower-id car
+                // m_localPointA / m_localPointB in the respective car's frame (A = the higher car, see car_car)
                 V3 wp = swapped ? cp.posB : cp.posA;
                 const CarS& own = a.cars[c1];
                 V3 local = tmul(wp - own.pos, own.rot);
@@ -379,8 +380,8 @@ RL_HD inline void sphere_meshes(CollideCtx& x, ContactSink& cs, const MeshSet& m
 // one candidate triangle of the hitbox-vs-mesh narrowphase (shared by the direct walk and the candidate-list path)
 // The geometric part is a pure function of (car pose, triangle) — the role kernel evaluates it for many (car, triangle)
 // pairs at once, one pair per lane (engine.cu box_meshes_warp); the manifold bookkeeping stays with the car's own lane.
-RL_HDI bool box_mesh_item(const CarS& c, const CarConsts& k, V3 boxCenter, V3 mn, V3 mx, const Tri& t, float breaking, V3& normal, V3& pointOnB,
-                          float& dist) {
+RL_HDI bool box_mesh_item(const CarS& c, const CarConsts& k, V3 boxCenter, V3 mn, V3 mx, const Tri& t, float breaking, EpaWs* ws, V3& normal,
+                          V3& pointOnB, float& dist) {
     if (!tri_vs_aabb(t, mn, mx)) return false;
     auto sup = [&](V3 d) {  // btBoxShape::localGetSupportingVertex (with margin)
         V3 dl = tmul(d, c.rot);
@@ -388,12 +389,12 @@ RL_HDI bool box_mesh_item(const CarS& c, const CarConsts& k, V3 boxCenter, V3 mn
         return boxCenter + c.rot * v;
     };
     if (tri_early_out(t, breaking, sup)) return false;
-    return box_triangle_contact(boxCenter, c.rot, k.halfExt, k.coreHalf, k.boxMargin, t, breaking, normal, pointOnB, dist);
+    return box_triangle_contact(boxCenter, c.rot, k.coreHalf, k.boxMargin, t, breaking, ws, normal, pointOnB, dist);
 }
 RL_HDI void box_mesh_triangle(CollideCtx& x, Manifold& m, const MeshSet& ms, const CarS& c, const CarConsts& k, V3 boxCenter, V3 mn, V3 mx,
                               int triIdx, float breaking) {
     V3 normal, pointOnB; float dist;
-    if (box_mesh_item(c, k, boxCenter, mn, mx, ms.tris[triIdx], breaking, normal, pointOnB, dist))
+    if (box_mesh_item(c, k, boxCenter, mn, mx, ms.tris[triIdx], breaking, x.epa, normal, pointOnB, dist))
         manifold_add(x, m, normal, pointOnB, dist, &ms, triIdx);
 }
 
@@ -452,22 +453,27 @@ RL_HD inline void car_ball(CollideCtx& x, ContactSink& cs, int ci, float breakin
     float radius = C::BALL_RADIUS * UU2BT;
     V3 boxCenter = c.pos + c.rot * k.hitboxOffset;
     V3 normal, pointOnB; float dist;
-    if (box_sphere_contact(boxCenter, c.rot, k.halfExt, k.coreHalf, k.boxMargin, x.ballPos, radius, breaking, normal, pointOnB, dist)) {
+    if (box_sphere_contact(boxCenter, c.rot, k.coreHalf, k.boxMargin, x.ballPos, radius, breaking, x.epa, normal, pointOnB, dist)) {
         Manifold m; m.a = 1 + ci; m.b = 0; m.n = 0; m.breaking = breaking;
         manifold_add(x, m, normal, pointOnB, dist, nullptr, -1);
         manifold_flush(cs, m);
     }
 }
 
+// car c1 vs car c2 (c1 < c2).  Body order of the manifold: the pair reaches btCompoundCompoundCollisionAlgorithm as
+// (c1, c2), which — the compounds have no dynamic AABB tree (btCompoundShape(false, 1), Car.cpp _BulletSetup) — defers to
+// btCompoundCollisionAlgorithm: child box of c1 vs compound c2 goes through the SWAPPED compound algorithm, whose child
+// call is (box of c2, box of c1), and the box-box algorithm creates the manifold for its own (body0, body1).  So body A
+// of a car-car manifold (and box 1 of btBoxBoxDetector, and "car1" of the first bump test) is the HIGHER car.
 RL_HD RL_NOINLINE inline void car_car(CollideCtx& x, ContactSink& cs, int c1, int c2, float breaking) {
-    const CarS& A = x.a->cars[c1];
-    const CarS& B = x.a->cars[c2];
+    const CarS& A = x.a->cars[c2];
+    const CarS& B = x.a->cars[c1];
     const CarConsts& k = *x.k;
     V3 ca = A.pos + A.rot * k.hitboxOffset, cb = B.pos + B.rot * k.hitboxOffset;
     BoxBoxResult r;
     box_box(ca, A.rot, k.halfExt, cb, B.rot, k.halfExt, r);
     if (r.n > 0) {
-        Manifold m; m.a = 1 + c1; m.b = 1 + c2; m.n = 0; m.breaking = breaking;
+        Manifold m; m.a = 1 + c2; m.b = 1 + c1; m.n = 0; m.breaking = breaking;
         for (int i = 0; i < r.n; i++) manifold_add(x, m, r.normal, r.point[i], r.depth[i], nullptr, -1);
         manifold_flush(cs, m);
     }

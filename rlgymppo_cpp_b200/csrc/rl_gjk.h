@@ -5,10 +5,11 @@
 // with btVoronoiSimplexSolver, and box-box through btBoxBoxDetector.  This file restates
 // those algorithms for the three concrete support mappings involved (box core, triangle,
 // point), without any polymorphism: GJK distance on the margin-less cores, margins added
-// afterwards; when the cores overlap (the reference switches to EPA on the rounded box) a
-// 13-axis separating-axis search on box vs triangle yields the minimum translation.
+// afterwards; when the cores overlap or nearly touch, the reference's penetration-depth solver
+// (GJK + EPA on the shapes with margins, rl_epa.h) takes over exactly as in btGjkPairDetector.
 #pragma once
 #include "rl_mesh.h"
+#include "rl_epa.h"
 
 namespace rl {
 
@@ -198,28 +199,31 @@ RL_HDI bool simplex_contains(const Simplex& s, V3 w) {
     return w.x == s.lastW.x && w.y == s.lastW.y && w.z == s.lastW.z;
 }
 
-// GJK between a box core (A) and a convex B given by a support functor in world space.
-// Returns true with separated cores: pA/pB closest points on the cores, axis = pA - pB.
-// Returns false if the cores overlap/touch (penetration path).
+// The front half of btGjkPairDetector::getClosestPointsNonVirtual (btGjkPairDetector.cpp:690-850) for A = box core and a convex B
+// given by a support functor in world space: GJK distance between the margin-less cores in the frame shifted by `offset`.
+struct GjkOut {
+    bool valid;        // isValid: a usable separating axis was found
+    int degenerate;    // m_degenerateSimplex
+    V3 axis;           // m_cachedSeparatingAxis (unnormalised)
+    V3 pB;             // closest point on B's core, shifted frame
+    float sqDist;      // squaredDistance
+};
 template <class SupportB>
-RL_HD inline bool gjk_box_core(V3 boxCenter, const M3& rot, V3 coreHalf, V3 originB, SupportB supB, float maxDistSq, V3& pA, V3& pB, V3& axis, float& sqDist, bool& tooFar) {
-    V3 offset = (boxCenter + originB) * 0.5f;
-    V3 cA = boxCenter - offset;
+RL_HD inline void gjk_box_core(V3 cA, const M3& rot, V3 coreHalf, V3 offset, SupportB supB, float maxDistSq, GjkOut& o) {
     Simplex s; s.n = 0; s.lastW = V3(1e18f, 1e18f, 1e18f);
     V3 sepAxis(0, 1, 0);
     float squaredDistance = 1e18f;
     bool checkSimplex = false;
     int degenerate = 0;
-    tooFar = false;
     const float REL_ERROR2 = 1.0e-6f;
-    for (int iter = 0; iter < 64; iter++) {
+    for (int iter = 0; iter <= 1000; iter++) {
         V3 dirA = tmul(-sepAxis, rot);
         V3 pInA(dirA.x >= 0 ? coreHalf.x : -coreHalf.x, dirA.y >= 0 ? coreHalf.y : -coreHalf.y, dirA.z >= 0 ? coreHalf.z : -coreHalf.z);
         V3 pWorld = cA + rot * pInA;
         V3 qWorld = supB(sepAxis) - offset;
         V3 w = pWorld - qWorld;
         float delta = dot(sepAxis, w);
-        if (delta > 0.f && delta * delta > squaredDistance * maxDistSq) { degenerate = 10; checkSimplex = true; tooFar = true; break; }
+        if (delta > 0.f && delta * delta > squaredDistance * maxDistSq) { degenerate = 10; checkSimplex = true; break; }
         if (simplex_contains(s, w)) { degenerate = 1; checkSimplex = true; break; }
         float f0 = squaredDistance - delta, f1 = squaredDistance * REL_ERROR2;
         if (f0 <= f1) { degenerate = f0 <= 0.f ? 2 : 11; checkSimplex = true; break; }
@@ -233,21 +237,64 @@ RL_HD inline bool gjk_box_core(V3 boxCenter, const M3& rot, V3 coreHalf, V3 orig
         sepAxis = newAxis;
         if (s.n == 4) { degenerate = 13; break; }
     }
-    (void)degenerate;
+    o.valid = false; o.degenerate = degenerate; o.axis = sepAxis; o.sqDist = squaredDistance; o.pB = V3();
     if (checkSimplex) {
         V3 dummy; simplex_closest(s, dummy);
-        pA = s.cachedP1 + offset; pB = s.cachedP2 + offset;
-        float lenSqr = len2(sepAxis);
-        if (lenSqr > kEps * kEps) { axis = sepAxis; sqDist = squaredDistance; return true; }
+        o.pB = s.cachedP2;
+        if (len2(sepAxis) > kEps * kEps) o.valid = true;
+    }
+}
+
+// The back half (btGjkPairDetector.cpp:850-1000): the penetration-depth solver when the cores overlap or the distance is
+// degenerate-small, the "only replace when deeper / closer" rules, the contact-normal direction fix, the distance gate.
+// In: the GJK result as (valid, normal, pointOnB in the shifted frame, distance).  supBLocal(dir, withMargin) is B's support
+// mapping in B's own frame (identity basis, origin oB in the shifted frame); posB = centre of B's bounding box.
+template <class SupBLocal>
+RL_HD inline bool pair_finish(bool isValid, bool degenerate, V3 normalInB, V3 pointOnB, float distance, V3 cA, const M3& rot, V3 coreHalf, float marginA,
+                              float marginB, V3 oB, SupBLocal supBLocal, V3 posB, V3 offset, float maxDistSq, EpaWs* ws, V3& outNormal, V3& outPoint,
+                              float& outDist) {
+    const float margin = marginA + marginB;
+    const bool catchDegenerate = degenerate && (distance + margin) < 0.01f;
+    if (!isValid || catchDegenerate) {
+        with_epa_ws(ws, [&](EpaWs* w) {
+            Mink<SupBLocal> sh(rot, cA, oB, coreHalf, marginA, supBLocal);
+            PenResult r;
+            const int pr = calc_pen_depth(w, sh, cA, oB, r);
+            const V3 v = r.normal;  // m_cachedSeparatingAxis after calcPenDepth (A's local frame: reference quirk)
+            if (pr == 1) {
+                V3 tmpN = r.witnessB - r.witnessA;
+                float lenSqr = len2(tmpN);
+                if (lenSqr <= kEps * kEps) { tmpN = v; lenSqr = len2(v); }
+                if (lenSqr > kEps * kEps) {
+                    tmpN = tmpN / sqrtf(lenSqr);
+                    const float distance2 = -len(r.witnessA - r.witnessB);
+                    if (!isValid || distance2 < distance) { distance = distance2; pointOnB = r.witnessB; normalInB = tmpN; isValid = true; }
+                }
+            } else if (len2(v) > 0.f) {
+                const float distance2 = len(r.witnessA - r.witnessB) - margin;
+                if (!isValid || distance2 < distance) {
+                    distance = distance2;
+                    pointOnB = r.witnessB + v * marginB;
+                    normalInB = normalized(v);
+                    isValid = true;
+                }
+            }
+        });
+    }
+    if (isValid && (distance < 0 || distance * distance < maxDistSq)) {
+        // m_fixContactNormalDirection: the normal must point from B's bounding-box centre towards A's
+        if (dot(cA - posB, normalInB) < 0.f) normalInB = normalInB * -1.f;
+        outNormal = normalInB; outPoint = pointOnB + offset; outDist = distance;
+        return true;
     }
     return false;
 }
 
 // ---- box vs sphere (car hitbox vs ball) ---------------------------------------------------------
-// A = box (margin 0.04), B = sphere (point core, margin = radius).  GJK between a box core and a point
-// converges to the closest point on the core; written in closed form.
-RL_HD RL_NOINLINE inline bool box_sphere_contact(V3 boxCenter, const M3& rot, V3 halfExt, V3 core, float marginA, V3 sphereCenter, float radius, float breaking,
-                                     V3& normalOnB, V3& pointOnB, float& dist) {
+// A = box (margin 0.04), B = sphere (point core, margin = radius).  GJK between a box core and a point converges to the
+// closest point on the core; written in closed form.  Centre within 0.01 of the core (or inside it): penetration solver.
+RL_HD RL_NOINLINE inline bool box_sphere_contact(V3 boxCenter, const M3& rot, V3 core, float marginA, V3 sphereCenter, float radius, float breaking,
+                                                 EpaWs* ws, V3& normalOnB, V3& pointOnB, float& dist) {
     V3 l = tmul(sphereCenter - boxCenter, rot);
     V3 q(clampf(l.x, -core.x, core.x), clampf(l.y, -core.y, core.y), clampf(l.z, -core.z, core.z));
     V3 d = q - l;  // from sphere centre (B) to box core (A)
@@ -255,112 +302,67 @@ RL_HD RL_NOINLINE inline bool box_sphere_contact(V3 boxCenter, const M3& rot, V3
     float margin = marginA + radius;
     float maxDist = margin + breaking;
     if (d2 > maxDist * maxDist) return false;
-    if (d2 > kEps * kEps) {
-        float dl = sqrtf(d2);
+    const float dl = sqrtf(d2);
+    if (d2 > kEps * kEps && dl >= 0.01f) {
         V3 nl = d * (1.f / dl);
         normalOnB = rot * nl;
         pointOnB = sphereCenter + normalOnB * radius;
         dist = dl - margin;
         return true;
     }
-    // sphere centre inside the core: minimum translation through the nearest face (stands in for EPA)
-    float best = 1e18f; int ax = 0; float sg = 1.f;
-    for (int a = 0; a < 3; a++) {
-        float dp = halfExt[a] - l[a], dn = halfExt[a] + l[a];
-        if (dp < best) { best = dp; ax = a; sg = 1.f; }
-        if (dn < best) { best = dn; ax = a; sg = -1.f; }
-    }
-    V3 nl(0, 0, 0); nl[ax] = -sg;  // from sphere towards the box interior
-    normalOnB = rot * nl;
-    pointOnB = sphereCenter + normalOnB * radius;
-    dist = -(best + radius);
-    return true;
+    const V3 offset = (boxCenter + sphereCenter) * 0.5f;
+    const bool valid = d2 > kEps * kEps;
+    V3 n0 = valid ? rot * (d * (1.f / dl)) : V3();
+    auto supLocal = [radius](V3 dir, bool withMargin) {
+        if (!withMargin) return V3(0, 0, 0);
+        V3 dn = dir;
+        if (len2(dn) < kEps * kEps) dn = V3(-1, -1, -1);
+        return normalized(dn) * radius;
+    };
+    return pair_finish(valid, true, n0, (sphereCenter - offset) + n0 * radius, dl - margin, boxCenter - offset, rot, core, marginA, radius, sphereCenter - offset,
+                       supLocal, sphereCenter - offset, offset, maxDist * maxDist, ws, normalOnB, pointOnB, dist);
 }
 
 // ---- box vs triangle -------------------------------------------------------------------------------
-RL_HDI void project_box(V3 axis, V3 center, const M3& rot, V3 half, float& mn, float& mx) {
-    float c = dot(axis, center);
-    float r = fabsf(dot(axis, rot.col(0))) * half.x + fabsf(dot(axis, rot.col(1))) * half.y + fabsf(dot(axis, rot.col(2))) * half.z;
-    mn = c - r; mx = c + r;
-}
-
-// cores overlap: 13-axis SAT between the full box and the triangle -> minimum translation (B -> A)
-RL_HD inline bool box_triangle_sat(V3 boxCenter, const M3& rot, V3 halfExt, const Tri& t, V3& normalOnB, V3& pointOnB, float& dist) {
-    V3 e[3] = {t.v1 - t.v0, t.v2 - t.v1, t.v0 - t.v2};
-    V3 axes[13];
-    int na = 0;
-    axes[na++] = cross(e[0], t.v2 - t.v0);
-    for (int i = 0; i < 3; i++) axes[na++] = rot.col(i);
-    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) axes[na++] = cross(rot.col(i), e[j]);
-    float bestDepth = 1e18f; V3 bestAxis(0, 0, 1); int bestIdx = -1;
-    for (int i = 0; i < na; i++) {
-        float l2 = len2(axes[i]);
-        if (l2 < 1e-10f) continue;
-        V3 ax = axes[i] * (1.f / sqrtf(l2));
-        float bmn, bmx; project_box(ax, boxCenter, rot, halfExt, bmn, bmx);
-        float p0 = dot(ax, t.v0), p1 = dot(ax, t.v1), p2 = dot(ax, t.v2);
-        float tmn = fminf_(fminf_(p0, p1), p2), tmx = fmaxf_(fmaxf_(p0, p1), p2);
-        // push A (box) along +ax out of B: depth = tmx - bmn ; along -ax: bmx - tmn
-        float dPos = tmx - bmn, dNeg = bmx - tmn;
-        if (dPos < 0.f || dNeg < 0.f) return false;  // separated
-        float bias = i >= 4 ? 1.0001f : 1.f;        // prefer face axes on ties, like most SAT implementations
-        if (dPos * bias < bestDepth) { bestDepth = dPos * bias; bestAxis = ax; bestIdx = i; }
-        if (dNeg * bias < bestDepth) { bestDepth = dNeg * bias; bestAxis = -ax; bestIdx = i; }
-    }
-    if (bestIdx < 0) return false;
-    normalOnB = bestAxis;
-    // witness on the triangle: for box-face axes the deepest triangle vertex, otherwise the deepest box vertex projected
-    float depth = bestDepth / (bestIdx >= 4 ? 1.0001f : 1.f);
-    if (bestIdx >= 1 && bestIdx <= 3) {
-        float p0 = dot(bestAxis, t.v0), p1 = dot(bestAxis, t.v1), p2 = dot(bestAxis, t.v2);
-        float mx = fmaxf_(fmaxf_(p0, p1), p2);
-        V3 sum(0, 0, 0); int cnt = 0;
-        if (mx - p0 < 1e-4f) { sum += t.v0; cnt++; }
-        if (mx - p1 < 1e-4f) { sum += t.v1; cnt++; }
-        if (mx - p2 < 1e-4f) { sum += t.v2; cnt++; }
-        pointOnB = sum * (1.f / (float)cnt);
-    } else {
-        V3 dl = tmul(-bestAxis, rot);
-        V3 sum(0, 0, 0); int cnt = 0;
-        for (int v = 0; v < 8; v++) {
-            V3 lv((v & 1) ? halfExt.x : -halfExt.x, (v & 2) ? halfExt.y : -halfExt.y, (v & 4) ? halfExt.z : -halfExt.z);
-            float sup = fabsf(dl.x) * halfExt.x + fabsf(dl.y) * halfExt.y + fabsf(dl.z) * halfExt.z;
-            if (sup - dot(dl, lv) < 1e-4f) { sum += lv; cnt++; }
-        }
-        V3 pa = boxCenter + rot * (sum * (1.f / (float)cnt));
-        pointOnB = closest_pt_triangle(pa + bestAxis * depth, t.v0, t.v1, t.v2);
-    }
-    dist = -depth;
-    return true;
-}
-
-RL_HD RL_NOINLINE inline bool box_triangle_contact(V3 boxCenter, const M3& rot, V3 halfExt, V3 core, float marginA, const Tri& t, float breaking,
-                                       V3& normalOnB, V3& pointOnB, float& dist) {
-    float maxDist = marginA + 0.f + breaking;
-    auto supB = [&](V3 axis) {  // btTriangleShape::localGetSupportingVertexWithoutMargin(axis * basisB), basisB = I
-        float d0 = dot(axis, t.v0), d1 = dot(axis, t.v1), d2 = dot(axis, t.v2);
+RL_HD RL_NOINLINE inline bool box_triangle_contact(V3 boxCenter, const M3& rot, V3 core, float marginA, const Tri& t, float breaking, EpaWs* ws,
+                                                   V3& normalOnB, V3& pointOnB, float& dist) {
+    const float maxDist = marginA + 0.f + breaking;
+    const V3 v0 = t.v0, v1 = t.v1, v2 = t.v2;
+    auto supWorld = [&](V3 axis) {  // btTriangleShape::localGetSupportingVertexWithoutMargin(axis * basisB), basisB = I
+        float d0 = dot(axis, v0), d1 = dot(axis, v1), d2 = dot(axis, v2);
         int mi = d0 < d1 ? (d1 < d2 ? 2 : 1) : (d0 < d2 ? 2 : 0);
-        return mi == 0 ? t.v0 : (mi == 1 ? t.v1 : t.v2);
+        return mi == 0 ? v0 : (mi == 1 ? v1 : v2);
     };
-    V3 pA, pB, axis; float sq; bool tooFar;
-    if (gjk_box_core(boxCenter, rot, core, V3(), supB, maxDist * maxDist, pA, pB, axis, sq, tooFar)) {
-        float lenSqr = len2(axis);
-        float rlen = 1.f / sqrtf(lenSqr);
-        V3 n = axis * rlen;
-        float s = sqrtf(sq);
-        V3 pointB = pB + axis * (0.f / s);
-        float distance = (1.f / rlen) - marginA;
-        bool catchDegenerate = (distance + marginA) < 0.01f;  // m_catchDegeneracies path re-checks with the penetration solver
-        if (!catchDegenerate) {
-            if (distance < 0 || distance * distance < maxDist * maxDist) { normalOnB = n; pointOnB = pointB; dist = distance; return true; }
-            return false;
-        }
-        V3 n2, p2; float d2;
-        if (box_triangle_sat(boxCenter, rot, halfExt, t, n2, p2, d2) && d2 < distance) { normalOnB = n2; pointOnB = p2; dist = d2; return true; }
-        normalOnB = n; pointOnB = pointB; dist = distance;
-        return distance < 0 || distance * distance < maxDist * maxDist;
+    const V3 offset = boxCenter * 0.5f;  // (originA + originB) / 2, originB = 0
+    const V3 cA = boxCenter - offset;
+    GjkOut g;
+    gjk_box_core(cA, rot, core, offset, supWorld, maxDist * maxDist, g);
+    bool isValid = false;
+    V3 normalInB(0, 0, 0), pB = g.pB;
+    float distance = 0.f;
+    if (g.valid) {
+        const float rlen = 1.f / sqrtf(len2(g.axis));
+        normalInB = g.axis * rlen;
+        const float s = sqrtf(g.sqDist);
+        pB = g.pB + g.axis * (0.f / s);  // marginB = 0
+        distance = (1.f / rlen) - marginA;
+        isValid = true;
     }
-    return box_triangle_sat(boxCenter, rot, halfExt, t, normalOnB, pointOnB, dist);
+    auto supLocal = [v0, v1, v2](V3 dir, bool withMargin) {  // btConvexShape::localGetSupportVertex[WithoutMargin]NonVirtual, triangle, margin 0
+        V3 dn = dir;
+        if (withMargin) {
+            if (len2(dn) < kEps * kEps) dn = V3(-1, -1, -1);
+            dn = normalized(dn);
+        }
+        float d0 = dot(dn, v0), d1 = dot(dn, v1), d2 = dot(dn, v2);
+        int mi = d0 < d1 ? (d1 < d2 ? 2 : 1) : (d0 < d2 ? 2 : 0);
+        return mi == 0 ? v0 : (mi == 1 ? v1 : v2);
+    };
+    // centre of the triangle's bounding box in the shifted frame (btPolyhedralConvexShape::getAabb via the support mapping, margin 0)
+    const V3 oB = V3() - offset;
+    const V3 posB = ((vmin(vmin(v0, v1), v2) + oB) + (vmax(vmax(v0, v1), v2) + oB)) * 0.5f;
+    return pair_finish(isValid, g.degenerate != 0, normalInB, pB, distance, cA, rot, core, marginA, 0.f, oB, supLocal, posB, offset, maxDist * maxDist, ws, normalOnB,
+                       pointOnB, dist);
 }
 
 // ---- box vs box (btBoxBoxDetector / ODE dBoxBox2) --------------------------------------------------

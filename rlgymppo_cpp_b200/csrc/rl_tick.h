@@ -91,6 +91,7 @@ RL_HD inline void pads_post_tick(ArenaS& a, const SimCfg& cfg, const uint64_t* h
 
 #ifdef RL_DEBUG_CONTACTS
 static ContactSet g_dbg_contacts;
+static CarW g_dbg_carw[kMaxCars];  // the wheels' workspace after the last tick (host debugging only)
 #endif
 
 // ---- one physics tick, split by ROLE ------------------------------------------------------------------------------
@@ -134,6 +135,7 @@ RL_HDI void tick_s0_ball(const ArenaS& a, TickX x) {
     x.h->ballPos = a.ball.pos; x.h->ballVel = a.ball.vel; x.h->ballAngvel = a.ball.angvel;
     // ball zero-velocity sleeping (Arena.cpp:721-727)
     x.h->ballActive = !(len2(a.ball.vel) == 0.f && len2(a.ball.angvel) == 0.f);
+    x.h->solverDt = a.worldStepped ? kTickTime : (1.f / 60.f);
 }
 
 // tick_p1_car = pose (respawn, mesh candidates) + mesh part of the wheel rays + begin (vehicle update, control model,
@@ -152,7 +154,7 @@ RL_HD inline void tick_p1_car_pose(ArenaS& a, TickX x, const SimCfg& cfg, const 
 }
 // between the two: w.meshHit (+ the hitbox pre-filter) from wheel_mesh_rays or the role kernel's cooperative pass
 RL_HD inline void tick_p1_car_begin(ArenaS& a, TickX x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, const Thresholds& thr, int c, CarW& w,
-                                    Contact* scratch, int firstTickOfStep, CollideCtx& cx, ContactSink& cw) {
+                                    Contact* scratch, int firstTickOfStep, CollideCtx& cx, ContactSink& cw, EpaWs* epa = nullptr) {
     CarS& car = a.cars[c];
     CarX& o = x.car[c];
     car_pre_tick_b(car, x, cfg, ms, k, c, w);
@@ -162,7 +164,7 @@ RL_HD inline void tick_p1_car_begin(ArenaS& a, TickX x, const SimCfg& cfg, const
     V3 ext(dot(vabs(car.rot.r[0]), k.halfExt), dot(vabs(car.rot.r[1]), k.halfExt), dot(vabs(car.rot.r[2]), k.halfExt));
     o.cmn = center - ext; o.cmx = center + ext;
 
-    cx.a = &a; cx.cfg = &cfg; cx.tx = x; cx.k = &k; cx.tick = get_i64(a.tickLo, a.tickHi); cx.firstTickOfStep = firstTickOfStep;
+    cx.a = &a; cx.cfg = &cfg; cx.tx = x; cx.k = &k; cx.tick = get_i64(a.tickLo, a.tickHi); cx.firstTickOfStep = firstTickOfStep; cx.epa = epa;
     cx.ballPos = x.h->ballPos; cx.ballVel = x.h->ballVel * cfg.ballDampFactor;  // predictUnconstraintMotion damping precedes the narrowphase
     // car-ball (manifold order: all car-ball pairs precede the car-world pairs)
     ContactSink cb = make_sink(seg_car(scratch, c), 1);
@@ -198,7 +200,7 @@ RL_HD inline void tick_p1_ball(ArenaS& a, TickX x, const SimCfg& cfg, const Mesh
     RL_PT(-1);
     if (cfg.numCars > 0) pads_pre_tick(a);
     RL_PT(7);
-    CollideCtx cx; cx.a = &a; cx.cfg = &cfg; cx.tx = x; cx.k = &k; cx.tick = get_i64(a.tickLo, a.tickHi); cx.firstTickOfStep = 0;
+    CollideCtx cx; cx.a = &a; cx.cfg = &cfg; cx.tx = x; cx.k = &k; cx.tick = get_i64(a.tickLo, a.tickHi); cx.firstTickOfStep = 0; cx.epa = nullptr;
     cx.ballPos = x.h->ballPos; cx.ballVel = x.h->ballVel * cfg.ballDampFactor;
     ContactSink cs = make_sink(seg_ball(scratch), kSegBall);
     // a sleeping ball vs the (always "sleeping") static bodies is skipped by btCollisionDispatcher::needsCollision
@@ -291,8 +293,8 @@ RL_HD inline void tick_p2_solve(ArenaS& a, TickX x, const SimCfg& cfg, const Car
             if (car_is_coupled(x, P, c)) coupled |= 1u << c;
         }
     }
-    // car-car pairs in the reference's pair order; contacts of pair (c, d) carry a == 1 + c
-    CollideCtx cx; cx.a = &a; cx.cfg = &cfg; cx.tx = x; cx.k = &k; cx.tick = tick; cx.firstTickOfStep = firstTickOfStep;
+    // car-car pairs in the reference's pair order; contacts of pair (c, d > c) carry b == 1 + c, a == 1 + d (car_car)
+    CollideCtx cx; cx.a = &a; cx.cfg = &cfg; cx.tx = x; cx.k = &k; cx.tick = tick; cx.firstTickOfStep = firstTickOfStep; cx.epa = nullptr;
     cx.ballPos = x.h->ballPos; cx.ballVel = a.ball.vel;
     ContactSink cp = make_sink(seg_pair(scratch, P), kSegPair);
     for (int c = 0; c < P; c++)
@@ -314,7 +316,7 @@ RL_HD inline void tick_p2_solve(ArenaS& a, TickX x, const SimCfg& cfg, const Car
         for (int c = 0; c < P; c++) {
             take(seg_car(scratch, c) + 1, x.car[c].nCarWorld);
             const Contact* pr = seg_pair(scratch, P);
-            for (int i = 0; i < cp.n; i++) if (pr[i].a == 1 + c) take(pr + i, 1);
+            for (int i = 0; i < cp.n; i++) if (pr[i].b == 1 + c) take(pr + i, 1);
         }
     }
 #endif
@@ -363,7 +365,7 @@ RL_HD inline void tick_p2_solve(ArenaS& a, TickX x, const SimCfg& cfg, const Car
             if (!((coupled >> c) & 1u)) continue;
             take(seg_car(scratch, c) + 1, x.car[c].nCarWorld);
             const Contact* pr = seg_pair(scratch, P);
-            for (int i = 0; i < cp.n; i++) if (pr[i].a == 1 + c) take(pr + i, 1);
+            for (int i = 0; i < cp.n; i++) if (pr[i].b == 1 + c) take(pr + i, 1);
         }
         for (int c = 0; c < P; c++) {
             if ((coupled >> c) & 1u) solver_body_from_car(sb[1 + c], a.cars[c], x.car[c], k);
@@ -393,6 +395,7 @@ RL_HD inline void tick_p2_solve(ArenaS& a, TickX x, const SimCfg& cfg, const Car
         if (len2(a.ball.angvel) > C::BALL_MAX_ANG_SPEED * C::BALL_MAX_ANG_SPEED) a.ball.angvel = normalized(a.ball.angvel) * C::BALL_MAX_ANG_SPEED;
     }
     a.ball.updateCounterLo++;
+    a.worldStepped = 1;
     set_i64(a.tickLo, a.tickHi, tick + 1);
     RL_PT(12);
 }
@@ -401,7 +404,13 @@ RL_HD inline void tick_p3_car(ArenaS& a, TickX x, const Tables& tb, const CarCon
     CarS& car = a.cars[c];
     CarX& o = x.car[c];
     RL_PT(-1);
-    if (!o.noResponse) integrate_transform(car.pos, car.rot, car.vel, car.angvel, kTickTime);
+    if (!o.noResponse) {
+        integrate_transform(car.pos, car.rot, car.vel, car.angvel, kTickTime);
+        // demolished during this tick: the body still integrates, but Car::_PostTickUpdate returns before it refreshes
+        // CarState::rotMat (Car.cpp:133-138), so the rotation every reader sees (GetState -> obs, the next SetState)
+        // stays the start-of-tick one until the respawn replaces it
+        if (car.isDemoed) car.rot = o.rot;
+    }
     w.velCache = o.velCache;
     car_post_tick(car, w);
     uint64_t hit = pads_check_car(a, tb, k, c);
@@ -436,6 +445,9 @@ RL_HD inline void arena_tick(ArenaS& a, const SimCfg& cfg, const MeshSet& ms, co
     tick_p2_solve(a, x, cfg, k, thr, scratch, firstTickOfStep);
     for (int c = 0; c < P; c++) if (!self[c]) tick_p3_car(a, x, tb, k, c, w[c]);
     tick_p4_pads(a, x, cfg);
+#if defined(RL_DEBUG_CONTACTS) && !defined(__CUDA_ARCH__)
+    for (int c = 0; c < P; c++) g_dbg_carw[c] = w[c];
+#endif
 }
 
 // ---- Gym::Step (G/Gym.cpp:68-102) + GameInst::Step auto-reset --------------------------------------

@@ -13,12 +13,26 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 # "close enough" is BallState::Matches(0.8 uu, 0.4 uu/s, 0.02 rad/s) (RocketSim Ball.cpp:12-17); ticks
 # without hitbox-vs-world contact are required to be ~1000x tighter than that.
 TOL_TIGHT = dict(pos=2e-3, vel=2e-2, ang=2e-4, rot=2e-5)
-# ticks in which a car hitbox touches the world or another car: the reference resolves deep penetration with EPA on a
-# rounded box and orders solver rows through an unstable quicksort; we use an exact SAT and a fixed order.
-TOL_CONTACT = dict(pos=4.0, vel=320.0, ang=3.0, rot=0.1)
+# A handful of ticks with a deep hitbox contact leave TOL_TIGHT: the penetration-depth search (GJK + EPA on the rounded box,
+# rl_epa.h) takes threshold decisions (1e-4 accuracy, duplicate-vertex and plane epsilons) on values the reference computes
+# with SSE reciprocal-square-root estimates, so single iterations can differ.  They must still meet the reference's own
+# notion of "the same state", BallState::Matches (Ball.cpp:12-17: 0.8 uu, 0.4 uu/s, 0.02 rad/s) — pos 8x tighter here — and
+# may be at most 0.5 % of a recording's ticks (measured, profiles/parity_r02_*.json: host build 1 of 13 712, 0.026 uu/s).
+TOL_CONTACT = dict(pos=0.1, vel=0.4, ang=0.02, rot=1e-3)
+ALLOW_CONTACT_FRAC = 0.005
+
+# every tick test appends its summary here; the -m gpu session writes it to profiles/parity_r02_gpu.json (conftest.py)
+PARITY_LOG = {}
+_current_fixture = [None]
+
+
+def record_parity(groups, res):
+    name = _current_fixture[0] or "+".join(sorted(groups))[:60]
+    PARITY_LOG[name] = dict(res)
 
 
 def load_tick_file(name):
+    _current_fixture[0] = name
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
     groups = {}
     for k in z.files:
@@ -49,45 +63,87 @@ def within(e, tol):
     return all(e[k] <= tol[k] for k in tol)
 
 
-def check_single_tick_run(groups, set_state, tick, get_state, allow_contact_frac=0.06):
+class _TickTally:
+    """Classifies every (reference state before, one tick, state after) experiment: inside TOL_TIGHT, inside TOL_CONTACT
+    ("loose"), or a failure."""
+
+    def __init__(self):
+        self.total = 0
+        self.loose = 0
+        self.worst = dict(pos=0.0, vel=0.0, ang=0.0, rot=0.0)
+        self.worst_loose = dict(pos=0.0, vel=0.0, ang=0.0, rot=0.0)
+        self.loose_ticks = []
+        self.failures = []
+
+    def add(self, gname, t, g, cars1, ball1, pads1, tick1):
+        # Car::Respawn picks one of the team's four respawn spots with the global RNG (Car.cpp:43-56, RLConst.h
+        # CAR_RESPAWN_LOCATIONS): the engine's per-arena RNG differs by construction, so on the tick a car respawns its spot
+        # is checked for membership and the reference's x is taken for the comparison (y, z, yaw are the same for all four)
+        resp = (g["cars"][t]["is_demoed"] != 0) & (g["cars"][t + 1]["is_demoed"] == 0)
+        if resp.any():
+            cars1 = cars1.copy()
+            for ci in np.nonzero(resp)[0]:
+                assert min(abs(abs(float(cars1["pos"][ci][0])) - v) for v in (2304.0, 2688.0)) < 1e-2, (gname, t, cars1["pos"][ci])
+                cars1["pos"][ci][0] = g["cars"][t + 1]["pos"][ci][0]
+        e = phys_err(g["cars"][t + 1], g["ball"][t + 1:t + 2], cars1, ball1)
+        self.total += 1
+        flags_ok = all(np.array_equal(g["cars"][t + 1][f] != 0, cars1[f] != 0) for f in FLAGS)
+        scal_ok = all(np.allclose(g["cars"][t + 1][f], cars1[f], atol=1e-4, rtol=1e-5) for f in SCALARS)
+        pads_ok = np.array_equal(g["pads"][t + 1]["is_active"] != 0, pads1["is_active"] != 0)
+        if within(e, TOL_TIGHT) and flags_ok and scal_ok and pads_ok and tick1 == int(g["tick"][t + 1]):
+            for k in self.worst:
+                self.worst[k] = max(self.worst[k], e[k])
+        elif within(e, TOL_CONTACT) and flags_ok and scal_ok and pads_ok:
+            self.loose += 1
+            for k in self.worst_loose:
+                self.worst_loose[k] = max(self.worst_loose[k], e[k])
+            self.loose_ticks.append((gname, t, {k: round(v, 5) for k, v in e.items()}))
+        else:
+            self.failures.append((gname, t, e, flags_ok, scal_ok, pads_ok))
+
+    def finish(self, groups, allow_contact_frac, detail):
+        assert not self.failures, f"{len(self.failures)} ticks outside the contact tolerance, first: {self.failures[:3]}"
+        assert self.loose <= allow_contact_frac * self.total, f"{self.loose}/{self.total} ticks needed the loose contact tolerance: {self.loose_ticks[:5]}"
+        res = dict(total=self.total, loose=self.loose, worst_tight=self.worst, worst_loose=self.worst_loose)
+        if detail:
+            res["loose_ticks"] = self.loose_ticks
+        record_parity(groups, res)
+        return res
+
+
+def check_single_tick_run(groups, set_state, tick, get_state, allow_contact_frac=ALLOW_CONTACT_FRAC, detail=False):
     """For every recorded reference tick: inject the reference state BEFORE the tick, run one tick with the recorded
     controls, compare with the reference state AFTER the tick. Returns a summary dict; raises on violations."""
-    total = 0
-    loose = 0
-    worst = dict(pos=0.0, vel=0.0, ang=0.0, rot=0.0)
-    failures = []
+    tally = _TickTally()
+    # the fixtures are recorded on a world that has already stepped (make_golden.record): step ours once too, so the
+    # cold-start quirk of a world's very first vehicle update (ArenaS::worldStepped) stays out of the comparison
+    g0 = next(iter(groups.values()))
+    set_state(g0["cars"][0], g0["ball"][0:1], g0["pads"][0], int(g0["tick"][0]))
+    tick(g0["controls"][0])
     for gname, g in groups.items():
-        T = len(g["controls"])
-        for t in range(T):
-            cars0, ball0, pads0, tick0 = g["cars"][t], g["ball"][t:t + 1], g["pads"][t], int(g["tick"][t])
-            set_state(cars0, ball0, pads0, tick0)
+        for t in range(len(g["controls"])):
+            set_state(g["cars"][t], g["ball"][t:t + 1], g["pads"][t], int(g["tick"][t]))
             tick(g["controls"][t])
             cars1, ball1, pads1, tick1 = get_state()
-            # Car::Respawn picks one of the team's four respawn spots with the global RNG (Car.cpp:43-56, RLConst.h
-            # CAR_RESPAWN_LOCATIONS): the engine's per-arena RNG differs by construction, so on the tick a car respawns its spot
-            # is checked for membership and the reference's x is taken for the comparison (y, z, yaw are the same for all four)
-            resp = (g["cars"][t]["is_demoed"] != 0) & (g["cars"][t + 1]["is_demoed"] == 0)
-            if resp.any():
-                cars1 = cars1.copy()
-                for ci in np.nonzero(resp)[0]:
-                    assert min(abs(abs(float(cars1["pos"][ci][0])) - v) for v in (2304.0, 2688.0)) < 1e-2, (gname, t, cars1["pos"][ci])
-                    cars1["pos"][ci][0] = g["cars"][t + 1]["pos"][ci][0]
-            e = phys_err(g["cars"][t + 1], g["ball"][t + 1:t + 2], cars1, ball1)
-            total += 1
-            flags_ok = all(np.array_equal(g["cars"][t + 1][f] != 0, cars1[f] != 0) for f in FLAGS)
-            scal_ok = all(np.allclose(g["cars"][t + 1][f], cars1[f], atol=1e-4, rtol=1e-5) for f in SCALARS)
-            pads_ok = np.array_equal(g["pads"][t + 1]["is_active"] != 0, pads1["is_active"] != 0)
-            if within(e, TOL_TIGHT) and flags_ok and scal_ok and pads_ok and tick1 == int(g["tick"][t + 1]):
-                for k in worst:
-                    worst[k] = max(worst[k], e[k])
-                continue
-            if within(e, TOL_CONTACT) and pads_ok:
-                loose += 1
-                continue
-            failures.append((gname, t, e, flags_ok, scal_ok, pads_ok))
-    assert not failures, f"{len(failures)} ticks outside the contact tolerance, first: {failures[:3]}"
-    assert loose <= allow_contact_frac * total, f"{loose}/{total} ticks needed the loose contact tolerance"
-    return dict(total=total, loose=loose, worst_tight=worst)
+            tally.add(gname, t, g, cars1, ball1, pads1, tick1)
+    return tally.finish(groups, allow_contact_frac, detail)
+
+
+def check_single_tick_batch(groups, run_batch, allow_contact_frac=ALLOW_CONTACT_FRAC, detail=False):
+    """The same experiment with every recorded tick of the file in its own arena of ONE engine: run_batch(cars [N,P], balls [N],
+    pads [N,34], ticks [N], controls [N,P]) injects state i into arena i, steps all arenas one tick with their own controls and
+    returns the states after (it also steps the engine once beforehand, see check_single_tick_run)."""
+    index = [(gname, t) for gname, g in groups.items() for t in range(len(g["controls"]))]
+    cars = np.stack([groups[n]["cars"][t] for n, t in index])
+    balls = np.stack([groups[n]["ball"][t] for n, t in index])
+    pads = np.stack([groups[n]["pads"][t] for n, t in index])
+    ticks = np.array([int(groups[n]["tick"][t]) for n, t in index], dtype=np.int64)
+    ctl = np.stack([groups[n]["controls"][t] for n, t in index])
+    cars1, balls1, pads1, ticks1 = run_batch(cars, balls, pads, ticks, ctl)
+    tally = _TickTally()
+    for i, (gname, t) in enumerate(index):
+        tally.add(gname, t, groups[gname], cars1[i], balls1[i:i + 1], pads1[i], int(ticks1[i]))
+    return tally.finish(groups, allow_contact_frac, detail)
 
 
 CAR_PRESETS = ((1, "dominus"), (2, "plank"), (3, "breakout"), (4, "hybrid"), (5, "merc"))

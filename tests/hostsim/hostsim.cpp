@@ -155,6 +155,56 @@ int hs_dump_contacts(float* out, int maxRows) {
     }
     return n;
 }
+// debug: wheel rays of the last tick: rows {contact point xyz, normal xyz, suspension length, in contact, ground} per wheel
+void hs_dump_wheels(int car, float* out) {
+    for (int i = 0; i < 4; i++) {
+        const WheelW& w = g_dbg_carw[car].w[i];
+        float* r = out + 9 * i;
+        for (int k = 0; k < 3; k++) { r[k] = w.contactPoint[k]; r[3 + k] = w.contactNormal[k]; }
+        r[6] = w.suspLen; r[7] = (float)w.inContact; r[8] = (float)w.ground;
+    }
+}
+// unit probes of the narrowphase (same argument layout as oracle/ref_harness.cpp ref_probe_*): boxT = origin xyz + basis rows,
+// halfExt = the btBoxShape constructor argument (half extents WITH margin); out = {normal xyz, point xyz, depth}
+static void probe_box(const float* halfExt, const float* boxT, V3& center, M3& rot, V3& core, float& margin) {
+    center = V3(boxT[0], boxT[1], boxT[2]);
+    rot = M3(V3(boxT[3], boxT[4], boxT[5]), V3(boxT[6], boxT[7], boxT[8]), V3(boxT[9], boxT[10], boxT[11]));
+    // btBoxShape(halfExtents): implicit dimensions = halfExtents - 0.04, THEN setSafeMargin may shrink the margin (btBoxShape.cpp:17-26)
+    float mn = fminf_(fminf_(halfExt[0], halfExt[1]), halfExt[2]);
+    margin = fminf_(0.04f, 0.1f * mn);
+    core = V3(halfExt[0] - 0.04f, halfExt[1] - 0.04f, halfExt[2] - 0.04f);
+}
+int hs_probe_box_triangle(const float* halfExt, const float* boxT, const float* tri, float breaking, float* out) {
+    V3 c, core; M3 r; float margin;
+    probe_box(halfExt, boxT, c, r, core, margin);
+    Tri t; t.v0 = V3(tri[0], tri[1], tri[2]); t.v1 = V3(tri[3], tri[4], tri[5]); t.v2 = V3(tri[6], tri[7], tri[8]);
+    V3 n, p; float d;
+    if (!box_triangle_contact(c, r, core, margin, t, breaking, nullptr, n, p, d)) return 0;
+    for (int k = 0; k < 3; k++) { out[k] = n[k]; out[3 + k] = p[k]; }
+    out[6] = d;
+    return 1;
+}
+int hs_probe_box_sphere(const float* halfExt, const float* boxT, const float* center, float radius, float breaking, float* out) {
+    V3 c, core; M3 r; float margin;
+    probe_box(halfExt, boxT, c, r, core, margin);
+    V3 n, p; float d;
+    if (!box_sphere_contact(c, r, core, margin, V3(center[0], center[1], center[2]), radius, breaking, nullptr, n, p, d)) return 0;
+    for (int k = 0; k < 3; k++) { out[k] = n[k]; out[3 + k] = p[k]; }
+    out[6] = d;
+    return 1;
+}
+int hs_probe_box_box(const float* halfA, const float* tA, const float* halfB, const float* tB, float* out, int cap) {
+    V3 ca(tA[0], tA[1], tA[2]), cb(tB[0], tB[1], tB[2]);
+    M3 ra(V3(tA[3], tA[4], tA[5]), V3(tA[6], tA[7], tA[8]), V3(tA[9], tA[10], tA[11])), rb(V3(tB[3], tB[4], tB[5]), V3(tB[6], tB[7], tB[8]), V3(tB[9], tB[10], tB[11]));
+    // btBoxBoxDetector works on getHalfExtentsWithMargin() = (requested - 0.04) + the safe margin
+    V3 c0, coreA, coreB; M3 r0; float mA, mB;
+    probe_box(halfA, tA, c0, r0, coreA, mA);
+    probe_box(halfB, tB, c0, r0, coreB, mB);
+    BoxBoxResult r;
+    box_box(ca, ra, coreA + V3(mA, mA, mA), cb, rb, coreB + V3(mB, mB, mB), r);
+    for (int i = 0; i < r.n && i < cap; i++) { float* o = out + 7 * i; for (int k = 0; k < 3; k++) { o[k] = r.normal[k]; o[3 + k] = r.point[i][k]; } o[6] = r.depth[i]; }
+    return r.n;
+}
 size_t hs_sizeof_arena() { return sizeof(ArenaS); }
 
 // leaf grid vs stackless BVH walk on random query boxes (centres over the whole arena incl. the goal boxes, half extents

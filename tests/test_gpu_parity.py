@@ -55,46 +55,59 @@ def test_action_table(golden_dir):
     assert np.array_equal(engine.action_table(), np.load(os.path.join(golden_dir, "action_table.npy")))
 
 
+def _batch_runner(team, torch, **kw):
+    """Every recorded tick of a fixture in its own arena of ONE engine: N injected states, one launch, N states read back (the
+    role kernel at a realistic block shape — groups of 32 arenas with mixed situations per warp — instead of one live lane)."""
+    def run(cars, balls, pads, ticks, ctl):
+        n = len(ticks)
+        e = _engine(team, n=n, **kw)
+        ids = np.arange(n, dtype=np.int32)
+        buf = torch.from_numpy(np.frombuffer(np.ascontiguousarray(ctl).tobytes(), dtype=np.uint8).copy()).cuda()
+        e.tick_device(buf.data_ptr(), 1)  # the fixtures come from worlds that have stepped before (common.check_single_tick_run)
+        e.set_state(ids, np.ascontiguousarray(cars), np.ascontiguousarray(balls), np.ascontiguousarray(pads), ticks)
+        e.tick_device(buf.data_ptr(), 1)
+        e.sync()
+        return e.get_state(ids)
+    return run
+
+
+def _tick_file(name, team, torch, **kw):
+    res = common.check_single_tick_batch(common.load_tick_file(name), _batch_runner(team, torch, **kw), detail=True)
+    print(name, res)
+    return res
+
+
 def test_single_tick_scenarios_1v1(torch_cuda):
+    _tick_file("tick_scenarios_1v1", 1, torch_cuda)
+    # ... and the one-arena-at-a-time protocol on a slice of it (a single live lane per warp)
     r = _TickRunner(1, torch_cuda)
-    res = common.check_single_tick_run(common.load_tick_file("tick_scenarios_1v1"), r.set_state, r.tick, r.get_state)
-    print(res)
+    g = common.load_tick_file("tick_scenarios_1v1")
+    common.check_single_tick_run({k: g[k] for k in ("car_hits_ball", "car_into_goal")}, r.set_state, r.tick, r.get_state)
 
 
 @pytest.mark.parametrize("team", [1, 2, 3])
 def test_single_tick_random_play(team, torch_cuda):
-    r = _TickRunner(team, torch_cuda)
-    res = common.check_single_tick_run(common.load_tick_file(f"tick_random_{team}v{team}"), r.set_state, r.tick, r.get_state,
-                                       allow_contact_frac=0.08)
-    print(res)
+    _tick_file(f"tick_random_{team}v{team}", team, torch_cuda)
 
 
 @pytest.mark.parametrize("preset,name", list(common.CAR_PRESETS))
 def test_single_tick_random_play_car_presets(preset, name, torch_cuda):
     """The five non-Octane CarConfigs (CarConfig.cpp:20-88) against the reference's trajectories, same tolerances."""
-    r = _TickRunner(1, torch_cuda, car_preset=preset)
-    res = common.check_single_tick_run(common.load_tick_file(f"tick_random_1v1_{name}"), r.set_state, r.tick, r.get_state,
-                                       allow_contact_frac=0.08)
-    print(res)
+    _tick_file(f"tick_random_1v1_{name}", 1, torch_cuda, car_preset=preset)
 
 
 @pytest.mark.parametrize("team", [1, 2])
 def test_single_tick_random_play_mutators(team, torch_cuda):
     """Non-default MutatorConfig (every honoured field changed, common.apply_test_mutators) against the reference's
     trajectories under the same mutators, same tolerances."""
-    r = _TickRunner(team, torch_cuda, mutate=common.apply_test_mutators)
-    res = common.check_single_tick_run(common.load_tick_file(f"tick_random_{team}v{team}_mutators"), r.set_state, r.tick, r.get_state,
-                                       allow_contact_frac=0.08)
-    print(res)
+    _tick_file(f"tick_random_{team}v{team}_mutators", team, torch_cuda, mutate=common.apply_test_mutators)
 
 
 def test_single_tick_scenarios_mutators(torch_cuda):
     """The scripted scenarios under the test mutators (demolition on contact, 1 s respawn, team-mate demolition, pad cooldowns,
     ball-hit scale, repeated flips) against the reference's recordings."""
-    r = _TickRunner(1, torch_cuda, mutate=common.apply_test_mutators)
-    print(common.check_single_tick_run(common.load_tick_file("tick_scenarios_1v1_mutators"), r.set_state, r.tick, r.get_state))
-    r = _TickRunner(2, torch_cuda, mutate=common.apply_test_mutators)
-    print(common.check_single_tick_run(common.load_tick_file("tick_scenarios_2v2_mutators"), r.set_state, r.tick, r.get_state))
+    _tick_file("tick_scenarios_1v1_mutators", 1, torch_cuda, mutate=common.apply_test_mutators)
+    _tick_file("tick_scenarios_2v2_mutators", 2, torch_cuda, mutate=common.apply_test_mutators)
 
 
 def test_mutators_unsupported_rejected():

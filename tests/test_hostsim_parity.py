@@ -32,7 +32,7 @@ def test_single_tick_scenarios_1v1():
 @pytest.mark.parametrize("team", [1, 2, 3])
 def test_single_tick_random_play(team):
     s, t, g = _runner(team)
-    res = common.check_single_tick_run(common.load_tick_file(f"tick_random_{team}v{team}"), s, t, g, allow_contact_frac=0.08)
+    res = common.check_single_tick_run(common.load_tick_file(f"tick_random_{team}v{team}"), s, t, g)
     print(res)
 
 
@@ -40,7 +40,7 @@ def test_single_tick_random_play(team):
 def test_single_tick_random_play_car_presets(preset, name):
     """The five non-Octane CarConfigs (CarConfig.cpp:20-88): hitbox, wheel and suspension geometry."""
     s, t, g = _runner(1, preset)
-    res = common.check_single_tick_run(common.load_tick_file(f"tick_random_1v1_{name}"), s, t, g, allow_contact_frac=0.08)
+    res = common.check_single_tick_run(common.load_tick_file(f"tick_random_1v1_{name}"), s, t, g)
     print(res)
 
 
@@ -50,7 +50,7 @@ def test_single_tick_random_play_mutators(team):
     components, drag, frictions / restitutions, jump and boost accelerations, pad cooldowns, demo-on-contact with team demos,
     unlimited flips): random play recorded from the reference under common.apply_test_mutators."""
     s, t, g = _runner(team, mutate=common.apply_test_mutators)
-    res = common.check_single_tick_run(common.load_tick_file(f"tick_random_{team}v{team}_mutators"), s, t, g, allow_contact_frac=0.08)
+    res = common.check_single_tick_run(common.load_tick_file(f"tick_random_{team}v{team}_mutators"), s, t, g)
     print(res)
 
 
