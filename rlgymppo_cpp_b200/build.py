@@ -16,6 +16,10 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 #    (obs, rewards, event tracker), which must be bit-exact against the FMA-free x86 reference build, uses the strict
 #    s_* helpers of rl_math.h and is unaffected by these flags.
 #  * everything else (collector.cu: GAE is bit-exact against the numpy oracle) stays IEEE without contraction.
+#    One consequence, measured (profiles/r02d_fp_model_ab.txt): with FMA contraction the GJK / EPA of deep hitbox contacts takes
+#    single threshold decisions differently and 6 of the 13 712 recorded reference ticks land up to 0.09 uu / 2.8 uu/s from the
+#    reference instead of < 0.03 uu/s (no-FMA builds reproduce the host build's parity exactly); compiling only that code IEEE needs a
+#    second translation unit + relocatable device code, which costs the role kernel 28 % (1.26 -> 1.61 ms), so it stays fast.
 FP_FLAGS = {"engine.cu": ["-fmad=true", "-prec-div=false", "-prec-sqrt=false"]}
 FP_DEFAULT = ["-fmad=false"]
 

@@ -55,7 +55,7 @@ struct rlg_engine {
     cudaStream_t copyStream = nullptr; cudaEvent_t evFirst = nullptr;  // host-buffer step: D2H of the results overlaps ticks 1..
     int32_t* resetCount = nullptr; int32_t* hResetCount = nullptr; int32_t* hResetIds = nullptr; float* hResetObs = nullptr;
     int32_t* dResetIds = nullptr; float* dResetObs = nullptr;  // device views of the two mapped host buffers
-    EpaWs* epa = nullptr;        // [block][warp] penetration-depth workspaces of the role kernel
+    unsigned char* epa = nullptr;  // [block] full-size penetration-depth workspaces of the role kernel
     float* metrics = nullptr;    // [kMetricWords][A]: stepTotal, stepCount (u32), epTotal, epCount (u32), curEpRew, totalSteps (u32)
     int xwords = 0, stride = 0, scratchSlots = 0;
     int arenasPerBlock = 32, groupsPerBlock = 1;
@@ -162,7 +162,7 @@ struct RolesArgs {
     int32_t* resetCount; int32_t* resetIds; float* resetObs;
     const int32_t* actions; float* obs; float* reward; uint8_t* done; int autoReset;
     float* metrics;  // GameInst reward metrics, word-transposed [kMetricWords][A] (nullptr: not tracked)
-    EpaWs* epa;      // [block][warp] penetration-depth workspaces (rl_epa.h): deep hitbox contacts are rare, a warp's lanes take turns
+    unsigned char* epa;  // [block][kEpaFullBytes] full-size penetration-depth workspaces (rl_epa.h), used when a warp's small one overflows
 };
 constexpr int kMetricWords = 6;
 
@@ -194,6 +194,10 @@ __device__ __forceinline__ void cp_async4(uint32_t* smemDst, const uint32_t* gme
 constexpr int kWqItems = 128;                      // pairs queued per warp and pass
 constexpr int kWqResWords = 8;
 constexpr int kWqWords = kWqItems + 32 * kWqResWords;
+// one small penetration-depth workspace per block (rl_epa.h: lock word + storage), behind the queues.  Shared memory is
+// budgeted to the byte: at 16 384 arenas a block's slots + queues + this stay under the 196 KiB carve-out step, which leaves
+// the L1 its 60 KiB for the per-thread stacks (the next step, 228 KiB, costs 0.19 ms per launch).
+constexpr int kEpaSmallWords = (int)(kEpaSmallBytes / 4);
 
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 #pragma unroll
@@ -340,7 +344,7 @@ __device__ __forceinline__ void cands_pass_warp(CarW& w, int ci, bool active, co
 
 // Pass 2 (after car-ball): hitbox vs the pre-filtered candidate triangles -> the car's car-world contact segment.
 __device__ __forceinline__ void box_meshes_warp(CollideCtx& cx, ContactSink& cw, const MeshSet& ms, const CarW& w, int ci, float breaking,
-                                                bool active, const CarConsts& k, const uint32_t* mine, uint32_t* wq, int stride, EpaWs* ws) {
+                                                bool active, const CarConsts& k, const uint32_t* mine, uint32_t* wq, int stride, const EpaCtx* ws) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const MeshCands& cands = w.cands;
@@ -434,6 +438,10 @@ __global__ void __maxnreg__(168) k_roles(const __grid_constant__ RolesArgs g) {
     const int barId = 1 + group, barThreads = 32 * roles;
 #define SYNC_GROUP() do { PT_WORK(9); if (g.barMode == 0) __syncthreads(); else bar_named(barId, barThreads); PT_WORK(7); } while (0)
 #define SYNC_TICK() do { PT_WORK(9); if (g.barMode == 1) bar_named(barId, barThreads); else __syncthreads(); PT_WORK(7); } while (0)
+    // penetration-depth workspaces: the block's small one behind the pair queues, its full-size one in global memory
+    uint32_t* epaSmall = smem + (size_t)g.arenasPerBlock * g.stride + (size_t)(blockDim.x >> 5) / roles * P * kWqWords;
+    const EpaCtx epaCtx = epa_ctx(epaSmall, g.epa + (size_t)blockIdx.x * kEpaFullBytes);
+    if (threadIdx.x == 0) epaSmall[0] = 0;  // lock free (ordered before its first use by the barriers below)
     PT_DECL();
     if (valid) {
         if (g.asyncLoad) {
@@ -476,8 +484,8 @@ __global__ void __maxnreg__(168) k_roles(const __grid_constant__ RolesArgs g) {
             if (valid) tick_p1_car_pose(s, x, g.cfg, g.ms, k, role - 1, w, false);
             collect_candidates_warp(w, role - 1, valid, k, g.ms, mine, wq);  // whole warp
             cands_pass_warp(w, role - 1, valid, k, g.ms, mine, wq, g.stride);  // whole warp
-            if (valid) tick_p1_car_begin(s, x, g.cfg, g.ms, k, thr, role - 1, w, scratch, first, cx, cw, g.epa + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp));
-            box_meshes_warp(cx, cw, g.ms, w, role - 1, thr.car, valid, k, mine, wq, g.stride, g.epa + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp));  // whole warp
+            if (valid) tick_p1_car_begin(s, x, g.cfg, g.ms, k, thr, role - 1, w, scratch, first, cx, cw, &epaCtx);
+            box_meshes_warp(cx, cw, g.ms, w, role - 1, thr.car, valid, k, mine, wq, g.stride, &epaCtx);  // whole warp
             if (valid) tick_p1_car_end(cx, cw, x, thr, role - 1);
         }
         PT_WORK(2);
@@ -611,6 +619,13 @@ int rlg_action_table(float* table_host) {
 int rlg_engine_destroy(rlg_engine* e) {
     if (!e) return RLG_OK;
     cudaSetDevice(e->device);
+#ifdef RLG_EPA_TIMING
+    {   // diagnostic build: time spent in the penetration-depth search
+        unsigned long long t[2] = {0, 0};
+        cudaMemcpyFromSymbol(t, g_epa_timing, sizeof(t));
+        fprintf(stderr, "[epa timing] calls %llu cycles %llu (%.0f per call), role launches %d\n", t[1], t[0], t[1] ? (double)t[0] / (double)t[1] : 0.0, (int)e->launches);
+    }
+#endif
 #ifdef RLG_PHASE_TIMING
     if (e->prof) {  // diagnostic build: dump the per-warp phase cycle counters
         const int blocks = (e->cfg.numArenas + e->arenasPerBlock - 1) / e->arenasPerBlock, warps = e->groupsPerBlock * (1 + e->cfg.numCars);
@@ -677,7 +692,7 @@ int rlg_engine_create(const rlg_engine_cfg* cfg, rlg_engine** out) {
         int perSm = (A + prop.multiProcessorCount - 1) / prop.multiProcessorCount;
         // per arena slot: its words + its share of the car warps' pair queues; slots are allocated in whole groups of 32
         // (the last group may be partial: keep one group's queues in reserve)
-        int maxBySmem = (int)((prop.sharedMemPerBlockOptin - 1024 - (size_t)P * kWqWords * 4) / (((size_t)e->stride + (size_t)P * kWqWords / 32) * 4));
+        int maxBySmem = (int)((prop.sharedMemPerBlockOptin - 1024 - (size_t)P * kWqWords * 4 - kEpaSmallBytes) / (((size_t)e->stride + (size_t)P * kWqWords / 32) * 4));
         cudaFuncAttributes fa;
         CKD(cudaFuncGetAttributes(&fa, k_roles));
         int maxThreads = prop.regsPerBlock / (fa.numRegs > 0 ? fa.numRegs : 1);
@@ -707,15 +722,15 @@ int rlg_engine_create(const rlg_engine_cfg* cfg, rlg_engine** out) {
         CKD(cudaMemcpyToSymbol(g_rl_pt, &e->prof2, sizeof(e->prof2)));
     }
 #endif
-    e->rolesSmem = ((size_t)e->arenasPerBlock * e->stride + (size_t)e->groupsPerBlock * P * kWqWords) * 4;
+    e->rolesSmem = ((size_t)e->arenasPerBlock * e->stride + (size_t)e->groupsPerBlock * P * kWqWords) * 4 + kEpaSmallBytes;
     CKD(cudaFuncSetAttribute(k_roles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->rolesSmem));
     if (const char* cv = getenv("RLG_SMEM_CARVEOUT")) CKD(cudaFuncSetAttribute(k_roles, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
     CKD(cudaMalloc(&e->state, (size_t)e->nwords * A * 4));
     CKD(cudaMalloc(&e->scratch, (size_t)A * e->scratchSlots * sizeof(Contact)));
-    {   // one penetration-depth workspace per warp of the role kernel's grid (their locks start free)
-        const size_t blocks = (A + e->arenasPerBlock - 1) / e->arenasPerBlock, warps = (size_t)e->groupsPerBlock * (1 + P);
-        CKD(cudaMalloc(&e->epa, blocks * warps * sizeof(EpaWs)));
-        CKD(cudaMemsetAsync(e->epa, 0, blocks * warps * sizeof(EpaWs), e->stream));
+    {   // one full-size penetration-depth workspace per block of the role kernel's grid (their locks start free)
+        const size_t blocks = (A + e->arenasPerBlock - 1) / e->arenasPerBlock;
+        CKD(cudaMalloc(&e->epa, blocks * kEpaFullBytes));
+        CKD(cudaMemsetAsync(e->epa, 0, blocks * kEpaFullBytes, e->stream));
     }
     CKD(cudaMalloc(&e->metrics, (size_t)kMetricWords * A * 4));
     CKD(cudaMemsetAsync(e->metrics, 0, (size_t)kMetricWords * A * 4, e->stream));

@@ -24,6 +24,11 @@ struct CarW {
     // candidate of every mesh (haveMask = 0: not computed, the narrowphase takes its serial path)
     uint32_t candMask, candGroupStart;
     int32_t haveMask;
+    // btContactSolverInfo::m_timeStep as this tick's vehicle update sees it: the tick time — except during the very first tick
+    // of an arena's life (tick count 0; the count only ever grows, Arena.cpp:810), when the field still holds its constructor
+    // default 1/60: it is set inside stepSimulation, after Car::_PreTickUpdate.  The wheels' extra push-back reads it
+    // (btVehicleRL.cpp:183-199 -> resolveSingleCollision).
+    float solverDt;
 };
 
 // ---- per-arena exchange between the roles of a tick (ball role + one role per car) --------------------------------
@@ -46,7 +51,6 @@ struct CarX {
 struct TickXHdr {
     V3 ballPos, ballVel, ballAngvel;  // start-of-tick snapshot (vel undamped)
     int32_t nBall, nPair, ballActive;
-    float solverDt;                   // btContactSolverInfo::m_timeStep as the vehicle update sees it (ArenaS::worldStepped)
 };
 constexpr int kTickXHdrWords = sizeof(TickXHdr) / 4;
 constexpr int kCarXWords = sizeof(CarX) / 4;
@@ -251,7 +255,7 @@ RL_HD inline void vehicle_first(CarS& c, const TickX& x, const SimCfg& cfg, cons
                     // (B/BulletDynamics/ConstraintSolver/btContactConstraint.cpp:60-106; m_erp = 0.2)
                     float delta = traceLen - thresh;
                     float rel_vel = dot(hit.normal, velAt);
-                    float positionalError = 0.2f * -delta / x.h->solverDt;
+                    float positionalError = 0.2f * -delta / w.solverDt;
                     float velocityError = -(1.0f + 0.f) * rel_vel;
                     float denom0 = impulse_denom(c.pos, w.invInertiaWorld, k.invMass, wh.contactPoint, hit.normal);
                     float jacDiagABInv = 1.f / (denom0 + 0.f);

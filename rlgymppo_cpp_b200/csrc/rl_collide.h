@@ -87,7 +87,7 @@ struct CollideCtx {
     int64_t tick;
     V3 ballPos, ballVel;      // the ball as the narrowphase sees it: start-of-tick position, DAMPED velocity
     int32_t firstTickOfStep;  // bump counters only stick when the callback fires during Gym::Step's first tick (see rl_tick.h)
-    EpaWs* epa;               // penetration-depth workspace (device: the warp's; host: nullptr = local, rl_epa.h)
+    const EpaCtx* epa;               // penetration-depth workspace (device: the warp's; host: nullptr = local, rl_epa.h)
 };
 
 // ---- Arena::_BulletContactAddedCallback ------------------------------------------------------
@@ -380,7 +380,7 @@ RL_HD inline void sphere_meshes(CollideCtx& x, ContactSink& cs, const MeshSet& m
 // one candidate triangle of the hitbox-vs-mesh narrowphase (shared by the direct walk and the candidate-list path)
 // The geometric part is a pure function of (car pose, triangle) — the role kernel evaluates it for many (car, triangle)
 // pairs at once, one pair per lane (engine.cu box_meshes_warp); the manifold bookkeeping stays with the car's own lane.
-RL_HDI bool box_mesh_item(const CarS& c, const CarConsts& k, V3 boxCenter, V3 mn, V3 mx, const Tri& t, float breaking, EpaWs* ws, V3& normal,
+RL_HDI bool box_mesh_item(const CarS& c, const CarConsts& k, V3 boxCenter, V3 mn, V3 mx, const Tri& t, float breaking, const EpaCtx* ws, V3& normal,
                           V3& pointOnB, float& dist) {
     if (!tri_vs_aabb(t, mn, mx)) return false;
     auto sup = [&](V3 d) {  // btBoxShape::localGetSupportingVertex (with margin)

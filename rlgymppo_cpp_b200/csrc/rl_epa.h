@@ -18,10 +18,15 @@
 // an EpaWs workspace (~13 KB): the host build puts it on the stack, the role kernel keeps one per warp in global memory
 // (contacts this deep are rare; lanes take turns — engine.cu).
 #pragma once
+#include <stddef.h>
 #include "rl_math.h"
 
 namespace rl {
 
+#if defined(RL_DEBUG_CONTACTS) && !defined(__CUDA_ARCH__)
+static long g_dbg_epa_overflows = 0;
+static long g_dbg_epa_calls = 0, g_dbg_epa_iters = 0, g_dbg_epa_maxface = 0, g_dbg_epa_maxsv = 0, g_dbg_epa_hist[8] = {0};  // host debugging only
+#endif
 constexpr int kEpaMaxVerts = 128, kEpaMaxFaces = 256, kEpaMaxIter = 255, kGjk2MaxIter = 128;
 constexpr float kGjk2Accuracy = 1e-4f, kGjk2MinDist = 1e-4f, kGjk2DupEps = 1e-4f;
 constexpr float kEpaAccuracy = 1e-4f, kEpaPlaneEps = 1e-5f;
@@ -36,13 +41,46 @@ struct EpaFace {
     uint8_t pass;
     RL_HDI EpaFace() : n(NoInit()) {}
 };
+// A workspace is a view of raw storage with capacities.  Full capacity (128 vertices / 256 faces) is the reference's; the
+// role kernel first runs in a SMALL workspace in shared memory (every evaluation seen in play fits: the high-water marks over
+// 600 k car-ticks of random play and the scripted wall / goal / ramp hits are 19 faces and 8 vertices) and repeats the
+// evaluation in the full-size one only if the small one runs out — the algorithm is deterministic, so a run that fits is the
+// same run.
 struct EpaWs {
-    int32_t lock;                    // device: taken by one lane at a time
-    int32_t pad_[3];
-    EpaSV sv[4 + kEpaMaxVerts];      // [0,4): the GJK simplex store, [4, 4+128): polytope vertices
-    EpaFace fc[kEpaMaxFaces];
-    uint16_t stack[2 * kEpaMaxFaces];  // horizon walk: (face << 2 | edge) << 2 | stage — two entries may be open per face
+    EpaSV* sv;        // [4 + maxVerts]: [0,4) the GJK simplex store, then the polytope vertices
+    EpaFace* fc;      // [maxFaces]
+    uint16_t* stack;  // [2 * maxFaces] horizon walk frames: (face << 4) | (edge << 2) | stage
+    int32_t maxVerts, maxFaces;
 };
+constexpr int kEpaSmallVerts = 10, kEpaSmallFaces = 24;
+RL_HDI constexpr size_t epa_ws_bytes(int verts, int faces) { return sizeof(EpaSV) * (4 + verts) + sizeof(EpaFace) * faces + 2 * 2 * faces; }
+// a workspace block = 16 bytes (lock word + padding) followed by the storage
+constexpr size_t kEpaSmallBytes = 16 + (epa_ws_bytes(kEpaSmallVerts, kEpaSmallFaces) + 15) / 16 * 16;
+constexpr size_t kEpaFullBytes = 16 + (epa_ws_bytes(kEpaMaxVerts, kEpaMaxFaces) + 15) / 16 * 16;
+
+RL_HDI EpaWs epa_ws_view(void* mem, int verts, int faces) {  // mem: 4-byte aligned, epa_ws_bytes(verts, faces) long
+    EpaWs w;
+    w.sv = reinterpret_cast<EpaSV*>(mem);
+    w.fc = reinterpret_cast<EpaFace*>(w.sv + 4 + verts);
+    w.stack = reinterpret_cast<uint16_t*>(w.fc + faces);
+    w.maxVerts = verts; w.maxFaces = faces;
+    return w;
+}
+#if !defined(__CUDA_ARCH__)
+static int g_epa_host_small_verts = kEpaSmallVerts, g_epa_host_small_faces = kEpaSmallFaces;  // tests shrink them to force the fallback
+#endif
+// What a caller hands down (device): the block's small workspace in shared memory and its full-size one in global memory,
+// each behind a lock word (lanes take turns; deep contacts are rare: ~5e-4 per car-tick in random play).  Host: nullptr = a local full-size workspace.
+struct EpaCtx {
+    int32_t* smallLock; void* smallMem;
+    int32_t* fullLock; void* fullMem;
+};
+RL_HDI EpaCtx epa_ctx(void* smallBlock, void* fullBlock) {
+    EpaCtx c;
+    c.smallLock = reinterpret_cast<int32_t*>(smallBlock); c.smallMem = reinterpret_cast<unsigned char*>(smallBlock) + 16;
+    c.fullLock = reinterpret_cast<int32_t*>(fullBlock); c.fullMem = reinterpret_cast<unsigned char*>(fullBlock) + 16;
+    return c;
+}
 
 // The Minkowski difference A - B in A's local frame (gjkepa2_impl::MinkowskiDiff).  A = box core (+ margin sphere),
 // B = any convex given by supB(dirInB, withMargin) in B's local frame.
@@ -70,25 +108,40 @@ struct Mink {
     RL_HDI V3 to_world(V3 p) const { return rotA * p + originA; }
 };
 
-// One evaluation at a time per workspace.  Device: the warp's lanes (and nobody else) share ws, so a lane takes ws->lock
-// for the duration; every entry of the workspace is written before it is read within one evaluation, so no stale data
-// of the previous holder is ever consumed.  Host (ws == nullptr): a local workspace.
-template <class F>
-RL_HDI void with_epa_ws(EpaWs* ws, F f) {
+// One evaluation at a time per workspace.  f(ws) returns false when the workspace ran out of room (small workspace only).
+// Every entry of a workspace is written before it is read within one evaluation, so nothing of the previous holder is consumed.
 #if defined(__CUDA_ARCH__)
-    bool done = false;
+template <class F>
+RL_HDI bool epa_locked(int32_t* lock, F f) {
+    bool done = false, ok = false;
     while (!done) {
-        if (atomicCAS(&ws->lock, 0, 1) == 0) {
-            f(ws);
-            __threadfence();
-            atomicExch(&ws->lock, 0);
+        if (atomicCAS(lock, 0, 1) == 0) {
+            ok = f();
+            __threadfence_block();
+            atomicExch(lock, 0);
             done = true;
         }
     }
+    return ok;
+}
+#endif
+template <class F>
+RL_HDI void with_epa_ws(const EpaCtx* ctx, F f) {
+#if defined(RLG_NO_EPA)  // A/B builds only: what the penetration-depth search costs
+    (void)ctx; (void)f;
+#elif defined(__CUDA_ARCH__)
+    if (epa_locked(ctx->smallLock, [&]() { EpaWs w = epa_ws_view(ctx->smallMem, kEpaSmallVerts, kEpaSmallFaces); return f(w); })) return;
+    epa_locked(ctx->fullLock, [&]() { EpaWs w = epa_ws_view(ctx->fullMem, kEpaMaxVerts, kEpaMaxFaces); return f(w); });
 #else
-    if (ws) { f(ws); return; }
-    EpaWs local;
-    f(&local);
+    (void)ctx;  // host test build: the same two-step protocol on local storage
+    static thread_local unsigned char mem[kEpaFullBytes];
+    EpaWs w = epa_ws_view(mem, g_epa_host_small_verts, g_epa_host_small_faces);
+    if (f(w)) return;
+#if defined(RL_DEBUG_CONTACTS)
+    g_dbg_epa_overflows++;
+#endif
+    w = epa_ws_view(mem, kEpaMaxVerts, kEpaMaxFaces);
+    f(w);
 #endif
 }
 
@@ -332,9 +385,14 @@ RL_HD inline bool gjk2_enclose_origin(Gjk2& g, EpaSV* store, const Sh& sh) {
 // ---- the polytope --------------------------------------------------------------------------------------------------
 struct EpaList { int root, count; };
 struct Epa {
-    EpaWs* ws;
-    EpaList hull, stock;
+    EpaWs ws;
+    EpaList hull, stock;  // stock: the faces handed back (LIFO) on top of the never-used range [fresh, maxFaces)
+    int fresh;
+    bool overflow;        // ran out of room in a workspace smaller than the reference's
     int nextsv;
+#if defined(RL_DEBUG_CONTACTS) && !defined(__CUDA_ARCH__)
+    int dbgMaxFace = 0;
+#endif
     int status;  // 0 valid, 1 touching, 2 degenerated, 3 non-convex, 4 invalid hull, 5 out of faces, 6 out of vertices, 7 accuracy reached, 8 fall-back, 9 failed
     V3 normal; float depth;
     Gjk2Simplex result;
@@ -359,16 +417,25 @@ RL_HDI void epa_list_remove(EpaFace* fc, EpaList& list, int face) {
     if (face == list.root) list.root = fc[face].l[1];
     --list.count;
 }
-RL_HD inline void epa_init(Epa& e, EpaWs* ws) {
+RL_HD inline void epa_init(Epa& e, const EpaWs& ws) {
     e.ws = ws;
     e.status = EPA_FAILED;
     e.normal = V3(0, 0, 0);
     e.depth = 0;
     e.nextsv = 0;
     e.hull.root = -1; e.hull.count = 0;
-    // the stock hands faces out in ascending index order (EPA::Initialize appends them from the back)
-    for (int i = 0; i < kEpaMaxFaces; i++) { ws->fc[i].l[0] = (int16_t)(i - 1); ws->fc[i].l[1] = (int16_t)(i + 1 < kEpaMaxFaces ? i + 1 : -1); }
-    e.stock.root = 0; e.stock.count = kEpaMaxFaces;
+    // EPA::Initialize appends the faces to the stock from the back, so it hands them out in ascending index order; faces that
+    // come back are pushed on top.  Kept as a LIFO of returned faces over a counter of never-used ones (no 256-entry set-up).
+    e.stock.root = -1; e.stock.count = 0;
+    e.fresh = 0;
+    e.overflow = false;
+}
+// take the face EPA::newface would take from m_stock.root; -1: none left
+RL_HDI int epa_stock_take(Epa& e) {
+    EpaFace* fc = e.ws.fc;
+    if (e.stock.root >= 0) { const int f = e.stock.root; epa_list_remove(fc, e.stock, f); return f; }
+    if (e.fresh < e.ws.maxFaces) return e.fresh++;
+    return -1;
 }
 // EPA::getedgedist: the origin projects outside edge a->b of the face -> distance to that edge or its end points
 RL_HD inline bool epa_edge_dist(V3 n, V3 a, V3 b, float& dist) {
@@ -390,11 +457,14 @@ RL_HD inline bool epa_edge_dist(V3 n, V3 a, V3 b, float& dist) {
     return false;
 }
 RL_HD inline int epa_newface(Epa& e, int a, int b, int c, bool forced) {
-    EpaFace* fc = e.ws->fc;
-    const EpaSV* sv = e.ws->sv;
-    if (e.stock.root >= 0) {
-        const int face = e.stock.root;
-        epa_list_remove(fc, e.stock, face);
+    EpaFace* fc = e.ws.fc;
+    const EpaSV* sv = e.ws.sv;
+    const int face = epa_stock_take(e);
+    if (face >= 0) {
+#if defined(RL_DEBUG_CONTACTS) && !defined(__CUDA_ARCH__)
+        if (face > g_dbg_epa_maxface) g_dbg_epa_maxface = face;
+        if (face > e.dbgMaxFace) e.dbgMaxFace = face;
+#endif
         epa_list_append(fc, e.hull, face);
         EpaFace& f = fc[face];
         f.pass = 0;
@@ -417,10 +487,11 @@ RL_HD inline int epa_newface(Epa& e, int a, int b, int c, bool forced) {
         return -1;
     }
     e.status = EPA_OUT_OF_FACES;
+    if (e.ws.maxFaces < kEpaMaxFaces) e.overflow = true;
     return -1;
 }
 RL_HD inline int epa_findbest(const Epa& e) {
-    const EpaFace* fc = e.ws->fc;
+    const EpaFace* fc = e.ws.fc;
     int minf = e.hull.root;
     float mind = fc[minf].d * fc[minf].d;
     for (int f = fc[minf].l[1]; f >= 0; f = fc[f].l[1]) {
@@ -433,9 +504,9 @@ struct EpaHorizon { int cf, ff, nf; };
 // EPA::expand: silhouette walk from (face f, edge e), depth first, edge e+1 before e+2, as an explicit stack.
 // A frame is (face, edge, stage): stage 0 = entered, 1 = first child returned, 2 = second child returned.
 RL_HD inline bool epa_expand(Epa& ep, unsigned pass, int w, int f0, int e0, EpaHorizon& hz) {
-    EpaFace* fc = ep.ws->fc;
-    const EpaSV* sv = ep.ws->sv;
-    uint16_t* st = ep.ws->stack;
+    EpaFace* fc = ep.ws.fc;
+    const EpaSV* sv = ep.ws.sv;
+    uint16_t* st = ep.ws.stack;
     int sp = 0;
     st[sp++] = (uint16_t)((f0 << 4) | (e0 << 2));
     bool ret = false;
@@ -484,9 +555,8 @@ RL_HD inline bool epa_expand(Epa& ep, unsigned pass, int w, int f0, int e0, EpaH
 // EPA::Evaluate (btGjkEpa2.cpp:653-778)
 template <class Sh>
 RL_HD inline int epa_evaluate(Epa& ep, Gjk2& g, const Sh& sh, V3 guess) {
-    EpaWs* ws = ep.ws;
-    EpaFace* fc = ws->fc;
-    EpaSV* sv = ws->sv;
+    EpaFace* fc = ep.ws.fc;
+    EpaSV* sv = ep.ws.sv;
     Gjk2Simplex& sx = g.sx[g.current];
     if (sx.rank > 1 && gjk2_enclose_origin(g, sv, sh)) {
         ep.status = EPA_VALID;
@@ -512,10 +582,14 @@ RL_HD inline int epa_evaluate(Epa& ep, Gjk2& g, const Sh& sh, V3 guess) {
             epa_bind(fc, tetra[2], 2, tetra[3], 1);
             ep.status = EPA_VALID;
             for (int iterations = 0; iterations < kEpaMaxIter; ++iterations) {
+                if (ep.nextsv >= ep.ws.maxVerts && ep.ws.maxVerts < kEpaMaxVerts) { ep.overflow = true; break; }
                 if (ep.nextsv < kEpaMaxVerts) {
                     EpaHorizon hz; hz.cf = -1; hz.ff = -1; hz.nf = 0;
                     const int w = 4 + ep.nextsv++;
                     bool valid = true;
+#if defined(RL_DEBUG_CONTACTS) && !defined(__CUDA_ARCH__)
+                    g_dbg_epa_iters++;
+#endif
                     fc[best].pass = (uint8_t)(++pass);
                     gjk2_support(sh, fc[best].n, sv[w]);
                     const float wdist = dot(fc[best].n, sv[w].w) - fc[best].d;
@@ -560,17 +634,22 @@ struct PenResult { V3 witnessA, witnessB, normal; };
 
 // btGjkEpaSolver2::Penetration (btGjkEpa2.cpp:980-1027), margins on
 template <class Sh>
-RL_HD inline bool epa_penetration(EpaWs* ws, Sh& sh, V3 guess, PenResult& r) {
+RL_HD inline bool epa_penetration(const EpaWs& ws, Sh& sh, V3 guess, PenResult& r, bool& overflow) {
     sh.margins = true;
     Gjk2 g;
-    const int gs = gjk2_evaluate(g, ws->sv, sh, -guess);
+    const int gs = gjk2_evaluate(g, ws.sv, sh, -guess);
     if (gs == 1) {
         Epa ep;
         epa_init(ep, ws);
         const int es = epa_evaluate(ep, g, sh, -guess);
+        if (ep.overflow) { overflow = true; return false; }
+#if defined(RL_DEBUG_CONTACTS) && !defined(__CUDA_ARCH__)
+        if (ep.nextsv > g_dbg_epa_maxsv) g_dbg_epa_maxsv = ep.nextsv;
+        { int b = ep.dbgMaxFace < 8 ? 0 : ep.dbgMaxFace < 12 ? 1 : ep.dbgMaxFace < 16 ? 2 : ep.dbgMaxFace < 24 ? 3 : ep.dbgMaxFace < 32 ? 4 : ep.dbgMaxFace < 48 ? 5 : ep.dbgMaxFace < 64 ? 6 : 7; g_dbg_epa_hist[b]++; }
+#endif
         if (es != EPA_FAILED) {
             V3 w0(0, 0, 0);
-            for (int i = 0; i < ep.result.rank; ++i) w0 += sh.support0(ws->sv[ep.result.c[i]].d) * ep.result.p[i];
+            for (int i = 0; i < ep.result.rank; ++i) w0 += sh.support0(ws.sv[ep.result.c[i]].d) * ep.result.p[i];
             r.witnessA = sh.to_world(w0);
             r.witnessB = sh.to_world(w0 - ep.normal * ep.depth);
             r.normal = -ep.normal;
@@ -581,17 +660,17 @@ RL_HD inline bool epa_penetration(EpaWs* ws, Sh& sh, V3 guess, PenResult& r) {
 }
 // btGjkEpaSolver2::Distance (btGjkEpa2.cpp:944-976), margins off
 template <class Sh>
-RL_HD inline bool epa_distance(EpaWs* ws, Sh& sh, V3 guess, PenResult& r) {
+RL_HD inline bool epa_distance(const EpaWs& ws, Sh& sh, V3 guess, PenResult& r) {
     sh.margins = false;
     Gjk2 g;
-    const int gs = gjk2_evaluate(g, ws->sv, sh, guess);
+    const int gs = gjk2_evaluate(g, ws.sv, sh, guess);
     if (gs == 0) {
         V3 w0(0, 0, 0), w1(0, 0, 0);
         const Gjk2Simplex& sx = g.sx[g.current];
         for (int i = 0; i < sx.rank; ++i) {
             const float p = sx.p[i];
-            w0 += sh.support0(ws->sv[sx.c[i]].d) * p;
-            w1 += sh.support1(-ws->sv[sx.c[i]].d) * p;
+            w0 += sh.support0(ws.sv[sx.c[i]].d) * p;
+            w1 += sh.support1(-ws.sv[sx.c[i]].d) * p;
         }
         r.witnessA = sh.to_world(w0);
         r.witnessB = sh.to_world(w1);
@@ -603,13 +682,19 @@ RL_HD inline bool epa_distance(EpaWs* ws, Sh& sh, V3 guess, PenResult& r) {
     return false;
 }
 
-// btGjkEpaPenetrationDepthSolver::calcPenDepth: -> 1 penetration found, 0 separated (witnesses valid, v set), -1 nothing (v = 0)
+// btGjkEpaPenetrationDepthSolver::calcPenDepth: -> 1 penetration found, 0 separated (witnesses valid, v set), -1 nothing (v = 0),
+// -2 the (small) workspace ran out of room: repeat in a larger one
 template <class Sh>
-RL_HD inline int calc_pen_depth(EpaWs* ws, Sh& sh, V3 originA, V3 originB, PenResult& r) {
+RL_HD inline int calc_pen_depth(const EpaWs& ws, Sh& sh, V3 originA, V3 originB, PenResult& r) {
+#if defined(RL_DEBUG_CONTACTS) && !defined(__CUDA_ARCH__)
+    g_dbg_epa_calls++;
+#endif
     const V3 guesses[9] = {safe_normalized(originB - originA), safe_normalized(originA - originB), V3(0, 0, 1), V3(0, 1, 0), V3(1, 0, 0),
                            V3(1, 1, 0), V3(1, 1, 1), V3(0, 1, 1), V3(1, 0, 1)};
     for (int i = 0; i < 9; i++) {
-        if (epa_penetration(ws, sh, guesses[i], r)) return 1;
+        bool overflow = false;
+        if (epa_penetration(ws, sh, guesses[i], r, overflow)) return 1;
+        if (overflow) return -2;
         if (epa_distance(ws, sh, guesses[i], r)) return 0;
     }
     r.witnessA = r.witnessB = r.normal = V3(0, 0, 0);

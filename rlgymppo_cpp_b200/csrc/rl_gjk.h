@@ -245,42 +245,83 @@ RL_HD inline void gjk_box_core(V3 cA, const M3& rot, V3 coreHalf, V3 offset, Sup
     }
 }
 
-// The back half (btGjkPairDetector.cpp:850-1000): the penetration-depth solver when the cores overlap or the distance is
-// degenerate-small, the "only replace when deeper / closer" rules, the contact-normal direction fix, the distance gate.
-// In: the GJK result as (valid, normal, pointOnB in the shifted frame, distance).  supBLocal(dir, withMargin) is B's support
-// mapping in B's own frame (identity basis, origin oB in the shifted frame); posB = centre of B's bounding box.
-template <class SupBLocal>
-RL_HD inline bool pair_finish(bool isValid, bool degenerate, V3 normalInB, V3 pointOnB, float distance, V3 cA, const M3& rot, V3 coreHalf, float marginA,
-                              float marginB, V3 oB, SupBLocal supBLocal, V3 posB, V3 offset, float maxDistSq, EpaWs* ws, V3& outNormal, V3& outPoint,
-                              float& outDist) {
-    const float margin = marginA + marginB;
-    const bool catchDegenerate = degenerate && (distance + margin) < 0.01f;
-    if (!isValid || catchDegenerate) {
-        with_epa_ws(ws, [&](EpaWs* w) {
-            Mink<SupBLocal> sh(rot, cA, oB, coreHalf, marginA, supBLocal);
-            PenResult r;
-            const int pr = calc_pen_depth(w, sh, cA, oB, r);
-            const V3 v = r.normal;  // m_cachedSeparatingAxis after calcPenDepth (A's local frame: reference quirk)
-            if (pr == 1) {
-                V3 tmpN = r.witnessB - r.witnessA;
-                float lenSqr = len2(tmpN);
-                if (lenSqr <= kEps * kEps) { tmpN = v; lenSqr = len2(v); }
-                if (lenSqr > kEps * kEps) {
-                    tmpN = tmpN / sqrtf(lenSqr);
-                    const float distance2 = -len(r.witnessA - r.witnessB);
-                    if (!isValid || distance2 < distance) { distance = distance2; pointOnB = r.witnessB; normalInB = tmpN; isValid = true; }
-                }
-            } else if (len2(v) > 0.f) {
-                const float distance2 = len(r.witnessA - r.witnessB) - margin;
-                if (!isValid || distance2 < distance) {
-                    distance = distance2;
-                    pointOnB = r.witnessB + v * marginB;
-                    normalInB = normalized(v);
-                    isValid = true;
-                }
-            }
-        });
+// Shape B of the penetration-depth search in its own frame (identity basis): a triangle (margin 0) or the ball (point core,
+// margin = radius) — btConvexShape::localGetSupportVertex[WithoutMargin]NonVirtual for the two.  One non-template description,
+// so the search below exists once in the kernel image.
+struct ConvexB {
+    V3 v0, v1, v2;
+    float radius;
+    int32_t sphere;
+    RL_HDI V3 operator()(V3 dir, bool withMargin) const {
+        V3 dn = dir;
+        if (withMargin) {
+            if (len2(dn) < kEps * kEps) dn = V3(-1, -1, -1);
+            dn = normalized(dn);
+        }
+        if (sphere) return withMargin ? dn * radius : V3(0, 0, 0);
+        float d0 = dot(dn, v0), d1 = dot(dn, v1), d2 = dot(dn, v2);
+        int mi = d0 < d1 ? (d1 < d2 ? 2 : 1) : (d0 < d2 ? 2 : 0);
+        return mi == 0 ? v0 : (mi == 1 ? v1 : v2);
     }
+};
+
+#if defined(RL_DEBUG_CONTACTS) && !defined(__CUDA_ARCH__)
+static long g_dbg_pen_kind[2] = {0, 0};  // host debugging: calls with overlapping cores / with a degenerate-small GJK distance
+#endif
+#if defined(RLG_EPA_TIMING) && defined(__CUDACC__)
+static __device__ unsigned long long g_epa_timing[2];  // diagnostic builds: cycles inside the search, calls
+#endif
+// btGjkPairDetector.cpp:860-940: the penetration-depth solver and the "only replace when deeper / closer" rules.  Rare and
+// long: out of line, one copy.  Updates (isValid, normalInB, pointOnB, distance) in place.
+RL_HD RL_NOINLINE inline void pair_penetration(const EpaCtx* ws, const M3& rot, V3 cA, V3 oB, V3 coreHalf, float marginA, float marginB, const ConvexB& shapeB,
+                                               bool& isValid, V3& normalInB, V3& pointOnB, float& distance) {
+    const float margin = marginA + marginB;
+#if defined(RLG_EPA_TIMING) && defined(__CUDA_ARCH__)
+    const long long epaT0 = clock64();
+#endif
+    with_epa_ws(ws, [&](const EpaWs& w) {
+        Mink<ConvexB> sh(rot, cA, oB, coreHalf, marginA, shapeB);
+        PenResult r;
+        const int pr = calc_pen_depth(w, sh, cA, oB, r);
+        if (pr == -2) return false;
+        const V3 v = r.normal;  // m_cachedSeparatingAxis after calcPenDepth (A's local frame: reference quirk)
+        if (pr == 1) {
+            V3 tmpN = r.witnessB - r.witnessA;
+            float lenSqr = len2(tmpN);
+            if (lenSqr <= kEps * kEps) { tmpN = v; lenSqr = len2(v); }
+            if (lenSqr > kEps * kEps) {
+                tmpN = tmpN / sqrtf(lenSqr);
+                const float distance2 = -len(r.witnessA - r.witnessB);
+                if (!isValid || distance2 < distance) { distance = distance2; pointOnB = r.witnessB; normalInB = tmpN; isValid = true; }
+            }
+        } else if (len2(v) > 0.f) {
+            const float distance2 = len(r.witnessA - r.witnessB) - margin;
+            if (!isValid || distance2 < distance) {
+                distance = distance2;
+                pointOnB = r.witnessB + v * marginB;
+                normalInB = normalized(v);
+                isValid = true;
+            }
+        }
+        return true;
+    });
+#if defined(RLG_EPA_TIMING) && defined(__CUDA_ARCH__)
+    atomicAdd(&g_epa_timing[0], (unsigned long long)(clock64() - epaT0));
+    atomicAdd(&g_epa_timing[1], 1ULL);
+#endif
+}
+
+// The back half (btGjkPairDetector.cpp:850-1000): penetration-depth solver when the cores overlap or the distance is
+// degenerate-small, the contact-normal direction fix, the distance gate.  In: the GJK result as (valid, normal, pointOnB in
+// the shifted frame, distance); oB = B's origin in the shifted frame, posB = centre of B's bounding box.
+RL_HDI bool pair_finish(bool isValid, bool degenerate, V3 normalInB, V3 pointOnB, float distance, V3 cA, const M3& rot, V3 coreHalf, float marginA,
+                        float marginB, V3 oB, const ConvexB& shapeB, V3 posB, V3 offset, float maxDistSq, const EpaCtx* ws, V3& outNormal, V3& outPoint,
+                        float& outDist) {
+    const bool catchDegenerate = degenerate && (distance + (marginA + marginB)) < 0.01f;
+#if defined(RL_DEBUG_CONTACTS) && !defined(__CUDA_ARCH__)
+    if (!isValid) g_dbg_epa_hist[0 + 0] += 0, g_dbg_pen_kind[0]++; else if (catchDegenerate) g_dbg_pen_kind[1]++;
+#endif
+    if (!isValid || catchDegenerate) pair_penetration(ws, rot, cA, oB, coreHalf, marginA, marginB, shapeB, isValid, normalInB, pointOnB, distance);
     if (isValid && (distance < 0 || distance * distance < maxDistSq)) {
         // m_fixContactNormalDirection: the normal must point from B's bounding-box centre towards A's
         if (dot(cA - posB, normalInB) < 0.f) normalInB = normalInB * -1.f;
@@ -294,7 +335,7 @@ RL_HD inline bool pair_finish(bool isValid, bool degenerate, V3 normalInB, V3 po
 // A = box (margin 0.04), B = sphere (point core, margin = radius).  GJK between a box core and a point converges to the
 // closest point on the core; written in closed form.  Centre within 0.01 of the core (or inside it): penetration solver.
 RL_HD RL_NOINLINE inline bool box_sphere_contact(V3 boxCenter, const M3& rot, V3 core, float marginA, V3 sphereCenter, float radius, float breaking,
-                                                 EpaWs* ws, V3& normalOnB, V3& pointOnB, float& dist) {
+                                                 const EpaCtx* ws, V3& normalOnB, V3& pointOnB, float& dist) {
     V3 l = tmul(sphereCenter - boxCenter, rot);
     V3 q(clampf(l.x, -core.x, core.x), clampf(l.y, -core.y, core.y), clampf(l.z, -core.z, core.z));
     V3 d = q - l;  // from sphere centre (B) to box core (A)
@@ -313,18 +354,13 @@ RL_HD RL_NOINLINE inline bool box_sphere_contact(V3 boxCenter, const M3& rot, V3
     const V3 offset = (boxCenter + sphereCenter) * 0.5f;
     const bool valid = d2 > kEps * kEps;
     V3 n0 = valid ? rot * (d * (1.f / dl)) : V3();
-    auto supLocal = [radius](V3 dir, bool withMargin) {
-        if (!withMargin) return V3(0, 0, 0);
-        V3 dn = dir;
-        if (len2(dn) < kEps * kEps) dn = V3(-1, -1, -1);
-        return normalized(dn) * radius;
-    };
+    ConvexB sb; sb.sphere = 1; sb.radius = radius;
     return pair_finish(valid, true, n0, (sphereCenter - offset) + n0 * radius, dl - margin, boxCenter - offset, rot, core, marginA, radius, sphereCenter - offset,
-                       supLocal, sphereCenter - offset, offset, maxDist * maxDist, ws, normalOnB, pointOnB, dist);
+                       sb, sphereCenter - offset, offset, maxDist * maxDist, ws, normalOnB, pointOnB, dist);
 }
 
 // ---- box vs triangle -------------------------------------------------------------------------------
-RL_HD RL_NOINLINE inline bool box_triangle_contact(V3 boxCenter, const M3& rot, V3 core, float marginA, const Tri& t, float breaking, EpaWs* ws,
+RL_HD RL_NOINLINE inline bool box_triangle_contact(V3 boxCenter, const M3& rot, V3 core, float marginA, const Tri& t, float breaking, const EpaCtx* ws,
                                                    V3& normalOnB, V3& pointOnB, float& dist) {
     const float maxDist = marginA + 0.f + breaking;
     const V3 v0 = t.v0, v1 = t.v1, v2 = t.v2;
@@ -348,20 +384,11 @@ RL_HD RL_NOINLINE inline bool box_triangle_contact(V3 boxCenter, const M3& rot, 
         distance = (1.f / rlen) - marginA;
         isValid = true;
     }
-    auto supLocal = [v0, v1, v2](V3 dir, bool withMargin) {  // btConvexShape::localGetSupportVertex[WithoutMargin]NonVirtual, triangle, margin 0
-        V3 dn = dir;
-        if (withMargin) {
-            if (len2(dn) < kEps * kEps) dn = V3(-1, -1, -1);
-            dn = normalized(dn);
-        }
-        float d0 = dot(dn, v0), d1 = dot(dn, v1), d2 = dot(dn, v2);
-        int mi = d0 < d1 ? (d1 < d2 ? 2 : 1) : (d0 < d2 ? 2 : 0);
-        return mi == 0 ? v0 : (mi == 1 ? v1 : v2);
-    };
     // centre of the triangle's bounding box in the shifted frame (btPolyhedralConvexShape::getAabb via the support mapping, margin 0)
     const V3 oB = V3() - offset;
     const V3 posB = ((vmin(vmin(v0, v1), v2) + oB) + (vmax(vmax(v0, v1), v2) + oB)) * 0.5f;
-    return pair_finish(isValid, g.degenerate != 0, normalInB, pB, distance, cA, rot, core, marginA, 0.f, oB, supLocal, posB, offset, maxDist * maxDist, ws, normalOnB,
+    ConvexB sb; sb.sphere = 0; sb.radius = 0.f; sb.v0 = v0; sb.v1 = v1; sb.v2 = v2;
+    return pair_finish(isValid, g.degenerate != 0, normalInB, pB, distance, cA, rot, core, marginA, 0.f, oB, sb, posB, offset, maxDist * maxDist, ws, normalOnB,
                        pointOnB, dist);
 }
 

@@ -193,10 +193,6 @@ struct ArenaS {
     int32_t stepsSinceTouch;
     // RNG (pcg32 state), keyed by global arena id
     uint32_t rngLo, rngHi;
-    // 0 until this arena's world has stepped once: btContactSolverInfo::m_timeStep still holds its constructor default (1/60)
-    // during the very first Car::_PreTickUpdate of an arena's life (it is set inside stepSimulation, after the vehicle update),
-    // and the wheels' extra push-back reads it (btVehicleRL.cpp:183-199 -> resolveSingleCollision)
-    int32_t worldStepped;
     CarS cars[kMaxCars];
 };
 

@@ -135,7 +135,6 @@ RL_HDI void tick_s0_ball(const ArenaS& a, TickX x) {
     x.h->ballPos = a.ball.pos; x.h->ballVel = a.ball.vel; x.h->ballAngvel = a.ball.angvel;
     // ball zero-velocity sleeping (Arena.cpp:721-727)
     x.h->ballActive = !(len2(a.ball.vel) == 0.f && len2(a.ball.angvel) == 0.f);
-    x.h->solverDt = a.worldStepped ? kTickTime : (1.f / 60.f);
 }
 
 // tick_p1_car = pose (respawn, mesh candidates) + mesh part of the wheel rays + begin (vehicle update, control model,
@@ -149,12 +148,13 @@ RL_HD inline void tick_p1_car_pose(ArenaS& a, TickX x, const SimCfg& cfg, const 
     // and a car demolished DURING this tick still responds and integrates until the next tick (Car.cpp:38-41,69-87)
     o.noResponse = car.isDemoed;
     o.ballVelCache = V3(); o.velCache = V3();
+    w.solverDt = (a.tickLo | a.tickHi) ? kTickTime : (1.f / 60.f);
     RL_PT(-1);
     car_pre_tick_a(car, cfg, ms, k, c, w, respawn_rnd(a, c), collect);
 }
 // between the two: w.meshHit (+ the hitbox pre-filter) from wheel_mesh_rays or the role kernel's cooperative pass
 RL_HD inline void tick_p1_car_begin(ArenaS& a, TickX x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, const Thresholds& thr, int c, CarW& w,
-                                    Contact* scratch, int firstTickOfStep, CollideCtx& cx, ContactSink& cw, EpaWs* epa = nullptr) {
+                                    Contact* scratch, int firstTickOfStep, CollideCtx& cx, ContactSink& cw, const EpaCtx* epa = nullptr) {
     CarS& car = a.cars[c];
     CarX& o = x.car[c];
     car_pre_tick_b(car, x, cfg, ms, k, c, w);
@@ -395,7 +395,6 @@ RL_HD inline void tick_p2_solve(ArenaS& a, TickX x, const SimCfg& cfg, const Car
         if (len2(a.ball.angvel) > C::BALL_MAX_ANG_SPEED * C::BALL_MAX_ANG_SPEED) a.ball.angvel = normalized(a.ball.angvel) * C::BALL_MAX_ANG_SPEED;
     }
     a.ball.updateCounterLo++;
-    a.worldStepped = 1;
     set_i64(a.tickLo, a.tickHi, tick + 1);
     RL_PT(12);
 }

@@ -35,9 +35,9 @@ def record(arena, cars, ball, pads, controls_fn, nticks):
     answer to precisely the recorded before-state — without it the body keeps sub-ulp information the uu round trip drops and
     even the reference cannot reproduce its own recording from the recorded states on sensitive contact ticks.  The arena is
     stepped once before the recording starts: a world that has never stepped still carries btContactSolverInfo's default
-    time step (1/60) into its first vehicle update (cold-start quirk, covered by its own live test)."""
+    time step (1/60) into its first vehicle update (cold-start quirk of tick count 0, covered by its own live test)."""
     arena.step(None, 1)
-    arena.set_state(cars, ball, pads, 0)
+    arena.set_state(cars, ball, pads, -1)  # keep the tick count (>= 1: "has stepped" is tick count != 0 on both sides)
     P = arena.num_cars
     C = np.zeros((nticks + 1, P), dtype=abi.CAR_DTYPE)
     B = np.zeros(nticks + 1, dtype=abi.BALL_DTYPE)

@@ -5,6 +5,7 @@
 // kernel logic against the reference oracle / golden vectors before the code ever reaches a B200.
 // The product path is rlgymppo_cpp_b200/csrc/engine.cu; it fails loudly without a CUDA device.
 #define RL_DEBUG_CONTACTS 1
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -205,6 +206,20 @@ int hs_probe_box_box(const float* halfA, const float* tA, const float* halfB, co
     for (int i = 0; i < r.n && i < cap; i++) { float* o = out + 7 * i; for (int k = 0; k < 3; k++) { o[k] = r.normal[k]; o[3 + k] = r.point[i][k]; } o[6] = r.depth[i]; }
     return r.n;
 }
+// ns per box_triangle_contact call on one pose (host timing of the penetration path)
+double hs_bench_box_triangle(const float* halfExt, const float* boxT, const float* tri, float breaking, int n) {
+    V3 c, core; M3 r; float margin;
+    probe_box(halfExt, boxT, c, r, core, margin);
+    Tri t; t.v0 = V3(tri[0], tri[1], tri[2]); t.v1 = V3(tri[3], tri[4], tri[5]); t.v2 = V3(tri[6], tri[7], tri[8]);
+    V3 nn, p; float d; volatile float sink = 0;
+    auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < n; i++) { V3 cc = c + V3(0, 0, 1e-6f * (i & 7)); if (box_triangle_contact(cc, r, core, margin, t, breaking, nullptr, nn, p, d)) sink += d; }
+    return std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t0).count() / n;
+}
+void hs_epa_small_capacity(int verts, int faces) { g_epa_host_small_verts = verts; g_epa_host_small_faces = faces; }
+long hs_epa_overflows() { return g_dbg_epa_overflows; }
+void hs_pen_kinds(long* out) { out[0] = g_dbg_pen_kind[0]; out[1] = g_dbg_pen_kind[1]; }
+void hs_epa_stats(long* out) { out[0] = g_dbg_epa_calls; out[1] = g_dbg_epa_iters; out[2] = g_dbg_epa_maxface; out[3] = g_dbg_epa_maxsv; for (int i = 0; i < 8; i++) out[4 + i] = g_dbg_epa_hist[i]; }
 size_t hs_sizeof_arena() { return sizeof(ArenaS); }
 
 // leaf grid vs stackless BVH walk on random query boxes (centres over the whole arena incl. the goal boxes, half extents

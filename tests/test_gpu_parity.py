@@ -63,7 +63,6 @@ def _batch_runner(team, torch, **kw):
         e = _engine(team, n=n, **kw)
         ids = np.arange(n, dtype=np.int32)
         buf = torch.from_numpy(np.frombuffer(np.ascontiguousarray(ctl).tobytes(), dtype=np.uint8).copy()).cuda()
-        e.tick_device(buf.data_ptr(), 1)  # the fixtures come from worlds that have stepped before (common.check_single_tick_run)
         e.set_state(ids, np.ascontiguousarray(cars), np.ascontiguousarray(balls), np.ascontiguousarray(pads), ticks)
         e.tick_device(buf.data_ptr(), 1)
         e.sync()
@@ -82,6 +81,7 @@ def test_single_tick_scenarios_1v1(torch_cuda):
     # ... and the one-arena-at-a-time protocol on a slice of it (a single live lane per warp)
     r = _TickRunner(1, torch_cuda)
     g = common.load_tick_file("tick_scenarios_1v1")
+    common._current_fixture[0] = "tick_scenarios_1v1 (two scenarios, one arena at a time)"
     common.check_single_tick_run({k: g[k] for k in ("car_hits_ball", "car_into_goal")}, r.set_state, r.tick, r.get_state)
 
 

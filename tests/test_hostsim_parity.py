@@ -1,5 +1,7 @@
 """CPU suite: the device headers (compiled for the host by tests/hostsim — a TEST TOOL, not a product path) against
 the golden fixtures of the reference.  Same checks the -m gpu suite runs through the C ABI on the B200."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -21,6 +23,52 @@ def test_action_table(golden_dir):
     import os
 
     assert np.array_equal(hostsim.action_table(), np.load(os.path.join(golden_dir, "action_table.npy")))
+
+
+def test_batched_tick_protocol_equals_the_serial_one():
+    """common.check_single_tick_batch (what the -m gpu suite uses: every recorded tick in its own arena, one launch) on the host
+    build, arena by arena: same tallies as the one-arena protocol."""
+    cfg = abi.default_cfg(num_arenas=1, team_size=2)
+    hs = hostsim.HostSim(cfg)
+
+    def run(cars, balls, pads, ticks, ctl):
+        out = []
+        for i in range(len(ticks)):
+            hs.set_state(0, cars[i], balls[i:i + 1], pads[i], int(ticks[i]))
+            hs.tick(0, ctl[i], 1)
+            out.append(hs.get_state(0))
+        c = np.zeros((len(out), hs.P), dtype=abi.CAR_DTYPE)
+        b = np.zeros(len(out), dtype=abi.BALL_DTYPE)
+        p = np.zeros((len(out), abi.RLG_NUM_PADS), dtype=abi.PAD_DTYPE)
+        for i, o in enumerate(out):
+            c[i], b[i], p[i] = o[0], o[1][0], o[2]
+        return c, b, p, np.array([o[3] for o in out], dtype=np.int64)
+
+    g = common.load_tick_file("tick_random_2v2")
+    a = common.check_single_tick_batch(g, run)
+    s, t, gs = _runner(2)
+    b = common.check_single_tick_run(g, s, t, gs)
+    assert a["total"] == b["total"] == 384 and a["loose"] == b["loose"] and a["worst_tight"] == b["worst_tight"]
+
+
+def test_epa_small_workspace_fallback():
+    """The penetration-depth search first runs in a small workspace and is repeated in the reference-size one when that runs
+    out (rl_epa.h with_epa_ws): with the small one shrunk until most evaluations overflow, the results are unchanged."""
+    g = {k: v for k, v in common.load_tick_file("tick_scenarios_1v1").items() if k in ("car_into_goal", "car_up_side_ramp")}
+    L = hostsim.lib()
+    L.hs_epa_overflows.restype = C.c_long
+    s, t, gs = _runner(1)
+    before = L.hs_epa_overflows()
+    a = common.check_single_tick_run(g, s, t, gs)
+    assert L.hs_epa_overflows() == before  # the production capacity fits all of them
+    try:
+        L.hs_epa_small_capacity(2, 6)
+        s, t, gs = _runner(1)
+        b = common.check_single_tick_run(g, s, t, gs)
+        assert L.hs_epa_overflows() >= before + 3
+    finally:
+        L.hs_epa_small_capacity(10, 24)
+    assert a["worst_tight"] == b["worst_tight"] and a["loose"] == b["loose"]
 
 
 def test_single_tick_scenarios_1v1():

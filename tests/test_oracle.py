@@ -39,16 +39,19 @@ def test_numpy_gym_oracle_bit_exact_vs_reference_golden(name, cfg, golden_dir):
 
 @pytest.mark.skipif(not refsim.available(), reason="oracle/_ref not built")
 def test_compiled_reference_reproduces_tick_fixtures(golden_dir):
+    """The recording protocol of make_golden.record (state re-injected before every tick) replayed on a fresh compiled reference:
+    bit-identical trajectories, i.e. the fixtures ARE what the reference answers to the recorded states."""
     groups = common.load_tick_file("tick_scenarios_1v1")
     arena = refsim.RefArena(1, True)
-    for name in ("free_flight", "jump_flip", "car_hits_ball", "ball_corner_mesh"):
+    arena.step(None, 1)
+    for name in ("free_flight", "jump_flip", "car_hits_ball", "ball_corner_mesh", "car_into_goal"):
         g = groups[name]
-        arena.set_state(g["cars"][0], g["ball"][0:1], g["pads"][0], int(g["tick"][0]))
         for t in range(len(g["controls"])):
-            arena.step(g["controls"][t], 1)
-        cars, ball, pads, tick = arena.get_state()
-        assert np.array_equal(cars["pos"], g["cars"][-1]["pos"]), name
-        assert np.array_equal(ball["vel"][0], g["ball"][-1]["vel"]), name
+            arena.set_state(g["cars"][t].copy(), g["ball"][t:t + 1].copy(), g["pads"][t].copy(), int(g["tick"][t]))
+            arena.step(g["controls"][t].copy(), 1)
+            cars, ball, pads, tick = arena.get_state()
+            assert np.array_equal(cars["pos"], g["cars"][t + 1]["pos"]) and np.array_equal(cars["vel"], g["cars"][t + 1]["vel"]), (name, t)
+            assert np.array_equal(ball["vel"][0], g["ball"][t + 1]["vel"]) and tick == int(g["tick"][t + 1]), (name, t)
 
 
 @pytest.mark.skipif(not refsim.available(), reason="oracle/_ref not built")
