@@ -233,3 +233,54 @@ def obs_equal(cfg, ref, got):
             if a != b:
                 return False
     return True
+
+
+# ---- state setters: distributions against the live reference --------------------------------------------------------------
+def setter_features(cars, ball):
+    """Scalar features of one reset state (cars [P] CAR_DTYPE, ball [1] BALL_DTYPE) whose distributions RandomState / KickoffState
+    define (RandomState.cpp:8-62, Arena.cpp:112-216)."""
+    f = {}
+    b = ball[0] if ball.shape else ball
+    for i, ax in enumerate("xyz"):
+        f["ball_pos_" + ax] = [float(b["pos"][i])]
+        f["ball_angvel_" + ax] = [float(b["ang_vel"][i])]
+    v = np.asarray(b["vel"], np.float64)
+    sp = float(np.linalg.norm(v))
+    f["ball_speed"] = [sp]
+    f["ball_vel_dir_z"] = [float(v[2] / sp)] if sp > 1e-6 else []
+    f["car_pos_x"] = [float(c["pos"][0]) for c in cars]
+    f["car_pos_y"] = [float(c["pos"][1]) for c in cars]
+    f["car_yaw"] = [float(np.arctan2(c["rot_forward"][1], c["rot_forward"][0])) for c in cars]
+    f["car_speed"] = [float(np.linalg.norm(np.asarray(c["vel"], np.float64))) for c in cars]
+    f["car_vel_heading"] = [float(np.arctan2(c["vel"][1], c["vel"][0])) for c in cars if np.linalg.norm(c["vel"]) > 1e-6]
+    f["car_boost"] = [float(c["boost"]) for c in cars]
+    return f
+
+
+def ks_two_sample(a, b):
+    """Two-sample Kolmogorov-Smirnov statistic D and its asymptotic critical value at alpha = 1e-4."""
+    a, b = np.sort(np.asarray(a, np.float64)), np.sort(np.asarray(b, np.float64))
+    allv = np.concatenate([a, b])
+    d = float(np.max(np.abs(np.searchsorted(a, allv, side="right") / len(a) - np.searchsorted(b, allv, side="right") / len(b))))
+    crit = float(np.sqrt(-0.5 * np.log(1e-4 / 2)) * np.sqrt((len(a) + len(b)) / (len(a) * len(b))))
+    return d, crit
+
+
+def compare_setter_samples(ours, ref):
+    """ours / ref: lists of (cars, ball, pads) reset states.  Every feature's distribution must pass a KS test against the
+    reference's at alpha = 1e-4 per feature (14 features: family-wise < 0.2 %), the deterministic parts must be equal."""
+    fo, fr = {}, {}
+    for acc, samples in ((fo, ours), (fr, ref)):
+        for cars, ball, pads in samples:
+            for k, v in setter_features(cars, ball).items():
+                acc.setdefault(k, []).extend(v)
+            assert np.all(pads["is_active"] != 0)
+            assert np.allclose(cars["pos"][:, 2], 17.0) and np.all(cars["is_on_ground"] != 0)  # carsOnGround = true (examplemain.cpp:85)
+            assert np.all(cars["vel"][:, 2] == 0) and np.all(cars["ang_vel"] == 0)
+            assert np.allclose(cars["rot_up"], [0, 0, 1], atol=1e-6)
+    report = {}
+    for k in fr:
+        d, crit = ks_two_sample(fo[k], fr[k])
+        report[k] = (round(d, 4), round(crit, 4), len(fo[k]), len(fr[k]))
+        assert d < crit, (k, report[k])
+    return report

@@ -358,65 +358,143 @@ def test_against_compiled_reference_if_present(torch_cuda):
 
 def test_rollout_statistics_match_the_reference(torch_cuda):
     """Free-running collection (RandomState resets, uniform random actions, auto-reset) on both sides: the per-step statistics a
-    learner sees — mean reward, episode-end rate, ball height / speed, cars on the ground, boost, demolitions — agree within
-    the reference sample's own standard error (4 sigma + a small absolute slack).  The two runs share no random numbers, so
-    this is the distribution-level check behind "learning curves statistically indistinguishable"."""
+    learner sees — mean reward, episode-end rate, ball height / speed, car height / speed, cars on the ground, boost, flips,
+    demolitions — agree within 3 standard errors of the difference (no absolute slack).  1 024 reference gyms against 4 096
+    engine arenas, 160 env-steps each after a 60-step warm-up; the standard errors come from the per-gym / per-arena means.
+    The two runs share no random numbers, so this is the distribution-level check behind "learning curves statistically
+    indistinguishable".  Both sides take the observation statistics over the steps that did NOT end an episode (GameInst::Step
+    hands back the reset observation for a finished arena, the reference loop sees the terminal one); reward and the episode-end
+    rate are taken over all steps."""
+    from oracle import refsim
+
+    if not refsim.available():
+        pytest.skip("oracle/_ref/librlref.so not present")
+    steps, warm = 220, 60  # warm-up: both sides forget the all-fresh start
+    names = ("ball_z", "ball_speed", "car_z", "car_speed", "boost", "on_ground", "has_flip", "demoed")
+
+    def obs_stats(o):
+        """o [..., P, 89] -> [..., 8]: ball pos/vel at 0:6, self block at 51 (pos 51:54, vel 60:63, boost 66, onGround 67, hasFlip 68, demoed 69)."""
+        return np.stack([o[..., 0, 2], np.linalg.norm(o[..., 0, 3:6], axis=-1), o[..., 53].mean(-1), np.linalg.norm(o[..., 60:63], axis=-1).mean(-1),
+                         o[..., 66].mean(-1), o[..., 67].mean(-1), o[..., 68].mean(-1), o[..., 69].mean(-1)], axis=-1)
+
+    def summarise(per_unit):
+        """per_unit [units, k] means -> (mean, standard error) over the units (gyms / arenas are independent)."""
+        return per_unit.mean(0), per_unit.std(0, ddof=1) / np.sqrt(per_unit.shape[0])
+
+    # reference
+    G = 1024
+    refsim.seed(4242)
+    rng = np.random.default_rng(77)
+    g = refsim.RefGym(abi.default_cfg(num_arenas=1, team_size=1))
+    ref_units = np.zeros((G, 2 + len(names)))
+    for i in range(G):
+        g.reset()
+        rew, done, ob = [], [], []
+        for s in range(steps):
+            o, r, d = g.step(rng.integers(0, 90, size=2))
+            if s >= warm:
+                rew.append(float(np.mean(r))); done.append(float(d))
+                if not d:
+                    ob.append(obs_stats(o))
+            if d:
+                g.reset()
+        ref_units[i] = np.concatenate([[np.mean(rew), np.mean(done)], np.mean(ob, axis=0)])
+    ref_mean, ref_se = summarise(ref_units)
+
+    e = engine.Engine(abi.default_cfg(num_arenas=4096, team_size=1))
+    e.reset()
+    rng = np.random.default_rng(78)
+    A, P = e.A, e.P
+    rew_sum, done_sum, ob_sum, ob_cnt = np.zeros(A), np.zeros(A), np.zeros((A, len(names))), np.zeros(A)
+    for s in range(steps):
+        o, r, d = e.step_host(rng.integers(0, 90, size=A * P).astype(np.int32))
+        if s >= warm:
+            rew_sum += r.reshape(A, P).mean(1); done_sum += d
+            live = d == 0
+            ob_sum[live] += obs_stats(o.reshape(A, P, -1)[live]); ob_cnt += live
+    n = steps - warm
+    eng_units = np.concatenate([(rew_sum / n)[:, None], (done_sum / n)[:, None], ob_sum / np.maximum(ob_cnt, 1)[:, None]], axis=1)
+    eng_mean, eng_se = summarise(eng_units)
+    keys = ("reward", "done") + names
+    report = {k: dict(engine=float(eng_mean[i]), reference=float(ref_mean[i]), se_diff=float(np.hypot(ref_se[i], eng_se[i])),
+                      sigmas=float((eng_mean[i] - ref_mean[i]) / np.hypot(ref_se[i], eng_se[i]))) for i, k in enumerate(keys)}
+    print(report)
+    import json
+
+    for d_ in (os.environ.get("RLG_STATS_DIR"), os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")):
+        if d_ and os.path.isdir(d_):
+            with open(os.path.join(d_, "rollout_stats_r02.json"), "w") as f:
+                json.dump(dict(reference_gyms=G, engine_arenas=A, steps=n, stats=report), f, indent=1)
+    bad = {k: v for k, v in report.items() if abs(v["sigmas"]) > 3.0}
+    assert not bad, bad
+
+
+def test_state_setters_match_the_reference_distribution(torch_cuda):
+    """The device state setters (rl_gym.h gym_reset, run by k_reset and by the auto-reset of k_roles) against the live reference:
+    RandomState marginals by two-sample KS tests (common.compare_setter_samples), KickoffState's spawn-slot assignment by a
+    chi-square test on the 20 ordered (blue slot, orange slot) pairs + the exact kickoff poses."""
     from oracle import refsim
 
     if not refsim.available():
         pytest.skip("oracle/_ref/librlref.so not present")
     cfg = abi.default_cfg(num_arenas=4096, team_size=1)
-    steps, warm = 220, 60  # warm-up: both sides forget the all-fresh start
-
-    def stats(obs, rew, done):
-        """obs [n, P, 89]: ball pos/vel at 0:6 (scaled by 1/2300, 1/2300), self block at 51 (boost 66, onGround 67, demoed 69)."""
-        o = obs.reshape(-1, obs.shape[-1])
-        return dict(reward=rew.reshape(-1), done=done.reshape(-1).astype(np.float64), ball_z=o[:, 2], ball_speed=np.linalg.norm(o[:, 3:6], axis=1),
-                    car_z=o[:, 53], car_speed=np.linalg.norm(o[:, 60:63], axis=1), boost=o[:, 66], on_ground=o[:, 67], has_flip=o[:, 68],
-                    demoed=o[:, 69])
-
-    # reference: G gyms, one (correlated) sample per gym-step; the standard error is taken over per-gym means
-    G = 96
-    refsim.seed(4242)
-    gyms = [refsim.RefGym(abi.default_cfg(num_arenas=1, team_size=1)) for _ in range(G)]
-    rng = np.random.default_rng(77)
-    per_gym = []
-    for g in gyms:
+    refsim.seed(5)
+    g = refsim.RefGym(cfg)
+    ref = []
+    for _ in range(4096):
         g.reset()
-        acc = {}
-        for s in range(steps):
-            o, r, d = g.step(rng.integers(0, 90, size=2))
-            if s >= warm:
-                for k, v in stats(o[None], r[None], np.array([d])).items():
-                    acc.setdefault(k, []).append(np.mean(v))
-            if d:
-                g.reset()
-        per_gym.append({k: float(np.mean(v)) for k, v in acc.items()})
-    ref_mean = {k: float(np.mean([p[k] for p in per_gym])) for k in per_gym[0]}
-    ref_se = {k: float(np.std([p[k] for p in per_gym], ddof=1) / np.sqrt(G)) for k in per_gym[0]}
-
+        c, b, p, _t = g.arena.get_state()
+        ref.append((c, b, p))
     e = engine.Engine(cfg)
     e.reset()
-    rng = np.random.default_rng(78)
-    acc = {}
-    for s in range(steps):
-        o, r, d = e.step_host(rng.integers(0, 90, size=e.A * e.P).astype(np.int32))
-        if s >= warm:
-            # GameInst::Step hands back the RESET observation for a finished arena; the reference loop above looks at the
-            # terminal one and discards the reset's, so finished arenas are left out of the observation statistics here
-            live = d == 0
-            st = stats(o.reshape(e.A, e.P, -1)[live], r.reshape(e.A, e.P)[live], d[live])
-            st["done"], st["reward"] = d.astype(np.float64), r
-            for k, v in st.items():
-                acc.setdefault(k, []).append(np.mean(v))
-    got = {k: float(np.mean(v)) for k, v in acc.items()}
-    slack = dict(reward=0.01, done=0.001, ball_z=0.01, ball_speed=0.01, car_z=0.003, car_speed=0.01, boost=0.01, on_ground=0.008, has_flip=0.01,
-                 demoed=0.001)
-    out = os.environ.get("RLG_STATS_OUT")
-    if out:  # evidence file for profiles/: engine mean, reference mean, reference standard error per statistic
-        import json
+    ids = np.arange(e.A, dtype=np.int32)
+    cars, balls, pads, _t = e.get_state(ids)
+    ours = [(cars[i], balls[i:i + 1], pads[i]) for i in range(e.A)]
+    print(common.compare_setter_samples(ours, ref))
+    # ... and again after a round of auto-resets inside the fused step (every arena finishes: NoTouch horizon 1 step)
+    cfg2 = abi.default_cfg(num_arenas=2048, team_size=1)
+    cfg2.no_touch_max_steps = 1
+    e2 = engine.Engine(cfg2)
+    e2.reset()
+    rng = np.random.default_rng(1)
+    for _ in range(3):
+        _o, _r, d = e2.step_host(rng.integers(0, 90, size=e2.A * e2.P).astype(np.int32))
+    assert d.all()
+    cars, balls, pads, _t = e2.get_state(np.arange(e2.A, dtype=np.int32))
+    print(common.compare_setter_samples([(cars[i], balls[i:i + 1], pads[i]) for i in range(e2.A)], ref))
 
-        with open(out, "w") as f:
-            json.dump({k: dict(engine=got[k], reference=ref_mean[k], reference_se=ref_se[k]) for k in got}, f, indent=1)
-    bad = {k: (got[k], ref_mean[k], ref_se[k]) for k in got if abs(got[k] - ref_mean[k]) > 4 * ref_se[k] + slack[k]}
-    assert not bad, bad
+    # KickoffState (Arena::ResetToRandomKickoff, Arena.cpp:112-216): 5 spawn slots, shuffled, blue takes slot k, orange mirrors
+    cfgk = abi.default_cfg(num_arenas=4000, team_size=1)
+    cfgk.state_setter = abi.RLG_SETTER_KICKOFF
+    ek = engine.Engine(cfgk)
+    ek.reset()
+    cars, balls, pads, _t = ek.get_state(np.arange(ek.A, dtype=np.int32))
+    spots = [(-2048, -2560), (2048, -2560), (-256, -3840), (256, -3840), (0, -4608)]
+    yaws = [np.pi / 4, 3 * np.pi / 4, np.pi / 2, np.pi / 2, np.pi / 2]
+    gk = refsim.RefGym(cfgk)
+    counts = {"ours": np.zeros(5), "ref": np.zeros(5)}
+
+    def slot_of(c):
+        x, y = float(c["pos"][0]), float(c["pos"][1])
+        yaw = float(np.arctan2(c["rot_forward"][1], c["rot_forward"][0]))
+        if c["team"] == 1:
+            x, y, yaw = -x, -y, float(np.arctan2(-c["rot_forward"][1], -c["rot_forward"][0]))
+        k = spots.index((round(x), round(y)))
+        assert abs(yaw - yaws[k]) < 1e-5 and abs(float(c["pos"][2]) - 17.0) < 1e-4 and abs(float(c["boost"]) - 100 / 3) < 1e-4
+        return k
+
+    for i in range(ek.A):
+        assert np.allclose(balls[i]["pos"], [0, 0, 93.15], atol=1e-4) and np.all(balls[i]["vel"] == 0)
+        kb, ko = slot_of(cars[i][0]), slot_of(cars[i][1])
+        assert kb == ko  # 1v1: the orange car mirrors the blue car's slot (same index of the shuffled list)
+        counts["ours"][kb] += 1
+    for _ in range(2000):
+        gk.reset()
+        c, b, p, _t = gk.arena.get_state()
+        kb, ko = slot_of(c[0]), slot_of(c[1])
+        assert kb == ko
+        counts["ref"][kb] += 1
+    for k, n in counts.items():
+        chi2 = float((((n - n.sum() / 5) ** 2) / (n.sum() / 5)).sum())
+        print(k, n, chi2)
+        assert chi2 < 23.5, (k, n, chi2)  # chi-square, 4 dof, alpha = 1e-4

@@ -178,6 +178,37 @@ def test_state_setters_statistics():
             assert abs(c["boost"] - 100 / 3) < 1e-4
 
 
+def _ref_reset_samples(cfg, n, seed):
+    from oracle import refsim
+
+    refsim.seed(seed)
+    g = refsim.RefGym(cfg)
+    out = []
+    for _ in range(n):
+        g.reset()
+        c, b, p, _t = g.arena.get_state()
+        out.append((c, b, p))
+    return out
+
+
+def test_random_state_distribution_matches_the_reference():
+    """RandomState(true, true, true) (RandomState.cpp:8-62) on the host build vs the live reference: every marginal the setter
+    defines passes a two-sample KS test (the RNG engines differ by construction, so only distributions can agree)."""
+    from oracle import refsim
+
+    if not refsim.available():
+        pytest.skip("oracle/_ref not built")
+    cfg = abi.default_cfg(num_arenas=1, team_size=1)
+    ref = _ref_reset_samples(cfg, 3000, 3)
+    hs = hostsim.HostSim(cfg)
+    ours = []
+    for _ in range(3000):
+        hs.reset(0)
+        c, b, p, _t = hs.get_state(0)
+        ours.append((c, b, p))
+    print(common.compare_setter_samples(ours, ref))
+
+
 def test_leaf_grid_returns_the_bvh_walks_leaves_in_order():
     """The per-cell leaf lists (rl_mesh.h grid_lookup) must give exactly the stackless walks' candidate leaves, in the
     walks' order, for every query box the grid accepts; bigger boxes must fall back to the walk."""
