@@ -173,15 +173,26 @@ def run_reference(args, rank, world):
     cfg = abi.default_cfg(num_arenas=T * G, team_size=TEAM)
     with stdout_to_stderr():
         b = refsim.RefBench(cfg, T, G, 7)
-        t_probe = b.run(10)
-        inner = int(max(10, min(1000, 10 * 2.0 / max(t_probe, 1e-3))))  # ~2 s per bench step
-        for _ in range(args.warmup):
+        b.run(160)  # one NoTouch horizon: the gyms reach their steady-state mix of resets / contacts, caches and threads are warm
+        t_probe = b.run(100)
+        # one bench step = one long burst (~2.5 s of every host thread; thread start-up is < 0.1 % of it), so that K steps are
+        # >= 2 000 env-steps per gym for K >= 8 and the arm reads the same as one long run (cpu_baseline_sample)
+        inner = int(max(250, min(20000, 100 * 2.5 / max(t_probe, 1e-3))))
+        for _ in range(min(args.warmup, 3)):
             b.run(inner)
         ts = [b.run(inner) for _ in range(args.steps)]
         b.close()
     total = sum(ts)
     v = T * G * inner * b.P * args.steps / total
-    sample = f"{T} threads x {G} gyms, {inner} env-steps per gym per bench step (bounded sample of the 16384-arena workload)"
+    sample = (f"{T} threads x {G} gyms, {inner} env-steps per gym per bench step x {args.steps} steps = {inner * args.steps} env-steps per gym after a "
+              f"160-step settle + {min(args.warmup, 3)} warm-up bursts (bounded sample of the 16384-arena workload); per-step rates min/median/max "
+              f"{T * G * inner * b.P / max(ts) / 1e6:.3f}/{T * G * inner * b.P / float(np.median(ts)) / 1e6:.3f}/{T * G * inner * b.P / min(ts) / 1e6:.3f} M/s")
+    ppo_ref = None
+    if not args.no_ppo:
+        try:
+            ppo_ref = reference_ppo_learn_time(args)
+        except Exception as ex:
+            ppo_ref = {"error": f"{type(ex).__name__}: {ex}"}
     out = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -192,7 +203,53 @@ def run_reference(args, rank, world):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if ppo_ref is not None:
+        out["ppo_iteration"] = ppo_ref
     emit(json.dumps(out))
+
+
+def reference_ppo_learn_time(args, iters=4):
+    """The metric's second half on the reference side: PPOLearner::Learn (PPOLearner.cpp:67-349) as the reference runs it — eager
+    libtorch operators (autograd, cuBLAS GEMMs, clip_grad_norm_, Adam) — through the line-by-line torch restatement
+    oracle/ppo_torch.py on THIS box's GPU (CPU when there is none), same batch shape as our arm's ppo_iteration: 131 072 rows,
+    4 minibatches, 1 epoch, 256x256x256 nets.  Both cuBLAS modes are timed: fp32 (libtorch's default, what the reference gets)
+    and TF32-allowed (the arithmetic our update uses)."""
+    import torch
+
+    from oracle import ppo_torch as PT
+    from rlgymppo_cpp_b200 import learner as L
+
+    dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+    rows = args.arenas * 2 * TEAM * args.env_steps
+    if dev == "cpu":
+        rows = min(rows, 8192)
+    obs = 51 + 19 * 2 * TEAM
+    out = {"device": dev, "rows": rows, "config": "batch = rows, 4 minibatches, 1 epoch, Adam lr 2e-4, policy/critic 256x256x256 (oracle/ppo_torch.py: eager torch)"}
+    g = np.random.default_rng(0)
+    data = {"states": torch.from_numpy(g.normal(size=(rows, obs)).astype(np.float32)).to(dev), "actions": torch.from_numpy(g.integers(0, 90, size=rows)).to(dev),
+            "log_probs": torch.from_numpy(np.log(g.uniform(0.008, 0.014, size=rows)).astype(np.float32)).to(dev),
+            "values": torch.from_numpy(g.normal(size=rows).astype(np.float32)).to(dev), "advantages": torch.from_numpy(g.normal(size=rows).astype(np.float32)).to(dev)}
+    for mode, allow in (("fp32", False), ("tf32", True)):
+        torch.backends.cuda.matmul.allow_tf32 = allow
+        torch.backends.cudnn.allow_tf32 = allow
+        torch.manual_seed(0)
+        cfg = L.PPOLearnerConfig(batchSize=rows, miniBatchSize=rows // 4, epochs=1, policyLR=2e-4, criticLR=2e-4, entCoef=0.01)
+        ppo = PT.TorchPPOLearner(obs, 90, cfg, dev)
+        exp = PT.ExperienceBuffer(rows, 0, dev)
+        exp.submit(data)
+        ts = []
+        for _ in range(iters + 2):
+            rep = {}
+            if dev != "cpu":
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ppo.learn(exp, rep)
+            if dev != "cpu":
+                torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        out[f"learn_time_{mode}_s"] = float(np.median(ts[2:]))
+    out["reference_s"] = out["learn_time_fp32_s"]
+    return out
 
 
 def run_ours(args, rank, local_rank, world):
@@ -235,9 +292,10 @@ def run_ours(args, rank, local_rank, world):
     # clocks / throttle reasons are sampled under load: from the warm-up on (nvidia-smi needs ~0.1 s to produce its first line)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    # settle the arenas into their steady-state mix (resets, contacts) before timing
+    # settle the arenas into their steady-state mix (resets, contacts) before timing: at least 160 env-steps (one NoTouch horizon)
+    W_run = max(W, -(-160 // T))
     with torch.cuda.stream(ext):
-        for i in range(W):
+        for i in range(W_run):
             one_iteration()
     barrier()
     launches0 = e.launch_count + col.launch_count
@@ -268,6 +326,37 @@ def run_ours(args, rank, local_rank, world):
     total_ms = float(total_ms.item())
     ms_per_step = total_ms / K
     value = world * A * P * T * K / (total_ms * 1e-3)
+    nb = 5 if K >= 5 else 1  # the K timed steps as 5 blocks: median block rate (this rank) next to the whole-region value
+    block_rates = [world * A * P * T * len(b) / (sum(b) * 1e-3) for b in np.array_split(np.array(ms), nb) if len(b)]
+
+    # e2e_collect: the SAME workload as `value` through the public API with HOST buffers on both sides: the policy / critic weights
+    # come from page-locked host memory every step (what ThreadAgentManager::SetNewPolicy hands the agents), collect + GAE run on
+    # the device, and the ExperienceBuffer rows (states, actions, log-probs, value targets, advantages) land in page-locked host memory
+    rows_c = A * P * T
+    st_d = torch.empty((rows_c, OBS), dtype=torch.float32, device="cuda"); ac_d = torch.empty(rows_c, dtype=torch.int64, device="cuda")
+    lp_d, vt_d, ad_d = (torch.empty(rows_c, dtype=torch.float32, device="cuda") for _ in range(3))
+    host_rows = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (st_d, ac_d, lp_d, vt_d, ad_d)]
+    n_ec = min(max(K, 8), 40)
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(n_ec):
+        col.set_weights(0, col.weights[0]); col.set_weights(1, col.weights[1])   # H2D: 1.3 MB of weights
+        col.collect(T)
+        col.gae(0.99, 0.95, 1.0, 10.0)
+        col.export_rows(states=st_d.data_ptr(), actions=ac_d.data_ptr(), log_probs=lp_d.data_ptr(), value_targets=vt_d.data_ptr(), advantages=ad_d.data_ptr())
+        e.sync()
+        for h, d in zip(host_rows, (st_d, ac_d, lp_d, vt_d, ad_d)):
+            h.copy_(d, non_blocking=True)
+        torch.cuda.synchronize()
+    barrier()
+    ec_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ec_t, op=dist.ReduceOp.MAX)
+    e2e_collect = {"value": world * rows_c * n_ec / float(ec_t.item()), "unit": UNIT,
+                   "h2d_bytes_per_step": int(sum(W_.nbytes + b_.nbytes for net in col.weights for W_, b_ in net)),
+                   "d2h_bytes_per_step": int(sum(h.numel() * h.element_size() for h in host_rows)), "steps": n_ec,
+                   "call": "Collector.set_weights (host) -> collect -> gae -> export_rows -> D2H of the ExperienceBuffer rows into page-locked memory"}
 
     # e2e: the reference-facing Gym::Step call with HOST buffers (H2D action indices from pinned memory, fused step,
     # D2H obs/reward/done), i.e. what a host-side policy (the reference's ThreadAgent) would drive
@@ -324,7 +413,8 @@ def run_ours(args, rank, local_rank, world):
             tf_peak = 1125.0
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (sim, gym layer, GAE) / tf32-in fp32-acc (MLP)", "data": "synthetic",
+            "value_median_of_blocks": float(np.median(block_rates)), "block_rates": block_rates, "warmup_run": W_run,
             "config": {"workload": f"{'cfg2: ' if (TEAM == 1 and A == ARENAS_PER_GPU) else 'sweep: '}{TEAM}v{TEAM} soccar, {A} arenas/GPU, {'DefaultOBSPadded(3)' if PADDED_OBS else 'DefaultObs'} + examplemain rewards{' in ZeroSumReward(0.3)' if ZERO_SUM else ''}/terminals, RandomState, tickSkip 8, "
                                    "on-device policy (256x256x256) + critic inference, sampling, trajectory ring, GAE; placeholder mesh set v1; "
                                    f"one bench step = one collect of {T} env-steps over every arena + GAE",
@@ -336,6 +426,7 @@ def run_ours(args, rank, local_rank, world):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "call": "rlg_engine_step_pinned (Gym::Step for every arena through the engine's page-locked host buffers: H2D action indices, "
                             "fused step, D2H obs/reward/done; uniform random host actions)", "reward_checksum": e2e_checksum},
+            "e2e_collect": e2e_collect,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "k_roles (fused Gym::Step)", "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": k_step_ms, "launches_timed": step_n,
@@ -367,17 +458,30 @@ def ppo_iteration_time(args, rank, local_rank, world, iters=6):
     A, T = args.arenas, args.env_steps
     rows = A * 2 * TEAM * T  # per rank
     cfg = learner.LearnerConfig(timestepsPerIteration=rows * world, expBufferSize=rows * world, randomSeed=123)
-    cfg.ppo = learner.PPOLearnerConfig(batchSize=rows, miniBatchSize=rows // 4, epochs=1, policyLR=2e-4, criticLR=2e-4, entCoef=0.01)
-    L = learner.Learner(workload_cfg(A, local_rank, rank), cfg, device_index=local_rank)
-    reports = L.learn(max_iterations=iters)
-    torch.cuda.synchronize()
-    tail = reports[2:]
-    med = lambda k: float(np.median([r[k] for r in tail]))
-    return {"total_iteration_time_s": med("Total Iteration Time"), "collection_time_s": med("Collection Time"),
-            "consumption_time_s": med("Consumption Time"), "ppo_learn_time_s": med("PPO Learn Time"),
-            "timesteps_per_iteration": int(tail[-1]["Timesteps Collected"]), "overall_steps_per_s": med("Overall Steps/Second"),
-            "config": f"batch {rows} rows/rank, 4 minibatches, 1 epoch, Adam lr 2e-4, policy/critic 256x256x256, the update's GEMMs on the hand-written tcgen05/TMA TF32 kernel (csrc/gemm.cu), minibatch step as a CUDA graph, "
-                      f"{world} data-parallel rank(s)", "iterations_timed": len(tail)}
+    cfg.sendMetrics = False
+    cfg.checkpointLoadFolder = cfg.checkpointSaveFolder = ""
+    cfg.ppo = learner.PPOLearnerConfig(batchSize=rows * world, miniBatchSize=rows * world // 4, epochs=1, policyLR=2e-4, criticLR=2e-4, entCoef=0.01)  # GLOBAL sizes
+    out = {}
+    for key, during in (("", False), ("collection_during_learn", True)):
+        cfg.collectionDuringLearn = during
+        L = learner.Learner(workload_cfg(A, local_rank, rank), cfg, device_index=local_rank)
+        reports = L.learn(max_iterations=iters + (2 if during else 0))
+        torch.cuda.synchronize()
+        tail = reports[2:-1] if during else reports[2:]
+        med = lambda k: float(np.median([r[k] for r in tail]))
+        r = {"total_iteration_time_s": med("Total Iteration Time"), "collection_time_s": med("Collection Time"),
+             "consumption_time_s": med("Consumption Time"), "ppo_learn_time_s": med("PPO Learn Time"), "ppo_learn_device_time_s": med("PPO Learn Device Time"),
+             "timesteps_per_iteration": int(tail[-1]["Timesteps Collected"]), "overall_steps_per_s": med("Overall Steps/Second"), "iterations_timed": len(tail)}
+        if key:
+            out[key] = r
+        else:
+            out.update(r)
+            out["ppo_launches_per_iteration"] = int(L.ppo.dev.launch_count // max(len(reports), 1))
+        del L
+    out["config"] = (f"global batch {rows * world} rows ({rows}/rank), 4 minibatches, 1 epoch, Adam lr 2e-4, policy/critic 256x256x256; the whole update on the device "
+                     f"(csrc/ppo.cu: gather, tcgen05/TMA TF32 GEMMs of csrc/gemm.cu, fused loss forward+backward, clip-by-norm + Adam), {world} data-parallel rank(s), "
+                     "one NCCL all-reduce of the flat gradient per optimiser step")
+    return out
 
 
 _REAL_STDOUT = None
@@ -397,8 +501,8 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=500, help="timed collects (default 500 = 2 000 env-steps per arena)")
+    ap.add_argument("--warmup", type=int, default=40, help="untimed collects (floored at 160 env-steps: one NoTouch horizon)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--arenas", type=int, default=ARENAS_PER_GPU, help="arenas per GPU (default: BASELINE configs[1])")
     ap.add_argument("--env-steps", type=int, default=4, help="env-steps per bench step (one collect call; cfg1's 100k timesteps/iteration ~ 4 x 32768)")

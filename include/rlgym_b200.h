@@ -400,6 +400,70 @@ uint64_t rlg_collector_launch_count(const rlg_collector* c);
  * (P/private/RLGymPPO_CPP/Threading/ThreadAgent.h "envStepTime"/"policyInferTime", ThreadAgentManager.cpp:82-117). */
 int rlg_collector_enable_timing(rlg_collector* c, int on);
 int rlg_collector_kernel_times(rlg_collector* c, double* step_ms, int32_t* step_launches, double* infer_ms, int32_t* infer_launches);
+/* rlg_collector_set_layer from DEVICE memory (W_dev [out, in] row-major, leading dimension ldw; b_dev [out]), packed by a kernel on
+ * `stream` (NULL = the engine's stream) — no host round trip. */
+int rlg_collector_set_layer_device(rlg_collector* c, int net, int layer, const float* W_dev, int ldw, const float* b_dev, int out_dim, int in_dim,
+                                   void* stream);
+/* Learner::AddNewExperience's report values (P/public/RLGymPPO_CPP/Learner.cpp:660-682) of the last collect + GAE, reduced on the
+ * device: out3_host = { mean |returns|, mean |advantages|, mean |value targets| } and the first n_first returns in the
+ * reference's concatenation order (what WelfordRunningStat::Increment receives, maxReturnsPerStatsInc). Synchronises. */
+int rlg_collector_return_stats(rlg_collector* c, double* out3_host, float* first_returns_host, int n_first, void* stream);
+
+/* ---- PPO learner on the device (csrc/ppo.cu) ---------------------------------------------------------------------------------
+ * Replaces PPOLearner (P/private/RLGymPPO_CPP/PPO/PPOLearner.cpp:17-349, 504-517) and ExperienceBuffer
+ * (PPO/ExperienceBuffer.cpp:12-121): the networks' parameters, gradients and Adam moments are ONE flat device vector each
+ * ([policy | critic], weights padded to multiples of 4 floats per dimension), the experience FIFO is a device ring, and
+ * Learn is hand-written kernels + the tcgen05 GEMM above — no autograd, no torch. */
+typedef struct rlg_ppo_cfg {
+    int32_t device;
+    int32_t obs_size, num_actions;
+    int32_t num_hidden;                             /* layerSizes.size() */
+    int32_t policy_hidden[RLG_MAX_HIDDEN_LAYERS];   /* PPOLearnerConfig::policyLayerSizes (multiples of 4) */
+    int32_t critic_hidden[RLG_MAX_HIDDEN_LAYERS];   /* PPOLearnerConfig::criticLayerSizes */
+    int64_t batch_size, mini_batch_size;            /* per replica; mini_batch_size 0 = batch_size (PPOLearner.cpp:19-23) */
+    int32_t epochs;
+    float policy_lr, critic_lr, ent_coef, clip_range, temperature;
+    int64_t exp_buffer_size;                        /* ExperienceBuffer maxSize, per replica */
+    uint64_t seed;                                  /* shuffle stream */
+    int32_t world;                                  /* data-parallel replicas (gradients = all-reduce SUM / world) */
+} rlg_ppo_cfg;
+typedef struct rlg_ppo_report {   /* the report keys PPOLearner::Learn writes (PPOLearner.cpp:296-347) */
+    double entropy, kl, ratio, value_loss, clip_fraction;      /* means over the minibatches */
+    double policy_update_magnitude, critic_update_magnitude;   /* |params before - after| */
+    int64_t batches, minibatches, cumulative_model_updates;
+    double device_ms;                                          /* CUDA-event time of the call on its stream */
+} rlg_ppo_report;
+typedef struct rlg_ppo rlg_ppo;
+/* In-place SUM all-reduce of count floats at grads_dev over the replicas, enqueued on `stream` (NCCL in the Python host). */
+typedef void (*rlg_allreduce_hook)(void* user, float* grads_dev, int64_t count, void* stream);
+
+int rlg_ppo_create(const rlg_ppo_cfg* cfg, rlg_ppo** out);
+int rlg_ppo_destroy(rlg_ppo* p);
+/* torch::nn::Linear default initialisation of every layer (DiscretePolicy.cpp:13-27, ValueEstimator.cpp:10-24). */
+int rlg_ppo_init_weights(rlg_ppo* p, uint64_t seed);
+/* which: 0 parameters, 1 gradients, 2 Adam exp_avg, 3 Adam exp_avg_sq; net: 0 policy, 1 critic; W_host [out, in], b_host [out]. */
+int rlg_ppo_set_layer(rlg_ppo* p, int which, int net, int layer, const float* W_host, const float* b_host, int out_dim, int in_dim);
+int rlg_ppo_get_layer(rlg_ppo* p, int which, int net, int layer, float* W_host, float* b_host, int out_dim, int in_dim);
+int rlg_ppo_adam_steps(rlg_ppo* p, int64_t* policy_steps, int64_t* critic_steps, int set);
+int rlg_ppo_flat(rlg_ppo* p, int which, float** dev, int64_t* count, int64_t* policy_count);
+int rlg_ppo_set_lr(rlg_ppo* p, float policy_lr, float critic_lr); /* PPOLearner::UpdateLearningRates */
+int rlg_ppo_set_allreduce_hook(rlg_ppo* p, rlg_allreduce_hook hook, void* user, int world);
+/* ExperienceBuffer::SubmitExperience: n rows of DEVICE data (states [n, obs], actions i64, log_probs, value targets, advantages). */
+int rlg_ppo_submit(rlg_ppo* p, const float* states, const int64_t* actions, const float* log_probs, const float* value_targets,
+                   const float* advantages, int64_t n, void* stream);
+int rlg_ppo_submit_collector(rlg_ppo* p, rlg_collector* c, void* stream); /* the collector's last collect (after rlg_collector_gae) */
+int64_t rlg_ppo_buffer_size(const rlg_ppo* p);
+int rlg_ppo_buffer_read(rlg_ppo* p, float* states_host, int64_t* actions_host, float* log_probs_host, float* value_targets_host,
+                        float* advantages_host);   /* FIFO order, oldest first */
+int rlg_ppo_peek_shuffle(rlg_ppo* p, int32_t* perm_host, uint64_t counter); /* the permutation epoch `counter` uses */
+uint64_t rlg_ppo_shuffle_counter(const rlg_ppo* p);
+/* PPOLearner::Learn on the buffer's current contents; report may be NULL (then the call does not synchronise). */
+int rlg_ppo_learn(rlg_ppo* p, rlg_ppo_report* report, void* stream);
+/* New weights to the agents (ThreadAgentManager::SetNewPolicy + the critic), device to device. */
+int rlg_ppo_push_weights(rlg_ppo* p, rlg_collector* c, void* stream);
+void* rlg_ppo_stream(rlg_ppo* p);
+uint64_t rlg_ppo_launch_count(const rlg_ppo* p);
+int64_t rlg_ppo_model_updates(const rlg_ppo* p);
 
 #ifdef __cplusplus
 }

@@ -153,5 +153,50 @@ def load_learner(learner, folder: Optional[str] = None) -> Optional[str]:
         p = os.path.join(src, name)
         if os.path.isfile(p):
             opt.load_state_dict(torch.load(p, map_location=learner.device))
+    if hasattr(learner.ppo, "upload_modules"):  # host mirrors -> the device learner's parameters
+        learner.ppo.upload_modules()
     learner._push_weights()
+    if st is not None and st.config.loadOldVersionsFromCheckpoints:
+        load_old_versions(learner, folder)
     return src
+
+
+def load_rating_set(st, r) -> dict:
+    """SkillTracker::LoadRatingSet (SkillTracker.cpp:259-291)."""
+    if isinstance(r, dict):
+        if st.config.perModeRatings:
+            out = {st.mode: float(st.config.initialRating)}
+            out.update({k: float(v) for k, v in r.items()})
+            return out
+        return {"": float(st.config.initialRating)}
+    return {st.mode: float(r)}
+
+
+def load_old_versions(learner, folder: str) -> int:
+    """Learner::Load's old-version scan (Learner.cpp:311-371): for i = 1..maxVersions the checkpoint closest to
+    totalTimesteps - i * timestepsPerVersion (below the previous target, at most one interval short) that carries a
+    skill_rating becomes an old policy version with that rating."""
+    st = learner.skill_tracker
+    interval = int(st.config.timestepsPerVersion)
+    target = int(learner.total_timesteps)
+    found = 0
+    for _ in range(st.config.maxVersions):
+        target -= interval
+        best, best_rating = -1, None
+        for n in numbered_folders(folder):
+            if n < target + interval and (best == -1 or abs(n - target) < abs(best - target)):
+                sp = os.path.join(folder, str(n), STATS_FILE_NAME)
+                if os.path.isfile(sp):
+                    j = load_stats(sp)
+                    if "skill_rating" in j:
+                        best, best_rating = n, j["skill_rating"]
+        if best != -1 and best >= target - interval:
+            mp = os.path.join(folder, str(best), MODEL_FILE_NAMES[0])
+            if os.path.isfile(mp):
+                from .learner import make_mlp, mlp_layers_numpy
+
+                seq = make_mlp(learner.engine.obs_size, list(learner.cfg.ppo.policyLayerSizes), 90)
+                load_seq(seq, mp)
+                st.append_old_policy(mlp_layers_numpy(seq), load_rating_set(st, best_rating))
+                found += 1
+    return found

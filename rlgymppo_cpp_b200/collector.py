@@ -181,6 +181,19 @@ class Collector:
         _check(self.L.rlg_engine_copy_to_host(self.engine.h, out.ctypes.data_as(C.c_void_p), C.c_void_p(getattr(v, name)), C.c_size_t(out.nbytes)))
         return out
 
+    def return_stats(self, n_first: int = 0):
+        """(means [3] = mean |returns|, |advantages|, |value targets| of the last collect + GAE; the first n_first returns in the
+        reference's concatenation order) — reduced on the device, one small D2H (Learner.cpp:660-682)."""
+        means = np.zeros(3, dtype=np.float64)
+        first = np.zeros(max(n_first, 1), dtype=np.float32)
+        _check(self.L.rlg_collector_return_stats(self.h, means.ctypes.data_as(C.c_void_p), first.ctypes.data_as(C.c_void_p), int(n_first), None))
+        v = self.view()
+        return means, first[: min(n_first, v.T * v.N)]
+
+    def set_weights_device(self, net: int, layer: int, w_ptr: int, ldw: int, b_ptr: int, out_dim: int, in_dim: int, stream: int = 0):
+        _check(self.L.rlg_collector_set_layer_device(self.h, net, layer, C.c_void_p(w_ptr), ldw, C.c_void_p(b_ptr), out_dim, in_dim,
+                                                     C.c_void_p(stream) if stream else None))
+
     def enable_timing(self, on=True):
         _check(self.L.rlg_collector_enable_timing(self.h, int(on)))
 

@@ -437,6 +437,38 @@ __global__ void k_export_rows(int T, int N, int P, int obsSize, const float* __r
     }
 }
 
+// mean |returns|, |advantages|, |value targets| of a collect (block sums -> 3 double atomics) and its first nFirst returns in the
+// reference's concatenation order (row i = n * T + t)
+__global__ void __launch_bounds__(256) k_return_stats(int T, int N, const float* __restrict__ ret, const float* __restrict__ adv, const float* __restrict__ tgt,
+                                                      double* __restrict__ sums, float* __restrict__ first, int nFirst) {
+    __shared__ float red[3][8];
+    const size_t total = (size_t)T * N;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) { s0 += fabsf(ret[i]); s1 += fabsf(adv[i]); s2 += fabsf(tgt[i]); }
+    for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s0; red[1][threadIdx.x >> 5] = s1; red[2][threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float t = 0.f;
+        for (int w = 0; w < 8; w++) t += red[threadIdx.x][w];
+        atomicAdd(sums + threadIdx.x, (double)t);
+    }
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < nFirst; i += 256) { const int n = i / T, t = i - n * T; first[i] = ret[(size_t)t * N + n]; }
+}
+
+// nn.Linear weight [out, in] (leading dimension ldw) -> the inference kernel's packed layout: [kPad / 32] canonical (nPad x 32)
+// blocks, TF32-rounded, zero padded; bias -> [nPad]
+__global__ void k_pack_layer(const float* __restrict__ W, int ldw, const float* __restrict__ b, int out, int in, int kPad, int nPad, float* __restrict__ dW,
+                             float* __restrict__ dB) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kPad * nPad) return;
+    const int n = i / kPad, k = i - n * kPad;
+    const float v = (n < out && k < in) ? to_tf32(W[(size_t)n * ldw + k]) : 0.f;
+    dW[(size_t)(k / kBlockK) * nPad * kBlockK + canon_off(n, k % kBlockK) / 4] = v;
+    if (k == 0) dB[n] = n < out ? b[n] : 0.f;
+}
+
 }  // namespace
 
 // ---- host side ------------------------------------------------------------------------------------------------------
@@ -453,6 +485,7 @@ struct rlg_collector {
     float* dObs = nullptr; int32_t* dAction = nullptr; float* dLogprob = nullptr; float* dReward = nullptr; uint8_t* dDone = nullptr;
     float* dValue = nullptr; float* dAdv = nullptr; float* dTarget = nullptr; float* dRet = nullptr;
     bool haveObs0 = false;
+    double* dStats = nullptr;  // rlg_collector_return_stats workspace
     uint64_t stepCounter = 0, launches = 0;
     rlg_reset_hook resetHook = nullptr;
     void* resetUser = nullptr;
@@ -517,7 +550,7 @@ int rlg_collector_destroy(rlg_collector* c) {
     cudaSetDevice(c->device);
     for (int n = 0; n < 2; n++) for (int l = 0; l < kMaxLayers; l++) { cudaFree(c->L[n][l].dW); cudaFree(c->L[n][l].dB); }
     cudaFree(c->dObs); cudaFree(c->dAction); cudaFree(c->dLogprob); cudaFree(c->dReward); cudaFree(c->dDone);
-    cudaFree(c->dValue); cudaFree(c->dAdv); cudaFree(c->dTarget); cudaFree(c->dRet);
+    cudaFree(c->dValue); cudaFree(c->dAdv); cudaFree(c->dTarget); cudaFree(c->dRet); cudaFree(c->dStats);
     for (auto ev : c->evStep) cudaEventDestroy(ev);
     for (auto ev : c->evInfer) cudaEventDestroy(ev);
     delete c;
@@ -600,6 +633,24 @@ int rlg_collector_set_layer(rlg_collector* c, int net, int layer, const float* W
     CKC(cudaMemcpyAsync(h.dW, pw.data(), pw.size() * 4, cudaMemcpyHostToDevice, s));
     CKC(cudaMemcpyAsync(h.dB, pb.data(), pb.size() * 4, cudaMemcpyHostToDevice, s));
     CKC(cudaStreamSynchronize(s));
+    h.set = true;
+    return RLG_OK;
+}
+
+// The same from DEVICE memory (W_dev [out, in] row-major with leading dimension ldw, b_dev [out]): packed by a kernel on `stream`
+// (NULL = the engine's stream), no host round trip — how the native PPO learner (ppo.cu) hands new weights to the agents.
+int rlg_collector_set_layer_device(rlg_collector* c, int net, int layer, const float* W_dev, int ldw, const float* b_dev, int out_dim, int in_dim,
+                                   void* stream) {
+    if (!c || !W_dev || !b_dev) return failc(RLG_ERR_INVALID, "null argument");
+    if (net < 0 || net > 1 || layer < 0 || layer >= c->numLayers) return failc(RLG_ERR_INVALID, "bad net/layer index");
+    auto& h = c->L[net][layer];
+    if (out_dim != h.out || in_dim != h.in || ldw < in_dim) return failc(RLG_ERR_INVALID, "layer shape does not match the collector configuration");
+    CKC(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : (cudaStream_t)rlg_engine_stream(c->e);
+    const int total = h.kPad * h.nPad;
+    k_pack_layer<<<(total + 255) / 256, 256, 0, s>>>(W_dev, ldw, b_dev, h.out, h.in, h.kPad, h.nPad, h.dW, h.dB);
+    c->launches++;
+    CKC(cudaGetLastError());
     h.set = true;
     return RLG_OK;
 }
@@ -728,6 +779,28 @@ int rlg_collector_export(rlg_collector* c, float* states, int64_t* actions, floa
                                                    states, actions, log_probs, rewards, next_states, dones, truncateds, value_targets, advantages);
     c->launches++;
     CKC(cudaGetLastError());
+    return RLG_OK;
+}
+
+int rlg_collector_return_stats(rlg_collector* c, double* out3_host, float* first_returns_host, int n_first, void* stream) {
+    if (!c || !out3_host) return failc(RLG_ERR_INVALID, "null argument");
+    if (c->T < 1) return failc(RLG_ERR_STATE, "rlg_collector_collect has not run");
+    CKC(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : (cudaStream_t)rlg_engine_stream(c->e);
+    const long total = (long)c->T * c->N;
+    if (n_first < 0 || !first_returns_host) n_first = 0;
+    if (n_first > total) n_first = (int)total;
+    if (!c->dStats) CKC(cudaMalloc(&c->dStats, 3 * 8 + 4096 * 4));
+    if (n_first > 4096) return failc(RLG_ERR_INVALID, "n_first must be <= 4096");
+    float* first = reinterpret_cast<float*>(c->dStats + 3);
+    CKC(cudaMemsetAsync(c->dStats, 0, 24, s));
+    k_return_stats<<<148, 256, 0, s>>>(c->T, c->N, c->dRet, c->dAdv, c->dTarget, c->dStats, first, n_first);
+    c->launches++;
+    CKC(cudaGetLastError());
+    CKC(cudaMemcpyAsync(out3_host, c->dStats, 24, cudaMemcpyDeviceToHost, s));
+    if (n_first > 0) CKC(cudaMemcpyAsync(first_returns_host, first, (size_t)n_first * 4, cudaMemcpyDeviceToHost, s));
+    CKC(cudaStreamSynchronize(s));
+    for (int i = 0; i < 3; i++) out3_host[i] /= (double)total;
     return RLG_OK;
 }
 

@@ -31,6 +31,12 @@ EXPORTS = [
     "rlg_collector_create", "rlg_collector_destroy", "rlg_collector_set_layer", "rlg_collector_infer", "rlg_collector_collect",
     "rlg_collector_gae", "rlg_collector_view", "rlg_collector_export", "rlg_collector_launch_count",
     "rlg_collector_enable_timing", "rlg_collector_kernel_times", "rlg_collector_set_reset_hook", "rlg_engine_reset_current_to",
+    "rlg_collector_set_layer_device", "rlg_collector_return_stats",
+    # device PPO learner (bound in rlgymppo_cpp_b200.ppo)
+    "rlg_ppo_create", "rlg_ppo_destroy", "rlg_ppo_init_weights", "rlg_ppo_set_layer", "rlg_ppo_get_layer", "rlg_ppo_adam_steps", "rlg_ppo_flat",
+    "rlg_ppo_set_lr", "rlg_ppo_set_allreduce_hook", "rlg_ppo_submit", "rlg_ppo_submit_collector", "rlg_ppo_buffer_size", "rlg_ppo_buffer_read",
+    "rlg_ppo_peek_shuffle", "rlg_ppo_shuffle_counter", "rlg_ppo_learn", "rlg_ppo_push_weights", "rlg_ppo_stream", "rlg_ppo_launch_count",
+    "rlg_ppo_model_updates",
 ]
 
 _lib = None

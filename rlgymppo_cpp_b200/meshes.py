@@ -139,6 +139,24 @@ def parse_cmf(blob: bytes):
     return tris, verts
 
 
+def read_cmf_folder(folder: str, game_mode: str = "soccar") -> List[bytes]:
+    """The .cmf files RocketSim::Init(folder) loads for a game mode (R/RocketSim.cpp:70-212: <folder>/<mode>/*.cmf), as blobs in
+    directory order, e.g. the real arena meshes dumped with the reference's asset tool."""
+    import os
+
+    d = os.path.join(folder, game_mode)
+    if not os.path.isdir(d):
+        raise RuntimeError(f"RocketSim::Init: collision mesh folder {d} does not exist")
+    names = sorted(n for n in os.listdir(d) if n.lower().endswith(".cmf"))
+    if not names:
+        raise RuntimeError(f"RocketSim::Init: no .cmf files in {d}")
+    blobs = []
+    for n in names:
+        with open(os.path.join(d, n), "rb") as f:
+            blobs.append(f.read())
+    return blobs
+
+
 def write_placeholder_set(folder: str) -> List[str]:
     """Writes the set as <folder>/soccar/placeholder_<i>.cmf (what RocketSim::Init reads)."""
     import os

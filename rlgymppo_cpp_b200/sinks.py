@@ -103,7 +103,7 @@ class MetricSender:
         if run_id:
             kw.update(id=run_id, resume="allow")
         self.run = wandb.init(**kw)
-        self.cur_run_id = self.run.id
+        self.cur_run_id = self.run_id = self.run.id
 
     def send(self, report: Dict[str, float]):
         self.run.log({k: v for k, v in report.items()})

@@ -164,7 +164,7 @@ class SkillTracker:
 
     # ---- device wiring -------------------------------------------------------------------------------------------
     @classmethod
-    def on_engine(cls, config: SkillTrackerConfig, train_engine_cfg, policy_hidden, device_index: int = 0, seed: int = 0):
+    def on_engine(cls, config: SkillTrackerConfig, train_engine_cfg, policy_hidden, device_index: int = 0, seed: int = 0, mesh_blobs=None):
         """Eval pool = a second engine with numEnvs arenas of the training configuration (same mode, obs builder,
         terminal conditions), dummy rewards, kickoff states if configured; inference through one deterministic collector."""
         import torch
@@ -177,9 +177,10 @@ class SkillTracker:
         ecfg.arena_id_base = 1 << 24  # RNG streams apart from the training arenas
         ecfg.num_reward_terms = 0     # DummyReward
         ecfg.zero_sum = 0
-        if config.kickoffStatesOnly:
+        if config.kickoffStatesOnly or ecfg.state_setter == abi.RLG_SETTER_HOST:
+            # a host StateSetter of the training pool is not wired into the eval pool: its games start from kickoffs
             ecfg.state_setter = abi.RLG_SETTER_KICKOFF
-        e = engine.Engine(ecfg)
+        e = engine.Engine(ecfg, mesh_blobs=mesh_blobs)
         col = collector.Collector(e, tuple(policy_hidden), tuple(policy_hidden), max_steps=1, seed=seed, deterministic=True)
         st = cls(config, int(ecfg.team_size), bool(ecfg.spawn_opponents), int(ecfg.tick_skip), seed)
         st.engine, st.collector = e, col
@@ -189,13 +190,32 @@ class SkillTracker:
         act = torch.empty(A * P, dtype=torch.int32, device=f"cuda:{device_index}")
         counter = [0]
 
+        # one collector (= one packed TF32 weight set on the device) per policy version in play: a version is packed once,
+        # when it first plays, not on every step.  The cache holds a reference to the weight object, so its id stays unique.
+        packed = {}
+        spare = [col]
+
+        def collector_for(weights):
+            hit = packed.get(id(weights))
+            if hit is not None:
+                return hit[1]
+            if len(packed) > config.maxVersions + 2:  # versions that left the pool (and previous current policies)
+                live = {id(w) for w in st.old_policies}
+                for k in [k for k in packed if k not in live]:
+                    spare.append(packed.pop(k)[1])
+            c = spare.pop() if spare else collector.Collector(e, tuple(policy_hidden), tuple(policy_hidden), max_steps=1, seed=seed, deterministic=True)
+            if c.weights[1] is None:
+                c.init_default(seed)  # the critic is never run
+            c.set_weights(0, weights)
+            packed[id(weights)] = (weights, c)
+            return c
+
         def infer(weights):
-            col.set_weights(0, weights)
+            c = collector_for(weights)
             obs_ptr, _, _ = e.output_ptrs()
-            col.infer(obs_ptr, A * P, counter[0], action_ptr=act.data_ptr())
+            c.infer(obs_ptr, A * P, counter[0], action_ptr=act.data_ptr())
             counter[0] += 1
             e.sync()
-            torch.cuda.synchronize()
             return act.cpu().numpy().copy()
 
         prev_lines = np.zeros((A, 2), dtype=np.int32)
@@ -221,6 +241,5 @@ class SkillTracker:
             prev_lines[:] = 0
 
         st.infer_fn, st.step_fn, st.reset_all_fn = infer, step, reset_all
-        col.init_default(seed)  # the critic is never run; the policy weights are pushed per call
         e.reset()
         return st

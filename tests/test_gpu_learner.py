@@ -29,7 +29,7 @@ def test_learner_two_iterations_and_weight_roundtrip():
     assert abs(reps[0]["Mean Ratio"] - 1) < 5e-2  # first epoch starts at ratio ~1: TF32 inference vs the update's forward
     assert reps[1]["Cumulative Model Updates"] > reps[0]["Cumulative Model Updates"]
     assert any(not torch.equal(a, b) for a, b in zip(w0, lr.ppo.policy.parameters()))
-    assert lr.exp.cur_size == 6144
+    assert lr.ppo.dev.buffer_size == 6144
     # the collector now infers with the UPDATED weights
     obs = np.random.default_rng(0).uniform(-1, 1, size=(256, lr.engine.obs_size)).astype(np.float32)
     t_obs = torch.from_numpy(obs).cuda()
