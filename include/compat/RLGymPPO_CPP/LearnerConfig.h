@@ -1,0 +1,3 @@
+// Source-compatibility forwarder: <RLGymPPO_CPP/LearnerConfig.h> of the reference resolves to the B200 shim (include/rlgym_b200_shim.hpp).
+#pragma once
+#include "../../rlgym_b200_shim.hpp"

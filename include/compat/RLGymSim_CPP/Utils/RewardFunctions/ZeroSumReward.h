@@ -1,0 +1,3 @@
+// Source-compatibility forwarder: <RLGymSim_CPP/Utils/RewardFunctions/ZeroSumReward.h> of the reference resolves to the B200 shim (include/rlgym_b200_shim.hpp).
+#pragma once
+#include "../../../../rlgym_b200_shim.hpp"

@@ -313,6 +313,46 @@ int rlg_engine_sync(rlg_engine* e);
 int rlg_engine_step_to(rlg_engine* e, const int32_t* action_idx, float* obs_out, float* reward_out, uint8_t* done_out,
                        void* stream);
 
+/* ---- host-plugin path: user-defined OBSBuilder / RewardFunction / TerminalCondition / StepCallback -------------------------------
+ * (G/Utils/OBSBuilders/OBSBuilder.h:10-15, RewardFunctions/RewardFunction.h:9-35, TerminalConditions/TerminalCondition.h:7-8,
+ * P/public/RLGymPPO_CPP/Threading/GameInst.h:7).  Gym::Step is split where the reference takes its GameState (G/Gym.cpp:84-93):
+ * step_begin = ParseActions + the first tick + GameEventTracker::Update + GameState::UpdateFromArena (+ the fused built-in obs /
+ * reward / done into the given buffers, NULL = the engine's own); export_gamestates = that GameState for the host;
+ * step_end = the other tickSkip - 1 ticks.  No auto-reset and no reward metrics: the host decides `done` and keeps GameInst's
+ * trackers.  Arrays: cars / players are [n * P] in PLAYER order (GameState::players), balls / gym [n]; ids NULL = every arena. */
+typedef struct rlg_gym_player {   /* PlayerData minus its CarState (G/Utils/Gamestates/PlayerData.h:7-38) */
+    int32_t match_goals, match_saves, match_assists, match_shots, match_shot_passes, match_bumps, match_demos, boost_pickups;
+    int32_t ball_touched_step, ball_touched_tick;
+    float prev_action[8];         /* Match::prevActions row */
+} rlg_gym_player;
+typedef struct rlg_gym_state {    /* GameState minus players / ball (G/Utils/Gamestates/GameState.h:19-57) */
+    int64_t tick_count;           /* Arena::tickCount == GameState::lastTickCount after the update */
+    int32_t score_line[2], last_touch_car_id;
+    int32_t steps_since_touch;    /* NoTouchCondition's counter (informational) */
+    int32_t pad_active[RLG_NUM_PADS];  /* GameState::boostPads order = CommonValues::BOOST_LOCATIONS */
+    float pad_cooldown[RLG_NUM_PADS];  /* GameState::boostPadTimers */
+} rlg_gym_state;
+size_t rlg_sizeof_gym_state(void);
+size_t rlg_sizeof_gym_player(void);
+int rlg_engine_step_begin(rlg_engine* e, const int32_t* action_idx, float* obs_out, float* reward_out, uint8_t* done_out, void* stream);
+int rlg_engine_step_end(rlg_engine* e, const int32_t* action_idx, void* stream);
+int rlg_engine_export_gamestates(rlg_engine* e, const int32_t* arena_ids_host, int n, rlg_car_state* cars_host, rlg_ball_state* balls_host,
+                                 rlg_gym_state* gym_host, rlg_gym_player* players_host);
+/* The same in two halves so that step_end can run on the GPU while the copy is in flight and the host plugins work. */
+int rlg_engine_export_gamestates_async(rlg_engine* e, const int32_t* arena_ids_host, int n, rlg_car_state* cars_host, rlg_ball_state* balls_host,
+                                       rlg_gym_state* gym_host, rlg_gym_player* players_host);
+int rlg_engine_export_wait(rlg_engine* e);
+/* Gym::Reset (state setter + EpisodeReset) with the obs rows written to a caller DEVICE buffer [A*P, obs]. */
+int rlg_engine_reset_to(rlg_engine* e, const uint8_t* mask_host, float* obs_out, void* stream);
+/* Page-locked host memory for the export / upload buffers. */
+void* rlg_host_alloc(size_t bytes);
+void rlg_host_free(void* p);
+/* Device memory on the engine's GPU for callers without a CUDA runtime of their own (the C++ shim's trajectory tensors). */
+void* rlg_device_alloc(rlg_engine* e, size_t bytes);
+void rlg_device_free(rlg_engine* e, void* p);
+/* Lets a host callback (step / reset hook) report why it failed through rlg_last_error(). */
+void rlg_set_last_error(const char* msg);
+
 /* ---- collector: device-resident ThreadAgent loop --------------------------------------------------------------------
  * Replaces ThreadAgent::_RunFunc (P/private/RLGymPPO_CPP/Threading/ThreadAgent.cpp:24-195: infer -> step -> append),
  * DiscretePolicy::GetAction (P/private/RLGymPPO_CPP/PPO/DiscretePolicy.cpp:44-62), ValueEstimator::Forward
@@ -394,6 +434,13 @@ int rlg_collector_export(rlg_collector* c, float* states, int64_t* actions, floa
  * (G/Envs/Match.cpp:54-70) reached from GameInst::Step's auto-reset (GameInst.cpp:20-24). */
 typedef void (*rlg_reset_hook)(void* user, const int32_t* arena_ids_host, int n, float* obs_out);
 int rlg_collector_set_reset_hook(rlg_collector* c, rlg_reset_hook hook, void* user);
+/* Host-plugin collection: with a step hook installed every env-step of a collect runs as
+ *   infer -> rlg_engine_step_begin (built-in outputs into the ring slot) -> hook(user, t, actions, obs_next, reward, done)
+ * and the hook finishes the step: it exports the GameStates, launches rlg_engine_step_end, runs the user's plugins, uploads the rows
+ * they produced into the DEVICE slots it was given (obs_next [A*P, obs], reward [A*P], done [A] u8) and re-sets finished arenas
+ * (writing their post-reset obs into obs_next).  Replaces GameInst::Step's body for that configuration (GameInst.cpp:7-38). */
+typedef int (*rlg_step_hook)(void* user, int t, const int32_t* actions_dev, float* obs_next_dev, float* reward_dev, uint8_t* done_dev);
+int rlg_collector_set_step_hook(rlg_collector* c, rlg_step_hook hook, void* user);
 uint64_t rlg_collector_launch_count(const rlg_collector* c);
 /* Per-kernel CUDA-event timing of the LAST collect on its launching stream (bench roofline): summed durations and launch
  * counts of the fused Gym::Step kernel and of the MLP inference kernel. Replaces ThreadAgent::Times

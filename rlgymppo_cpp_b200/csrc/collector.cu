@@ -489,6 +489,8 @@ struct rlg_collector {
     uint64_t stepCounter = 0, launches = 0;
     rlg_reset_hook resetHook = nullptr;
     void* resetUser = nullptr;
+    rlg_step_hook stepHook = nullptr;
+    void* stepUser = nullptr;
     std::vector<uint8_t> hDone;
     std::vector<int32_t> hIds;
     // optional per-kernel timing of the last collect (CUDA events on the launching stream)
@@ -693,6 +695,18 @@ int rlg_collector_collect(rlg_collector* c, int n_steps, void* stream) {
         mark(c->evInfer, c->nInferEv);
         if (rc != RLG_OK) return rc;
         mark(c->evStep, c->nStepEv);
+        if (c->stepHook) {  // host plugins finish the step (and re-set finished arenas themselves)
+            if (rlg_engine_step_begin(c->e, c->dAction + (size_t)t * N, c->dObs + (size_t)(t + 1) * N * c->obs, c->dReward + (size_t)t * N,
+                                      c->dDone + (size_t)t * c->A, s) != RLG_OK)
+                return failc(RLG_ERR_STATE, rlg_last_error());
+            if (c->stepHook(c->stepUser, t, c->dAction + (size_t)t * N, c->dObs + (size_t)(t + 1) * N * c->obs, c->dReward + (size_t)t * N,
+                            c->dDone + (size_t)t * c->A) != RLG_OK)
+                return failc(RLG_ERR_STATE, std::string("step hook failed: ") + rlg_last_error());
+            mark(c->evStep, c->nStepEv);
+            c->launches++;
+            c->stepCounter++;
+            continue;
+        }
         if (rlg_engine_step_to(c->e, c->dAction + (size_t)t * N, c->dObs + (size_t)(t + 1) * N * c->obs, c->dReward + (size_t)t * N,
                                c->dDone + (size_t)t * c->A, s) != RLG_OK)
             return failc(RLG_ERR_STATE, rlg_last_error());
@@ -718,6 +732,12 @@ int rlg_collector_collect(rlg_collector* c, int n_steps, void* stream) {
 int rlg_collector_set_reset_hook(rlg_collector* c, rlg_reset_hook hook, void* user) {
     if (!c) return failc(RLG_ERR_INVALID, "null collector");
     c->resetHook = hook; c->resetUser = user;
+    return RLG_OK;
+}
+
+int rlg_collector_set_step_hook(rlg_collector* c, rlg_step_hook hook, void* user) {
+    if (!c) return failc(RLG_ERR_INVALID, "null collector");
+    c->stepHook = hook; c->stepUser = user;
     return RLG_OK;
 }
 

@@ -63,6 +63,10 @@ struct rlg_engine {
     int barMode = 0, asyncLoad = 1;
     uint32_t *prof = nullptr, *prof2 = nullptr;  // RLG_PHASE_TIMING builds only
     uint64_t launches = 0;
+    // host-plugin path: device staging of rlg_engine_export_gamestates (grown on demand)
+    int32_t* xIds = nullptr; rlg_car_state* xCars = nullptr; rlg_ball_state* xBalls = nullptr; rlg_gym_state* xGym = nullptr; rlg_gym_player* xPlayers = nullptr;
+    int xCap = 0;
+    cudaEvent_t evExport = nullptr;
 };
 
 // ---- state movement -----------------------------------------------------------------------------
@@ -131,6 +135,52 @@ __global__ void k_get_state(const uint32_t* state, SimCfg cfg, int nwords, const
     if (balls) { rlg_ball_state o; ball_to_pod(o, s.ball); balls[i] = o; }
     if (pads) for (int p = 0; p < kNumPads; p++) { rlg_pad_state o; pad_to_pod(o, s.pads, p); pads[(size_t)i * kNumPads + p] = o; }
     if (ticks) ticks[i] = get_i64(s.tickLo, s.tickHi);
+}
+
+// GameState::UpdateFromArena's view of n arenas for host plugins (G/Utils/Gamestates/GameState.cpp:52-104, PlayerData.cpp:4-33):
+// the CarStates in PLAYER order, the ball, and the gym-layer members (match counters, touch flags, prevActions, score line, pads
+// in CommonValues::BOOST_LOCATIONS order).  Run on the state as the step's snapshot left it (tick 0 of a split step, or a reset).
+__global__ void k_export_gamestates(const uint32_t* state, SimCfg cfg, int nwords, const Tables* __restrict__ tb, const int32_t* __restrict__ ids, int n,
+                                    rlg_car_state* __restrict__ cars, rlg_ball_state* __restrict__ balls, rlg_gym_state* __restrict__ gym,
+                                    rlg_gym_player* __restrict__ players) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int a = ids ? ids[i] : i;
+    ArenaS s;
+    load_arena(s, state, cfg.numArenas, a, nwords);
+    const int64_t tick = get_i64(s.tickLo, s.tickHi);
+    for (int p = 0; p < cfg.numCars; p++) {
+        const int ci = cfg.playerOrder[p];
+        const CarS& c = s.cars[ci];
+        if (cars) {
+            rlg_car_state o;
+            memset(&o, 0, sizeof(o));
+            car_to_pod(o, c, ci, cfg.spawnOpponents);
+            cars[(size_t)i * cfg.numCars + p] = o;
+        }
+        if (players) {
+            rlg_gym_player o;
+            o.match_goals = c.matchGoals; o.match_saves = c.matchSaves; o.match_assists = c.matchAssists; o.match_shots = c.matchShots;
+            o.match_shot_passes = c.matchShotPasses; o.match_bumps = c.matchBumps; o.match_demos = c.matchDemos; o.boost_pickups = c.boostPickups;
+            o.ball_touched_step = c.touchedStep;
+            o.ball_touched_tick = c.hitValid ? (get_i64(c.hitTickLo, c.hitTickHi) == tick - 1) : 0;  // PlayerData.cpp:22
+            for (int k = 0; k < 8; k++) o.prev_action[k] = c.prevAction[k];
+            players[(size_t)i * cfg.numCars + p] = o;
+        }
+    }
+    if (balls) { rlg_ball_state o; ball_to_pod(o, s.ball); balls[i] = o; }
+    if (gym) {
+        rlg_gym_state o;
+        o.tick_count = tick;
+        o.score_line[0] = s.scoreLine[0]; o.score_line[1] = s.scoreLine[1]; o.last_touch_car_id = s.lastTouchCarId;
+        o.steps_since_touch = s.stepsSinceTouch;
+        for (int g = 0; g < kNumPads; g++) {
+            const int pi = tb->padMap[g];
+            o.pad_active[g] = (int32_t)((pads_active(s.pads) >> pi) & 1ULL);
+            o.pad_cooldown[g] = s.pads.cooldown[pi];
+        }
+        gym[i] = o;
+    }
 }
 
 // ---- the role kernel: Arena::Step x n (mode 0) or the fused Gym::Step + GameInst auto-reset (mode 1) -----------------------
@@ -644,6 +694,8 @@ int rlg_engine_destroy(rlg_engine* e) {
     }
 #endif
     cudaFree(e->scratch); cudaFree(e->metrics); cudaFree(e->epa);
+    cudaFree(e->xIds); cudaFree(e->xCars); cudaFree(e->xBalls); cudaFree(e->xGym); cudaFree(e->xPlayers);
+    if (e->evExport) cudaEventDestroy(e->evExport);
     cudaFree(e->state); cudaFree(e->tables); cudaFree(e->obs); cudaFree(e->reward); cudaFree(e->done); cudaFree(e->actions);
     for (void* p : e->meshMem) cudaFree(p);
     cudaFreeHost(e->hActions); cudaFreeHost(e->hObs); cudaFreeHost(e->hReward); cudaFreeHost(e->hDone);
@@ -1094,6 +1146,93 @@ int rlg_engine_step_pinned(rlg_engine* e, int want_obs) {
     CK(cudaSetDevice(e->device));
     return step_pinned_impl(e, want_obs);
 }
+
+// ---- host-plugin path (user OBSBuilder / RewardFunction / TerminalCondition / StepCallback on the host) ---------------------------
+// Gym::Step split at the point where the reference takes its GameState (G/Gym.cpp:84-93):
+//   rlg_engine_step_begin   parse + first tick + event tracker + GameState::UpdateFromArena (+ the fused built-in obs / reward / done)
+//   rlg_engine_export_gamestates_async / _wait   that snapshot to the host (kernel on the engine's stream, D2H on its copy stream)
+//   rlg_engine_step_end     the remaining tickSkip - 1 ticks (no auto-reset: the host decides `done`)
+int rlg_engine_step_begin(rlg_engine* e, const int32_t* action_idx, float* obs_out, float* reward_out, uint8_t* done_out, void* stream) {
+    if (!e || !action_idx) return fail(RLG_ERR_INVALID, "null argument");
+    if (!e->meshesLoaded) return fail(RLG_ERR_STATE, "rlg_engine_load_meshes must be called first (RocketSim::Init)");
+    CK(cudaSetDevice(e->device));
+    return do_step(e, action_idx, pick(e, stream), 0, obs_out, reward_out, done_out, 0, 1);
+}
+int rlg_engine_step_end(rlg_engine* e, const int32_t* action_idx, void* stream) {
+    if (!e || !action_idx) return fail(RLG_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(e->device));
+    if (e->cfg.tickSkip < 2) return RLG_OK;
+    return do_step(e, action_idx, pick(e, stream), 0, nullptr, nullptr, nullptr, 1, e->cfg.tickSkip);
+}
+int rlg_engine_export_gamestates_async(rlg_engine* e, const int32_t* ids, int n, rlg_car_state* cars, rlg_ball_state* balls, rlg_gym_state* gym,
+                                       rlg_gym_player* players) {
+    if (!e || n < 0) return fail(RLG_ERR_INVALID, "bad argument");
+    const int A = e->cfg.numArenas, P = e->cfg.numCars;
+    if (!ids) n = A;
+    if (n == 0) return RLG_OK;
+    if (ids) for (int i = 0; i < n; i++) if (ids[i] < 0 || ids[i] >= A) return fail(RLG_ERR_INVALID, "arena id out of range");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t s = e->stream, c = e->copyStream;
+    if (!e->xCars) {  // staging for every arena, once
+        CK(cudaMalloc(&e->xIds, (size_t)A * 4));
+        CK(cudaMalloc(&e->xCars, (size_t)A * P * sizeof(rlg_car_state)));
+        CK(cudaMalloc(&e->xBalls, (size_t)A * sizeof(rlg_ball_state)));
+        CK(cudaMalloc(&e->xGym, (size_t)A * sizeof(rlg_gym_state)));
+        CK(cudaMalloc(&e->xPlayers, (size_t)A * P * sizeof(rlg_gym_player)));
+        CK(cudaEventCreateWithFlags(&e->evExport, cudaEventDisableTiming));
+        e->xCap = A;
+    }
+    if (n > e->xCap) return fail(RLG_ERR_INVALID, "more arena ids than arenas");
+    CK(cudaStreamSynchronize(c));  // the previous export's copies have left the staging buffers
+    if (ids) CK(cudaMemcpyAsync(e->xIds, ids, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    k_export_gamestates<<<grid_for(n, 64), 64, 0, s>>>(e->state, e->cfg, e->nwords, e->tables, ids ? e->xIds : nullptr, n, cars ? e->xCars : nullptr,
+                                                      balls ? e->xBalls : nullptr, gym ? e->xGym : nullptr, players ? e->xPlayers : nullptr);
+    e->launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e->evExport, s));
+    CK(cudaStreamWaitEvent(c, e->evExport, 0));
+    if (cars) CK(cudaMemcpyAsync(cars, e->xCars, (size_t)n * P * sizeof(rlg_car_state), cudaMemcpyDeviceToHost, c));
+    if (balls) CK(cudaMemcpyAsync(balls, e->xBalls, (size_t)n * sizeof(rlg_ball_state), cudaMemcpyDeviceToHost, c));
+    if (gym) CK(cudaMemcpyAsync(gym, e->xGym, (size_t)n * sizeof(rlg_gym_state), cudaMemcpyDeviceToHost, c));
+    if (players) CK(cudaMemcpyAsync(players, e->xPlayers, (size_t)n * P * sizeof(rlg_gym_player), cudaMemcpyDeviceToHost, c));
+    return RLG_OK;
+}
+int rlg_engine_export_wait(rlg_engine* e) {
+    if (!e) return fail(RLG_ERR_INVALID, "null engine");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->copyStream));
+    return RLG_OK;
+}
+int rlg_engine_export_gamestates(rlg_engine* e, const int32_t* ids, int n, rlg_car_state* cars, rlg_ball_state* balls, rlg_gym_state* gym,
+                                 rlg_gym_player* players) {
+    int rc = rlg_engine_export_gamestates_async(e, ids, n, cars, balls, gym, players);
+    return rc != RLG_OK ? rc : rlg_engine_export_wait(e);
+}
+// Gym::Reset through the engine's own state setter with the obs rows written into a caller DEVICE buffer [A*P, obs]
+int rlg_engine_reset_to(rlg_engine* e, const uint8_t* mask_host, float* obs_out, void* stream) { return do_reset(e, mask_host, stream, 1, obs_out); }
+// page-locked host memory for the buffers above (plain malloc'ed memory works too, just slower)
+void* rlg_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void rlg_host_free(void* p) { if (p) cudaFreeHost(p); }
+void* rlg_device_alloc(rlg_engine* e, size_t bytes) {
+    if (!e) { fail(RLG_ERR_INVALID, "null engine"); return nullptr; }
+    void* p = nullptr;
+    cudaError_t err = cudaSetDevice(e->device);
+    if (err == cudaSuccess) err = cudaMalloc(&p, bytes ? bytes : 1);
+    if (err != cudaSuccess) { fail(RLG_ERR_CUDA, std::string("rlg_device_alloc: ") + cudaGetErrorString(err)); return nullptr; }
+    return p;
+}
+void rlg_device_free(rlg_engine* e, void* p) {
+    if (!p) return;
+    if (e) cudaSetDevice(e->device);
+    cudaFree(p);
+}
+void rlg_set_last_error(const char* msg) { g_last_error = msg ? msg : ""; }
+size_t rlg_sizeof_gym_state(void) { return sizeof(rlg_gym_state); }
+size_t rlg_sizeof_gym_player(void) { return sizeof(rlg_gym_player); }
 
 int rlg_engine_copy_to_host(rlg_engine* e, void* dst_host, const void* src_dev, size_t bytes) {
     if (!e || (bytes && (!dst_host || !src_dev))) return fail(RLG_ERR_INVALID, "null argument");
