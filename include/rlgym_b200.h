@@ -441,6 +441,11 @@ int rlg_collector_set_reset_hook(rlg_collector* c, rlg_reset_hook hook, void* us
  * (writing their post-reset obs into obs_next).  Replaces GameInst::Step's body for that configuration (GameInst.cpp:7-38). */
 typedef int (*rlg_step_hook)(void* user, int t, const int32_t* actions_dev, float* obs_next_dev, float* reward_dev, uint8_t* done_dev);
 int rlg_collector_set_step_hook(rlg_collector* c, rlg_step_hook hook, void* user);
+/* A trajectory collected elsewhere (HOST arrays in the ring's T-major layout: obs [T+1][N][obs], action [T][N] i32, logprob / reward
+ * [T][N], done [T][A] u8, value [T+1][N]) becomes the collector's last collect, so that rlg_collector_gae / _return_stats / _export
+ * and rlg_ppo_submit_collector work on it (e.g. timesteps gathered by CPU RLGymSim gyms next to the device pool). */
+int rlg_collector_load_external(rlg_collector* c, int n_steps, const float* obs_host, const int32_t* action_host, const float* logprob_host,
+                                const float* reward_host, const uint8_t* done_host, const float* value_host);
 uint64_t rlg_collector_launch_count(const rlg_collector* c);
 /* Per-kernel CUDA-event timing of the LAST collect on its launching stream (bench roofline): summed durations and launch
  * counts of the fused Gym::Step kernel and of the MLP inference kernel. Replaces ThreadAgent::Times

@@ -661,6 +661,81 @@ void ref_bench_destroy(void* h) {
     delete b;
 }
 
+// ---- policy-driven collection for the learning-curve A/B (tools/learning_curves.py): persistent worker threads, one call steps every
+// gym once with the caller's actions, GameInst::Step semantics (GameInst.cpp:7-38: a finished gym is reset and hands back the reset obs)
+struct RefPool {
+    std::vector<std::vector<RefGym*>> gyms;
+    std::vector<std::thread> workers;
+    int P = 0, obs = 0, G = 0;
+    std::atomic<uint64_t> generation{0};
+    std::atomic<int> finished{0};
+    std::atomic<bool> quit{false};
+    const int32_t* actions = nullptr; float* obsOut = nullptr; float* rewOut = nullptr; uint8_t* doneOut = nullptr;
+    int mode = 0;  // 0 = step, 1 = reset all + obs
+};
+static void pool_worker(RefPool* b, int t, uint32_t seed) {
+    RocketSim::Math::GetRandEngine().seed(seed + 977 * t);
+    uint64_t seen = 0;
+    const int perThread = (int)b->gyms[t].size();
+    while (true) {
+        while (b->generation.load(std::memory_order_acquire) == seen) { if (b->quit.load()) return; std::this_thread::yield(); }
+        seen = b->generation.load(std::memory_order_acquire);
+        int base = 0;
+        for (int k = 0; k < t; k++) base += (int)b->gyms[k].size();
+        for (int i = 0; i < perThread; i++) {
+            RefGym* g = b->gyms[t][i];
+            const int gi = base + i;
+            float* o = b->obsOut + (size_t)gi * b->P * b->obs;
+            if (b->mode == 1) { flatten_obs(g->gym->Reset(), o); continue; }
+            IList acts(b->actions + (size_t)gi * b->P, b->actions + (size_t)(gi + 1) * b->P);
+            auto r = g->gym->Step(acts);
+            for (int p = 0; p < b->P; p++) b->rewOut[(size_t)gi * b->P + p] = r.reward[p];
+            b->doneOut[gi] = r.done;
+            if (r.done) flatten_obs(g->gym->Reset(), o); else flatten_obs(r.obs, o);
+        }
+        b->finished.fetch_add(1, std::memory_order_release);
+    }
+}
+void* ref_pool_create(const rlg_engine_cfg* cfg, int num_threads, int gyms_per_thread, uint32_t seed) {
+    RefPool* b = new RefPool();
+    b->gyms.resize(num_threads);
+    {
+        std::vector<std::thread> ths;
+        for (int t = 0; t < num_threads; t++)
+            ths.emplace_back([&, t] {
+                RocketSim::Math::GetRandEngine().seed(seed + 977 * t);
+                for (int i = 0; i < gyms_per_thread; i++) b->gyms[t].push_back(make_gym(cfg));
+            });
+        for (auto& th : ths) th.join();
+    }
+    b->P = b->gyms[0][0]->match->playerAmount;
+    b->G = num_threads * gyms_per_thread;
+    std::vector<float> tmp(4096);
+    b->obs = flatten_obs(b->gyms[0][0]->gym->Reset(), tmp.data()) ;
+    for (int t = 0; t < num_threads; t++) b->workers.emplace_back(pool_worker, b, t, seed + 13);
+    return b;
+}
+int ref_pool_obs_size(void* h) { return ((RefPool*)h)->obs; }
+static void pool_run(RefPool* b, int mode) {
+    b->mode = mode;
+    b->finished.store(0);
+    b->generation.fetch_add(1, std::memory_order_release);
+    while (b->finished.load(std::memory_order_acquire) < (int)b->workers.size()) std::this_thread::yield();
+}
+void ref_pool_reset(void* h, float* obs_out) { RefPool* b = (RefPool*)h; b->obsOut = obs_out; pool_run(b, 1); }
+void ref_pool_step(void* h, const int32_t* actions, float* obs_out, float* rew_out, uint8_t* done_out) {
+    RefPool* b = (RefPool*)h;
+    b->actions = actions; b->obsOut = obs_out; b->rewOut = rew_out; b->doneOut = done_out;
+    pool_run(b, 0);
+}
+void ref_pool_destroy(void* h) {
+    RefPool* b = (RefPool*)h;
+    b->quit = true;
+    for (auto& th : b->workers) th.join();
+    for (auto& v : b->gyms) for (auto g : v) delete g;
+    delete b;
+}
+
 size_t ref_sizeof_car_state() { return sizeof(rlg_car_state); }
 
 } // extern "C"

@@ -189,6 +189,36 @@ def bench_collect(cfg: abi.EngineCfg, num_threads: int, gyms_per_thread: int, wa
                                          C.c_uint32(seed_)))
 
 
+class RefPool:
+    """Persistent worker threads stepping T x G reference gyms with the caller's actions (GameInst::Step semantics)."""
+
+    def __init__(self, cfg: abi.EngineCfg, num_threads: int, gyms_per_thread: int, seed_: int = 1):
+        self.L = lib()
+        self.L.ref_pool_create.restype = C.c_void_p
+        self.h = C.c_void_p(self.L.ref_pool_create(C.byref(cfg), num_threads, gyms_per_thread, C.c_uint32(seed_)))
+        self.G = num_threads * gyms_per_thread
+        self.P = abi.num_players(cfg)
+        self.obs_size = int(self.L.ref_pool_obs_size(self.h))
+        self.obs = np.zeros((self.G * self.P, self.obs_size), dtype=np.float32)
+        self.rew = np.zeros(self.G * self.P, dtype=np.float32)
+        self.done = np.zeros(self.G, dtype=np.uint8)
+
+    def reset(self) -> np.ndarray:
+        self.L.ref_pool_reset(self.h, self.obs.ctypes.data_as(C.c_void_p))
+        return self.obs
+
+    def step(self, actions: np.ndarray):
+        a = np.ascontiguousarray(actions, dtype=np.int32)
+        self.L.ref_pool_step(self.h, a.ctypes.data_as(C.c_void_p), self.obs.ctypes.data_as(C.c_void_p), self.rew.ctypes.data_as(C.c_void_p),
+                             self.done.ctypes.data_as(C.c_void_p))
+        return self.obs, self.rew, self.done
+
+    def close(self):
+        if self.h:
+            self.L.ref_pool_destroy(self.h)
+            self.h = None
+
+
 class RefBench:
     """Persistent multithreaded reference collection loop (Gym::Step + auto-reset, random actions)."""
 

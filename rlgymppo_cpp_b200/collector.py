@@ -194,6 +194,15 @@ class Collector:
         _check(self.L.rlg_collector_set_layer_device(self.h, net, layer, C.c_void_p(w_ptr), ldw, C.c_void_p(b_ptr), out_dim, in_dim,
                                                      C.c_void_p(stream) if stream else None))
 
+    def load_external(self, obs, action, logprob, reward, done, value):
+        """A trajectory collected elsewhere (host arrays, T-major like the ring) becomes the last collect (rlg_collector_load_external)."""
+        T = action.shape[0]
+        arrs = [np.ascontiguousarray(obs, np.float32), np.ascontiguousarray(action, np.int32), np.ascontiguousarray(logprob, np.float32),
+                np.ascontiguousarray(reward, np.float32), np.ascontiguousarray(done, np.uint8), np.ascontiguousarray(value, np.float32)]
+        N, A = self.engine.A * self.engine.P, self.engine.A
+        assert arrs[0].shape == (T + 1, N, self.engine.obs_size) and arrs[4].shape == (T, A) and arrs[5].shape == (T + 1, N)
+        _check(self.L.rlg_collector_load_external(self.h, T, *[a.ctypes.data_as(C.c_void_p) for a in arrs]))
+
     def enable_timing(self, on=True):
         _check(self.L.rlg_collector_enable_timing(self.h, int(on)))
 

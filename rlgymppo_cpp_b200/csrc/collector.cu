@@ -735,6 +735,28 @@ int rlg_collector_set_reset_hook(rlg_collector* c, rlg_reset_hook hook, void* us
     return RLG_OK;
 }
 
+// A trajectory collected elsewhere (host arrays, T-major like the ring) becomes the collector's "last collect": GAE, return
+// statistics, export and the learner hand-over then work on it as on its own.  obs [T+1][N][obs], action [T][N] i32,
+// logprob / reward [T][N], done [T][A] u8, value [T+1][N].
+int rlg_collector_load_external(rlg_collector* c, int n_steps, const float* obs_host, const int32_t* action_host, const float* logprob_host,
+                                const float* reward_host, const uint8_t* done_host, const float* value_host) {
+    if (!c || !obs_host || !action_host || !logprob_host || !reward_host || !done_host || !value_host) return failc(RLG_ERR_INVALID, "null argument");
+    if (n_steps < 1 || n_steps > c->maxT) return failc(RLG_ERR_INVALID, "n_steps must be in [1, max_steps]");
+    CKC(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)rlg_engine_stream(c->e);
+    const size_t T = n_steps, N = c->N;
+    CKC(cudaMemcpyAsync(c->dObs, obs_host, (T + 1) * N * c->obs * 4, cudaMemcpyHostToDevice, s));
+    CKC(cudaMemcpyAsync(c->dAction, action_host, T * N * 4, cudaMemcpyHostToDevice, s));
+    CKC(cudaMemcpyAsync(c->dLogprob, logprob_host, T * N * 4, cudaMemcpyHostToDevice, s));
+    CKC(cudaMemcpyAsync(c->dReward, reward_host, T * N * 4, cudaMemcpyHostToDevice, s));
+    CKC(cudaMemcpyAsync(c->dDone, done_host, T * c->A, cudaMemcpyHostToDevice, s));
+    CKC(cudaMemcpyAsync(c->dValue, value_host, (T + 1) * N * 4, cudaMemcpyHostToDevice, s));
+    CKC(cudaStreamSynchronize(s));
+    c->T = n_steps;
+    c->haveObs0 = true;
+    return RLG_OK;
+}
+
 int rlg_collector_set_step_hook(rlg_collector* c, rlg_step_hook hook, void* user) {
     if (!c) return failc(RLG_ERR_INVALID, "null collector");
     c->stepHook = hook; c->stepUser = user;

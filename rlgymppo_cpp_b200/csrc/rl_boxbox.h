@@ -103,215 +103,227 @@ RL_HD RL_NOINLINE inline void adjust_internal_edge(Contact& cp, const MeshSet& m
     }
 }
 
-// ---- btBoxBoxDetector (ODE dBoxBox2; B/BulletCollision/CollisionDispatch/btBoxBoxDetector.cpp:260-720) ----------
-// 15-axis separating-axis search (edge axes handicapped by fudge 1.05), then either one edge-edge point or the
-// incident face clipped against the reference face, culled to at most 4 points.  Contacts only when the full
-// (with-margin) boxes interpenetrate.  out.normal is normalWorldOnB (from box B towards box A), points lie on B.
-RL_HD inline int bb_clip_rect_quad(const float h[2], const float p[8], float ret[16]) {
-    int nq = 4, nr = 0;
-    float buffer[16];
-    const float* q = p;
-    float* r = ret;
-    for (int dir = 0; dir <= 1; dir++) {
-        for (int sign = -1; sign <= 1; sign += 2) {
-            const float* pq = q;
-            float* pr = r;
-            nr = 0;
-            for (int i = nq; i > 0; i--) {
-                if (sign * pq[dir] < h[dir]) {
-                    pr[0] = pq[0]; pr[1] = pq[1]; pr += 2; nr++;
-                    if (nr & 8) { q = r; goto done; }
-                }
-                const float* nextq = (i > 1) ? pq + 2 : q;
-                if ((sign * pq[dir] < h[dir]) ^ (sign * nextq[dir] < h[dir])) {
-                    pr[1 - dir] = pq[1 - dir] + (nextq[1 - dir] - pq[1 - dir]) / (nextq[dir] - pq[dir]) * (sign * h[dir] - pq[dir]);
-                    pr[dir] = sign * h[dir];
-                    pr += 2; nr++;
-                    if (nr & 8) { q = r; goto done; }
-                }
-                pq += 2;
-            }
-            q = r;
-            r = (q == ret) ? buffer : ret;
-            nq = nr;
+// ---- box vs box ------------------------------------------------------------------------------------------------------------------
+// Contact manifold of two oriented boxes with the decisions of Bullet's btBoxBoxDetector
+// (B/BulletCollision/CollisionDispatch/btBoxBoxDetector.cpp:260-720) so that car-car contacts reproduce the reference:
+//   1. separating-axis search over the 3 + 3 face normals and the 9 edge-pair cross products, in that order; an edge axis only
+//      wins when its (normalised) overlap beats the best face overlap by more than 5 % (kEdgeHandicap), and the edge tests use
+//      |R| + 1e-5 so that near-parallel edges never produce a spurious axis;
+//   2. an edge axis gives ONE point: the closest point of B's edge to A's edge;
+//   3. a face axis gives the incident face of the other box clipped to the reference face's rectangle (at most 8 vertices), the
+//      vertices below the reference face kept, and when more than 4 remain the deepest one plus the three nearest to evenly
+//      spaced directions around the polygon's centroid.
+// Written for one lane per car pair: the axis loops are index arithmetic over (i, j), the clipping works on a small P2 polygon
+// in registers / local memory.  out.normal points from box B towards box A, the points lie on B, depths are negative.
+struct P2 { float u, v; RL_HDI float get(int k) const { return k ? v : u; } RL_HDI void set(int k, float x) { if (k) v = x; else u = x; } };
+
+// One pass of polygon clipping against the half-plane  side * coord[k] < limit.  The output is cut off at 8 vertices (the caller
+// then stops clipping altogether, like the reference does).  Returns the vertex count; `full` tells that the cut-off happened.
+RL_HD inline int clip_against_halfplane(const P2* in, int nIn, P2* outPoly, int k, float side, float limit, bool& full) {
+    int nOut = 0;
+    full = false;
+    for (int i = 0; i < nIn; i++) {
+        const P2 cur = in[i], nxt = in[(i + 1 == nIn) ? 0 : i + 1];
+        const bool curIn = side * cur.get(k) < limit, nxtIn = side * nxt.get(k) < limit;
+        if (curIn) {
+            outPoly[nOut++] = cur;
+            if (nOut == 8) { full = true; return nOut; }
+        }
+        if (curIn != nxtIn) {  // the edge crosses the boundary: its intersection with coord[k] = side * limit
+            P2 x;
+            x.set(1 - k, cur.get(1 - k) + (nxt.get(1 - k) - cur.get(1 - k)) / (nxt.get(k) - cur.get(k)) * (side * limit - cur.get(k)));
+            x.set(k, side * limit);
+            outPoly[nOut++] = x;
+            if (nOut == 8) { full = true; return nOut; }
         }
     }
-done:
-    if (q != ret) for (int i = 0; i < nr * 2; i++) ret[i] = q[i];
-    return nr;
+    return nOut;
 }
 
-RL_HD inline void bb_cull_points(int n, const float* p, int m, int i0, int* iret) {
-    const float PI_ = 3.14159265f;
-    float a, cx, cy, q;
-    if (n == 1) { cx = p[0]; cy = p[1]; }
-    else if (n == 2) { cx = 0.5f * (p[0] + p[2]); cy = 0.5f * (p[1] + p[3]); }
-    else {
-        a = 0; cx = 0; cy = 0;
-        for (int i = 0; i < (n - 1); i++) {
-            q = p[i * 2] * p[i * 2 + 3] - p[i * 2 + 2] * p[i * 2 + 1];
-            a += q; cx += q * (p[i * 2] + p[i * 2 + 2]); cy += q * (p[i * 2 + 1] + p[i * 2 + 3]);
-        }
-        q = p[n * 2 - 2] * p[1] - p[0] * p[n * 2 - 1];
-        if (fabsf(a + q) > kEps) a = 1.f / (3.0f * (a + q)); else a = 1e18f;
-        cx = a * (cx + q * (p[n * 2 - 2] + p[0]));
-        cy = a * (cy + q * (p[n * 2 - 1] + p[1]));
+// quad (4 vertices) clipped to the rectangle |u| < hu, |v| < hv: -u, +u, -v, +v in turn
+RL_HD inline int clip_quad_to_rect(float hu, float hv, const P2 quad[4], P2 result[8]) {
+    P2 bufA[8], bufB[8];
+    const P2* src = quad;
+    int n = 4;
+    P2* dst = bufA;
+    for (int pass = 0; pass < 4; pass++) {
+        const int k = pass >> 1;
+        const float side = (pass & 1) ? 1.f : -1.f;
+        bool full;
+        n = clip_against_halfplane(src, n, dst, k, side, k ? hv : hu, full);
+        src = dst;
+        dst = (dst == bufA) ? bufB : bufA;
+        if (full) break;
     }
-    float A[8];
-    int avail[8];
-    for (int i = 0; i < n; i++) { A[i] = rl_atan2(p[i * 2 + 1] - cy, p[i * 2] - cx); avail[i] = 1; }
-    avail[i0] = 0;
-    iret[0] = i0;
-    iret++;
-    for (int j = 1; j < m; j++) {
-        a = (float)j * (2 * PI_ / m) + A[i0];
-        if (a > PI_) a -= 2 * PI_;
-        float maxdiff = 1e9f, diff;
-        *iret = i0;
+    for (int i = 0; i < n; i++) result[i] = src[i];
+    return n;
+}
+
+// Picks `want` of the n polygon vertices: `first` and then, for each of the remaining evenly spaced directions around the
+// centroid (starting at `first`'s direction), the unused vertex whose direction is nearest.
+RL_HD inline void pick_spread_vertices(int n, const P2* poly, int want, int first, int* chosen) {
+    const float kPi_ = 3.14159265f;
+    float cu, cv;
+    if (n == 1) { cu = poly[0].u; cv = poly[0].v; }
+    else if (n == 2) { cu = 0.5f * (poly[0].u + poly[1].u); cv = 0.5f * (poly[0].v + poly[1].v); }
+    else {  // area-weighted centroid of the polygon (shoelace terms; the closing edge last)
+        float area = 0, su = 0, sv = 0;
+        for (int i = 0; i + 1 < n; i++) {
+            const float w = poly[i].u * poly[i + 1].v - poly[i + 1].u * poly[i].v;
+            area += w; su += w * (poly[i].u + poly[i + 1].u); sv += w * (poly[i].v + poly[i + 1].v);
+        }
+        const float w = poly[n - 1].u * poly[0].v - poly[0].u * poly[n - 1].v;
+        const float scale = fabsf(area + w) > kEps ? 1.f / (3.0f * (area + w)) : 1e18f;
+        cu = scale * (su + w * (poly[n - 1].u + poly[0].u));
+        cv = scale * (sv + w * (poly[n - 1].v + poly[0].v));
+    }
+    float dir[8];
+    unsigned freeMask = 0;
+    for (int i = 0; i < n; i++) { dir[i] = rl_atan2(poly[i].v - cv, poly[i].u - cu); freeMask |= 1u << i; }
+    freeMask &= ~(1u << first);
+    chosen[0] = first;
+    for (int j = 1; j < want; j++) {
+        float target = (float)j * (2 * kPi_ / want) + dir[first];
+        if (target > kPi_) target -= 2 * kPi_;
+        int best = first;
+        float bestGap = 1e9f;
         for (int i = 0; i < n; i++) {
-            if (avail[i]) {
-                diff = fabsf(A[i] - a);
-                if (diff > PI_) diff = 2 * PI_ - diff;
-                if (diff < maxdiff) { maxdiff = diff; *iret = i; }
-            }
+            if (!((freeMask >> i) & 1u)) continue;
+            float gap = fabsf(dir[i] - target);
+            if (gap > kPi_) gap = 2 * kPi_ - gap;
+            if (gap < bestGap) { bestGap = gap; best = i; }
         }
-        avail[*iret] = 0;
-        iret++;
+        freeMask &= ~(1u << best);
+        chosen[j] = best;
     }
 }
 
-RL_HD RL_NOINLINE inline void box_box(V3 p1, const M3& R1, V3 A, V3 p2, const M3& R2, V3 B, BoxBoxResult& out) {
+RL_HD RL_NOINLINE inline void box_box(V3 ca, const M3& ra, V3 ha, V3 cb, const M3& rb, V3 hb, BoxBoxResult& out) {
     out.n = 0;
-    const float fudge_factor = 1.05f;
-    V3 p = p2 - p1;
-    V3 pp = tmul(p, R1);
-    float R[3][3], Q[3][3];
-    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { R[i][j] = dot(R1.col(i), R2.col(j)); Q[i][j] = fabsf(R[i][j]); }
-    float s = -3.402823466e+38f, s2, l;
-    int invert_normal = 0, code = 0;
-    int normalRBox = 0, normalRCol = 0;  // which box / column the best face axis comes from
-    bool normalIsFace = false;
-    V3 normalC(0, 0, 0);
-#define RL_TST_FACE(expr1, expr2, box, col, cc) \
-    s2 = fabsf(expr1) - (expr2);                \
-    if (s2 > 0) return;                         \
-    if (s2 > s) { s = s2; normalIsFace = true; normalRBox = box; normalRCol = col; invert_normal = ((expr1) < 0); code = (cc); }
-    RL_TST_FACE(pp[0], (A[0] + B[0] * Q[0][0] + B[1] * Q[0][1] + B[2] * Q[0][2]), 1, 0, 1);
-    RL_TST_FACE(pp[1], (A[1] + B[0] * Q[1][0] + B[1] * Q[1][1] + B[2] * Q[1][2]), 1, 1, 2);
-    RL_TST_FACE(pp[2], (A[2] + B[0] * Q[2][0] + B[1] * Q[2][1] + B[2] * Q[2][2]), 1, 2, 3);
-    RL_TST_FACE(dot(R2.col(0), p), (A[0] * Q[0][0] + A[1] * Q[1][0] + A[2] * Q[2][0] + B[0]), 2, 0, 4);
-    RL_TST_FACE(dot(R2.col(1), p), (A[0] * Q[0][1] + A[1] * Q[1][1] + A[2] * Q[2][1] + B[1]), 2, 1, 5);
-    RL_TST_FACE(dot(R2.col(2), p), (A[0] * Q[0][2] + A[1] * Q[1][2] + A[2] * Q[2][2] + B[2]), 2, 2, 6);
-#undef RL_TST_FACE
-#define RL_TST_EDGE(expr1, expr2, n1, n2, n3, cc)          \
-    s2 = fabsf(expr1) - (expr2);                           \
-    if (s2 > kEps) return;                                 \
-    l = sqrtf((n1) * (n1) + (n2) * (n2) + (n3) * (n3));    \
-    if (l > kEps) {                                        \
-        s2 /= l;                                           \
-        if (s2 * fudge_factor > s) { s = s2; normalIsFace = false; normalC = V3((n1) / l, (n2) / l, (n3) / l); invert_normal = ((expr1) < 0); code = (cc); } \
+    const float kEdgeHandicap = 1.05f, kParallelPad = 1.0e-5f;
+    const V3 d = cb - ca;          // centre offset, world
+    const V3 dA = tmul(d, ra);     // ... in A's frame
+    float R[3][3], Q[3][3];        // R[i][j] = a_i . b_j, Q = |R|
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { R[i][j] = dot(ra.col(i), rb.col(j)); Q[i][j] = fabsf(R[i][j]); }
+
+    // ---- 1. separating-axis search: code 1..3 = A's faces, 4..6 = B's faces, 7 + 3 i + j = edge a_i x b_j
+    float best = -3.402823466e+38f;
+    int code = 0;
+    bool flip = false;
+    V3 edgeAxisA(0, 0, 0);  // winning edge axis in A's frame (unit)
+    for (int i = 0; i < 3; i++) {  // faces of A
+        const float dist = dA[i], reach = ha[i] + hb[0] * Q[i][0] + hb[1] * Q[i][1] + hb[2] * Q[i][2];
+        const float sep = fabsf(dist) - reach;
+        if (sep > 0) return;
+        if (sep > best) { best = sep; code = 1 + i; flip = dist < 0; }
     }
-    const float fudge2 = 1.0e-5f;
-    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Q[i][j] += fudge2;
-    RL_TST_EDGE(pp[2] * R[1][0] - pp[1] * R[2][0], (A[1] * Q[2][0] + A[2] * Q[1][0] + B[1] * Q[0][2] + B[2] * Q[0][1]), 0.f, -R[2][0], R[1][0], 7);
-    RL_TST_EDGE(pp[2] * R[1][1] - pp[1] * R[2][1], (A[1] * Q[2][1] + A[2] * Q[1][1] + B[0] * Q[0][2] + B[2] * Q[0][0]), 0.f, -R[2][1], R[1][1], 8);
-    RL_TST_EDGE(pp[2] * R[1][2] - pp[1] * R[2][2], (A[1] * Q[2][2] + A[2] * Q[1][2] + B[0] * Q[0][1] + B[1] * Q[0][0]), 0.f, -R[2][2], R[1][2], 9);
-    RL_TST_EDGE(pp[0] * R[2][0] - pp[2] * R[0][0], (A[0] * Q[2][0] + A[2] * Q[0][0] + B[1] * Q[1][2] + B[2] * Q[1][1]), R[2][0], 0.f, -R[0][0], 10);
-    RL_TST_EDGE(pp[0] * R[2][1] - pp[2] * R[0][1], (A[0] * Q[2][1] + A[2] * Q[0][1] + B[0] * Q[1][2] + B[2] * Q[1][0]), R[2][1], 0.f, -R[0][1], 11);
-    RL_TST_EDGE(pp[0] * R[2][2] - pp[2] * R[0][2], (A[0] * Q[2][2] + A[2] * Q[0][2] + B[0] * Q[1][1] + B[1] * Q[1][0]), R[2][2], 0.f, -R[0][2], 12);
-    RL_TST_EDGE(pp[1] * R[0][0] - pp[0] * R[1][0], (A[0] * Q[1][0] + A[1] * Q[0][0] + B[1] * Q[2][2] + B[2] * Q[2][1]), -R[1][0], R[0][0], 0.f, 13);
-    RL_TST_EDGE(pp[1] * R[0][1] - pp[0] * R[1][1], (A[0] * Q[1][1] + A[1] * Q[0][1] + B[0] * Q[2][2] + B[2] * Q[2][0]), -R[1][1], R[0][1], 0.f, 14);
-    RL_TST_EDGE(pp[1] * R[0][2] - pp[0] * R[1][2], (A[0] * Q[1][2] + A[1] * Q[0][2] + B[0] * Q[2][1] + B[1] * Q[2][0]), -R[1][2], R[0][2], 0.f, 15);
-#undef RL_TST_EDGE
+    for (int j = 0; j < 3; j++) {  // faces of B
+        const float dist = dot(rb.col(j), d), reach = ha[0] * Q[0][j] + ha[1] * Q[1][j] + ha[2] * Q[2][j] + hb[j];
+        const float sep = fabsf(dist) - reach;
+        if (sep > 0) return;
+        if (sep > best) { best = sep; code = 4 + j; flip = dist < 0; }
+    }
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Q[i][j] += kParallelPad;
+    for (int i = 0; i < 3; i++) {
+        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;          // a_i x b_j has no component along a_i
+        const int il = i == 0 ? 1 : 0, ih = i == 2 ? 1 : 2;    // the other two axes of A, ascending
+        for (int j = 0; j < 3; j++) {
+            const int jl = j == 0 ? 1 : 0, jh = j == 2 ? 1 : 2;
+            const float dist = dA[i2] * R[i1][j] - dA[i1] * R[i2][j];
+            const float reach = ha[il] * Q[ih][j] + ha[ih] * Q[il][j] + hb[jl] * Q[i][jh] + hb[jh] * Q[i][jl];
+            float sep = fabsf(dist) - reach;
+            if (sep > kEps) return;
+            V3 n(0, 0, 0);
+            n[i1] = -R[i2][j]; n[i2] = R[i1][j];
+            const float nl = sqrtf(n.x * n.x + n.y * n.y + n.z * n.z);
+            if (nl > kEps) {
+                sep /= nl;
+                if (sep * kEdgeHandicap > best) { best = sep; code = 7 + 3 * i + j; flip = dist < 0; edgeAxisA = V3(n.x / nl, n.y / nl, n.z / nl); }
+            }
+        }
+    }
     if (!code) return;
-    V3 normal;
-    if (normalIsFace) normal = (normalRBox == 1 ? R1 : R2).col(normalRCol);
-    else normal = R1 * normalC;
-    if (invert_normal) normal = -normal;
-    float depth = -s;
-    out.normal = -normal;
+    V3 axis = code <= 3 ? ra.col(code - 1) : (code <= 6 ? rb.col(code - 4) : ra * edgeAxisA);  // from A towards B
+    if (flip) axis = -axis;
+    const float overlap = -best;
+    out.normal = -axis;
+
+    // ---- 2. edge-edge: one point, on B's edge
     if (code > 6) {
-        V3 pa = p1;
-        for (int j = 0; j < 3; j++) { float sign = (dot(normal, R1.col(j)) > 0) ? 1.f : -1.f; pa += R1.col(j) * (sign * A[j]); }
-        V3 pb = p2;
-        for (int j = 0; j < 3; j++) { float sign = (dot(normal, R2.col(j)) > 0) ? -1.f : 1.f; pb += R2.col(j) * (sign * B[j]); }
-        V3 ua = R1.col((code - 7) / 3), ub = R2.col((code - 7) % 3);
-        // dLineClosestApproach
-        V3 dpp = pb - pa;
-        float uaub = dot(ua, ub), q1 = dot(ua, dpp), q2 = -dot(ub, dpp);
-        float d = 1 - uaub * uaub, alpha, beta;
-        if (d <= 0.0001f) { alpha = 0; beta = 0; }
-        else { d = 1.f / d; alpha = (q1 + uaub * q2) * d; beta = (uaub * q1 + q2) * d; }
-        (void)alpha;
-        pb += ub * beta;
-        out.point[0] = pb; out.depth[0] = -depth; out.n = 1;
+        V3 onA = ca, onB = cb;  // the supporting vertices along the axis
+        for (int k = 0; k < 3; k++) onA += ra.col(k) * ((dot(axis, ra.col(k)) > 0 ? 1.f : -1.f) * ha[k]);
+        for (int k = 0; k < 3; k++) onB += rb.col(k) * ((dot(axis, rb.col(k)) > 0 ? -1.f : 1.f) * hb[k]);
+        const V3 ea = ra.col((code - 7) / 3), eb = rb.col((code - 7) % 3);
+        const V3 gap = onB - onA;
+        const float cosAB = dot(ea, eb), alongA = dot(ea, gap), alongB = -dot(eb, gap);
+        float denom = 1 - cosAB * cosAB, tB = 0;
+        if (denom > 0.0001f) { denom = 1.f / denom; tB = (cosAB * alongA + alongB) * denom; }
+        out.point[0] = onB + eb * tB; out.depth[0] = -overlap; out.n = 1;
         return;
     }
-    const M3 &Ra = code <= 3 ? R1 : R2, &Rb = code <= 3 ? R2 : R1;
-    V3 pa = code <= 3 ? p1 : p2, pb = code <= 3 ? p2 : p1;
-    V3 Sa = code <= 3 ? A : B, Sb = code <= 3 ? B : A;
-    V3 normal2 = code <= 3 ? normal : -normal;
-    V3 nr = tmul(normal2, Rb);
-    V3 anr = vabs(nr);
-    int lanr, a1, a2;
-    if (anr[1] > anr[0]) {
-        if (anr[1] > anr[2]) { a1 = 0; lanr = 1; a2 = 2; } else { a1 = 0; a2 = 1; lanr = 2; }
+
+    // ---- 3. face contact: the reference face belongs to the box that owns the axis, the incident face to the other box
+    const bool refIsA = code <= 3;
+    const M3 &Rr = refIsA ? ra : rb, &Ri = refIsA ? rb : ra;
+    const V3 cr = refIsA ? ca : cb, ci = refIsA ? cb : ca;
+    const V3 hr = refIsA ? ha : hb, hi = refIsA ? hb : ha;
+    const V3 outward = refIsA ? axis : -axis;      // reference face normal, pointing at the incident box
+    const V3 inInc = tmul(outward, Ri);            // ... in the incident box's frame
+    const V3 mag = vabs(inInc);
+    int face, s1, s2;  // incident face axis = the most anti-parallel one; s1 < s2 span the face
+    if (mag[1] > mag[0]) {
+        if (mag[1] > mag[2]) { face = 1; s1 = 0; s2 = 2; } else { face = 2; s1 = 0; s2 = 1; }
     } else {
-        if (anr[0] > anr[2]) { lanr = 0; a1 = 1; a2 = 2; } else { a1 = 0; a2 = 1; lanr = 2; }
+        if (mag[0] > mag[2]) { face = 0; s1 = 1; s2 = 2; } else { face = 2; s1 = 0; s2 = 1; }
     }
-    V3 center;
-    if (nr[lanr] < 0) center = pb - pa + Rb.col(lanr) * Sb[lanr];
-    else center = pb - pa - Rb.col(lanr) * Sb[lanr];
-    int codeN = code <= 3 ? code - 1 : code - 4, code1, code2;
-    if (codeN == 0) { code1 = 1; code2 = 2; } else if (codeN == 1) { code1 = 0; code2 = 2; } else { code1 = 0; code2 = 1; }
-    float quad[8];
-    float c1 = dot(center, Ra.col(code1)), c2 = dot(center, Ra.col(code2));
-    float m11 = dot(Ra.col(code1), Rb.col(a1)), m12 = dot(Ra.col(code1), Rb.col(a2));
-    float m21 = dot(Ra.col(code2), Rb.col(a1)), m22 = dot(Ra.col(code2), Rb.col(a2));
+    V3 centre = ci - cr;  // incident face centre relative to the reference box
+    if (inInc[face] < 0) centre = centre + Ri.col(face) * hi[face]; else centre = centre - Ri.col(face) * hi[face];
+    const int refAxis = refIsA ? code - 1 : code - 4;
+    const int t1 = refAxis == 0 ? 1 : 0, t2 = refAxis == 2 ? 1 : 2;  // the reference face's in-plane axes
+    // incident face corners in the reference face's 2-D frame
+    const float cu = dot(centre, Rr.col(t1)), cv = dot(centre, Rr.col(t2));
+    float j11 = dot(Rr.col(t1), Ri.col(s1)), j12 = dot(Rr.col(t1), Ri.col(s2));
+    float j21 = dot(Rr.col(t2), Ri.col(s1)), j22 = dot(Rr.col(t2), Ri.col(s2));
+    P2 quad[4];
     {
-        float k1 = m11 * Sb[a1], k2 = m21 * Sb[a1], k3 = m12 * Sb[a2], k4 = m22 * Sb[a2];
-        quad[0] = c1 - k1 - k3; quad[1] = c2 - k2 - k4;
-        quad[2] = c1 - k1 + k3; quad[3] = c2 - k2 + k4;
-        quad[4] = c1 + k1 + k3; quad[5] = c2 + k2 + k4;
-        quad[6] = c1 + k1 - k3; quad[7] = c2 + k2 - k4;
+        const float e1u = j11 * hi[s1], e1v = j21 * hi[s1], e2u = j12 * hi[s2], e2v = j22 * hi[s2];
+        quad[0].u = cu - e1u - e2u; quad[0].v = cv - e1v - e2v;
+        quad[1].u = cu - e1u + e2u; quad[1].v = cv - e1v + e2v;
+        quad[2].u = cu + e1u + e2u; quad[2].v = cv + e1v + e2v;
+        quad[3].u = cu + e1u - e2u; quad[3].v = cv + e1v - e2v;
     }
-    float rect[2] = {Sa[code1], Sa[code2]};
-    float ret[16];
-    int n = bb_clip_rect_quad(rect, quad, ret);
-    if (n < 1) return;
-    V3 point[8];
-    float dep[8];
-    float det1 = 1.f / (m11 * m22 - m12 * m21);
-    m11 *= det1; m12 *= det1; m21 *= det1; m22 *= det1;
-    int cnum = 0;
-    for (int j = 0; j < n; j++) {
-        float k1 = m22 * (ret[j * 2] - c1) - m12 * (ret[j * 2 + 1] - c2);
-        float k2 = -m21 * (ret[j * 2] - c1) + m11 * (ret[j * 2 + 1] - c2);
-        point[cnum] = center + Rb.col(a1) * k1 + Rb.col(a2) * k2;
-        dep[cnum] = Sa[codeN] - dot(normal2, point[cnum]);
-        if (dep[cnum] >= 0) { ret[cnum * 2] = ret[j * 2]; ret[cnum * 2 + 1] = ret[j * 2 + 1]; cnum++; }
+    P2 poly[8];
+    const int nClip = clip_quad_to_rect(hr[t1], hr[t2], quad, poly);
+    if (nClip < 1) return;
+    // back to 3-D through the inverse of the 2x2 projection, keeping the vertices that are below the reference face
+    const float invDet = 1.f / (j11 * j22 - j12 * j21);
+    j11 *= invDet; j12 *= invDet; j21 *= invDet; j22 *= invDet;
+    V3 pts[8];
+    float deep[8];
+    int kept = 0;
+    for (int v = 0; v < nClip; v++) {
+        const float a1 = j22 * (poly[v].u - cu) - j12 * (poly[v].v - cv);
+        const float a2 = -j21 * (poly[v].u - cu) + j11 * (poly[v].v - cv);
+        pts[kept] = centre + Ri.col(s1) * a1 + Ri.col(s2) * a2;
+        deep[kept] = hr[refAxis] - dot(outward, pts[kept]);
+        if (deep[kept] >= 0) { poly[kept] = poly[v]; kept++; }
     }
-    if (cnum < 1) return;
-    int maxc = 4;
-    if (maxc > cnum) maxc = cnum;
-    if (maxc < 1) maxc = 1;
-    if (cnum <= maxc) {
-        for (int j = 0; j < cnum; j++) {
-            V3 w = point[j] + pa;
-            if (code >= 4) w = w - normal * dep[j];
-            out.point[out.n] = w; out.depth[out.n] = -dep[j]; out.n++;
-        }
+    if (kept < 1) return;
+    int order[8];
+    int nOut = kept;
+    if (kept <= 4) {
+        for (int v = 0; v < kept; v++) order[v] = v;
     } else {
-        int i1 = 0;
-        float maxdepth = dep[0];
-        for (int i = 1; i < cnum; i++) if (dep[i] > maxdepth) { maxdepth = dep[i]; i1 = i; }
-        int iret[8];
-        bb_cull_points(cnum, ret, maxc, i1, iret);
-        for (int j = 0; j < maxc; j++) {
-            V3 w = point[iret[j]] + pa;
-            if (code >= 4) w = w - normal * dep[iret[j]];
-            out.point[out.n] = w; out.depth[out.n] = -dep[iret[j]]; out.n++;
-        }
+        int deepest = 0;
+        for (int v = 1; v < kept; v++) if (deep[v] > deep[deepest]) deepest = v;
+        pick_spread_vertices(kept, poly, 4, deepest, order);
+        nOut = 4;
+    }
+    for (int v = 0; v < nOut; v++) {
+        const int q = order[v];
+        V3 w = pts[q] + cr;
+        if (!refIsA) w = w - axis * deep[q];  // the points are reported on B: project off A's ... off the reference face when B owns it
+        out.point[out.n] = w; out.depth[out.n] = -deep[q]; out.n++;
     }
 }
 

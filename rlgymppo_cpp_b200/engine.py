@@ -31,7 +31,10 @@ EXPORTS = [
     "rlg_collector_create", "rlg_collector_destroy", "rlg_collector_set_layer", "rlg_collector_infer", "rlg_collector_collect",
     "rlg_collector_gae", "rlg_collector_view", "rlg_collector_export", "rlg_collector_launch_count",
     "rlg_collector_enable_timing", "rlg_collector_kernel_times", "rlg_collector_set_reset_hook", "rlg_engine_reset_current_to",
-    "rlg_collector_set_layer_device", "rlg_collector_return_stats",
+    "rlg_collector_set_layer_device", "rlg_collector_return_stats", "rlg_collector_load_external", "rlg_collector_set_step_hook",
+    "rlg_engine_step_begin", "rlg_engine_step_end", "rlg_engine_export_gamestates", "rlg_engine_export_gamestates_async", "rlg_engine_export_wait",
+    "rlg_engine_reset_to", "rlg_host_alloc", "rlg_host_free", "rlg_device_alloc", "rlg_device_free", "rlg_set_last_error", "rlg_sizeof_gym_state",
+    "rlg_sizeof_gym_player",
     # device PPO learner (bound in rlgymppo_cpp_b200.ppo)
     "rlg_ppo_create", "rlg_ppo_destroy", "rlg_ppo_init_weights", "rlg_ppo_set_layer", "rlg_ppo_get_layer", "rlg_ppo_adam_steps", "rlg_ppo_flat",
     "rlg_ppo_set_lr", "rlg_ppo_set_allreduce_hook", "rlg_ppo_submit", "rlg_ppo_submit_collector", "rlg_ppo_buffer_size", "rlg_ppo_buffer_read",

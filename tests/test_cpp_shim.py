@@ -99,7 +99,7 @@ def test_examplemain_trains_on_gpu(example_bin, mesh_dir, flags, host):
     last, out = _run(example_bin, mesh_dir, 3, *flags)
     assert last["arenas"] == 16 * 24 and last["custom_setter"] == ("--custom-setter" in flags) and last["host_path"] == host
     assert last["iterations"] == 3 and last["timesteps_collected"] == 100608  # ceil(100000 / 768) = 131 env-steps x 768 players
-    assert last["model_updates"] == 3  # batch 100 000 of the 100 608 rows per iteration
+    assert last["model_updates"] == 1 + 2 + 3  # the FIFO (300 000 rows) fills up: 1, 2, 3 full batches of 100 000 (ExperienceBuffer.cpp:106-121)
     assert 0 < last["last_entropy"] <= 4.5 and last["first_entropy"] > 4.3
     assert -5 < last["mean_step_reward"] < 5 and last["steps_per_second"] > 1000
     assert out.count("ITERATION COMPLETED") == 3 and "Policy Entropy" in out and "Average Step Reward" in out
@@ -114,9 +114,9 @@ def test_examplemain_saves_and_resumes(example_bin, mesh_dir, tmp_path):
     assert a["start_timesteps"] == 0 and a["total_timesteps"] == 2 * 100608
     assert os.listdir(d) == ["201216"] and sorted(os.listdir(os.path.join(d, "201216"))) == ["PPO_CRITIC.rlgb", "PPO_POLICY.rlgb", "RUNNING_STATS.json"]
     j = json.load(open(os.path.join(d, "201216", "RUNNING_STATS.json")))
-    assert j["cumulative_timesteps"] == 201216 and j["cumulative_model_updates"] == 2 and j["reward_running_stats"]["count"] == 300
+    assert j["cumulative_timesteps"] == 201216 and j["cumulative_model_updates"] == 3 and j["reward_running_stats"]["count"] == 300
     b, _ = _run(example_bin, mesh_dir, 1, "--save", d)
-    assert b["start_timesteps"] == 201216 and b["model_updates"] == 3 and b["total_timesteps"] == 3 * 100608
+    assert b["start_timesteps"] == 201216 and b["model_updates"] == 3 + 1 and b["total_timesteps"] == 3 * 100608  # the FIFO itself is not saved
 
 
 @pytest.mark.gpu

@@ -29,7 +29,13 @@ def _rows(n, obs, seed, policy=None):
     if policy is not None:
         with torch.no_grad():
             lp = torch.log_softmax(policy(torch.from_numpy(states)), -1).numpy()[np.arange(n), actions]
-        log_probs = (lp + g.normal(scale=0.15, size=n)).astype(np.float32)
+        # ratio = exp(lp - old): spread over both sides of the clip range, but no row within 1 % of a clip boundary — the clipped
+        # surrogate's gradient is discontinuous there and a TF32-sized difference in one logit would switch a whole row on or off
+        delta = g.normal(scale=0.15, size=n)
+        for edge in (np.log(0.8), np.log(1.2)):
+            near = np.abs(-delta - edge) < 0.01
+            delta[near] += 0.03 * np.sign(-delta[near] - edge + 1e-12) * -1
+        log_probs = (lp + delta).astype(np.float32)
     else:
         log_probs = np.log(g.uniform(0.005, 0.05, size=n)).astype(np.float32)
     return {"states": states, "actions": actions.astype(np.int64), "log_probs": log_probs, "values": g.normal(size=n).astype(np.float32),
