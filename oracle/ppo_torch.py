@@ -68,13 +68,42 @@ class ExperienceBuffer:
             yield {k: self.data[k].index_select(0, idx) for k in self.KEYS}
 
 
-def make_mlp(in_dim: int, hidden: List[int], out_dim: int) -> torch.nn.Sequential:
+def tf32_trunc(t: torch.Tensor) -> torch.Tensor:
+    """fp32 -> the TF32 value a tcgen05 kind::tf32 MMA sees when it is fed raw fp32 bits: the low 13 mantissa bits are ignored."""
+    return (t.contiguous().view(torch.int32) & -8192).view(torch.float32)
+
+
+class _TF32LinearFn(torch.autograd.Function):
+    """y = x W^T + b with both operands of EVERY contraction (forward, input gradient, weight gradient) truncated to TF32 and the
+    products summed in fp32 — the arithmetic of csrc/gemm.cu's TMA path up to summation order.  With it the restatement's ReLU masks
+    and clip decisions coincide with the device's, so gradients can be compared at 1e-4 instead of the ~2 % element noise that a
+    plain fp32 reference shows (a hidden unit whose pre-activation is within TF32 rounding of 0 switches its whole row term)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        return tf32_trunc(x) @ tf32_trunc(w).t() + b
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dyt = tf32_trunc(dy)
+        return dyt @ tf32_trunc(w), dyt.t() @ tf32_trunc(x), dy.sum(0)
+
+
+class TF32Linear(torch.nn.Linear):
+    def forward(self, x):
+        return _TF32LinearFn.apply(x, self.weight, self.bias)
+
+
+def make_mlp(in_dim: int, hidden: List[int], out_dim: int, emulate_tf32: bool = False) -> torch.nn.Sequential:
     """DiscretePolicy.cpp:13-27 / ValueEstimator.cpp:10-24: Linear+ReLU per hidden layer, final Linear."""
+    lin = TF32Linear if emulate_tf32 else torch.nn.Linear
     layers, prev = [], in_dim
     for h in hidden:
-        layers += [torch.nn.Linear(prev, h), torch.nn.ReLU()]
+        layers += [lin(prev, h), torch.nn.ReLU()]
         prev = h
-    layers.append(torch.nn.Linear(prev, out_dim))
+    layers.append(lin(prev, out_dim))
     return torch.nn.Sequential(*layers)
 
 
@@ -85,15 +114,15 @@ def mlp_layers_numpy(seq: torch.nn.Sequential):
 class TorchPPOLearner:
     """PPOLearner.cpp:17-349 (clipped PPO, entropy bonus, MSE value loss, clip-grad 0.5, Adam) + data-parallel replicas."""
 
-    def __init__(self, obs_size: int, num_actions: int, cfg: PPOLearnerConfig, device, process_group=None):
+    def __init__(self, obs_size: int, num_actions: int, cfg: PPOLearnerConfig, device, process_group=None, emulate_tf32: bool = False):
         self.cfg = cfg
         self.device = torch.device(device)
         if cfg.miniBatchSize == 0:
             cfg.miniBatchSize = cfg.batchSize  # PPOLearner.cpp:19-20
         if cfg.batchSize % cfg.miniBatchSize != 0:
             raise RuntimeError("PPOLearner: batchSize must be a multiple of miniBatchSize")  # PPOLearner.cpp:22-23
-        self.policy = make_mlp(obs_size, cfg.policyLayerSizes, num_actions).to(self.device)
-        self.value_net = make_mlp(obs_size, cfg.criticLayerSizes, 1).to(self.device)
+        self.policy = make_mlp(obs_size, cfg.policyLayerSizes, num_actions, emulate_tf32).to(self.device)
+        self.value_net = make_mlp(obs_size, cfg.criticLayerSizes, 1, emulate_tf32).to(self.device)
         self.policy_opt = torch.optim.Adam(self.policy.parameters(), lr=cfg.policyLR)
         self.value_opt = torch.optim.Adam(self.value_net.parameters(), lr=cfg.criticLR)
         self.policy_fwd, self.value_fwd = self.policy, self.value_net

@@ -56,6 +56,7 @@ struct rlg_engine {
     int32_t* resetCount = nullptr; int32_t* hResetCount = nullptr; int32_t* hResetIds = nullptr; float* hResetObs = nullptr;
     int32_t* dResetIds = nullptr; float* dResetObs = nullptr;  // device views of the two mapped host buffers
     unsigned char* epa = nullptr;  // [block] full-size penetration-depth workspaces of the role kernel
+    void* hbJobs = nullptr;        // [arena][car] HbJob records of the role kernel
     float* metrics = nullptr;    // [kMetricWords][A]: stepTotal, stepCount (u32), epTotal, epCount (u32), curEpRew, totalSteps (u32)
     int xwords = 0, stride = 0, scratchSlots = 0;
     int arenasPerBlock = 32, groupsPerBlock = 1;
@@ -213,6 +214,7 @@ struct RolesArgs {
     const int32_t* actions; float* obs; float* reward; uint8_t* done; int autoReset;
     float* metrics;  // GameInst reward metrics, word-transposed [kMetricWords][A] (nullptr: not tracked)
     unsigned char* epa;  // [block][kEpaFullBytes] full-size penetration-depth workspaces (rl_epa.h), used when a warp's small one overflows
+    struct HbJob* hbJobs;  // [arena][car] hitbox-narrowphase hand-over records
 };
 constexpr int kMetricWords = 6;
 
@@ -392,8 +394,20 @@ __device__ __forceinline__ void cands_pass_warp(CarW& w, int ci, bool active, co
     RL_PT(18);
 }
 
-// Pass 2 (after car-ball): hitbox vs the pre-filtered candidate triangles -> the car's car-world contact segment.
-__device__ __forceinline__ void box_meshes_warp(CollideCtx& cx, ContactSink& cw, const MeshSet& ms, const CarW& w, int ci, float breaking,
+// What the hitbox-mesh narrowphase of one car needs from the candidate passes: published by the car's role in P1a (global memory,
+// one record per arena and car), consumed in P1b by whichever warp evaluates the pairs — the group's ball warp for the first
+// kHbOffload cars (it would idle through the cars' vehicle update otherwise), the car's own warp for the rest.  The consumer
+// leaves the car-world callback's result (CollideCtx::wcHas) and nothing else here.
+struct HbJob {
+    uint32_t candMask, candGroupStart;
+    int32_t haveMask, wcHas;
+    V3 wcNormal;
+    MeshCands cands;
+};
+constexpr int kHbOffload = 3;
+
+// Pass 2: hitbox vs the pre-filtered candidate triangles -> the car's world contact slots.
+__device__ __forceinline__ void box_meshes_warp(CollideCtx& cx, ContactSink& cw, const MeshSet& ms, const HbJob& w, int ci, float breaking,
                                                 bool active, const CarConsts& k, const uint32_t* mine, uint32_t* wq, int stride, const EpaCtx* ws) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -527,23 +541,55 @@ __global__ void __maxnreg__(168) k_roles(const __grid_constant__ RolesArgs g) {
         if (valid) { if (role == 0) tick_s0_ball(s, x); else tick_s0_car(s, x, role - 1); }
         PT_WORK(1);
         if (g.barMode == 2 && t > tBegin) SYNC_TICK(); else SYNC_GROUP();  // B1
+        // P1a: the ball's own narrowphase | the cars' mesh candidates, wheel-ray mesh part and hitbox pre-filter
+        HbJob* jobs = g.hbJobs + (size_t)(valid ? a : 0) * P;
         if (role == 0) {
             if (valid) tick_p1_ball(s, x, g.cfg, g.ms, k, thr, scratch);
         } else {
-            CollideCtx cx; ContactSink cw;
             if (valid) tick_p1_car_pose(s, x, g.cfg, g.ms, k, role - 1, w, false);
             collect_candidates_warp(w, role - 1, valid, k, g.ms, mine, wq);  // whole warp
             cands_pass_warp(w, role - 1, valid, k, g.ms, mine, wq, g.stride);  // whole warp
+            if (valid) {  // hand the hitbox narrowphase's input over
+                HbJob& j = jobs[role - 1];
+                j.candMask = w.candMask; j.candGroupStart = w.candGroupStart; j.haveMask = w.haveMask; j.wcHas = 0;
+                j.cands.n = w.cands.n;
+                for (int q = 0; q < w.cands.n; q++) j.cands.node[q] = w.cands.node[q];
+            }
+        }
+        PT_WORK(2);
+        SYNC_GROUP();  // B1b
+        // P1b: the cars' vehicle / control model, car-ball, hitbox-plane | the hitbox-mesh pairs of the first cars on the ball warp
+        const int nOff = P < kHbOffload ? P : kHbOffload;
+        if (role == 0) {
+            for (int c = 0; c < nOff; c++) {
+                CollideCtx cx; ContactSink cw;
+                HbJob& j = jobs[c];
+                if (valid) {
+                    cx.a = &s; cx.cfg = &g.cfg; cx.tx = x; cx.k = &k; cx.tick = get_i64(s.tickLo, s.tickHi); cx.firstTickOfStep = first; cx.epa = &epaCtx;
+                    cx.wcHas = &j.wcHas; cx.wcNormal = &j.wcNormal;
+                    cw = make_sink(seg_car_world(scratch, c), kSegCarWorld);
+                }
+                box_meshes_warp(cx, cw, g.ms, j, c, thr.car, valid, k, mine, wq, g.stride, &epaCtx);  // whole warp (car 0's queue: its warp is not in a pass now)
+                if (valid) car_set_mesh_count(x.car[c], cw.n);
+            }
+        } else {
+            CollideCtx cx; ContactSink cw;
             if (valid) tick_p1_car_begin(s, x, g.cfg, g.ms, k, thr, role - 1, w, scratch, first, cx, cw, &epaCtx);
-            box_meshes_warp(cx, cw, g.ms, w, role - 1, thr.car, valid, k, mine, wq, g.stride, &epaCtx);  // whole warp
-            if (valid) tick_p1_car_end(cx, cw, x, thr, role - 1);
+            if (role - 1 >= nOff) {
+                box_meshes_warp(cx, cw, g.ms, jobs[role - 1], role - 1, thr.car, valid, k, mine, wq, g.stride, &epaCtx);  // whole warp
+                if (valid) car_set_mesh_count(x.car[role - 1], cw.n);
+            }
+            if (valid) tick_p1_car_end(cx, x, thr, role - 1, scratch);
         }
         PT_WORK(2);
         SYNC_GROUP();  // B2
         bool self = false;
         if (valid) {
             if (role == 0) tick_p2_solve(s, x, g.cfg, k, thr, scratch, first);
-            else if ((self = tick_p2_car_self(s, x, g.cfg, k, role - 1, scratch))) tick_p3_car(s, x, *g.tb, k, role - 1, w);
+            else {
+                if (role - 1 < nOff) car_world_merge(s, x, role - 1, jobs[role - 1].wcHas, jobs[role - 1].wcNormal);
+                if ((self = tick_p2_car_self(s, x, g.cfg, k, role - 1, scratch))) tick_p3_car(s, x, *g.tb, k, role - 1, w);
+            }
         }
         PT_WORK(3);
         SYNC_GROUP();  // B3
@@ -693,7 +739,7 @@ int rlg_engine_destroy(rlg_engine* e) {
         cudaFree(e->prof); cudaFree(e->prof2);
     }
 #endif
-    cudaFree(e->scratch); cudaFree(e->metrics); cudaFree(e->epa);
+    cudaFree(e->scratch); cudaFree(e->metrics); cudaFree(e->epa); cudaFree(e->hbJobs);
     cudaFree(e->xIds); cudaFree(e->xCars); cudaFree(e->xBalls); cudaFree(e->xGym); cudaFree(e->xPlayers);
     if (e->evExport) cudaEventDestroy(e->evExport);
     cudaFree(e->state); cudaFree(e->tables); cudaFree(e->obs); cudaFree(e->reward); cudaFree(e->done); cudaFree(e->actions);
@@ -784,6 +830,8 @@ int rlg_engine_create(const rlg_engine_cfg* cfg, rlg_engine** out) {
         CKD(cudaMalloc(&e->epa, blocks * kEpaFullBytes));
         CKD(cudaMemsetAsync(e->epa, 0, blocks * kEpaFullBytes, e->stream));
     }
+    CKD(cudaMalloc(&e->hbJobs, (size_t)A * P * sizeof(HbJob)));
+    CKD(cudaMemsetAsync(e->hbJobs, 0, (size_t)A * P * sizeof(HbJob), e->stream));
     CKD(cudaMalloc(&e->metrics, (size_t)kMetricWords * A * 4));
     CKD(cudaMemsetAsync(e->metrics, 0, (size_t)kMetricWords * A * 4, e->stream));
     CKD(cudaMalloc(&e->tables, sizeof(Tables)));
@@ -855,6 +903,7 @@ static RolesArgs roles_args(rlg_engine* e) {
     g.barMode = e->barMode; g.asyncLoad = e->asyncLoad; g.prof = e->prof;
     g.k = car_consts(e->cfg.carPreset); g.thr = contact_thresholds(g.k);
     g.epa = e->epa;
+    g.hbJobs = reinterpret_cast<HbJob*>(e->hbJobs);
     return g;
 }
 

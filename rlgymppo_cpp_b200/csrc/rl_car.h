@@ -45,9 +45,13 @@ struct CarX {
     V3 ballVelCache;      // this car's contribution to Ball::_velocityImpulseCache
     V3 velCache;          // Car::_velocityImpulseCache (bumps), written by the pair phase
     int32_t noResponse;   // demoed when the tick started
-    int32_t nCarBall, nCarWorld;  // contacts written to this car's scratch segments
+    int32_t nCarBall, nCarPlane;  // contacts written to this car's scratch segments (car-ball slot, plane staging slots)
+    // P3 -> P4: the boost pads this car overlaps.  Between P1 and P3 the low word is free and carries the number of hitbox-mesh
+    // contacts in the car's world slots (car_mesh_count), written by whichever role ran that narrowphase.
     uint32_t padHitLo, padHitHi;
 };
+RL_HDI int car_mesh_count(const CarX& o) { return (int)o.padHitLo; }
+RL_HDI void car_set_mesh_count(CarX& o, int n) { o.padHitLo = (uint32_t)n; }
 struct TickXHdr {
     V3 ballPos, ballVel, ballAngvel;  // start-of-tick snapshot (vel undamped)
     int32_t nBall, nPair, ballActive;

@@ -37,8 +37,11 @@ struct ContactSet {
 };
 
 // Where a role appends the contacts it finds: a segment of the arena's contact scratch (global memory on the device).
-// Segment layout per arena: [ball: kSegBall][per car: 1 car-ball slot + kSegCarWorld world slots][car-car: kSegPair]
-constexpr int kSegBall = 12, kSegCarWorld = 13, kSegCar = 1 + kSegCarWorld, kSegPair = 16;
+// Segment layout per arena: [ball: kSegBall][per car: 1 car-ball slot + kSegCarWorld world slots + kSegCarPlane staging slots][car-car: kSegPair]
+// A car's world contacts are produced in two pieces that may be written by different roles at the same time (rl_tick.h): the
+// hitbox-mesh contacts fill the world slots from the front, the (at most 4) hitbox-plane contacts go to the staging slots; readers
+// see "mesh piece, then plane piece", capped at kSegCarWorld in total — the order and the cap of one shared sink.
+constexpr int kSegBall = 12, kSegCarWorld = 13, kSegCarPlane = 4, kSegCar = 1 + kSegCarWorld + kSegCarPlane, kSegPair = 16;
 RL_HDI int contact_scratch_slots(int ncars) { return kSegBall + ncars * kSegCar + kSegPair; }
 struct ContactSink {
     Contact* base;
@@ -88,6 +91,10 @@ struct CollideCtx {
     V3 ballPos, ballVel;      // the ball as the narrowphase sees it: start-of-tick position, DAMPED velocity
     int32_t firstTickOfStep;  // bump counters only stick when the callback fires during Gym::Step's first tick (see rl_tick.h)
     const EpaCtx* epa;               // penetration-depth workspace (device: the warp's; host: nullptr = local, rl_epa.h)
+    // car-world callback target: nullptr = the car's own CarState::worldContact; the role kernel's ball warp, which evaluates the
+    // hitbox-mesh pairs while the car's own role is still inside Car::_PreTickUpdate (that reads and clears worldContact), records
+    // the callback's result here instead and the car's role applies it afterwards (engine.cu, rl_tick.h car_world_merge)
+    int32_t* wcHas = nullptr; V3* wcNormal = nullptr;
 };
 
 // ---- Arena::_BulletContactAddedCallback ------------------------------------------------------
@@ -175,9 +182,12 @@ RL_HD inline void on_car_car(CollideCtx& x, int c1, int c2, Contact& cp) {
 }
 
 RL_HDI void on_car_world(CollideCtx& x, int ci, Contact& cp) {
-    CarS& car = x.a->cars[ci];
-    car.worldContactHas = 1;
-    car.worldContactNormal = cp.normal;
+    if (x.wcHas) { *x.wcHas = 1; *x.wcNormal = cp.normal; }
+    else {
+        CarS& car = x.a->cars[ci];
+        car.worldContactHas = 1;
+        car.worldContactNormal = cp.normal;
+    }
     cp.friction = x.cfg->mut.carWorldFriction; cp.restitution = x.cfg->mut.carWorldRestitution;
 }
 

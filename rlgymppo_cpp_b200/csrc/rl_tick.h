@@ -92,6 +92,7 @@ RL_HD inline void pads_post_tick(ArenaS& a, const SimCfg& cfg, const uint64_t* h
 #ifdef RL_DEBUG_CONTACTS
 static ContactSet g_dbg_contacts;
 static CarW g_dbg_carw[kMaxCars];  // the wheels' workspace after the last tick (host debugging only)
+static int g_dbg_nmesh[kMaxCars], g_dbg_nplane[kMaxCars];  // a car's world-contact piece sizes as P1 left them (the mesh count's word is reused by P3)
 #endif
 
 // ---- one physics tick, split by ROLE ------------------------------------------------------------------------------
@@ -105,6 +106,10 @@ static CarW g_dbg_carw[kMaxCars];  // the wheels' workspace after the last tick 
 //   P1  car c : Car::_PreTickUpdate (wheel rays read the snapshots), gravity, hitbox AABB,
 //               car-ball, hitbox-mesh, hitbox-plane narrowphase -> own contact segments
 //       ball  : pads pre-tick, sphere-mesh, sphere-plane narrowphase -> own contact segment          | barrier B2
+//       (role kernel: P1 is split in two by one more barrier — P1a: the cars find their mesh candidates, run the wheel rays'
+//        mesh part and publish the hitbox pre-filter while the ball does its own narrowphase; P1b: the cars run the vehicle /
+//        control model, car-ball and hitbox-plane while the otherwise idle BALL warp evaluates the cars' hitbox-mesh pairs,
+//        which only depend on the start-of-tick pose; engine.cu)
 //   P2  ball  : ball damping, car-car pairs (+bump/demo callbacks), sequential-impulse solve of the island(s) of the
 //               ball and the COUPLED cars (contacts gathered in the reference's manifold order), write back,
 //               integrate + finish the ball, tick count
@@ -118,6 +123,11 @@ struct Thresholds;
 RL_HDI Contact* seg_ball(Contact* scratch) { return scratch; }
 RL_HDI Contact* seg_car(Contact* scratch, int c) { return scratch + kSegBall + c * kSegCar; }
 RL_HDI Contact* seg_pair(Contact* scratch, int ncars) { return scratch + kSegBall + ncars * kSegCar; }
+RL_HDI Contact* seg_car_world(Contact* scratch, int c) { return seg_car(scratch, c) + 1; }                  // hitbox-mesh contacts, then ...
+RL_HDI Contact* seg_car_plane(Contact* scratch, int c) { return seg_car(scratch, c) + 1 + kSegCarWorld; }   // ... the staged hitbox-plane contacts
+// a car's world contacts as the solver sees them: the mesh piece followed by the plane piece, kSegCarWorld at most
+RL_HDI int car_plane_taken(const CarX& o) { int room = kSegCarWorld - car_mesh_count(o); return o.nCarPlane < room ? o.nCarPlane : (room > 0 ? room : 0); }
+RL_HDI int car_world_count(const CarX& o) { return car_mesh_count(o) + car_plane_taken(o); }
 
 RL_HDI uint32_t respawn_rnd(const ArenaS& a, int ci) {
     uint64_t z = (((uint64_t)a.rngHi << 32) | a.rngLo) + 0x9E3779B97F4A7C15ULL * (uint64_t)(uint32_t)(a.tickLo + 1) + 0xD1B54A32D192ED03ULL * (uint64_t)(ci + 1);
@@ -174,15 +184,24 @@ RL_HD inline void tick_p1_car_begin(ArenaS& a, TickX x, const SimCfg& cfg, const
     if (overlapBall && !(!x.h->ballActive && o.noResponse)) car_ball(cx, cb, c, fminf_(thr.ball, thr.car));
     o.nCarBall = cb.n;
     RL_PT(4);
-    cw = make_sink(seg_car(scratch, c) + 1, kSegCarWorld);
+    cw = make_sink(seg_car_world(scratch, c), kSegCarWorld);
 }
 
-RL_HD inline void tick_p1_car_end(CollideCtx& cx, ContactSink& cw, TickX x, const Thresholds& thr, int c) {
+// the hitbox-plane narrowphase into the staging slots (after the hitbox-mesh narrowphase in callback order: when both fire in one
+// role the car's worldContact ends up the plane's; when the mesh piece ran elsewhere car_world_merge restores that order)
+RL_HD inline void tick_p1_car_end(CollideCtx& cx, TickX x, const Thresholds& thr, int c, Contact* scratch) {
     RL_PT(5);
+    ContactSink cpl = make_sink(seg_car_plane(scratch, c), kSegCarPlane);
 #pragma unroll 1
-    for (int p = 0; p < 4; p++) box_plane(cx, cw, c, p, thr.car);
-    x.car[c].nCarWorld = cw.n;
+    for (int p = 0; p < 4; p++) box_plane(cx, cpl, c, p, thr.car);
+    x.car[c].nCarPlane = cpl.n;
     RL_PT(6);
+}
+// the car-world callback of a mesh piece that was evaluated by another role (CollideCtx::wcHas): it precedes the plane callbacks
+// in the reference's manifold order, so it only sticks when no plane callback fired this tick
+RL_HDI void car_world_merge(ArenaS& a, TickX x, int c, int meshHas, V3 meshNormal) {
+    const CarX& o = x.car[c];
+    if (meshHas && !(o.nCarPlane > 0 && !o.noResponse)) { a.cars[c].worldContactHas = 1; a.cars[c].worldContactNormal = meshNormal; }
 }
 
 RL_HD inline void tick_p1_car(ArenaS& a, TickX x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, const Thresholds& thr, int c, CarW& w,
@@ -193,7 +212,11 @@ RL_HD inline void tick_p1_car(ArenaS& a, TickX x, const SimCfg& cfg, const MeshS
     tick_p1_car_begin(a, x, cfg, ms, k, thr, c, w, scratch, firstTickOfStep, cx, cw);
     if (w.cands.n >= 0) box_meshes_candidates(cx, cw, ms, w.cands, c, thr.car);
     else box_meshes(cx, cw, ms, c, thr.car);
-    tick_p1_car_end(cx, cw, x, thr, c);
+    car_set_mesh_count(x.car[c], cw.n);
+    tick_p1_car_end(cx, x, thr, c, scratch);
+#if defined(RL_DEBUG_CONTACTS) && !defined(__CUDA_ARCH__)
+    g_dbg_nmesh[c] = car_mesh_count(x.car[c]); g_dbg_nplane[c] = car_plane_taken(x.car[c]);
+#endif
 }
 
 RL_HD inline void tick_p1_ball(ArenaS& a, TickX x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, const Thresholds& thr, Contact* scratch) {
@@ -254,7 +277,8 @@ RL_HD inline bool tick_p2_car_self(ArenaS& a, TickX x, const SimCfg& cfg, const 
     if (car_is_coupled(x, cfg.numCars, c)) return false;
     if (o.noResponse) return true;
     CarS& car = a.cars[c];
-    if (o.nCarWorld == 0) {
+    const int nWorld = car_world_count(o);
+    if (nWorld == 0) {
         // no manifold: the solver degenerates to writeBackBodies (btSequentialImpulseConstraintSolver.cpp:1878-1904):
         // v += 0 (deltas), then v += externalForceImpulse
         M3 iiw = world_inertia(car.rot, k.invInertiaLocal);
@@ -264,7 +288,13 @@ RL_HD inline bool tick_p2_car_self(ArenaS& a, TickX x, const SimCfg& cfg, const 
     }
     SolverBody b;
     solver_body_from_car(b, car, o, k);
-    solve_island_one(b, 1 + c, seg_car(scratch, c) + 1, o.nCarWorld);
+    {   // this car alone reads its world slots now: put the staged plane contacts behind the mesh contacts
+        Contact* world = seg_car_world(scratch, c);
+        const Contact* plane = seg_car_plane(scratch, c);
+        const int nm = car_mesh_count(o), np = car_plane_taken(o);
+        for (int i = 0; i < np; i++) world[nm + i] = plane[i];
+    }
+    solve_island_one(b, 1 + c, seg_car_world(scratch, c), nWorld);
     car.vel = b.linVel; car.angvel = b.angVel; car.pos = b.pos; car.rot = b.rot;
     RL_PT(13);
     return true;
@@ -314,7 +344,10 @@ RL_HD inline void tick_p2_solve(ArenaS& a, TickX x, const SimCfg& cfg, const Car
         take(seg_ball(scratch), x.h->nBall);
         for (int c = 0; c < P; c++) take(seg_car(scratch, c), x.car[c].nCarBall);
         for (int c = 0; c < P; c++) {
-            take(seg_car(scratch, c) + 1, x.car[c].nCarWorld);
+            // (an uncoupled car has already run P3 in the serial driver: its counts come from the P1 snapshot; its own island solve
+            // moved the plane piece behind the mesh piece, so the world slots hold both)
+            take(seg_car_world(scratch, c), g_dbg_nmesh[c]);
+            take(((coupled >> c) & 1u) ? seg_car_plane(scratch, c) : seg_car_world(scratch, c) + g_dbg_nmesh[c], g_dbg_nplane[c]);
             const Contact* pr = seg_pair(scratch, P);
             for (int i = 0; i < cp.n; i++) if (pr[i].b == 1 + c) take(pr + i, 1);
         }
@@ -363,7 +396,8 @@ RL_HD inline void tick_p2_solve(ArenaS& a, TickX x, const SimCfg& cfg, const Car
         for (int c = 0; c < P; c++) if ((coupled >> c) & 1u) take(seg_car(scratch, c), x.car[c].nCarBall);
         for (int c = 0; c < P; c++) {
             if (!((coupled >> c) & 1u)) continue;
-            take(seg_car(scratch, c) + 1, x.car[c].nCarWorld);
+            take(seg_car_world(scratch, c), car_mesh_count(x.car[c]));
+            take(seg_car_plane(scratch, c), car_plane_taken(x.car[c]));
             const Contact* pr = seg_pair(scratch, P);
             for (int i = 0; i < cp.n; i++) if (pr[i].b == 1 + c) take(pr + i, 1);
         }

@@ -1,11 +1,14 @@
 """-m gpu: the device PPO learner (csrc/ppo.cu through rlgymppo_cpp_b200.ppo / learner.PPOLearner) against the torch fp32
 restatement of PPOLearner::Learn (oracle/ppo_torch.py, CPU) from identical weights, buffer contents and batch permutations.
 
-Tolerances: the device runs every GEMM with TF32 inputs / FP32 accumulation (SURVEY 8d allows it), the restatement is plain
-fp32.  Gradients (test_gradients_match_autograd) agree within 2e-3 of each tensor's largest gradient.  Adam's first step moves
-every weight by ~lr * sign(g) whatever the gradient's size, so an element whose gradient is below the TF32 noise may step the
-other way (2 * lr apart): the step tests therefore bound the FRACTION of such elements (< 1 %, all others within 15 % of one
-step) and ask for a cosine similarity > 0.995 between the two parameter updates; reported diagnostics within 2e-3 relative.  Adam and clip_grad_norm_ are torch's own operators in the restatement (unpinned against the
+Tolerances.  The device runs every GEMM with TF32 inputs / FP32 accumulation (SURVEY 8d allows it).  Against a PLAIN fp32
+restatement the difference is not small element-wise: a hidden unit whose pre-activation lies within TF32 rounding of zero takes
+its ReLU-backward decision the other way and switches a whole row's term of that unit's weight gradient (measured: ~2-4 % of a
+tensor's largest gradient, at any batch size), and Adam's first step turns a flipped gradient sign into 2 * lr.  So the sharp
+comparisons use the restatement with its contractions' operands truncated to TF32 (oracle/ppo_torch.py TF32Linear: the same
+arithmetic up to fp32 summation order): gradients within 3e-4 of each tensor's largest entry, parameter updates with cosine
+similarity > 0.999 and < 0.2 % of the parameters further than 15 % of a step apart.  One plain-fp32 comparison stays, with the
+bounds that the effect above allows (cosine > 0.98, < 1 % of the parameters off); reported diagnostics within 2e-3 relative.  Adam and clip_grad_norm_ are torch's own operators in the restatement (unpinned against the
 reference binary by construction: the reference calls the same libtorch code)."""
 import os
 
@@ -74,7 +77,7 @@ def _submit(dev, rows):
     ours_stream_sync(dev)
 
 
-def _make_pair(obs, hidden, batch, mini, epochs, seed, ent=0.01, lr=2e-4, exp_size=None):
+def _make_pair(obs, hidden, batch, mini, epochs, seed, ent=0.01, lr=2e-4, exp_size=None, tf32=True):
     import torch
 
     torch.manual_seed(seed)
@@ -83,7 +86,7 @@ def _make_pair(obs, hidden, batch, mini, epochs, seed, ent=0.01, lr=2e-4, exp_si
     ours = L.PPOLearner(obs, 90, cfg, "cuda:0", exp_buffer_size=exp_size or batch, seed=seed)
     import copy
 
-    ref = PT.TorchPPOLearner(obs, 90, copy.deepcopy(cfg), "cpu")
+    ref = PT.TorchPPOLearner(obs, 90, copy.deepcopy(cfg), "cpu", emulate_tf32=tf32)
     ref.policy.load_state_dict(ours.policy.state_dict())
     ref.value_net.load_state_dict(ours.value_net.state_dict())
     return ours, ref, cfg
@@ -111,11 +114,12 @@ def test_device_experience_buffer_is_the_reference_fifo():
     assert not np.array_equal(perm, ours.dev.peek_shuffle(counter=5))
 
 
-@pytest.mark.parametrize("hidden,obs,batch,mini", [((64, 64), 89, 512, 256), ((256, 256, 256), 89, 4096, 1024), ((32,), 70, 256, 256)])
-def test_learn_step_matches_the_torch_restatement(hidden, obs, batch, mini):
+@pytest.mark.parametrize("hidden,obs,batch,mini,tf32", [((64, 64), 89, 512, 256, True), ((256, 256, 256), 89, 4096, 1024, True), ((32,), 70, 256, 256, True),
+                                                        ((256, 256, 256), 89, 4096, 1024, False)])
+def test_learn_step_matches_the_torch_restatement(hidden, obs, batch, mini, tf32):
     import torch
 
-    ours, ref, cfg = _make_pair(obs, hidden, batch, mini, 1, seed=3)
+    ours, ref, cfg = _make_pair(obs, hidden, batch, mini, 1, seed=3, tf32=tf32)
     rows = _rows(batch, obs, 11, policy=ref.policy)
     _submit(ours.dev, rows)
     exp = PT.ExperienceBuffer(batch, 0, "cpu")
@@ -127,7 +131,10 @@ def test_learn_step_matches_the_torch_restatement(hidden, obs, batch, mini):
     ref.learn(exp, rep_r)
     assert rep_o["Cumulative Model Updates"] == rep_r["Cumulative Model Updates"] == 1
     print({k: (rep_o[k], rep_r[k]) for k in ("Policy Entropy", "Mean KL Divergence", "Mean Ratio", "Value Function Loss", "SB3 Clip Fraction")})
-    _compare_updates(init, _flat(ours), _flat(ref), 2e-4)
+    if tf32:
+        _compare_updates(init, _flat(ours), _flat(ref), 2e-4, frac_bad=0.002, cos_min=0.999)
+    else:
+        _compare_updates(init, _flat(ours), _flat(ref), 2e-4, frac_bad=0.01, cos_min=0.98)
     for k in ("Policy Entropy", "Mean Ratio", "Value Function Loss", "Policy Update Magnitude", "Value Function Update Magnitude"):
         assert abs(rep_o[k] - rep_r[k]) <= 2e-3 * abs(rep_r[k]) + 1e-6, (k, rep_o[k], rep_r[k])
     assert abs(rep_o["Mean KL Divergence"] - rep_r["Mean KL Divergence"]) < 2e-4
@@ -137,7 +144,7 @@ def test_learn_step_matches_the_torch_restatement(hidden, obs, batch, mini):
 
 def test_gradients_match_autograd():
     """The hand-written backward (loss kernels + GEMMs + bias sums, accumulated over two minibatches) against torch autograd on
-    the restatement's losses: every gradient within 2e-3 of the largest gradient of its tensor."""
+    the TF32-operand restatement's losses: every gradient within 3e-4 of the largest gradient of its tensor."""
     import torch
 
     from rlgymppo_cpp_b200 import ppo as P
@@ -169,7 +176,7 @@ def test_gradients_match_autograd():
         for l, (m, (gw, gb)) in enumerate(zip(lin, grabbed[name])):
             for got, want in ((gw, m.weight.grad.numpy()), (gb, m.bias.grad.numpy())):
                 scale = float(np.abs(want).max()) + 1e-12
-                assert float(np.abs(got - want).max()) <= 2e-3 * scale, (name, l, float(np.abs(got - want).max()), scale)
+                assert float(np.abs(got - want).max()) <= 3e-4 * scale, (name, l, float(np.abs(got - want).max()), scale)
 
 
 def test_many_steps_track_the_restatement_and_frozen_networks_stay_put():
@@ -191,7 +198,7 @@ def test_many_steps_track_the_restatement_and_frozen_networks_stay_put():
         ref.learn(exp, rr)
         assert ro["Cumulative Model Updates"] == rr["Cumulative Model Updates"]
     assert ro["Cumulative Model Updates"] == 8 + 10
-    _compare_updates(init, _flat(ours), _flat(ref), 18 * 2e-4, frac_bad=0.02, cos_min=0.99, close=0.1)  # 18 steps: within 10 % of the total path
+    _compare_updates(init, _flat(ours), _flat(ref), 18 * 2e-4, frac_bad=0.01, cos_min=0.998, close=0.1)  # 18 steps: within 10 % of the total path
     for k in ("Policy Entropy", "Value Function Loss", "Mean Ratio"):
         assert abs(ro[k] - rr[k]) <= 5e-3 * abs(rr[k]) + 1e-5, (k, ro[k], rr[k])
     p0 = [p.detach().clone() for p in ours.policy.parameters()]
@@ -263,7 +270,7 @@ def test_data_parallel_two_ranks_nccl(tmp_path):
     assert torch.equal(g["params"][0], g["params"][1]), "replicas diverged"
     torch.manual_seed(100)
     cfg = L.PPOLearnerConfig(policyLayerSizes=[64, 64], criticLayerSizes=[64, 64], batchSize=256, miniBatchSize=128, epochs=2, policyLR=2e-4, criticLR=2e-4)
-    ref = PT.TorchPPOLearner(89, 90, cfg, "cpu")
+    ref = PT.TorchPPOLearner(89, 90, cfg, "cpu", emulate_tf32=True)
     flat0 = torch.cat([p.detach().reshape(-1) for p in list(ref.policy.parameters()) + list(ref.value_net.parameters())])
     assert torch.equal(flat0, g["init"]), "rank 0's initialisation was not the broadcast one"
     shards = [_rows(256, 89, 10), _rows(256, 89, 11)]
@@ -279,4 +286,4 @@ def test_data_parallel_two_ranks_nccl(tmp_path):
         torch.nn.utils.clip_grad_norm_(ref.policy.parameters(), 0.5); torch.nn.utils.clip_grad_norm_(ref.value_net.parameters(), 0.5)
         ref.policy_opt.step(); ref.value_opt.step()
     flat = torch.cat([p.detach().reshape(-1) for p in list(ref.policy.parameters()) + list(ref.value_net.parameters())])
-    _compare_updates(g["init"], g["params"][0], flat, 2 * 2e-4, frac_bad=0.02, cos_min=0.99)
+    _compare_updates(g["init"], g["params"][0], flat, 2 * 2e-4, frac_bad=0.005, cos_min=0.998)
