@@ -413,7 +413,7 @@ def run_ours(args, rank, local_rank, world):
             tf_peak = 1125.0
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (sim, gym layer, GAE) / tf32-in fp32-acc (MLP)", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f32 (sim, gym layer, GAE) / tf32-in fp32-acc (MLP)", "data": "synthetic",
             "value_median_of_blocks": float(np.median(block_rates)), "block_rates": block_rates, "warmup_run": W_run,
             "config": {"workload": f"{'cfg2: ' if (TEAM == 1 and A == ARENAS_PER_GPU) else 'sweep: '}{TEAM}v{TEAM} soccar, {A} arenas/GPU, {'DefaultOBSPadded(3)' if PADDED_OBS else 'DefaultObs'} + examplemain rewards{' in ZeroSumReward(0.3)' if ZERO_SUM else ''}/terminals, RandomState, tickSkip 8, "
                                    "on-device policy (256x256x256) + critic inference, sampling, trajectory ring, GAE; placeholder mesh set v1; "
@@ -444,6 +444,74 @@ def run_ours(args, rank, local_rank, world):
                 out["cpu_baseline"] = cpu_baseline_sample()
             except Exception as ex:  # the baseline is reported, never required for the GPU number
                 out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
+        emit(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_cfg4(args, rank, local_rank, world):
+    """BASELINE configs[3] end to end: 3v3 soccar, a user StateSetter on the host (every reset goes through Python), ELO skill tracking
+    against frozen versions on rank 0, collectionDuringLearn, the PPO update data parallel over the ranks.  One bench step = one
+    Learner iteration; value = player-timesteps per second over whole iterations (collection + consumption)."""
+    import torch
+    import torch.distributed as dist
+
+    from rlgymppo_cpp_b200 import build, learner, skill_tracker
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    build.build()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    global TEAM
+    TEAM = 3
+    A, T = args.arenas, args.env_steps
+    rows = A * 6 * T
+    cfg = learner.LearnerConfig(timestepsPerIteration=rows * world, expBufferSize=rows * world, randomSeed=123, collectionDuringLearn=True)
+    cfg.sendMetrics = False
+    cfg.checkpointLoadFolder = cfg.checkpointSaveFolder = ""
+    cfg.ppo = learner.PPOLearnerConfig(batchSize=rows * world, miniBatchSize=rows * world // 4, epochs=1, policyLR=2e-4, criticLR=2e-4, entCoef=0.01)
+    cfg.skillTrackerConfig = skill_tracker.SkillTrackerConfig(enabled=True, numEnvs=8, simTime=8 * 8 * 4 / 120, updateInterval=2, timestepsPerVersion=4 * rows * world)
+    rng = np.random.default_rng(1234 + rank)
+
+    def setter(ids, cars, balls):  # "custom StateSetter": ball dropped over midfield, cars on their own half facing it
+        n, P = cars.shape
+        balls["pos"][:, 0] = rng.uniform(-2000, 2000, n); balls["pos"][:, 1] = 0; balls["pos"][:, 2] = rng.uniform(300, 1200, n)
+        side = np.where(cars["team"] == 0, -1.0, 1.0)
+        cars["pos"][:, :, 0] = rng.uniform(-2500, 2500, (n, P)); cars["pos"][:, :, 1] = side * rng.uniform(1500, 3500, (n, P)); cars["pos"][:, :, 2] = 17
+        yaw = np.where(side < 0, np.pi / 2, -np.pi / 2)
+        cars["rot_forward"][:, :, 0] = np.cos(yaw); cars["rot_forward"][:, :, 1] = np.sin(yaw); cars["rot_forward"][:, :, 2] = 0
+        cars["rot_right"][:, :, 0] = -np.sin(yaw); cars["rot_right"][:, :, 1] = np.cos(yaw); cars["rot_right"][:, :, 2] = 0
+        cars["boost"] = 50.0
+
+    with stdout_to_stderr():
+        L = learner.Learner(workload_cfg(A, local_rank, rank), cfg, device_index=local_rank, state_setter=setter)
+        K, W = args.steps, max(args.warmup, 3)
+        L.learn(max_iterations=W)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        reports = L.learn(max_iterations=K)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    dt = float(dt.item())
+    if rank == 0:
+        med = lambda k: float(np.median([r[k] for r in reports if k in r]))
+        out = {"metric": "PPO iteration, configs[3] (3v3, host StateSetter, ELO skill tracking, collection during learn)", "value": world * rows * K / dt,
+               "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * dt / K, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f32 (sim) / tf32-in fp32-acc (MLP, PPO update)", "data": "synthetic",
+               "config": {"workload": f"cfg4: 3v3 soccar, {A} arenas/GPU, DefaultObs, Python host StateSetter, SkillTracker (8 eval arenas on rank 0), "
+                                      f"collectionDuringLearn, one bench step = one Learner iteration of {rows * world} timesteps (global batch, 4 minibatches, 1 epoch)",
+                          "arenas_per_gpu": A, "players_per_arena": 6, "timesteps_per_iteration": rows * world, "parallelism": f"arena-sharded x{world}, NCCL gradient all-reduce"},
+               "iteration": {"total_s": med("Total Iteration Time"), "learn_s": med("PPO Learn Time"), "entropy": med("Policy Entropy"),
+                             "skill_rating": reports[-1].get("Skill Rating 3v3")},
+               "gpu_launches": int(L.engine.launch_count + L.collector.launch_count + L.ppo.dev.launch_count)}
         emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -513,7 +581,11 @@ def main():
     ap.add_argument("--team", type=int, default=1, help="players per team (sweep only: the headline metric is quoted on 1v1)")
     ap.add_argument("--padded-obs", action="store_true", help="DefaultOBSPadded(3) (sweep only: BASELINE configs[2])")
     ap.add_argument("--zero-sum", action="store_true", help="ZeroSumReward(teamSpirit 0.3) around the reward set (sweep only)")
+    ap.add_argument("--total-arenas", type=int, default=0, help="STRONG scaling: a fixed pool split evenly over the GPUs (overrides --arenas)")
+    ap.add_argument("--cfg4", action="store_true", help="BASELINE configs[3]: 3v3, host StateSetter, ELO skill tracking, collection during learn, "
+                    "data-parallel PPO update (NCCL all-reduce): whole Learner iterations instead of the collection loop")
     args = ap.parse_args()
+    args.strong = args.total_arenas > 0
     global TEAM, METRIC, PADDED_OBS, ZERO_SUM
     PADDED_OBS, ZERO_SUM = args.padded_obs, args.zero_sum
     if args.team != 1:
@@ -523,8 +595,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.total_arenas:
+        if args.total_arenas % world:
+            raise SystemExit("--total-arenas must be a multiple of the GPU count")
+        args.arenas = args.total_arenas // world
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.cfg4:
+        run_cfg4(args, rank, local_rank, world)
     else:
         run_ours(args, rank, local_rank, world)
 

@@ -31,6 +31,7 @@ static int fail(int code, const std::string& msg) { g_last_error = msg; return c
         if (_e != cudaSuccess) return fail(RLG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
     } while (0)
 
+constexpr int kHbOffloadDefault = 0;  // see HbJob below: measured 3 % slower with the ball warp taking the hitbox passes (profiles/r02k_ab.txt)
 struct rlg_engine {
     rlg_engine_cfg cfgIn;
     SimCfg cfg;
@@ -57,6 +58,7 @@ struct rlg_engine {
     int32_t* dResetIds = nullptr; float* dResetObs = nullptr;  // device views of the two mapped host buffers
     unsigned char* epa = nullptr;  // [block] full-size penetration-depth workspaces of the role kernel
     void* hbJobs = nullptr;        // [arena][car] HbJob records of the role kernel
+    int hbOffload = kHbOffloadDefault;
     float* metrics = nullptr;    // [kMetricWords][A]: stepTotal, stepCount (u32), epTotal, epCount (u32), curEpRew, totalSteps (u32)
     int xwords = 0, stride = 0, scratchSlots = 0;
     int arenasPerBlock = 32, groupsPerBlock = 1;
@@ -215,6 +217,7 @@ struct RolesArgs {
     float* metrics;  // GameInst reward metrics, word-transposed [kMetricWords][A] (nullptr: not tracked)
     unsigned char* epa;  // [block][kEpaFullBytes] full-size penetration-depth workspaces (rl_epa.h), used when a warp's small one overflows
     struct HbJob* hbJobs;  // [arena][car] hitbox-narrowphase hand-over records
+    int hbOffload;         // cars whose hitbox-mesh narrowphase the ball warp runs (0: every car its own, no extra barrier)
 };
 constexpr int kMetricWords = 6;
 
@@ -404,7 +407,7 @@ struct HbJob {
     V3 wcNormal;
     MeshCands cands;
 };
-constexpr int kHbOffload = 3;
+
 
 // Pass 2: hitbox vs the pre-filtered candidate triangles -> the car's world contact slots.
 __device__ __forceinline__ void box_meshes_warp(CollideCtx& cx, ContactSink& cw, const MeshSet& ms, const HbJob& w, int ci, float breaking,
@@ -557,9 +560,9 @@ __global__ void __maxnreg__(168) k_roles(const __grid_constant__ RolesArgs g) {
             }
         }
         PT_WORK(2);
-        SYNC_GROUP();  // B1b
+        const int nOff = P < g.hbOffload ? P : g.hbOffload;
+        if (nOff > 0) SYNC_GROUP();  // B1b
         // P1b: the cars' vehicle / control model, car-ball, hitbox-plane | the hitbox-mesh pairs of the first cars on the ball warp
-        const int nOff = P < kHbOffload ? P : kHbOffload;
         if (role == 0) {
             for (int c = 0; c < nOff; c++) {
                 CollideCtx cx; ContactSink cw;
@@ -807,6 +810,7 @@ int rlg_engine_create(const rlg_engine_cfg* cfg, rlg_engine** out) {
         e->arenasPerBlock = apb;
         e->groupsPerBlock = (apb + 31) / 32;
     }
+    if (const char* ev = getenv("RLG_HB_OFFLOAD")) e->hbOffload = atoi(ev);  // profiling A/B only
     if (const char* ev = getenv("RLG_BARRIER_MODE")) e->barMode = atoi(ev);
     if (const char* ev = getenv("RLG_ASYNC_LOAD")) e->asyncLoad = atoi(ev);
     if (e->groupsPerBlock > 15) e->barMode = 0;  // 16 hardware barriers per block
@@ -904,6 +908,7 @@ static RolesArgs roles_args(rlg_engine* e) {
     g.k = car_consts(e->cfg.carPreset); g.thr = contact_thresholds(g.k);
     g.epa = e->epa;
     g.hbJobs = reinterpret_cast<HbJob*>(e->hbJobs);
+    g.hbOffload = e->hbOffload;
     return g;
 }
 

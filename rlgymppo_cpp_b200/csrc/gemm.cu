@@ -330,45 +330,90 @@ __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tma(const __grid_constant
     mbar_wait(barDone, 0);
     tc_fence_after();
 
-    // epilogue (as k_gemm_tf32)
+    // epilogue: thread t owns accumulator row t & 127 (TMEM lane), the two warpgroups take alternate 32-column chunks.  Per chunk the
+    // row's 32 mask values (ReLU backward) are fetched as eight independent 16-byte loads BEFORE the accumulator load is waited
+    // for, the bias comes in as float4, C goes out as 16-byte stores and the transposed copy as 32 stores that are coalesced across
+    // the warp (consecutive lanes = consecutive rows = consecutive addresses of one C^T row).
     const int r = t & (kGM - 1), half = t >> 7;
     const uint32_t tmemLane = tmemBase + ((uint32_t)((warp & 3) * 32) << 16);
     const int row = m0 + r;
+    const bool rowOk = row < g.M;
     const bool addBias = g.bias != nullptr && blockIdx.z == 0;
+    const bool vecMask = g.mask != nullptr && (g.ldm & 3) == 0 && (((uintptr_t)g.mask) & 15) == 0;
+    const bool vecBias = addBias && (((uintptr_t)g.bias) & 15) == 0;
     for (int c = half; c * 32 < NT; c += 2) {
         uint32_t v[32];
         tc_ld32(tmemLane + c * 32, v);
-        tc_wait_ld();
-        if (row < g.M) {
-            float* dst = g.C + (size_t)row * g.ldc + n0 + c * 32;
+        const int nc = n0 + c * 32;                                  // first global column of the chunk
+        const int valid = nValid - c * 32 < 32 ? nValid - c * 32 : 32;  // columns of the chunk inside N
+        float4 mk[8];
+        if (g.mask && rowOk) {
+            const float* mrow = g.mask + (size_t)row * g.ldm + nc;
 #pragma unroll
             for (int q = 0; q < 8; q++) {
-                const int n = c * 32 + 4 * q;
-                if (n >= nValid) break;
-                float o[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    o[i] = __uint_as_float(v[4 * q + i]);
-                    if (addBias && n + i < nValid) o[i] += __ldg(g.bias + n0 + n + i);
-                    if (g.flags & RLG_GEMM_RELU) o[i] = fmaxf(o[i], 0.f);
-                    if (g.mask && n + i < nValid && !(__ldg(g.mask + (size_t)row * g.ldm + n0 + n + i) > 0.f)) o[i] = 0.f;
+                if (vecMask && 4 * q + 3 < valid) mk[q] = __ldg(reinterpret_cast<const float4*>(mrow + 4 * q));
+                else {
+                    mk[q].x = 4 * q + 0 < valid ? __ldg(mrow + 4 * q + 0) : 1.f; mk[q].y = 4 * q + 1 < valid ? __ldg(mrow + 4 * q + 1) : 1.f;
+                    mk[q].z = 4 * q + 2 < valid ? __ldg(mrow + 4 * q + 2) : 1.f; mk[q].w = 4 * q + 3 < valid ? __ldg(mrow + 4 * q + 3) : 1.f;
                 }
-                if (g.Ct) {
+            }
+        }
+        tc_wait_ld();
+        if (!rowOk) continue;
+        float o[32];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) if (n + i < nValid) g.Ct[(size_t)(n0 + n + i) * g.ldct + row] = o[i];
+        for (int q = 0; q < 8; q++) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (addBias) {
+                if (vecBias && 4 * q + 3 < valid) b = __ldg(reinterpret_cast<const float4*>(g.bias + nc + 4 * q));
+                else {
+                    if (4 * q + 0 < valid) b.x = __ldg(g.bias + nc + 4 * q + 0);
+                    if (4 * q + 1 < valid) b.y = __ldg(g.bias + nc + 4 * q + 1);
+                    if (4 * q + 2 < valid) b.z = __ldg(g.bias + nc + 4 * q + 2);
+                    if (4 * q + 3 < valid) b.w = __ldg(g.bias + nc + 4 * q + 3);
                 }
-                if (g.flags & RLG_GEMM_ATOMIC) {
-                    if (n + 3 < nValid && (g.flags & RLG_GEMM_SCALAR_STORE) == 0) {
-                        atomicAdd(reinterpret_cast<float4*>(dst + 4 * q), make_float4(o[0], o[1], o[2], o[3]));  // one 16-byte reduction
-                    } else {
+            }
+            o[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + b.x; o[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + b.y;
+            o[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + b.z; o[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + b.w;
+        }
+        if (g.flags & RLG_GEMM_RELU) {
 #pragma unroll
-                        for (int i = 0; i < 4; i++) if (n + i < nValid) atomicAdd(dst + 4 * q + i, o[i]);
-                    }
-                } else if (n + 3 < nValid && (g.flags & (RLG_GEMM_ACCUMULATE | RLG_GEMM_SCALAR_STORE)) == 0) {
-                    *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
+            for (int i = 0; i < 32; i++) o[i] = fmaxf(o[i], 0.f);
+        }
+        if (g.mask) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                if (!(mk[q].x > 0.f)) o[4 * q + 0] = 0.f;
+                if (!(mk[q].y > 0.f)) o[4 * q + 1] = 0.f;
+                if (!(mk[q].z > 0.f)) o[4 * q + 2] = 0.f;
+                if (!(mk[q].w > 0.f)) o[4 * q + 3] = 0.f;
+            }
+        }
+        if (g.Ct) {
+            float* ct = g.Ct + (size_t)nc * g.ldct + row;
+#pragma unroll
+            for (int i = 0; i < 32; i++) if (i < valid) ct[(size_t)i * g.ldct] = o[i];
+        }
+        float* dst = g.C + (size_t)row * g.ldc + nc;
+        if (g.flags & RLG_GEMM_ATOMIC) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                if (4 * q + 3 < valid && (g.flags & RLG_GEMM_SCALAR_STORE) == 0) {
+                    atomicAdd(reinterpret_cast<float4*>(dst + 4 * q), make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));  // one 16-byte reduction
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 4; i++) if (n + i < nValid) dst[4 * q + i] = ((g.flags & RLG_GEMM_ACCUMULATE) ? dst[4 * q + i] : 0.f) + o[i];
+                    for (int i = 0; i < 4; i++) if (4 * q + i < valid) atomicAdd(dst + 4 * q + i, o[4 * q + i]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                if (4 * q + 3 < valid && (g.flags & (RLG_GEMM_ACCUMULATE | RLG_GEMM_SCALAR_STORE)) == 0) {
+                    *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        if (4 * q + i < valid) dst[4 * q + i] = ((g.flags & RLG_GEMM_ACCUMULATE) ? dst[4 * q + i] : 0.f) + o[4 * q + i];
                 }
             }
         }

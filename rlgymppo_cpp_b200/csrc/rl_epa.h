@@ -130,7 +130,23 @@ RL_HDI void with_epa_ws(const EpaCtx* ctx, F f) {
 #if defined(RLG_NO_EPA)  // A/B builds only: what the penetration-depth search costs
     (void)ctx; (void)f;
 #elif defined(__CUDA_ARCH__)
-    if (epa_locked(ctx->smallLock, [&]() { EpaWs w = epa_ws_view(ctx->smallMem, kEpaSmallVerts, kEpaSmallFaces); return f(w); })) return;
+    // 1. the block's shared-memory workspace when nobody holds it — no waiting: a car that digs into the mesh overlaps several
+    //    triangles at once, its pairs sit on neighbouring lanes of one warp, and lanes queueing for one workspace would run their
+    //    searches one after the other with the waiting lanes spinning next to the working one (measured: 100 k cycles per call);
+    // 2. otherwise a private small workspace on the lane's own stack: those lanes search side by side in the same code;
+    // 3. the full-size workspace of the block (global memory, behind its lock) in the rare case the small capacity runs out.
+    bool ok = false;
+    if (atomicCAS(ctx->smallLock, 0, 1) == 0) {
+        EpaWs w = epa_ws_view(ctx->smallMem, kEpaSmallVerts, kEpaSmallFaces);
+        ok = f(w);
+        __threadfence_block();
+        atomicExch(ctx->smallLock, 0);
+    } else {
+        alignas(16) unsigned char mem[(epa_ws_bytes(kEpaSmallVerts, kEpaSmallFaces) + 15) / 16 * 16];
+        EpaWs w = epa_ws_view(mem, kEpaSmallVerts, kEpaSmallFaces);
+        ok = f(w);
+    }
+    if (ok) return;
     epa_locked(ctx->fullLock, [&]() { EpaWs w = epa_ws_view(ctx->fullMem, kEpaMaxVerts, kEpaMaxFaces); return f(w); });
 #else
     (void)ctx;  // host test build: the same two-step protocol on local storage
