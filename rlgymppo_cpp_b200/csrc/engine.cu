@@ -720,9 +720,10 @@ int rlg_engine_destroy(rlg_engine* e) {
     cudaSetDevice(e->device);
 #ifdef RLG_EPA_TIMING
     {   // diagnostic build: time spent in the penetration-depth search
-        unsigned long long t[2] = {0, 0};
+        unsigned long long t[8] = {0};
         cudaMemcpyFromSymbol(t, g_epa_timing, sizeof(t));
         fprintf(stderr, "[epa timing] calls %llu cycles %llu (%.0f per call), role launches %d\n", t[1], t[0], t[1] ? (double)t[0] / (double)t[1] : 0.0, (int)e->launches);
+        fprintf(stderr, "[epa timing] guesses %llu; GJK: %llu evaluations, %llu iterations, %llu cycles; EPA: %llu iterations, %llu cycles\n", t[7], t[3], t[4], t[2], t[6], t[5]);
     }
 #endif
 #ifdef RLG_PHASE_TIMING

@@ -27,6 +27,18 @@ namespace rl {
 static long g_dbg_epa_overflows = 0;
 static long g_dbg_epa_calls = 0, g_dbg_epa_iters = 0, g_dbg_epa_maxface = 0, g_dbg_epa_maxsv = 0, g_dbg_epa_hist[8] = {0};  // host debugging only
 #endif
+#if defined(RLG_EPA_TIMING) && defined(__CUDACC__)
+// diagnostic builds: [0] cycles inside the search, [1] calls, [2] cycles in GJK::Evaluate, [3] GJK evaluations, [4] GJK iterations,
+// [5] cycles in EPA::Evaluate, [6] EPA iterations, [7] guesses tried
+static __device__ unsigned long long g_epa_timing[8];
+#define EPA_T0() const long long epaT0_ = clock64()
+#define EPA_T(i) atomicAdd(&g_epa_timing[i], (unsigned long long)(clock64() - epaT0_))
+#define EPA_N(i, n) atomicAdd(&g_epa_timing[i], (unsigned long long)(n))
+#else
+#define EPA_T0() do {} while (0)
+#define EPA_T(i) do {} while (0)
+#define EPA_N(i, n) do {} while (0)
+#endif
 constexpr int kEpaMaxVerts = 128, kEpaMaxFaces = 256, kEpaMaxIter = 255, kGjk2MaxIter = 128;
 constexpr float kGjk2Accuracy = 1e-4f, kGjk2MinDist = 1e-4f, kGjk2DupEps = 1e-4f;
 constexpr float kEpaAccuracy = 1e-4f, kEpaPlaneEps = 1e-5f;
@@ -108,6 +120,10 @@ struct Mink {
     RL_HDI V3 to_world(V3 p) const { return rotA * p + originA; }
 };
 
+// (Measured, profiles/r02o_epa_outofline.txt: the search costs ~104 k cycles per call, 50-90 % of its stall samples are instruction
+// fetch — one lane running cold, branchy code pays every fetch alone.  Making every helper with several call sites a real function
+// shrank k_roles from 907 to 737 KB but made a call SLOWER (117 k cycles, k_roles 1.26 -> 1.32 ms): the calls spill the live state
+// of a 168-register kernel.  So the helpers stay inlined.)
 // One evaluation at a time per workspace.  f(ws) returns false when the workspace ran out of room (small workspace only).
 // Every entry of a workspace is written before it is read within one evaluation, so nothing of the previous holder is consumed.
 #if defined(__CUDA_ARCH__)
@@ -272,6 +288,9 @@ template <class Sh>
 RL_HD inline int gjk2_evaluate(Gjk2& g, EpaSV* store, const Sh& sh, V3 guess) {
     int iterations = 0;
     float sqdist = 0, alpha = 0;
+#if defined(__CUDA_ARCH__)
+    EPA_T0();
+#endif
     V3 lastw[4];
     int clastw = 0;
     for (int i = 0; i < 4; i++) g.freeList[i] = (uint8_t)i;
@@ -329,6 +348,9 @@ RL_HD inline int gjk2_evaluate(Gjk2& g, EpaSV* store, const Sh& sh, V3 guess) {
     } while (g.status == 0);
     if (g.status == 0) g.distance = len(g.ray);
     else if (g.status == 1) g.distance = 0;
+#if defined(__CUDA_ARCH__)
+    EPA_T(2); EPA_N(3, 1); EPA_N(4, iterations);
+#endif
     return g.status;
 }
 
@@ -657,7 +679,13 @@ RL_HD inline bool epa_penetration(const EpaWs& ws, Sh& sh, V3 guess, PenResult& 
     if (gs == 1) {
         Epa ep;
         epa_init(ep, ws);
+#if defined(__CUDA_ARCH__)
+        EPA_T0();
+#endif
         const int es = epa_evaluate(ep, g, sh, -guess);
+#if defined(__CUDA_ARCH__)
+        EPA_T(5); EPA_N(6, ep.nextsv);
+#endif
         if (ep.overflow) { overflow = true; return false; }
 #if defined(RL_DEBUG_CONTACTS) && !defined(__CUDA_ARCH__)
         if (ep.nextsv > g_dbg_epa_maxsv) g_dbg_epa_maxsv = ep.nextsv;
@@ -709,6 +737,9 @@ RL_HD inline int calc_pen_depth(const EpaWs& ws, Sh& sh, V3 originA, V3 originB,
                            V3(1, 1, 0), V3(1, 1, 1), V3(0, 1, 1), V3(1, 0, 1)};
     for (int i = 0; i < 9; i++) {
         bool overflow = false;
+#if defined(__CUDA_ARCH__)
+        EPA_N(7, 1);
+#endif
         if (epa_penetration(ws, sh, guesses[i], r, overflow)) return 1;
         if (overflow) return -2;
         if (epa_distance(ws, sh, guesses[i], r)) return 0;

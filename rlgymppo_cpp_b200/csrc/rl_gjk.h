@@ -268,9 +268,6 @@ struct ConvexB {
 #if defined(RL_DEBUG_CONTACTS) && !defined(__CUDA_ARCH__)
 static long g_dbg_pen_kind[2] = {0, 0};  // host debugging: calls with overlapping cores / with a degenerate-small GJK distance
 #endif
-#if defined(RLG_EPA_TIMING) && defined(__CUDACC__)
-static __device__ unsigned long long g_epa_timing[2];  // diagnostic builds: cycles inside the search, calls
-#endif
 // btGjkPairDetector.cpp:860-940: the penetration-depth solver and the "only replace when deeper / closer" rules.  Rare and
 // long: out of line, one copy.  Updates (isValid, normalInB, pointOnB, distance) in place.
 RL_HD RL_NOINLINE inline void pair_penetration(const EpaCtx* ws, const M3& rot, V3 cA, V3 oB, V3 coreHalf, float marginA, float marginB, const ConvexB& shapeB,
