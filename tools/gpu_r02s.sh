@@ -1,0 +1,17 @@
+#!/bin/bash
+# r02s: deferred searches with the producers' hardware barrier: parity, A/B, phase profile
+mkdir -p gpurun_out
+tag=${1:-r02s}
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "single_tick or compiled_reference or many_arenas or sharded" > gpurun_out/pytest_$tag.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_$tag.log
+grep -E "passed|failed|^FAILED|rc=|^E  " gpurun_out/pytest_$tag.log | head -20 | cut -c1-300
+rm -f gpurun_out/${tag}_ab.txt gpurun_out/${tag}_phase_prof.txt
+for i in 1 2; do for d in 0 1; do
+RLG_EPA_DEFER=$d timeout 300 python bench.py --steps 60 --warmup 40 --no-cpu-baseline --no-ppo > gpurun_out/ab.json 2> gpurun_out/ab.err || tail -3 gpurun_out/ab.err
+python -c "
+import json; b=json.load(open('gpurun_out/ab.json')); print('$tag defer=$d', 'value %.3fM' % (b['value']/1e6), 'k_roles %.3f ms' % b['roofline']['launch_ms'], 'e2e %.3fM' % (b['e2e']['value']/1e6))" | tee -a gpurun_out/${tag}_ab.txt
+done; done
+for d in 1; do
+RLG_EPA_DEFER=$d RLG_B200_LIB=$PWD/build_ab/lib_pt.so RLG_PHASE_DUMP=$PWD/gpurun_out/phase_prof_$d.bin timeout 300 python bench.py --steps 40 --warmup 40 --no-cpu-baseline --no-ppo > gpurun_out/pt.json 2> gpurun_out/pt.err
+echo "== defer=$d" | tee -a gpurun_out/${tag}_phase_prof.txt
+python tools/phase_prof.py gpurun_out/phase_prof_$d.bin | tee -a gpurun_out/${tag}_phase_prof.txt | head -12
+done
