@@ -70,7 +70,32 @@ struct rlg_engine {
     int32_t* xIds = nullptr; rlg_car_state* xCars = nullptr; rlg_ball_state* xBalls = nullptr; rlg_gym_state* xGym = nullptr; rlg_gym_player* xPlayers = nullptr;
     int xCap = 0;
     cudaEvent_t evExport = nullptr;
+    // rlg_engine_set_state / reset masks: one device staging buffer, grown on demand (no allocation per call); evStage orders its
+    // reuse after the last kernel that read it, whatever stream that ran on
+    unsigned char* stage = nullptr; size_t stageCap = 0; cudaEvent_t evStage = nullptr; bool stageBusy = false;
 };
+
+// the staging buffer, at least `bytes` long, safe to overwrite from stream s
+static int stage_acquire(rlg_engine* e, size_t bytes, cudaStream_t s, unsigned char** out) {
+    if (!e->evStage) CK(cudaEventCreateWithFlags(&e->evStage, cudaEventDisableTiming));
+    if (bytes > e->stageCap) {
+        if (e->stageBusy) CK(cudaEventSynchronize(e->evStage));
+        e->stageBusy = false;
+        if (e->stage) CK(cudaFree(e->stage));
+        e->stage = nullptr; e->stageCap = 0;
+        size_t cap = bytes < (1u << 20) ? (1u << 20) : bytes + bytes / 2;
+        CK(cudaMalloc(&e->stage, cap));
+        e->stageCap = cap;
+    }
+    if (e->stageBusy) CK(cudaStreamWaitEvent(s, e->evStage, 0));
+    *out = e->stage;
+    return RLG_OK;
+}
+static int stage_release(rlg_engine* e, cudaStream_t s) {
+    CK(cudaEventRecord(e->evStage, s));
+    e->stageBusy = true;
+    return RLG_OK;
+}
 
 // ---- state movement -----------------------------------------------------------------------------
 __device__ __forceinline__ void load_arena(ArenaS& s, const uint32_t* __restrict__ buf, int A, int a, int nwords) {
@@ -743,7 +768,8 @@ int rlg_engine_destroy(rlg_engine* e) {
         cudaFree(e->prof); cudaFree(e->prof2);
     }
 #endif
-    cudaFree(e->scratch); cudaFree(e->metrics); cudaFree(e->epa); cudaFree(e->hbJobs);
+    cudaFree(e->scratch); cudaFree(e->metrics); cudaFree(e->epa); cudaFree(e->hbJobs); cudaFree(e->stage);
+    if (e->evStage) cudaEventDestroy(e->evStage);
     cudaFree(e->xIds); cudaFree(e->xCars); cudaFree(e->xBalls); cudaFree(e->xGym); cudaFree(e->xPlayers);
     if (e->evExport) cudaEventDestroy(e->evExport);
     cudaFree(e->state); cudaFree(e->tables); cudaFree(e->obs); cudaFree(e->reward); cudaFree(e->done); cudaFree(e->actions);
@@ -923,13 +949,13 @@ static int do_reset(rlg_engine* e, const uint8_t* mask_host, void* stream, int u
     cudaStream_t s = pick(e, stream);
     uint8_t* dmask = nullptr;
     if (mask_host) {
-        CK(cudaMallocAsync(&dmask, e->cfg.numArenas, s));
+        if (int rc = stage_acquire(e, (size_t)e->cfg.numArenas, s, &dmask)) return rc;
         CK(cudaMemcpyAsync(dmask, mask_host, e->cfg.numArenas, cudaMemcpyHostToDevice, s));
     }
     k_reset<<<grid_for(e->cfg.numArenas, 64), 64, 0, s>>>(e->state, e->cfg, e->nwords, e->tables, dmask, useSetter, obs_out ? obs_out : e->obs);
     e->launches++;
     CK(cudaGetLastError());
-    if (dmask) CK(cudaFreeAsync(dmask, s));
+    if (dmask) return stage_release(e, s);
     return RLG_OK;
 }
 int rlg_engine_reset(rlg_engine* e, const uint8_t* mask_host, void* stream) { return do_reset(e, mask_host, stream, 1); }
@@ -962,20 +988,22 @@ int rlg_engine_set_state(rlg_engine* e, const int32_t* ids, int n, const rlg_car
     cudaStream_t s = e->stream;
     const int P = e->cfg.numCars;
     int32_t* dIds = nullptr; rlg_car_state* dCars = nullptr; rlg_ball_state* dBalls = nullptr; rlg_pad_state* dPads = nullptr; int64_t* dTicks = nullptr;
-    CK(cudaMallocAsync(&dIds, (size_t)n * 4, s));
+    // one staging buffer for the five pieces (16-byte aligned), no allocation per call
+    auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    const size_t bIds = up16((size_t)n * 4), bCars = cars ? up16((size_t)n * P * sizeof(rlg_car_state)) : 0, bBalls = balls ? up16((size_t)n * sizeof(rlg_ball_state)) : 0,
+                 bPads = pads ? up16((size_t)n * kNumPads * sizeof(rlg_pad_state)) : 0, bTicks = ticks ? up16((size_t)n * 8) : 0;
+    unsigned char* st = nullptr;
+    if (int rc = stage_acquire(e, bIds + bCars + bBalls + bPads + bTicks, s, &st)) return rc;
+    dIds = reinterpret_cast<int32_t*>(st); st += bIds;
     CK(cudaMemcpyAsync(dIds, ids, (size_t)n * 4, cudaMemcpyHostToDevice, s));
-    if (cars) { CK(cudaMallocAsync(&dCars, (size_t)n * P * sizeof(rlg_car_state), s)); CK(cudaMemcpyAsync(dCars, cars, (size_t)n * P * sizeof(rlg_car_state), cudaMemcpyHostToDevice, s)); }
-    if (balls) { CK(cudaMallocAsync(&dBalls, (size_t)n * sizeof(rlg_ball_state), s)); CK(cudaMemcpyAsync(dBalls, balls, (size_t)n * sizeof(rlg_ball_state), cudaMemcpyHostToDevice, s)); }
-    if (pads) { CK(cudaMallocAsync(&dPads, (size_t)n * kNumPads * sizeof(rlg_pad_state), s)); CK(cudaMemcpyAsync(dPads, pads, (size_t)n * kNumPads * sizeof(rlg_pad_state), cudaMemcpyHostToDevice, s)); }
-    if (ticks) { CK(cudaMallocAsync(&dTicks, (size_t)n * 8, s)); CK(cudaMemcpyAsync(dTicks, ticks, (size_t)n * 8, cudaMemcpyHostToDevice, s)); }
+    if (cars) { dCars = reinterpret_cast<rlg_car_state*>(st); st += bCars; CK(cudaMemcpyAsync(dCars, cars, (size_t)n * P * sizeof(rlg_car_state), cudaMemcpyHostToDevice, s)); }
+    if (balls) { dBalls = reinterpret_cast<rlg_ball_state*>(st); st += bBalls; CK(cudaMemcpyAsync(dBalls, balls, (size_t)n * sizeof(rlg_ball_state), cudaMemcpyHostToDevice, s)); }
+    if (pads) { dPads = reinterpret_cast<rlg_pad_state*>(st); st += bPads; CK(cudaMemcpyAsync(dPads, pads, (size_t)n * kNumPads * sizeof(rlg_pad_state), cudaMemcpyHostToDevice, s)); }
+    if (ticks) { dTicks = reinterpret_cast<int64_t*>(st); st += bTicks; CK(cudaMemcpyAsync(dTicks, ticks, (size_t)n * 8, cudaMemcpyHostToDevice, s)); }
     k_set_state<<<grid_for(n, 64), 64, 0, s>>>(e->state, e->cfg, e->nwords, dIds, n, dCars, dBalls, dPads, dTicks);
     e->launches++;
     CK(cudaGetLastError());
-    CK(cudaFreeAsync(dIds, s));
-    if (dCars) CK(cudaFreeAsync(dCars, s));
-    if (dBalls) CK(cudaFreeAsync(dBalls, s));
-    if (dPads) CK(cudaFreeAsync(dPads, s));
-    if (dTicks) CK(cudaFreeAsync(dTicks, s));
+    if (int rc = stage_release(e, s)) return rc;
     CK(cudaStreamSynchronize(s));
     return RLG_OK;
 }
