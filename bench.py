@@ -270,7 +270,6 @@ def run_ours(args, rank, local_rank, world):
     P, OBS = e.P, e.obs_size
     col = collector.Collector(e, policy_hidden=(256, 256, 256), critic_hidden=(256, 256, 256), max_steps=T, seed=123)
     col.init_default(seed=123)  # random-init weights of the examplemain architecture (256x256x256), same on every rank
-    col.enable_timing(True)
     ext = torch.cuda.ExternalStream(e.stream, device=torch.device("cuda", local_rank))
     K, W = args.steps, args.warmup
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
@@ -313,12 +312,26 @@ def run_ours(args, rank, local_rank, world):
             starts[i].record(ext)
             one_iteration()
             ends[i].record(ext)
-        sm, sn, im, inn = col.kernel_times()  # waits for this iteration's events
-        step_ms += sm; step_n += sn; infer_ms += im; infer_n += inn
+        torch.cuda.synchronize()
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
     launches = e.launch_count + col.launch_count - launches0
+    # per-launch durations (roofline legs): the same steps once more with a CUDA event around every launch on the engine's stream.  Kept out
+    # of the timed region above because an event between two launches serialises them, and the collector overlaps each inference with
+    # the tail of the fused step before it (programmatic dependent launch + per-block ready flags, csrc/collector.cu launch_infer)
+    K_t = min(K, 50)
+    col.enable_timing(True)
+    for i in range(K_t):
+        if not args.no_l2_flush:
+            flush.fill_(i & 255)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(ext):
+            one_iteration()
+        sm, sn, im, inn = col.kernel_times()  # waits for this iteration's events
+        step_ms += sm; step_n += sn; infer_ms += im; infer_n += inn
+    col.enable_timing(False)
+    barrier()
+    clocks = sampler.stop()
     ms = [s.elapsed_time(t) for s, t in zip(starts, ends)]
     total_ms = torch.tensor([sum(ms)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -405,7 +418,7 @@ def run_ours(args, rank, local_rank, world):
         # dense part: policy fwd + critic fwd per sample, every env-step, + one critic pass for the bootstrap
         fl_pol = 2 * (OBS * 256 + 2 * 256 * 256 + 256 * 90)
         fl_cri = 2 * (OBS * 256 + 2 * 256 * 256 + 256 * 1)
-        mlp_flops = A * P * (T * (fl_pol + fl_cri) + fl_cri) * K
+        mlp_flops = A * P * (T * (fl_pol + fl_cri) + fl_cri) * K_t
         mlp_tflops = mlp_flops / (infer_ms * 1e-3) / 1e12 if infer_ms > 0 else None
         try:
             tf_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]) / 2  # TF32 = half the bf16 rate
@@ -430,10 +443,12 @@ def run_ours(args, rank, local_rank, world):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "k_roles (fused Gym::Step)", "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": k_step_ms, "launches_timed": step_n,
-                         "share_of_step": step_ms / total_ms, "peak_source": peak_src},
+                         "share_of_step": (step_ms / K_t) / ms_per_step, "peak_source": peak_src,
+                         "timed_in": f"a second pass of {K_t} bench steps with an event around every launch (launches serialised); in the timed region each "
+                                     "inference overlaps the tail of the step before it, so the shares may add up to more than 1"},
             "roofline_mlp": {"bound": "tensor", "achieved": mlp_tflops, "peak": tf_peak, "unit": "TFLOP/s",
                              "frac": (mlp_tflops / tf_peak) if mlp_tflops else None, "kernel": "k_mlp_infer",
-                             "launch_ms": infer_ms / max(infer_n, 1), "launches_timed": infer_n, "share_of_step": infer_ms / total_ms,
+                             "launch_ms": infer_ms / max(infer_n, 1), "launches_timed": infer_n, "share_of_step": (infer_ms / K_t) / ms_per_step,
                              "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 rate)"},
             "wall_s_timed_region": t_wall,
         }

@@ -312,6 +312,13 @@ int rlg_engine_sync(rlg_engine* e);
  * trajectory ring (replaces GameTrajectory::AppendSingleStep, P/private/RLGymPPO_CPP/Threading/GameTrajectory.cpp:54-79). */
 int rlg_engine_step_to(rlg_engine* e, const int32_t* action_idx, float* obs_out, float* reward_out, uint8_t* done_out,
                        void* stream);
+/* Per-block completion flags of the LAST rlg_engine_step / _step_to launch, for a consumer kernel that wants to start on the
+ * outputs of the arena blocks that are done while the slowest blocks of the step are still running (the collector's inference
+ * kernel, launched as a programmatic dependent of the step): block b of the step's grid holds arenas
+ * [b * arenas_per_block, (b + 1) * arenas_per_block) and stores flags_dev[b] = seq (device scope, after its obs / reward / done /
+ * state stores) when it is finished.  flags_dev is NULL when the engine does not publish flags (per-group barrier modes).
+ * No reference counterpart: the reference's agents wait for Gym::Step to return (ThreadAgent.cpp:100-140). */
+int rlg_engine_step_ready(rlg_engine* e, const uint32_t** flags_dev, uint32_t* seq, int* arenas_per_block);
 
 /* ---- host-plugin path: user-defined OBSBuilder / RewardFunction / TerminalCondition / StepCallback -------------------------------
  * (G/Utils/OBSBuilders/OBSBuilder.h:10-15, RewardFunctions/RewardFunction.h:9-35, TerminalConditions/TerminalCondition.h:7-8,

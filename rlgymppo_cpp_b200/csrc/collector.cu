@@ -67,6 +67,8 @@ struct InferArgs {
     int32_t deterministic;
     float temperature;
     int32_t runNet[2];
+    // overlap with the step that produces obs (launched as its programmatic dependent): wait for the role blocks that own this tile's rows
+    const uint32_t* ready; uint32_t readySeq; int32_t arenasPerBlock, playersPerArena;
 };
 
 // byte offset of element (r, kk) inside one canonical (R x 32) tf32 block: core matrix = 8 rows x 16 B,
@@ -203,6 +205,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_infer(const InferArgs a) {
     loadIt.skip_to_valid(a);
     uint32_t nLoad = 0, nUse = 0, donePhase = 0;
 
+    if (a.ready) {
+        // Launched as the programmatic dependent of the fused step that writes obs: this CTA got the SM of a role block that has finished
+        // while the step's slowest blocks are still running.  Its rows belong to the arenas of one or two role blocks: wait for their flags.
+        // (Letting a CTA take ANY complete tile instead of its own was measured and is no faster: profiles/r02x_collect_overlap_ab.txt.)
+        if (t == 0) {
+            const int lastRow = (row0 + kTileM < a.nRows ? row0 + kTileM : a.nRows) - 1;
+            const int b0 = (row0 / a.playersPerArena) / a.arenasPerBlock, b1 = (lastRow / a.playersPerArena) / a.arenasPerBlock;
+            for (int b = b0; b <= b1; b++) {
+                const volatile uint32_t* f = a.ready + b;
+                for (unsigned spin = 0; *f != a.readySeq; spin++) {
+                    __nanosleep(200);
+                    if (spin > (1u << 24)) __trap();  // seconds: the producer is gone
+                }
+            }
+            __threadfence();
+        }
+        __syncthreads();
+    }
     for (int net = 0; net < 2; net++) {
         if (!a.runNet[net]) continue;
         const MlpNet& N = a.net[net];
@@ -218,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_infer(const InferArgs a) {
                     int idx = idx0 + u * kThreads;
                     int rr = idx / kPad0, k = idx - rr * kPad0;
                     int gr = row0 + rr;
-                    v[u] = (idx < total && gr < a.nRows && k < a.obsDim) ? __ldg(a.obs + (size_t)gr * a.obsDim + k) : 0.f;
+                    v[u] = (idx < total && gr < a.nRows && k < a.obsDim) ? __ldcg(a.obs + (size_t)gr * a.obsDim + k) : 0.f;  // L2: the rows may have been written while this kernel was already running
                 }
 #pragma unroll
                 for (int u = 0; u < 8; u++) {
@@ -495,6 +515,7 @@ struct rlg_collector {
     std::vector<int32_t> hIds;
     // optional per-kernel timing of the last collect (CUDA events on the launching stream)
     bool timing = false;
+    bool overlap = true;  // inference after a fused step starts as the step's programmatic dependent (RLG_COLLECT_OVERLAP=0: A/B only)
     std::vector<cudaEvent_t> evStep, evInfer;  // pairs (start, end)
     int nStepEv = 0, nInferEv = 0;
 };
@@ -526,7 +547,8 @@ int fill_net(const rlg_collector* c, int net, MlpNet& out) {
     return RLG_OK;
 }
 
-int launch_infer(rlg_collector* c, const float* obs, int nRows, uint64_t counter, int32_t* action, float* logprob, float* value, cudaStream_t s) {
+int launch_infer(rlg_collector* c, const float* obs, int nRows, uint64_t counter, int32_t* action, float* logprob, float* value, cudaStream_t s,
+                 bool afterStep = false) {
     InferArgs a;
     memset(&a, 0, sizeof(a));
     a.runNet[0] = (action || logprob) ? 1 : 0;
@@ -538,6 +560,25 @@ int launch_infer(rlg_collector* c, const float* obs, int nRows, uint64_t counter
     a.seed = c->cfg.seed; a.counter = counter; a.rowBase = c->rowBase;
     a.deterministic = c->cfg.deterministic; a.temperature = c->cfg.temperature;
     int grid = (nRows + kTileM - 1) / kTileM;
+    if (afterStep && c->overlap && !c->timing && nRows == (int)c->N) {
+        // obs is the output of the fused step launched just before on this stream: start as its programmatic dependent and wait per tile
+        // for the role blocks that own the tile's rows, so that inference runs under the tail of the step (its slowest blocks)
+        const uint32_t* flags = nullptr; uint32_t seq = 0; int apb = 0;
+        if (rlg_engine_step_ready(c->e, &flags, &seq, &apb) != RLG_OK) return failc(RLG_ERR_STATE, rlg_last_error());
+        if (flags) {
+            a.ready = flags; a.readySeq = seq; a.arenasPerBlock = apb; a.playersPerArena = c->P;
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemTotal; cfg.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            CKC(cudaLaunchKernelEx(&cfg, k_mlp_infer, a));
+            c->launches++;
+            return RLG_OK;
+        }
+    }
     k_mlp_infer<<<grid, kThreads, kSmemTotal, s>>>(a);
     c->launches++;
     CKC(cudaGetLastError());
@@ -571,6 +612,7 @@ int rlg_collector_create(rlg_engine* e, const rlg_collector_cfg* cfg, rlg_collec
     rlg_collector* c = new (std::nothrow) rlg_collector();
     if (!c) return failc(RLG_ERR_INVALID, "out of host memory");
     c->e = e; c->cfg = *cfg;
+    if (const char* ev = getenv("RLG_COLLECT_OVERLAP")) c->overlap = atoi(ev) != 0;
     c->device = rlg_engine_device(e);
     c->A = rlg_engine_num_arenas(e); c->P = rlg_engine_num_players(e); c->N = c->A * c->P; c->obs = rlg_engine_obs_size(e);
     c->maxT = cfg->max_steps;
@@ -688,10 +730,11 @@ int rlg_collector_collect(rlg_collector* c, int n_steps, void* stream) {
         if ((int)v.size() <= n) { cudaEvent_t ev; cudaEventCreate(&ev); v.push_back(ev); }
         cudaEventRecord(v[n++], s);
     };
+    bool prevStepFused = false;  // the previous op on the stream is the fused step that wrote this inference's obs
     for (int t = 0; t < n_steps; t++) {
         mark(c->evInfer, c->nInferEv);
         int rc = launch_infer(c, c->dObs + (size_t)t * N * c->obs, (int)N, c->stepCounter, c->dAction + (size_t)t * N, c->dLogprob + (size_t)t * N,
-                              c->dValue + (size_t)t * N, s);
+                              c->dValue + (size_t)t * N, s, t > 0 && prevStepFused);
         mark(c->evInfer, c->nInferEv);
         if (rc != RLG_OK) return rc;
         mark(c->evStep, c->nStepEv);
@@ -705,6 +748,7 @@ int rlg_collector_collect(rlg_collector* c, int n_steps, void* stream) {
             mark(c->evStep, c->nStepEv);
             c->launches++;
             c->stepCounter++;
+            prevStepFused = false;
             continue;
         }
         if (rlg_engine_step_to(c->e, c->dAction + (size_t)t * N, c->dObs + (size_t)(t + 1) * N * c->obs, c->dReward + (size_t)t * N,
@@ -713,6 +757,7 @@ int rlg_collector_collect(rlg_collector* c, int n_steps, void* stream) {
         mark(c->evStep, c->nStepEv);
         c->launches++;
         c->stepCounter++;
+        prevStepFused = !c->resetHook;
         if (c->resetHook) {  // host StateSetter: re-set finished arenas before the next inference reads their obs
             c->hDone.resize(c->A);
             CKC(cudaMemcpyAsync(c->hDone.data(), c->dDone + (size_t)t * c->A, c->A, cudaMemcpyDeviceToHost, s));
@@ -724,7 +769,7 @@ int rlg_collector_collect(rlg_collector* c, int n_steps, void* stream) {
     }
     // value of the state after the last step (Learner.cpp:618-640 appends nextStates[count-1])
     mark(c->evInfer, c->nInferEv);
-    int rc = launch_infer(c, c->dObs + (size_t)n_steps * N * c->obs, (int)N, c->stepCounter, nullptr, nullptr, c->dValue + (size_t)n_steps * N, s);
+    int rc = launch_infer(c, c->dObs + (size_t)n_steps * N * c->obs, (int)N, c->stepCounter, nullptr, nullptr, c->dValue + (size_t)n_steps * N, s, prevStepFused);
     mark(c->evInfer, c->nInferEv);
     return rc;
 }

@@ -73,6 +73,7 @@ struct rlg_engine {
     // rlg_engine_set_state / reset masks: one device staging buffer, grown on demand (no allocation per call); evStage orders its
     // reuse after the last kernel that read it, whatever stream that ran on
     unsigned char* stage = nullptr; size_t stageCap = 0; cudaEvent_t evStage = nullptr; bool stageBusy = false;
+    uint32_t* readyFlags = nullptr; uint32_t readySeq = 0;  // per-block completion flags of the last fused step (rlg_engine_step_ready)
 };
 
 // the staging buffer, at least `bytes` long, safe to overwrite from stream s
@@ -241,6 +242,7 @@ struct RolesArgs {
     const int32_t* actions; float* obs; float* reward; uint8_t* done; int autoReset;
     float* metrics;  // GameInst reward metrics, word-transposed [kMetricWords][A] (nullptr: not tracked)
     unsigned char* epa;  // [block][kEpaFullBytes] full-size penetration-depth workspaces (rl_epa.h), used when a warp's small one overflows
+    uint32_t* ready; uint32_t readySeq;  // [block] <- readySeq when the block has stored everything (nullptr: not published)
     struct HbJob* hbJobs;  // [arena][car] hitbox-narrowphase hand-over records
     int hbOffload;         // cars whose hitbox-mesh narrowphase the ball warp runs (0: every car its own, no extra barrier)
 };
@@ -534,6 +536,9 @@ __global__ void __maxnreg__(168) k_roles(const __grid_constant__ RolesArgs g) {
     uint32_t* epaSmall = smem + (size_t)g.arenasPerBlock * g.stride + (size_t)(blockDim.x >> 5) / roles * P * kWqWords;
     const EpaCtx epaCtx = epa_ctx(epaSmall, g.epa + (size_t)blockIdx.x * kEpaFullBytes);
     if (threadIdx.x == 0) epaSmall[0] = 0;  // lock free (ordered before its first use by the barriers below)
+    // a kernel launched as this one's programmatic dependent (the collector's inference) may be scheduled from now on: its blocks
+    // take the SMs of the role blocks that finish first and wait for the per-block flags below, not for the whole grid
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     PT_DECL();
     if (valid) {
         if (g.asyncLoad) {
@@ -671,6 +676,13 @@ __global__ void __maxnreg__(168) k_roles(const __grid_constant__ RolesArgs g) {
     SYNC_GROUP();
     if (valid)
         for (int w2 = role; w2 < g.nwords; w2 += roles) g.state[(size_t)w2 * A + a] = mine[w2];
+    if (g.ready) {  // everything this block writes is stored: publish (writers -> barrier -> one cumulative device-scope fence -> flag)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            *reinterpret_cast<volatile uint32_t*>(g.ready + blockIdx.x) = g.readySeq;
+        }
+    }
     PT_WORK(6);
 #ifdef RLG_PHASE_TIMING
     if (g.prof && lane == 0) {
@@ -768,7 +780,7 @@ int rlg_engine_destroy(rlg_engine* e) {
         cudaFree(e->prof); cudaFree(e->prof2);
     }
 #endif
-    cudaFree(e->scratch); cudaFree(e->metrics); cudaFree(e->epa); cudaFree(e->hbJobs); cudaFree(e->stage);
+    cudaFree(e->scratch); cudaFree(e->metrics); cudaFree(e->epa); cudaFree(e->hbJobs); cudaFree(e->stage); cudaFree(e->readyFlags);
     if (e->evStage) cudaEventDestroy(e->evStage);
     cudaFree(e->xIds); cudaFree(e->xCars); cudaFree(e->xBalls); cudaFree(e->xGym); cudaFree(e->xPlayers);
     if (e->evExport) cudaEventDestroy(e->evExport);
@@ -856,6 +868,11 @@ int rlg_engine_create(const rlg_engine_cfg* cfg, rlg_engine** out) {
     if (const char* cv = getenv("RLG_SMEM_CARVEOUT")) CKD(cudaFuncSetAttribute(k_roles, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
     CKD(cudaMalloc(&e->state, (size_t)e->nwords * A * 4));
     CKD(cudaMalloc(&e->scratch, (size_t)A * e->scratchSlots * sizeof(Contact)));
+    {
+        const size_t blocks = (A + e->arenasPerBlock - 1) / e->arenasPerBlock;
+        CKD(cudaMalloc(&e->readyFlags, blocks * 4));
+        CKD(cudaMemsetAsync(e->readyFlags, 0, blocks * 4, e->stream));
+    }
     {   // one full-size penetration-depth workspace per block of the role kernel's grid (their locks start free)
         const size_t blocks = (A + e->arenasPerBlock - 1) / e->arenasPerBlock;
         CKD(cudaMalloc(&e->epa, blocks * kEpaFullBytes));
@@ -1060,6 +1077,7 @@ static int do_step(rlg_engine* e, const int32_t* action_idx, cudaStream_t s, int
     g.mode = 1; g.actions = action_idx; g.obs = obs ? obs : e->obs; g.reward = reward ? reward : e->reward; g.done = done ? done : e->done;
     g.autoReset = autoReset;
     g.metrics = autoReset ? e->metrics : nullptr;  // GameInst::Step is the auto-resetting step
+    if (e->readyFlags && e->barMode == 0 && g.tickEnd == e->cfg.tickSkip) { g.ready = e->readyFlags; g.readySeq = ++e->readySeq; }
     k_roles<<<grid_for(e->cfg.numArenas, e->arenasPerBlock), 32 * e->groupsPerBlock * (1 + e->cfg.numCars), e->rolesSmem, s>>>(g);
     e->launches++;
     CK(cudaGetLastError());
@@ -1077,6 +1095,12 @@ int rlg_engine_step_to(rlg_engine* e, const int32_t* action_idx, float* obs_out,
     if (!e->meshesLoaded) return fail(RLG_ERR_STATE, "rlg_engine_load_meshes must be called first (RocketSim::Init)");
     CK(cudaSetDevice(e->device));
     return do_step(e, action_idx, pick(e, stream), 1, obs_out, reward_out, done_out);
+}
+int rlg_engine_step_ready(rlg_engine* e, const uint32_t** flags_dev, uint32_t* seq, int* arenas_per_block) {
+    if (!e || !flags_dev || !seq || !arenas_per_block) return fail(RLG_ERR_INVALID, "null argument");
+    *flags_dev = (e->barMode == 0 && e->readySeq > 0) ? e->readyFlags : nullptr;
+    *seq = e->readySeq; *arenas_per_block = e->arenasPerBlock;
+    return RLG_OK;
 }
 int rlg_engine_metrics(rlg_engine* e, rlg_metrics_host* out) {
     if (!e || !out) return fail(RLG_ERR_INVALID, "null argument");
