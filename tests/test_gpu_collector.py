@@ -153,6 +153,26 @@ def test_collect_ring_consistent_with_step_api_and_gae_bit_exact(torch_cuda):
     assert np.array_equal(c1.read("obs")[0], obs[T])
 
 
+def test_inference_under_the_tail_of_the_step_changes_nothing(torch_cuda, monkeypatch):
+    """Full-size pool (one role block per SM, 256 inference tiles): the collect loop with every inference launched as the programmatic
+    dependent of the step before it (per-block ready flags, rlg_engine_step_ready) fills the ring with exactly what the serialised
+    launches produce — observations, sampled actions, log-probs, values, rewards, done flags."""
+    rings = []
+    for overlap in ("0", "1"):
+        monkeypatch.setenv("RLG_COLLECT_OVERLAP", overlap)
+        e, c = _mk(16384, max_steps=3)
+        e.reset()
+        c.collect(3)
+        c.collect(3)  # the second collect starts from the ring's last slot
+        e.sync()
+        rings.append({k: c.read(k).copy() for k in ("obs", "action", "logprob", "value", "reward", "done")})
+        flags, seq, apb = e.step_ready()
+        assert seq == 6 and apb >= 32 and flags != 0
+        del c, e
+    for k in rings[0]:
+        assert np.array_equal(rings[0][k].view(np.uint8), rings[1][k].view(np.uint8)), k
+
+
 def test_collector_argument_errors(torch_cuda):
     e = engine.Engine(abi.default_cfg(num_arenas=4, team_size=1))
     with pytest.raises(engine.EngineError):
