@@ -319,6 +319,11 @@ int rlg_engine_step_to(rlg_engine* e, const int32_t* action_idx, float* obs_out,
  * state stores) when it is finished.  flags_dev is NULL when the engine does not publish flags (per-group barrier modes).
  * No reference counterpart: the reference's agents wait for Gym::Step to return (ThreadAgent.cpp:100-140). */
 int rlg_engine_step_ready(rlg_engine* e, const uint32_t** flags_dev, uint32_t* seq, int* arenas_per_block);
+/* rlg_engine_step_to launched as the programmatic dependent of the kernel before it on `stream` (the inference that writes action_idx):
+ * every block of the step waits until tile_flags_dev[i] >= seq for the tiles i of rows_per_tile consecutive action rows that cover its
+ * arenas, instead of for the whole producer kernel.  tile_flags_dev == NULL: exactly rlg_engine_step_to. */
+int rlg_engine_step_to_after(rlg_engine* e, const int32_t* action_idx, float* obs_out, float* reward_out, uint8_t* done_out, void* stream,
+                             const uint32_t* tile_flags_dev, uint32_t seq, int rows_per_tile);
 
 /* ---- host-plugin path: user-defined OBSBuilder / RewardFunction / TerminalCondition / StepCallback -------------------------------
  * (G/Utils/OBSBuilders/OBSBuilder.h:10-15, RewardFunctions/RewardFunction.h:9-35, TerminalConditions/TerminalCondition.h:7-8,

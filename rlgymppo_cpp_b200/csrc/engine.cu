@@ -243,6 +243,7 @@ struct RolesArgs {
     float* metrics;  // GameInst reward metrics, word-transposed [kMetricWords][A] (nullptr: not tracked)
     unsigned char* epa;  // [block][kEpaFullBytes] full-size penetration-depth workspaces (rl_epa.h), used when a warp's small one overflows
     uint32_t* ready; uint32_t readySeq;  // [block] <- readySeq when the block has stored everything (nullptr: not published)
+    const uint32_t* actReady; uint32_t actSeq; int actTileRows;  // wait for the producer's tiles that cover this block's action rows (nullptr: none)
     struct HbJob* hbJobs;  // [arena][car] hitbox-narrowphase hand-over records
     int hbOffload;         // cars whose hitbox-mesh narrowphase the ball warp runs (0: every car its own, no extra barrier)
 };
@@ -540,6 +541,22 @@ __global__ void __maxnreg__(168) k_roles(const __grid_constant__ RolesArgs g) {
     // take the SMs of the role blocks that finish first and wait for the per-block flags below, not for the whole grid
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     PT_DECL();
+    if (g.actReady) {  // launched as the programmatic dependent of the inference: its tiles for this block's rows (and with them the previous
+                       // step of this block, which those tiles waited for) must be complete before anything is read
+        if (threadIdx.x == 0) {
+            const int a0 = blockIdx.x * g.arenasPerBlock, a1 = (a0 + g.arenasPerBlock < A ? a0 + g.arenasPerBlock : A) - 1;
+            const int t0 = (a0 * P) / g.actTileRows, t1 = (a1 * P + P - 1) / g.actTileRows;
+            for (int i = t0; i <= t1; i++) {
+                const volatile uint32_t* f = g.actReady + i;
+                for (unsigned spin = 0; (int32_t)(*f - g.actSeq) < 0; spin++) {
+                    __nanosleep(200);
+                    if (spin > (1u << 24)) __trap();  // seconds: the producer is gone
+                }
+            }
+            __threadfence();
+        }
+        __syncthreads();
+    }
     if (valid) {
         if (g.asyncLoad) {
             for (int w = role; w < g.nwords; w += roles) cp_async4(mine + w, g.state + (size_t)w * A + a);
@@ -1070,7 +1087,8 @@ int rlg_engine_tick(rlg_engine* e, const rlg_controls* controls, int nticks, voi
 }
 
 static int do_step(rlg_engine* e, const int32_t* action_idx, cudaStream_t s, int autoReset, float* obs = nullptr, float* reward = nullptr,
-                   uint8_t* done = nullptr, int tickBegin = 0, int tickEnd = -1, bool listResets = false) {
+                   uint8_t* done = nullptr, int tickBegin = 0, int tickEnd = -1, bool listResets = false, const uint32_t* actReady = nullptr,
+                   uint32_t actSeq = 0, int actTileRows = 0) {
     RolesArgs g = roles_args(e);
     g.tickBegin = tickBegin; g.tickEnd = tickEnd < 0 ? e->cfg.tickSkip : tickEnd;
     if (listResets) { g.resetCount = e->resetCount; g.resetIds = e->dResetIds; g.resetObs = e->dResetObs; }
@@ -1078,10 +1096,33 @@ static int do_step(rlg_engine* e, const int32_t* action_idx, cudaStream_t s, int
     g.autoReset = autoReset;
     g.metrics = autoReset ? e->metrics : nullptr;  // GameInst::Step is the auto-resetting step
     if (e->readyFlags && e->barMode == 0 && g.tickEnd == e->cfg.tickSkip) { g.ready = e->readyFlags; g.readySeq = ++e->readySeq; }
+    if (actReady && actTileRows > 0 && e->barMode == 0) {
+        g.actReady = actReady; g.actSeq = actSeq; g.actTileRows = actTileRows;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid_for(e->cfg.numArenas, e->arenasPerBlock)); cfg.blockDim = dim3(32 * e->groupsPerBlock * (1 + e->cfg.numCars));
+        cfg.dynamicSmemBytes = e->rolesSmem; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, k_roles, g));
+        e->launches++;
+        return RLG_OK;
+    }
     k_roles<<<grid_for(e->cfg.numArenas, e->arenasPerBlock), 32 * e->groupsPerBlock * (1 + e->cfg.numCars), e->rolesSmem, s>>>(g);
     e->launches++;
     CK(cudaGetLastError());
     return RLG_OK;
+}
+
+int rlg_engine_step_to_after(rlg_engine* e, const int32_t* action_idx, float* obs_out, float* reward_out, uint8_t* done_out, void* stream,
+                             const uint32_t* tile_flags_dev, uint32_t seq, int rows_per_tile) {
+    if (!e || !action_idx || !obs_out || !reward_out || !done_out) return fail(RLG_ERR_INVALID, "null argument");
+    if (tile_flags_dev && rows_per_tile < 1) return fail(RLG_ERR_INVALID, "rows_per_tile must be positive");
+    if (!e->meshesLoaded) return fail(RLG_ERR_STATE, "rlg_engine_load_meshes must be called first (RocketSim::Init)");
+    CK(cudaSetDevice(e->device));
+    return do_step(e, action_idx, pick(e, stream), 1, obs_out, reward_out, done_out, 0, -1, false, tile_flags_dev, seq, rows_per_tile);
 }
 
 int rlg_engine_step(rlg_engine* e, const int32_t* action_idx, void* stream) {

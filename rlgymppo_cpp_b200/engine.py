@@ -27,7 +27,7 @@ EXPORTS = [
     "rlg_engine_step_host", "rlg_engine_host_buffers", "rlg_engine_step_pinned", "rlg_engine_read_outputs", "rlg_engine_launch_count", "rlg_engine_stream", "rlg_engine_sync",
     "rlg_engine_metrics", "rlg_engine_reset_metrics", "rlg_engine_score_lines", "rlg_gemm_tf32", "rlg_gemm_tf32_fused",
     # collector / plumbing (bound in rlgymppo_cpp_b200.collector)
-    "rlg_engine_step_to", "rlg_engine_step_ready", "rlg_engine_device", "rlg_engine_arena_id_base", "rlg_engine_copy_to_host", "rlg_engine_copy_to_device",
+    "rlg_engine_step_to", "rlg_engine_step_ready", "rlg_engine_step_to_after", "rlg_engine_device", "rlg_engine_arena_id_base", "rlg_engine_copy_to_host", "rlg_engine_copy_to_device",
     "rlg_collector_create", "rlg_collector_destroy", "rlg_collector_set_layer", "rlg_collector_infer", "rlg_collector_collect",
     "rlg_collector_gae", "rlg_collector_view", "rlg_collector_export", "rlg_collector_launch_count",
     "rlg_collector_enable_timing", "rlg_collector_kernel_times", "rlg_collector_set_reset_hook", "rlg_engine_reset_current_to",

@@ -158,8 +158,9 @@ def test_inference_under_the_tail_of_the_step_changes_nothing(torch_cuda, monkey
     dependent of the step before it (per-block ready flags, rlg_engine_step_ready) fills the ring with exactly what the serialised
     launches produce — observations, sampled actions, log-probs, values, rewards, done flags."""
     rings = []
-    for overlap in ("0", "1"):
+    for overlap, chain in (("0", "0"), ("1", "0"), ("1", "1")):  # serialised | inference under the step's tail | + per-block chains (opt-in)
         monkeypatch.setenv("RLG_COLLECT_OVERLAP", overlap)
+        monkeypatch.setenv("RLG_COLLECT_CHAIN", chain)
         e, c = _mk(16384, max_steps=3)
         e.reset()
         c.collect(3)
@@ -169,8 +170,9 @@ def test_inference_under_the_tail_of_the_step_changes_nothing(torch_cuda, monkey
         flags, seq, apb = e.step_ready()
         assert seq == 6 and apb >= 32 and flags != 0
         del c, e
-    for k in rings[0]:
-        assert np.array_equal(rings[0][k].view(np.uint8), rings[1][k].view(np.uint8)), k
+    for other in rings[1:]:
+        for k in rings[0]:
+            assert np.array_equal(rings[0][k].view(np.uint8), other[k].view(np.uint8)), k
 
 
 def test_collector_argument_errors(torch_cuda):
