@@ -73,6 +73,36 @@ public:
     }
 };
 
+class MyDiscrete : public ActionParser {  // DiscreteAction's table (G/Utils/ActionParsers/DiscreteAction.cpp:3-67) through the user interface
+public:
+    std::vector<Action> table;
+    MyDiscrete() {
+        for (float throttle : {-1.f, 0.f, 1.f})
+            for (float steer : {-1.f, 0.f, 1.f})
+                for (float boost : {0.f, 1.f})
+                    for (float handbrake : {0.f, 1.f}) {
+                        if (boost == 1 && throttle != 1) continue;
+                        table.push_back(Action{throttle, steer, 0, steer, 0, 0, boost, handbrake});
+                    }
+        for (float pitch : {-1.f, 0.f, 1.f})
+            for (float yaw : {-1.f, 0.f, 1.f})
+                for (float roll : {-1.f, 0.f, 1.f})
+                    for (float jump : {0.f, 1.f})
+                        for (float boost : {0.f, 1.f}) {
+                            if (jump == 1 && yaw != 0) continue;
+                            if (pitch == roll && roll == jump && jump == 0) continue;
+                            const bool handbrake = jump == 1 && (pitch != 0 || yaw != 0 || roll != 0);
+                            table.push_back(Action{boost, yaw, pitch, yaw, roll, jump, boost, (float)handbrake});
+                        }
+    }
+    ActionSet ParseActions(const IList& idx, const GameState&) override {
+        ActionSet out;
+        for (int i : idx) out.push_back(table[i]);
+        return out;
+    }
+    int GetActionAmount() override { return (int)table.size(); }
+};
+
 static EnvCreateResult MakeEnv(bool user) {
     RewardFunction* face = user ? (RewardFunction*)new MyFaceBall() : new FaceBallReward();
     RewardFunction* vel = user ? (RewardFunction*)new MyVelToBall() : new VelocityPlayerToBallReward();
@@ -80,7 +110,8 @@ static EnvCreateResult MakeEnv(bool user) {
                                                   {new EventReward({.teamGoal = 1.f, .concede = -1.f, .touch = 0.05f, .boostPickup = 0.1f}), 50.f}}, true);
     if (g_teamSize > 1) rewards = new ZeroSumReward(rewards, 0.3f, 1.f, true);
     std::vector<TerminalCondition*> conds = {user ? (TerminalCondition*)new MyNoTouch(40) : new NoTouchCondition(40), new GoalScoreCondition()};
-    Match* match = new Match(rewards, conds, user ? (OBSBuilder*)new MyObs() : new DefaultOBS(), new DiscreteAction(), new RandomState(true, true, true), g_teamSize, true);
+    Match* match = new Match(rewards, conds, user ? (OBSBuilder*)new MyObs() : new DefaultOBS(), user ? (ActionParser*)new MyDiscrete() : new DiscreteAction(),
+                             new RandomState(true, true, true), g_teamSize, true);
     return {match, new Gym(match, 8)};
 }
 

@@ -35,6 +35,7 @@ extern "C" {
 #define RLG_MAX_CARS 6   /* 3v3 */
 #define RLG_NUM_PADS 34  /* R/RLConst.h:192-253 */
 #define RLG_NUM_ACTIONS 90 /* G/Utils/ActionParsers/DiscreteAction.cpp:3-67 */
+#define RLG_MAX_ACTIONS 96 /* widest action head / table (rlg_engine_set_action_table) */
 
 /* ---- host-side AoS state structs (parity injection / extraction) ----------
  * Mirrors of RocketSim's CarState (R/Sim/Car/Car.h:17-115), BallState
@@ -319,6 +320,12 @@ int rlg_engine_step_to(rlg_engine* e, const int32_t* action_idx, float* obs_out,
  * state stores) when it is finished.  flags_dev is NULL when the engine does not publish flags (per-group barrier modes).
  * No reference counterpart: the reference's agents wait for Gym::Step to return (ThreadAgent.cpp:100-140). */
 int rlg_engine_step_ready(rlg_engine* e, const uint32_t** flags_dev, uint32_t* seq, int* arenas_per_block);
+/* A user ActionParser (G/Utils/ActionParsers/ActionParser.h:11-14) whose ParseActions maps an action index to an Action independently
+ * of the game state: its table, n_actions rows of 8 floats (throttle, steer, pitch, yaw, roll, jump, boost, handbrake — Action.h:5-9),
+ * replaces the DiscreteAction table of the fused step; 1 <= n_actions <= RLG_MAX_ACTIONS.  Call it before rlg_collector_create: the
+ * policy head gets rlg_engine_num_actions(e) outputs (ActionParser::GetActionAmount). */
+int rlg_engine_set_action_table(rlg_engine* e, const float* table_host, int n_actions);
+int rlg_engine_num_actions(const rlg_engine* e);
 /* rlg_engine_step_to launched as the programmatic dependent of the kernel before it on `stream` (the inference that writes action_idx):
  * every block of the step waits until tile_flags_dev[i] >= seq for the tiles i of rows_per_tile consecutive action rows that cover its
  * arenas, instead of for the whole producer kernel.  tile_flags_dev == NULL: exactly rlg_engine_step_to. */

@@ -30,7 +30,9 @@
 //   user TerminalCondition   -> OR-ed with the fused built-in conditions
 //   StepCallback             -> called per arena per step with a filled Gym::StepResult (GameInst.cpp:23-24)
 //   user StateSetter         -> Arena / Car / Ball proxies -> rlg_engine_set_state + rlg_engine_reset_current
-// A user ActionParser is not supported (the policy head is the 90-way DiscreteAction table).
+//   user ActionParser        -> probed once into its table (index -> Action for every index below GetActionAmount() <= 96) and uploaded
+//                               with rlg_engine_set_action_table; the policy head gets GetActionAmount() outputs.  The mapping must not depend
+//                               on the game state (checked on two different probe states; a state-dependent parser is refused loudly).
 // Errors: every failing C-ABI call is re-thrown as std::runtime_error(rlg_last_error()) like RG_ERR_CLOSE
 // (G/Framework.h:17-22).
 #pragma once
@@ -590,6 +592,7 @@ struct PluginPlan {
     rlg_engine_cfg cfg;
     bool obsOnHost = false, rewardOnHost = false;
     int hostTerminals = 0;  // user TerminalConditions (the built-in ones stay fused and are OR-ed in)
+    std::vector<float> actionTable;  // a user ActionParser's table, 8 floats per action index (empty: DiscreteAction)
     bool AnyHost() const { return obsOnHost || rewardOnHost || hostTerminals > 0; }
 };
 
@@ -625,7 +628,41 @@ inline PluginPlan PlanFromMatch(const Match& m, int tickSkip, int numArenas, int
     else if (m.obsBuilder) plan.obsOnHost = true;  // the ring keeps the DefaultOBS row width unless the probe below says otherwise
     else throw std::runtime_error("RLGB200: Match has no OBSBuilder");
     // action parser
-    if (!dynamic_cast<DiscreteAction*>(m.actionParser)) throw std::runtime_error("RLGB200: only DiscreteAction is supported (the policy head is its 90-way table)");
+    if (!m.actionParser) throw std::runtime_error("RLGB200: Match has no ActionParser");
+    if (typeid(*m.actionParser) != typeid(DiscreteAction)) {
+        // a user ActionParser (ActionParser.h:11-14): every index through ParseActions once, on two different probe states
+        const int n = m.actionParser->GetActionAmount();
+        if (n < 1 || n > RLG_MAX_ACTIONS) throw std::runtime_error("RLGB200: ActionParser::GetActionAmount() must be in [1, " + std::to_string(RLG_MAX_ACTIONS) + "]");
+        const int P = m.playerAmount > 0 ? m.playerAmount : 2;
+        GameState probe[2];
+        for (int k = 0; k < 2; k++) {
+            probe[k].players.resize(P);
+            for (int p = 0; p < P; p++) {
+                probe[k].players[p].carId = p + 1;
+                probe[k].players[p].team = (Team)(p & 1);
+                probe[k].players[p].phys.pos = Vec(k ? 1234.f : -800.f, k ? -2500.f : 300.f, k ? 600.f : 17.f);
+                probe[k].players[p].phys.vel = Vec(k ? 900.f : 0.f, k ? -300.f : 0.f, 0.f);
+                probe[k].players[p].boostFraction = k ? 0.f : 1.f;
+                probe[k].players[p].carState.isOnGround = k == 0;
+            }
+            probe[k].ball.pos = Vec(k ? -2000.f : 0.f, k ? 4000.f : 0.f, k ? 1500.f : 93.f);
+        }
+        plan.actionTable.resize((size_t)n * 8);
+        for (int i = 0; i < n; i++) {
+            for (int k = 0; k < 2; k++) {
+                ActionSet set = m.actionParser->ParseActions(IList((size_t)P, i), probe[k]);
+                if ((int)set.size() != P) throw std::runtime_error("RLGB200: ActionParser::ParseActions must return one Action per player");
+                for (int p = 0; p < P; p++) {
+                    const Action& a = set[p];
+                    const float row[8] = {a.throttle, a.steer, a.pitch, a.yaw, a.roll, a.jump, a.boost, a.handbrake};
+                    if (k == 0 && p == 0) memcpy(&plan.actionTable[(size_t)i * 8], row, sizeof(row));
+                    else if (memcmp(&plan.actionTable[(size_t)i * 8], row, sizeof(row)) != 0)
+                        throw std::runtime_error("RLGB200: this ActionParser maps an index to different Actions for different players / game states; "
+                                                 "only state-independent parsers (index -> Action tables) run on the device engine");
+                }
+            }
+        }
+    }
     // rewards
     RewardFunction* rf = m.rewardFn;
     c.zero_sum = 0;
@@ -1051,6 +1088,8 @@ public:
         ec.mutators_set = 1;
         engine.reset(new RLGB200::Engine(ec));
         engine->LoadMeshes(RocketSim::CollisionMeshBlobs());
+        if (!plan.actionTable.empty())  // a user ActionParser: its table replaces DiscreteAction's, the policy head follows (before the collector)
+            RLGB200::Check(rlg_engine_set_action_table(engine->h, plan.actionTable.data(), (int)(plan.actionTable.size() / 8)));
         if (plan.obsOnHost) {  // the ring's row width is the fused builder's: a user builder must produce rows of that width
             hostObsProbe = true;
         }
@@ -1353,6 +1392,7 @@ public:
             throw std::runtime_error("RLGB200: policy/critic need the same number (<= 4) of hidden layers");
         rlg_ppo_cfg c;
         memset(&c, 0, sizeof(c));
+        actionAmountValue = actionAmount;
         c.device = device.index; c.obs_size = obsSize; c.num_actions = actionAmount; c.num_hidden = (int32_t)config.policyLayerSizes.size();
         for (int i = 0; i < c.num_hidden; i++) { c.policy_hidden[i] = config.policyLayerSizes[i]; c.critic_hidden[i] = config.criticLayerSizes[i]; }
         c.batch_size = config.batchSize; c.mini_batch_size = config.miniBatchSize; c.epochs = config.epochs;
@@ -1394,10 +1434,11 @@ public:
         const IList& hsz = net == 0 ? config.policyLayerSizes : config.criticLayerSizes;
         int in = obsSize_();
         for (int hdim : hsz) { d.push_back({hdim, in}); in = hdim; }
-        d.push_back({net == 0 ? RLG_NUM_ACTIONS : 1, in});
+        d.push_back({net == 0 ? actionAmountValue : 1, in});
         return d;
     }
     int obsSizeValue = 0;
+    int actionAmountValue = RLG_NUM_ACTIONS;  // the policy head: ActionParser::GetActionAmount()
 
 private:
     int obsSize_() const { return obsSizeValue; }

@@ -195,7 +195,7 @@ def load_old_versions(learner, folder: str) -> int:
             if os.path.isfile(mp):
                 from .learner import make_mlp, mlp_layers_numpy
 
-                seq = make_mlp(learner.engine.obs_size, list(learner.cfg.ppo.policyLayerSizes), 90)
+                seq = make_mlp(learner.engine.obs_size, list(learner.cfg.ppo.policyLayerSizes), learner.engine.num_actions)
                 load_seq(seq, mp)
                 st.append_old_policy(mlp_layers_numpy(seq), load_rating_set(st, best_rating))
                 found += 1

@@ -61,7 +61,7 @@ class Collector:
         self.cfg = cfg
         self.h = C.c_void_p()
         _check(self.L.rlg_collector_create(engine.h, C.byref(cfg), C.byref(self.h)))
-        self.policy_dims = self._dims(policy_hidden, abi.RLG_NUM_ACTIONS)
+        self.policy_dims = self._dims(policy_hidden, engine.num_actions)  # ActionParser::GetActionAmount (90 unless Engine.set_action_table)
         self.critic_dims = self._dims(critic_hidden, 1)
         self.weights = [None, None]
 

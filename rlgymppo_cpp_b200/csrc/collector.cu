@@ -590,9 +590,13 @@ int launch_infer(rlg_collector* c, const float* obs, int nRows, uint64_t counter
             at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             at[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
-            CKC(cudaLaunchKernelEx(&cfg, k_mlp_infer, a));
-            c->launches++;
-            return RLG_OK;
+            const cudaError_t le = cudaLaunchKernelEx(&cfg, k_mlp_infer, a);
+            if (le == cudaSuccess) { c->launches++; return RLG_OK; }
+            // a driver without programmatic dependent launch: say so once and go on with ordinary launches (same results, no overlap)
+            (void)cudaGetLastError();
+            fprintf(stderr, "rlgym_b200: programmatic dependent launch unavailable (%s): the collect loop runs without the inference overlap\n", cudaGetErrorString(le));
+            c->overlap = false;
+            a.ready = nullptr;
         }
     }
     k_mlp_infer<<<grid, kThreads, kSmemTotal, s>>>(a);
@@ -635,13 +639,14 @@ int rlg_collector_create(rlg_engine* e, const rlg_collector_cfg* cfg, rlg_collec
     c->maxT = cfg->max_steps;
     c->rowBase = (uint64_t)rlg_engine_arena_id_base(e) * (uint64_t)c->P;  // sampling streams keyed by GLOBAL row id
     c->numLayers = cfg->num_hidden + 1;
-    if (RLG_NUM_ACTIONS > 96) { delete c; return failc(RLG_ERR_INVALID, "action head wider than 96"); }
+    const int numActions = rlg_engine_num_actions(e);  // ActionParser::GetActionAmount of the engine's action table
+    if (numActions < 1 || numActions > 96) { delete c; return failc(RLG_ERR_INVALID, "action head wider than 96"); }
     for (int n = 0; n < 2; n++) {
         int in = c->obs;
         for (int l = 0; l < c->numLayers; l++) {
             auto& h = c->L[n][l];
             h.in = in;
-            h.out = (l < cfg->num_hidden) ? (n == 0 ? cfg->policy_hidden[l] : cfg->critic_hidden[l]) : (n == 0 ? RLG_NUM_ACTIONS : 1);
+            h.out = (l < cfg->num_hidden) ? (n == 0 ? cfg->policy_hidden[l] : cfg->critic_hidden[l]) : (n == 0 ? numActions : 1);
             h.kPad = (in + kBlockK - 1) / kBlockK * kBlockK;
             h.nPad = (l < cfg->num_hidden) ? h.out : (h.out + 15) / 16 * 16;
             if (h.kPad > kMaxWidth) { delete c; return failc(RLG_ERR_INVALID, "observation wider than 256 floats is not supported by the fused MLP"); }

@@ -580,7 +580,7 @@ __global__ void __maxnreg__(168) k_roles(const __grid_constant__ RolesArgs g) {
             int32_t act[kMaxCars];
             for (int p = 0; p < P; p++) {
                 int v = g.actions[(size_t)a * P + p];
-                act[p] = v < 0 ? 0 : (v >= RLG_NUM_ACTIONS ? RLG_NUM_ACTIONS - 1 : v);
+                act[p] = v < 0 ? 0 : (v >= g.cfg.numActions ? g.cfg.numActions - 1 : v);
             }
             parse_actions(s, g.cfg, *g.tb, act);
         }
@@ -723,7 +723,7 @@ __global__ void k_eval(uint32_t* state, SimCfg cfg, int nwords, const Tables* __
     int32_t act[kMaxCars];
     for (int p = 0; p < cfg.numCars; p++) {
         int v = actions[(size_t)a * cfg.numCars + p];
-        act[p] = v < 0 ? 0 : (v >= RLG_NUM_ACTIONS ? RLG_NUM_ACTIONS - 1 : v);
+        act[p] = v < 0 ? 0 : (v >= cfg.numActions ? cfg.numActions - 1 : v);
     }
     parse_actions(s, cfg, *tb, act);
     snapshot_update(s, cfg);
@@ -1137,6 +1137,17 @@ int rlg_engine_step_to(rlg_engine* e, const int32_t* action_idx, float* obs_out,
     CK(cudaSetDevice(e->device));
     return do_step(e, action_idx, pick(e, stream), 1, obs_out, reward_out, done_out);
 }
+int rlg_engine_set_action_table(rlg_engine* e, const float* table_host, int n_actions) {
+    if (!e || !table_host) return fail(RLG_ERR_INVALID, "null argument");
+    if (n_actions < 1 || n_actions > RLG_MAX_ACTIONS) return fail(RLG_ERR_INVALID, "n_actions must be in [1, RLG_MAX_ACTIONS]");
+    for (int i = 0; i < n_actions * 8; i++) if (!std::isfinite(table_host[i])) return fail(RLG_ERR_INVALID, "action table holds a non-finite value");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(reinterpret_cast<char*>(e->tables) + offsetof(Tables, actions), table_host, (size_t)n_actions * 8 * 4, cudaMemcpyHostToDevice));
+    e->cfg.numActions = n_actions;
+    return RLG_OK;
+}
+int rlg_engine_num_actions(const rlg_engine* e) { return e ? e->cfg.numActions : 0; }
 int rlg_engine_step_ready(rlg_engine* e, const uint32_t** flags_dev, uint32_t* seq, int* arenas_per_block) {
     if (!e || !flags_dev || !seq || !arenas_per_block) return fail(RLG_ERR_INVALID, "null argument");
     *flags_dev = (e->barMode == 0 && e->readySeq > 0) ? e->readyFlags : nullptr;

@@ -14,7 +14,7 @@
 namespace rl {
 
 struct Tables {
-    float actions[90 * 8];    // DiscreteAction table (G/Utils/ActionParsers/DiscreteAction.cpp:3-67)
+    float actions[96 * 8];    // DiscreteAction table (G/Utils/ActionParsers/DiscreteAction.cpp:3-67: 90 rows) or a user parser's (SimCfg::numActions rows)
     int32_t padMap[kNumPads]; // GameState pad i -> RocketSim pad index (G/Utils/Gamestates/GameState.cpp:10-50)
     float padPos[kNumPads * 3]; // RocketSim pad order (6 big, 28 small), uu
     float padPosBT[kNumPads * 3]; // same, Bullet units (uu * (1/50), as BoostPad::_BulletSetup stores it)

@@ -423,6 +423,7 @@ inline void host_build_simcfg(const rlg_engine_cfg& c, SimCfg& s) {
     s.spawnOpponents = c.spawn_opponents != 0;
     s.numCars = c.team_size * (s.spawnOpponents ? 2 : 1);
     s.tickSkip = c.tick_skip;
+    s.numActions = RLG_NUM_ACTIONS;
     if (c.car_preset < 0 || c.car_preset >= C::kNumCarPresets) throw std::runtime_error("bad car_preset");
     s.carPreset = c.car_preset;
     s.obsKind = c.obs_kind; s.obsMaxPlayers = c.obs_max_players;

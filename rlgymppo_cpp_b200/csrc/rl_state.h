@@ -238,6 +238,7 @@ struct Mut {  // MutatorConfig as the tick reads it (rlg_mutators; Bullet units 
 struct SimCfg {
     Mut mut;
     int32_t numArenas, numCars, spawnOpponents, tickSkip;
+    int32_t numActions;  // rows of Tables::actions (90 unless rlg_engine_set_action_table replaced the table)
     int32_t carPreset;  // rlg_engine_cfg.car_preset
     int32_t obsKind, obsMaxPlayers, obsSize;
     int32_t numRewardTerms;

@@ -27,7 +27,7 @@ EXPORTS = [
     "rlg_engine_step_host", "rlg_engine_host_buffers", "rlg_engine_step_pinned", "rlg_engine_read_outputs", "rlg_engine_launch_count", "rlg_engine_stream", "rlg_engine_sync",
     "rlg_engine_metrics", "rlg_engine_reset_metrics", "rlg_engine_score_lines", "rlg_gemm_tf32", "rlg_gemm_tf32_fused",
     # collector / plumbing (bound in rlgymppo_cpp_b200.collector)
-    "rlg_engine_step_to", "rlg_engine_step_ready", "rlg_engine_step_to_after", "rlg_engine_device", "rlg_engine_arena_id_base", "rlg_engine_copy_to_host", "rlg_engine_copy_to_device",
+    "rlg_engine_step_to", "rlg_engine_step_ready", "rlg_engine_step_to_after", "rlg_engine_set_action_table", "rlg_engine_num_actions", "rlg_engine_device", "rlg_engine_arena_id_base", "rlg_engine_copy_to_host", "rlg_engine_copy_to_device",
     "rlg_collector_create", "rlg_collector_destroy", "rlg_collector_set_layer", "rlg_collector_infer", "rlg_collector_collect",
     "rlg_collector_gae", "rlg_collector_view", "rlg_collector_export", "rlg_collector_launch_count",
     "rlg_collector_enable_timing", "rlg_collector_kernel_times", "rlg_collector_set_reset_hook", "rlg_engine_reset_current_to",
@@ -172,6 +172,25 @@ class Engine:
     def step_device(self, actions_ptr: int, auto_reset: bool = True):
         fn = self.L.rlg_engine_step if auto_reset else self.L.rlg_engine_step_noreset
         _check(fn(self.h, C.c_void_p(actions_ptr), None))
+
+    def set_action_table(self, table: np.ndarray):
+        """A user ActionParser as its table [n_actions, 8] (throttle, steer, pitch, yaw, roll, jump, boost, handbrake) in place of the
+        DiscreteAction table; call it before a Collector is created on this engine (its policy head gets n_actions outputs)."""
+        t = np.ascontiguousarray(table, dtype=np.float32)
+        if t.ndim != 2 or t.shape[1] != 8:
+            raise EngineError("action table must be [n_actions, 8]")
+        _check(self.L.rlg_engine_set_action_table(self.h, t.ctypes.data_as(C.c_void_p), int(t.shape[0])))
+        self._action_table = t.copy()
+
+    @property
+    def action_table(self) -> np.ndarray:
+        """The table the fused step parses action indices with: DiscreteAction's 90 rows unless set_action_table replaced it."""
+        t = getattr(self, "_action_table", None)
+        return t.copy() if t is not None else action_table()
+
+    @property
+    def num_actions(self) -> int:
+        return int(self.L.rlg_engine_num_actions(self.h))
 
     def step_ready(self):
         """(device address of the per-block completion flags of the last fused step or 0, its sequence number, arenas per block)."""

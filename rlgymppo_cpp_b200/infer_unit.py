@@ -43,9 +43,9 @@ class InferUnit:
         self.engine = engine
         self.is_policy = bool(is_policy)
         self.layer_sizes = tuple(int(x) for x in layer_sizes)
-        self.num_actions = abi.RLG_NUM_ACTIONS  # actionParser->GetActionAmount()
+        self.num_actions = engine.num_actions  # actionParser->GetActionAmount()
         self.device = torch.device("cuda", engine.L.rlg_engine_device(engine.h))
-        self.table = action_table()  # DiscreteAction::ParseActions lookup (G/Utils/ActionParsers/DiscreteAction.cpp)
+        self.table = engine.action_table  # ActionParser::ParseActions lookup (DiscreteAction.cpp unless the engine carries a user table)
         seq = make_mlp(obs_size, list(self.layer_sizes), self.num_actions if self.is_policy else 1)
         checkpoint.load_seq(seq, os.fspath(model_path))  # raises like RG_ERR_CLOSE("Failed to load model ...")
         self.seq = seq.to(self.device)

@@ -297,7 +297,7 @@ class Learner:
     GLOBAL sizes split evenly over the ranks (shard_sizes)."""
 
     def __init__(self, engine_cfg, cfg: LearnerConfig, device_index: int = 0, iteration_callback=None, state_setter=None, mesh_blobs=None,
-                 collision_meshes_folder: Optional[str] = None, step_callback=None):
+                 collision_meshes_folder: Optional[str] = None, step_callback=None, action_table=None):
         from . import abi, collector, engine  # CUDA extension: fails loudly if missing
 
         self.cfg = cfg
@@ -319,6 +319,8 @@ class Learner:
             mesh_blobs = meshes.read_cmf_folder(collision_meshes_folder)
         self.mesh_blobs = mesh_blobs
         self.engine = engine.Engine(engine_cfg, mesh_blobs=mesh_blobs)
+        if action_table is not None:  # a user ActionParser as its [n_actions, 8] table (ActionParser.h:11-14); the policy head follows it
+            self.engine.set_action_table(action_table)
         A, P = self.engine.A, self.engine.P
         self.steps_per_iter = max(1, math.ceil(cfg.timestepsPerIteration / (self.world * A * P)))  # CollectTimesteps: >= amount rows
         self.collector = collector.Collector(self.engine, tuple(cfg.ppo.policyLayerSizes), tuple(cfg.ppo.criticLayerSizes),
@@ -326,7 +328,7 @@ class Learner:
                                              temperature=cfg.ppo.policyTemperature, deterministic=cfg.deterministic)
         sizes = shard_sizes(cfg, self.world)
         self.rank_ppo_cfg = dataclasses.replace(cfg.ppo, batchSize=sizes["batchSize"], miniBatchSize=sizes["miniBatchSize"])
-        self.ppo = PPOLearner(self.engine.obs_size, abi.RLG_NUM_ACTIONS, self.rank_ppo_cfg, self.device, exp_buffer_size=sizes["expBufferSize"],
+        self.ppo = PPOLearner(self.engine.obs_size, self.engine.num_actions, self.rank_ppo_cfg, self.device, exp_buffer_size=sizes["expBufferSize"],
                               seed=cfg.randomSeed + self.rank)
         self.return_stats = WelfordRunningStat()
         self.total_timesteps = 0
@@ -340,7 +342,7 @@ class Learner:
             from . import skill_tracker
 
             self.skill_tracker = skill_tracker.SkillTracker.on_engine(stc, engine_cfg, tuple(cfg.ppo.policyLayerSizes), device_index, cfg.randomSeed,
-                                                                      mesh_blobs=mesh_blobs)
+                                                                      mesh_blobs=mesh_blobs, action_table=action_table)
         self.save_folder = cfg.checkpointSaveFolder
         if self.save_folder and cfg.saveFolderAddUnixTimestamp:  # Learner.cpp:30-31
             self.save_folder = os.path.join(self.save_folder, str(int(time.time())))

@@ -164,7 +164,8 @@ class SkillTracker:
 
     # ---- device wiring -------------------------------------------------------------------------------------------
     @classmethod
-    def on_engine(cls, config: SkillTrackerConfig, train_engine_cfg, policy_hidden, device_index: int = 0, seed: int = 0, mesh_blobs=None):
+    def on_engine(cls, config: SkillTrackerConfig, train_engine_cfg, policy_hidden, device_index: int = 0, seed: int = 0, mesh_blobs=None,
+                  action_table=None):
         """Eval pool = a second engine with numEnvs arenas of the training configuration (same mode, obs builder,
         terminal conditions), dummy rewards, kickoff states if configured; inference through one deterministic collector."""
         import torch
@@ -181,6 +182,8 @@ class SkillTracker:
             # a host StateSetter of the training pool is not wired into the eval pool: its games start from kickoffs
             ecfg.state_setter = abi.RLG_SETTER_KICKOFF
         e = engine.Engine(ecfg, mesh_blobs=mesh_blobs)
+        if action_table is not None:  # the training pool's user ActionParser
+            e.set_action_table(action_table)
         col = collector.Collector(e, tuple(policy_hidden), tuple(policy_hidden), max_steps=1, seed=seed, deterministic=True)
         st = cls(config, int(ecfg.team_size), bool(ecfg.spawn_opponents), int(ecfg.tick_skip), seed)
         st.engine, st.collector = e, col

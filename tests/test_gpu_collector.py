@@ -175,6 +175,42 @@ def test_inference_under_the_tail_of_the_step_changes_nothing(torch_cuda, monkey
             assert np.array_equal(rings[0][k].view(np.uint8), other[k].view(np.uint8)), k
 
 
+def test_user_action_table_replaces_discrete_action(torch_cuda):
+    """A user ActionParser as its table (rlg_engine_set_action_table): (1) a permutation of DiscreteAction's rows with the indices mapped
+    through it reproduces the default engine bit for bit; (2) a narrower table narrows the policy head (GetActionAmount) and the collect
+    loop only samples its indices; (3) bad tables are refused."""
+    torch = torch_cuda
+    A = 96
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(90)
+    e0 = engine.Engine(abi.default_cfg(num_arenas=A, team_size=1))
+    e1 = engine.Engine(abi.default_cfg(num_arenas=A, team_size=1))
+    table = engine.action_table()
+    e1.set_action_table(table[perm])          # row j of the user table = DiscreteAction row perm[j]
+    inv = np.argsort(perm)                    # DiscreteAction index i sits at user index inv[i]
+    assert e1.num_actions == 90 and np.array_equal(e1.action_table, table[perm])
+    e0.reset(); e1.reset()
+    for s in range(12):
+        a = rng.integers(0, 90, size=A * 2).astype(np.int32)
+        o0, r0, d0 = e0.step_host(a)
+        o1, r1, d1 = e1.step_host(inv[a].astype(np.int32))
+        assert np.array_equal(o0.view(np.uint32), o1.view(np.uint32)) and np.array_equal(r0.view(np.uint32), r1.view(np.uint32)) and np.array_equal(d0, d1)
+    e2 = engine.Engine(abi.default_cfg(num_arenas=A, team_size=1))
+    e2.set_action_table(table[:37])
+    c2 = collector.Collector(e2, max_steps=4, seed=3)
+    c2.init_default(seed=7)
+    assert c2.policy_dims[-1][0] == 37
+    e2.reset()
+    c2.collect(4)
+    e2.sync()
+    act = c2.read("action")
+    assert act.min() >= 0 and act.max() < 37 and len(np.unique(act)) > 20
+    with pytest.raises(engine.EngineError):
+        e2.set_action_table(np.zeros((97, 8), np.float32))
+    with pytest.raises(engine.EngineError):
+        e2.set_action_table(np.full((4, 8), np.nan, np.float32))
+
+
 def test_collector_argument_errors(torch_cuda):
     e = engine.Engine(abi.default_cfg(num_arenas=4, team_size=1))
     with pytest.raises(engine.EngineError):
