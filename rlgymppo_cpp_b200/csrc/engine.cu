@@ -966,7 +966,7 @@ static RolesArgs roles_args(rlg_engine* e) {
     g.ms = e->ms; g.tb = e->tables; g.scratch = e->scratch; g.scratchSlots = e->scratchSlots;
     g.arenasPerBlock = e->arenasPerBlock;
     g.barMode = e->barMode; g.asyncLoad = e->asyncLoad; g.prof = e->prof;
-    g.k = car_consts(e->cfg.carPreset); g.thr = contact_thresholds(g.k);
+    g.k = car_consts(e->cfg.carPreset); g.thr = contact_thresholds(g.k, e->cfg.mut.ballRadius);
     g.epa = e->epa;
     g.hbJobs = reinterpret_cast<HbJob*>(e->hbJobs);
     g.hbOffload = e->hbOffload;

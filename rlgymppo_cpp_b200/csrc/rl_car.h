@@ -142,14 +142,14 @@ struct DynView {
     int32_t responds;  // hasContactResponse (false for demoed cars)
 };
 
-RL_HD inline DynView dyn_view(const TickX& x, int body, const CarConsts& k) {
+RL_HD inline DynView dyn_view(const TickX& x, int body, const CarConsts& k, const Mut& mu) {
     DynView d;
     if (body == 0) {
         d.pos = x.h->ballPos; d.vel = x.h->ballVel; d.angvel = x.h->ballAngvel; d.rot = M3::identity();
-        float r = C::BALL_RADIUS * UU2BT;
-        float inertia = 0.4f * C::BALL_MASS * r * r;
+        float r = mu.ballRadius * UU2BT;
+        float inertia = 0.4f * mu.ballMass * r * r;
         d.invInertiaLocal = V3(1.f / inertia, 1.f / inertia, 1.f / inertia);
-        d.invMass = 1.f / C::BALL_MASS; d.responds = 1;
+        d.invMass = 1.f / mu.ballMass; d.responds = 1;
     } else {
         const CarX& c = x.car[body - 1];
         d.pos = c.pos; d.vel = c.vel; d.angvel = c.angvel; d.rot = c.rot;
@@ -198,7 +198,7 @@ RL_HD inline void wheel_mesh_rays(const CarS& c, const CarConsts& k, const MeshS
 RL_HD inline RayHit wheel_ray(const TickX& x, const SimCfg& cfg, const MeshSet& ms, const CarConsts& k, const RayHit& meshHit, int self, V3 from, V3 to) {
     RayHit hit = meshHit;  // static meshes first (wheel_mesh_rays), then planes, ball, other cars
     for (int p = 0; p < 4; p++) ray_plane(from, to, world_plane(p), hit);
-    ray_sphere(from, to, x.h->ballPos, C::BALL_RADIUS * UU2BT, 0, hit);
+    ray_sphere(from, to, x.h->ballPos, cfg.mut.ballRadius * UU2BT, 0, hit);
     for (int c = 0; c < cfg.numCars; c++) {
         if (c == self) continue;
         const CarX& o = x.car[c];
@@ -293,7 +293,7 @@ RL_HD inline void vehicle_first(CarS& c, const TickX& x, const SimCfg& cfg, cons
         // resolveSingleBilateral (btContactConstraint.cpp:108-157)
         DynView g;
         bool dynGround = wh.ground >= 0;
-        if (dynGround) g = dyn_view(x, wh.ground, k);
+        if (dynGround) g = dyn_view(x, wh.ground, k, cfg.mut);
         V3 rel1 = wh.contactPoint - c.pos;
         V3 rel2 = dynGround ? (wh.contactPoint - g.pos) : V3();
         V3 vel1 = vel_at(c.vel, c.angvel, rel1);

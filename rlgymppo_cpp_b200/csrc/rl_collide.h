@@ -52,10 +52,10 @@ RL_HDI ContactSink make_sink(Contact* base, int cap) { ContactSink s; s.base = b
 // relative contact breaking thresholds (btCollisionDispatcher::getNewManifold,
 // btCollisionShape::getContactBreakingThreshold): 0.02 * angularMotionDisc of the shape
 struct Thresholds { float ball, car; };
-RL_HDI Thresholds contact_thresholds(const CarConsts& k) {
+RL_HDI Thresholds contact_thresholds(const CarConsts& k, float ballRadiusUU = C::BALL_RADIUS) {
     Thresholds t;
     // btCollisionShape::getBoundingSphere, sphere case (ROCKETSIM CHANGE: radius + 0.08), centre 0
-    t.ball = (float)((double)(C::BALL_RADIUS * UU2BT) + 0.08) * C::CONTACT_BREAKING;
+    t.ball = (float)((double)(ballRadiusUU * UU2BT) + 0.08) * C::CONTACT_BREAKING;
     // compound: local AABB = hitbox offset +- half extents
     V3 mn = k.hitboxOffset - k.halfExt, mx = k.hitboxOffset + k.halfExt;
     float radius = len(mx - mn) * 0.5f;
@@ -460,7 +460,7 @@ RL_HD inline void box_meshes(CollideCtx& x, ContactSink& cs, const MeshSet& ms, 
 RL_HD inline void car_ball(CollideCtx& x, ContactSink& cs, int ci, float breaking) {
     const CarS& c = x.a->cars[ci];
     const CarConsts& k = *x.k;
-    float radius = C::BALL_RADIUS * UU2BT;
+    float radius = x.cfg->mut.ballRadius * UU2BT;
     V3 boxCenter = c.pos + c.rot * k.hitboxOffset;
     V3 normal, pointOnB; float dist;
     if (box_sphere_contact(boxCenter, c.rot, k.coreHalf, k.boxMargin, x.ballPos, radius, breaking, x.epa, normal, pointOnB, dist)) {

@@ -61,7 +61,7 @@ RL_HD RL_NOINLINE inline bool ball_probably_going_in(const BallS& b, const Mut& 
     float ex = s_add(s_add(pos.x, s_mul(vel.x, timeToGoal)), s_div(s_mul(s_mul(mu.gravityX, timeToGoal), timeToGoal), 2.f));
     float ez = s_add(s_add(pos.z, s_mul(vel.z, timeToGoal)), s_div(s_mul(s_mul(mu.gravityZ, timeToGoal), timeToGoal), 2.f));
     const float APPROX_GOAL_HALF_WIDTH = 892.755f, APPROX_GOAL_HEIGHT = (float)642.775;
-    float scoreMargin = s_add(s_mul(C::BALL_RADIUS, 0.1f), extraMargin);
+    float scoreMargin = s_add(s_mul(mu.ballRadius, 0.1f), extraMargin);
     if (ez > APPROX_GOAL_HEIGHT + scoreMargin) return false;
     if (fabsf(ex) > APPROX_GOAL_HALF_WIDTH + scoreMargin) return false;
     if (goalTeamOut) *goalTeamOut = scoreDirSgn < 0 ? 0 : 1;  // RS_TEAM_FROM_Y(scoreDirSgn)
@@ -102,7 +102,7 @@ RL_HDI void event_tracker_update(ArenaS& a, const SimCfg& cfg) {
     // default GameEventTrackerConfig (GameEventTracker.h:11-40); tick rate 120
     const float shotMinSpeed = 1750, predScoreExtraMargin = 0, shotEventCooldown = 1.0f, shotMinScoreTime = 2.0f;
     const int64_t goalMaxTouchTicks = 480, passMaxTouchTicks = 240, shotMinTouchDelayTicks = 36;
-    bool scored = fabsf(s_mul(a.ball.pos.y, BT2UU)) > cfg.mut.goalBaseThresholdY + C::BALL_RADIUS;  // Arena::IsBallScored (Arena.cpp:949-957)
+    bool scored = fabsf(s_mul(a.ball.pos.y, BT2UU)) > cfg.mut.goalBaseThresholdY + cfg.mut.ballRadius;  // Arena::IsBallScored (Arena.cpp:949-957)
     int32_t cnt = a.ball.updateCounterLo;
     if (cnt > a.lastBallUpdateCount) {
         int64_t deltaTicks = (int64_t)cnt - a.lastBallUpdateCount;

@@ -449,8 +449,17 @@ inline void host_build_simcfg(const rlg_engine_cfg& c, SimCfg& s) {
     rlg_mutators m;
     host_mutators_default(m);
     if (c.mutators_set) m = c.mutators;
-    if (m.car_mass != C::CAR_MASS || m.ball_mass != C::BALL_MASS || m.ball_radius != C::BALL_RADIUS)
-        throw std::runtime_error("mutators: car_mass, ball_mass and ball_radius must keep their defaults (not supported by the engine)");
+    // car_mass: accepted, and without effect — exactly as in the reference's Gym: Gym::Gym calls Arena::SetMutatorConfig BEFORE it adds the cars
+    // (G/Gym.cpp:40-49), SetMutatorConfig only re-masses cars that already exist (Arena.cpp:34-40) and Car::_BulletSetup builds every
+    // car with RLConst::CAR_MASS_BT (Car.cpp:206-209), so a Gym's cars weigh 180 whatever MutatorConfig::carMass says.
+    if (!(m.car_mass > 0.f)) throw std::runtime_error("mutators: car_mass must be positive");
+    if (!(m.ball_mass > 0.f)) throw std::runtime_error("mutators: ball_mass must be positive");
+    {   // the reference refuses a dynamic object whose AABB diagonal exceeds a broadphase cell (btRSBroadphase.cpp:229-230, cell size 7.4 Bullet
+        // units in soccar: "Object AABB size exceeds maximum cell size"); the ball's AABB is its radius + 0.08 on every side
+        const float half = m.ball_radius * UU2BT + 0.08f;
+        if (!(m.ball_radius >= 10.f) || 2.f * half * 1.7320508f > 7.4f)
+            throw std::runtime_error("mutators: ball_radius must be in [10, 102] uu (the reference's broadphase refuses a larger ball)");
+    }
     if (m.demo_mode < 0 || m.demo_mode > 2) throw std::runtime_error("mutators: bad demo_mode");
     if (!(m.ball_drag >= 0.f && m.ball_drag < 1.f)) throw std::runtime_error("mutators: ball_drag must be in [0, 1)");
     Mut& u = s.mut;
@@ -464,6 +473,7 @@ inline void host_build_simcfg(const rlg_engine_cfg& c, SimCfg& s) {
     u.padCooldownBig = m.boost_pad_cooldown_big; u.padCooldownSmall = m.boost_pad_cooldown_small;
     u.carSpawnBoost = m.car_spawn_boost_amount; u.ballHitExtraForceScale = m.ball_hit_extra_force_scale; u.bumpForceScale = m.bump_force_scale;
     u.goalBaseThresholdY = m.goal_base_threshold_y;
+    u.ballMass = m.ball_mass; u.ballRadius = m.ball_radius;
     u.unlimitedFlips = m.unlimited_flips != 0; u.unlimitedDoubleJumps = m.unlimited_double_jumps != 0;
     u.demoMode = m.demo_mode; u.enableTeamDemos = m.enable_team_demos != 0;
     s.ballDampFactor = powf(1.f - m.ball_drag, kTickTime);                  // btRigidBody::applyDamping

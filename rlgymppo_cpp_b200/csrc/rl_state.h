@@ -233,6 +233,7 @@ struct Mut {  // MutatorConfig as the tick reads it (rlg_mutators; Bullet units 
     float ballMaxSpeed, jumpAccel, jumpImmediateForce, boostAccelGround, boostAccelAir, boostUsedPerSecond;
     float respawnDelay, bumpCooldownTime, padCooldownBig, padCooldownSmall, carSpawnBoost, ballHitExtraForceScale, bumpForceScale;
     float goalBaseThresholdY;
+    float ballMass, ballRadius;  // Bullet mass units, uu (the ball's rigid body and sphere are built from them: Ball.cpp:74-91)
     int32_t unlimitedFlips, unlimitedDoubleJumps, demoMode, enableTeamDemos;
 };
 struct SimCfg {

@@ -178,7 +178,7 @@ RL_HD inline void tick_p1_car_begin(ArenaS& a, TickX x, const SimCfg& cfg, const
     cx.ballPos = x.h->ballPos; cx.ballVel = x.h->ballVel * cfg.ballDampFactor;  // predictUnconstraintMotion damping precedes the narrowphase
     // car-ball (manifold order: all car-ball pairs precede the car-world pairs)
     ContactSink cb = make_sink(seg_car(scratch, c), 1);
-    float ballAabb = C::BALL_RADIUS * UU2BT + 0.08f;
+    float ballAabb = cfg.mut.ballRadius * UU2BT + 0.08f;
     V3 bmn = cx.ballPos - V3(ballAabb, ballAabb, ballAabb), bmx = cx.ballPos + V3(ballAabb, ballAabb, ballAabb);
     bool overlapBall = !(bmn.x > o.cmx.x || bmx.x < o.cmn.x || bmn.y > o.cmx.y || bmx.y < o.cmn.y || bmn.z > o.cmx.z || bmx.z < o.cmn.z);
     if (overlapBall && !(!x.h->ballActive && o.noResponse)) car_ball(cx, cb, c, fminf_(thr.ball, thr.car));
@@ -229,7 +229,7 @@ RL_HD inline void tick_p1_ball(ArenaS& a, TickX x, const SimCfg& cfg, const Mesh
     // a sleeping ball vs the (always "sleeping") static bodies is skipped by btCollisionDispatcher::needsCollision
     // (both inactive): on the tick it is woken by a car it has no world contacts yet.
     if (x.h->ballActive) {
-        float ballR = C::BALL_RADIUS * UU2BT;
+        float ballR = cfg.mut.ballRadius * UU2BT;
         sphere_meshes(cx, cs, ms, cx.ballPos, ballR, thr.ball);
         RL_PT(8);
 #pragma unroll 1
@@ -305,7 +305,7 @@ RL_HD inline void tick_p2_solve(ArenaS& a, TickX x, const SimCfg& cfg, const Car
     const int P = cfg.numCars;
     const int64_t tick = get_i64(a.tickLo, a.tickHi);
     const bool ballActive = x.h->ballActive != 0;
-    const float ballR = C::BALL_RADIUS * UU2BT;
+    const float ballR = cfg.mut.ballRadius * UU2BT;
     RL_PT(-1);
     // predictUnconstraintMotion: damping (ball only: linear 0.03)
     a.ball.vel = a.ball.vel * cfg.ballDampFactor;
@@ -336,7 +336,7 @@ RL_HD inline void tick_p2_solve(ArenaS& a, TickX x, const SimCfg& cfg, const Car
     x.h->nPair = cp.n;
     RL_PT(10);
 
-    const V3 gImp = cfg.mut.gravityBT * C::BALL_MASS;
+    const V3 gImp = cfg.mut.gravityBT * cfg.mut.ballMass;
 #ifdef RL_DEBUG_CONTACTS
     {   // every contact of the tick in the reference's manifold order (host debugging only)
         ContactSet& cs = g_dbg_contacts; cs.n = 0; cs.overflow = 0;
@@ -358,8 +358,8 @@ RL_HD inline void tick_p2_solve(ArenaS& a, TickX x, const SimCfg& cfg, const Car
         SolverBody& b = sb[0];
         b.pos = a.ball.pos; b.rot = M3::identity();
         b.linVel = a.ball.vel; b.angVel = a.ball.angvel;
-        b.invMass = 1.f / C::BALL_MASS;
-        float inertia = 0.4f * C::BALL_MASS * ballR * ballR;
+        b.invMass = 1.f / cfg.mut.ballMass;
+        float inertia = 0.4f * cfg.mut.ballMass * ballR * ballR;
         float ii = 1.f / inertia;
         b.invInertiaWorld = M3(V3(ii, 0, 0), V3(0, ii, 0), V3(0, 0, ii));
         V3 ballForce;
@@ -465,7 +465,7 @@ RL_HDI int tick_scratch_words(int ncars) { return tickx_words(ncars); }
 // xwords: tickx_words(numCars) uint32 words, scratch: contact_scratch_slots(numCars) contacts.
 RL_HD inline void arena_tick(ArenaS& a, const SimCfg& cfg, const MeshSet& ms, const Tables& tb, int firstTickOfStep, uint32_t* xwords, Contact* scratch) {
     const CarConsts k = car_consts(cfg.carPreset);
-    const Thresholds thr = contact_thresholds(k);
+    const Thresholds thr = contact_thresholds(k, cfg.mut.ballRadius);
     TickX x = make_tickx(xwords);
     const int P = cfg.numCars;
     CarW w[kMaxCars];

@@ -174,6 +174,16 @@ def apply_test_mutators(cfg):
     return cfg
 
 
+def apply_ball_mutators(cfg):
+    """The three mass / size fields of MutatorConfig (MutatorConfig.h:21,29,59): a heavier, larger ball (Ball.cpp:74-91 builds the ball
+    from them) and a carMass that the reference's Gym never applies (Gym.cpp:40-49 sets the mutators before the cars exist)."""
+    m = abi.default_mutators()
+    m.ball_mass, m.ball_radius, m.car_mass = 45.0, 100.0, 260.0  # (the reference's broadphase refuses balls above ~102 uu)
+    cfg.mutators = m
+    cfg.mutators_set = 1
+    return cfg
+
+
 def gym_cfgs():
     c = abi.default_cfg(1, 1)
     for k in range(11):

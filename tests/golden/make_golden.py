@@ -256,7 +256,7 @@ def main():
         save(f"tick_random_{team}v{team}", flat)
     np.save(os.path.join(HERE, "action_table.npy"), refsim.action_table())
     if len(sys.argv) > 1 and sys.argv[1] == "ticks":  # python tests/golden/make_golden.py ticks — every tick_* file, nothing else
-        presets(); mutators(); mutator_scenarios()
+        presets(); mutators(); mutator_scenarios(); ball_mutators()
         return
     # gym layer
     cfg = abi.default_cfg(num_arenas=1, team_size=1)
@@ -384,6 +384,26 @@ def mutator_scenarios():
     save("tick_scenarios_2v2_mutators", flat)
 
 
+def ball_mutators():
+    """python tests/golden/make_golden.py ball_mutators — MutatorConfig::ballMass / ballRadius / carMass (common.apply_ball_mutators): random
+    play and the scripted 1v1 scenarios (ball hits, dribbles, wall and ground bounces, wheels on the ball) from the reference"""
+    import common
+
+    chunks = random_play(1, 6, 61, mutate=common.apply_ball_mutators)
+    flat = {}
+    for i, d in enumerate(chunks):
+        for k, v in d.items():
+            flat[f"ep{i}/{k}"] = v
+    save("tick_random_1v1_ballmut", flat)
+    cfg = common.apply_ball_mutators(abi.default_cfg(num_arenas=1, team_size=1))
+    arena = refsim.RefArena(cfg=cfg)
+    flat = {}
+    for name, d in scenarios_1v1(arena).items():
+        for k, v in d.items():
+            flat[f"{name}/{k}"] = v
+    save("tick_scenarios_1v1_ballmut", flat)
+
+
 def presets():
     """python tests/golden/make_golden.py presets — random play with the five non-Octane CarConfigs"""
     for preset, name in ((1, "dominus"), (2, "plank"), (3, "breakout"), (4, "hybrid"), (5, "merc")):
@@ -404,6 +424,8 @@ if __name__ == "__main__":
         presets()
     elif len(sys.argv) > 1 and sys.argv[1] == "mutators":
         mutators()
+    elif len(sys.argv) > 1 and sys.argv[1] == "ball_mutators":
+        ball_mutators()
     elif len(sys.argv) > 1 and sys.argv[1] == "mutator_scenarios":
         mutator_scenarios()
     elif len(sys.argv) > 1 and sys.argv[1] == "ppo":

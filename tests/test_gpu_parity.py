@@ -110,12 +110,22 @@ def test_single_tick_scenarios_mutators(torch_cuda):
     _tick_file("tick_scenarios_2v2_mutators", 2, torch_cuda, mutate=common.apply_test_mutators)
 
 
-def test_mutators_unsupported_rejected():
-    cfg = abi.default_cfg(num_arenas=1, team_size=1)
-    cfg.mutators_set = 1
-    cfg.mutators.ball_radius = 120.0
-    with pytest.raises(Exception):
-        engine.Engine(cfg)
+def test_single_tick_ball_mass_radius_mutators(torch_cuda):
+    """MutatorConfig::ballMass / ballRadius (a 45-unit, 100 uu ball) and a carMass the reference's Gym never applies: random play and the
+    scripted scenarios (bounces on floor / walls / mesh, car hits, wheels and hitbox on the ball) recorded from the reference."""
+    _tick_file("tick_random_1v1_ballmut", 1, torch_cuda, mutate=common.apply_ball_mutators)
+    _tick_file("tick_scenarios_1v1_ballmut", 1, torch_cuda, mutate=common.apply_ball_mutators)
+
+
+def test_mutators_out_of_range_rejected():
+    """What the reference itself refuses or cannot simulate is refused loudly: a ball wider than a broadphase cell
+    (btRSBroadphase.cpp:229-230 throws), non-positive masses."""
+    for field, value in (("ball_radius", 120.0), ("ball_mass", 0.0), ("car_mass", -1.0)):
+        cfg = abi.default_cfg(num_arenas=1, team_size=1)
+        cfg.mutators_set = 1
+        setattr(cfg.mutators, field, value)
+        with pytest.raises(Exception):
+            engine.Engine(cfg)
 
 
 @pytest.mark.parametrize("name,cfg", list(common.gym_cfgs()))

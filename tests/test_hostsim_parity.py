@@ -102,6 +102,15 @@ def test_single_tick_random_play_mutators(team):
     print(res)
 
 
+def test_single_tick_ball_mass_radius_mutators():
+    """MutatorConfig::ballMass / ballRadius (45 units, 100 uu) and a carMass that the reference's Gym never applies (Gym.cpp:40-49 sets the
+    mutators before the cars exist; Car.cpp:206-209 builds cars with RLConst::CAR_MASS_BT): random play + the scripted scenarios."""
+    s, t, g = _runner(1, mutate=common.apply_ball_mutators)
+    print(common.check_single_tick_run(common.load_tick_file("tick_random_1v1_ballmut"), s, t, g))
+    s, t, g = _runner(1, mutate=common.apply_ball_mutators)
+    print(common.check_single_tick_run(common.load_tick_file("tick_scenarios_1v1_ballmut"), s, t, g))
+
+
 def test_single_tick_scenarios_mutators():
     """The scripted scenarios under the test mutators: demolition on contact at bump speed, 1 s respawn with 60 boost, team-mate
     demolition (2v2), pad cooldowns of 1.5 / 3 s, ball hits with the extra-impulse scale, repeated flips in one jump."""
@@ -123,8 +132,9 @@ def test_mutators_default_is_identity():
     assert bytes(m) == bytes(d)
 
 
-@pytest.mark.parametrize("field,value", [("car_mass", 200.0), ("ball_mass", 20.0), ("ball_radius", 100.0), ("demo_mode", 7)])
+@pytest.mark.parametrize("field,value", [("car_mass", -1.0), ("ball_mass", 0.0), ("ball_radius", 120.0), ("demo_mode", 7)])
 def test_mutators_unsupported_rejected(field, value):
+    """Values the reference itself refuses (a ball wider than a broadphase cell: btRSBroadphase.cpp:229-230) or cannot simulate."""
     cfg = abi.default_cfg(num_arenas=1, team_size=1)
     cfg.mutators_set = 1
     setattr(cfg.mutators, field, type(getattr(cfg.mutators, field))(value))
