@@ -438,7 +438,8 @@ struct HbJob {
 
 
 // Pass 2: hitbox vs the pre-filtered candidate triangles -> the car's world contact slots.
-__device__ __forceinline__ void box_meshes_warp(CollideCtx& cx, ContactSink& cw, const MeshSet& ms, const HbJob& w, int ci, float breaking,
+template <class HbIn>  // HbJob (the hand-over record, when another warp evaluates the pairs) or the car's own CarW
+__device__ __forceinline__ void box_meshes_warp(CollideCtx& cx, ContactSink& cw, const MeshSet& ms, const HbIn& w, int ci, float breaking,
                                                 bool active, const CarConsts& k, const uint32_t* mine, uint32_t* wq, int stride, const EpaCtx* ws) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -599,7 +600,7 @@ __global__ void __maxnreg__(168) k_roles(const __grid_constant__ RolesArgs g) {
             if (valid) tick_p1_car_pose(s, x, g.cfg, g.ms, k, role - 1, w, false);
             collect_candidates_warp(w, role - 1, valid, k, g.ms, mine, wq);  // whole warp
             cands_pass_warp(w, role - 1, valid, k, g.ms, mine, wq, g.stride);  // whole warp
-            if (valid) {  // hand the hitbox narrowphase's input over
+            if (valid && role - 1 < (P < g.hbOffload ? P : g.hbOffload)) {  // hand the hitbox narrowphase's input over (only to another warp)
                 HbJob& j = jobs[role - 1];
                 j.candMask = w.candMask; j.candGroupStart = w.candGroupStart; j.haveMask = w.haveMask; j.wcHas = 0;
                 j.cands.n = w.cands.n;
@@ -626,7 +627,7 @@ __global__ void __maxnreg__(168) k_roles(const __grid_constant__ RolesArgs g) {
             CollideCtx cx; ContactSink cw;
             if (valid) tick_p1_car_begin(s, x, g.cfg, g.ms, k, thr, role - 1, w, scratch, first, cx, cw, &epaCtx);
             if (role - 1 >= nOff) {
-                box_meshes_warp(cx, cw, g.ms, jobs[role - 1], role - 1, thr.car, valid, k, mine, wq, g.stride, &epaCtx);  // whole warp
+                box_meshes_warp(cx, cw, g.ms, w, role - 1, thr.car, valid, k, mine, wq, g.stride, &epaCtx);  // whole warp, from the car's own work state
                 if (valid) car_set_mesh_count(x.car[role - 1], cw.n);
             }
             if (valid) tick_p1_car_end(cx, x, thr, role - 1, scratch);
