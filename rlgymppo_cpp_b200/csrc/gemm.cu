@@ -23,6 +23,7 @@
 #include <string>
 
 #include "../../include/rlgym_b200.h"
+#include "pdl.h"
 
 extern "C" void rlg_internal_set_error(const char* msg);
 
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tf32(const GemmArgs g) {
     tc_fence_after();
     const uint32_t tmemBase = *tmemSlot;
     const uint32_t idesc = make_idesc(kGM, NT);
+    pdl_enter();  // (see k_gemm_tma)
 
     constexpr int kUA = kGM * (kGK / 4) / kGThreads;   // 4 float4 per thread for the A block
     constexpr int kUB = 256 * (kGK / 4) / kGThreads;   // 8 for a full-width B block
@@ -299,6 +301,7 @@ __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tma(const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmemBase = *tmemSlot;
+    pdl_enter();  // barriers and TMEM are set up: from here on the operands (written by the kernels before this one) are read
 
     if (warp == 0 && lane == 0) {  // producer
         // a TMA box always delivers its full size (out-of-bounds rows / columns arrive as zeros): A box + B box = one stage
@@ -504,11 +507,11 @@ extern "C" int rlg_gemm_tf32_fused(int M, int N, int K, const float* A, int lda,
             if (err != cudaSuccess) return failg(RLG_ERR_CUDA, std::string("rlg_gemm_tf32: ") + cudaGetErrorString(err));
             g_attr_tma[dev] = true;
         }
-        k_gemm_tma<<<grid, kGThreads, smemBytes, (cudaStream_t)stream>>>(mapA, mapB, ta);
+        err = launch_pdl(k_gemm_tma, grid, dim3(kGThreads), (size_t)smemBytes, (cudaStream_t)stream, mapA, mapB, ta);
     } else {
-        k_gemm_tf32<<<grid, kGThreads, kGSmem, (cudaStream_t)stream>>>(g);
+        err = launch_pdl(k_gemm_tf32, grid, dim3(kGThreads), (size_t)kGSmem, (cudaStream_t)stream, g);
     }
-    err = cudaGetLastError();
+    if (err == cudaSuccess) err = cudaGetLastError();
     if (err != cudaSuccess) return failg(RLG_ERR_CUDA, std::string("rlg_gemm_tf32 launch: ") + cudaGetErrorString(err));
     return RLG_OK;
 }

@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "../../include/rlgym_b200.h"
+#include "pdl.h"
 
 extern "C" void rlg_internal_set_error(const char* msg);
 
@@ -62,6 +63,7 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
 
 // ---- ExperienceBuffer::GetAllBatchesShuffled: a fresh permutation = sort of random keys ------------------------------------------
 __global__ void k_shuffle_keys(uint64_t* keys, int32_t* idx, long n, uint64_t seed, uint64_t counter) {
+    pdl_enter();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     keys[i] = mix64(mix64(seed ^ (counter * 0xD1B54A32D192ED03ull)) + (uint64_t)i);
@@ -76,6 +78,7 @@ __global__ void __launch_bounds__(256) k_gather_rows(const int32_t* __restrict__
                                                      float* __restrict__ X, float* __restrict__ Xt, int32_t* __restrict__ act, float* __restrict__ oldLp,
                                                      float* __restrict__ tgt, float* __restrict__ adv) {
     extern __shared__ float tile[];  // [32][obsP + 1]
+    pdl_enter();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long row0 = (long)blockIdx.x * 32;
     const int ts = obsP + 1;
@@ -110,6 +113,7 @@ __global__ void __launch_bounds__(256) k_policy_loss(const float* __restrict__ l
                                                      float invTemp, float clipRange, float entCoef, float ratioB, float* __restrict__ dZ,
                                                      float* __restrict__ dZt, double* __restrict__ acc) {
     extern __shared__ float tile[];  // [32][nActP + 1]
+    pdl_enter();
     __shared__ float red[8][4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long row0 = (long)blockIdx.x * 32;
@@ -201,6 +205,7 @@ __global__ void __launch_bounds__(256) k_policy_loss(const float* __restrict__ l
 __global__ void k_value_loss(const float* __restrict__ vals, int ldv, long n, long ldT, const float* __restrict__ tgt, float ratioB, float* __restrict__ dV,
                              float* __restrict__ dVt, double* __restrict__ acc) {
     __shared__ float red[8];
+    pdl_enter();
     const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
     float sq = 0.f;
     if (row < n) {
@@ -225,6 +230,7 @@ __global__ void k_value_loss(const float* __restrict__ vals, int ldv, long n, lo
 // db[o] += sum over the rows of dY^T[o, :]
 __global__ void __launch_bounds__(256) k_bias_grad(const float* __restrict__ dYt, long n, long ldT, float* __restrict__ db) {
     __shared__ float red[8];
+    pdl_enter();
     const float* src = dYt + (size_t)blockIdx.x * ldT;
     float s = 0.f;
     const long n4 = n >> 2;
@@ -245,6 +251,7 @@ __global__ void __launch_bounds__(256) k_bias_grad(const float* __restrict__ dYt
 __global__ void __launch_bounds__(256) k_sumsq2(const float* __restrict__ a, const float* __restrict__ b, size_t n0, size_t n1, float scale,
                                                 double* __restrict__ out) {
     __shared__ float red[2][8];
+    pdl_enter();
     float s0 = 0.f, s1 = 0.f;
     const size_t total = n0 + n1;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
@@ -265,6 +272,7 @@ __global__ void __launch_bounds__(256) k_sumsq2(const float* __restrict__ a, con
 struct AdamNet { float lr, stepSize, bc2Sqrt; int32_t train; };
 __global__ void k_adam(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n0, size_t n1, AdamNet a0,
                        AdamNet a1, float gradScale, float maxNorm, const double* __restrict__ normSq) {
+    pdl_enter();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n0 + n1) return;
     const int net = i < n0 ? 0 : 1;
@@ -285,6 +293,7 @@ __global__ void k_adam(float* __restrict__ p, float* __restrict__ g, float* __re
 
 __global__ void k_transpose(const float* __restrict__ W, int rows, int cols, float* __restrict__ Wt) {  // Wt[c][r] = W[r][c]
     __shared__ float t[32][33];
+    pdl_enter();
     const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
     for (int j = threadIdx.y; j < 32; j += 8) { int r = r0 + j, c = c0 + threadIdx.x; t[j][threadIdx.x] = (r < rows && c < cols) ? W[(size_t)r * cols + c] : 0.f; }
     __syncthreads();
@@ -343,7 +352,7 @@ int refresh_transposes(rlg_ppo* p, cudaStream_t s) {
         for (int l = 1; l < p->net[n].L; l++) {
             const PpoNet& N = p->net[n];
             dim3 grid((N.inP[l] + 31) / 32, (N.outP[l] + 31) / 32);
-            k_transpose<<<grid, dim3(32, 8), 0, s>>>(Wp(p, p->params, n, l), N.outP[l], N.inP[l], N.Wt[l]);
+            launch_pdl(k_transpose, grid, dim3(32, 8), 0, s, Wp(p, p->params, n, l), N.outP[l], N.inP[l], N.Wt[l]);
             p->launches++;
         }
     CKP(cudaGetLastError());
@@ -380,7 +389,7 @@ int backward_net(rlg_ppo* p, int n, long rows, cudaStream_t s) {
         if (split < 1) split = 1;
         CKR(rlg_gemm_tf32_fused(N.outP[l], N.inP[l], K, dYt, K, inT, K, Wp(p, p->grads, n, l), N.inP[l], nullptr, RLG_GEMM_ATOMIC, split, nullptr, 0,
                                 nullptr, 0, s));
-        k_bias_grad<<<N.outP[l], 256, 0, s>>>(dYt, rows, p->ldT, Bp(p, p->grads, n, l));
+        launch_pdl(k_bias_grad, dim3(N.outP[l]), dim3(256), 0, s, dYt, rows, p->ldT, Bp(p, p->grads, n, l));
         p->launches += 2;
         if (l > 0) {
             CKR(rlg_gemm_tf32_fused((int)rows, N.inP[l], N.outP[l], dY, N.outP[l], N.Wt[l], N.outP[l], p->dAct[cur ^ 1], N.inP[l], nullptr, 0, 1,
@@ -549,7 +558,7 @@ static int layer_io(rlg_ppo* p, int which, int net, int layer, float* W, float* 
         if (b) CKP(cudaMemcpy(dB, b, (size_t)out_dim * 4, cudaMemcpyHostToDevice));
         if (which == 0 && layer > 0 && W) {
             dim3 grid((N.inP[layer] + 31) / 32, (N.outP[layer] + 31) / 32);
-            k_transpose<<<grid, dim3(32, 8), 0, p->own>>>(dW, N.outP[layer], N.inP[layer], N.Wt[layer]);
+            launch_pdl(k_transpose, grid, dim3(32, 8), 0, p->own, dW, N.outP[layer], N.inP[layer], N.Wt[layer]);
             CKP(cudaStreamSynchronize(p->own));
         }
     } else {
@@ -668,7 +677,7 @@ int rlg_ppo_peek_shuffle(rlg_ppo* p, int32_t* perm_host, uint64_t counter) {
     if (p->cur < 1) return RLG_OK;
     CKP(cudaSetDevice(p->device));
     const long n = p->cur;
-    k_shuffle_keys<<<(unsigned)((n + 255) / 256), 256, 0, p->own>>>(p->keysIn, p->idxIn, n, p->cfg.seed, counter);
+    launch_pdl(k_shuffle_keys, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, p->own, p->keysIn, p->idxIn, n, p->cfg.seed, counter);
     CKP(cub::DeviceRadixSort::SortPairs(p->cubTemp, p->cubBytes, p->keysIn, p->keysOut, p->idxIn, p->perm, (int)n, 0, 64, p->own));
     CKP(cudaMemcpyAsync(perm_host, p->perm, (size_t)n * 4, cudaMemcpyDeviceToHost, p->own));
     CKP(cudaStreamSynchronize(p->own));
@@ -695,19 +704,19 @@ int rlg_ppo_learn(rlg_ppo* p, rlg_ppo_report* report, void* stream) {
     for (int epoch = 0; epoch < cfg.epochs; epoch++) {
         const long n = p->cur;
         if (n < batch) break;  // full batches only (ExperienceBuffer.cpp:114)
-        k_shuffle_keys<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p->keysIn, p->idxIn, n, cfg.seed, p->shuffleCounter++);
+        launch_pdl(k_shuffle_keys, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, p->keysIn, p->idxIn, n, cfg.seed, p->shuffleCounter++);
         CKP(cub::DeviceRadixSort::SortPairs(p->cubTemp, p->cubBytes, p->keysIn, p->keysOut, p->idxIn, p->perm, (int)n, 0, 64, s));
         p->launches += 2;
         for (long b0 = 0; b0 + batch <= n; b0 += batch) {
             for (long m0 = 0; m0 < batch; m0 += mbs) {
-                k_gather_rows<<<(unsigned)((mbs + 31) / 32), 256, gatherSmem, s>>>(p->perm + b0 + m0, mbs, p->ldT, p->head, p->cap, cfg.obs_size, p->obsP,
+                launch_pdl(k_gather_rows, dim3((unsigned)((mbs + 31) / 32)), dim3(256), gatherSmem, s, p->perm + b0 + m0, mbs, p->ldT, p->head, p->cap, cfg.obs_size, p->obsP,
                                                                                  p->bStates, p->bActions, p->bLogp, p->bTarget, p->bAdv, p->X, p->Xt, p->act,
                                                                                  p->oldLp, p->tgt, p->adv);
                 p->launches++;
                 if (trainCritic) {
                     CKR(forward_net(p, 1, mbs, s));
                     const PpoNet& C = p->net[1];
-                    k_value_loss<<<(unsigned)((mbs + 255) / 256), 256, 0, s>>>(C.Y[C.L - 1], C.outP[C.L - 1], mbs, p->ldT, p->tgt, ratioB, p->dAct[0], p->dActT[0],
+                    launch_pdl(k_value_loss, dim3((unsigned)((mbs + 255) / 256)), dim3(256), 0, s, C.Y[C.L - 1], C.outP[C.L - 1], mbs, p->ldT, p->tgt, ratioB, p->dAct[0], p->dActT[0],
                                                                               p->acc);
                     p->launches++;
                     CKR(backward_net(p, 1, mbs, s));
@@ -715,7 +724,7 @@ int rlg_ppo_learn(rlg_ppo* p, rlg_ppo_report* report, void* stream) {
                 if (trainPolicy) {
                     CKR(forward_net(p, 0, mbs, s));
                     const PpoNet& P = p->net[0];
-                    k_policy_loss<<<(unsigned)((mbs + 31) / 32), 256, lossSmem, s>>>(P.Y[P.L - 1], P.outP[P.L - 1], cfg.num_actions, p->actP, mbs, p->ldT, p->act,
+                    launch_pdl(k_policy_loss, dim3((unsigned)((mbs + 31) / 32)), dim3(256), lossSmem, s, P.Y[P.L - 1], P.outP[P.L - 1], cfg.num_actions, p->actP, mbs, p->ldT, p->act,
                                                                                    p->adv, p->oldLp, 1.f / cfg.temperature, cfg.clip_range, cfg.ent_coef, ratioB,
                                                                                    p->dAct[0], p->dActT[0], p->acc);
                     p->launches++;
@@ -727,7 +736,7 @@ int rlg_ppo_learn(rlg_ppo* p, rlg_ppo_report* report, void* stream) {
             if (p->hook && cfg.world > 1) p->hook(p->hookUser, p->grads, (int64_t)p->total, (void*)s);
             const float gradScale = 1.f / (float)cfg.world;
             CKP(cudaMemsetAsync(p->acc + 5, 0, 16, s));
-            k_sumsq2<<<148, 256, 0, s>>>(p->grads, nullptr, n0, n1, gradScale, p->acc + 5);
+            launch_pdl(k_sumsq2, dim3(148), dim3(256), 0, s, p->grads, nullptr, n0, n1, gradScale, p->acc + 5);
             AdamNet a[2];
             for (int net = 0; net < 2; net++) {
                 const bool train = net == 0 ? trainPolicy : trainCritic;
@@ -739,14 +748,14 @@ int rlg_ppo_learn(rlg_ppo* p, rlg_ppo_report* report, void* stream) {
                 a[net].bc2Sqrt = (float)std::sqrt(1.0 - std::pow(0.999, t));
                 a[net].train = train ? 1 : 0;
             }
-            k_adam<<<(unsigned)((p->total + 255) / 256), 256, 0, s>>>(p->params, p->grads, p->m, p->v, n0, n1, a[0], a[1], gradScale, 0.5f, p->acc + 5);
+            launch_pdl(k_adam, dim3((unsigned)((p->total + 255) / 256)), dim3(256), 0, s, p->params, p->grads, p->m, p->v, n0, n1, a[0], a[1], gradScale, 0.5f, p->acc + 5);
             p->launches += 2;
             CKR(refresh_transposes(p, s));
             nBatches++;
         }
     }
     CKP(cudaMemsetAsync(p->acc + 7, 0, 16, s));
-    k_sumsq2<<<148, 256, 0, s>>>(p->params, p->before, n0, n1, 1.f, p->acc + 7);
+    launch_pdl(k_sumsq2, dim3(148), dim3(256), 0, s, p->params, p->before, n0, n1, 1.f, p->acc + 7);
     p->launches++;
     CKP(cudaEventRecord(p->ev1, s));
     CKP(cudaGetLastError());
