@@ -176,8 +176,10 @@ def run_reference(args, rank, world):
         b.run(160)  # one NoTouch horizon: the gyms reach their steady-state mix of resets / contacts, caches and threads are warm
         t_probe = b.run(100)
         # one bench step = one long burst (~2.5 s of every host thread; thread start-up is < 0.1 % of it), so that K steps are
-        # >= 2 000 env-steps per gym for K >= 8 and the arm reads the same as one long run (cpu_baseline_sample)
-        inner = int(max(250, min(20000, 100 * 2.5 / max(t_probe, 1e-3))))
+        # >= 2 000 env-steps per gym for K >= 8 and the arm reads the same as one long run (cpu_baseline_sample); the whole arm is
+        # bounded to ~100 s of bursts whatever K is (the default K = 500 would otherwise keep every host core busy for 20 minutes)
+        burst_s = min(2.5, 100.0 / max(args.steps, 1))
+        inner = int(max(50, min(20000, 100 * burst_s / max(t_probe, 1e-3))))
         for _ in range(min(args.warmup, 3)):
             b.run(inner)
         ts = [b.run(inner) for _ in range(args.steps)]
