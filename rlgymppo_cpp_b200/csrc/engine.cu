@@ -244,6 +244,7 @@ struct RolesArgs {
     unsigned char* epa;  // [block][kEpaFullBytes] full-size penetration-depth workspaces (rl_epa.h), used when a warp's small one overflows
     uint32_t* ready; uint32_t readySeq;  // [block] <- readySeq when the block has stored everything (nullptr: not published)
     const uint32_t* actReady; uint32_t actSeq; int actTileRows;  // wait for the producer's tiles that cover this block's action rows (nullptr: none)
+    const uint32_t* prevReady; uint32_t prevSeq;  // wait for THIS block of the launch before (the split host-buffer step: tick 0 | ticks 1..)
     struct HbJob* hbJobs;  // [arena][car] hitbox-narrowphase hand-over records
     int hbOffload;         // cars whose hitbox-mesh narrowphase the ball warp runs (0: every car its own, no extra barrier)
 };
@@ -553,6 +554,17 @@ __global__ void __maxnreg__(168) k_roles(const __grid_constant__ RolesArgs g) {
                     __nanosleep(200);
                     if (spin > (1u << 24)) __trap();  // seconds: the producer is gone
                 }
+            }
+            __threadfence();
+        }
+        __syncthreads();
+    }
+    if (g.prevReady) {  // launched as the programmatic dependent of the launch that ran this block's previous ticks: wait for that block only
+        if (threadIdx.x == 0) {
+            const volatile uint32_t* f = g.prevReady + blockIdx.x;
+            for (unsigned spin = 0; (int32_t)(*f - g.prevSeq) < 0; spin++) {
+                __nanosleep(100);
+                if (spin > (1u << 25)) __trap();
             }
             __threadfence();
         }
@@ -1095,16 +1107,17 @@ int rlg_engine_tick(rlg_engine* e, const rlg_controls* controls, int nticks, voi
 
 static int do_step(rlg_engine* e, const int32_t* action_idx, cudaStream_t s, int autoReset, float* obs = nullptr, float* reward = nullptr,
                    uint8_t* done = nullptr, int tickBegin = 0, int tickEnd = -1, bool listResets = false, const uint32_t* actReady = nullptr,
-                   uint32_t actSeq = 0, int actTileRows = 0) {
+                   uint32_t actSeq = 0, int actTileRows = 0, int chain = 0 /* 1: publish flags for a chained launch, 2: wait for the launch before */) {
     RolesArgs g = roles_args(e);
     g.tickBegin = tickBegin; g.tickEnd = tickEnd < 0 ? e->cfg.tickSkip : tickEnd;
     if (listResets) { g.resetCount = e->resetCount; g.resetIds = e->dResetIds; g.resetObs = e->dResetObs; }
     g.mode = 1; g.actions = action_idx; g.obs = obs ? obs : e->obs; g.reward = reward ? reward : e->reward; g.done = done ? done : e->done;
     g.autoReset = autoReset;
     g.metrics = autoReset ? e->metrics : nullptr;  // GameInst::Step is the auto-resetting step
-    if (e->readyFlags && e->barMode == 0 && g.tickEnd == e->cfg.tickSkip) { g.ready = e->readyFlags; g.readySeq = ++e->readySeq; }
-    if (actReady && actTileRows > 0 && e->barMode == 0) {
-        g.actReady = actReady; g.actSeq = actSeq; g.actTileRows = actTileRows;
+    if (chain == 2 && e->readyFlags && e->barMode == 0 && e->readySeq > 0) { g.prevReady = e->readyFlags; g.prevSeq = e->readySeq; }
+    if (e->readyFlags && e->barMode == 0 && (g.tickEnd == e->cfg.tickSkip || chain == 1)) { g.ready = e->readyFlags; g.readySeq = ++e->readySeq; }
+    if ((actReady && actTileRows > 0 && e->barMode == 0) || g.prevReady) {
+        if (actReady) { g.actReady = actReady; g.actSeq = actSeq; g.actTileRows = actTileRows; }
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3(grid_for(e->cfg.numArenas, e->arenasPerBlock)); cfg.blockDim = dim3(32 * e->groupsPerBlock * (1 + e->cfg.numCars));
@@ -1264,14 +1277,16 @@ static int step_pinned_impl(rlg_engine* e, int want_obs) {
         return RLG_OK;
     }
     CK(cudaMemsetAsync(e->resetCount, 0, 4, s));
-    int rc = do_step(e, e->actions, s, 1, nullptr, nullptr, nullptr, 0, 1);
+    static const bool chainSplit = [] { const char* ev = getenv("RLG_SPLIT_CHAIN"); return !(ev && atoi(ev) == 0); }();
+    int rc = do_step(e, e->actions, s, 1, nullptr, nullptr, nullptr, 0, 1, false, nullptr, 0, 0, chainSplit ? 1 : 0);
     if (rc != RLG_OK) return rc;
     CK(cudaEventRecord(e->evFirst, s));
     CK(cudaStreamWaitEvent(c, e->evFirst, 0));
     if (want_obs) CK(cudaMemcpyAsync(e->hObs, e->obs, (size_t)A * row * 4, cudaMemcpyDeviceToHost, c));
     CK(cudaMemcpyAsync(e->hReward, e->reward, (size_t)A * P * 4, cudaMemcpyDeviceToHost, c));
     CK(cudaMemcpyAsync(e->hDone, e->done, (size_t)A, cudaMemcpyDeviceToHost, c));
-    rc = do_step(e, e->actions, s, 1, nullptr, nullptr, nullptr, 1, e->cfg.tickSkip, want_obs != 0);
+    // the rest of the step as the programmatic dependent of the first launch: every block goes on as soon as ITS first tick is stored
+    rc = do_step(e, e->actions, s, 1, nullptr, nullptr, nullptr, 1, e->cfg.tickSkip, want_obs != 0, nullptr, 0, 0, chainSplit ? 2 : 0);
     if (rc != RLG_OK) return rc;
     CK(cudaMemcpyAsync(e->hResetCount, e->resetCount, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(c));
