@@ -1,7 +1,7 @@
 #!/bin/bash
-# r02zf: final numbers of round 2 on the final code: bench (+ cpu baseline, ppo iteration), reference arm, launch list
+# r02zm: final numbers of round 2 on the final code (after the chained split step and the small-pool block shape): bench (+ cpu baseline, ppo iteration), reference arm, launch list
 mkdir -p gpurun_out
-tag=r02zf
+tag=r02zm
 timeout 900 python bench.py --steps 100 --warmup 40 > gpurun_out/bench_$tag.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 timeout 600 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/bench_reference_$tag.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_$tag.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-ppo > gpurun_out/ncu_bench.log 2>&1
