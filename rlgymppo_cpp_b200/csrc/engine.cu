@@ -900,7 +900,15 @@ int rlg_engine_create(const rlg_engine_cfg* cfg, rlg_engine** out) {
     }
 #endif
     e->rolesSmem = ((size_t)e->arenasPerBlock * e->stride + (size_t)e->groupsPerBlock * P * kWqWords) * 4 + kEpaSmallBytes;
-    CKD(cudaFuncSetAttribute(k_roles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->rolesSmem));
+    {   // the attribute belongs to the FUNCTION (per device), not to this engine: a later, smaller engine (the SkillTracker's eval pool) must not
+        // lower it under an earlier engine's blocks — keep the high-water mark of every engine created on the device
+        static size_t s_rolesSmemMax[64] = {0};
+        const int d = e->device >= 0 && e->device < 64 ? e->device : 0;
+        if (e->rolesSmem > s_rolesSmemMax[d]) {
+            CKD(cudaFuncSetAttribute(k_roles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->rolesSmem));
+            s_rolesSmemMax[d] = e->rolesSmem;
+        }
+    }
     if (const char* cv = getenv("RLG_SMEM_CARVEOUT")) CKD(cudaFuncSetAttribute(k_roles, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
     CKD(cudaMalloc(&e->state, (size_t)e->nwords * A * 4));
     CKD(cudaMalloc(&e->scratch, (size_t)A * e->scratchSlots * sizeof(Contact)));

@@ -352,7 +352,7 @@ int refresh_transposes(rlg_ppo* p, cudaStream_t s) {
         for (int l = 1; l < p->net[n].L; l++) {
             const PpoNet& N = p->net[n];
             dim3 grid((N.inP[l] + 31) / 32, (N.outP[l] + 31) / 32);
-            launch_pdl(k_transpose, grid, dim3(32, 8), 0, s, Wp(p, p->params, n, l), N.outP[l], N.inP[l], N.Wt[l]);
+            CKP(launch_pdl(k_transpose, grid, dim3(32, 8), 0, s, Wp(p, p->params, n, l), N.outP[l], N.inP[l], N.Wt[l]));
             p->launches++;
         }
     CKP(cudaGetLastError());
@@ -389,7 +389,7 @@ int backward_net(rlg_ppo* p, int n, long rows, cudaStream_t s) {
         if (split < 1) split = 1;
         CKR(rlg_gemm_tf32_fused(N.outP[l], N.inP[l], K, dYt, K, inT, K, Wp(p, p->grads, n, l), N.inP[l], nullptr, RLG_GEMM_ATOMIC, split, nullptr, 0,
                                 nullptr, 0, s));
-        launch_pdl(k_bias_grad, dim3(N.outP[l]), dim3(256), 0, s, dYt, rows, p->ldT, Bp(p, p->grads, n, l));
+        CKP(launch_pdl(k_bias_grad, dim3(N.outP[l]), dim3(256), 0, s, dYt, rows, p->ldT, Bp(p, p->grads, n, l)));
         p->launches += 2;
         if (l > 0) {
             CKR(rlg_gemm_tf32_fused((int)rows, N.inP[l], N.outP[l], dY, N.outP[l], N.Wt[l], N.outP[l], p->dAct[cur ^ 1], N.inP[l], nullptr, 0, 1,
@@ -558,7 +558,7 @@ static int layer_io(rlg_ppo* p, int which, int net, int layer, float* W, float* 
         if (b) CKP(cudaMemcpy(dB, b, (size_t)out_dim * 4, cudaMemcpyHostToDevice));
         if (which == 0 && layer > 0 && W) {
             dim3 grid((N.inP[layer] + 31) / 32, (N.outP[layer] + 31) / 32);
-            launch_pdl(k_transpose, grid, dim3(32, 8), 0, p->own, dW, N.outP[layer], N.inP[layer], N.Wt[layer]);
+            CKP(launch_pdl(k_transpose, grid, dim3(32, 8), 0, p->own, dW, N.outP[layer], N.inP[layer], N.Wt[layer]));
             CKP(cudaStreamSynchronize(p->own));
         }
     } else {
@@ -677,7 +677,7 @@ int rlg_ppo_peek_shuffle(rlg_ppo* p, int32_t* perm_host, uint64_t counter) {
     if (p->cur < 1) return RLG_OK;
     CKP(cudaSetDevice(p->device));
     const long n = p->cur;
-    launch_pdl(k_shuffle_keys, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, p->own, p->keysIn, p->idxIn, n, p->cfg.seed, counter);
+    CKP(launch_pdl(k_shuffle_keys, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, p->own, p->keysIn, p->idxIn, n, p->cfg.seed, counter));
     CKP(cub::DeviceRadixSort::SortPairs(p->cubTemp, p->cubBytes, p->keysIn, p->keysOut, p->idxIn, p->perm, (int)n, 0, 64, p->own));
     CKP(cudaMemcpyAsync(perm_host, p->perm, (size_t)n * 4, cudaMemcpyDeviceToHost, p->own));
     CKP(cudaStreamSynchronize(p->own));
@@ -704,29 +704,29 @@ int rlg_ppo_learn(rlg_ppo* p, rlg_ppo_report* report, void* stream) {
     for (int epoch = 0; epoch < cfg.epochs; epoch++) {
         const long n = p->cur;
         if (n < batch) break;  // full batches only (ExperienceBuffer.cpp:114)
-        launch_pdl(k_shuffle_keys, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, p->keysIn, p->idxIn, n, cfg.seed, p->shuffleCounter++);
+        CKP(launch_pdl(k_shuffle_keys, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, p->keysIn, p->idxIn, n, cfg.seed, p->shuffleCounter++));
         CKP(cub::DeviceRadixSort::SortPairs(p->cubTemp, p->cubBytes, p->keysIn, p->keysOut, p->idxIn, p->perm, (int)n, 0, 64, s));
         p->launches += 2;
         for (long b0 = 0; b0 + batch <= n; b0 += batch) {
             for (long m0 = 0; m0 < batch; m0 += mbs) {
-                launch_pdl(k_gather_rows, dim3((unsigned)((mbs + 31) / 32)), dim3(256), gatherSmem, s, p->perm + b0 + m0, mbs, p->ldT, p->head, p->cap, cfg.obs_size, p->obsP,
+                CKP(launch_pdl(k_gather_rows, dim3((unsigned)((mbs + 31) / 32)), dim3(256), gatherSmem, s, p->perm + b0 + m0, mbs, p->ldT, p->head, p->cap, cfg.obs_size, p->obsP,
                                                                                  p->bStates, p->bActions, p->bLogp, p->bTarget, p->bAdv, p->X, p->Xt, p->act,
-                                                                                 p->oldLp, p->tgt, p->adv);
+                                                                                 p->oldLp, p->tgt, p->adv));
                 p->launches++;
                 if (trainCritic) {
                     CKR(forward_net(p, 1, mbs, s));
                     const PpoNet& C = p->net[1];
-                    launch_pdl(k_value_loss, dim3((unsigned)((mbs + 255) / 256)), dim3(256), 0, s, C.Y[C.L - 1], C.outP[C.L - 1], mbs, p->ldT, p->tgt, ratioB, p->dAct[0], p->dActT[0],
-                                                                              p->acc);
+                    CKP(launch_pdl(k_value_loss, dim3((unsigned)((mbs + 255) / 256)), dim3(256), 0, s, C.Y[C.L - 1], C.outP[C.L - 1], mbs, p->ldT, p->tgt, ratioB, p->dAct[0], p->dActT[0],
+                                                                              p->acc));
                     p->launches++;
                     CKR(backward_net(p, 1, mbs, s));
                 }
                 if (trainPolicy) {
                     CKR(forward_net(p, 0, mbs, s));
                     const PpoNet& P = p->net[0];
-                    launch_pdl(k_policy_loss, dim3((unsigned)((mbs + 31) / 32)), dim3(256), lossSmem, s, P.Y[P.L - 1], P.outP[P.L - 1], cfg.num_actions, p->actP, mbs, p->ldT, p->act,
+                    CKP(launch_pdl(k_policy_loss, dim3((unsigned)((mbs + 31) / 32)), dim3(256), lossSmem, s, P.Y[P.L - 1], P.outP[P.L - 1], cfg.num_actions, p->actP, mbs, p->ldT, p->act,
                                                                                    p->adv, p->oldLp, 1.f / cfg.temperature, cfg.clip_range, cfg.ent_coef, ratioB,
-                                                                                   p->dAct[0], p->dActT[0], p->acc);
+                                                                                   p->dAct[0], p->dActT[0], p->acc));
                     p->launches++;
                     CKR(backward_net(p, 0, mbs, s));
                 }
@@ -736,7 +736,7 @@ int rlg_ppo_learn(rlg_ppo* p, rlg_ppo_report* report, void* stream) {
             if (p->hook && cfg.world > 1) p->hook(p->hookUser, p->grads, (int64_t)p->total, (void*)s);
             const float gradScale = 1.f / (float)cfg.world;
             CKP(cudaMemsetAsync(p->acc + 5, 0, 16, s));
-            launch_pdl(k_sumsq2, dim3(148), dim3(256), 0, s, p->grads, nullptr, n0, n1, gradScale, p->acc + 5);
+            CKP(launch_pdl(k_sumsq2, dim3(148), dim3(256), 0, s, p->grads, nullptr, n0, n1, gradScale, p->acc + 5));
             AdamNet a[2];
             for (int net = 0; net < 2; net++) {
                 const bool train = net == 0 ? trainPolicy : trainCritic;
@@ -748,14 +748,14 @@ int rlg_ppo_learn(rlg_ppo* p, rlg_ppo_report* report, void* stream) {
                 a[net].bc2Sqrt = (float)std::sqrt(1.0 - std::pow(0.999, t));
                 a[net].train = train ? 1 : 0;
             }
-            launch_pdl(k_adam, dim3((unsigned)((p->total + 255) / 256)), dim3(256), 0, s, p->params, p->grads, p->m, p->v, n0, n1, a[0], a[1], gradScale, 0.5f, p->acc + 5);
+            CKP(launch_pdl(k_adam, dim3((unsigned)((p->total + 255) / 256)), dim3(256), 0, s, p->params, p->grads, p->m, p->v, n0, n1, a[0], a[1], gradScale, 0.5f, p->acc + 5));
             p->launches += 2;
             CKR(refresh_transposes(p, s));
             nBatches++;
         }
     }
     CKP(cudaMemsetAsync(p->acc + 7, 0, 16, s));
-    launch_pdl(k_sumsq2, dim3(148), dim3(256), 0, s, p->params, p->before, n0, n1, 1.f, p->acc + 7);
+    CKP(launch_pdl(k_sumsq2, dim3(148), dim3(256), 0, s, p->params, p->before, n0, n1, 1.f, p->acc + 7));
     p->launches++;
     CKP(cudaEventRecord(p->ev1, s));
     CKP(cudaGetLastError());

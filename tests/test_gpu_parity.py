@@ -117,6 +117,19 @@ def test_single_tick_ball_mass_radius_mutators(torch_cuda):
     _tick_file("tick_scenarios_1v1_ballmut", 1, torch_cuda, mutate=common.apply_ball_mutators)
 
 
+def test_a_second_smaller_engine_does_not_break_the_first(torch_cuda):
+    """The role kernel's dynamic shared-memory limit is an attribute of the function, not of an engine: creating a small engine (the
+    SkillTracker's eval pool next to a training pool) after a large one must not lower it under the large engine's blocks."""
+    rng = np.random.default_rng(0)
+    big = engine.Engine(abi.default_cfg(num_arenas=16384, team_size=1))
+    big.reset()
+    small = engine.Engine(abi.default_cfg(num_arenas=8, team_size=1))
+    small.reset()
+    for e in (big, small, big):
+        obs, rew, done = e.step_host(rng.integers(0, 90, size=e.A * e.P).astype(np.int32))
+        assert np.isfinite(obs).all() and np.isfinite(rew).all()
+
+
 def test_mutators_out_of_range_rejected():
     """What the reference itself refuses or cannot simulate is refused loudly: a ball wider than a broadphase cell
     (btRSBroadphase.cpp:229-230 throws), non-positive masses."""
